@@ -1,0 +1,239 @@
+/*
+ * gpba.h -- C ABI of libgpba.so, the B200-native GP-interpolated bundle-adjustment
+ * solver that replaces what runs inside g2o::SparseOptimizer::optimize for AMC-SLAM's
+ * Optimizer::LocalGPBA / Optimizer::BundleAdjustment.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * AMC-SLAM tree).  All arrays are caller-owned HOST pointers, SoA, f64 / int32 / uint8.
+ * All functions return 0 on success and a negative gpba_status on error; no exception
+ * ever crosses this boundary.  One handle is used by one host thread (same rule as one
+ * g2o::SparseOptimizer instance, Thirdparty/g2o/g2o/core/sparse_optimizer.h).
+ *
+ * Two levels share one handle:
+ *   L1  Solver-shaped   mirrors g2o::Solver / g2o::BlockSolver<Traits>
+ *                       (Thirdparty/g2o/g2o/core/solver.h:43-148, block_solver.h:96-176)
+ *   L2  whole optimize  mirrors g2o::SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve
+ *                       (sparse_optimizer.cpp:354-419, optimization_algorithm_levenberg.cpp:61-169)
+ */
+#ifndef GPBA_H
+#define GPBA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPBA_MAX_ITERS 64
+
+typedef enum gpba_status {
+  GPBA_OK = 0,
+  GPBA_ERR_INVALID = -1,   /* bad argument / inconsistent problem            */
+  GPBA_ERR_CUDA = -2,      /* CUDA runtime error (message via gpba_last_error) */
+  GPBA_ERR_NO_DEVICE = -3, /* no CUDA device: there is NO CPU fallback        */
+  GPBA_ERR_STATE = -4,     /* call order violated (e.g. solve before build)   */
+  GPBA_ERR_NCCL = -5
+} gpba_status;
+
+/* g2o::OptimizationAlgorithm::SolverResult (optimization_algorithm.h) */
+typedef enum gpba_solver_result { GPBA_TERMINATE = 2, GPBA_RESULT_OK = 1, GPBA_FAIL = -1 } gpba_solver_result;
+
+/* Reduced-camera-system solver.  DENSE_CHOL replaces LinearSolverDense (Eigen::LDLT,
+ * g2o/solvers/linear_solver_dense.h:65-113, LocalGPBA Optimizer.cc:841); PCG is the
+ * block-Jacobi preconditioned CG used for the sparse global systems (replaces
+ * LinearSolverEigen / SimplicialLDLT, linear_solver_eigen.h:94-124, Optimizer.cc:70). */
+typedef enum gpba_linear_solver { GPBA_SOLVER_DENSE_CHOL = 0, GPBA_SOLVER_PCG = 1 } gpba_linear_solver;
+
+/* obs_flags bits */
+#define GPBA_OBS_CLOSE 0x1u   /* MapPoint::mvTrackDepth[cam] < 10 m  (Optimizer.cc:1273)     */
+#define GPBA_OBS_LEVEL1 0x2u  /* edge->level()==1: inactive          (optimizable_graph.h:467) */
+#define GPBA_OBS_NO_KERNEL 0x4u /* setRobustKernel(0)                 (Optimizer.cc:611)       */
+
+/*
+ * Flattened problem = what the adapter extracts from the g2o graph that
+ * Optimizer::BundleAdjustment (src/Optimizer.cc:61-367) / Optimizer::LocalGPBA (:713-1432)
+ * build.  Keyframes are listed in ascending vertex id, so the Hessian index of a free
+ * keyframe is its rank among free keyframes (SparseOptimizer::buildIndexMapping,
+ * sparse_optimizer.cpp:166-190); points follow (marginalized).
+ *
+ * A "record" is one (KF_prev, KF_cur, camera, capture time) tuple: everything a GP edge
+ * computes that does not depend on the landmark.  rec_kf1 == -1 marks a
+ * synchronous record (EdgeMono / EdgeStereo on the reference camera, G2oTypes.h:423-468).
+ * An observation with obs_ur >= 0 is a stereo edge (EdgeStereo / EdgeStereoGP).
+ */
+typedef struct gpba_problem {
+  int32_t n_cam;                 /* async cameras + the reference camera (last)                    */
+  const double* cam_intr;        /* [n_cam][4] fx fy cx cy, float-rounded (GeometricCamera.h:101)  */
+  const double* cam_Tbc;         /* [n_cam][7] qx qy qz qw tx ty tz of MultiKeyFrame::mTbc / VertexExtrinsic */
+  double bf;                     /* PoseVelocity::bf (G2oTypes.h:78)                               */
+
+  int32_t n_kf;
+  const double* kf_pose;         /* [n_kf][7] Twb: qx qy qz qw tx ty tz   (PoseVelocity::Twb)      */
+  const double* kf_vel;          /* [n_kf][6] [lin; ang]                  (PoseVelocity::Vel)      */
+  const double* kf_time;         /* [n_kf]                                (PoseVelocity::time)     */
+  const uint8_t* kf_fixed;       /* [n_kf] vertex->fixed()                                         */
+
+  int32_t n_pt;
+  const double* pt_xyz;          /* [n_pt][3] VertexSBAPointXYZ estimate                           */
+
+  int32_t n_rec;
+  const int32_t* rec_kf1;        /* [n_rec] index into kf arrays, -1 = synchronous record          */
+  const int32_t* rec_kf2;        /* [n_rec]                                                        */
+  const int32_t* rec_cam;        /* [n_rec] cam_idx (EdgeMonoGP::cam_idx, G2oTypes.h:398)          */
+  const double* rec_t;           /* [n_rec] capture time t (EdgeMonoGP::t, G2oTypes.h:399)         */
+
+  int64_t n_obs;                 /* reprojection edges, in g2o insertion (internalId) order        */
+  const double* obs_u;           /* [n_obs] measurement()[0]                                       */
+  const double* obs_v;           /* [n_obs] measurement()[1]                                       */
+  const double* obs_ur;          /* [n_obs] measurement()[2], <0 => mono; NULL => all mono         */
+  const double* obs_inv_sigma2;  /* [n_obs] information()(0,0) (float-rounded, Optimizer.cc:182)   */
+  const int32_t* obs_rec;        /* [n_obs]                                                        */
+  const int32_t* obs_pt;         /* [n_obs]                                                        */
+  const uint8_t* obs_flags;      /* [n_obs] GPBA_OBS_* bits; NULL => 0                             */
+
+  int32_t n_prior;               /* EdgeGaussianPrior (G2oTypes.h:147-184), info = QiInv(dt)       */
+  const int32_t* prior_kf1;
+  const int32_t* prior_kf2;
+  int32_t n_velp;                /* EdgeVelocity (G2oTypes.h:496-519), info = QcInv(2,2)           */
+  const int32_t* velp_kf;
+
+  double qc[6];                  /* diagonal of GaussianProcess::mQc (GaussianProcess.h:59)        */
+  double huber_mono;             /* RobustKernelHuber delta, (float)sqrt(5.991); 0 = no kernel     */
+  double huber_stereo;           /* (float)sqrt(7.815)                                             */
+  double huber_prior;            /* 21.026 in BundleAdjustment (Optimizer.cc:128-130), 0 in LocalGPBA */
+  double lambda_init;            /* setUserLambdaInit: 1e-5 global (:75), 1.0 local (:854)         */
+  int32_t linear_solver;         /* gpba_linear_solver                                             */
+} gpba_problem;
+
+/* Per-outer-iteration record of what OptimizationAlgorithmLevenberg::solve did
+ * (optimization_algorithm_levenberg.cpp:61-169); field names follow G2OBatchStatistics
+ * (g2o/core/batch_stats.h:39-78) where one exists. */
+typedef struct gpba_lm_trace {
+  int32_t n_iters;                       /* cjIterations returned by optimize()              */
+  int32_t result;                        /* gpba_solver_result of the last solve()           */
+  int32_t levenberg_iterations[GPBA_MAX_ITERS]; /* trials (qmax) of each outer iteration     */
+  double chi2_before[GPBA_MAX_ITERS];    /* iniChi: robust chi2 at linearisation             */
+  double chi2_after[GPBA_MAX_ITERS];     /* currentChi when solve() returned                 */
+  double lambda[GPBA_MAX_ITERS];         /* _currentLambda when solve() returned             */
+  int32_t total_trials;
+  int32_t cg_iterations;                 /* PCG only: total CG iterations                    */
+  double last_trial_chi2;                /* tempChi of the last evaluated trial (stale-error quirk) */
+} gpba_lm_trace;
+
+typedef struct gpba_lm_params {
+  int32_t max_trials_after_failure;      /* 10  (optimization_algorithm_levenberg.cpp:50)    */
+  double tau;                            /* 1e-5 (:46) used when lambda_init <= 0            */
+  double good_step_lower;                /* 1/3 (:48) */
+  double good_step_upper;                /* 2/3 (:47) */
+  double pcg_tolerance;                  /* relative residual for PCG (parity mode 1e-12)    */
+  int32_t pcg_max_iterations;
+} gpba_lm_params;
+
+/* chi2 thresholds of LocalGPBA's inlier check (Optimizer.cc:975-978,1263-1348), float-rounded. */
+typedef struct gpba_thresholds {
+  double chi2_mono;        /* (float)5.991  */
+  double chi2_mono_close;  /* 1.5f*(float)5.991 */
+  double chi2_stereo;      /* (float)7.815  */
+} gpba_thresholds;
+
+/* Sizes fixed by gpba_build_structure (BlockSolver::buildStructure, block_solver.hpp:142-295). */
+typedef struct gpba_structure_info {
+  int32_t n_free_kf;       /* _numPoses                                 */
+  int32_t n_active_pt;     /* _numLandmarks                             */
+  int64_t n_active_obs;    /* active reprojection edges                 */
+  int64_t n_hpl;           /* #(pose, landmark) blocks of Hpl           */
+  int32_t n_hpp;           /* #upper blocks of Hpp (incl. diagonal)     */
+  int32_t n_hschur;        /* #upper blocks of Hschur (incl. diagonal)  */
+} gpba_structure_info;
+
+typedef struct gpba_handle gpba_handle;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+/* replaces: new g2o::BlockSolverX(linearSolver) + new OptimizationAlgorithmLevenberg
+ * (Optimizer.cc:68-76, 840-856).  device < 0 => current device.  Uploads the problem. */
+int gpba_create(const gpba_problem* prob, int device, gpba_handle** out);
+/* replaces: ~SparseOptimizer -> ~OptimizationAlgorithmWithHessian -> ~BlockSolver
+ * (sparse_optimizer.cpp:56-59, optimization_algorithm_with_hessian.cpp:45-48). */
+int gpba_destroy(gpba_handle* h);
+const char* gpba_last_error(void);
+void gpba_default_lm_params(gpba_lm_params* p);
+/* Multi-GPU (global BA): this rank owns the points with (pt % nranks == rank)-style shard
+ * given by gpba_shard_points; partial Hschur/bschur/chi2 are summed with ncclAllReduce.
+ * nccl_unique_id = 128 bytes from ncclGetUniqueId on rank 0 (gpba_nccl_unique_id). */
+int gpba_nccl_unique_id(unsigned char id_out[128]);
+int gpba_create_dist(const gpba_problem* prob, int device, int rank, int nranks,
+                     const unsigned char nccl_unique_id[128], gpba_handle** out);
+
+/* ---- L1: g2o::Solver / BlockSolver-shaped --------------------------------------- */
+/* BlockSolver::buildStructure (block_solver.hpp:142-295) + SparseOptimizer::initializeOptimization
+ * (sparse_optimizer.cpp:199-267): active set, index mapping, Hpp/Hpl/Hschur block pattern. */
+int gpba_build_structure(gpba_handle* h, gpba_structure_info* info);
+/* Upper-triangular block (row, col) lists, sorted by (col, row) like SparseBlockMatrix columns
+ * (sparse_block_matrix.h); used for the bit-exact pattern comparison. */
+int gpba_get_hpp_pattern(gpba_handle* h, int32_t* rows, int32_t* cols);
+int gpba_get_hschur_pattern(gpba_handle* h, int32_t* rows, int32_t* cols);
+/* SparseOptimizer::computeActiveErrors + activeRobustChi2 (sparse_optimizer.cpp:61-114). */
+int gpba_compute_errors(gpba_handle* h, double* robust_chi2);
+/* BlockSolver::buildSystem (block_solver.hpp:502-560). */
+int gpba_build_system(gpba_handle* h);
+/* BlockSolver::setLambda / restoreDiagonal (block_solver.hpp:563-604). */
+int gpba_set_lambda(gpba_handle* h, double lambda, int backup);
+int gpba_restore_diagonal(gpba_handle* h);
+/* BlockSolver::solve (block_solver.hpp:353-486): Schur, reduced solve, back-substitution.
+ * *ok = 0 mirrors solve()==false (non-positive reduced system). */
+int gpba_solve(gpba_handle* h, int* ok);
+/* Solver::x() / Solver::b() / vectorSize() (solver.h:95-102): poses (12 each) then landmarks (3 each). */
+int gpba_vector_size(gpba_handle* h, int64_t* n);
+int gpba_get_x(gpba_handle* h, double* x);
+int gpba_get_b(gpba_handle* h, double* b);
+/* Block values for parity tests; layouts: Hpp/Hschur blocks 12x12 row-major in pattern order,
+ * Hll 3x3 row-major per active landmark, Hpl 12x3 row-major in (landmark, pose) order. */
+int gpba_get_hpp(gpba_handle* h, double* blocks);
+int gpba_get_hschur(gpba_handle* h, double* blocks, double* bschur);
+int gpba_get_hll(gpba_handle* h, double* blocks);
+/* SparseOptimizer::update (oplus on every free vertex, sparse_optimizer.cpp:422-435),
+ * push / pop / discardTop (sparse_optimizer.cpp:600-613). */
+int gpba_oplus(gpba_handle* h, const double* x /* NULL = the solver's own x */);
+int gpba_push(gpba_handle* h);
+int gpba_pop(gpba_handle* h);
+int gpba_discard_top(gpba_handle* h);
+
+/* ---- L2: whole optimize ---------------------------------------------------------- */
+/* SparseOptimizer::optimize(iters) with OptimizationAlgorithmLevenberg (one call = the whole
+ * LM loop on device).  stop_flag mirrors setForceStopFlag(bool*) (sparse_optimizer.h:188);
+ * it is polled once per LM trial and between outer iterations; may be NULL. */
+int gpba_optimize(gpba_handle* h, int iters, const volatile unsigned char* stop_flag,
+                  const gpba_lm_params* params, gpba_lm_trace* trace);
+/* vertex->estimate() read-back (Optimizer.cc:324-366, 1360-1430). Any pointer may be NULL. */
+int gpba_download_state(gpba_handle* h, double* kf_pose, double* kf_vel, double* pt_xyz);
+/* edge->chi2() of every reprojection edge from its stored _error (base_edge.h:58-61),
+ * original observation order; inactive edges keep their last computed error. */
+int gpba_edge_chi2(gpba_handle* h, double* chi2);
+/* activeRobustChi2() over the stored errors (what LocalGPBA reads as err / err_end, Optimizer.cc:1223,1254). */
+int gpba_active_robust_chi2(gpba_handle* h, double* chi2);
+/* LocalGPBA's inlier check (Optimizer.cc:1263-1348): flag = chi2 > threshold || !isDepthPositive. */
+int gpba_outlier_flags(gpba_handle* h, const gpba_thresholds* th, uint8_t* flags);
+/* e->setLevel / e->setRobustKernel(0) / e->computeError() on inactive edges, as the chi2
+ * rejection rounds do (Optimizer.cc:559-675). */
+int gpba_set_levels(gpba_handle* h, const uint8_t* level /* [n_obs] 0/1 */);
+int gpba_set_robust_kernel(gpba_handle* h, int enabled);
+int gpba_compute_errors_inactive(gpba_handle* h);
+/* 4 x (initializeOptimization(0) + optimize(iters)) with re-flagging after every round,
+ * kernel removed after round index 2 (structure of Optimizer.cc:548-675 with LocalGPBA thresholds). */
+int gpba_rejection_rounds(gpba_handle* h, int n_rounds, int iters, const gpba_thresholds* th,
+                          const gpba_lm_params* params, uint8_t* flags_out, gpba_lm_trace* traces /* [n_rounds] */);
+
+/* ---- measurement ------------------------------------------------------------------- */
+/* Mean device time (ms, CUDA events on the library stream) and launch count per stage since the
+ * last reset; stage names follow G2OBatchStatistics: 0 records, 1 residuals, 2 quadratic form,
+ * 3 schur, 4 linear solver, 5 back-substitution+update, 6 collective. */
+#define GPBA_N_STAGES 7
+int gpba_stage_stats(gpba_handle* h, double ms_total[GPBA_N_STAGES], int64_t launches[GPBA_N_STAGES], int reset);
+int gpba_set_profiling(gpba_handle* h, int enabled);
+/* Re-upload estimates only (same structure): lets a benchmark repeat optimize() from the same start. */
+int gpba_reset_state(gpba_handle* h, const double* kf_pose, const double* kf_vel, const double* pt_xyz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPBA_H */
