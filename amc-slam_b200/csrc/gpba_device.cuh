@@ -1,0 +1,65 @@
+// gpba_device.cuh -- device-side views shared by the kernels and the host driver of libgpba.
+#pragma once
+#include <stdint.h>
+#include "gpba_math.cuh"
+
+namespace gpba {
+
+// Per-camera constants derived from MultiKeyFrame::mTbc / VertexExtrinsic and the Pinhole intrinsics.
+struct CamConst {
+  double fx, fy, cx, cy;
+  double Rcb[9], tcb[3];  // Tcb = Tbc^-1
+  double Rbc[9], tbc[3];
+  double qbc[4];          // Tbc quaternion xyzw (for se3 products in K0)
+};
+
+// Record table (output of K0), one row per (KF_prev, KF_cur, cam, t) record:
+//   [0..8]  R_cw   [9..11] t_cw      so that X_c = R_cw X_w + t_cw with T_cw = (T_wb(t) T_bc)^-1
+//   [12..155] M (6 x 24, row-major): [M_T1 | M_V1 | M_T2 | M_V2]  
+#define GPBA_REC_STRIDE 156
+#define GPBA_REC_M 12
+#define GPBA_REC_LITE_STRIDE 12
+
+#define GPBA_NO_SLOT 0xFFFFu
+
+struct DevView {
+  // ---- static problem
+  int n_cam, n_kf, n_pt, n_rec, n_prior, n_velp;
+  const CamConst* cam;
+  const double* kf_time;
+  const int* kf_h;        // hessian index of each KF or -1
+  const int* rec_kf1; const int* rec_kf2; const int* rec_cam; const double* rec_t;
+  const int* prior_kf1; const int* prior_kf2; const int* velp_kf;
+  double qc_inv[6];
+  double bf;
+  double hub_mono_delta, hub_mono_dsqr;     // delta <= 0: no kernel
+  double hub_stereo_delta, hub_stereo_dsqr;
+  double hub_prior_delta, hub_prior_dsqr;
+  // ---- active observations, sorted by (landmark order, insertion order)
+  int64_t n_aobs;
+  const double* o_u; const double* o_v; const double* o_ur; const double* o_w;
+  const int* o_rec; const int* o_lm;          // o_lm: sorted landmark index
+  const uint8_t* o_flags;
+  const uint16_t* o_slot1; const uint16_t* o_slot2;  // Hpl slot (relative to the landmark) of kf1 / kf2, GPBA_NO_SLOT if fixed/absent
+  const int64_t* o_orig;                      // original observation index
+  // ---- landmarks (sorted order)
+  int n_lm;
+  const int* lm_pt;                           // sorted landmark -> point index
+  const int64_t* lm_obs_begin;                // [n_lm+1] into sorted obs
+  const int64_t* lm_hpl_begin;                // [n_lm+1] into Hpl blocks
+  const int* hpl_pose;                        // [n_hpl] hessian pose index
+  // ---- record-major permutation (K2b)
+  const int64_t* rperm;                       // [n_aobs] sorted-obs indices grouped by record
+  int n_rseg;
+  const int* rseg_rec; const int64_t* rseg_begin;  // [n_rseg], [n_rseg+1]
+  // ---- Hessian storage
+  int n_pose;                                 // free keyframes
+  int n_hpp, n_hs;
+  const int* rec_hpp11; const int* rec_hpp12; const int* rec_hpp22;  // Hpp block index per record (-1 if n/a); hpp12 < 0 => none, bit30 set => transposed
+  const int* prior_hpp11; const int* prior_hpp12; const int* prior_hpp22;
+  const int* pose_hpp_diag;                   // [n_pose]
+  const int* hs_from_hpp;                     // [n_hs] index into Hpp or -1
+  const int* hs_diag_pose;                    // [n_hs] pose index if diagonal block else -1
+};
+
+}  // namespace gpba

@@ -1,0 +1,1287 @@
+// gpba_host.cu -- host side of libgpba.so: problem upload, structure builder (P0), LM controller (K7),
+// and the C ABI of include/gpba.h.  Mirrors the reference's plugin surface:
+//   g2o::BlockSolver<Traits>          (Thirdparty/g2o/g2o/core/block_solver.h:96-176, block_solver.hpp)  -> struct Solver, L1 calls
+//   g2o::OptimizationAlgorithmLevenberg (optimization_algorithm_levenberg.cpp:61-194)                  -> Solver::lm_solve
+//   g2o::SparseOptimizer::optimize    (sparse_optimizer.cpp:354-419)                                     -> Solver::optimize
+// There is NO CPU fallback: every entry point fails with GPBA_ERR_NO_DEVICE / GPBA_ERR_CUDA if the
+// device path is unavailable.
+#include "../../include/gpba.h"
+#include "gpba_chol.cuh"
+#include "gpba_pcg.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+
+using namespace gpba;
+
+static thread_local std::string g_err;
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \
+      return GPBA_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+#define CKR(call)                   \
+  do {                              \
+    int r_ = (call);                \
+    if (r_ != GPBA_OK) return r_;   \
+  } while (0)
+
+namespace {
+
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  int alloc(size_t count) {
+    if (count <= n && p) return GPBA_OK;
+    release();
+    if (count == 0) count = 1;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+    return GPBA_OK;
+  }
+  int upload(const std::vector<T>& v, cudaStream_t s) {
+    CKR(alloc(v.size()));
+    if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return GPBA_OK;
+  }
+  int upload(const T* v, size_t count, cudaStream_t s) {
+    CKR(alloc(count));
+    if (count) CK(cudaMemcpyAsync(p, v, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return GPBA_OK;
+  }
+};
+
+// ---- NCCL through dlopen: the library stays loadable without NCCL; multi-GPU needs libnccl.so.2
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, unsigned char[128], int) = nullptr;  // ncclUniqueId passed by value (128 B)
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+    GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && AllReduce && CommDestroy && dlsym(lib, "ncclCommInitRank");
+  }
+};
+static NcclApi g_nccl;
+struct NcclId { char internal[128]; };
+typedef int (*ncclCommInitRank_t)(ncclComm_t*, int, NcclId, int);
+
+struct Solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // ------------------------------------------------------------------ host copy of the problem
+  int n_cam = 0, n_kf = 0, n_pt = 0, n_rec = 0, n_prior = 0, n_velp = 0;
+  int64_t n_obs = 0;
+  bool stereo = false;
+  std::vector<double> h_pose, h_vel, h_pt, h_time;
+  std::vector<uint8_t> kf_fixed, obs_flags;
+  std::vector<int> rec_kf1, rec_kf2, rec_cam, obs_rec, obs_pt, prior_kf1, prior_kf2, velp_kf;
+  std::vector<double> rec_t, obs_u, obs_v, obs_ur, obs_w;
+  double lambda_init = 0;
+  int linear_solver = 0;
+  // ------------------------------------------------------------------ device: static
+  DBuf<CamConst> d_cam;
+  DBuf<double> d_time, d_rec_t;
+  DBuf<int> d_rec_kf1, d_rec_kf2, d_rec_cam, d_prior_kf1, d_prior_kf2, d_velp_kf;
+  DBuf<double> d_pt_full;                       // [n_pt*3] always-current copy in original order
+  DBuf<double> d_chi2;                          // [n_obs] stored edge chi2 (original order)
+  DBuf<double> d_all_ur; DBuf<int> d_all_rec, d_all_pt; DBuf<uint8_t> d_all_flags;  // original-order obs (K8)
+  // ------------------------------------------------------------------ device: state (double buffered)
+  DBuf<double> d_pose[2], d_vel[2], d_ptS[2];   // d_ptS: landmarks in sorted order
+  int cur = 0;
+  int last_eval = 0;                            // buffer the last error evaluation ran on
+  std::vector<std::vector<double>> stack_pose, stack_vel, stack_pt;  // push/pop (L1)
+  // ------------------------------------------------------------------ structure (host)
+  bool structure_ok = false, system_ok = false;
+  gpba_structure_info info{};
+  std::vector<int> kf_h, lm_pt, pt_lm, lm_rank;  // lm_rank[sorted lm] = landmark index in g2o order (ascending point id)
+  std::vector<int64_t> lm_obs_begin, lm_hpl_begin, o_orig;
+  std::vector<int> hpl_pose, hpp_row, hpp_col, hs_row, hs_col;
+  int64_t n_aobs = 0;
+  int n_lm = 0, n_pose = 0, n_hpp = 0, n_hs = 0, n_items = 0, n_rseg = 0;
+  int64_t n_hpl = 0, n_pairs = 0;
+  // ------------------------------------------------------------------ structure (device)
+  DBuf<int> d_kf_h, d_o_rec, d_o_lm, d_lm_pt, d_hpl_pose, d_hpl_lm, d_rseg_rec;
+  DBuf<double> d_o_u, d_o_v, d_o_ur, d_o_w;
+  DBuf<uint8_t> d_o_flags;
+  DBuf<uint16_t> d_o_slot1, d_o_slot2;
+  DBuf<int64_t> d_o_orig, d_lm_obs_begin, d_lm_hpl_begin, d_rperm, d_rseg_begin, d_item_begin;
+  DBuf<int> d_rec_hpp11, d_rec_hpp12, d_rec_hpp22, d_prior_hpp11, d_prior_hpp12, d_prior_hpp22, d_pose_hpp_diag;
+  DBuf<int> d_hs_from_hpp, d_hs_diag_pose, d_hs_row, d_hs_col, d_item_blk, d_pair_i, d_pair_j;
+  // ------------------------------------------------------------------ Hessian storage (device)
+  DBuf<double> d_rec, d_rec_lite, d_recS, d_hll, d_bl, d_hpl, d_U, d_ptL, d_hpp, d_bp, d_hs, d_bs, d_x, d_xl;
+  DBuf<double> d_partial, d_prior_rho, d_pose_scale, d_scal;
+  DBuf<int> d_fail;
+  double* h_scal = nullptr;   // pinned: [0] chi2 [1] scale [2..] spare
+  int* h_fail = nullptr;      // pinned
+  int grid_obs = 0;
+  // ------------------------------------------------------------------ Cholesky
+  int NT = 0;
+  int64_t chol_doubles = 0;
+  DBuf<int64_t> d_tile_off;
+  DBuf<int> d_col_begin, d_col_rows;
+  DBuf<double> d_tiles, d_chol_work;
+  std::vector<int> chol_col_begin;
+  // ------------------------------------------------------------------ PCG
+  PcgBuffers pcg;
+  // ------------------------------------------------------------------ LM state
+  double lambda_cur = -1, ni = 2, lambda_set = 0;
+  int nBad = 0;
+  bool lambda_applied = false;
+  double huber_mono = 0, huber_stereo = 0, huber_prior = 0, qc[6], bf = 0;
+  // ------------------------------------------------------------------ distribution
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  DBuf<double> d_red;   // packed [Hschur values | bschur | chi2] for the allreduce
+  // ------------------------------------------------------------------ profiling
+  bool profiling = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double stage_ms[GPBA_N_STAGES] = {0};
+  int64_t stage_launches[GPBA_N_STAGES] = {0};
+
+  DevView V{};
+
+  ~Solver() {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    if (h_scal) cudaFreeHost(h_scal);
+    if (h_fail) cudaFreeHost(h_fail);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // stage timing helpers
+  void t0() { if (profiling) cudaEventRecord(ev0, stream); }
+  void t1(int stage, int launches) {
+    stage_launches[stage] += launches;
+    if (!profiling) return;
+    cudaEventRecord(ev1, stream);
+    cudaEventSynchronize(ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    stage_ms[stage] += ms;
+  }
+
+  int init(const gpba_problem* P, int dev);
+  int build_structure();
+  int build_cholesky_structure();
+  void fill_view();
+  int compute_records(int buf, bool full);
+  int compute_errors(int buf, bool store, double* chi2);
+  int build_system();
+  int solve(double lambda, bool* ok);
+  int apply_update(double lambda, double* scale);
+  int lm_solve(int iteration, const gpba_lm_params& P, const volatile unsigned char* stop, gpba_lm_trace* tr, int* result);
+  int optimize(int iters, const volatile unsigned char* stop, const gpba_lm_params& P, gpba_lm_trace* tr);
+  int scatter_points(int buf);
+  int download_state(double* kf_pose, double* kf_vel, double* pt_xyz);
+  int allreduce_system();
+  int allreduce_scalar(double* v);
+};
+
+static double f32sq(double d) { return (double)(float)(d * d); }  // RobustKernelHuber::setDelta: float dsqr
+
+int Solver::init(const gpba_problem* P, int dev) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device (libgpba has no CPU fallback)"; return GPBA_ERR_NO_DEVICE; }
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  device = dev;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  CK(cudaMallocHost(&h_scal, 8 * sizeof(double)));
+  CK(cudaMallocHost(&h_fail, sizeof(int)));
+  n_cam = P->n_cam; n_kf = P->n_kf; n_pt = P->n_pt; n_rec = P->n_rec; n_obs = P->n_obs;
+  n_prior = P->n_prior; n_velp = P->n_velp;
+  if (n_cam <= 0 || n_kf <= 0 || n_pt < 0 || n_obs < 0) { g_err = "empty problem"; return GPBA_ERR_INVALID; }
+  bf = P->bf;
+  h_pose.assign(P->kf_pose, P->kf_pose + 7 * (size_t)n_kf);
+  h_vel.assign(P->kf_vel, P->kf_vel + 6 * (size_t)n_kf);
+  h_time.assign(P->kf_time, P->kf_time + n_kf);
+  kf_fixed.assign(P->kf_fixed, P->kf_fixed + n_kf);
+  h_pt.assign(P->pt_xyz, P->pt_xyz + 3 * (size_t)n_pt);
+  rec_kf1.assign(P->rec_kf1, P->rec_kf1 + n_rec); rec_kf2.assign(P->rec_kf2, P->rec_kf2 + n_rec);
+  rec_cam.assign(P->rec_cam, P->rec_cam + n_rec); rec_t.assign(P->rec_t, P->rec_t + n_rec);
+  obs_u.assign(P->obs_u, P->obs_u + n_obs); obs_v.assign(P->obs_v, P->obs_v + n_obs);
+  obs_w.assign(P->obs_inv_sigma2, P->obs_inv_sigma2 + n_obs);
+  stereo = false;
+  if (P->obs_ur) {
+    obs_ur.assign(P->obs_ur, P->obs_ur + n_obs);
+    for (int64_t i = 0; i < n_obs; ++i) if (obs_ur[i] >= 0) { stereo = true; break; }
+  }
+  if (!stereo) obs_ur.clear();
+  obs_rec.assign(P->obs_rec, P->obs_rec + n_obs); obs_pt.assign(P->obs_pt, P->obs_pt + n_obs);
+  if (P->obs_flags) obs_flags.assign(P->obs_flags, P->obs_flags + n_obs); else obs_flags.assign(n_obs, 0);
+  prior_kf1.assign(P->prior_kf1, P->prior_kf1 + n_prior); prior_kf2.assign(P->prior_kf2, P->prior_kf2 + n_prior);
+  velp_kf.assign(P->velp_kf, P->velp_kf + n_velp);
+  for (int i = 0; i < 6; ++i) qc[i] = P->qc[i];
+  huber_mono = P->huber_mono; huber_stereo = P->huber_stereo; huber_prior = P->huber_prior;
+  lambda_init = P->lambda_init; linear_solver = P->linear_solver;
+  for (int64_t i = 0; i < n_obs; ++i) {
+    if (obs_rec[i] < 0 || obs_rec[i] >= n_rec || obs_pt[i] < 0 || obs_pt[i] >= n_pt) { g_err = "observation index out of range"; return GPBA_ERR_INVALID; }
+  }
+  for (int r = 0; r < n_rec; ++r)
+    if (rec_kf2[r] < 0 || rec_kf2[r] >= n_kf || rec_kf1[r] >= n_kf || rec_cam[r] < 0 || rec_cam[r] >= n_cam) { g_err = "record index out of range"; return GPBA_ERR_INVALID; }
+
+  // per-camera constants
+  std::vector<CamConst> cams(n_cam);
+  for (int c = 0; c < n_cam; ++c) {
+    CamConst& cc = cams[c];
+    cc.fx = P->cam_intr[4 * c]; cc.fy = P->cam_intr[4 * c + 1]; cc.cx = P->cam_intr[4 * c + 2]; cc.cy = P->cam_intr[4 * c + 3];
+    SE3 Tbc = load_se3(P->cam_Tbc + 7 * c);
+    SE3 Tcb = se3_inv(Tbc);
+    M3 Rcb = quat_to_R(Tcb.q), Rbc = quat_to_R(Tbc.q);
+    for (int i = 0; i < 9; ++i) { cc.Rcb[i] = Rcb.a[i]; cc.Rbc[i] = Rbc.a[i]; }
+    for (int i = 0; i < 3; ++i) { cc.tcb[i] = Tcb.t[i]; cc.tbc[i] = Tbc.t[i]; }
+    cc.qbc[0] = Tbc.q.x; cc.qbc[1] = Tbc.q.y; cc.qbc[2] = Tbc.q.z; cc.qbc[3] = Tbc.q.w;
+  }
+  CKR(d_cam.upload(cams, stream));
+  CKR(d_time.upload(h_time, stream));
+  CKR(d_rec_kf1.upload(rec_kf1, stream)); CKR(d_rec_kf2.upload(rec_kf2, stream));
+  CKR(d_rec_cam.upload(rec_cam, stream)); CKR(d_rec_t.upload(rec_t, stream));
+  CKR(d_prior_kf1.upload(prior_kf1, stream)); CKR(d_prior_kf2.upload(prior_kf2, stream));
+  CKR(d_velp_kf.upload(velp_kf, stream));
+  CKR(d_pt_full.upload(h_pt, stream));
+  for (int b = 0; b < 2; ++b) { CKR(d_pose[b].upload(h_pose, stream)); CKR(d_vel[b].upload(h_vel, stream)); }
+  CKR(d_chi2.alloc((size_t)n_obs));
+  CK(cudaMemsetAsync(d_chi2.p, 0, sizeof(double) * (size_t)std::max<int64_t>(n_obs, 1), stream));
+  CKR(d_all_rec.upload(obs_rec, stream)); CKR(d_all_pt.upload(obs_pt, stream));
+  if (stereo) CKR(d_all_ur.upload(obs_ur, stream));
+  CKR(d_scal.alloc(8)); CKR(d_fail.alloc(1));
+  CKR(d_rec.alloc((size_t)n_rec * GPBA_REC_STRIDE)); CKR(d_rec_lite.alloc((size_t)n_rec * GPBA_REC_LITE_STRIDE));
+  CKR(d_recS.alloc((size_t)n_rec * 27));
+  CKR(d_prior_rho.alloc((size_t)n_prior + n_velp));
+  CK(cudaStreamSynchronize(stream));
+  return GPBA_OK;
+}
+
+void Solver::fill_view() {
+  V.n_cam = n_cam; V.n_kf = n_kf; V.n_pt = n_pt; V.n_rec = n_rec; V.n_prior = n_prior; V.n_velp = n_velp;
+  V.cam = d_cam.p; V.kf_time = d_time.p; V.kf_h = d_kf_h.p;
+  V.rec_kf1 = d_rec_kf1.p; V.rec_kf2 = d_rec_kf2.p; V.rec_cam = d_rec_cam.p; V.rec_t = d_rec_t.p;
+  V.prior_kf1 = d_prior_kf1.p; V.prior_kf2 = d_prior_kf2.p; V.velp_kf = d_velp_kf.p;
+  for (int i = 0; i < 6; ++i) V.qc_inv[i] = 1.0 / qc[i];  // GaussianProcess::mQcInv of a diagonal Qc
+  V.bf = bf;
+  V.hub_mono_delta = huber_mono; V.hub_mono_dsqr = f32sq(huber_mono);
+  V.hub_stereo_delta = huber_stereo; V.hub_stereo_dsqr = f32sq(huber_stereo);
+  V.hub_prior_delta = huber_prior; V.hub_prior_dsqr = f32sq(huber_prior);
+  V.n_aobs = n_aobs;
+  V.o_u = d_o_u.p; V.o_v = d_o_v.p; V.o_ur = d_o_ur.p; V.o_w = d_o_w.p; V.o_rec = d_o_rec.p; V.o_lm = d_o_lm.p;
+  V.o_flags = d_o_flags.p; V.o_slot1 = d_o_slot1.p; V.o_slot2 = d_o_slot2.p; V.o_orig = d_o_orig.p;
+  V.n_lm = n_lm; V.lm_pt = d_lm_pt.p; V.lm_obs_begin = d_lm_obs_begin.p; V.lm_hpl_begin = d_lm_hpl_begin.p;
+  V.hpl_pose = d_hpl_pose.p;
+  V.rperm = d_rperm.p; V.n_rseg = n_rseg; V.rseg_rec = d_rseg_rec.p; V.rseg_begin = d_rseg_begin.p;
+  V.n_pose = n_pose; V.n_hpp = n_hpp; V.n_hs = n_hs;
+  V.rec_hpp11 = d_rec_hpp11.p; V.rec_hpp12 = d_rec_hpp12.p; V.rec_hpp22 = d_rec_hpp22.p;
+  V.prior_hpp11 = d_prior_hpp11.p; V.prior_hpp12 = d_prior_hpp12.p; V.prior_hpp22 = d_prior_hpp22.p;
+  V.pose_hpp_diag = d_pose_hpp_diag.p; V.hs_from_hpp = d_hs_from_hpp.p; V.hs_diag_pose = d_hs_diag_pose.p;
+}
+
+// device helpers for point gather / scatter between the full (original order) and sorted-landmark arrays
+__global__ void k_gather_pts(int n_lm, const int* __restrict__ lm_pt, const double* __restrict__ full, double* __restrict__ s0, double* __restrict__ s1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lm * 3) return;
+  const double v = full[3 * (size_t)lm_pt[i / 3] + i % 3];
+  s0[i] = v; s1[i] = v;
+}
+__global__ void k_scatter_pts(int n_lm, const int* __restrict__ lm_pt, const double* __restrict__ s, double* __restrict__ full) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lm * 3) return;
+  full[3 * (size_t)lm_pt[i / 3] + i % 3] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// P0: SparseOptimizer::initializeOptimization + buildIndexMapping + BlockSolver::buildStructure
+// (sparse_optimizer.cpp:199-267,166-190; block_solver.hpp:142-295), integer and bit-exact.
+int Solver::build_structure() {
+  CK(cudaSetDevice(device));
+  if (structure_ok && n_lm > 0) CKR(scatter_points(cur));  // keep d_pt_full current before re-sorting
+  // --- active set
+  std::vector<char> kf_act(n_kf, 0), pt_act(n_pt, 0);
+  std::vector<int64_t> act;
+  act.reserve(n_obs);
+  for (int64_t i = 0; i < n_obs; ++i) {
+    if (obs_flags[i] & GPBA_OBS_LEVEL1) continue;
+    act.push_back(i);
+    const int r = obs_rec[i];
+    pt_act[obs_pt[i]] = 1;
+    if (rec_kf1[r] >= 0) kf_act[rec_kf1[r]] = 1;
+    kf_act[rec_kf2[r]] = 1;
+  }
+  for (int i = 0; i < n_prior; ++i)
+    if (!(kf_fixed[prior_kf1[i]] && kf_fixed[prior_kf2[i]])) kf_act[prior_kf1[i]] = kf_act[prior_kf2[i]] = 1;
+  for (int i = 0; i < n_velp; ++i)
+    if (!kf_fixed[velp_kf[i]]) kf_act[velp_kf[i]] = 1;
+  kf_h.assign(n_kf, -1);
+  n_pose = 0;
+  for (int k = 0; k < n_kf; ++k)
+    if (kf_act[k] && !kf_fixed[k]) kf_h[k] = n_pose++;
+  n_aobs = (int64_t)act.size();
+  // --- landmark order: ascending first keyframe (locality of record / pose accesses), ties by point id
+  std::vector<int> first_kf(n_pt, std::numeric_limits<int>::max());
+  for (int64_t i : act) first_kf[obs_pt[i]] = std::min(first_kf[obs_pt[i]], rec_kf2[obs_rec[i]]);
+  lm_pt.clear();
+  for (int p = 0; p < n_pt; ++p) if (pt_act[p]) lm_pt.push_back(p);
+  n_lm = (int)lm_pt.size();
+  lm_rank.resize(n_lm);
+  {
+    std::vector<int> rank_of_pt(n_pt, -1);
+    for (int l = 0; l < n_lm; ++l) rank_of_pt[lm_pt[l]] = l;  // g2o landmark index = rank among active points
+    std::stable_sort(lm_pt.begin(), lm_pt.end(), [&](int a, int b) { return first_kf[a] < first_kf[b]; });
+    for (int l = 0; l < n_lm; ++l) lm_rank[l] = rank_of_pt[lm_pt[l]];
+  }
+  pt_lm.assign(n_pt, -1);
+  for (int l = 0; l < n_lm; ++l) pt_lm[lm_pt[l]] = l;
+  // --- observations sorted by landmark (stable: insertion order inside a landmark)
+  lm_obs_begin.assign(n_lm + 1, 0);
+  for (int64_t i : act) lm_obs_begin[pt_lm[obs_pt[i]] + 1]++;
+  for (int l = 0; l < n_lm; ++l) lm_obs_begin[l + 1] += lm_obs_begin[l];
+  o_orig.assign(n_aobs, 0);
+  {
+    std::vector<int64_t> cursor(lm_obs_begin.begin(), lm_obs_begin.end() - 1);
+    for (int64_t i : act) o_orig[cursor[pt_lm[obs_pt[i]]]++] = i;
+  }
+  std::vector<double> su(n_aobs), sv(n_aobs), sw(n_aobs), sur;
+  std::vector<int> srec(n_aobs), slm(n_aobs);
+  std::vector<uint8_t> sfl(n_aobs);
+  if (stereo) sur.resize(n_aobs);
+  for (int64_t j = 0; j < n_aobs; ++j) {
+    const int64_t i = o_orig[j];
+    su[j] = obs_u[i]; sv[j] = obs_v[i]; sw[j] = obs_w[i]; srec[j] = obs_rec[i]; slm[j] = pt_lm[obs_pt[i]]; sfl[j] = obs_flags[i];
+    if (stereo) sur[j] = obs_ur[i];
+  }
+  // --- Hpl blocks: per landmark the sorted free poses touched by ACTIVE edges (block_solver.hpp:206-254)
+  lm_hpl_begin.assign(n_lm + 1, 0);
+  hpl_pose.clear();
+  std::vector<uint16_t> slot1(n_aobs, GPBA_NO_SLOT), slot2(n_aobs, GPBA_NO_SLOT);
+  std::vector<int> hpl_lm;
+  {
+    std::vector<int> tmp;
+    for (int l = 0; l < n_lm; ++l) {
+      tmp.clear();
+      for (int64_t j = lm_obs_begin[l]; j < lm_obs_begin[l + 1]; ++j) {
+        const int r = srec[j];
+        if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0) tmp.push_back(kf_h[rec_kf1[r]]);
+        if (kf_h[rec_kf2[r]] >= 0) tmp.push_back(kf_h[rec_kf2[r]]);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      if (tmp.size() >= GPBA_NO_SLOT) { g_err = "landmark observed by too many keyframes"; return GPBA_ERR_INVALID; }
+      lm_hpl_begin[l] = (int64_t)hpl_pose.size();
+      for (int64_t j = lm_obs_begin[l]; j < lm_obs_begin[l + 1]; ++j) {
+        const int r = srec[j];
+        if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0)
+          slot1[j] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), kf_h[rec_kf1[r]]) - tmp.begin());
+        if (kf_h[rec_kf2[r]] >= 0)
+          slot2[j] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), kf_h[rec_kf2[r]]) - tmp.begin());
+      }
+      hpl_pose.insert(hpl_pose.end(), tmp.begin(), tmp.end());
+      hpl_lm.insert(hpl_lm.end(), tmp.size(), l);
+    }
+    lm_hpl_begin[n_lm] = (int64_t)hpl_pose.size();
+  }
+  n_hpl = (int64_t)hpl_pose.size();
+  // --- Hpp pattern (upper): diagonals + pose pairs of active edges
+  std::vector<std::vector<int>> pp_rows(n_pose), hs_rows(n_pose);
+  auto add_pair = [](std::vector<std::vector<int>>& rows, int a, int b) {
+    if (a < 0 || b < 0) return;
+    if (a > b) std::swap(a, b);
+    rows[a].push_back(b);
+  };
+  for (int i = 0; i < n_pose; ++i) pp_rows[i].push_back(i);
+  for (int i = 0; i < n_prior; ++i) add_pair(pp_rows, kf_h[prior_kf1[i]], kf_h[prior_kf2[i]]);
+  {
+    std::vector<char> rec_used(n_rec, 0);
+    for (int64_t j = 0; j < n_aobs; ++j) rec_used[srec[j]] = 1;
+    for (int r = 0; r < n_rec; ++r)
+      if (rec_used[r] && rec_kf1[r] >= 0) add_pair(pp_rows, kf_h[rec_kf1[r]], kf_h[rec_kf2[r]]);
+  }
+  auto uniq = [](std::vector<std::vector<int>>& rows) {
+    for (auto& v : rows) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+  };
+  uniq(pp_rows);
+  // --- Hschur pattern: Hpp pattern U pose pairs of ALL edges (any level) of active landmarks (block_solver.hpp:262-288)
+  hs_rows = pp_rows;
+  {
+    std::vector<std::vector<int>> lm_all(n_lm);
+    bool any_inactive = n_aobs != n_obs;
+    if (any_inactive) {
+      for (int64_t i = 0; i < n_obs; ++i) {
+        const int l = pt_lm[obs_pt[i]];
+        if (l < 0) continue;
+        const int r = obs_rec[i];
+        if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0) lm_all[l].push_back(kf_h[rec_kf1[r]]);
+        if (kf_h[rec_kf2[r]] >= 0) lm_all[l].push_back(kf_h[rec_kf2[r]]);
+      }
+    }
+    std::vector<int> tmp;
+    for (int l = 0; l < n_lm; ++l) {
+      const int* v; int nv;
+      if (any_inactive) {
+        tmp = lm_all[l];
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        v = tmp.data(); nv = (int)tmp.size();
+      } else {
+        v = &hpl_pose[lm_hpl_begin[l]]; nv = (int)(lm_hpl_begin[l + 1] - lm_hpl_begin[l]);
+      }
+      for (int a = 0; a < nv; ++a) {
+        std::vector<int>& row = hs_rows[v[a]];
+        for (int c = a; c < nv; ++c)
+          if (row.empty() || row.back() != v[c]) row.push_back(v[c]);  // cheap de-dup of runs; exact unique below
+      }
+      if ((l & 0xfff) == 0xfff) {  // keep the rows from growing without bound
+        for (int a = 0; a < nv; ++a) { auto& row = hs_rows[v[a]]; if (row.size() > 4096) { std::sort(row.begin(), row.end()); row.erase(std::unique(row.begin(), row.end()), row.end()); } }
+      }
+    }
+  }
+  uniq(hs_rows);
+  auto flatten = [&](const std::vector<std::vector<int>>& rows, std::vector<int>& prow, std::vector<int>& pcol,
+                     std::vector<std::vector<int>>& ids) {
+    // order by (col, row) like the columns of a SparseBlockMatrix
+    std::vector<std::pair<int, int>> cr;
+    for (int r = 0; r < (int)rows.size(); ++r) for (int c : rows[r]) cr.push_back({c, r});
+    std::sort(cr.begin(), cr.end());
+    prow.resize(cr.size()); pcol.resize(cr.size());
+    ids.assign(rows.size(), {});
+    for (int r = 0; r < (int)rows.size(); ++r) ids[r].assign(rows[r].size(), -1);
+    for (size_t k = 0; k < cr.size(); ++k) {
+      prow[k] = cr[k].second; pcol[k] = cr[k].first;
+      const std::vector<int>& row = rows[cr[k].second];
+      ids[cr[k].second][std::lower_bound(row.begin(), row.end(), cr[k].first) - row.begin()] = (int)k;
+    }
+  };
+  std::vector<std::vector<int>> pp_ids, hs_ids;
+  flatten(pp_rows, hpp_row, hpp_col, pp_ids);
+  flatten(hs_rows, hs_row, hs_col, hs_ids);
+  n_hpp = (int)hpp_row.size(); n_hs = (int)hs_row.size();
+  auto lookup = [](const std::vector<std::vector<int>>& rows, const std::vector<std::vector<int>>& ids, int r, int c) {
+    const std::vector<int>& row = rows[r];
+    return ids[r][std::lower_bound(row.begin(), row.end(), c) - row.begin()];
+  };
+  auto pp = [&](int a, int b) { return lookup(pp_rows, pp_ids, a, b); };
+  std::vector<int> rec11(n_rec, -1), rec12(n_rec, -1), rec22(n_rec, -1), pr11(n_prior, -1), pr12(n_prior, -1), pr22(n_prior, -1);
+  auto pair_blocks = [&](int h1, int h2, int& b11, int& b12, int& b22) {
+    if (h1 >= 0) b11 = pp(h1, h1);
+    if (h2 >= 0) b22 = pp(h2, h2);
+    if (h1 >= 0 && h2 >= 0) b12 = h1 <= h2 ? pp(h1, h2) : (pp(h2, h1) | 0x40000000);
+  };
+  {
+    std::vector<char> rec_used(n_rec, 0);
+    for (int64_t j = 0; j < n_aobs; ++j) rec_used[srec[j]] = 1;
+    for (int r = 0; r < n_rec; ++r)
+      if (rec_used[r]) pair_blocks(rec_kf1[r] >= 0 ? kf_h[rec_kf1[r]] : -1, kf_h[rec_kf2[r]], rec11[r], rec12[r], rec22[r]);
+  }
+  for (int i = 0; i < n_prior; ++i) pair_blocks(kf_h[prior_kf1[i]], kf_h[prior_kf2[i]], pr11[i], pr12[i], pr22[i]);
+  std::vector<int> pose_diag(n_pose), hs_from(n_hs, -1), hs_diag(n_hs, -1);
+  for (int i = 0; i < n_pose; ++i) pose_diag[i] = pp(i, i);
+  for (int k = 0; k < n_hpp; ++k) hs_from[lookup(hs_rows, hs_ids, hpp_row[k], hpp_col[k])] = k;
+  for (int k = 0; k < n_hs; ++k) if (hs_row[k] == hs_col[k]) hs_diag[k] = hs_row[k];
+  // --- Schur work lists: for every Hschur block the (U_i, U_j) block pairs of the landmarks seen by both poses
+  std::vector<int64_t> blk_count(n_hs + 1, 0);
+  for (int l = 0; l < n_lm; ++l) {
+    const int64_t hb = lm_hpl_begin[l], he = lm_hpl_begin[l + 1];
+    for (int64_t a = hb; a < he; ++a) {
+      const std::vector<int>& row = hs_rows[hpl_pose[a]];
+      const std::vector<int>& idr = hs_ids[hpl_pose[a]];
+      size_t it = 0;
+      for (int64_t c = a; c < he; ++c) {
+        while (row[it] < hpl_pose[c]) ++it;
+        blk_count[idr[it] + 1]++;
+      }
+    }
+  }
+  for (int k = 0; k < n_hs; ++k) blk_count[k + 1] += blk_count[k];
+  n_pairs = blk_count[n_hs];
+  std::vector<int> pair_i(n_pairs), pair_j(n_pairs);
+  {
+    std::vector<int64_t> cursor(blk_count.begin(), blk_count.end() - 1);
+    for (int l = 0; l < n_lm; ++l) {
+      const int64_t hb = lm_hpl_begin[l], he = lm_hpl_begin[l + 1];
+      for (int64_t a = hb; a < he; ++a) {
+        const std::vector<int>& row = hs_rows[hpl_pose[a]];
+        const std::vector<int>& idr = hs_ids[hpl_pose[a]];
+        size_t it = 0;
+        for (int64_t c = a; c < he; ++c) {
+          while (row[it] < hpl_pose[c]) ++it;
+          const int64_t pos = cursor[idr[it]]++;
+          pair_i[pos] = (int)a; pair_j[pos] = (int)c;
+        }
+      }
+    }
+  }
+  const int CH = 256;
+  std::vector<int> item_blk;
+  std::vector<int64_t> item_begin;
+  for (int k = 0; k < n_hs; ++k)
+    for (int64_t b = blk_count[k]; b < blk_count[k + 1]; b += CH) { item_blk.push_back(k); item_begin.push_back(b); }
+  // item_begin[it+1] must be the end of item it: insert explicit ends by making items contiguous per block
+  {
+    std::vector<int64_t> ends;
+    std::vector<int64_t> begins2; std::vector<int> blk2;
+    for (size_t it = 0; it < item_blk.size(); ++it) {
+      const int64_t e = std::min(item_begin[it] + CH, blk_count[item_blk[it] + 1]);
+      begins2.push_back(item_begin[it]); blk2.push_back(item_blk[it]); ends.push_back(e);
+    }
+    // pairs are laid out block after block, so consecutive items are contiguous: end(it) == begin(it+1)
+    item_begin = begins2; item_begin.push_back(n_pairs); item_blk = blk2;
+  }
+  n_items = (int)item_blk.size();
+  // --- record-major permutation (K2b): sorted-obs indices grouped by record, split into segments
+  std::vector<int64_t> rcount(n_rec + 1, 0), rperm(n_aobs);
+  for (int64_t j = 0; j < n_aobs; ++j) rcount[srec[j] + 1]++;
+  for (int r = 0; r < n_rec; ++r) rcount[r + 1] += rcount[r];
+  {
+    std::vector<int64_t> cursor(rcount.begin(), rcount.end() - 1);
+    for (int64_t j = 0; j < n_aobs; ++j) rperm[cursor[srec[j]]++] = j;
+  }
+  const int SEG = 512;
+  std::vector<int> rseg_rec; std::vector<int64_t> rseg_begin;
+  for (int r = 0; r < n_rec; ++r)
+    for (int64_t b = rcount[r]; b < rcount[r + 1]; b += SEG) { rseg_rec.push_back(r); rseg_begin.push_back(b); }
+  rseg_begin.push_back(n_aobs);
+  n_rseg = (int)rseg_rec.size();
+
+  // --- upload
+  CKR(d_kf_h.upload(kf_h, stream));
+  CKR(d_o_u.upload(su, stream)); CKR(d_o_v.upload(sv, stream)); CKR(d_o_w.upload(sw, stream));
+  if (stereo) CKR(d_o_ur.upload(sur, stream));
+  CKR(d_o_rec.upload(srec, stream)); CKR(d_o_lm.upload(slm, stream)); CKR(d_o_flags.upload(sfl, stream));
+  CKR(d_o_slot1.upload(slot1, stream)); CKR(d_o_slot2.upload(slot2, stream)); CKR(d_o_orig.upload(o_orig, stream));
+  CKR(d_lm_pt.upload(lm_pt, stream)); CKR(d_lm_obs_begin.upload(lm_obs_begin, stream));
+  CKR(d_lm_hpl_begin.upload(lm_hpl_begin, stream)); CKR(d_hpl_pose.upload(hpl_pose, stream)); CKR(d_hpl_lm.upload(hpl_lm, stream));
+  CKR(d_rperm.upload(rperm, stream)); CKR(d_rseg_rec.upload(rseg_rec, stream)); CKR(d_rseg_begin.upload(rseg_begin, stream));
+  CKR(d_rec_hpp11.upload(rec11, stream)); CKR(d_rec_hpp12.upload(rec12, stream)); CKR(d_rec_hpp22.upload(rec22, stream));
+  CKR(d_prior_hpp11.upload(pr11, stream)); CKR(d_prior_hpp12.upload(pr12, stream)); CKR(d_prior_hpp22.upload(pr22, stream));
+  CKR(d_pose_hpp_diag.upload(pose_diag, stream)); CKR(d_hs_from_hpp.upload(hs_from, stream)); CKR(d_hs_diag_pose.upload(hs_diag, stream));
+  CKR(d_hs_row.upload(hs_row, stream)); CKR(d_hs_col.upload(hs_col, stream));
+  CKR(d_item_blk.upload(item_blk, stream)); CKR(d_item_begin.upload(item_begin, stream));
+  CKR(d_pair_i.upload(pair_i, stream)); CKR(d_pair_j.upload(pair_j, stream));
+  CKR(d_all_flags.upload(obs_flags, stream));
+  // --- storage
+  CKR(d_ptS[0].alloc((size_t)n_lm * 3)); CKR(d_ptS[1].alloc((size_t)n_lm * 3));
+  CKR(d_hll.alloc((size_t)n_lm * 9)); CKR(d_bl.alloc((size_t)n_lm * 3)); CKR(d_ptL.alloc((size_t)n_lm * 9)); CKR(d_xl.alloc((size_t)n_lm * 3));
+  CKR(d_hpl.alloc((size_t)n_hpl * 36)); CKR(d_U.alloc((size_t)n_hpl * 36));
+  CKR(d_hpp.alloc((size_t)n_hpp * 144)); CKR(d_bp.alloc((size_t)n_pose * 12));
+  CKR(d_hs.alloc((size_t)n_hs * 144 + (size_t)n_pose * 12 + 8)); CKR(d_x.alloc((size_t)n_pose * 12)); CKR(d_pose_scale.alloc((size_t)n_pose));
+  d_bs.release();
+  grid_obs = (int)std::min<int64_t>((n_aobs + 255) / 256, 148 * 8);
+  if (grid_obs < 1) grid_obs = 1;
+  CKR(d_partial.alloc((size_t)std::max(grid_obs, 148 * 16) + 16));
+  fill_view();
+  if (n_lm > 0) {
+    k_gather_pts<<<(n_lm * 3 + 255) / 256, 256, 0, stream>>>(n_lm, d_lm_pt.p, d_pt_full.p, d_ptS[0].p, d_ptS[1].p);
+    CK(cudaGetLastError());
+  }
+  // both state buffers must agree on fixed / inactive vertices
+  CK(cudaMemcpyAsync(d_pose[1 - cur].p, d_pose[cur].p, sizeof(double) * 7 * (size_t)n_kf, cudaMemcpyDeviceToDevice, stream));
+  CK(cudaMemcpyAsync(d_vel[1 - cur].p, d_vel[cur].p, sizeof(double) * 6 * (size_t)n_kf, cudaMemcpyDeviceToDevice, stream));
+  if (linear_solver == GPBA_SOLVER_DENSE_CHOL) CKR(build_cholesky_structure());
+  else CKR(pcg.setup(n_pose, n_hs, hs_row, hs_col, stream));
+  CK(cudaStreamSynchronize(stream));
+  info.n_free_kf = n_pose; info.n_active_pt = n_lm; info.n_active_obs = n_aobs; info.n_hpl = n_hpl; info.n_hpp = n_hpp; info.n_hschur = n_hs;
+  structure_ok = true; system_ok = false; lambda_applied = false;
+  last_eval = cur;
+  return GPBA_OK;
+}
+
+// tile-level symbolic factorization (the analyzePattern of the sparse path)
+int Solver::build_cholesky_structure() {
+  const int n = n_pose * 12;
+  NT = (n + GPBA_NB - 1) / GPBA_NB;
+  if (NT == 0) NT = 1;
+  const int bpt = GPBA_NB / 12;  // pose blocks per tile
+  std::vector<char> nz((size_t)NT * NT, 0);
+  for (int t = 0; t < NT; ++t) nz[(size_t)t * NT + t] = 1;
+  for (int k = 0; k < n_hs; ++k) {
+    const int ti = hs_col[k] / bpt, tj = hs_row[k] / bpt;  // lower: row tile from the larger index
+    nz[(size_t)ti * NT + tj] = 1;
+  }
+  std::vector<int> col_rows;
+  chol_col_begin.assign(NT + 1, 0);
+  std::vector<int> rows;
+  for (int k = 0; k < NT; ++k) {
+    rows.clear();
+    for (int i = k + 1; i < NT; ++i) if (nz[(size_t)i * NT + k]) rows.push_back(i);
+    for (size_t a = 0; a < rows.size(); ++a)
+      for (size_t b = 0; b <= a; ++b) nz[(size_t)rows[a] * NT + rows[b]] = 1;  // fill
+    chol_col_begin[k] = (int)col_rows.size();
+    col_rows.insert(col_rows.end(), rows.begin(), rows.end());
+  }
+  chol_col_begin[NT] = (int)col_rows.size();
+  std::vector<int64_t> off((size_t)NT * NT, -1);
+  int64_t cursor = 0;
+  for (int i = 0; i < NT; ++i)
+    for (int j = 0; j <= i; ++j)
+      if (nz[(size_t)i * NT + j]) { off[(size_t)i * NT + j] = cursor; cursor += GPBA_NB * GPBA_NB; }
+  chol_doubles = cursor;
+  CKR(d_tile_off.upload(off, stream)); CKR(d_col_begin.upload(chol_col_begin, stream)); CKR(d_col_rows.upload(col_rows, stream));
+  CKR(d_tiles.alloc((size_t)chol_doubles)); CKR(d_chol_work.alloc((size_t)NT * GPBA_NB));
+  return GPBA_OK;
+}
+
+int Solver::compute_records(int buf, bool full) {
+  t0();
+  if (full) k_records<true><<<(n_rec + 63) / 64, 64, 0, stream>>>(V, d_pose[buf].p, d_vel[buf].p, d_rec.p);
+  else k_records<false><<<(n_rec + 63) / 64, 64, 0, stream>>>(V, d_pose[buf].p, d_vel[buf].p, d_rec_lite.p);
+  CK(cudaGetLastError());
+  t1(0, 1);
+  return GPBA_OK;
+}
+
+// SparseOptimizer::computeActiveErrors + activeRobustChi2 on state buffer `buf`.
+int Solver::compute_errors(int buf, bool store, double* chi2) {
+  CKR(compute_records(buf, false));
+  t0();
+  double* out = store ? d_chi2.p : nullptr;
+  if (stereo) k_residual<true><<<grid_obs, 256, 0, stream>>>(V, d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
+  else k_residual<false><<<grid_obs, 256, 0, stream>>>(V, d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
+  CK(cudaGetLastError());
+  const int np = n_prior + (n_velp + 63) / 64;
+  const bool priors_here = rank == 0;  // priors are replicated: counted once
+  if (np > 0 && priors_here) {
+    k_priors<<<np, 64, 0, stream>>>(V, d_pose[buf].p, d_vel[buf].p, 0, d_prior_rho.p, nullptr, nullptr);
+    CK(cudaGetLastError());
+  }
+  k_reduce<<<1, 256, 0, stream>>>(d_partial.p, n_aobs > 0 ? grid_obs : 0, d_prior_rho.p, priors_here ? n_prior + n_velp : 0, d_scal.p);
+  CK(cudaGetLastError());
+  t1(1, 3);
+  if (nranks > 1) CKR(allreduce_scalar(d_scal.p));
+  CK(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  *chi2 = h_scal[0];
+  last_eval = buf;
+  return GPBA_OK;
+}
+
+// BlockSolver::buildSystem at the current state.
+int Solver::build_system() {
+  CKR(compute_records(cur, true));
+  t0();
+  CK(cudaMemsetAsync(d_recS.p, 0, sizeof(double) * 27 * (size_t)n_rec, stream));
+  CK(cudaMemsetAsync(d_hpp.p, 0, sizeof(double) * 144 * (size_t)n_hpp, stream));
+  CK(cudaMemsetAsync(d_bp.p, 0, sizeof(double) * 12 * (size_t)std::max(n_pose, 1), stream));
+  int launches = 0;
+  if (n_lm > 0) {
+    const int g = std::min((n_lm + GPBA_K2_WARPS - 1) / GPBA_K2_WARPS, 148 * 16);
+    if (stereo) k_lin_points<true><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_hpl.p);
+    else k_lin_points<false><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_hpl.p);
+    CK(cudaGetLastError());
+    const int g2 = std::min((n_rseg + 3) / 4, 148 * 16);
+    if (stereo) k_lin_records<true><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p);
+    else k_lin_records<false><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p);
+    CK(cudaGetLastError());
+    k_rec_to_hpp<<<n_rec, 128, 0, stream>>>(V, d_rec.p, d_recS.p, d_hpp.p, d_bp.p);
+    CK(cudaGetLastError());
+    launches += 3;
+  }
+  const int np = n_prior + (n_velp + 63) / 64;
+  if (np > 0 && rank == 0) {
+    k_priors<<<np, 64, 0, stream>>>(V, d_pose[cur].p, d_vel[cur].p, 1, nullptr, d_hpp.p, d_bp.p);
+    CK(cudaGetLastError());
+    launches++;
+  }
+  t1(2, launches);
+  system_ok = true;
+  return GPBA_OK;
+}
+
+int Solver::allreduce_system() {
+  if (nranks <= 1) return GPBA_OK;
+  t0();
+  const size_t count = (size_t)n_hs * 144 + (size_t)n_pose * 12;
+  int rc = g_nccl.AllReduce(d_hs.p, d_hs.p, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream);
+  if (rc != 0) { g_err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return GPBA_ERR_NCCL; }
+  t1(6, 1);
+  return GPBA_OK;
+}
+int Solver::allreduce_scalar(double* v) {
+  t0();
+  int rc = g_nccl.AllReduce(v, v, 1, 8, 0, comm, stream);
+  if (rc != 0) { g_err = "ncclAllReduce(scalar) failed"; return GPBA_ERR_NCCL; }
+  t1(6, 1);
+  return GPBA_OK;
+}
+
+// BlockSolver::solve with lambda on the diagonals of Hpp and Hll (setLambda folded in: block_solver.hpp:563-589,353-486).
+int Solver::solve(double lambda, bool* ok) {
+  double* bs = d_hs.p + (size_t)n_hs * 144;  // bschur lives right behind the Hschur values (one allreduce)
+  CK(cudaMemsetAsync(d_fail.p, 0, sizeof(int), stream));
+  t0();
+  // rank 0 carries Hpp + lambda (pose priors / damping must enter the sum exactly once);
+  // the GP-edge part of Hpp is a per-rank partial, so every rank adds its own Hpp but only rank 0 adds lambda.
+  k_schur_init<<<std::min(((int64_t)n_hs * 144 + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(V, rank == 0 ? lambda : 0.0, d_hpp.p, d_bp.p, d_hs.p, bs);
+  CK(cudaGetLastError());
+  int launches = 1;
+  if (n_lm > 0) {
+    k_schur_prep<<<std::min((n_lm + 3) / 4, 148 * 16), 128, 0, stream>>>(V, lambda, d_hll.p, d_bl.p, d_hpl.p, d_U.p, d_ptL.p, d_fail.p);
+    CK(cudaGetLastError());
+    k_schur_gather<<<std::min((n_items + 3) / 4, 148 * 16), 128, 0, stream>>>(n_items, d_item_blk.p, d_item_begin.p, d_pair_i.p, d_pair_j.p,
+                                                                              d_hpl_lm.p, d_hs_diag_pose.p, d_U.p, d_ptL.p, d_hs.p, bs);
+    CK(cudaGetLastError());
+    launches += 2;
+  }
+  t1(3, launches);
+  CKR(allreduce_system());
+  t0();
+  launches = 0;
+  if (linear_solver == GPBA_SOLVER_DENSE_CHOL) {
+    CholView C{NT, n_pose * 12, d_tile_off.p, d_col_begin.p, d_col_rows.p, d_tiles.p};
+    k_chol_clear<<<std::min((chol_doubles + 255) / 256, (int64_t)148 * 16), 256, 0, stream>>>(C, chol_doubles);
+    const int npad = NT * GPBA_NB - n_pose * 12;
+    if (npad > 0) k_chol_pad<<<(npad + 63) / 64, 64, 0, stream>>>(C);
+    k_chol_scatter<<<std::min(((int64_t)n_hs * 144 + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(C, n_hs, d_hs_row.p, d_hs_col.p, d_hs.p);
+    launches += 3;
+    for (int k = 0; k < NT; ++k) {
+      k_chol_potrf<<<1, 256, 0, stream>>>(C, k, d_fail.p);
+      const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
+      if (nr > 0) {
+        k_chol_trsm<<<nr, GPBA_NB, 0, stream>>>(C, k);
+        k_chol_update<<<nr * (nr + 1) / 2, 128, 0, stream>>>(C, k);
+        launches += 2;
+      }
+      launches++;
+    }
+    CK(cudaGetLastError());
+    k_chol_solve<<<1, 256, 0, stream>>>(C, bs, d_x.p, d_chol_work.p);
+    CK(cudaGetLastError());
+    launches++;
+  } else {
+    int it = 0;
+    CKR(pcg.solve(n_pose, n_hs, d_hs.p, bs, d_x.p, stream, &it, d_fail.p));
+    launches += it * 3 + 2;
+  }
+  t1(4, launches);
+  CK(cudaMemcpyAsync(h_fail, d_fail.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  *ok = (*h_fail == 0);
+  return GPBA_OK;
+}
+
+// SparseOptimizer::update: cur (+) x -> the other buffer; also computeScale's sum x (lambda x + b).
+int Solver::apply_update(double lambda, double* scale) {
+  const int nb = 1 - cur;
+  t0();
+  int gp = 0;
+  if (n_lm > 0) {
+    gp = std::min((n_lm + 3) / 4, 148 * 16);
+    k_backsub<<<gp, 128, 0, stream>>>(V, lambda, d_U.p, d_ptL.p, d_bl.p, d_x.p, d_ptS[cur].p, d_ptS[nb].p, d_xl.p, d_partial.p);
+    CK(cudaGetLastError());
+  }
+  k_update_poses<<<(n_kf + 63) / 64, 64, 0, stream>>>(V, lambda, d_x.p, d_bp.p, d_pose[cur].p, d_vel[cur].p, d_pose[nb].p, d_vel[nb].p, d_pose_scale.p);
+  CK(cudaGetLastError());
+  // pose part of computeScale is replicated on every rank; landmark part is per-rank
+  k_reduce<<<1, 256, 0, stream>>>(d_partial.p, gp, d_pose_scale.p, rank == 0 ? n_pose : 0, d_scal.p + 1);
+  CK(cudaGetLastError());
+  t1(5, 3);
+  if (nranks > 1) CKR(allreduce_scalar(d_scal.p + 1));
+  if (scale) {
+    CK(cudaMemcpyAsync(h_scal + 1, d_scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    *scale = h_scal[1];
+  }
+  return GPBA_OK;
+}
+
+// OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-169)
+int Solver::lm_solve(int iteration, const gpba_lm_params& P, const volatile unsigned char* stop, gpba_lm_trace* tr, int* result) {
+  if (iteration == 0) CKR(build_structure());
+  double currentChi = 0;
+  CKR(compute_errors(cur, false, &currentChi));
+  double tempChi = currentChi;
+  const double iniChi = currentChi;
+  CKR(build_system());
+  if (iteration == 0) {
+    if (lambda_init > 0) lambda_cur = lambda_init;
+    else {  // computeLambdaInit: tau * max |H_jj| over poses and landmarks (:171-185)
+      std::vector<double> hp((size_t)n_hpp * 144), hl((size_t)n_lm * 9);
+      CK(cudaMemcpyAsync(hp.data(), d_hpp.p, hp.size() * 8, cudaMemcpyDeviceToHost, stream));
+      if (n_lm) CK(cudaMemcpyAsync(hl.data(), d_hll.p, hl.size() * 8, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      double mx = 0;
+      for (int k = 0; k < n_hpp; ++k) if (hpp_row[k] == hpp_col[k]) for (int j = 0; j < 12; ++j) mx = std::max(mx, std::fabs(hp[(size_t)k * 144 + j * 13]));
+      for (int l = 0; l < n_lm; ++l) for (int j = 0; j < 3; ++j) mx = std::max(mx, std::fabs(hl[(size_t)l * 9 + j * 4]));
+      lambda_cur = P.tau * mx;
+    }
+    ni = 2; nBad = 0;
+  }
+  double rho = 0;
+  int qmax = 0;
+  do {
+    bool ok2 = false;
+    CKR(solve(lambda_cur, &ok2));
+    double scale = 0;
+    CKR(apply_update(lambda_cur, &scale));
+    CKR(compute_errors(1 - cur, false, &tempChi));
+    if (!ok2) tempChi = std::numeric_limits<double>::max();
+    rho = (currentChi - tempChi);
+    scale += 1e-3;
+    rho /= scale;
+    if (rho > 0 && std::isfinite(tempChi)) {
+      double alpha = 1. - std::pow((2 * rho - 1), 3);
+      alpha = (std::min)(alpha, P.good_step_upper);
+      const double scaleFactor = (std::max)(P.good_step_lower, alpha);
+      lambda_cur *= scaleFactor;
+      ni = 2;
+      currentChi = tempChi;
+      cur = 1 - cur;  // discardTop(): the trial buffer becomes the estimate
+    } else {
+      lambda_cur *= ni;
+      ni *= 2;       // pop(): the estimate buffer is untouched
+    }
+    qmax++;
+  } while (rho < 0 && qmax < P.max_trials_after_failure && !(stop && *stop));
+  if (tr && iteration < GPBA_MAX_ITERS) {
+    tr->levenberg_iterations[iteration] = qmax;
+    tr->chi2_before[iteration] = iniChi;
+    tr->chi2_after[iteration] = currentChi;
+    tr->lambda[iteration] = lambda_cur;
+    tr->total_trials += qmax;
+    tr->last_trial_chi2 = tempChi;
+  }
+  *result = GPBA_RESULT_OK;
+  if (qmax == P.max_trials_after_failure || rho == 0) { *result = GPBA_TERMINATE; return GPBA_OK; }
+  if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+  if (nBad >= 3) *result = GPBA_TERMINATE;
+  return GPBA_OK;
+}
+
+int Solver::scatter_points(int buf) {
+  if (n_lm > 0) {
+    k_scatter_pts<<<(n_lm * 3 + 255) / 256, 256, 0, stream>>>(n_lm, d_lm_pt.p, d_ptS[buf].p, d_pt_full.p);
+    CK(cudaGetLastError());
+  }
+  return GPBA_OK;
+}
+
+int Solver::optimize(int iters, const volatile unsigned char* stop, const gpba_lm_params& P, gpba_lm_trace* tr) {
+  CK(cudaSetDevice(device));
+  if (tr) { std::memset(tr, 0, sizeof(*tr)); tr->result = GPBA_RESULT_OK; }
+  pcg.total_iterations = 0;
+  int cj = 0, result = GPBA_RESULT_OK;
+  bool ok = true;
+  for (int i = 0; i < iters && !(stop && *stop) && ok; ++i) {
+    CKR(lm_solve(i, P, stop, tr, &result));
+    ok = (result == GPBA_RESULT_OK);
+    ++cj;
+  }
+  if (tr) { tr->n_iters = cj; tr->result = result; tr->cg_iterations = pcg.total_iterations; }
+  if (structure_ok) {
+    // stale-error quirk: edge errors are those of the LAST EVALUATED trial, even if it was rejected
+    double dummy;
+    const int ev = last_eval;
+    CKR(compute_errors(ev, true, &dummy));
+    CKR(scatter_points(cur));
+    CK(cudaStreamSynchronize(stream));
+  }
+  return GPBA_OK;
+}
+
+int Solver::download_state(double* kf_pose, double* kf_vel, double* pt_xyz) {
+  CK(cudaSetDevice(device));
+  if (structure_ok) CKR(scatter_points(cur));
+  if (kf_pose) CK(cudaMemcpyAsync(kf_pose, d_pose[cur].p, sizeof(double) * 7 * (size_t)n_kf, cudaMemcpyDeviceToHost, stream));
+  if (kf_vel) CK(cudaMemcpyAsync(kf_vel, d_vel[cur].p, sizeof(double) * 6 * (size_t)n_kf, cudaMemcpyDeviceToHost, stream));
+  if (pt_xyz) CK(cudaMemcpyAsync(pt_xyz, d_pt_full.p, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  return GPBA_OK;
+}
+
+}  // namespace
+
+// ===================================================================================== C ABI
+struct gpba_handle { Solver s; };
+#define S(h) ((h)->s)
+#define NEED(h) do { if (!(h)) { g_err = "null handle"; return GPBA_ERR_INVALID; } } while (0)
+#define NEED_STRUCT(h) do { NEED(h); if (!S(h).structure_ok) { g_err = "call gpba_build_structure first"; return GPBA_ERR_STATE; } if (cudaSetDevice(S(h).device) != cudaSuccess) return GPBA_ERR_CUDA; } while (0)
+
+extern "C" {
+
+const char* gpba_last_error(void) { return g_err.c_str(); }
+
+void gpba_default_lm_params(gpba_lm_params* p) {
+  p->max_trials_after_failure = 10; p->tau = 1e-5; p->good_step_lower = 1. / 3.; p->good_step_upper = 2. / 3.;
+  p->pcg_tolerance = 1e-12; p->pcg_max_iterations = 4000;
+}
+
+int gpba_create(const gpba_problem* prob, int device, gpba_handle** out) {
+  if (!prob || !out) { g_err = "null argument"; return GPBA_ERR_INVALID; }
+  gpba_handle* h = new (std::nothrow) gpba_handle();
+  if (!h) return GPBA_ERR_INVALID;
+  int rc = h->s.init(prob, device);
+  if (rc != GPBA_OK) { delete h; return rc; }
+  *out = h;
+  return GPBA_OK;
+}
+
+int gpba_destroy(gpba_handle* h) {
+  if (h) { cudaSetDevice(h->s.device); delete h; }
+  return GPBA_OK;
+}
+
+int gpba_nccl_unique_id(unsigned char id_out[128]) {
+  if (!g_nccl.load()) { g_err = "libnccl.so.2 not found"; return GPBA_ERR_NCCL; }
+  return g_nccl.GetUniqueId(id_out) == 0 ? GPBA_OK : GPBA_ERR_NCCL;
+}
+
+int gpba_create_dist(const gpba_problem* prob, int device, int rank, int nranks, const unsigned char id[128], gpba_handle** out) {
+  int rc = gpba_create(prob, device, out);
+  if (rc != GPBA_OK) return rc;
+  Solver& s = (*out)->s;
+  s.rank = rank; s.nranks = nranks;
+  if (nranks > 1) {
+    if (!g_nccl.load()) { g_err = "libnccl.so.2 not found"; gpba_destroy(*out); return GPBA_ERR_NCCL; }
+    NcclId nid;
+    std::memcpy(nid.internal, id, 128);
+    ncclCommInitRank_t init = (ncclCommInitRank_t)dlsym(g_nccl.lib, "ncclCommInitRank");
+    int nrc = init(&s.comm, nranks, nid, rank);
+    if (nrc != 0) { g_err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"); gpba_destroy(*out); return GPBA_ERR_NCCL; }
+  }
+  return GPBA_OK;
+}
+
+int gpba_build_structure(gpba_handle* h, gpba_structure_info* info) {
+  NEED(h);
+  CKR(S(h).build_structure());
+  if (info) *info = S(h).info;
+  return GPBA_OK;
+}
+int gpba_get_hpp_pattern(gpba_handle* h, int32_t* rows, int32_t* cols) {
+  NEED_STRUCT(h);
+  std::memcpy(rows, S(h).hpp_row.data(), S(h).hpp_row.size() * 4); std::memcpy(cols, S(h).hpp_col.data(), S(h).hpp_col.size() * 4);
+  return GPBA_OK;
+}
+int gpba_get_hschur_pattern(gpba_handle* h, int32_t* rows, int32_t* cols) {
+  NEED_STRUCT(h);
+  std::memcpy(rows, S(h).hs_row.data(), S(h).hs_row.size() * 4); std::memcpy(cols, S(h).hs_col.data(), S(h).hs_col.size() * 4);
+  return GPBA_OK;
+}
+int gpba_compute_errors(gpba_handle* h, double* robust_chi2) {
+  NEED_STRUCT(h);
+  double c = 0;
+  CKR(S(h).compute_errors(S(h).cur, true, &c));
+  if (robust_chi2) *robust_chi2 = c;
+  return GPBA_OK;
+}
+int gpba_build_system(gpba_handle* h) { NEED_STRUCT(h); return S(h).build_system(); }
+int gpba_set_lambda(gpba_handle* h, double lambda, int) {
+  NEED_STRUCT(h);
+  S(h).lambda_set = lambda; S(h).lambda_applied = true;  // damping is applied inside the Schur kernels, Hpp/Hll stay undamped
+  return GPBA_OK;
+}
+int gpba_restore_diagonal(gpba_handle* h) { NEED_STRUCT(h); S(h).lambda_applied = false; return GPBA_OK; }
+int gpba_solve(gpba_handle* h, int* ok) {
+  NEED_STRUCT(h);
+  if (!S(h).system_ok) { g_err = "call gpba_build_system first"; return GPBA_ERR_STATE; }
+  bool k = false;
+  Solver& s = S(h);
+  const double lam = s.lambda_applied ? s.lambda_set : 0.0;
+  CKR(s.solve(lam, &k));
+  // landmark part of x (no state change): run the back-substitution into the scratch buffer
+  CKR(s.apply_update(lam, nullptr));
+  CK(cudaStreamSynchronize(s.stream));
+  if (ok) *ok = k ? 1 : 0;
+  return GPBA_OK;
+}
+int gpba_vector_size(gpba_handle* h, int64_t* n) { NEED_STRUCT(h); *n = (int64_t)S(h).n_pose * 12 + (int64_t)S(h).n_lm * 3; return GPBA_OK; }
+int gpba_get_x(gpba_handle* h, double* x) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  CK(cudaMemcpy(x, s.d_x.p, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost));
+  std::vector<double> xl((size_t)s.n_lm * 3);
+  if (s.n_lm) CK(cudaMemcpy(xl.data(), s.d_xl.p, xl.size() * 8, cudaMemcpyDeviceToHost));
+  for (int l = 0; l < s.n_lm; ++l) for (int c = 0; c < 3; ++c) x[(size_t)s.n_pose * 12 + (size_t)s.lm_rank[l] * 3 + c] = xl[(size_t)l * 3 + c];
+  return GPBA_OK;
+}
+int gpba_get_b(gpba_handle* h, double* b) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaMemcpy(b, s.d_bp.p, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost));
+  std::vector<double> bl((size_t)s.n_lm * 3);
+  if (s.n_lm) CK(cudaMemcpy(bl.data(), s.d_bl.p, bl.size() * 8, cudaMemcpyDeviceToHost));
+  for (int l = 0; l < s.n_lm; ++l) for (int c = 0; c < 3; ++c) b[(size_t)s.n_pose * 12 + (size_t)s.lm_rank[l] * 3 + c] = bl[(size_t)l * 3 + c];
+  return GPBA_OK;
+}
+int gpba_get_hpp(gpba_handle* h, double* blocks) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaMemcpy(blocks, s.d_hpp.p, sizeof(double) * 144 * (size_t)s.n_hpp, cudaMemcpyDeviceToHost));
+  if (s.lambda_applied)
+    for (int k = 0; k < s.n_hpp; ++k) if (s.hpp_row[k] == s.hpp_col[k]) for (int j = 0; j < 12; ++j) blocks[(size_t)k * 144 + j * 13] += s.lambda_set;
+  return GPBA_OK;
+}
+int gpba_get_hschur(gpba_handle* h, double* blocks, double* bschur) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  CK(cudaStreamSynchronize(s.stream));
+  if (blocks) CK(cudaMemcpy(blocks, s.d_hs.p, sizeof(double) * 144 * (size_t)s.n_hs, cudaMemcpyDeviceToHost));
+  if (bschur) CK(cudaMemcpy(bschur, s.d_hs.p + (size_t)s.n_hs * 144, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost));
+  return GPBA_OK;
+}
+int gpba_get_hll(gpba_handle* h, double* blocks) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  CK(cudaStreamSynchronize(s.stream));
+  std::vector<double> hl((size_t)s.n_lm * 9);
+  if (s.n_lm) CK(cudaMemcpy(hl.data(), s.d_hll.p, hl.size() * 8, cudaMemcpyDeviceToHost));
+  for (int l = 0; l < s.n_lm; ++l) {
+    for (int c = 0; c < 9; ++c) blocks[(size_t)s.lm_rank[l] * 9 + c] = hl[(size_t)l * 9 + c];
+    if (s.lambda_applied) for (int j = 0; j < 3; ++j) blocks[(size_t)s.lm_rank[l] * 9 + j * 4] += s.lambda_set;
+  }
+  return GPBA_OK;
+}
+int gpba_get_hpl(gpba_handle* h, int64_t* lm_begin, int32_t* pose, double* blocks) {  // (landmark, pose) order of the g2o landmark numbering
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  CK(cudaStreamSynchronize(s.stream));
+  std::vector<double> hp((size_t)s.n_hpl * 36);
+  if (s.n_hpl) CK(cudaMemcpy(hp.data(), s.d_hpl.p, hp.size() * 8, cudaMemcpyDeviceToHost));
+  std::vector<int> inv(s.n_lm);
+  for (int l = 0; l < s.n_lm; ++l) inv[s.lm_rank[l]] = l;
+  int64_t cursor = 0;
+  for (int g = 0; g < s.n_lm; ++g) {
+    const int l = inv[g];
+    if (lm_begin) lm_begin[g] = cursor;
+    for (int64_t a = s.lm_hpl_begin[l]; a < s.lm_hpl_begin[l + 1]; ++a, ++cursor) {
+      if (pose) pose[cursor] = s.hpl_pose[a];
+      if (blocks) std::memcpy(blocks + cursor * 36, hp.data() + a * 36, 36 * 8);
+    }
+  }
+  if (lm_begin) lm_begin[s.n_lm] = cursor;
+  return GPBA_OK;
+}
+int gpba_oplus(gpba_handle* h, const double* x) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  if (x) {  // caller-provided update in g2o order
+    CK(cudaMemcpy(s.d_x.p, x, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyHostToDevice));
+    std::vector<double> xl((size_t)s.n_lm * 3);
+    for (int l = 0; l < s.n_lm; ++l) for (int c = 0; c < 3; ++c) xl[(size_t)l * 3 + c] = x[(size_t)s.n_pose * 12 + (size_t)s.lm_rank[l] * 3 + c];
+    if (s.n_lm) CK(cudaMemcpy(s.d_xl.p, xl.data(), xl.size() * 8, cudaMemcpyHostToDevice));
+    // landmarks: plain addition of the provided update
+    std::vector<double> pt((size_t)s.n_lm * 3);
+    if (s.n_lm) {
+      CK(cudaMemcpy(pt.data(), s.d_ptS[s.cur].p, pt.size() * 8, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < pt.size(); ++i) pt[i] += xl[i];
+      CK(cudaMemcpy(s.d_ptS[1 - s.cur].p, pt.data(), pt.size() * 8, cudaMemcpyHostToDevice));
+    }
+    k_update_poses<<<(s.n_kf + 63) / 64, 64, 0, s.stream>>>(s.V, 0.0, s.d_x.p, s.d_bp.p, s.d_pose[s.cur].p, s.d_vel[s.cur].p,
+                                                           s.d_pose[1 - s.cur].p, s.d_vel[1 - s.cur].p, s.d_pose_scale.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s.stream));
+  }
+  // x == NULL: gpba_solve already wrote state (+) x into the other buffer
+  s.cur = 1 - s.cur;
+  return GPBA_OK;
+}
+int gpba_push(gpba_handle* h) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  std::vector<double> p((size_t)s.n_kf * 7), v((size_t)s.n_kf * 6), q((size_t)s.n_lm * 3);
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaMemcpy(p.data(), s.d_pose[s.cur].p, p.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(v.data(), s.d_vel[s.cur].p, v.size() * 8, cudaMemcpyDeviceToHost));
+  if (s.n_lm) CK(cudaMemcpy(q.data(), s.d_ptS[s.cur].p, q.size() * 8, cudaMemcpyDeviceToHost));
+  s.stack_pose.push_back(p); s.stack_vel.push_back(v); s.stack_pt.push_back(q);
+  return GPBA_OK;
+}
+int gpba_pop(gpba_handle* h) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  if (s.stack_pose.empty()) { g_err = "pop on empty stack"; return GPBA_ERR_STATE; }
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMemcpy(s.d_pose[b].p, s.stack_pose.back().data(), s.stack_pose.back().size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.d_vel[b].p, s.stack_vel.back().data(), s.stack_vel.back().size() * 8, cudaMemcpyHostToDevice));
+    if (s.n_lm) CK(cudaMemcpy(s.d_ptS[b].p, s.stack_pt.back().data(), s.stack_pt.back().size() * 8, cudaMemcpyHostToDevice));
+  }
+  s.stack_pose.pop_back(); s.stack_vel.pop_back(); s.stack_pt.pop_back();
+  return GPBA_OK;
+}
+int gpba_discard_top(gpba_handle* h) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  if (s.stack_pose.empty()) { g_err = "discardTop on empty stack"; return GPBA_ERR_STATE; }
+  s.stack_pose.pop_back(); s.stack_vel.pop_back(); s.stack_pt.pop_back();
+  return GPBA_OK;
+}
+
+int gpba_optimize(gpba_handle* h, int iters, const volatile unsigned char* stop_flag, const gpba_lm_params* params, gpba_lm_trace* trace) {
+  NEED(h);
+  gpba_lm_params d;
+  gpba_default_lm_params(&d);
+  if (params) d = *params;
+  S(h).pcg.tolerance = d.pcg_tolerance; S(h).pcg.max_iterations = d.pcg_max_iterations;
+  return S(h).optimize(iters, stop_flag, d, trace);
+}
+int gpba_download_state(gpba_handle* h, double* kf_pose, double* kf_vel, double* pt_xyz) { NEED(h); return S(h).download_state(kf_pose, kf_vel, pt_xyz); }
+int gpba_edge_chi2(gpba_handle* h, double* chi2) {
+  NEED(h);
+  Solver& s = S(h);
+  CK(cudaSetDevice(s.device));
+  CK(cudaStreamSynchronize(s.stream));
+  if (s.n_obs) CK(cudaMemcpy(chi2, s.d_chi2.p, sizeof(double) * (size_t)s.n_obs, cudaMemcpyDeviceToHost));
+  return GPBA_OK;
+}
+
+__global__ void k_robust_sum(DevView V, int64_t n_obs, const double* __restrict__ chi2, const uint8_t* __restrict__ flags,
+                             const double* __restrict__ ur, double* __restrict__ partial) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    if (flags[i] & 0x2u) continue;
+    const bool st = ur && ur[i] >= 0.0;
+    const double delta = st ? V.hub_stereo_delta : V.hub_mono_delta, dsqr = st ? V.hub_stereo_dsqr : V.hub_mono_dsqr;
+    double r1;
+    acc += (delta > 0.0 && !(flags[i] & 0x4u)) ? huber(chi2[i], delta, dsqr, &r1) : chi2[i];
+  }
+  const double s = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+int gpba_active_robust_chi2(gpba_handle* h, double* chi2) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  const int g = (int)std::min<int64_t>((s.n_obs + 255) / 256 + 1, 148 * 8);
+  k_robust_sum<<<g, 256, 0, s.stream>>>(s.V, s.n_obs, s.d_chi2.p, s.d_all_flags.p, s.stereo ? s.d_all_ur.p : nullptr, s.d_partial.p);
+  CK(cudaGetLastError());
+  const int np = s.n_prior + (s.n_velp + 63) / 64;
+  if (np > 0) { k_priors<<<np, 64, 0, s.stream>>>(s.V, s.d_pose[s.last_eval].p, s.d_vel[s.last_eval].p, 0, s.d_prior_rho.p, nullptr, nullptr); CK(cudaGetLastError()); }
+  k_reduce<<<1, 256, 0, s.stream>>>(s.d_partial.p, g, s.d_prior_rho.p, s.n_prior + s.n_velp, s.d_scal.p + 2);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(s.h_scal + 2, s.d_scal.p + 2, 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  *chi2 = s.h_scal[2];
+  return GPBA_OK;
+}
+
+int gpba_outlier_flags(gpba_handle* h, const gpba_thresholds* th, uint8_t* flags) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  if (!th || !flags) { g_err = "null argument"; return GPBA_ERR_INVALID; }
+  CKR(s.scatter_points(s.cur));
+  DBuf<uint8_t> d_flags;
+  CKR(d_flags.alloc((size_t)s.n_obs));
+  const int g = (int)std::min<int64_t>((s.n_obs + 255) / 256 + 1, 148 * 8);
+  k_flags<<<g, 256, 0, s.stream>>>(s.V, s.n_obs, s.d_chi2.p, s.stereo ? s.d_all_ur.p : nullptr, s.d_all_rec.p, s.d_all_flags.p, nullptr,
+                                   s.d_all_pt.p, s.d_pt_full.p, s.d_pose[s.cur].p, th->chi2_mono, th->chi2_mono_close, th->chi2_stereo, d_flags.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(flags, d_flags.p, (size_t)s.n_obs, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return GPBA_OK;
+}
+
+int gpba_set_levels(gpba_handle* h, const uint8_t* level) {
+  NEED(h);
+  Solver& s = S(h);
+  for (int64_t i = 0; i < s.n_obs; ++i) { if (level[i]) s.obs_flags[i] |= GPBA_OBS_LEVEL1; else s.obs_flags[i] &= ~GPBA_OBS_LEVEL1; }
+  return GPBA_OK;  // takes effect at the next build_structure / optimize (initializeOptimization)
+}
+int gpba_set_robust_kernel(gpba_handle* h, int enabled) {
+  NEED(h);
+  Solver& s = S(h);
+  for (int64_t i = 0; i < s.n_obs; ++i) { if (!enabled) s.obs_flags[i] |= GPBA_OBS_NO_KERNEL; else s.obs_flags[i] &= ~GPBA_OBS_NO_KERNEL; }
+  return GPBA_OK;
+}
+
+// chi2 of the currently inactive (level 1) edges at the current estimate: "if (mvbOutlier[idx]) e->computeError()" (Optimizer.cc:591-592)
+__global__ void k_chi2_inactive(DevView V, int64_t n_obs, const uint8_t* __restrict__ flags, const int* __restrict__ obs_rec,
+                                const int* __restrict__ obs_pt, const double* __restrict__ u, const double* __restrict__ v,
+                                const double* __restrict__ ur, const double* __restrict__ w, const double* __restrict__ rec_lite,
+                                const double* __restrict__ pt_full, double* __restrict__ chi2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!(flags[i] & 0x2u)) continue;
+    const int r = obs_rec[i];
+    const size_t p = (size_t)obs_pt[i];
+    ObsEval<true> E;
+    eval_obs<true, false>(V, rec_lite + (size_t)r * GPBA_REC_LITE_STRIDE, V.cam[V.rec_cam[r]], pt_full[3 * p], pt_full[3 * p + 1],
+                          pt_full[3 * p + 2], u[i], v[i], ur ? ur[i] : -1.0, w[i], flags[i], E, nullptr, nullptr);
+    chi2[i] = E.chi2;
+  }
+}
+
+int gpba_compute_errors_inactive(gpba_handle* h) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  CKR(s.scatter_points(s.cur));
+  CKR(s.compute_records(s.cur, false));
+  DBuf<double> du, dv, dw;
+  CKR(du.upload(s.obs_u, s.stream)); CKR(dv.upload(s.obs_v, s.stream)); CKR(dw.upload(s.obs_w, s.stream));
+  const int g = (int)std::min<int64_t>((s.n_obs + 255) / 256 + 1, 148 * 8);
+  k_chi2_inactive<<<g, 256, 0, s.stream>>>(s.V, s.n_obs, s.d_all_flags.p, s.d_all_rec.p, s.d_all_pt.p, du.p, dv.p,
+                                           s.stereo ? s.d_all_ur.p : nullptr, dw.p, s.d_rec_lite.p, s.d_pt_full.p, s.d_chi2.p);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s.stream));
+  return GPBA_OK;
+}
+
+int gpba_rejection_rounds(gpba_handle* h, int n_rounds, int iters, const gpba_thresholds* th, const gpba_lm_params* params,
+                          uint8_t* flags_out, gpba_lm_trace* traces) {
+  NEED(h);
+  Solver& s = S(h);
+  std::vector<uint8_t> fl((size_t)s.n_obs, 0);
+  for (int it = 0; it < n_rounds; ++it) {
+    CKR(gpba_optimize(h, iters, nullptr, params, traces ? &traces[it] : nullptr));
+    CKR(gpba_compute_errors_inactive(h));
+    CKR(gpba_outlier_flags(h, th, fl.data()));
+    CKR(gpba_set_levels(h, fl.data()));
+    if (it == 2) CKR(gpba_set_robust_kernel(h, 0));
+    CKR(s.d_all_flags.upload(s.obs_flags, s.stream));
+  }
+  if (flags_out) std::memcpy(flags_out, fl.data(), fl.size());
+  return GPBA_OK;
+}
+
+int gpba_stage_stats(gpba_handle* h, double ms_total[GPBA_N_STAGES], int64_t launches[GPBA_N_STAGES], int reset) {
+  NEED(h);
+  for (int i = 0; i < GPBA_N_STAGES; ++i) {
+    if (ms_total) ms_total[i] = S(h).stage_ms[i];
+    if (launches) launches[i] = S(h).stage_launches[i];
+    if (reset) { S(h).stage_ms[i] = 0; S(h).stage_launches[i] = 0; }
+  }
+  return GPBA_OK;
+}
+int gpba_set_profiling(gpba_handle* h, int enabled) { NEED(h); S(h).profiling = enabled != 0; return GPBA_OK; }
+
+int gpba_reset_state(gpba_handle* h, const double* kf_pose, const double* kf_vel, const double* pt_xyz) {
+  NEED(h);
+  Solver& s = S(h);
+  CK(cudaSetDevice(s.device));
+  if (kf_pose) for (int b = 0; b < 2; ++b) CK(cudaMemcpyAsync(s.d_pose[b].p, kf_pose, sizeof(double) * 7 * (size_t)s.n_kf, cudaMemcpyHostToDevice, s.stream));
+  if (kf_vel) for (int b = 0; b < 2; ++b) CK(cudaMemcpyAsync(s.d_vel[b].p, kf_vel, sizeof(double) * 6 * (size_t)s.n_kf, cudaMemcpyHostToDevice, s.stream));
+  if (pt_xyz) {
+    CK(cudaMemcpyAsync(s.d_pt_full.p, pt_xyz, sizeof(double) * 3 * (size_t)s.n_pt, cudaMemcpyHostToDevice, s.stream));
+    if (s.structure_ok && s.n_lm > 0) {
+      k_gather_pts<<<(s.n_lm * 3 + 255) / 256, 256, 0, s.stream>>>(s.n_lm, s.d_lm_pt.p, s.d_pt_full.p, s.d_ptS[0].p, s.d_ptS[1].p);
+      CK(cudaGetLastError());
+    }
+  }
+  CK(cudaStreamSynchronize(s.stream));
+  return GPBA_OK;
+}
+
+}  // extern "C"

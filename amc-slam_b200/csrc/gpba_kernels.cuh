@@ -1,0 +1,728 @@
+// gpba_kernels.cuh -- hot-path kernels of libgpba (sm_100a), K0..K8 of SURVEY.md §2.3.
+//
+//  K0  k_records          GaussianProcess::QueryPose + the pose-chain part of EdgeMonoGP::linearizeOplus
+//                         (src/GaussianProcess.cc:23-42, src/G2oTypes.cc:343-357) once per (KF,cam) record
+//  K1  k_residual         SparseOptimizer::computeActiveErrors + activeRobustChi2 (sparse_optimizer.cpp:61-114)
+//  K2  k_lin_points       BlockSolver::buildSystem, landmark side: Hll, b_l, Hpl (block_solver.hpp:502-560)
+//      k_lin_records      ... pose side in the 6-dim record tangent space: S_r = sum w J1^T J1, g_r
+//      k_rec_to_hpp       ... Hpp += M_r^T S_r M_r, b_p += M_r^T g_r
+//  K3  k_priors           EdgeGaussianPrior / EdgeVelocity (G2oTypes.cc:100-118, G2oTypes.h:155-163,496-519)
+//  K4  k_schur_prep/init/gather   BlockSolver::solve, Schur part (block_solver.hpp:367-439)
+//  K6  k_backsub / k_update_poses landmark back-substitution + oplus (block_solver.hpp:459-483,
+//                         sparse_optimizer.cpp:422-435, G2oTypes.cc:41-46)
+//  K8  k_flags            LocalGPBA inlier check (src/Optimizer.cc:1263-1348)
+#pragma once
+#include "gpba_device.cuh"
+
+namespace gpba {
+
+// ------------------------------------------------------------------------------------------------ helpers
+GPBA_D double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum to thread 0 (blockDim.x multiple of 32, <= 1024)
+GPBA_D double block_sum(double v, double* smem32) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) smem32[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < (int)((blockDim.x + 31) >> 5) ? smem32[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+// Per-observation geometry shared by K1/K2/K8: residual, chi2, robust weight, J1 (rows x 6), Jp (rows x 3).
+template <bool STEREO>
+struct ObsEval {
+  double e[STEREO ? 3 : 2];
+  double chi2, rho, rho1;
+  int rows;
+};
+
+template <bool STEREO, bool JAC>
+GPBA_D void eval_obs(const DevView& V, const double* __restrict__ R /* R_cw[9], t_cw[3] */, const CamConst& cam,
+                     double X0, double X1, double X2, double u, double v, double ur, double w, unsigned flags,
+                     ObsEval<STEREO>& E, double (*J1)[6], double (*Jp)[3]) {
+  const double xc = fma(R[0], X0, fma(R[1], X1, fma(R[2], X2, R[9])));
+  const double yc = fma(R[3], X0, fma(R[4], X1, fma(R[5], X2, R[10])));
+  const double zc = fma(R[6], X0, fma(R[7], X1, fma(R[8], X2, R[11])));
+  const double pu = cam.fx * xc / zc + cam.cx;  // Pinhole::project (src/CameraModels/Pinhole.cpp:35-41)
+  const double pv = cam.fy * yc / zc + cam.cy;
+  E.e[0] = u - pu;
+  E.e[1] = v - pv;
+  double chi2 = E.e[0] * (w * E.e[0]) + E.e[1] * (w * E.e[1]);  // BaseEdge::chi2, Omega = I * invSigma2
+  bool stereo = false;
+  if (STEREO) {
+    stereo = ur >= 0.0;
+    if (stereo) {
+      const double invz = 1 / zc;
+      E.e[2] = ur - (pu - V.bf * invz);  // EdgeStereoGP::computeError (src/G2oTypes.cc:380-385)
+      chi2 += E.e[2] * (w * E.e[2]);
+    } else {
+      E.e[2] = 0.0;
+    }
+  }
+  E.rows = stereo ? 3 : 2;
+  E.chi2 = chi2;
+  const double delta = stereo ? V.hub_stereo_delta : V.hub_mono_delta;
+  const double dsqr = stereo ? V.hub_stereo_dsqr : V.hub_mono_dsqr;
+  if (delta > 0.0 && !(flags & 0x4u)) {
+    E.rho = huber(chi2, delta, dsqr, &E.rho1);
+  } else {
+    E.rho = chi2;
+    E.rho1 = 1.0;
+  }
+  if (JAC) {
+    // proj_jac (Pinhole.cpp:71-81), stereo row (G2oTypes.cc:407-412)
+    double P[STEREO ? 3 : 2][3];
+    P[0][0] = cam.fx / zc; P[0][1] = 0.0; P[0][2] = -cam.fx * xc / (zc * zc);
+    P[1][0] = 0.0; P[1][1] = cam.fy / zc; P[1][2] = -cam.fy * yc / (zc * zc);
+    if (STEREO) {
+      P[2][0] = stereo ? P[0][0] : 0.0; P[2][1] = 0.0;
+      P[2][2] = stereo ? P[0][2] + V.bf * (1.0 / (zc * zc)) : 0.0;
+    }
+    // X_b = T_bc X_c
+    const double xb = fma(cam.Rbc[0], xc, fma(cam.Rbc[1], yc, fma(cam.Rbc[2], zc, cam.tbc[0])));
+    const double yb = fma(cam.Rbc[3], xc, fma(cam.Rbc[4], yc, fma(cam.Rbc[5], zc, cam.tbc[1])));
+    const double zb = fma(cam.Rbc[6], xc, fma(cam.Rbc[7], yc, fma(cam.Rbc[8], zc, cam.tbc[2])));
+#pragma unroll
+    for (int r = 0; r < (STEREO ? 3 : 2); ++r) {
+      // G = P * R_cb ; J1 = -P [-R_cb, R_cb X_b^] = [G, -G X_b^]   (G2oTypes.cc:337-341)
+      const double g0 = P[r][0] * cam.Rcb[0] + P[r][1] * cam.Rcb[3] + P[r][2] * cam.Rcb[6];
+      const double g1 = P[r][0] * cam.Rcb[1] + P[r][1] * cam.Rcb[4] + P[r][2] * cam.Rcb[7];
+      const double g2 = P[r][0] * cam.Rcb[2] + P[r][1] * cam.Rcb[5] + P[r][2] * cam.Rcb[8];
+      J1[r][0] = g0; J1[r][1] = g1; J1[r][2] = g2;
+      // (G X_b^)[j]: X_b^ = [[0,-zb,yb],[zb,0,-xb],[-yb,xb,0]]
+      J1[r][3] = -(g1 * zb - g2 * yb);
+      J1[r][4] = -(-g0 * zb + g2 * xb);
+      J1[r][5] = -(g0 * yb - g1 * xb);
+      // J_point = -P R_cb R_bw = -P R_cw   (G2oTypes.cc:366)
+      Jp[r][0] = -(P[r][0] * R[0] + P[r][1] * R[3] + P[r][2] * R[6]);
+      Jp[r][1] = -(P[r][0] * R[1] + P[r][1] * R[4] + P[r][2] * R[7]);
+      Jp[r][2] = -(P[r][0] * R[2] + P[r][1] * R[5] + P[r][2] * R[8]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K0
+template <bool FULL>
+__global__ void k_records(DevView V, const double* __restrict__ pose, const double* __restrict__ vel,
+                          double* __restrict__ rec_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= V.n_rec) return;
+  const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
+  const CamConst& cam = V.cam[V.rec_cam[r]];
+  double* out = rec_out + (size_t)r * (FULL ? GPBA_REC_STRIDE : GPBA_REC_LITE_STRIDE);
+  const SE3 T2 = load_se3(pose + 7 * k2);
+  SE3 Twb = T2;
+  if (k1 >= 0) {
+    const SE3 T1 = load_se3(pose + 7 * k1);
+    const V6 v1 = load_v6(vel + 6 * k1), v2 = load_v6(vel + 6 * k2);
+    const GpWeights gw = gp_weights(V.kf_time[k1], V.kf_time[k2], V.rec_t[r]);
+    const V6 xi12 = se3_log(se3_mul(se3_inv(T1), T2));
+    const M6 K = RightJacobianPose3Inv(xi12);
+    const V6 Kv2 = mul(K, v2);
+    V6 arg;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) arg[i] = gw.l12 * v1[i] + gw.p11 * xi12[i] + gw.p12 * Kv2[i];
+    const SE3 dT = se3_exp(arg);
+    Twb = se3_mul(T1, dT);
+    if (FULL) {
+      const V6 dxi = se3_log(dT);
+      const M6 Ad = se3_Adj(se3_exp(neg6(dxi)));
+      const M6 Jd = RightJacobianPose3(dxi);
+      const M6 a = se3Adj(v2);
+      const M6 A12inv = se3_Adj(se3_inv(se3_exp(xi12)));  // Adj(T)^-1 == Adj(T^-1)
+      const M6 Jt = scale(-1.0, mul(K, A12inv));          // JinT1 top   (G2oTypes.cc:352)
+      const M6 haJt = mul(scale(-0.5, a), Jt);            // JinT1 bottom (:353)
+      const M6 haK = mul(scale(-0.5, a), K);              // JinT2 bottom (:356)
+      const M6 MT1 = add(mul(Jd, add(scale(gw.p11, Jt), scale(gw.p12, haJt))), Ad);
+      const M6 MV1 = scale(gw.l12, Jd);
+      const M6 MT2 = mul(Jd, add(scale(gw.p11, K), scale(gw.p12, haK)));
+      const M6 MV2 = scale(gw.p12, mul(Jd, K));
+      double* M = out + GPBA_REC_M;
+#pragma unroll
+      for (int m = 0; m < 6; ++m)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          M[m * 24 + c] = MT1(m, c);
+          M[m * 24 + 6 + c] = MV1(m, c);
+          M[m * 24 + 12 + c] = MT2(m, c);
+          M[m * 24 + 18 + c] = MV2(m, c);
+        }
+    }
+  }
+  SE3 Tbc;
+  Tbc.q.x = cam.qbc[0]; Tbc.q.y = cam.qbc[1]; Tbc.q.z = cam.qbc[2]; Tbc.q.w = cam.qbc[3];
+  Tbc.t = v3(cam.tbc[0], cam.tbc[1], cam.tbc[2]);
+  const SE3 Tcw = se3_inv(se3_mul(Twb, Tbc));
+  const M3 R = quat_to_R(Tcw.q);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[i] = R.a[i];
+  out[9] = Tcw.t[0]; out[10] = Tcw.t[1]; out[11] = Tcw.t[2];
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+// One thread per observation (sorted by landmark: u/v/w/rec/lm loads are coalesced, the landmark
+// and record rows come from L1/L2).  Writes nothing per observation unless chi2_out != nullptr.
+template <bool STEREO>
+__global__ void __launch_bounds__(256) k_residual(DevView V, const double* __restrict__ rec, int rec_stride,
+                                                  const double* __restrict__ pt, double* __restrict__ partial,
+                                                  double* __restrict__ chi2_out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V.n_aobs; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = V.o_rec[i];
+    const int lm = V.o_lm[i];
+    const double* R = rec + (size_t)r * rec_stride;
+    ObsEval<STEREO> E;
+    eval_obs<STEREO, false>(V, R, V.cam[V.rec_cam[r]], pt[3 * (size_t)lm], pt[3 * (size_t)lm + 1], pt[3 * (size_t)lm + 2],
+                            V.o_u[i], V.o_v[i], STEREO ? V.o_ur[i] : -1.0, V.o_w[i], V.o_flags[i], E, nullptr, nullptr);
+    acc += E.rho;
+    if (chi2_out) chi2_out[V.o_orig[i]] = E.chi2;
+  }
+  const double s = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// Sum of `n` partials + `m` prior terms in a fixed order -> out[0] (deterministic, single block).
+__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ a, int n, const double* __restrict__ b, int m,
+                                                double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i];
+  for (int i = threadIdx.x; i < m; i += blockDim.x) acc += b[i];
+  const double s = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ K2a
+// One warp per landmark.  Phase A: lane = observation (residual, weight, J1, Jp; W = J1^T w Jp).
+// Phase B: lane = Hpl entry; the record's 6x24 chain matrix M_r turns W (6x3) into the two 12x3
+// pose blocks, accumulated in a per-warp shared-memory tile and written out once (no atomics).
+#define GPBA_K2_WARPS 4
+#define GPBA_K2_DMAX 24
+template <bool STEREO>
+__global__ void __launch_bounds__(GPBA_K2_WARPS * 32) k_lin_points(DevView V, const double* __restrict__ rec,
+                                                                   const double* __restrict__ pt, double* __restrict__ hll,
+                                                                   double* __restrict__ bl, double* __restrict__ hpl) {
+  __shared__ double sW[GPBA_K2_WARPS][32][18];
+  __shared__ int sRec[GPBA_K2_WARPS][32];
+  __shared__ uint16_t sS1[GPBA_K2_WARPS][32], sS2[GPBA_K2_WARPS][32];
+  __shared__ double sTile[GPBA_K2_WARPS][GPBA_K2_DMAX * 36];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ROWS = STEREO ? 3 : 2;
+  for (int lm = blockIdx.x * GPBA_K2_WARPS + warp; lm < V.n_lm; lm += gridDim.x * GPBA_K2_WARPS) {
+    const int64_t ob = V.lm_obs_begin[lm], oe = V.lm_obs_begin[lm + 1];
+    const int64_t hb = V.lm_hpl_begin[lm];
+    const int d = (int)(V.lm_hpl_begin[lm + 1] - hb);
+    const bool use_tile = d <= GPBA_K2_DMAX;
+    double* tile = use_tile ? sTile[warp] : hpl + (size_t)hb * 36;
+    for (int j = lane; j < d * 36; j += 32) tile[j] = 0.0;
+    __syncwarp();
+    const double X0 = pt[3 * (size_t)lm], X1 = pt[3 * (size_t)lm + 1], X2 = pt[3 * (size_t)lm + 2];
+    double h[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+    for (int64_t base = ob; base < oe; base += 32) {
+      const int64_t i = base + lane;
+      if (i < oe) {
+        const int r = V.o_rec[i];
+        ObsEval<STEREO> E;
+        double J1[ROWS][6], Jp[ROWS][3];
+        eval_obs<STEREO, true>(V, rec + (size_t)r * GPBA_REC_STRIDE, V.cam[V.rec_cam[r]], X0, X1, X2, V.o_u[i], V.o_v[i],
+                               STEREO ? V.o_ur[i] : -1.0, V.o_w[i], V.o_flags[i], E, J1, Jp);
+        const double wr = E.rho1 * V.o_w[i];  // robustInformation = rho' * Omega (base_edge.h:96-102)
+#pragma unroll
+        for (int m = 0; m < 6; ++m)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) s = fma(wr * J1[rr][m], Jp[rr][c], s);
+            sW[warp][lane][m * 3 + c] = s;
+          }
+        sRec[warp][lane] = r;
+        sS1[warp][lane] = V.o_slot1[i];
+        sS2[warp][lane] = V.o_slot2[i];
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) {
+          const double w0 = wr * Jp[rr][0], w1 = wr * Jp[rr][1], w2 = wr * Jp[rr][2];
+          h[0] = fma(w0, Jp[rr][0], h[0]); h[1] = fma(w0, Jp[rr][1], h[1]); h[2] = fma(w0, Jp[rr][2], h[2]);
+          h[3] = fma(w1, Jp[rr][1], h[3]); h[4] = fma(w1, Jp[rr][2], h[4]); h[5] = fma(w2, Jp[rr][2], h[5]);
+          b[0] = fma(-w0, E.e[rr], b[0]); b[1] = fma(-w1, E.e[rr], b[1]); b[2] = fma(-w2, E.e[rr], b[2]);
+        }
+      }
+      __syncwarp();
+      const int n = (int)((oe - base) < 32 ? (oe - base) : 32);
+      for (int o = 0; o < n; ++o) {
+        const int r = sRec[warp][o];
+        const unsigned s1 = sS1[warp][o], s2 = sS2[warp][o];
+        const bool is_gp = V.rec_kf1[r] >= 0;
+        const double* M = rec + (size_t)r * GPBA_REC_STRIDE + GPBA_REC_M;
+        const double* W = sW[warp][o];
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const int e = lane + 32 * pass;
+          if (e < 72) {
+            const int ap = e / 3, c = e - 3 * ap;
+            const unsigned slot = ap < 12 ? s1 : s2;
+            if (slot != GPBA_NO_SLOT) {
+              double val;
+              bool live = true;
+              if (is_gp) {
+                val = 0.0;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) val = fma(M[m * 24 + ap], W[m * 3 + c], val);
+              } else {  // EdgeMono / EdgeStereo: pose block = J1, velocity block = 0 (G2oTypes.cc:465-467)
+                live = ap >= 12 && ap < 18;
+                val = live ? W[(ap - 12) * 3 + c] : 0.0;
+              }
+              if (live) tile[slot * 36 + (ap % 12) * 3 + c] += val;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) h[k] = warp_sum(h[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) b[k] = warp_sum(b[k]);
+    if (lane == 0) {
+      double* H = hll + 9 * (size_t)lm;
+      H[0] = h[0]; H[1] = h[1]; H[2] = h[2];
+      H[3] = h[1]; H[4] = h[3]; H[5] = h[4];
+      H[6] = h[2]; H[7] = h[4]; H[8] = h[5];
+      bl[3 * (size_t)lm] = b[0]; bl[3 * (size_t)lm + 1] = b[1]; bl[3 * (size_t)lm + 2] = b[2];
+    }
+    if (use_tile) {
+      double* out = hpl + (size_t)hb * 36;
+      for (int j = lane; j < d * 36; j += 32) out[j] = tile[j];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2b
+// One warp per record segment (observations grouped by record).  Accumulates the 6x6 S_r = sum w J1^T J1
+// (upper, 21 values) and g_r = -sum w J1^T e in registers, warp-shuffle reduces, one atomicAdd per value.
+template <bool STEREO>
+__global__ void __launch_bounds__(128) k_lin_records(DevView V, const double* __restrict__ rec,
+                                                     const double* __restrict__ pt, double* __restrict__ recS) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ROWS = STEREO ? 3 : 2;
+  for (int s = blockIdx.x * 4 + warp; s < V.n_rseg; s += gridDim.x * 4) {
+    const int r = V.rseg_rec[s];
+    const double* R = rec + (size_t)r * GPBA_REC_STRIDE;
+    const CamConst& cam = V.cam[V.rec_cam[r]];
+    double acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+    for (int64_t j = V.rseg_begin[s] + lane; j < V.rseg_begin[s + 1]; j += 32) {
+      const int64_t i = V.rperm[j];
+      const int lm = V.o_lm[i];
+      ObsEval<STEREO> E;
+      double J1[ROWS][6], Jp[ROWS][3];
+      eval_obs<STEREO, true>(V, R, cam, pt[3 * (size_t)lm], pt[3 * (size_t)lm + 1], pt[3 * (size_t)lm + 2], V.o_u[i],
+                             V.o_v[i], STEREO ? V.o_ur[i] : -1.0, V.o_w[i], V.o_flags[i], E, J1, Jp);
+      const double wr = E.rho1 * V.o_w[i];
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) {
+        int k = 0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+          const double wj = wr * J1[rr][m];
+#pragma unroll
+          for (int n = m; n < 6; ++n) { acc[k] = fma(wj, J1[rr][n], acc[k]); ++k; }
+          acc[21 + m] = fma(-wj, E.e[rr], acc[21 + m]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 27; ++k) atomicAdd(&recS[(size_t)r * 27 + k], acc[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2c
+// One CTA per record: Hpp blocks += M_r^T S_r M_r, b_p += M_r^T g_r.
+__global__ void __launch_bounds__(128) k_rec_to_hpp(DevView V, const double* __restrict__ rec,
+                                                    const double* __restrict__ recS, double* __restrict__ hpp,
+                                                    double* __restrict__ bp) {
+  __shared__ double S[36], g[6], M[144], T[144];
+  const int r = blockIdx.x;
+  const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
+  const int h1 = k1 >= 0 ? V.kf_h[k1] : -1, h2 = V.kf_h[k2];
+  if (h1 < 0 && h2 < 0) return;
+  const int tid = threadIdx.x;
+  if (tid < 27) {
+    const double v = recS[(size_t)r * 27 + tid];
+    if (tid < 21) {
+      int m = 0, k = tid;
+      while (k >= 6 - m) { k -= 6 - m; ++m; }
+      const int n = m + k;
+      S[m * 6 + n] = v; S[n * 6 + m] = v;
+    } else {
+      g[tid - 21] = v;
+    }
+  }
+  const int b11 = V.rec_hpp11[r], b12 = V.rec_hpp12[r], b22 = V.rec_hpp22[r];
+  if (k1 < 0) {  // synchronous record: pose block = S, velocity rows/cols = 0
+    __syncthreads();
+    if (tid < 36) atomicAdd(&hpp[(size_t)b22 * 144 + (tid / 6) * 12 + (tid % 6)], S[tid]);
+    if (tid < 6) atomicAdd(&bp[(size_t)h2 * 12 + tid], g[tid]);
+    return;
+  }
+  for (int j = tid; j < 144; j += blockDim.x) M[j] = rec[(size_t)r * GPBA_REC_STRIDE + GPBA_REC_M + j];
+  __syncthreads();
+  for (int j = tid; j < 144; j += blockDim.x) {
+    const int m = j / 24, c = j % 24;
+    double s = 0.0;
+#pragma unroll
+    for (int n = 0; n < 6; ++n) s = fma(S[m * 6 + n], M[n * 24 + c], s);
+    T[j] = s;
+  }
+  __syncthreads();
+  for (int j = tid; j < 576; j += blockDim.x) {
+    const int ap = j / 24, bpp = j % 24;
+    const int A = ap / 12, B = bpp / 12;
+    if (A > B) continue;
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) s = fma(M[m * 24 + ap], T[m * 24 + bpp], s);
+    const int ra = ap % 12, cb = bpp % 12;
+    if (A == 0 && B == 0) { if (h1 >= 0) atomicAdd(&hpp[(size_t)b11 * 144 + ra * 12 + cb], s); }
+    else if (A == 1) { if (h2 >= 0) atomicAdd(&hpp[(size_t)b22 * 144 + ra * 12 + cb], s); }
+    else if (b12 >= 0) {
+      const int blk = b12 & 0x3fffffff;
+      if (b12 & 0x40000000) atomicAdd(&hpp[(size_t)blk * 144 + cb * 12 + ra], s);  // stored transposed
+      else atomicAdd(&hpp[(size_t)blk * 144 + ra * 12 + cb], s);
+    }
+  }
+  if (tid < 24) {
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) s = fma(M[m * 24 + tid], g[m], s);
+    const int hh = tid < 12 ? h1 : h2;
+    if (hh >= 0) atomicAdd(&bp[(size_t)hh * 12 + (tid % 12)], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// One CTA (64 threads) per EdgeGaussianPrior; EdgeVelocity handled by the tail CTAs (one thread each).
+// mode 0: robustified chi2 -> prior_rho[]; mode 1: accumulate Hpp / b_p.
+__global__ void __launch_bounds__(64) k_priors(DevView V, const double* __restrict__ pose, const double* __restrict__ vel,
+                                               int mode, double* __restrict__ prior_rho, double* __restrict__ hpp,
+                                               double* __restrict__ bp) {
+  __shared__ double Ji[144], Jj[144], OJi[144], OJj[144], e[12], Oe[12];
+  __shared__ double s_rho1;
+  const int tid = threadIdx.x;
+  const int idx = blockIdx.x;
+  if (idx >= V.n_prior) {  // EdgeVelocity: e = Vel[2], J = [0_6 | 0 0 1 0 0 0], Omega = QcInv(2,2)
+    const int j = (idx - V.n_prior) * 64 + tid;
+    if (j >= V.n_velp) return;
+    const int k = V.velp_kf[j];
+    const int h = V.kf_h[k];
+    const double ev = vel[6 * k + 2];
+    const double O = V.qc_inv[2];
+    if (mode == 0) { prior_rho[V.n_prior + j] = h >= 0 ? ev * (O * ev) : 0.0; return; }
+    if (h < 0) return;
+    atomicAdd(&hpp[(size_t)V.pose_hpp_diag[h] * 144 + 8 * 12 + 8], O);
+    atomicAdd(&bp[(size_t)h * 12 + 8], -(O * ev));
+    return;
+  }
+  const int k1 = V.prior_kf1[idx], k2 = V.prior_kf2[idx];
+  const int h1 = V.kf_h[k1], h2 = V.kf_h[k2];
+  if (h1 < 0 && h2 < 0) {  // allVerticesFixed: inactive
+    if (mode == 0 && tid == 0) prior_rho[idx] = 0.0;
+    return;
+  }
+  const double dt = V.kf_time[k2] - V.kf_time[k1];
+  if (tid == 0) {
+    const SE3 T1 = load_se3(pose + 7 * k1), T2 = load_se3(pose + 7 * k2);
+    const V6 v1 = load_v6(vel + 6 * k1), v2 = load_v6(vel + 6 * k2);
+    const SE3 T = se3_mul(se3_inv(T1), T2);
+    const V6 xi = se3_log(T);
+    const M6 K = RightJacobianPose3Inv(xi);
+    const V6 Kv2 = mul(K, v2);
+    for (int i = 0; i < 6; ++i) { e[i] = xi[i] - dt * v1[i]; e[6 + i] = Kv2[i] - v1[i]; }
+    if (mode == 1) {
+      const M6 a = se3Adj(v2);
+      const M6 A = scale(-1.0, mul(K, se3_Adj(se3_inv(T))));  // -Jr^-1 Adj(T)^-1  (G2oTypes.cc:110)
+      const M6 haA = mul(scale(-0.5, a), A);
+      const M6 haK = mul(scale(-0.5, a), K);
+      for (int j = 0; j < 144; ++j) { Ji[j] = 0.0; Jj[j] = 0.0; }
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+          Ji[r * 12 + c] = A(r, c);
+          Ji[(6 + r) * 12 + c] = haA(r, c);
+          Jj[r * 12 + c] = K(r, c);
+          Jj[(6 + r) * 12 + c] = haK(r, c);
+          Jj[(6 + r) * 12 + 6 + c] = K(r, c);
+        }
+      for (int r = 0; r < 6; ++r) { Ji[r * 12 + 6 + r] = -dt; Ji[(6 + r) * 12 + 6 + r] = -1.0; }
+    }
+  }
+  __syncthreads();
+  // Omega = QiInv(dt) = [[12/dt^3, -6/dt^2], [-6/dt^2, 4/dt]] (x) QcInv   (GaussianProcess.h:31-41)
+  const double dt2 = dt * dt, dt3 = dt2 * dt;
+  const double o11 = 12.0 / dt3, o12 = -6.0 / dt2, o22 = 4.0 / dt;
+  if (tid < 12) {
+    const int i = tid % 6;
+    Oe[tid] = tid < 6 ? V.qc_inv[i] * o11 * e[i] + V.qc_inv[i] * o12 * e[6 + i]
+                      : V.qc_inv[i] * o12 * e[i] + V.qc_inv[i] * o22 * e[6 + i];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double chi2 = 0.0;
+    for (int i = 0; i < 12; ++i) chi2 += e[i] * Oe[i];
+    double rho1 = 1.0, rho = chi2;
+    if (V.hub_prior_delta > 0.0) rho = huber(chi2, V.hub_prior_delta, V.hub_prior_dsqr, &rho1);
+    s_rho1 = rho1;
+    if (mode == 0) prior_rho[idx] = rho;
+  }
+  __syncthreads();
+  if (mode == 0) return;
+  const double rho1 = s_rho1;
+  for (int j = tid; j < 144; j += 64) {
+    const int r = j / 12, c = j % 12, i = r % 6;
+    const double q = V.qc_inv[i] * rho1;
+    if (r < 6) { OJi[j] = q * (o11 * Ji[i * 12 + c] + o12 * Ji[(6 + i) * 12 + c]); OJj[j] = q * (o11 * Jj[i * 12 + c] + o12 * Jj[(6 + i) * 12 + c]); }
+    else { OJi[j] = q * (o12 * Ji[i * 12 + c] + o22 * Ji[(6 + i) * 12 + c]); OJj[j] = q * (o12 * Jj[i * 12 + c] + o22 * Jj[(6 + i) * 12 + c]); }
+  }
+  __syncthreads();
+  const int b11 = V.prior_hpp11[idx], b12 = V.prior_hpp12[idx], b22 = V.prior_hpp22[idx];
+  for (int j = tid; j < 144; j += 64) {
+    const int r = j / 12, c = j % 12;
+    double sii = 0.0, sjj = 0.0, sij = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      sii = fma(Ji[k * 12 + r], OJi[k * 12 + c], sii);
+      sjj = fma(Jj[k * 12 + r], OJj[k * 12 + c], sjj);
+      sij = fma(Ji[k * 12 + r], OJj[k * 12 + c], sij);
+    }
+    if (h1 >= 0) atomicAdd(&hpp[(size_t)b11 * 144 + j], sii);
+    if (h2 >= 0) atomicAdd(&hpp[(size_t)b22 * 144 + j], sjj);
+    if (b12 >= 0) {
+      const int blk = b12 & 0x3fffffff;
+      if (b12 & 0x40000000) atomicAdd(&hpp[(size_t)blk * 144 + c * 12 + r], sij);
+      else atomicAdd(&hpp[(size_t)blk * 144 + j], sij);
+    }
+  }
+  if (tid < 24) {
+    const int r = tid % 12;
+    const double* J = tid < 12 ? Ji : Jj;
+    const int hh = tid < 12 ? h1 : h2;
+    double s = 0.0;
+    for (int k = 0; k < 12; ++k) s = fma(J[k * 12 + r], -rho1 * Oe[k], s);
+    if (hh >= 0) atomicAdd(&bp[(size_t)hh * 12 + r], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// K4a: one warp per landmark: D = Hll + lambda I = L L^T, U_il = Hpl_il L^-T (so that Hpl D^-1 Hpl^T = U U^T),
+// z = L^-1 b_l.  ptL[9*lm] = {l00,l10,l11,l20,l21,l22, z0,z1,z2}.  Pure streaming: reads/writes each Hpl block once.
+__global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, const double* __restrict__ hll,
+                                                    const double* __restrict__ bl, const double* __restrict__ hpl,
+                                                    double* __restrict__ U, double* __restrict__ ptL, int* __restrict__ fail) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int lm = blockIdx.x * 4 + warp; lm < V.n_lm; lm += gridDim.x * 4) {
+    const double* H = hll + 9 * (size_t)lm;
+    const double d00 = H[0] + lambda, d10 = H[3], d11 = H[4] + lambda, d20 = H[6], d21 = H[7], d22 = H[8] + lambda;
+    const double l00 = sqrt(d00);
+    const double l10 = d10 / l00, l20 = d20 / l00;
+    const double l11 = sqrt(d11 - l10 * l10);
+    const double l21 = (d21 - l20 * l10) / l11;
+    const double l22 = sqrt(d22 - l20 * l20 - l21 * l21);
+    if (lane == 0) {
+      if (!(l00 > 0.0) || !(l11 > 0.0) || !(l22 > 0.0)) atomicExch(fail, 1);
+      const double z0 = bl[3 * (size_t)lm] / l00;
+      const double z1 = (bl[3 * (size_t)lm + 1] - l10 * z0) / l11;
+      const double z2 = (bl[3 * (size_t)lm + 2] - l20 * z0 - l21 * z1) / l22;
+      double* o = ptL + 9 * (size_t)lm;
+      o[0] = l00; o[1] = l10; o[2] = l11; o[3] = l20; o[4] = l21; o[5] = l22; o[6] = z0; o[7] = z1; o[8] = z2;
+    }
+    const int64_t hb = V.lm_hpl_begin[lm];
+    const int nrow = (int)(V.lm_hpl_begin[lm + 1] - hb) * 12;
+    const double* B = hpl + (size_t)hb * 36;
+    double* Uo = U + (size_t)hb * 36;
+    for (int rr = lane; rr < nrow; rr += 32) {
+      const double b0 = B[rr * 3], b1 = B[rr * 3 + 1], b2 = B[rr * 3 + 2];
+      const double u0 = b0 / l00;
+      const double u1 = (b1 - u0 * l10) / l11;
+      const double u2 = (b2 - u0 * l20 - u1 * l21) / l22;
+      Uo[rr * 3] = u0; Uo[rr * 3 + 1] = u1; Uo[rr * 3 + 2] = u2;
+    }
+  }
+}
+
+// Hschur := Hpp (+ lambda on the diagonal), bschur := b_p.   (block_solver.hpp:373-374, 436-439, 563-589)
+__global__ void k_schur_init(DevView V, double lambda, const double* __restrict__ hpp, const double* __restrict__ bp,
+                             double* __restrict__ hs, double* __restrict__ bs) {
+  const int64_t n = (int64_t)V.n_hs * 144;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int blk = (int)(j / 144), e = (int)(j % 144);
+    const int src = V.hs_from_hpp[blk];
+    double v = src >= 0 ? hpp[(size_t)src * 144 + e] : 0.0;
+    if (V.hs_diag_pose[blk] >= 0 && (e / 12) == (e % 12)) v += lambda;
+    hs[j] = v;
+  }
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < (int64_t)V.n_pose * 12; j += (int64_t)gridDim.x * blockDim.x)
+    bs[j] = bp[j];
+}
+
+// K4b: block-sparse SYRK on the FP64 tensor pipe.  One warp per work item = (Hschur block (i,j), chunk of
+// landmarks seen by both poses).  Hs_ij -= sum_l U_il U_jl^T is a 12 x 12 x 3L GEMM evaluated as 16x16 with
+// mma.sync.m8n8k4.f64 (DMMA); the padding column 12 of diagonal blocks carries z_l, which yields
+// bschur_i -= sum_l U_il z_l for free.
+GPBA_D void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128) k_schur_gather(int n_items, const int* __restrict__ item_blk,
+                                                      const int64_t* __restrict__ item_begin,
+                                                      const int* __restrict__ pair_i, const int* __restrict__ pair_j,
+                                                      const int* __restrict__ hpl_lm, const int* __restrict__ hs_diag_pose,
+                                                      const double* __restrict__ U, const double* __restrict__ ptL,
+                                                      double* __restrict__ hs, double* __restrict__ bs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  for (int it = blockIdx.x * 4 + warp; it < n_items; it += gridDim.x * 4) {
+    const int blk = item_blk[it];
+    const int64_t pb = item_begin[it];
+    const int kmax = 3 * (int)(item_begin[it + 1] - pb);
+    const int diag = hs_diag_pose[blk];
+    double c[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+    for (int k0 = 0; k0 < kmax; k0 += 4) {
+      const int kk = k0 + tig;
+      const bool valid = kk < kmax;
+      const int p = kk / 3, cc = kk - 3 * p;
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      if (valid) {
+        const int oi = pair_i[pb + p], oj = pair_j[pb + p];
+        const double* Ui = U + (size_t)oi * 36 + cc;
+        const double* Uj = U + (size_t)oj * 36 + cc;
+        a0 = Ui[gid * 3];
+        b0 = Uj[gid * 3];
+        if (gid < 4) { a1 = Ui[(8 + gid) * 3]; b1 = Uj[(8 + gid) * 3]; }
+        else if (gid == 4 && diag >= 0) b1 = ptL[(size_t)hpl_lm[oi] * 9 + 6 + cc];
+      }
+      dmma884(c[0][0][0], c[0][0][1], a0, b0);
+      dmma884(c[0][1][0], c[0][1][1], a0, b1);
+      dmma884(c[1][0][0], c[1][0][1], a1, b0);
+      dmma884(c[1][1][0], c[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int row = mt * 8 + gid, col = nt * 8 + 2 * tig + q;
+          if (row < 12) {
+            if (col < 12) atomicAdd(&hs[(size_t)blk * 144 + row * 12 + col], -c[mt][nt][q]);
+            else if (col == 12 && diag >= 0) atomicAdd(&bs[(size_t)diag * 12 + row], -c[mt][nt][q]);
+          }
+        }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K6
+// Landmarks: x_l = D^-1 (b_l - Hpl^T x_p) = L^-T (z - sum_i U_il^T x_i); pt_new = pt + x_l.
+// partial[] receives sum x_l (lambda x_l + b_l) for computeScale (optimization_algorithm_levenberg.cpp:187-194).
+__global__ void __launch_bounds__(128) k_backsub(DevView V, double lambda, const double* __restrict__ U,
+                                                 const double* __restrict__ ptL, const double* __restrict__ bl,
+                                                 const double* __restrict__ xp, const double* __restrict__ pt_cur,
+                                                 double* __restrict__ pt_new, double* __restrict__ xl,
+                                                 double* __restrict__ partial) {
+  __shared__ double red[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double sc = 0.0;
+  for (int lm = blockIdx.x * 4 + warp; lm < V.n_lm; lm += gridDim.x * 4) {
+    const int64_t hb = V.lm_hpl_begin[lm];
+    const int d = (int)(V.lm_hpl_begin[lm + 1] - hb);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int rr = lane; rr < d * 12; rr += 32) {
+      const double x = xp[(size_t)V.hpl_pose[hb + rr / 12] * 12 + rr % 12];
+      const double* u = U + (size_t)hb * 36 + rr * 3;
+      a0 = fma(u[0], x, a0); a1 = fma(u[1], x, a1); a2 = fma(u[2], x, a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) {
+      const double* L = ptL + 9 * (size_t)lm;
+      const double y0 = L[6] - a0, y1 = L[7] - a1, y2 = L[8] - a2;
+      const double x2 = y2 / L[5];
+      const double x1 = (y1 - L[4] * x2) / L[2];
+      const double x0 = (y0 - L[1] * x1 - L[3] * x2) / L[0];
+      pt_new[3 * (size_t)lm] = pt_cur[3 * (size_t)lm] + x0;          // VertexSBAPointXYZ::oplusImpl (types_sba.h:41-57)
+      pt_new[3 * (size_t)lm + 1] = pt_cur[3 * (size_t)lm + 1] + x1;
+      pt_new[3 * (size_t)lm + 2] = pt_cur[3 * (size_t)lm + 2] + x2;
+      xl[3 * (size_t)lm] = x0; xl[3 * (size_t)lm + 1] = x1; xl[3 * (size_t)lm + 2] = x2;
+      sc += x0 * (lambda * x0 + bl[3 * (size_t)lm]) + x1 * (lambda * x1 + bl[3 * (size_t)lm + 1]) +
+            x2 * (lambda * x2 + bl[3 * (size_t)lm + 2]);
+    }
+  }
+  const double s = block_sum(sc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// Keyframes: Twb <- Twb * exp(x[0:6]), Vel += x[6:12]   (PoseVelocity::Update, src/G2oTypes.cc:41-46).
+// pose_scale[h] = sum over the 12 dims of x (lambda x + b).
+__global__ void k_update_poses(DevView V, double lambda, const double* __restrict__ xp, const double* __restrict__ bp,
+                               const double* __restrict__ pose_cur, const double* __restrict__ vel_cur,
+                               double* __restrict__ pose_new, double* __restrict__ vel_new, double* __restrict__ pose_scale) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= V.n_kf) return;
+  const int h = V.kf_h[k];
+  if (h < 0) return;  // fixed / inactive: both buffers already hold the same value
+  const double* x = xp + (size_t)h * 12;
+  const SE3 T = se3_mul(load_se3(pose_cur + 7 * k), se3_exp(load_v6(x)));
+  store_se3(T, pose_new + 7 * k);
+  double sc = 0.0;
+  for (int i = 0; i < 6; ++i) vel_new[6 * k + i] = vel_cur[6 * k + i] + x[6 + i];
+  for (int i = 0; i < 12; ++i) sc += x[i] * (lambda * x[i] + bp[(size_t)h * 12 + i]);
+  pose_scale[h] = sc;
+}
+
+// ------------------------------------------------------------------------------------------------ K8
+// flag = chi2 > threshold (close / far) || !isDepthPositive at BOTH keyframe poses (G2oTypes.h:362-370);
+// stereo edges: chi2 only (Optimizer.cc:1283-1296).  Runs over ALL observations in original order.
+__global__ void k_flags(DevView V, int64_t n_obs, const double* __restrict__ chi2, const double* __restrict__ ur,
+                        const int* __restrict__ obs_rec, const uint8_t* __restrict__ obs_flags,
+                        const double* __restrict__ obs_X /* current landmark xyz per observation's point, gathered by host index */,
+                        const int* __restrict__ obs_pt, const double* __restrict__ pt_all, const double* __restrict__ pose,
+                        double th_mono, double th_close, double th_stereo, uint8_t* __restrict__ flags) {
+  (void)obs_X;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    const double c2 = chi2[i];
+    bool out;
+    if (ur && ur[i] >= 0.0) {
+      out = c2 > th_stereo;
+    } else {
+      const int r = obs_rec[i];
+      const CamConst& cam = V.cam[V.rec_cam[r]];
+      SE3 Tbc;
+      Tbc.q.x = cam.qbc[0]; Tbc.q.y = cam.qbc[1]; Tbc.q.z = cam.qbc[2]; Tbc.q.w = cam.qbc[3];
+      Tbc.t = v3(cam.tbc[0], cam.tbc[1], cam.tbc[2]);
+      const V3 X = v3(pt_all[3 * (size_t)obs_pt[i]], pt_all[3 * (size_t)obs_pt[i] + 1], pt_all[3 * (size_t)obs_pt[i] + 2]);
+      bool pos = se3_act(se3_inv(se3_mul(load_se3(pose + 7 * V.rec_kf2[r]), Tbc)), X)[2] > 0;
+      if (V.rec_kf1[r] >= 0) pos = (se3_act(se3_inv(se3_mul(load_se3(pose + 7 * V.rec_kf1[r]), Tbc)), X)[2] > 0) && pos;
+      const bool close = obs_flags[i] & 0x1u;
+      out = (c2 > th_mono && !close) || (c2 > th_close && close) || !pos;
+    }
+    flags[i] = out ? 1 : 0;
+  }
+}
+
+}  // namespace gpba

@@ -1,0 +1,219 @@
+// gpba_pcg.cuh -- K5a: block-Jacobi preconditioned conjugate gradients on the block-sparse reduced
+// camera system (upper 12x12 blocks of Hschur).  Replaces the reduced-system solve of
+// BlockSolver::solve (block_solver.hpp:447) for systems too large / sparse for the dense factorization
+// (the reference uses Eigen::SimplicialLDLT there, g2o/solvers/linear_solver_eigen.h:94-124).
+//
+// One persistent cooperative kernel runs the whole iteration (grid-wide barriers between the SpMV,
+// the vector updates and the direction update), so a CG iteration costs three grid syncs instead of
+// ~6 kernel launches; all dot products are reduced in a fixed order from per-CTA partials (deterministic).
+#pragma once
+#include <cooperative_groups.h>
+#include <vector>
+#include "gpba_kernels.cuh"
+
+namespace gpba {
+
+namespace cg = cooperative_groups;
+
+struct PcgView {
+  int n_pose, n_hs;
+  const int* row_begin;  // [n_pose+1] into ent_*
+  const int* ent_blk;    // Hschur block id
+  const int* ent_col;    // block column
+  const unsigned char* ent_tr;  // 1: use the block transposed (lower part of the symmetric matrix)
+  const int* diag_blk;   // [n_pose]
+  const double* hs;      // block values
+  const double* b;
+  double* x;
+  double *r, *z, *p, *Ap, *Minv;  // Minv: 144 per pose
+  double* partial;       // [3][gridDim.x]
+  double tol;
+  int max_it;
+  int* out_it;           // [0] iterations, [1] converged
+  int* fail;
+};
+
+GPBA_D double grid_partial_sum(const double* partial, int n) {
+  // every thread sums the same n values in the same order
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += partial[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k_pcg(PcgView P) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[32];
+  const int tid = threadIdx.x, nthr = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+  const int n = P.n_pose * 12;
+  double* part0 = P.partial;
+  double* part1 = P.partial + gridDim.x;
+  double* part2 = P.partial + 2 * gridDim.x;
+  // ---- Jacobi preconditioner: inverse of every diagonal block (Gauss-Jordan on the SPD block, one thread per block)
+  for (int i = gtid; i < P.n_pose; i += nthr) {
+    double A[144], I[144];
+    const double* D = P.hs + (size_t)P.diag_blk[i] * 144;
+    for (int k = 0; k < 144; ++k) { A[k] = D[k]; I[k] = 0.0; }
+    for (int k = 0; k < 12; ++k) I[k * 13] = 1.0;
+    bool bad = false;
+    for (int c = 0; c < 12; ++c) {
+      const double piv = A[c * 12 + c];
+      if (!(piv > 0.0)) bad = true;
+      const double ip = 1.0 / piv;
+      for (int k = 0; k < 12; ++k) { A[c * 12 + k] *= ip; I[c * 12 + k] *= ip; }
+      for (int r2 = 0; r2 < 12; ++r2) {
+        if (r2 == c) continue;
+        const double f = A[r2 * 12 + c];
+        for (int k = 0; k < 12; ++k) { A[r2 * 12 + k] -= f * A[c * 12 + k]; I[r2 * 12 + k] -= f * I[c * 12 + k]; }
+      }
+    }
+    if (bad) atomicExch(P.fail, 1);
+    for (int k = 0; k < 144; ++k) P.Minv[(size_t)i * 144 + k] = I[k];
+  }
+  // ---- x = 0, r = b
+  for (int i = gtid; i < n; i += nthr) { P.x[i] = 0.0; P.r[i] = P.b[i]; }
+  grid.sync();
+  // z = Minv r, p = z, rz = r.z, bb = b.b
+  double l0 = 0.0, l1 = 0.0;
+  for (int i = gtid; i < n; i += nthr) {
+    const int blk = i / 12, rr = i % 12;
+    double s = 0.0;
+    for (int k = 0; k < 12; ++k) s = fma(P.Minv[(size_t)blk * 144 + rr * 12 + k], P.r[blk * 12 + k], s);
+    P.z[i] = s; P.p[i] = s;
+    l0 += P.r[i] * s;
+    l1 += P.b[i] * P.b[i];
+  }
+  l0 = block_sum(l0, red); l1 = block_sum(l1, red);
+  if (tid == 0) { part0[blockIdx.x] = l0; part1[blockIdx.x] = l1; }
+  grid.sync();
+  double rz = grid_partial_sum(part0, gridDim.x);
+  const double bb = grid_partial_sum(part1, gridDim.x);
+  const double thresh = P.tol * P.tol * bb;
+  int it = 0, converged = (bb == 0.0) ? 1 : 0;
+  grid.sync();
+  while (!converged && it < P.max_it) {
+    // ---- Ap = H p (one thread per scalar row), pAp
+    double lp = 0.0;
+    for (int i = gtid; i < n; i += nthr) {
+      const int brow = i / 12, rr = i % 12;
+      double s = 0.0;
+      for (int e = P.row_begin[brow]; e < P.row_begin[brow + 1]; ++e) {
+        const double* B = P.hs + (size_t)P.ent_blk[e] * 144;
+        const double* pv = P.p + (size_t)P.ent_col[e] * 12;
+        if (P.ent_tr[e]) {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) s = fma(B[k * 12 + rr], pv[k], s);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) s = fma(B[rr * 12 + k], pv[k], s);
+        }
+      }
+      P.Ap[i] = s;
+      lp += P.p[i] * s;
+    }
+    lp = block_sum(lp, red);
+    if (tid == 0) part0[blockIdx.x] = lp;
+    grid.sync();
+    const double pAp = grid_partial_sum(part0, gridDim.x);
+    const double alpha = rz / pAp;
+    // ---- x += alpha p ; r -= alpha Ap
+    for (int i = gtid; i < n; i += nthr) { P.x[i] = fma(alpha, P.p[i], P.x[i]); P.r[i] = fma(-alpha, P.Ap[i], P.r[i]); }
+    grid.sync();
+    // ---- z = Minv r ; rz_new, rr
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = gtid; i < n; i += nthr) {
+      const int blk = i / 12, rr = i % 12;
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) s = fma(P.Minv[(size_t)blk * 144 + rr * 12 + k], P.r[blk * 12 + k], s);
+      P.z[i] = s;
+      a0 += P.r[i] * s;
+      a1 += P.r[i] * P.r[i];
+    }
+    a0 = block_sum(a0, red); a1 = block_sum(a1, red);
+    if (tid == 0) { part1[blockIdx.x] = a0; part2[blockIdx.x] = a1; }
+    grid.sync();
+    const double rz_new = grid_partial_sum(part1, gridDim.x);
+    const double rr2 = grid_partial_sum(part2, gridDim.x);
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    ++it;
+    if (!(rr2 > thresh)) converged = 1;  // also exits on NaN
+    for (int i = gtid; i < n; i += nthr) P.p[i] = fma(beta, P.p[i], P.z[i]);
+    grid.sync();
+  }
+  if (gtid == 0) { P.out_it[0] = it; P.out_it[1] = converged; if (!isfinite(rz)) atomicExch(P.fail, 1); }
+}
+
+struct PcgBuffers {
+  double tolerance = 1e-12;
+  int max_iterations = 4000;
+  int total_iterations = 0;
+  int grid = 0;
+  int *d_row_begin = nullptr, *d_ent_blk = nullptr, *d_ent_col = nullptr, *d_diag = nullptr, *d_out = nullptr;
+  unsigned char* d_ent_tr = nullptr;
+  double *d_vec = nullptr, *d_minv = nullptr, *d_partial = nullptr;
+  int* h_out = nullptr;
+  int cap_pose = 0;
+  ~PcgBuffers() { release(); }
+  void release() {
+    cudaFree(d_row_begin); cudaFree(d_ent_blk); cudaFree(d_ent_col); cudaFree(d_diag); cudaFree(d_out); cudaFree(d_ent_tr);
+    cudaFree(d_vec); cudaFree(d_minv); cudaFree(d_partial);
+    if (h_out) cudaFreeHost(h_out);
+    d_row_begin = d_ent_blk = d_ent_col = d_diag = d_out = nullptr; d_ent_tr = nullptr; d_vec = d_minv = d_partial = nullptr; h_out = nullptr;
+  }
+  int setup(int n_pose, int n_hs, const std::vector<int>& hs_row, const std::vector<int>& hs_col, cudaStream_t s) {
+    release();
+    std::vector<int> cnt(n_pose + 1, 0), diag(n_pose, -1);
+    for (int k = 0; k < n_hs; ++k) { cnt[hs_row[k] + 1]++; if (hs_row[k] != hs_col[k]) cnt[hs_col[k] + 1]++; else diag[hs_row[k]] = k; }
+    for (int i = 0; i < n_pose; ++i) cnt[i + 1] += cnt[i];
+    std::vector<int> eb(cnt[n_pose]), ec(cnt[n_pose]), cur(cnt.begin(), cnt.end() - 1);
+    std::vector<unsigned char> et(cnt[n_pose]);
+    for (int k = 0; k < n_hs; ++k) {
+      int p = cur[hs_row[k]]++; eb[p] = k; ec[p] = hs_col[k]; et[p] = 0;
+      if (hs_row[k] != hs_col[k]) { p = cur[hs_col[k]]++; eb[p] = k; ec[p] = hs_row[k]; et[p] = 1; }
+    }
+#define PCG_CK(x) do { if ((x) != cudaSuccess) return -2; } while (0)
+    PCG_CK(cudaMalloc(&d_row_begin, sizeof(int) * (n_pose + 1)));
+    PCG_CK(cudaMalloc(&d_ent_blk, sizeof(int) * (eb.size() + 1)));
+    PCG_CK(cudaMalloc(&d_ent_col, sizeof(int) * (eb.size() + 1)));
+    PCG_CK(cudaMalloc(&d_ent_tr, eb.size() + 1));
+    PCG_CK(cudaMalloc(&d_diag, sizeof(int) * (n_pose + 1)));
+    PCG_CK(cudaMalloc(&d_out, sizeof(int) * 2));
+    PCG_CK(cudaMalloc(&d_vec, sizeof(double) * 12 * 4 * (size_t)(n_pose + 1)));
+    PCG_CK(cudaMalloc(&d_minv, sizeof(double) * 144 * (size_t)(n_pose + 1)));
+    PCG_CK(cudaMallocHost(&h_out, sizeof(int) * 2));
+    PCG_CK(cudaMemcpyAsync(d_row_begin, cnt.data(), sizeof(int) * (n_pose + 1), cudaMemcpyHostToDevice, s));
+    PCG_CK(cudaMemcpyAsync(d_ent_blk, eb.data(), sizeof(int) * eb.size(), cudaMemcpyHostToDevice, s));
+    PCG_CK(cudaMemcpyAsync(d_ent_col, ec.data(), sizeof(int) * ec.size(), cudaMemcpyHostToDevice, s));
+    PCG_CK(cudaMemcpyAsync(d_ent_tr, et.data(), et.size(), cudaMemcpyHostToDevice, s));
+    PCG_CK(cudaMemcpyAsync(d_diag, diag.data(), sizeof(int) * n_pose, cudaMemcpyHostToDevice, s));
+    int dev = 0, sms = 0, per_sm = 0;
+    PCG_CK(cudaGetDevice(&dev));
+    PCG_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PCG_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0));
+    const int want = (n_pose * 12 + 255) / 256;
+    grid = std::max(1, std::min(want, sms * std::max(1, std::min(per_sm, 2))));
+    PCG_CK(cudaMalloc(&d_partial, sizeof(double) * 3 * grid));
+    PCG_CK(cudaStreamSynchronize(s));  // host vectors go out of scope
+    cap_pose = n_pose;
+    return 0;
+  }
+  int solve(int n_pose, int n_hs, const double* hs, const double* b, double* x, cudaStream_t s, int* iters, int* d_fail) {
+    PcgView P;
+    P.n_pose = n_pose; P.n_hs = n_hs; P.row_begin = d_row_begin; P.ent_blk = d_ent_blk; P.ent_col = d_ent_col; P.ent_tr = d_ent_tr;
+    P.diag_blk = d_diag; P.hs = hs; P.b = b; P.x = x;
+    const size_t n = (size_t)n_pose * 12;
+    P.r = d_vec; P.z = d_vec + n; P.p = d_vec + 2 * n; P.Ap = d_vec + 3 * n; P.Minv = d_minv; P.partial = d_partial;
+    P.tol = tolerance; P.max_it = max_iterations; P.out_it = d_out; P.fail = d_fail;
+    void* args[] = {&P};
+    PCG_CK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(grid), dim3(256), args, 0, s));
+    PCG_CK(cudaMemcpyAsync(h_out, d_out, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    PCG_CK(cudaStreamSynchronize(s));
+    *iters = h_out[0];
+    total_iterations += h_out[0];
+    return 0;
+#undef PCG_CK
+  }
+};
+
+}  // namespace gpba

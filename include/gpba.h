@@ -191,6 +191,7 @@ int gpba_get_b(gpba_handle* h, double* b);
 int gpba_get_hpp(gpba_handle* h, double* blocks);
 int gpba_get_hschur(gpba_handle* h, double* blocks, double* bschur);
 int gpba_get_hll(gpba_handle* h, double* blocks);
+int gpba_get_hpl(gpba_handle* h, int64_t* lm_begin /* [n_active_pt+1] */, int32_t* pose /* [n_hpl] */, double* blocks /* [n_hpl][12][3] */);
 /* SparseOptimizer::update (oplus on every free vertex, sparse_optimizer.cpp:422-435),
  * push / pop / discardTop (sparse_optimizer.cpp:600-613). */
 int gpba_oplus(gpba_handle* h, const double* x /* NULL = the solver's own x */);

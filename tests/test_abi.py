@@ -1,0 +1,65 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/gpba.h declares; without a CUDA device the product path fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from pygpba import lib as gl
+from pygpba import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "gpba.h")).read()
+    return sorted(set(re.findall(r"^\s*(?:int|void|const char\*)\s+(gpba_\w+)\s*\(", src, re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = gl.lib()
+    declared = header_symbols()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/gpba.h but not exported by libgpba.so"
+    assert sorted(gl.SYMBOLS) == declared
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors must have the sizes the C compiler gives the header structs."""
+    import subprocess, tempfile, textwrap
+    code = textwrap.dedent("""
+        #include <stdio.h>
+        #include "gpba.h"
+        int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(gpba_problem), sizeof(gpba_lm_trace), sizeof(gpba_lm_params),
+                                sizeof(gpba_thresholds), sizeof(gpba_structure_info)); return 0; }
+    """)
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(code)
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        sizes = list(map(int, subprocess.check_output([os.path.join(d, "t")]).split()))
+    from pygpba.problem import CProblem, LmTrace, LmParams, Thresholds, StructureInfo
+    assert sizes == [C.sizeof(CProblem), C.sizeof(LmTrace), C.sizeof(LmParams), C.sizeof(Thresholds), C.sizeof(StructureInfo)]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    P = synth.make_problem("tiny")
+    with pytest.raises(gl.GpbaError) as e:
+        gl.GpBa(P)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_reference_oracle():
+    """The product tree must not import / link / execute anything under oracle/."""
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "amc-slam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"oracle_py|libgpba_oracle|oracle/|numpy_mirror", txt):
+                    bad.append(os.path.join(base, f))
+    assert not bad, bad
