@@ -24,6 +24,7 @@ struct CholView {
   const int* col_begin;         // [NT+1] into col_rows
   const int* col_rows;          // rows i>k with L_ik != 0, ascending
   double* tiles;
+  const int* perm;              // [n/12] fill-reducing order of the pose blocks: permuted index of block b
 };
 
 // zero the allocated tiles and put 1 on the padded part of the diagonal
@@ -45,14 +46,15 @@ __global__ void k_chol_scatter(CholView C, int n_hs, const int* __restrict__ hs_
     const int blk = (int)(j / 144), e = (int)(j % 144);
     const int r = e / 12, c = e % 12;
     const int bi = hs_row[blk], bj = hs_col[blk];
-    // element (bi*12+r, bj*12+c) of the upper triangle == element (bj*12+c, bi*12+r) of the lower one
-    const int R = bj * 12 + c, Cc = bi * 12 + r;
-    if (bi == bj && c < r) continue;  // diagonal block: take its lower half from the (symmetric) upper entries
+    const int pi = C.perm[bi], pj = C.perm[bj];
+    // symmetric matrix: element (bi*12+r, bj*12+c) == element (bj*12+c, bi*12+r); store whichever lands in the
+    // lower triangle of the permuted matrix
+    int R, Cc;
+    if (pi == pj) { if (c < r) continue; R = pi * 12 + c; Cc = pi * 12 + r; }
+    else if (pi > pj) { R = pi * 12 + r; Cc = pj * 12 + c; }
+    else { R = pj * 12 + c; Cc = pi * 12 + r; }
     const int ti = R / GPBA_NB, tj = Cc / GPBA_NB;
     C.tiles[C.tile_off[(size_t)ti * C.NT + tj] + (R % GPBA_NB) * GPBA_NB + (Cc % GPBA_NB)] = hs[j];
-    if (ti == tj && R != Cc && bi != bj) {
-      // off-diagonal block inside a diagonal tile: nothing to mirror (only the lower triangle is used)
-    }
   }
 }
 
@@ -147,7 +149,9 @@ __global__ void __launch_bounds__(256) k_chol_solve(CholView C, const double* __
   __shared__ double yk[GPBA_NB];
   __shared__ double Ld[GPBA_NB][GPBA_NBP];
   const int tid = threadIdx.x, NTNB = C.NT * GPBA_NB;
-  for (int j = tid; j < NTNB; j += blockDim.x) work[j] = j < C.n ? rhs[j] : 0.0;
+  for (int j = tid; j < NTNB; j += blockDim.x) work[j] = 0.0;
+  __syncthreads();
+  for (int j = tid; j < C.n; j += blockDim.x) work[C.perm[j / 12] * 12 + j % 12] = rhs[j];
   __syncthreads();
   for (int k = 0; k < C.NT; ++k) {  // L y = b
     const double* Lkk = C.tiles + C.tile_off[(size_t)k * C.NT + k];
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(CholView C, const double* __
     if (tid < GPBA_NB) work[k * GPBA_NB + tid] = yk[tid];
     __syncthreads();
   }
-  for (int j = tid; j < C.n; j += blockDim.x) x[j] = work[j];
+  for (int j = tid; j < C.n; j += blockDim.x) x[j] = work[C.perm[j / 12] * 12 + j % 12];
 }
 
 }  // namespace gpba

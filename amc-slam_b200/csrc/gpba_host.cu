@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -141,7 +142,7 @@ struct Solver {
   int NT = 0;
   int64_t chol_doubles = 0;
   DBuf<int64_t> d_tile_off;
-  DBuf<int> d_col_begin, d_col_rows;
+  DBuf<int> d_col_begin, d_col_rows, d_chol_perm;
   DBuf<double> d_tiles, d_chol_work;
   std::vector<int> chol_col_begin;
   // ------------------------------------------------------------------ PCG
@@ -160,6 +161,12 @@ struct Solver {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double stage_ms[GPBA_N_STAGES] = {0};
   int64_t stage_launches[GPBA_N_STAGES] = {0};
+  // event pairs recorded on the library stream around every stage; elapsed times are read back
+  // (cudaEventElapsedTime) only in gpba_stage_stats, so the timed region is never synchronised by profiling
+  struct EvPair { cudaEvent_t a, b; int stage; };
+  std::vector<EvPair> ev_pool;
+  size_t ev_used = 0;
+  bool structure_dirty = true;
 
   DevView V{};
 
@@ -169,19 +176,35 @@ struct Solver {
     if (h_fail) cudaFreeHost(h_fail);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (stream) cudaStreamDestroy(stream);
   }
 
   // stage timing helpers
-  void t0() { if (profiling) cudaEventRecord(ev0, stream); }
+  void t0() {
+    if (!profiling) return;
+    if (ev_used == ev_pool.size()) {
+      EvPair e;
+      cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.stage = -1;
+      ev_pool.push_back(e);
+    }
+    cudaEventRecord(ev_pool[ev_used].a, stream);
+  }
   void t1(int stage, int launches) {
     stage_launches[stage] += launches;
     if (!profiling) return;
-    cudaEventRecord(ev1, stream);
-    cudaEventSynchronize(ev1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    stage_ms[stage] += ms;
+    ev_pool[ev_used].stage = stage;
+    cudaEventRecord(ev_pool[ev_used].b, stream);
+    ++ev_used;
+  }
+  void collect_events() {
+    if (ev_used == 0) return;
+    cudaStreamSynchronize(stream);
+    for (size_t i = 0; i < ev_used; ++i) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev_pool[i].a, ev_pool[i].b) == cudaSuccess) stage_ms[ev_pool[i].stage] += ms;
+    }
+    ev_used = 0;
   }
 
   int init(const gpba_problem* P, int dev);
@@ -339,20 +362,41 @@ int Solver::build_structure() {
   n_pose = 0;
   for (int k = 0; k < n_kf; ++k)
     if (kf_act[k] && !kf_fixed[k]) kf_h[k] = n_pose++;
-  n_aobs = (int64_t)act.size();
   // --- landmark order: ascending first keyframe (locality of record / pose accesses), ties by point id
   std::vector<int> first_kf(n_pt, std::numeric_limits<int>::max());
   for (int64_t i : act) first_kf[obs_pt[i]] = std::min(first_kf[obs_pt[i]], rec_kf2[obs_rec[i]]);
-  lm_pt.clear();
-  for (int p = 0; p < n_pt; ++p) if (pt_act[p]) lm_pt.push_back(p);
+  std::vector<int> all_lm_pt;
+  for (int p = 0; p < n_pt; ++p) if (pt_act[p]) all_lm_pt.push_back(p);
+  const int n_lm_all = (int)all_lm_pt.size();
+  std::vector<int> rank_of_pt(n_pt, -1), pt_lm_all(n_pt, -1);
+  for (int l = 0; l < n_lm_all; ++l) rank_of_pt[all_lm_pt[l]] = l;  // g2o landmark index = rank among active points
+  std::stable_sort(all_lm_pt.begin(), all_lm_pt.end(), [&](int a, int b) { return first_kf[a] < first_kf[b]; });
+  for (int l = 0; l < n_lm_all; ++l) pt_lm_all[all_lm_pt[l]] = l;
+  // --- multi-GPU: this rank owns a contiguous range of the sorted landmarks, balanced by observation count;
+  //     patterns (Hpp, Hschur) are built from ALL landmarks so that every rank packs the same block list
+  int own_lo = 0, own_hi = n_lm_all;
+  if (nranks > 1) {
+    std::vector<int64_t> cnt(n_lm_all + 1, 0);
+    for (int64_t i : act) cnt[pt_lm_all[obs_pt[i]] + 1]++;
+    for (int l = 0; l < n_lm_all; ++l) cnt[l + 1] += cnt[l];
+    const int64_t total = cnt[n_lm_all];
+    auto cut = [&](int r) { return (int)(std::lower_bound(cnt.begin(), cnt.end(), total * r / nranks) - cnt.begin()); };
+    own_lo = rank == 0 ? 0 : std::min(cut(rank), n_lm_all);
+    own_hi = rank == nranks - 1 ? n_lm_all : std::min(cut(rank + 1), n_lm_all);
+    if (own_hi < own_lo) own_hi = own_lo;
+  }
+  std::vector<int64_t> act_all;
+  if (nranks > 1) {
+    act_all = act;
+    std::vector<int64_t> mine;
+    for (int64_t i : act) { const int l = pt_lm_all[obs_pt[i]]; if (l >= own_lo && l < own_hi) mine.push_back(i); }
+    act.swap(mine);
+  }
+  n_aobs = (int64_t)act.size();
+  lm_pt.assign(all_lm_pt.begin() + own_lo, all_lm_pt.begin() + own_hi);
   n_lm = (int)lm_pt.size();
   lm_rank.resize(n_lm);
-  {
-    std::vector<int> rank_of_pt(n_pt, -1);
-    for (int l = 0; l < n_lm; ++l) rank_of_pt[lm_pt[l]] = l;  // g2o landmark index = rank among active points
-    std::stable_sort(lm_pt.begin(), lm_pt.end(), [&](int a, int b) { return first_kf[a] < first_kf[b]; });
-    for (int l = 0; l < n_lm; ++l) lm_rank[l] = rank_of_pt[lm_pt[l]];
-  }
+  for (int l = 0; l < n_lm; ++l) lm_rank[l] = rank_of_pt[lm_pt[l]];
   pt_lm.assign(n_pt, -1);
   for (int l = 0; l < n_lm; ++l) pt_lm[lm_pt[l]] = l;
   // --- observations sorted by landmark (stable: insertion order inside a landmark)
@@ -413,12 +457,11 @@ int Solver::build_structure() {
   };
   for (int i = 0; i < n_pose; ++i) pp_rows[i].push_back(i);
   for (int i = 0; i < n_prior; ++i) add_pair(pp_rows, kf_h[prior_kf1[i]], kf_h[prior_kf2[i]]);
-  {
-    std::vector<char> rec_used(n_rec, 0);
-    for (int64_t j = 0; j < n_aobs; ++j) rec_used[srec[j]] = 1;
-    for (int r = 0; r < n_rec; ++r)
-      if (rec_used[r] && rec_kf1[r] >= 0) add_pair(pp_rows, kf_h[rec_kf1[r]], kf_h[rec_kf2[r]]);
-  }
+  std::vector<char> rec_used(n_rec, 0);
+  for (int64_t j = 0; j < n_aobs; ++j) rec_used[srec[j]] = 1;
+  for (int64_t i : act_all) rec_used[obs_rec[i]] = 1;
+  for (int r = 0; r < n_rec; ++r)
+    if (rec_used[r] && rec_kf1[r] >= 0) add_pair(pp_rows, kf_h[rec_kf1[r]], kf_h[rec_kf2[r]]);
   auto uniq = [](std::vector<std::vector<int>>& rows) {
     for (auto& v : rows) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
   };
@@ -426,11 +469,12 @@ int Solver::build_structure() {
   // --- Hschur pattern: Hpp pattern U pose pairs of ALL edges (any level) of active landmarks (block_solver.hpp:262-288)
   hs_rows = pp_rows;
   {
-    std::vector<std::vector<int>> lm_all(n_lm);
-    bool any_inactive = n_aobs != n_obs;
+    const bool any_inactive = n_aobs != n_obs;  // level-1 edges or landmarks owned by other ranks
+    const int n_pat = any_inactive ? n_lm_all : n_lm;
+    std::vector<std::vector<int>> lm_all(any_inactive ? n_lm_all : 0);
     if (any_inactive) {
       for (int64_t i = 0; i < n_obs; ++i) {
-        const int l = pt_lm[obs_pt[i]];
+        const int l = pt_lm_all[obs_pt[i]];
         if (l < 0) continue;
         const int r = obs_rec[i];
         if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0) lm_all[l].push_back(kf_h[rec_kf1[r]]);
@@ -438,7 +482,7 @@ int Solver::build_structure() {
       }
     }
     std::vector<int> tmp;
-    for (int l = 0; l < n_lm; ++l) {
+    for (int l = 0; l < n_pat; ++l) {
       const int* v; int nv;
       if (any_inactive) {
         tmp = lm_all[l];
@@ -489,12 +533,8 @@ int Solver::build_structure() {
     if (h2 >= 0) b22 = pp(h2, h2);
     if (h1 >= 0 && h2 >= 0) b12 = h1 <= h2 ? pp(h1, h2) : (pp(h2, h1) | 0x40000000);
   };
-  {
-    std::vector<char> rec_used(n_rec, 0);
-    for (int64_t j = 0; j < n_aobs; ++j) rec_used[srec[j]] = 1;
-    for (int r = 0; r < n_rec; ++r)
-      if (rec_used[r]) pair_blocks(rec_kf1[r] >= 0 ? kf_h[rec_kf1[r]] : -1, kf_h[rec_kf2[r]], rec11[r], rec12[r], rec22[r]);
-  }
+  for (int r = 0; r < n_rec; ++r)
+    if (rec_used[r]) pair_blocks(rec_kf1[r] >= 0 ? kf_h[rec_kf1[r]] : -1, kf_h[rec_kf2[r]], rec11[r], rec12[r], rec22[r]);
   for (int i = 0; i < n_prior; ++i) pair_blocks(kf_h[prior_kf1[i]], kf_h[prior_kf2[i]], pr11[i], pr12[i], pr22[i]);
   std::vector<int> pose_diag(n_pose), hs_from(n_hs, -1), hs_diag(n_hs, -1);
   for (int i = 0; i < n_pose; ++i) pose_diag[i] = pp(i, i);
@@ -603,7 +643,7 @@ int Solver::build_structure() {
   else CKR(pcg.setup(n_pose, n_hs, hs_row, hs_col, stream));
   CK(cudaStreamSynchronize(stream));
   info.n_free_kf = n_pose; info.n_active_pt = n_lm; info.n_active_obs = n_aobs; info.n_hpl = n_hpl; info.n_hpp = n_hpp; info.n_hschur = n_hs;
-  structure_ok = true; system_ok = false; lambda_applied = false;
+  structure_ok = true; system_ok = false; lambda_applied = false; structure_dirty = false;
   last_eval = cur;
   return GPBA_OK;
 }
@@ -614,10 +654,42 @@ int Solver::build_cholesky_structure() {
   NT = (n + GPBA_NB - 1) / GPBA_NB;
   if (NT == 0) NT = 1;
   const int bpt = GPBA_NB / 12;  // pose blocks per tile
+  // fill-reducing order of the pose blocks: reverse Cuthill-McKee on the Hschur block graph (the role AMD plays
+  // for SimplicialLDLT, linear_solver_eigen.h:147-201); a revisited place then sits next to its first visit and
+  // the factor stays banded instead of filling the whole loop.
+  std::vector<int> perm(n_pose, 0);
+  {
+    std::vector<std::vector<int>> adj(n_pose);
+    for (int k = 0; k < n_hs; ++k) if (hs_row[k] != hs_col[k]) { adj[hs_row[k]].push_back(hs_col[k]); adj[hs_col[k]].push_back(hs_row[k]); }
+    std::vector<int> order; order.reserve(n_pose);
+    std::vector<char> seen(n_pose, 0);
+    auto bfs = [&](int start, std::vector<int>& out) {
+      size_t head = out.size();
+      out.push_back(start); seen[start] = 1;
+      while (head < out.size()) {
+        const int v = out[head++];
+        std::vector<int> nb;
+        for (int w : adj[v]) if (!seen[w]) { seen[w] = 1; nb.push_back(w); }
+        std::sort(nb.begin(), nb.end(), [&](int a, int b) { return adj[a].size() != adj[b].size() ? adj[a].size() < adj[b].size() : a < b; });
+        out.insert(out.end(), nb.begin(), nb.end());
+      }
+    };
+    for (int s0 = 0; s0 < n_pose; ++s0) {
+      if (seen[s0]) continue;
+      // pseudo-peripheral start: BFS from s0, restart from the last (farthest, lowest-degree) node
+      std::vector<int> probe;
+      bfs(s0, probe);
+      const int far = probe.back();
+      for (int v : probe) seen[v] = 0;
+      bfs(far, order);
+    }
+    for (int i = 0; i < n_pose; ++i) perm[order[n_pose - 1 - i]] = i;  // reversed
+  }
   std::vector<char> nz((size_t)NT * NT, 0);
   for (int t = 0; t < NT; ++t) nz[(size_t)t * NT + t] = 1;
   for (int k = 0; k < n_hs; ++k) {
-    const int ti = hs_col[k] / bpt, tj = hs_row[k] / bpt;  // lower: row tile from the larger index
+    int ti = perm[hs_col[k]] / bpt, tj = perm[hs_row[k]] / bpt;
+    if (ti < tj) std::swap(ti, tj);  // lower triangle
     nz[(size_t)ti * NT + tj] = 1;
   }
   std::vector<int> col_rows;
@@ -638,7 +710,9 @@ int Solver::build_cholesky_structure() {
     for (int j = 0; j <= i; ++j)
       if (nz[(size_t)i * NT + j]) { off[(size_t)i * NT + j] = cursor; cursor += GPBA_NB * GPBA_NB; }
   chol_doubles = cursor;
+  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: n=%d NT=%d tiles=%lld (dense lower would be %d), %.1f MB\n", n, NT, (long long)(cursor / (GPBA_NB * GPBA_NB)), NT * (NT + 1) / 2, cursor * 8 / 1e6);
   CKR(d_tile_off.upload(off, stream)); CKR(d_col_begin.upload(chol_col_begin, stream)); CKR(d_col_rows.upload(col_rows, stream));
+  CKR(d_chol_perm.upload(perm, stream));
   CKR(d_tiles.alloc((size_t)chol_doubles)); CKR(d_chol_work.alloc((size_t)NT * GPBA_NB));
   return GPBA_OK;
 }
@@ -690,13 +764,15 @@ int Solver::build_system() {
     if (stereo) k_lin_points<true><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_hpl.p);
     else k_lin_points<false><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_hpl.p);
     CK(cudaGetLastError());
+    t1(2, 1);
+    t0();
     const int g2 = std::min((n_rseg + 3) / 4, 148 * 16);
     if (stereo) k_lin_records<true><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p);
     else k_lin_records<false><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p);
     CK(cudaGetLastError());
     k_rec_to_hpp<<<n_rec, 128, 0, stream>>>(V, d_rec.p, d_recS.p, d_hpp.p, d_bp.p);
     CK(cudaGetLastError());
-    launches += 3;
+    launches += 2;
   }
   const int np = n_prior + (n_velp + 63) / 64;
   if (np > 0 && rank == 0) {
@@ -704,7 +780,7 @@ int Solver::build_system() {
     CK(cudaGetLastError());
     launches++;
   }
-  t1(2, launches);
+  t1(3, launches);
   system_ok = true;
   return GPBA_OK;
 }
@@ -715,14 +791,14 @@ int Solver::allreduce_system() {
   const size_t count = (size_t)n_hs * 144 + (size_t)n_pose * 12;
   int rc = g_nccl.AllReduce(d_hs.p, d_hs.p, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream);
   if (rc != 0) { g_err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return GPBA_ERR_NCCL; }
-  t1(6, 1);
+  t1(9, 1);
   return GPBA_OK;
 }
 int Solver::allreduce_scalar(double* v) {
   t0();
   int rc = g_nccl.AllReduce(v, v, 1, 8, 0, comm, stream);
   if (rc != 0) { g_err = "ncclAllReduce(scalar) failed"; return GPBA_ERR_NCCL; }
-  t1(6, 1);
+  t1(9, 1);
   return GPBA_OK;
 }
 
@@ -739,17 +815,20 @@ int Solver::solve(double lambda, bool* ok) {
   if (n_lm > 0) {
     k_schur_prep<<<std::min((n_lm + 3) / 4, 148 * 16), 128, 0, stream>>>(V, lambda, d_hll.p, d_bl.p, d_hpl.p, d_U.p, d_ptL.p, d_fail.p);
     CK(cudaGetLastError());
+    t1(4, 2);
+    t0();
     k_schur_gather<<<std::min((n_items + 3) / 4, 148 * 16), 128, 0, stream>>>(n_items, d_item_blk.p, d_item_begin.p, d_pair_i.p, d_pair_j.p,
                                                                               d_hpl_lm.p, d_hs_diag_pose.p, d_U.p, d_ptL.p, d_hs.p, bs);
     CK(cudaGetLastError());
-    launches += 2;
+    t1(5, 1);
+  } else {
+    t1(4, 1);
   }
-  t1(3, launches);
   CKR(allreduce_system());
   t0();
   launches = 0;
   if (linear_solver == GPBA_SOLVER_DENSE_CHOL) {
-    CholView C{NT, n_pose * 12, d_tile_off.p, d_col_begin.p, d_col_rows.p, d_tiles.p};
+    CholView C{NT, n_pose * 12, d_tile_off.p, d_col_begin.p, d_col_rows.p, d_tiles.p, d_chol_perm.p};
     k_chol_clear<<<std::min((chol_doubles + 255) / 256, (int64_t)148 * 16), 256, 0, stream>>>(C, chol_doubles);
     const int npad = NT * GPBA_NB - n_pose * 12;
     if (npad > 0) k_chol_pad<<<(npad + 63) / 64, 64, 0, stream>>>(C);
@@ -766,15 +845,18 @@ int Solver::solve(double lambda, bool* ok) {
       launches++;
     }
     CK(cudaGetLastError());
+    t1(6, launches);
+    t0();
+    launches = 1;
     k_chol_solve<<<1, 256, 0, stream>>>(C, bs, d_x.p, d_chol_work.p);
     CK(cudaGetLastError());
-    launches++;
+    t1(7, launches);
   } else {
     int it = 0;
     CKR(pcg.solve(n_pose, n_hs, d_hs.p, bs, d_x.p, stream, &it, d_fail.p));
-    launches += it * 3 + 2;
+    launches += 1;
+    t1(6, launches);
   }
-  t1(4, launches);
   CK(cudaMemcpyAsync(h_fail, d_fail.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   *ok = (*h_fail == 0);
@@ -796,7 +878,7 @@ int Solver::apply_update(double lambda, double* scale) {
   // pose part of computeScale is replicated on every rank; landmark part is per-rank
   k_reduce<<<1, 256, 0, stream>>>(d_partial.p, gp, d_pose_scale.p, rank == 0 ? n_pose : 0, d_scal.p + 1);
   CK(cudaGetLastError());
-  t1(5, 3);
+  t1(8, 3);
   if (nranks > 1) CKR(allreduce_scalar(d_scal.p + 1));
   if (scale) {
     CK(cudaMemcpyAsync(h_scal + 1, d_scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -808,7 +890,7 @@ int Solver::apply_update(double lambda, double* scale) {
 
 // OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-169)
 int Solver::lm_solve(int iteration, const gpba_lm_params& P, const volatile unsigned char* stop, gpba_lm_trace* tr, int* result) {
-  if (iteration == 0) CKR(build_structure());
+  if (iteration == 0 && structure_dirty) CKR(build_structure());
   double currentChi = 0;
   CKR(compute_errors(cur, false, &currentChi));
   double tempChi = currentChi;
@@ -1199,12 +1281,14 @@ int gpba_set_levels(gpba_handle* h, const uint8_t* level) {
   NEED(h);
   Solver& s = S(h);
   for (int64_t i = 0; i < s.n_obs; ++i) { if (level[i]) s.obs_flags[i] |= GPBA_OBS_LEVEL1; else s.obs_flags[i] &= ~GPBA_OBS_LEVEL1; }
+  s.structure_dirty = true;
   return GPBA_OK;  // takes effect at the next build_structure / optimize (initializeOptimization)
 }
 int gpba_set_robust_kernel(gpba_handle* h, int enabled) {
   NEED(h);
   Solver& s = S(h);
   for (int64_t i = 0; i < s.n_obs; ++i) { if (!enabled) s.obs_flags[i] |= GPBA_OBS_NO_KERNEL; else s.obs_flags[i] &= ~GPBA_OBS_NO_KERNEL; }
+  s.structure_dirty = true;
   return GPBA_OK;
 }
 
@@ -1258,6 +1342,7 @@ int gpba_rejection_rounds(gpba_handle* h, int n_rounds, int iters, const gpba_th
 
 int gpba_stage_stats(gpba_handle* h, double ms_total[GPBA_N_STAGES], int64_t launches[GPBA_N_STAGES], int reset) {
   NEED(h);
+  S(h).collect_events();
   for (int i = 0; i < GPBA_N_STAGES; ++i) {
     if (ms_total) ms_total[i] = S(h).stage_ms[i];
     if (launches) launches[i] = S(h).stage_launches[i];
@@ -1265,7 +1350,8 @@ int gpba_stage_stats(gpba_handle* h, double ms_total[GPBA_N_STAGES], int64_t lau
   }
   return GPBA_OK;
 }
-int gpba_set_profiling(gpba_handle* h, int enabled) { NEED(h); S(h).profiling = enabled != 0; return GPBA_OK; }
+int gpba_set_profiling(gpba_handle* h, int enabled) { NEED(h); S(h).collect_events(); S(h).profiling = enabled != 0; return GPBA_OK; }
+void* gpba_get_stream(gpba_handle* h) { return h ? (void*)S(h).stream : nullptr; }
 
 int gpba_reset_state(gpba_handle* h, const double* kf_pose, const double* kf_vel, const double* pt_xyz) {
   NEED(h);

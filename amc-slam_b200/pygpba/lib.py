@@ -21,8 +21,12 @@ SYMBOLS = [
     "gpba_get_hschur", "gpba_get_hll", "gpba_get_hpl", "gpba_oplus", "gpba_push", "gpba_pop", "gpba_discard_top",
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
-    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state",
+    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream",
 ]
+
+
+STAGE_NAMES = ["records", "residuals", "lin_landmarks", "lin_poses", "schur_prepare", "schur_gather", "factorize", "tri_solve",
+               "backsub_update", "collective"]
 
 
 class GpbaError(RuntimeError):
@@ -36,6 +40,7 @@ def lib():
             raise GpbaError(f"{LIB_PATH} is missing: build it with `python amc-slam_b200/build.py` (no CPU fallback exists)")
         L = C.CDLL(LIB_PATH)
         L.gpba_last_error.restype = C.c_char_p
+        L.gpba_get_stream.restype = C.c_void_p
         L.gpba_create.argtypes = [C.POINTER(CProblem), C.c_int, C.POINTER(C.c_void_p)]
         L.gpba_create_dist.argtypes = [C.POINTER(CProblem), C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
         _LIB = L
@@ -220,8 +225,11 @@ class GpBa:
     def stage_stats(self, reset=False):
         ms = (C.c_double * GPBA_N_STAGES)(); n = (C.c_int64 * GPBA_N_STAGES)()
         self._ck(self.L.gpba_stage_stats(self.h, ms, n, int(reset)), "gpba_stage_stats")
-        names = ["records", "residuals", "quadratic_form", "schur", "linear_solver", "backsub_update", "collective"]
+        names = STAGE_NAMES
         return {k: dict(ms=ms[i], launches=n[i]) for i, k in enumerate(names)}
+
+    def stream(self):
+        return self.L.gpba_get_stream(self.h)
 
     def reset_state(self, kf_pose=None, kf_vel=None, pt_xyz=None):
         P = self.prob

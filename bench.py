@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- GP-BA observations/s and LM iterations/s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4] [--impl gpba|reference]
+
+A "step" is one whole gpba_optimize() (the LM loop of SparseOptimizer::optimize, up to 10 outer iterations)
+over one synthetic map.  Workload at every N: BASELINE configs[3] = post-loop-closure global GP-BA, 5 async
+cameras, 1k keyframes, 500k points, ~5M observations (the config the north_star target is quoted on and the
+largest one that fits a single GPU); at N>1 the landmarks are sharded across ranks (strong scaling), partial
+reduced camera systems are summed with ncclAllReduce.
+
+value   = observations x executed LM iterations / device time, problem + structure already resident in HBM.
+e2e     = same metric through the C ABI from host buffers: gpba_create (H2D) + structure + optimize +
+          gpba_download_state (D2H) + destroy inside the timed region.
+--impl reference times the CPU restatement of the reference's g2o path (oracle/, all host cores) on a bounded
+sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "amc-slam_b200"))
+
+WORKLOADS = {
+    "c2": "local GP-BA (LocalGPBA): 4 async cameras, 30 keyframes, 20k points, ~300k observations",
+    "c3": "local GP-BA, 30% outliers: 4 async cameras, 50 keyframes, ~500k observations",
+    "c4": "post-loop-closure global GP-BA: 5 async cameras, 1k keyframes, 500k points, ~5M observations",
+    "c5": "10 km global GP-BA: 5 async cameras, 10k keyframes, 2M points, ~20M observations",
+}
+# bounded CPU sample of each workload (same generator family, fewer keyframes / points)
+CPU_SAMPLE = {
+    "c2": dict(n_kf=30, n_pt=6000), "c3": dict(n_kf=50, n_pt=6000),
+    "c4": dict(n_kf=120, n_pt=60000), "c5": dict(n_kf=120, n_pt=60000),
+}
+LM_ITERS = 10
+
+
+def load_problem(name, **override):
+    """Generate (or load from a /tmp cache written by an earlier arm of the same run) the seeded synthetic map."""
+    from pygpba import synth
+    from pygpba.problem import Problem
+    import pickle
+    key = name + "".join(f"_{k}{v}" for k, v in sorted(override.items()))
+    path = f"/tmp/gpba_bench_{key}.pkl"
+    if os.path.exists(path):
+        try:
+            with open(path, "rb") as f:
+                return pickle.load(f)
+        except Exception:
+            pass
+    P = synth.make_problem(name, **override)
+    P.truth = None
+    try:
+        with open(path + f".{os.getpid()}", "wb") as f:
+            pickle.dump(P, f, protocol=4)
+        os.replace(path + f".{os.getpid()}", path)
+    except Exception:
+        pass
+    return P
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def algorithmic_bytes(info, n_kf_free):
+    """Algorithmic bytes per launch of each HBM-bound stage (SURVEY.md §8d figures x this map's counts)."""
+    No, Np, Npl, Nhs, Nk = info.n_active_obs, info.n_active_pt, info.n_hpl, info.n_hschur, n_kf_free
+    return {
+        "residuals": 36 * No + 24 * Np,
+        "lin_landmarks": 36 * No + 24 * Np + 288 * Npl + 72 * Np,
+        "lin_poses": 36 * No + 24 * Np,
+        "schur_prepare": 288 * Npl + 72 * Np + 288 * Npl + 72 * Np,
+        "schur_gather": 288 * Npl + 72 * Np + 1152 * Nhs + 96 * Nk,
+        "backsub_update": 288 * Npl + 72 * Np + 96 * Nk + 48 * Np,
+    }
+
+
+def run_reference(args):
+    """CPU arm: the oracle (C++ restatement of the reference's g2o path) on the host cores, bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    sample = CPU_SAMPLE[args.workload]
+    P = load_problem(args.workload, **sample)
+    iters = 2
+    times, its = [], 0
+    for s in range(args.warmup + args.steps):
+        o = oracle_py.Oracle(P, threads=cores)
+        t = time.perf_counter()
+        tr = o.optimize(iters)
+        dt = time.perf_counter() - t
+        if s >= args.warmup:
+            times.append(dt); its += tr.n_iters
+        o.close()
+    total = sum(times)
+    value = P.n_obs * its / total
+    desc = f"{args.workload} family, {sample['n_kf']} keyframes, {P.n_pt} points, {P.n_obs} observations, {iters} LM iterations per step"
+    out = {
+        "impl": "reference", "metric": "gpba_observations_per_sec", "value": value, "unit": "obs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "lm_iters_per_sec": its / total,
+        "config": {"workload": WORKLOADS[args.workload], "name": args.workload, "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "obs/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def run_gpba(args):
+    import torch
+    import torch.distributed as dist
+    from pygpba import lib as gl
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(gl.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    P = load_problem(args.workload)
+    params = gl.default_lm_params()
+    if args.pcg:
+        from pygpba.problem import SOLVER_PCG
+        P.linear_solver = SOLVER_PCG
+        params.pcg_tolerance = args.pcg_tol
+
+    # pin the big host arrays so the e2e H2D copies run from pinned memory
+    cudart = torch.cuda.cudart()
+    pinned = []
+    for a in (P.obs_u, P.obs_v, P.obs_inv_sigma2, P.obs_rec, P.obs_pt, P.obs_flags, P.pt_xyz, P.kf_pose, P.kf_vel):
+        if a.nbytes >= 1 << 16 and int(cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
+            pinned.append(a)
+
+    # ---------------- device-resident arm: `value`
+    g = gl.GpBa(P, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+    info = g.build_structure()
+    stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local_rank))
+    total_ms, iters_done, trials_done, last = 0.0, 0, 0, None
+    sampler = ClockSampler(local_rank)
+    for s in range(args.warmup + args.steps):
+        g.reset_state()
+        timed = s >= args.warmup
+        if s == args.warmup:
+            g.stage_stats(reset=True)
+            g.set_profiling(True)
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        tr = g.optimize(LM_ITERS, params)
+        e1.record(stream)
+        barrier()
+        if timed:
+            total_ms += e0.elapsed_time(e1)
+            iters_done += tr.n_iters; trials_done += tr.total_trials; last = tr.summary()
+    clocks = sampler.stop()
+    stages = g.stage_stats(reset=True)
+    g.set_profiling(False)
+    t_max = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    total_ms = float(t_max.item())
+    n_obs_total = P.n_obs
+    value = n_obs_total * iters_done / (total_ms * 1e-3)
+    launches = int(sum(v["launches"] for v in stages.values()))
+
+    # ---------------- roofline of the dominant HBM-bound kernel (CUDA-event pairs recorded live in the timed region)
+    peak, peak_src = peaks()
+    ab = algorithmic_bytes(info, info.n_free_kf)
+    per_launch_count = {"residuals": None}
+    cand = {}
+    for k, nbytes in ab.items():
+        st = stages[k]
+        # number of kernel launches of the stage's main kernel in the timed region
+        n_main = {"residuals": trials_done + iters_done + args.steps, "lin_landmarks": iters_done, "lin_poses": iters_done,
+                  "schur_prepare": trials_done, "schur_gather": trials_done, "backsub_update": trials_done}[k]
+        if n_main > 0 and st["ms"] > 0:
+            cand[k] = dict(ms_per_launch=st["ms"] / n_main, bytes_per_launch=nbytes, gbs=nbytes / (st["ms"] / n_main * 1e-3) / 1e9)
+    dom = max(cand, key=lambda k: stages[k]["ms"]) if cand else None
+    roof = None
+    if dom:
+        roof = {"bound": "hbm", "kernel": dom, "achieved": cand[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": cand[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": cand[dom]["bytes_per_launch"], "ms_per_launch": cand[dom]["ms_per_launch"]}
+    g.close()
+
+    # ---------------- end-to-end arm through the C ABI from host buffers: `e2e`
+    e2e_ms, e2e_iters = 0.0, 0
+    kp = np.zeros((P.n_kf, 7)); kv = np.zeros((P.n_kf, 6)); pt = np.zeros((P.n_pt, 3))
+    for a in (kp, kv, pt):
+        if a.nbytes >= 1 << 16 and int(cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
+            pinned.append(a)
+    n_e2e = max(1, min(args.steps, 3))
+    for s in range(1 + n_e2e):
+        barrier()
+        t = time.perf_counter()
+        h = gl.GpBa(P, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+        tr = h.optimize(LM_ITERS, params)
+        h.download_into(kp, kv, pt)
+        h.close()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        if s >= 1:
+            e2e_ms += dt * 1e3; e2e_iters += tr.n_iters
+    t_max = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_max.item())
+    e2e_value = n_obs_total * e2e_iters / (e2e_ms * 1e-3)
+    for a in pinned:
+        cudart.cudaHostUnregister(a.ctypes.data)
+
+    # ---------------- CPU baseline (rank 0, N=1 only): oracle on a bounded sample, 1 core = the reference's configuration
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py
+        sample = CPU_SAMPLE[args.workload]
+        Ps = load_problem(args.workload, **sample)
+        o = oracle_py.Oracle(Ps, threads=1)
+        t = time.perf_counter()
+        trc = o.optimize(2)
+        dt = time.perf_counter() - t
+        cpu = {"value": Ps.n_obs * trc.n_iters / dt, "unit": "obs/s", "cores": 1, "kind": "port",
+               "sample": f"{args.workload} family, {sample['n_kf']} keyframes, {Ps.n_pt} points, {Ps.n_obs} observations, "
+                         f"{trc.n_iters} LM iterations, {dt:.1f} s on 1 core (G2O_OPENMP is off in the reference, Thirdparty/g2o/config.h:4)"}
+
+    if rank == 0:
+        out = {
+            "metric": "gpba_observations_per_sec", "value": value, "unit": "obs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "lm_iters_per_sec": iters_done / (total_ms * 1e-3), "ms_per_lm_iter": total_ms / max(iters_done, 1),
+            "config": {"workload": WORKLOADS[args.workload], "name": args.workload, "n_obs": int(P.n_obs), "n_pt": int(P.n_pt),
+                       "n_kf": int(P.n_kf), "lm_iters_executed_per_step": iters_done // max(args.steps, 1),
+                       "lm_trials_per_step": trials_done // max(args.steps, 1),
+                       "linear_solver": "pcg" if args.pcg else "tile_cholesky_dmma", "parallelism": f"landmark-sharded x{world}",
+                       "l2": "inputs larger than L2 (observation arrays + Hpl blocks >> 126 MB), no flush",
+                       "final_chi2": last["chi2_after"][last["n_iters"] - 1] if last else None},
+            "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": int(P.input_bytes()),
+                    "d2h_bytes_per_step": int(kp.nbytes + kv.nbytes + pt.nbytes), "ms_per_step": e2e_ms / n_e2e},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "stages_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in stages.items()},
+            "stage_gbs": {k: round(v["gbs"], 1) for k, v in cand.items()},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpba", choices=["gpba", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--pcg", action="store_true", help="block-Jacobi PCG instead of the tile Cholesky")
+    ap.add_argument("--pcg-tol", type=float, default=1e-12)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpba(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

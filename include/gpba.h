@@ -225,12 +225,17 @@ int gpba_rejection_rounds(gpba_handle* h, int n_rounds, int iters, const gpba_th
                           const gpba_lm_params* params, uint8_t* flags_out, gpba_lm_trace* traces /* [n_rounds] */);
 
 /* ---- measurement ------------------------------------------------------------------- */
-/* Mean device time (ms, CUDA events on the library stream) and launch count per stage since the
- * last reset; stage names follow G2OBatchStatistics: 0 records, 1 residuals, 2 quadratic form,
- * 3 schur, 4 linear solver, 5 back-substitution+update, 6 collective. */
-#define GPBA_N_STAGES 7
+/* Total device time (ms, CUDA event pairs recorded on the library stream, read back only here) and
+ * launch count per stage since the last reset: 0 records (K0), 1 residuals (K1), 2 linearize landmarks
+ * (K2a), 3 linearize poses + priors (K2b/K2c/K3), 4 schur prepare (K4 init + K4a), 5 schur gather (K4b),
+ * 6 reduced-system factorization / PCG (K5), 7 triangular solves, 8 back-substitution + update (K6),
+ * 9 collective.  Grouping follows G2OBatchStatistics (g2o/core/batch_stats.h:39-78):
+ * timeResiduals = 0+1, timeQuadraticForm = 2+3, timeSchurComplement = 4+5, timeLinearSolver = 6+7, timeUpdate = 8. */
+#define GPBA_N_STAGES 10
 int gpba_stage_stats(gpba_handle* h, double ms_total[GPBA_N_STAGES], int64_t launches[GPBA_N_STAGES], int reset);
 int gpba_set_profiling(gpba_handle* h, int enabled);
+/* cudaStream_t every kernel of this handle is launched on (for CUDA-event timing by the caller). */
+void* gpba_get_stream(gpba_handle* h);
 /* Re-upload estimates only (same structure): lets a benchmark repeat optimize() from the same start. */
 int gpba_reset_state(gpba_handle* h, const double* kf_pose, const double* kf_vel, const double* pt_xyz);
 

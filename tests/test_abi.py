@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def header_symbols():
     src = open(os.path.join(ROOT, "include", "gpba.h")).read()
-    return sorted(set(re.findall(r"^\s*(?:int|void|const char\*)\s+(gpba_\w+)\s*\(", src, re.M)))
+    return sorted(set(re.findall(r"^\s*(?:int|void\*?|const char\*)\s+(gpba_\w+)\s*\(", src, re.M)))
 
 
 def test_library_exports_every_declared_symbol():

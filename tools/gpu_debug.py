@@ -52,7 +52,7 @@ def run(name, solver=SOLVER_DENSE_CHOL, iters=10, **kw):
     print("  stored chi2", rel(g2.edge_chi2(), o2.edge_chi2()))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "rounds" not in sys.argv:
     cases = [("tiny", SOLVER_DENSE_CHOL), ("tiny_global", SOLVER_DENSE_CHOL), ("c1", SOLVER_DENSE_CHOL), ("loop", SOLVER_DENSE_CHOL),
              ("tiny", SOLVER_PCG), ("loop", SOLVER_PCG)]
     for name, solver in cases:
@@ -60,3 +60,29 @@ if __name__ == "__main__":
             run(name, solver)
         except Exception:
             traceback.print_exc()
+
+
+def rounds_debug():
+    from pygpba.problem import Thresholds
+    P = synth.make_problem("c1", n_pt=600, outliers=0.3, seed=33)
+    g = G.GpBa(P); o = O.Oracle(P)
+    th = Thresholds.local_gpba()
+    for it in range(4):
+        tg, tc = g.optimize(10).summary(), o.optimize(10).summary()
+        print(f"--- round {it}: iters {tg['n_iters']}/{tc['n_iters']} trials {tg['trials']} / {tc['trials']}")
+        print("   chi2_before rel", np.abs(np.array(tg['chi2_before']) - np.array(tc['chi2_before'])) / np.array(tc['chi2_before']))
+        print("   chi2_after rel", np.abs(np.array(tg['chi2_after']) - np.array(tc['chi2_after'])) / np.array(tc['chi2_after']))
+        sg, sc = g.state(), o.state()
+        print("   pose t", rel(sg[0][:, 4:], sc[0][:, 4:]), " pts", rel(sg[2], sc[2]))
+        g.compute_errors_inactive(); o.compute_errors_inactive()
+        cg, co = g.edge_chi2(), o.edge_chi2()
+        print("   stored chi2", rel(cg, co), "worst idx", int(np.argmax(np.abs(cg - co))))
+        fg, fo = g.outlier_flags(th), o.outlier_flags(th)
+        print("   flags differ", int((fg != fo).sum()), "of", len(fo), "flagged", int(fo.sum()))
+        g.set_levels(fg); o.set_levels(fo)
+        if it == 2:
+            g.set_robust_kernel(0); o.set_robust_kernel(0)
+
+
+if __name__ == "__main__" and "rounds" in sys.argv:
+    rounds_debug()
