@@ -143,7 +143,16 @@ struct Solver {
   int64_t chol_doubles = 0;
   DBuf<int64_t> d_tile_off;
   DBuf<int> d_col_begin, d_col_rows, d_chol_perm;
-  DBuf<double> d_tiles, d_chol_work;
+  DBuf<double> d_tiles, d_chol_work, d_chol_dinv, d_chol_x;
+  DBuf<int> d_row_begin, d_row_cols;
+  std::vector<int> chol_row_begin;
+  cudaGraphExec_t chol_graph = nullptr;       // load + (panel, update) x NT, captured once per structure
+  cudaGraphExec_t chol_back_graph = nullptr;  // backward substitution, one launch per tile row
+  int chol_graph_launches = 0, chol_back_launches = 0;
+  CholView chol_view() {
+    return CholView{NT, n_pose * 12, d_tile_off.p, d_col_begin.p, d_col_rows.p, d_row_begin.p, d_row_cols.p, d_tiles.p,
+                    d_chol_perm.p, d_chol_dinv.p, d_chol_work.p, d_chol_x.p};
+  }
   std::vector<int> chol_col_begin;
   // ------------------------------------------------------------------ PCG
   PcgBuffers pcg;
@@ -172,6 +181,8 @@ struct Solver {
 
   ~Solver() {
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    if (chol_graph) cudaGraphExecDestroy(chol_graph);
+    if (chol_back_graph) cudaGraphExecDestroy(chol_back_graph);
     if (h_scal) cudaFreeHost(h_scal);
     if (h_fail) cudaFreeHost(h_fail);
     if (ev0) cudaEventDestroy(ev0);
@@ -210,6 +221,7 @@ struct Solver {
   int init(const gpba_problem* P, int dev);
   int build_structure();
   int build_cholesky_structure();
+  int capture_cholesky_graph();
   void fill_view();
   int compute_records(int buf, bool full);
   int compute_errors(int buf, bool store, double* chi2);
@@ -714,6 +726,68 @@ int Solver::build_cholesky_structure() {
   CKR(d_tile_off.upload(off, stream)); CKR(d_col_begin.upload(chol_col_begin, stream)); CKR(d_col_rows.upload(col_rows, stream));
   CKR(d_chol_perm.upload(perm, stream));
   CKR(d_tiles.alloc((size_t)chol_doubles)); CKR(d_chol_work.alloc((size_t)NT * GPBA_NB));
+  CKR(d_chol_dinv.alloc((size_t)NT * GPBA_NB * GPBA_NB)); CKR(d_chol_x.alloc((size_t)NT * GPBA_NB));
+  // row-wise view of the factor pattern for the backward substitution
+  chol_row_begin.assign(NT + 1, 0);
+  for (int r : col_rows) chol_row_begin[r + 1]++;
+  for (int i = 0; i < NT; ++i) chol_row_begin[i + 1] += chol_row_begin[i];
+  std::vector<int> row_cols(col_rows.size()), cur_r(chol_row_begin.begin(), chol_row_begin.end() - 1);
+  for (int k = 0; k < NT; ++k)
+    for (int e = chol_col_begin[k]; e < chol_col_begin[k + 1]; ++e) row_cols[cur_r[col_rows[e]]++] = k;
+  CKR(d_row_begin.upload(chol_row_begin, stream)); CKR(d_row_cols.upload(row_cols, stream));
+  CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
+  if (chol_graph) { cudaGraphExecDestroy(chol_graph); chol_graph = nullptr; }
+  if (chol_back_graph) { cudaGraphExecDestroy(chol_back_graph); chol_back_graph = nullptr; }
+  return GPBA_OK;
+}
+
+// The factorization of one structure is a fixed launch sequence (2 kernels per tile column); replaying it as a
+// CUDA graph removes the per-launch host cost from the critical path of every LM trial.
+int Solver::capture_cholesky_graph() {
+  double* bs = d_hs.p + (size_t)n_hs * 144;
+  const CholView C = chol_view();
+  auto finish = [&](cudaError_t e, cudaGraphExec_t* exec) -> int {
+    cudaGraph_t graph = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(stream, &graph);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      g_err = std::string("cholesky graph capture: ") + cudaGetErrorString(e != cudaSuccess ? e : e2);
+      return GPBA_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { *exec = nullptr; g_err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return GPBA_ERR_CUDA; }
+    return GPBA_OK;
+  };
+  // ---- graph A: load + factorization + forward substitution
+  CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  int launches = 0;
+  cudaError_t e = cudaMemsetAsync(d_tiles.p, 0, sizeof(double) * (size_t)chol_doubles, stream);
+  if (e == cudaSuccess) {
+    const int64_t work = std::max((int64_t)n_hs * 144, (int64_t)NT * GPBA_NB);
+    k_chol_load<<<(int)std::min((work + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(C, n_hs, d_hs_row.p, d_hs_col.p, d_hs.p, bs);
+    ++launches;
+    for (int k = 0; k < NT; ++k) {
+      const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
+      k_chol_panel<<<1 + nr, GPBA_PANEL_THREADS, 0, stream>>>(C, k, d_fail.p);
+      ++launches;
+      if (nr > 0) { k_chol_update<<<nr * (nr + 1) / 2 + 1, 128, 0, stream>>>(C, k); ++launches; }
+    }
+    e = cudaGetLastError();
+  }
+  CKR(finish(e, &chol_graph));
+  chol_graph_launches = launches;
+  // ---- graph B: backward substitution
+  CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  launches = 0;
+  for (int i = NT - 1; i >= 0; --i) {
+    k_chol_back<<<1 + chol_row_begin[i + 1] - chol_row_begin[i], 192, 0, stream>>>(C, i);
+    ++launches;
+  }
+  k_chol_unpermute<<<(n_pose * 12 + 255) / 256, 256, 0, stream>>>(C, d_x.p);
+  ++launches;
+  CKR(finish(cudaGetLastError(), &chol_back_graph));
+  chol_back_launches = launches;
   return GPBA_OK;
 }
 
@@ -828,29 +902,12 @@ int Solver::solve(double lambda, bool* ok) {
   t0();
   launches = 0;
   if (linear_solver == GPBA_SOLVER_DENSE_CHOL) {
-    CholView C{NT, n_pose * 12, d_tile_off.p, d_col_begin.p, d_col_rows.p, d_tiles.p, d_chol_perm.p};
-    k_chol_clear<<<std::min((chol_doubles + 255) / 256, (int64_t)148 * 16), 256, 0, stream>>>(C, chol_doubles);
-    const int npad = NT * GPBA_NB - n_pose * 12;
-    if (npad > 0) k_chol_pad<<<(npad + 63) / 64, 64, 0, stream>>>(C);
-    k_chol_scatter<<<std::min(((int64_t)n_hs * 144 + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(C, n_hs, d_hs_row.p, d_hs_col.p, d_hs.p);
-    launches += 3;
-    for (int k = 0; k < NT; ++k) {
-      k_chol_potrf<<<1, 256, 0, stream>>>(C, k, d_fail.p);
-      const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
-      if (nr > 0) {
-        k_chol_trsm<<<nr, GPBA_NB, 0, stream>>>(C, k);
-        k_chol_update<<<nr * (nr + 1) / 2, 128, 0, stream>>>(C, k);
-        launches += 2;
-      }
-      launches++;
-    }
-    CK(cudaGetLastError());
-    t1(6, launches);
+    if (!chol_graph) CKR(capture_cholesky_graph());
+    CK(cudaGraphLaunch(chol_graph, stream));
+    t1(6, chol_graph_launches);
     t0();
-    launches = 1;
-    k_chol_solve<<<1, 256, 0, stream>>>(C, bs, d_x.p, d_chol_work.p);
-    CK(cudaGetLastError());
-    t1(7, launches);
+    CK(cudaGraphLaunch(chol_back_graph, stream));
+    t1(7, chol_back_launches);
   } else {
     int it = 0;
     CKR(pcg.solve(n_pose, n_hs, d_hs.p, bs, d_x.p, stream, &it, d_fail.p));
