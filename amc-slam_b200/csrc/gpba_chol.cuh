@@ -32,6 +32,20 @@ namespace gpba {
 #define GPBA_LD 52   // shared-memory row stride: DMMA fragment loads are bank-conflict free, rows 16-byte aligned
 #define GPBA_PANEL_THREADS 192
 
+#ifdef GPBA_CHOL_TIMING
+__device__ long long g_chol_clk[64];
+__device__ __forceinline__ long long* chol_clk_smem() { __shared__ long long b[64]; return b; }
+// ticks go to shared memory and are dumped at the end: a global store in front of a barrier stalls ~900 cycles
+#define GPBA_TICK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 1 && k == 100) chol_clk_smem()[slot] = clock64(); } while (0)
+#define GPBA_TICK_DUMP() do { if (threadIdx.x == 0 && blockIdx.x == 1 && k == 100) for (int q_ = 0; q_ < 64; ++q_) g_chol_clk[q_] = chol_clk_smem()[q_]; } while (0)
+#define GPBA_TICKP(slot) do { GPBA_TICK(16 + pb * 4 + (slot) - 5); \
+  if (blockIdx.x == 1 && k == 100 && pb == 5) { if (threadIdx.x == 74) chol_clk_smem()[40 + (slot) - 5] = clock64(); if (threadIdx.x == 160) chol_clk_smem()[44 + (slot) - 5] = clock64(); if (threadIdx.x == 64) chol_clk_smem()[48 + (slot) - 5] = clock64(); } } while (0)
+#else
+#define GPBA_TICK(slot) do { } while (0)
+#define GPBA_TICK_DUMP() do { } while (0)
+#define GPBA_TICKP(slot) do { } while (0)
+#endif
+
 struct CholView {
   int NT;                       // tiles per side
   int n;                        // true dimension (12 * n_pose)
@@ -77,90 +91,141 @@ __global__ void k_chol_load(CholView C, int n_hs, const int* __restrict__ hs_row
   for (int64_t j = t0; j < C.n; j += stride) C.work[C.perm[j / 12] * 12 + j % 12] = rhs[j];
 }
 
-// the two warps that own the 48 rows during a panel step
-GPBA_D void bar64() { asm volatile("barrier.sync 1, 64;" ::: "memory"); }
-
-// global 48x48 row-major tile -> shared [48][GPBA_LD] (16-byte loads), any CTA size
-GPBA_D void tile_to_smem(const double* __restrict__ T, double (*S)[GPBA_LD]) {
-  const double2* T2 = reinterpret_cast<const double2*>(T);
-  for (int j = threadIdx.x; j < GPBA_NB * GPBA_NB / 2; j += blockDim.x) {
-    const double2 v = T2[j];
+// global 48x48 row-major tile(s) -> shared [48][GPBA_LD]: all 16-byte loads are issued before the first store,
+// so a CTA pays one memory round trip for both tiles.  NTHR must divide 1152.
+template <int NTHR, int NTILES>
+GPBA_D void tiles_to_smem(const double* __restrict__ T0, double (*S0)[GPBA_LD], const double* __restrict__ T1,
+                          double (*S1)[GPBA_LD]) {
+  constexpr int PER = GPBA_NB * GPBA_NB / 2 / NTHR;
+  double2 v0[PER], v1[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    v0[q] = reinterpret_cast<const double2*>(T0)[threadIdx.x + q * NTHR];
+    if (NTILES > 1) v1[q] = reinterpret_cast<const double2*>(T1)[threadIdx.x + q * NTHR];
+  }
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int j = threadIdx.x + q * NTHR;
     const int r = j / (GPBA_NB / 2), c = 2 * (j % (GPBA_NB / 2));
-    *reinterpret_cast<double2*>(&S[r][c]) = v;
+    *reinterpret_cast<double2*>(&S0[r][c]) = v0[q];
+    if (NTILES > 1) *reinterpret_cast<double2*>(&S1[r][c]) = v1[q];
   }
 }
 
+// reciprocal for the pivot chain: MUFU seed + two Newton steps (55 cycles dependent vs 85 for the IEEE division,
+// tools/microbench.cu); relative error ~1 ulp, far below what the factorization needs
+GPBA_D double fast_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+}
+
+// inverse of the b-th 8x8 diagonal block of L (read from S), column `lane` per thread, lanes 0..7 of one warp
+GPBA_D void diag_block_inverse(const double (*S)[GPBA_LD], int b, int lane, double (*D8)[8][8]) {
+  if (lane >= 8) return;
+  const int c0 = 8 * b;
+  double x[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) x[q] = (q == lane) ? 1.0 : 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    x[q] *= fast_rcp(S[c0 + q][c0 + q]);
+#pragma unroll
+    for (int q2 = q + 1; q2 < 8; ++q2) x[q2] = fma(-S[c0 + q2][c0 + q], x[q], x[q2]);
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) D8[b][q][lane] = x[q];
+}
+
 // Cholesky of the 48x48 tile in S (lower part; the upper part is never read), GPBA_PANEL_THREADS threads.
-// Six panels of 8 columns: the panel is factorized one row per thread (registers, one 64-thread barrier per
-// pivot), the trailing tile is updated with DMMA by all warps.  On exit S = L, D8[b] = (b-th 8x8 diagonal block
-// of L)^-1, Sinv[j] = 1 / L[j][j].
-GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], double* Sinv, int* fail) {
+// Six panels of 8 columns.  Warps 0-1 own the 48 rows: every one of their threads factorizes the 8x8 diagonal
+// block of the panel redundantly in registers (LDL^T form: the pivot chain is one reciprocal + one FMA per pivot
+// and needs no communication -- a shared-memory + barrier round trip per pivot cost ~380 cycles) and solves its
+// own row of the panel with it.  Meanwhile warp 3 inverts the previous panel's diagonal block for the blocked
+// triangular solves; the other warps stay off the FP64 pipe.  The trailing tile is then updated with DMMA by all
+// warps.  On exit S = L, D8[b] = (b-th 8x8 diagonal block of L)^-1.
+GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], int* fail, int k = -1) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int r = tid;
 #pragma unroll 1
   for (int pb = 0; pb < GPBA_NB / 8; ++pb) {
     const int c0 = 8 * pb;
-    if (tid < 64) {
-      const bool own = r >= c0 && r < GPBA_NB;
-      double p[8];
+    if (warp < 2) {
+      double u[8][8], p[8], is[8];
+      const bool mine = r >= c0 && r < GPBA_NB;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) p[i] = own ? S[r][c0 + i] : 0.0;
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int i = 0; i <= q; ++i) u[q][i] = S[c0 + q][c0 + i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = mine ? S[r][c0 + i] : 0.0;  // rows of the block itself: entries i > r - c0 are unused
+      asm volatile("barrier.sync 1, 64;" ::: "memory");  // the block is in registers: its rows may be overwritten
+      GPBA_TICKP(5);
+      bool bad = false;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int col = c0 + i;
-        if (i > 0) {
-          if (own && r >= col) S[r][col] = p[i];  // publish the updated, still unscaled column
-          bar64();
-        }
-        const double d = S[col][col];
-        const double inv = rsqrt(d);
-        if (r == col) {
-          if (!(d > 0.0)) atomicExch(fail, 1);
-          Sinv[col] = inv;
-        }
-        if (own && r >= col) p[i] = (r == col) ? d * inv : p[i] * inv;
+        const double d = u[i][i];
+        bad = bad || !(d > 0.0);
+        const double rc = fast_rcp(d);
+        is[i] = rsqrt(d);  // off the pivot chain: L[q][i] = u[q][i] / sqrt(d_i)
 #pragma unroll
-        for (int i2 = i + 1; i2 < 8; ++i2)
-          if (own && r >= c0 + i2) p[i2] = fma(-p[i], S[c0 + i2][col] * inv, p[i2]);
+        for (int q = i + 1; q < 8; ++q) {
+          const double t = u[q][i] * rc;
+#pragma unroll
+          for (int i2 = i + 1; i2 <= q; ++i2) u[q][i2] = fma(-t, u[i2][i], u[q][i2]);
+        }
+        const double t = p[i] * rc;
+#pragma unroll
+        for (int i2 = i + 1; i2 < 8; ++i2) p[i2] = fma(-t, u[i2][i], p[i2]);
       }
-      bar64();  // every thread has read the unscaled diagonal before the scaled panel replaces it
-      if (own) {
+      GPBA_TICKP(6);
+      if (bad && tid == 0) atomicExch(fail, 1);
+      if (mine) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (r >= c0 + i) S[r][c0 + i] = p[i];
+          if (r >= c0 + i) S[r][c0 + i] = p[i] * is[i];
       }
+    } else if (warp == 3 && pb > 0) {
+      diag_block_inverse(S, pb - 1, lane, D8);
     }
     __syncthreads();
-    // trailing update S[mt][nt] -= P[mt] P[nt]^T over the tiles pb < nt <= mt < 6
+    GPBA_TICKP(7);
+    // trailing update S[mt][nt] -= P[mt] P[nt]^T over the tiles pb < nt <= mt < 6: up to three tiles per warp,
+    // interleaved so that the DMMA latencies overlap
     const int m = GPBA_NB / 8 - 1 - pb, cnt = m * (m + 1) / 2;
-    for (int t = warp; t < cnt; t += GPBA_PANEL_THREADS / 32) {
-      int a = 0;
-      while ((a + 1) * (a + 2) / 2 <= t) ++a;
-      const int mt = pb + 1 + a, nt = pb + 1 + (t - a * (a + 1) / 2);
-      double* cp = &S[8 * mt + gid][8 * nt + 2 * tig];
-      double2 c = *reinterpret_cast<double2*>(cp);
+    double2 c[3];
+    double* cp[3];
+    double af[3][2], bf[3][2];
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk)
-        dmma884(c.x, c.y, -S[8 * mt + gid][c0 + 4 * kk + tig], S[8 * nt + gid][c0 + 4 * kk + tig]);
-      *reinterpret_cast<double2*>(cp) = c;
-    }
-    // inverse of the 8x8 diagonal block (column t per thread) for the blocked triangular solves
-    if (tid >= GPBA_PANEL_THREADS - 8) {
-      const int t = tid - (GPBA_PANEL_THREADS - 8);
-      double x[8];
+    for (int s = 0; s < 3; ++s) {
+      const int t = warp + s * (GPBA_PANEL_THREADS / 32);
+      cp[s] = nullptr;
+      if (t < cnt) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= t) ++a;
+        const int mt = pb + 1 + a, nt = pb + 1 + (t - a * (a + 1) / 2);
+        cp[s] = &S[8 * mt + gid][8 * nt + 2 * tig];
+        c[s] = *reinterpret_cast<double2*>(cp[s]);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) x[q] = (q == t) ? 1.0 : 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        x[q] *= Sinv[c0 + q];
-#pragma unroll
-        for (int q2 = q + 1; q2 < 8; ++q2) x[q2] = fma(-S[c0 + q2][c0 + q], x[q], x[q2]);
+        for (int kk = 0; kk < 2; ++kk) { af[s][kk] = -S[8 * mt + gid][c0 + 4 * kk + tig]; bf[s][kk] = S[8 * nt + gid][c0 + 4 * kk + tig]; }
       }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) D8[pb][q][t] = x[q];
     }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+        if (cp[s]) dmma884(c[s].x, c[s].y, af[s][kk], bf[s][kk]);
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+      if (cp[s]) *reinterpret_cast<double2*>(cp[s]) = c[s];
     __syncthreads();
+    GPBA_TICKP(8);
   }
+  if (warp == 3) diag_block_inverse(S, GPBA_NB / 8 - 1, lane, D8);
+  __syncthreads();
 }
 
 // X = T L^-T in place (T: 48 x 48 in shared memory), blocked by 8: warp w owns the 8 rows of row-tile w, so the
@@ -196,21 +261,26 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, i
   __shared__ __align__(16) double S[GPBA_NB][GPBA_LD];
   __shared__ __align__(16) double T[GPBA_NB][GPBA_LD];
   __shared__ double D8[GPBA_NB / 8][8][8];
-  __shared__ double Sinv[GPBA_NB], Sy[GPBA_NB];
+  __shared__ double Sy[GPBA_NB];
   const int tid = threadIdx.x;
-  tile_to_smem(C.tiles + C.tile_off[(size_t)k * C.NT + k], S);
+  GPBA_TICK(0);
+  const double* Tkk = C.tiles + C.tile_off[(size_t)k * C.NT + k];
   double* A = nullptr;
   if (blockIdx.x == 0) {
+    tiles_to_smem<GPBA_PANEL_THREADS, 1>(Tkk, S, nullptr, nullptr);
     for (int j = tid; j < GPBA_NB * GPBA_NB; j += blockDim.x) T[j / GPBA_NB][j % GPBA_NB] = (j / GPBA_NB == j % GPBA_NB) ? 1.0 : 0.0;
     if (tid < GPBA_NB) Sy[tid] = C.work[k * GPBA_NB + tid];
   } else {
     A = C.tiles + C.tile_off[(size_t)C.col_rows[C.col_begin[k] + blockIdx.x - 1] * C.NT + k];
-    tile_to_smem(A, T);
+    tiles_to_smem<GPBA_PANEL_THREADS, 2>(Tkk, S, A, T);
   }
   __syncthreads();
-  potrf48(S, D8, Sinv, fail);
+  GPBA_TICK(1);
+  potrf48(S, D8, fail, k);
+  GPBA_TICK(2);
   trsm48(T, S, D8);
   __syncthreads();
+  GPBA_TICK(3);
   if (blockIdx.x == 0) {
     // T = L_kk^-T.  dinv[k] = L_kk^-1 = T^T (row-major), y_k = L_kk^-1 b_k
     double* D = C.dinv + (size_t)k * GPBA_NB * GPBA_NB;
@@ -226,33 +296,18 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, i
     for (int j = tid; j < GPBA_NB * GPBA_NB / 2; j += blockDim.x)
       A2[j] = *reinterpret_cast<double2*>(&T[j / (GPBA_NB / 2)][2 * (j % (GPBA_NB / 2))]);
   }
+  GPBA_TICK(4);
+  GPBA_TICK_DUMP();
 }
 
 // Trailing update of step k: A_ab -= L_ak L_bk^T for all pairs a >= b of column k's non-zero rows.
 // One CTA (4 warps) per pair; both L tiles staged in shared memory, the C tile prefetched into registers while
 // they arrive; each warp owns a 24 x 24 corner = 3 x 3 DMMA tiles (9 independent accumulator chains).
-// The extra last CTA applies column k to the right-hand side: b_i -= L_ik y_k.
+// The CTA of a diagonal pair (a == b) also applies its tile to the right-hand side: b_i -= L_ik y_k.
 __global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
   __shared__ __align__(16) double La[GPBA_NB][GPBA_LD], Lb[GPBA_NB][GPBA_LD];
+  __shared__ double yk[GPBA_NB];
   const int cb = C.col_begin[k];
-  const int nr = C.col_begin[k + 1] - cb;
-  if ((int)blockIdx.x == nr * (nr + 1) / 2) {
-    double* yk = &La[0][0];
-    if (threadIdx.x < GPBA_NB) yk[threadIdx.x] = C.work[k * GPBA_NB + threadIdx.x];
-    __syncthreads();
-    for (int q = threadIdx.x; q < nr * GPBA_NB; q += blockDim.x) {
-      const int i = C.col_rows[cb + q / GPBA_NB], r = q % GPBA_NB;
-      const double2* Lik = reinterpret_cast<const double2*>(C.tiles + C.tile_off[(size_t)i * C.NT + k] + r * GPBA_NB);
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll 8
-      for (int c = 0; c < GPBA_NB / 2; ++c) {
-        const double2 l = Lik[c];
-        s0 = fma(l.x, yk[2 * c], s0); s1 = fma(l.y, yk[2 * c + 1], s1);
-      }
-      C.work[i * GPBA_NB + r] -= s0 + s1;
-    }
-    return;
-  }
   // decode the triangular pair index: blockIdx.x = a*(a+1)/2 + b, a >= b
   int a = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
   while ((a + 1) * (a + 2) / 2 <= (int)blockIdx.x) ++a;
@@ -265,14 +320,14 @@ __global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int m0 = 3 * (warp >> 1), n0 = 3 * (warp & 1);
-  tile_to_smem(Ta, La);
-  tile_to_smem(Tb, Lb);
   double2 cin[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j)
       cin[i][j] = *reinterpret_cast<const double2*>(Tc + (8 * (m0 + i) + gid) * GPBA_NB + 8 * (n0 + j) + 2 * tig);
+  if (a == b && threadIdx.x < GPBA_NB) yk[threadIdx.x] = C.work[k * GPBA_NB + threadIdx.x];
+  tiles_to_smem<128, 2>(Ta, La, Tb, Lb);
   __syncthreads();
   double2 acc[3][3];
 #pragma unroll
@@ -297,6 +352,13 @@ __global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
       o.x -= acc[i][j].x; o.y -= acc[i][j].y;
       *reinterpret_cast<double2*>(Tc + (8 * (m0 + i) + gid) * GPBA_NB + 8 * (n0 + j) + 2 * tig) = o;
     }
+  if (a == b && threadIdx.x < GPBA_NB) {  // forward substitution: b_i -= L_ik y_k with the tile already staged
+    const int r = threadIdx.x;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < GPBA_NB; c += 2) { s0 = fma(La[r][c], yk[c], s0); s1 = fma(La[r][c + 1], yk[c + 1], s1); }
+    C.work[ra * GPBA_NB + r] -= s0 + s1;
+  }
 }
 
 // Backward substitution, tile row i (launched for i = NT-1 .. 0): every CTA computes x_i = L_ii^-T y_i
@@ -306,15 +368,20 @@ __global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
 __global__ void __launch_bounds__(192) k_chol_back(CholView C, int i) {
   __shared__ double yi[GPBA_NB], xi[GPBA_NB], part[4][GPBA_NB];
   const int tid = threadIdx.x, c = tid % GPBA_NB, h = tid / GPBA_NB;  // 4 row-quarters x 48 columns
+  // all global operands are requested up front (they do not depend on x_i): one memory round trip per launch
+  const double* D = C.dinv + (size_t)i * GPBA_NB * GPBA_NB;  // (L^-T)[c][r] = Linv[r][c], zero for r < c
+  const int k = blockIdx.x > 0 ? C.row_cols[C.row_begin[i] + blockIdx.x - 1] : 0;
+  const double* L = blockIdx.x > 0 ? C.tiles + C.tile_off[(size_t)i * C.NT + k] : D;
+  double dv[12], lv[12];
+#pragma unroll
+  for (int r = 0; r < 12; ++r) { dv[r] = D[(12 * h + r) * GPBA_NB + c]; lv[r] = L[(12 * h + r) * GPBA_NB + c]; }
+  const double yk_old = (blockIdx.x > 0 && tid < GPBA_NB) ? C.work[k * GPBA_NB + tid] : 0.0;
   if (tid < GPBA_NB) yi[tid] = C.work[i * GPBA_NB + tid];
   __syncthreads();
-  {
-    const double* D = C.dinv + (size_t)i * GPBA_NB * GPBA_NB;  // (L^-T)[c][r] = Linv[r][c], zero for r < c
-    double s = 0.0;
+  double s = 0.0;
 #pragma unroll
-    for (int r = 12 * h; r < 12 * h + 12; ++r) s = fma(D[r * GPBA_NB + c], yi[r], s);
-    part[h][c] = s;
-  }
+  for (int r = 0; r < 12; ++r) s = fma(dv[r], yi[12 * h + r], s);
+  part[h][c] = s;
   __syncthreads();
   if (tid < GPBA_NB) {
     const double x = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
@@ -323,14 +390,12 @@ __global__ void __launch_bounds__(192) k_chol_back(CholView C, int i) {
   }
   if (blockIdx.x == 0) return;
   __syncthreads();
-  const int k = C.row_cols[C.row_begin[i] + blockIdx.x - 1];
-  const double* L = C.tiles + C.tile_off[(size_t)i * C.NT + k];
-  double s = 0.0;
+  s = 0.0;
 #pragma unroll
-  for (int r = 12 * h; r < 12 * h + 12; ++r) s = fma(L[r * GPBA_NB + c], xi[r], s);
+  for (int r = 0; r < 12; ++r) s = fma(lv[r], xi[12 * h + r], s);
   part[h][c] = s;
   __syncthreads();
-  if (tid < GPBA_NB) C.work[k * GPBA_NB + tid] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+  if (tid < GPBA_NB) C.work[k * GPBA_NB + tid] = yk_old - ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]));
 }
 
 __global__ void k_chol_unpermute(CholView C, double* __restrict__ xout) {

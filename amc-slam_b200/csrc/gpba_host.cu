@@ -771,7 +771,7 @@ int Solver::capture_cholesky_graph() {
       const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
       k_chol_panel<<<1 + nr, GPBA_PANEL_THREADS, 0, stream>>>(C, k, d_fail.p);
       ++launches;
-      if (nr > 0) { k_chol_update<<<nr * (nr + 1) / 2 + 1, 128, 0, stream>>>(C, k); ++launches; }
+      if (nr > 0) { k_chol_update<<<nr * (nr + 1) / 2, 128, 0, stream>>>(C, k); ++launches; }
     }
     e = cudaGetLastError();
   }
@@ -1428,3 +1428,9 @@ int gpba_reset_state(gpba_handle* h, const double* kf_pose, const double* kf_vel
 }
 
 }  // extern "C"
+
+#ifdef GPBA_CHOL_TIMING
+extern "C" int gpba_debug_chol_clocks(long long* out) {
+  return cudaMemcpyFromSymbol(out, gpba::g_chol_clk, sizeof(long long) * 64) == cudaSuccess ? 0 : -2;
+}
+#endif
