@@ -15,7 +15,8 @@ struct CamConst {
 
 // Record table (output of K0), one row per (KF_prev, KF_cur, cam, t) record:
 //   [0..8]  R_cw   [9..11] t_cw      so that X_c = R_cw X_w + t_cw with T_cw = (T_wb(t) T_bc)^-1
-//   [12..155] M (6 x 24, row-major): [M_T1 | M_V1 | M_T2 | M_V2]  
+//   [12..155] M (6 x 24, row-major): [M_T1 | M_V1 | M_T2 | M_V2]  (SURVEY Appendix A.3); [0 | 0 | I | 0] for a
+//             synchronous record
 #define GPBA_REC_STRIDE 156
 #define GPBA_REC_M 12
 #define GPBA_REC_LITE_STRIDE 12
@@ -40,14 +41,11 @@ struct DevView {
   const double* o_u; const double* o_v; const double* o_ur; const double* o_w;
   const int* o_rec; const int* o_lm;          // o_lm: sorted landmark index
   const uint8_t* o_flags;
-  const uint16_t* o_slot1; const uint16_t* o_slot2;  // Hpl slot (relative to the landmark) of kf1 / kf2, GPBA_NO_SLOT if fixed/absent
   const int64_t* o_orig;                      // original observation index
   // ---- landmarks (sorted order)
   int n_lm;
   const int* lm_pt;                           // sorted landmark -> point index
   const int64_t* lm_obs_begin;                // [n_lm+1] into sorted obs
-  const int64_t* lm_hpl_begin;                // [n_lm+1] into Hpl blocks
-  const int* hpl_pose;                        // [n_hpl] hessian pose index
   // ---- record-major permutation (K2b)
   const int64_t* rperm;                       // [n_aobs] sorted-obs indices grouped by record
   int n_rseg;

@@ -8,6 +8,7 @@
 #include "../../include/gpba.h"
 #include "gpba_chol.cuh"
 #include "gpba_pcg.cuh"
+#include "gpba_structure.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -99,7 +100,7 @@ struct Solver {
   std::vector<double> h_pose, h_vel, h_pt, h_time;
   std::vector<uint8_t> kf_fixed, obs_flags;
   std::vector<int> rec_kf1, rec_kf2, rec_cam, obs_rec, obs_pt, prior_kf1, prior_kf2, velp_kf;
-  std::vector<double> rec_t, obs_u, obs_v, obs_ur, obs_w;
+  std::vector<double> rec_t;   // per-observation measurements live on the device only (d_all_*)
   double lambda_init = 0;
   int linear_solver = 0;
   // ------------------------------------------------------------------ device: static
@@ -108,7 +109,7 @@ struct Solver {
   DBuf<int> d_rec_kf1, d_rec_kf2, d_rec_cam, d_prior_kf1, d_prior_kf2, d_velp_kf;
   DBuf<double> d_pt_full;                       // [n_pt*3] always-current copy in original order
   DBuf<double> d_chi2;                          // [n_obs] stored edge chi2 (original order)
-  DBuf<double> d_all_ur; DBuf<int> d_all_rec, d_all_pt; DBuf<uint8_t> d_all_flags;  // original-order obs (K8)
+  DBuf<double> d_all_u, d_all_v, d_all_w, d_all_ur; DBuf<int> d_all_rec, d_all_pt; DBuf<uint8_t> d_all_flags;  // original-order obs
   // ------------------------------------------------------------------ device: state (double buffered)
   DBuf<double> d_pose[2], d_vel[2], d_ptS[2];   // d_ptS: landmarks in sorted order
   int cur = 0;
@@ -118,21 +119,23 @@ struct Solver {
   bool structure_ok = false, system_ok = false;
   gpba_structure_info info{};
   std::vector<int> kf_h, lm_pt, pt_lm, lm_rank;  // lm_rank[sorted lm] = landmark index in g2o order (ascending point id)
-  std::vector<int64_t> lm_obs_begin, lm_hpl_begin, o_orig;
-  std::vector<int> hpl_pose, hpp_row, hpp_col, hs_row, hs_col;
+  std::vector<int64_t> lm_obs_begin, o_orig;
+  std::vector<int> hpp_row, hpp_col, hs_row, hs_col;
   int64_t n_aobs = 0;
-  int n_lm = 0, n_pose = 0, n_hpp = 0, n_hs = 0, n_items = 0, n_rseg = 0;
+  int n_lm = 0, n_pose = 0, n_hpp = 0, n_hs = 0, n_items = 0, n_rseg = 0, n_rp = 0;
   int64_t n_hpl = 0, n_pairs = 0;
   // ------------------------------------------------------------------ structure (device)
-  DBuf<int> d_kf_h, d_o_rec, d_o_lm, d_lm_pt, d_hpl_pose, d_hpl_lm, d_rseg_rec;
+  DBuf<int> d_kf_h, d_o_rec, d_o_lm, d_lm_pt, d_rseg_rec, d_item_rp, d_con_begin;
   DBuf<double> d_o_u, d_o_v, d_o_ur, d_o_w;
-  DBuf<uint8_t> d_o_flags;
-  DBuf<uint16_t> d_o_slot1, d_o_slot2;
-  DBuf<int64_t> d_o_orig, d_lm_obs_begin, d_lm_hpl_begin, d_rperm, d_rseg_begin, d_item_begin;
+  DBuf<uint8_t> d_o_flags, d_item_flags;
+  DBuf<int64_t> d_o_orig, d_lm_obs_begin, d_rperm, d_rseg_begin, d_item_begin, d_item_end;
+  DBuf<unsigned long long> d_pairs;     // observation pairs grouped by record pair (sorted order)
+  DBuf<HsContrib> d_con;
+  CubTemp cub_tmp;
   DBuf<int> d_rec_hpp11, d_rec_hpp12, d_rec_hpp22, d_prior_hpp11, d_prior_hpp12, d_prior_hpp22, d_pose_hpp_diag;
-  DBuf<int> d_hs_from_hpp, d_hs_diag_pose, d_hs_row, d_hs_col, d_item_blk, d_pair_i, d_pair_j;
+  DBuf<int> d_hs_from_hpp, d_hs_diag_pose, d_hs_row, d_hs_col;
   // ------------------------------------------------------------------ Hessian storage (device)
-  DBuf<double> d_rec, d_rec_lite, d_recS, d_hll, d_bl, d_hpl, d_U, d_ptL, d_hpp, d_bp, d_hs, d_bs, d_x, d_xl;
+  DBuf<double> d_rec, d_rec_lite, d_recS, d_hll, d_bl, d_W, d_U, d_C, d_Y, d_ptL, d_hpp, d_bp, d_hs, d_bs, d_x, d_xl;
   DBuf<double> d_partial, d_prior_rho, d_pose_scale, d_scal;
   DBuf<int> d_fail;
   double* h_scal = nullptr;   // pinned: [0] chi2 [1] scale [2..] spare
@@ -260,14 +263,9 @@ int Solver::init(const gpba_problem* P, int dev) {
   h_pt.assign(P->pt_xyz, P->pt_xyz + 3 * (size_t)n_pt);
   rec_kf1.assign(P->rec_kf1, P->rec_kf1 + n_rec); rec_kf2.assign(P->rec_kf2, P->rec_kf2 + n_rec);
   rec_cam.assign(P->rec_cam, P->rec_cam + n_rec); rec_t.assign(P->rec_t, P->rec_t + n_rec);
-  obs_u.assign(P->obs_u, P->obs_u + n_obs); obs_v.assign(P->obs_v, P->obs_v + n_obs);
-  obs_w.assign(P->obs_inv_sigma2, P->obs_inv_sigma2 + n_obs);
   stereo = false;
-  if (P->obs_ur) {
-    obs_ur.assign(P->obs_ur, P->obs_ur + n_obs);
-    for (int64_t i = 0; i < n_obs; ++i) if (obs_ur[i] >= 0) { stereo = true; break; }
-  }
-  if (!stereo) obs_ur.clear();
+  if (P->obs_ur)
+    for (int64_t i = 0; i < n_obs; ++i) if (P->obs_ur[i] >= 0) { stereo = true; break; }
   obs_rec.assign(P->obs_rec, P->obs_rec + n_obs); obs_pt.assign(P->obs_pt, P->obs_pt + n_obs);
   if (P->obs_flags) obs_flags.assign(P->obs_flags, P->obs_flags + n_obs); else obs_flags.assign(n_obs, 0);
   prior_kf1.assign(P->prior_kf1, P->prior_kf1 + n_prior); prior_kf2.assign(P->prior_kf2, P->prior_kf2 + n_prior);
@@ -304,10 +302,12 @@ int Solver::init(const gpba_problem* P, int dev) {
   CKR(d_chi2.alloc((size_t)n_obs));
   CK(cudaMemsetAsync(d_chi2.p, 0, sizeof(double) * (size_t)std::max<int64_t>(n_obs, 1), stream));
   CKR(d_all_rec.upload(obs_rec, stream)); CKR(d_all_pt.upload(obs_pt, stream));
-  if (stereo) CKR(d_all_ur.upload(obs_ur, stream));
+  CKR(d_all_u.upload(P->obs_u, (size_t)n_obs, stream)); CKR(d_all_v.upload(P->obs_v, (size_t)n_obs, stream));
+  CKR(d_all_w.upload(P->obs_inv_sigma2, (size_t)n_obs, stream));
+  if (stereo) CKR(d_all_ur.upload(P->obs_ur, (size_t)n_obs, stream));
   CKR(d_scal.alloc(8)); CKR(d_fail.alloc(1));
   CKR(d_rec.alloc((size_t)n_rec * GPBA_REC_STRIDE)); CKR(d_rec_lite.alloc((size_t)n_rec * GPBA_REC_LITE_STRIDE));
-  CKR(d_recS.alloc((size_t)n_rec * 27));
+  CKR(d_recS.alloc((size_t)n_rec * 27)); CKR(d_Y.alloc((size_t)n_rec * 6));
   CKR(d_prior_rho.alloc((size_t)n_prior + n_velp));
   CK(cudaStreamSynchronize(stream));
   return GPBA_OK;
@@ -325,9 +325,8 @@ void Solver::fill_view() {
   V.hub_prior_delta = huber_prior; V.hub_prior_dsqr = f32sq(huber_prior);
   V.n_aobs = n_aobs;
   V.o_u = d_o_u.p; V.o_v = d_o_v.p; V.o_ur = d_o_ur.p; V.o_w = d_o_w.p; V.o_rec = d_o_rec.p; V.o_lm = d_o_lm.p;
-  V.o_flags = d_o_flags.p; V.o_slot1 = d_o_slot1.p; V.o_slot2 = d_o_slot2.p; V.o_orig = d_o_orig.p;
-  V.n_lm = n_lm; V.lm_pt = d_lm_pt.p; V.lm_obs_begin = d_lm_obs_begin.p; V.lm_hpl_begin = d_lm_hpl_begin.p;
-  V.hpl_pose = d_hpl_pose.p;
+  V.o_flags = d_o_flags.p; V.o_orig = d_o_orig.p;
+  V.n_lm = n_lm; V.lm_pt = d_lm_pt.p; V.lm_obs_begin = d_lm_obs_begin.p;
   V.rperm = d_rperm.p; V.n_rseg = n_rseg; V.rseg_rec = d_rseg_rec.p; V.rseg_begin = d_rseg_begin.p;
   V.n_pose = n_pose; V.n_hpp = n_hpp; V.n_hs = n_hs;
   V.rec_hpp11 = d_rec_hpp11.p; V.rec_hpp12 = d_rec_hpp12.p; V.rec_hpp22 = d_rec_hpp22.p;
@@ -350,22 +349,21 @@ __global__ void k_scatter_pts(int n_lm, const int* __restrict__ lm_pt, const dou
 
 // ---------------------------------------------------------------------------------------------------
 // P0: SparseOptimizer::initializeOptimization + buildIndexMapping + BlockSolver::buildStructure
-// (sparse_optimizer.cpp:199-267,166-190; block_solver.hpp:142-295), integer and bit-exact.
+// (sparse_optimizer.cpp:199-267,166-190; block_solver.hpp:142-295), integer and bit-exact.  The host does the O(n_obs)
+// bucket passes and the (small) pose-level patterns; the O(sum d^2) pairing runs on the device (gpba_structure.cuh).
 int Solver::build_structure() {
   CK(cudaSetDevice(device));
   if (structure_ok && n_lm > 0) CKR(scatter_points(cur));  // keep d_pt_full current before re-sorting
-  // --- active set
-  std::vector<char> kf_act(n_kf, 0), pt_act(n_pt, 0);
-  std::vector<int64_t> act;
-  act.reserve(n_obs);
+  // --- active set (edge active iff level 0; vertex active iff it has an active edge)
+  std::vector<char> kf_act(n_kf, 0), pt_act(n_pt, 0), rec_used(n_rec, 0);
+  bool any_level1 = false;
   for (int64_t i = 0; i < n_obs; ++i) {
-    if (obs_flags[i] & GPBA_OBS_LEVEL1) continue;
-    act.push_back(i);
-    const int r = obs_rec[i];
+    if (obs_flags[i] & GPBA_OBS_LEVEL1) { any_level1 = true; continue; }
     pt_act[obs_pt[i]] = 1;
-    if (rec_kf1[r] >= 0) kf_act[rec_kf1[r]] = 1;
-    kf_act[rec_kf2[r]] = 1;
+    rec_used[obs_rec[i]] = 1;
   }
+  for (int r = 0; r < n_rec; ++r)
+    if (rec_used[r]) { if (rec_kf1[r] >= 0) kf_act[rec_kf1[r]] = 1; kf_act[rec_kf2[r]] = 1; }
   for (int i = 0; i < n_prior; ++i)
     if (!(kf_fixed[prior_kf1[i]] && kf_fixed[prior_kf2[i]])) kf_act[prior_kf1[i]] = kf_act[prior_kf2[i]] = 1;
   for (int i = 0; i < n_velp; ++i)
@@ -374,22 +372,29 @@ int Solver::build_structure() {
   n_pose = 0;
   for (int k = 0; k < n_kf; ++k)
     if (kf_act[k] && !kf_fixed[k]) kf_h[k] = n_pose++;
-  // --- landmark order: ascending first keyframe (locality of record / pose accesses), ties by point id
-  std::vector<int> first_kf(n_pt, std::numeric_limits<int>::max());
-  for (int64_t i : act) first_kf[obs_pt[i]] = std::min(first_kf[obs_pt[i]], rec_kf2[obs_rec[i]]);
-  std::vector<int> all_lm_pt;
-  for (int p = 0; p < n_pt; ++p) if (pt_act[p]) all_lm_pt.push_back(p);
-  const int n_lm_all = (int)all_lm_pt.size();
-  std::vector<int> rank_of_pt(n_pt, -1), pt_lm_all(n_pt, -1);
-  for (int l = 0; l < n_lm_all; ++l) rank_of_pt[all_lm_pt[l]] = l;  // g2o landmark index = rank among active points
-  std::stable_sort(all_lm_pt.begin(), all_lm_pt.end(), [&](int a, int b) { return first_kf[a] < first_kf[b]; });
-  for (int l = 0; l < n_lm_all; ++l) pt_lm_all[all_lm_pt[l]] = l;
+  // --- landmark order: ascending first keyframe (locality of record / pose accesses), ties by point id (bucket sort)
+  std::vector<int> first_kf(n_pt, n_kf);
+  for (int64_t i = 0; i < n_obs; ++i) {
+    if (obs_flags[i] & GPBA_OBS_LEVEL1) continue;
+    const int k = rec_kf2[obs_rec[i]];
+    if (k < first_kf[obs_pt[i]]) first_kf[obs_pt[i]] = k;
+  }
+  std::vector<int> bucket(n_kf + 2, 0);
+  int n_lm_all = 0;
+  for (int p = 0; p < n_pt; ++p) if (pt_act[p]) { bucket[first_kf[p] + 1]++; ++n_lm_all; }
+  for (int k = 0; k <= n_kf; ++k) bucket[k + 1] += bucket[k];
+  std::vector<int> all_lm_pt(n_lm_all), rank_of_pt(n_pt, -1), pt_lm_all(n_pt, -1);
+  {
+    int g = 0;
+    for (int p = 0; p < n_pt; ++p)
+      if (pt_act[p]) { rank_of_pt[p] = g++; const int l = bucket[first_kf[p]]++; all_lm_pt[l] = p; pt_lm_all[p] = l; }  // g2o landmark index = rank among active points
+  }
   // --- multi-GPU: this rank owns a contiguous range of the sorted landmarks, balanced by observation count;
   //     patterns (Hpp, Hschur) are built from ALL landmarks so that every rank packs the same block list
   int own_lo = 0, own_hi = n_lm_all;
   if (nranks > 1) {
     std::vector<int64_t> cnt(n_lm_all + 1, 0);
-    for (int64_t i : act) cnt[pt_lm_all[obs_pt[i]] + 1]++;
+    for (int64_t i = 0; i < n_obs; ++i) if (!(obs_flags[i] & GPBA_OBS_LEVEL1)) cnt[pt_lm_all[obs_pt[i]] + 1]++;
     for (int l = 0; l < n_lm_all; ++l) cnt[l + 1] += cnt[l];
     const int64_t total = cnt[n_lm_all];
     auto cut = [&](int r) { return (int)(std::lower_bound(cnt.begin(), cnt.end(), total * r / nranks) - cnt.begin()); };
@@ -397,122 +402,153 @@ int Solver::build_structure() {
     own_hi = rank == nranks - 1 ? n_lm_all : std::min(cut(rank + 1), n_lm_all);
     if (own_hi < own_lo) own_hi = own_lo;
   }
-  std::vector<int64_t> act_all;
-  if (nranks > 1) {
-    act_all = act;
-    std::vector<int64_t> mine;
-    for (int64_t i : act) { const int l = pt_lm_all[obs_pt[i]]; if (l >= own_lo && l < own_hi) mine.push_back(i); }
-    act.swap(mine);
-  }
-  n_aobs = (int64_t)act.size();
   lm_pt.assign(all_lm_pt.begin() + own_lo, all_lm_pt.begin() + own_hi);
   n_lm = (int)lm_pt.size();
   lm_rank.resize(n_lm);
   for (int l = 0; l < n_lm; ++l) lm_rank[l] = rank_of_pt[lm_pt[l]];
-  pt_lm.assign(n_pt, -1);
-  for (int l = 0; l < n_lm; ++l) pt_lm[lm_pt[l]] = l;
-  // --- observations sorted by landmark (stable: insertion order inside a landmark)
+  // --- compute list: active observations of the own landmarks, sorted by landmark (stable: insertion order inside)
   lm_obs_begin.assign(n_lm + 1, 0);
-  for (int64_t i : act) lm_obs_begin[pt_lm[obs_pt[i]] + 1]++;
+  for (int64_t i = 0; i < n_obs; ++i) {
+    if (obs_flags[i] & GPBA_OBS_LEVEL1) continue;
+    const int l = pt_lm_all[obs_pt[i]] - own_lo;
+    if (l >= 0 && l < n_lm) lm_obs_begin[l + 1]++;
+  }
   for (int l = 0; l < n_lm; ++l) lm_obs_begin[l + 1] += lm_obs_begin[l];
-  o_orig.assign(n_aobs, 0);
+  n_aobs = lm_obs_begin[n_lm];
+  o_orig.assign((size_t)n_aobs, 0);
+  std::vector<int64_t> rcount(n_rec + 1, 0);
   {
     std::vector<int64_t> cursor(lm_obs_begin.begin(), lm_obs_begin.end() - 1);
-    for (int64_t i : act) o_orig[cursor[pt_lm[obs_pt[i]]]++] = i;
-  }
-  std::vector<double> su(n_aobs), sv(n_aobs), sw(n_aobs), sur;
-  std::vector<int> srec(n_aobs), slm(n_aobs);
-  std::vector<uint8_t> sfl(n_aobs);
-  if (stereo) sur.resize(n_aobs);
-  for (int64_t j = 0; j < n_aobs; ++j) {
-    const int64_t i = o_orig[j];
-    su[j] = obs_u[i]; sv[j] = obs_v[i]; sw[j] = obs_w[i]; srec[j] = obs_rec[i]; slm[j] = pt_lm[obs_pt[i]]; sfl[j] = obs_flags[i];
-    if (stereo) sur[j] = obs_ur[i];
-  }
-  // --- Hpl blocks: per landmark the sorted free poses touched by ACTIVE edges (block_solver.hpp:206-254)
-  lm_hpl_begin.assign(n_lm + 1, 0);
-  hpl_pose.clear();
-  std::vector<uint16_t> slot1(n_aobs, GPBA_NO_SLOT), slot2(n_aobs, GPBA_NO_SLOT);
-  std::vector<int> hpl_lm;
-  {
-    std::vector<int> tmp;
-    for (int l = 0; l < n_lm; ++l) {
-      tmp.clear();
-      for (int64_t j = lm_obs_begin[l]; j < lm_obs_begin[l + 1]; ++j) {
-        const int r = srec[j];
-        if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0) tmp.push_back(kf_h[rec_kf1[r]]);
-        if (kf_h[rec_kf2[r]] >= 0) tmp.push_back(kf_h[rec_kf2[r]]);
-      }
-      std::sort(tmp.begin(), tmp.end());
-      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-      if (tmp.size() >= GPBA_NO_SLOT) { g_err = "landmark observed by too many keyframes"; return GPBA_ERR_INVALID; }
-      lm_hpl_begin[l] = (int64_t)hpl_pose.size();
-      for (int64_t j = lm_obs_begin[l]; j < lm_obs_begin[l + 1]; ++j) {
-        const int r = srec[j];
-        if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0)
-          slot1[j] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), kf_h[rec_kf1[r]]) - tmp.begin());
-        if (kf_h[rec_kf2[r]] >= 0)
-          slot2[j] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), kf_h[rec_kf2[r]]) - tmp.begin());
-      }
-      hpl_pose.insert(hpl_pose.end(), tmp.begin(), tmp.end());
-      hpl_lm.insert(hpl_lm.end(), tmp.size(), l);
+    for (int64_t i = 0; i < n_obs; ++i) {
+      if (obs_flags[i] & GPBA_OBS_LEVEL1) continue;
+      const int l = pt_lm_all[obs_pt[i]] - own_lo;
+      if (l >= 0 && l < n_lm) { o_orig[cursor[l]++] = i; rcount[obs_rec[i] + 1]++; }
     }
-    lm_hpl_begin[n_lm] = (int64_t)hpl_pose.size();
   }
-  n_hpl = (int64_t)hpl_pose.size();
-  // --- Hpp pattern (upper): diagonals + pose pairs of active edges
-  std::vector<std::vector<int>> pp_rows(n_pose), hs_rows(n_pose);
+  for (int r = 0; r < n_rec; ++r) rcount[r + 1] += rcount[r];
+  // --- device: sorted observation arrays
+  CKR(d_kf_h.upload(kf_h, stream));
+  CKR(d_o_orig.upload(o_orig, stream)); CKR(d_lm_obs_begin.upload(lm_obs_begin, stream)); CKR(d_lm_pt.upload(lm_pt, stream));
+  CKR(d_all_flags.upload(obs_flags, stream));
+  const size_t na = (size_t)std::max<int64_t>(n_aobs, 1);
+  CKR(d_o_u.alloc(na)); CKR(d_o_v.alloc(na)); CKR(d_o_w.alloc(na)); CKR(d_o_rec.alloc(na)); CKR(d_o_lm.alloc(na)); CKR(d_o_flags.alloc(na));
+  if (stereo) CKR(d_o_ur.alloc(na));
+  const int gobs = (int)std::min<int64_t>((n_aobs + 255) / 256 + 1, 148 * 16);
+  if (n_aobs > 0) {
+    k_gather_obs<<<gobs, 256, 0, stream>>>(n_aobs, d_o_orig.p, d_all_u.p, d_all_v.p, stereo ? d_all_ur.p : nullptr, d_all_w.p, d_all_rec.p,
+                                           d_all_flags.p, d_o_u.p, d_o_v.p, stereo ? d_o_ur.p : nullptr, d_o_w.p, d_o_rec.p, d_o_flags.p);
+    k_fill_lm<<<std::min((n_lm + 7) / 8, 148 * 16), 256, 0, stream>>>(n_lm, d_lm_obs_begin.p, d_o_lm.p);
+    CK(cudaGetLastError());
+  }
+  // --- device: observation pairs grouped by record pair
+  std::vector<int64_t> lm_pair_begin(n_lm + 1, 0);
+  for (int l = 0; l < n_lm; ++l) { const int64_t n = lm_obs_begin[l + 1] - lm_obs_begin[l]; lm_pair_begin[l + 1] = lm_pair_begin[l] + n * (n + 1) / 2; }
+  n_pairs = lm_pair_begin[n_lm];
+  std::vector<unsigned long long> rp_key;   // unique record pairs of the compute list, ascending
+  std::vector<int> rp_count;
+  const int key_bits = bits_for((unsigned long long)n_rec * (unsigned long long)n_rec);
+  auto pair_pass = [&](int nl, const DBuf<int64_t>& d_lob, const std::vector<int64_t>& lpb, const int* d_rec_sorted, bool keep_pairs,
+                       std::vector<unsigned long long>& keys_out, std::vector<int>* counts_out) -> int {
+    const int64_t np = lpb[nl];
+    keys_out.clear();
+    if (counts_out) counts_out->clear();
+    if (np == 0) return GPBA_OK;
+    DBuf<int64_t> d_lpb;
+    DBuf<unsigned long long> k0, k1, v0, v1, uq;
+    DBuf<int> cnt, runs, dup;
+    CKR(d_lpb.upload(lpb, stream));
+    CKR(k0.alloc((size_t)np)); CKR(k1.alloc((size_t)np)); CKR(v0.alloc((size_t)np)); CKR(v1.alloc((size_t)np));
+    CKR(uq.alloc((size_t)np)); CKR(cnt.alloc((size_t)np)); CKR(runs.alloc(1)); CKR(dup.alloc(1));
+    CK(cudaMemsetAsync(dup.p, 0, sizeof(int), stream));
+    k_emit_pairs<<<std::min((nl + 7) / 8, 148 * 16), 256, 0, stream>>>(nl, d_lob.p, d_lpb.p, d_rec_sorted, (unsigned long long)n_rec, k0.p, v0.p, dup.p);
+    CK(cudaGetLastError());
+    int h_runs = 0;
+    unsigned long long *pk = k0.p, *pv = v0.p, *pka = k1.p, *pva = v1.p;
+    CK(sort_and_encode(cub_tmp, pk, pv, pka, pva, np, key_bits, uq.p, cnt.p, runs.p, &h_runs, stream));
+    keys_out.resize(h_runs);
+    CK(cudaMemcpyAsync(keys_out.data(), uq.p, sizeof(unsigned long long) * h_runs, cudaMemcpyDeviceToHost, stream));
+    if (counts_out) { counts_out->resize(h_runs); CK(cudaMemcpyAsync(counts_out->data(), cnt.p, sizeof(int) * h_runs, cudaMemcpyDeviceToHost, stream)); }
+    int h_dup = 0;
+    CK(cudaMemcpyAsync(&h_dup, dup.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (keep_pairs) {
+      CKR(d_pairs.alloc((size_t)np));
+      CK(cudaMemcpyAsync(d_pairs.p, pv, sizeof(unsigned long long) * (size_t)np, cudaMemcpyDeviceToDevice, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    if (keep_pairs && h_dup) { g_err = "two observations of one landmark share a (keyframe pair, camera) record"; return GPBA_ERR_INVALID; }
+    return GPBA_OK;
+  };
+  CKR(pair_pass(n_lm, d_lm_obs_begin, lm_pair_begin, d_o_rec.p, true, rp_key, &rp_count));
+  n_rp = (int)rp_key.size();
+  // pattern keys: all edges (any level) of all active landmarks (block_solver.hpp:262-288) -- a second, key-only pass
+  // when that set differs from the compute list (level-1 edges, or landmarks owned by other ranks)
+  std::vector<unsigned long long> pat_key_store;
+  const std::vector<unsigned long long>* pat_key = &rp_key;
+  if (any_level1 || nranks > 1) {
+    std::vector<int64_t> lob(n_lm_all + 1, 0);
+    for (int64_t i = 0; i < n_obs; ++i) { const int l = pt_lm_all[obs_pt[i]]; if (l >= 0) lob[l + 1]++; }
+    for (int l = 0; l < n_lm_all; ++l) lob[l + 1] += lob[l];
+    std::vector<int> recs((size_t)lob[n_lm_all]);
+    {
+      std::vector<int64_t> cursor(lob.begin(), lob.end() - 1);
+      for (int64_t i = 0; i < n_obs; ++i) { const int l = pt_lm_all[obs_pt[i]]; if (l >= 0) recs[cursor[l]++] = obs_rec[i]; }
+    }
+    std::vector<int64_t> lpb(n_lm_all + 1, 0);
+    for (int l = 0; l < n_lm_all; ++l) { const int64_t n = lob[l + 1] - lob[l]; lpb[l + 1] = lpb[l] + n * (n + 1) / 2; }
+    DBuf<int64_t> d_lob; DBuf<int> d_recs;
+    CKR(d_lob.upload(lob, stream)); CKR(d_recs.upload(recs, stream));
+    CKR(pair_pass(n_lm_all, d_lob, lpb, d_recs.p, false, pat_key_store, nullptr));
+    pat_key = &pat_key_store;
+  }
+  // --- #Hpl blocks (reported only)
+  fill_view();
+  {
+    DBuf<unsigned long long> d_cnt;
+    CKR(d_cnt.alloc(1));
+    CK(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), stream));
+    if (n_lm > 0) { k_count_hpl<<<std::min((n_lm + 7) / 8, 148 * 16), 256, 0, stream>>>(V, d_o_rec.p, d_cnt.p); CK(cudaGetLastError()); }
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    n_hpl = (int64_t)h;
+  }
+  // --- work items of K4b: chunks of every record pair's list
+  const int CH = 256;
+  std::vector<int> item_rp;
+  std::vector<int64_t> item_begin, item_end;
+  std::vector<unsigned char> item_flags;
+  {
+    int64_t off = 0;
+    for (int sidx = 0; sidx < n_rp; ++sidx) {
+      const int64_t c = rp_count[sidx];
+      const unsigned char fl = (unsigned char)(((rp_key[sidx] / (unsigned long long)n_rec == rp_key[sidx] % (unsigned long long)n_rec) ? 1 : 0) | (c > CH ? 2 : 0));
+      for (int64_t b = 0; b < c; b += CH) { item_rp.push_back(sidx); item_begin.push_back(off + b); item_end.push_back(off + std::min<int64_t>(b + CH, c)); item_flags.push_back(fl); }
+      off += c;
+    }
+  }
+  n_items = (int)item_rp.size();
+  // --- Hpp pattern (upper): diagonals + priors + the keyframe pair of every record with an active edge
+  std::vector<std::vector<int>> pp_rows(n_pose), hs_rows;
   auto add_pair = [](std::vector<std::vector<int>>& rows, int a, int b) {
     if (a < 0 || b < 0) return;
     if (a > b) std::swap(a, b);
-    rows[a].push_back(b);
+    if (rows[a].empty() || rows[a].back() != b) rows[a].push_back(b);
   };
   for (int i = 0; i < n_pose; ++i) pp_rows[i].push_back(i);
   for (int i = 0; i < n_prior; ++i) add_pair(pp_rows, kf_h[prior_kf1[i]], kf_h[prior_kf2[i]]);
-  std::vector<char> rec_used(n_rec, 0);
-  for (int64_t j = 0; j < n_aobs; ++j) rec_used[srec[j]] = 1;
-  for (int64_t i : act_all) rec_used[obs_rec[i]] = 1;
   for (int r = 0; r < n_rec; ++r)
     if (rec_used[r] && rec_kf1[r] >= 0) add_pair(pp_rows, kf_h[rec_kf1[r]], kf_h[rec_kf2[r]]);
   auto uniq = [](std::vector<std::vector<int>>& rows) {
     for (auto& v : rows) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
   };
   uniq(pp_rows);
-  // --- Hschur pattern: Hpp pattern U pose pairs of ALL edges (any level) of active landmarks (block_solver.hpp:262-288)
+  // --- Hschur pattern: Hpp pattern U pose pairs of all edges of active landmarks
   hs_rows = pp_rows;
-  {
-    const bool any_inactive = n_aobs != n_obs;  // level-1 edges or landmarks owned by other ranks
-    const int n_pat = any_inactive ? n_lm_all : n_lm;
-    std::vector<std::vector<int>> lm_all(any_inactive ? n_lm_all : 0);
-    if (any_inactive) {
-      for (int64_t i = 0; i < n_obs; ++i) {
-        const int l = pt_lm_all[obs_pt[i]];
-        if (l < 0) continue;
-        const int r = obs_rec[i];
-        if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0) lm_all[l].push_back(kf_h[rec_kf1[r]]);
-        if (kf_h[rec_kf2[r]] >= 0) lm_all[l].push_back(kf_h[rec_kf2[r]]);
-      }
-    }
-    std::vector<int> tmp;
-    for (int l = 0; l < n_pat; ++l) {
-      const int* v; int nv;
-      if (any_inactive) {
-        tmp = lm_all[l];
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        v = tmp.data(); nv = (int)tmp.size();
-      } else {
-        v = &hpl_pose[lm_hpl_begin[l]]; nv = (int)(lm_hpl_begin[l + 1] - lm_hpl_begin[l]);
-      }
-      for (int a = 0; a < nv; ++a) {
-        std::vector<int>& row = hs_rows[v[a]];
-        for (int c = a; c < nv; ++c)
-          if (row.empty() || row.back() != v[c]) row.push_back(v[c]);  // cheap de-dup of runs; exact unique below
-      }
-      if ((l & 0xfff) == 0xfff) {  // keep the rows from growing without bound
-        for (int a = 0; a < nv; ++a) { auto& row = hs_rows[v[a]]; if (row.size() > 4096) { std::sort(row.begin(), row.end()); row.erase(std::unique(row.begin(), row.end()), row.end()); } }
-      }
-    }
+  auto rec_pose = [&](int r, int which) { const int k = which ? rec_kf2[r] : rec_kf1[r]; return k >= 0 ? kf_h[k] : -1; };
+  for (unsigned long long key : *pat_key) {
+    const int r1 = (int)(key / (unsigned long long)n_rec), r2 = (int)(key % (unsigned long long)n_rec);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) add_pair(hs_rows, rec_pose(r1, a), rec_pose(r2, b));
   }
   uniq(hs_rows);
   auto flatten = [&](const std::vector<std::vector<int>>& rows, std::vector<int>& prow, std::vector<int>& pcol,
@@ -552,63 +588,46 @@ int Solver::build_structure() {
   for (int i = 0; i < n_pose; ++i) pose_diag[i] = pp(i, i);
   for (int k = 0; k < n_hpp; ++k) hs_from[lookup(hs_rows, hs_ids, hpp_row[k], hpp_col[k])] = k;
   for (int k = 0; k < n_hs; ++k) if (hs_row[k] == hs_col[k]) hs_diag[k] = hs_row[k];
-  // --- Schur work lists: for every Hschur block the (U_i, U_j) block pairs of the landmarks seen by both poses
-  std::vector<int64_t> blk_count(n_hs + 1, 0);
-  for (int l = 0; l < n_lm; ++l) {
-    const int64_t hb = lm_hpl_begin[l], he = lm_hpl_begin[l + 1];
-    for (int64_t a = hb; a < he; ++a) {
-      const std::vector<int>& row = hs_rows[hpl_pose[a]];
-      const std::vector<int>& idr = hs_ids[hpl_pose[a]];
-      size_t it = 0;
-      for (int64_t c = a; c < he; ++c) {
-        while (row[it] < hpl_pose[c]) ++it;
-        blk_count[idr[it] + 1]++;
-      }
-    }
-  }
-  for (int k = 0; k < n_hs; ++k) blk_count[k + 1] += blk_count[k];
-  n_pairs = blk_count[n_hs];
-  std::vector<int> pair_i(n_pairs), pair_j(n_pairs);
+  // --- K4c contribution lists: which record pairs feed which Hschur block (counting sort by block, stable)
+  std::vector<int> con_begin(n_hs + 1, 0);
+  std::vector<HsContrib> con;
   {
-    std::vector<int64_t> cursor(blk_count.begin(), blk_count.end() - 1);
-    for (int l = 0; l < n_lm; ++l) {
-      const int64_t hb = lm_hpl_begin[l], he = lm_hpl_begin[l + 1];
-      for (int64_t a = hb; a < he; ++a) {
-        const std::vector<int>& row = hs_rows[hpl_pose[a]];
-        const std::vector<int>& idr = hs_ids[hpl_pose[a]];
-        size_t it = 0;
-        for (int64_t c = a; c < he; ++c) {
-          while (row[it] < hpl_pose[c]) ++it;
-          const int64_t pos = cursor[idr[it]]++;
-          pair_i[pos] = (int)a; pair_j[pos] = (int)c;
+    struct Raw { int blk; HsContrib c; };
+    std::vector<Raw> raw;
+    raw.reserve((size_t)n_rp * 4);
+    for (int sidx = 0; sidx < n_rp; ++sidx) {
+      const int r1 = (int)(rp_key[sidx] / (unsigned long long)n_rec), r2 = (int)(rp_key[sidx] % (unsigned long long)n_rec);
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          if (r1 == r2 && a > b) continue;  // the mirror image of (b, a)
+          const int pa = rec_pose(r1, a), pb = rec_pose(r2, b);
+          if (pa < 0 || pb < 0) continue;
+          int mode = 0;
+          if (pa > pb) mode = 1; else if (pa == pb && r1 != r2) mode = 2;
+          const int blk = lookup(hs_rows, hs_ids, std::min(pa, pb), std::max(pa, pb));
+          HsContrib c{sidx, r1, r2, a | (b << 1) | (mode << 2) | ((r1 == r2 && a == b) ? 16 : 0)};
+          raw.push_back({blk, c});
+          con_begin[blk + 1]++;
         }
-      }
     }
+    for (int k = 0; k < n_hs; ++k) con_begin[k + 1] += con_begin[k];
+    con.resize(raw.size());
+    std::vector<int> cursor(con_begin.begin(), con_begin.end() - 1);
+    for (const Raw& x : raw) con[cursor[x.blk]++] = x.c;
   }
-  const int CH = 256;
-  std::vector<int> item_blk;
-  std::vector<int64_t> item_begin;
-  for (int k = 0; k < n_hs; ++k)
-    for (int64_t b = blk_count[k]; b < blk_count[k + 1]; b += CH) { item_blk.push_back(k); item_begin.push_back(b); }
-  // item_begin[it+1] must be the end of item it: insert explicit ends by making items contiguous per block
-  {
-    std::vector<int64_t> ends;
-    std::vector<int64_t> begins2; std::vector<int> blk2;
-    for (size_t it = 0; it < item_blk.size(); ++it) {
-      const int64_t e = std::min(item_begin[it] + CH, blk_count[item_blk[it] + 1]);
-      begins2.push_back(item_begin[it]); blk2.push_back(item_blk[it]); ends.push_back(e);
-    }
-    // pairs are laid out block after block, so consecutive items are contiguous: end(it) == begin(it+1)
-    item_begin = begins2; item_begin.push_back(n_pairs); item_blk = blk2;
-  }
-  n_items = (int)item_blk.size();
-  // --- record-major permutation (K2b): sorted-obs indices grouped by record, split into segments
-  std::vector<int64_t> rcount(n_rec + 1, 0), rperm(n_aobs);
-  for (int64_t j = 0; j < n_aobs; ++j) rcount[srec[j] + 1]++;
-  for (int r = 0; r < n_rec; ++r) rcount[r + 1] += rcount[r];
-  {
-    std::vector<int64_t> cursor(rcount.begin(), rcount.end() - 1);
-    for (int64_t j = 0; j < n_aobs; ++j) rperm[cursor[srec[j]]++] = j;
+  // --- record-major permutation (K2b): sorted-obs indices grouped by record (stable device sort), split into segments
+  CKR(d_rperm.alloc(na));
+  if (n_aobs > 0) {
+    DBuf<int> kin, kout; DBuf<int64_t> vin;
+    CKR(kout.alloc(na)); CKR(vin.alloc(na));
+    std::vector<int64_t> iota((size_t)n_aobs);
+    for (int64_t j = 0; j < n_aobs; ++j) iota[j] = j;
+    CKR(vin.upload(iota, stream));
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, d_o_rec.p, kout.p, vin.p, d_rperm.p, n_aobs, 0, bits_for((unsigned long long)n_rec), stream));
+    CK(cub_tmp.reserve(need));
+    CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, d_o_rec.p, kout.p, vin.p, d_rperm.p, n_aobs, 0, bits_for((unsigned long long)n_rec), stream));
+    CK(cudaStreamSynchronize(stream));
   }
   const int SEG = 512;
   std::vector<int> rseg_rec; std::vector<int64_t> rseg_begin;
@@ -616,27 +635,19 @@ int Solver::build_structure() {
     for (int64_t b = rcount[r]; b < rcount[r + 1]; b += SEG) { rseg_rec.push_back(r); rseg_begin.push_back(b); }
   rseg_begin.push_back(n_aobs);
   n_rseg = (int)rseg_rec.size();
-
   // --- upload
-  CKR(d_kf_h.upload(kf_h, stream));
-  CKR(d_o_u.upload(su, stream)); CKR(d_o_v.upload(sv, stream)); CKR(d_o_w.upload(sw, stream));
-  if (stereo) CKR(d_o_ur.upload(sur, stream));
-  CKR(d_o_rec.upload(srec, stream)); CKR(d_o_lm.upload(slm, stream)); CKR(d_o_flags.upload(sfl, stream));
-  CKR(d_o_slot1.upload(slot1, stream)); CKR(d_o_slot2.upload(slot2, stream)); CKR(d_o_orig.upload(o_orig, stream));
-  CKR(d_lm_pt.upload(lm_pt, stream)); CKR(d_lm_obs_begin.upload(lm_obs_begin, stream));
-  CKR(d_lm_hpl_begin.upload(lm_hpl_begin, stream)); CKR(d_hpl_pose.upload(hpl_pose, stream)); CKR(d_hpl_lm.upload(hpl_lm, stream));
-  CKR(d_rperm.upload(rperm, stream)); CKR(d_rseg_rec.upload(rseg_rec, stream)); CKR(d_rseg_begin.upload(rseg_begin, stream));
+  CKR(d_rseg_rec.upload(rseg_rec, stream)); CKR(d_rseg_begin.upload(rseg_begin, stream));
   CKR(d_rec_hpp11.upload(rec11, stream)); CKR(d_rec_hpp12.upload(rec12, stream)); CKR(d_rec_hpp22.upload(rec22, stream));
   CKR(d_prior_hpp11.upload(pr11, stream)); CKR(d_prior_hpp12.upload(pr12, stream)); CKR(d_prior_hpp22.upload(pr22, stream));
   CKR(d_pose_hpp_diag.upload(pose_diag, stream)); CKR(d_hs_from_hpp.upload(hs_from, stream)); CKR(d_hs_diag_pose.upload(hs_diag, stream));
   CKR(d_hs_row.upload(hs_row, stream)); CKR(d_hs_col.upload(hs_col, stream));
-  CKR(d_item_blk.upload(item_blk, stream)); CKR(d_item_begin.upload(item_begin, stream));
-  CKR(d_pair_i.upload(pair_i, stream)); CKR(d_pair_j.upload(pair_j, stream));
-  CKR(d_all_flags.upload(obs_flags, stream));
+  CKR(d_item_rp.upload(item_rp, stream)); CKR(d_item_begin.upload(item_begin, stream)); CKR(d_item_end.upload(item_end, stream));
+  CKR(d_item_flags.upload(item_flags, stream));
+  CKR(d_con_begin.upload(con_begin, stream)); CKR(d_con.upload(con, stream));
   // --- storage
   CKR(d_ptS[0].alloc((size_t)n_lm * 3)); CKR(d_ptS[1].alloc((size_t)n_lm * 3));
   CKR(d_hll.alloc((size_t)n_lm * 9)); CKR(d_bl.alloc((size_t)n_lm * 3)); CKR(d_ptL.alloc((size_t)n_lm * 9)); CKR(d_xl.alloc((size_t)n_lm * 3));
-  CKR(d_hpl.alloc((size_t)n_hpl * 36)); CKR(d_U.alloc((size_t)n_hpl * 36));
+  CKR(d_W.alloc(na * 18)); CKR(d_U.alloc(na * 18)); CKR(d_C.alloc((size_t)std::max(n_rp, 1) * GPBA_RP_STRIDE));
   CKR(d_hpp.alloc((size_t)n_hpp * 144)); CKR(d_bp.alloc((size_t)n_pose * 12));
   CKR(d_hs.alloc((size_t)n_hs * 144 + (size_t)n_pose * 12 + 8)); CKR(d_x.alloc((size_t)n_pose * 12)); CKR(d_pose_scale.alloc((size_t)n_pose));
   d_bs.release();
@@ -835,8 +846,8 @@ int Solver::build_system() {
   int launches = 0;
   if (n_lm > 0) {
     const int g = std::min((n_lm + GPBA_K2_WARPS - 1) / GPBA_K2_WARPS, 148 * 16);
-    if (stereo) k_lin_points<true><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_hpl.p);
-    else k_lin_points<false><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_hpl.p);
+    if (stereo) k_lin_points<true><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
+    else k_lin_points<false><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
     CK(cudaGetLastError());
     t1(2, 1);
     t0();
@@ -881,23 +892,29 @@ int Solver::solve(double lambda, bool* ok) {
   double* bs = d_hs.p + (size_t)n_hs * 144;  // bschur lives right behind the Hschur values (one allreduce)
   CK(cudaMemsetAsync(d_fail.p, 0, sizeof(int), stream));
   t0();
-  // rank 0 carries Hpp + lambda (pose priors / damping must enter the sum exactly once);
-  // the GP-edge part of Hpp is a per-rank partial, so every rank adds its own Hpp but only rank 0 adds lambda.
-  k_schur_init<<<std::min(((int64_t)n_hs * 144 + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(V, rank == 0 ? lambda : 0.0, d_hpp.p, d_bp.p, d_hs.p, bs);
-  CK(cudaGetLastError());
-  int launches = 1;
+  // K4a + K4b: per-landmark factor and the record-pair products
   if (n_lm > 0) {
-    k_schur_prep<<<std::min((n_lm + 3) / 4, 148 * 16), 128, 0, stream>>>(V, lambda, d_hll.p, d_bl.p, d_hpl.p, d_U.p, d_ptL.p, d_fail.p);
+    k_schur_prep<<<std::min((n_lm + 3) / 4, 148 * 16), 128, 0, stream>>>(V, lambda, d_hll.p, d_bl.p, d_W.p, d_U.p, d_ptL.p, d_fail.p);
     CK(cudaGetLastError());
-    t1(4, 2);
-    t0();
-    k_schur_gather<<<std::min((n_items + 3) / 4, 148 * 16), 128, 0, stream>>>(n_items, d_item_blk.p, d_item_begin.p, d_pair_i.p, d_pair_j.p,
-                                                                              d_hpl_lm.p, d_hs_diag_pose.p, d_U.p, d_ptL.p, d_hs.p, bs);
-    CK(cudaGetLastError());
-    t1(5, 1);
-  } else {
-    t1(4, 1);
   }
+  t1(4, n_lm > 0 ? 1 : 0);
+  t0();
+  int launches = 0;
+  if (n_items > 0) {
+    CK(cudaMemsetAsync(d_C.p, 0, sizeof(double) * (size_t)n_rp * GPBA_RP_STRIDE, stream));
+    k_schur_pairs<<<std::min((n_items + 3) / 4, 148 * 16), 128, 0, stream>>>(n_items, d_item_rp.p, d_item_begin.p, d_item_end.p, d_item_flags.p,
+                                                                             d_pairs.p, d_o_lm.p, d_U.p, d_ptL.p, d_C.p);
+    CK(cudaGetLastError());
+    ++launches;
+  }
+  // K4c: rank 0 carries lambda (pose priors / damping must enter the sum exactly once); the GP-edge part of
+  // Hpp is a per-rank partial, so every rank adds its own Hpp but only rank 0 adds lambda.
+  if (n_hs > 0) {
+    k_schur_expand<<<n_hs, 144, 0, stream>>>(V, rank == 0 ? lambda : 0.0, d_rec.p, d_hpp.p, d_bp.p, d_con_begin.p, d_con.p, d_C.p, d_hs.p, bs);
+    CK(cudaGetLastError());
+    ++launches;
+  }
+  t1(5, launches);
   CKR(allreduce_system());
   t0();
   launches = 0;
@@ -927,7 +944,8 @@ int Solver::apply_update(double lambda, double* scale) {
   int gp = 0;
   if (n_lm > 0) {
     gp = std::min((n_lm + 3) / 4, 148 * 16);
-    k_backsub<<<gp, 128, 0, stream>>>(V, lambda, d_U.p, d_ptL.p, d_bl.p, d_x.p, d_ptS[cur].p, d_ptS[nb].p, d_xl.p, d_partial.p);
+    k_rec_y<<<(n_rec * 6 + 127) / 128, 128, 0, stream>>>(V, d_rec.p, d_x.p, d_Y.p);
+    k_backsub<<<gp, 128, 0, stream>>>(V, lambda, d_U.p, d_ptL.p, d_bl.p, d_Y.p, d_ptS[cur].p, d_ptS[nb].p, d_xl.p, d_partial.p);
     CK(cudaGetLastError());
   }
   k_update_poses<<<(n_kf + 63) / 64, 64, 0, stream>>>(V, lambda, d_x.p, d_bp.p, d_pose[cur].p, d_vel[cur].p, d_pose[nb].p, d_vel[nb].p, d_pose_scale.p);
@@ -935,7 +953,7 @@ int Solver::apply_update(double lambda, double* scale) {
   // pose part of computeScale is replicated on every rank; landmark part is per-rank
   k_reduce<<<1, 256, 0, stream>>>(d_partial.p, gp, d_pose_scale.p, rank == 0 ? n_pose : 0, d_scal.p + 1);
   CK(cudaGetLastError());
-  t1(8, 3);
+  t1(8, 4);
   if (nranks > 1) CKR(allreduce_scalar(d_scal.p + 1));
   if (scale) {
     CK(cudaMemcpyAsync(h_scal + 1, d_scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -1195,21 +1213,55 @@ int gpba_get_hll(gpba_handle* h, double* blocks) {
   return GPBA_OK;
 }
 int gpba_get_hpl(gpba_handle* h, int64_t* lm_begin, int32_t* pose, double* blocks) {  // (landmark, pose) order of the g2o landmark numbering
+  // Debug / parity accessor: the product path never forms Hpl.  Hpl_(pose,l) = sum over the landmark's observations whose
+  // record touches the pose of (M_r^(pose))^T W_o, assembled here on the host from W and the record table.
   NEED_STRUCT(h);
   Solver& s = S(h);
   CK(cudaStreamSynchronize(s.stream));
-  std::vector<double> hp((size_t)s.n_hpl * 36);
-  if (s.n_hpl) CK(cudaMemcpy(hp.data(), s.d_hpl.p, hp.size() * 8, cudaMemcpyDeviceToHost));
+  std::vector<double> W((size_t)s.n_aobs * 18), R((size_t)s.n_rec * GPBA_REC_STRIDE);
+  std::vector<int> orec((size_t)s.n_aobs);
+  if (s.n_aobs) {
+    CK(cudaMemcpy(W.data(), s.d_W.p, W.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(orec.data(), s.d_o_rec.p, orec.size() * 4, cudaMemcpyDeviceToHost));
+  }
+  if (s.n_rec) CK(cudaMemcpy(R.data(), s.d_rec.p, R.size() * 8, cudaMemcpyDeviceToHost));
   std::vector<int> inv(s.n_lm);
   for (int l = 0; l < s.n_lm; ++l) inv[s.lm_rank[l]] = l;
   int64_t cursor = 0;
+  std::vector<int> poses;
   for (int g = 0; g < s.n_lm; ++g) {
     const int l = inv[g];
     if (lm_begin) lm_begin[g] = cursor;
-    for (int64_t a = s.lm_hpl_begin[l]; a < s.lm_hpl_begin[l + 1]; ++a, ++cursor) {
-      if (pose) pose[cursor] = s.hpl_pose[a];
-      if (blocks) std::memcpy(blocks + cursor * 36, hp.data() + a * 36, 36 * 8);
+    poses.clear();
+    for (int64_t j = s.lm_obs_begin[l]; j < s.lm_obs_begin[l + 1]; ++j) {
+      const int r = orec[j];
+      if (s.rec_kf1[r] >= 0 && s.kf_h[s.rec_kf1[r]] >= 0) poses.push_back(s.kf_h[s.rec_kf1[r]]);
+      if (s.kf_h[s.rec_kf2[r]] >= 0) poses.push_back(s.kf_h[s.rec_kf2[r]]);
     }
+    std::sort(poses.begin(), poses.end());
+    poses.erase(std::unique(poses.begin(), poses.end()), poses.end());
+    for (size_t a = 0; a < poses.size(); ++a) {
+      if (pose) pose[cursor + a] = poses[a];
+      if (blocks) std::fill(blocks + (cursor + a) * 36, blocks + (cursor + a + 1) * 36, 0.0);
+    }
+    if (blocks)
+      for (int64_t j = s.lm_obs_begin[l]; j < s.lm_obs_begin[l + 1]; ++j) {
+        const int r = orec[j];
+        const double* M = R.data() + (size_t)r * GPBA_REC_STRIDE + GPBA_REC_M;
+        for (int which = 0; which < 2; ++which) {
+          const int k = which ? s.rec_kf2[r] : s.rec_kf1[r];
+          const int hh = k >= 0 ? s.kf_h[k] : -1;
+          if (hh < 0) continue;
+          const size_t slot = cursor + (std::lower_bound(poses.begin(), poses.end(), hh) - poses.begin());
+          for (int c12 = 0; c12 < 12; ++c12)
+            for (int c = 0; c < 3; ++c) {
+              double acc = 0.0;
+              for (int m = 0; m < 6; ++m) acc += M[m * 24 + 12 * which + c12] * W[(size_t)j * 18 + m * 3 + c];
+              blocks[slot * 36 + c12 * 3 + c] += acc;
+            }
+        }
+      }
+    cursor += (int64_t)poses.size();
   }
   if (lm_begin) lm_begin[s.n_lm] = cursor;
   return GPBA_OK;
@@ -1370,11 +1422,9 @@ int gpba_compute_errors_inactive(gpba_handle* h) {
   Solver& s = S(h);
   CKR(s.scatter_points(s.cur));
   CKR(s.compute_records(s.cur, false));
-  DBuf<double> du, dv, dw;
-  CKR(du.upload(s.obs_u, s.stream)); CKR(dv.upload(s.obs_v, s.stream)); CKR(dw.upload(s.obs_w, s.stream));
   const int g = (int)std::min<int64_t>((s.n_obs + 255) / 256 + 1, 148 * 8);
-  k_chi2_inactive<<<g, 256, 0, s.stream>>>(s.V, s.n_obs, s.d_all_flags.p, s.d_all_rec.p, s.d_all_pt.p, du.p, dv.p,
-                                           s.stereo ? s.d_all_ur.p : nullptr, dw.p, s.d_rec_lite.p, s.d_pt_full.p, s.d_chi2.p);
+  k_chi2_inactive<<<g, 256, 0, s.stream>>>(s.V, s.n_obs, s.d_all_flags.p, s.d_all_rec.p, s.d_all_pt.p, s.d_all_u.p, s.d_all_v.p,
+                                           s.stereo ? s.d_all_ur.p : nullptr, s.d_all_w.p, s.d_rec_lite.p, s.d_pt_full.p, s.d_chi2.p);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s.stream));
   return GPBA_OK;

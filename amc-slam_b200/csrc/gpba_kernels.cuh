@@ -3,13 +3,20 @@
 //  K0  k_records          GaussianProcess::QueryPose + the pose-chain part of EdgeMonoGP::linearizeOplus
 //                         (src/GaussianProcess.cc:23-42, src/G2oTypes.cc:343-357) once per (KF,cam) record
 //  K1  k_residual         SparseOptimizer::computeActiveErrors + activeRobustChi2 (sparse_optimizer.cpp:61-114)
-//  K2  k_lin_points       BlockSolver::buildSystem, landmark side: Hll, b_l, Hpl (block_solver.hpp:502-560)
+//  K2  k_lin_points       BlockSolver::buildSystem, landmark side: Hll, b_l and W_o = J1^T (rho' Omega) J_p (6x3 per
+//                         observation; Hpl_(pose,l) = sum_o M_r^T W_o is never materialised) (block_solver.hpp:502-560)
 //      k_lin_records      ... pose side in the 6-dim record tangent space: S_r = sum w J1^T J1, g_r
 //      k_rec_to_hpp       ... Hpp += M_r^T S_r M_r, b_p += M_r^T g_r
 //  K3  k_priors           EdgeGaussianPrior / EdgeVelocity (G2oTypes.cc:100-118, G2oTypes.h:155-163,496-519)
-//  K4  k_schur_prep/init/gather   BlockSolver::solve, Schur part (block_solver.hpp:367-439)
-//  K6  k_backsub / k_update_poses landmark back-substitution + oplus (block_solver.hpp:459-483,
+//  K4  k_schur_prep       D = Hll + lambda I = L L^T, U_o = W_o L^-T, z = L^-1 b_l
+//      k_schur_pairs      C_(r,r') = sum over observation pairs of a landmark of U_o U_o'^T (6x6 per record pair, DMMA)
+//      k_schur_expand     Hschur_ij = Hpp_ij + lambda - sum M_r^T C_(r,r') M_r', bschur  (block_solver.hpp:367-439)
+//  K6  k_rec_y / k_backsub / k_update_poses   landmark back-substitution + oplus (block_solver.hpp:459-483,
 //                         sparse_optimizer.cpp:422-435, G2oTypes.cc:41-46)
+// The Schur complement is evaluated in the record tangent space: every reprojection edge of a
+// (KF_prev, KF_cur, camera) record shares the 6x24 chain matrix M_r, so Hpl D^-1 Hpl^T = sum M_r^T (W_o D^-1 W_o'^T) M_r'
+// needs a 6x6x3 product per observation pair instead of a 12x12x3 one per pose pair (about 7x fewer flops and 3.5x
+// less traffic at 10 observations per landmark); only the summation order differs from the reference.
 //  K8  k_flags            LocalGPBA inlier check (src/Optimizer.cc:1263-1348)
 #pragma once
 #include "gpba_device.cuh"
@@ -158,6 +165,14 @@ __global__ void k_records(DevView V, const double* __restrict__ pose, const doub
           M[m * 24 + 18 + c] = MV2(m, c);
         }
     }
+  } else if (FULL) {
+    // synchronous record (EdgeMono / EdgeStereo): pose block = J1, velocity block = 0 (G2oTypes.cc:465-467),
+    // i.e. M = [0 | 0 | I | 0], so that every consumer can treat the two record kinds alike
+    double* M = out + GPBA_REC_M;
+#pragma unroll
+    for (int m = 0; m < 6; ++m)
+#pragma unroll
+      for (int c = 0; c < 24; ++c) M[m * 24 + c] = (c == 12 + m) ? 1.0 : 0.0;
   }
   SE3 Tbc;
   Tbc.q.x = cam.qbc[0]; Tbc.q.y = cam.qbc[1]; Tbc.q.z = cam.qbc[2]; Tbc.q.w = cam.qbc[3];
@@ -204,90 +219,46 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ a, in
 }
 
 // ------------------------------------------------------------------------------------------------ K2a
-// One warp per landmark.  Phase A: lane = observation (residual, weight, J1, Jp; W = J1^T w Jp).
-// Phase B: lane = Hpl entry; the record's 6x24 chain matrix M_r turns W (6x3) into the two 12x3
-// pose blocks, accumulated in a per-warp shared-memory tile and written out once (no atomics).
-#define GPBA_K2_WARPS 4
-#define GPBA_K2_DMAX 24
+// One warp per landmark, lane = observation: residual, robust weight, J1, Jp; W_o = J1^T (rho' w) Jp goes out as
+// 18 contiguous doubles per observation, Hll / b_l are reduced with warp shuffles (no atomics, no shared memory).
+#define GPBA_K2_WARPS 8
 template <bool STEREO>
 __global__ void __launch_bounds__(GPBA_K2_WARPS * 32) k_lin_points(DevView V, const double* __restrict__ rec,
                                                                    const double* __restrict__ pt, double* __restrict__ hll,
-                                                                   double* __restrict__ bl, double* __restrict__ hpl) {
-  __shared__ double sW[GPBA_K2_WARPS][32][18];
-  __shared__ int sRec[GPBA_K2_WARPS][32];
-  __shared__ uint16_t sS1[GPBA_K2_WARPS][32], sS2[GPBA_K2_WARPS][32];
-  __shared__ double sTile[GPBA_K2_WARPS][GPBA_K2_DMAX * 36];
+                                                                   double* __restrict__ bl, double* __restrict__ W) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ROWS = STEREO ? 3 : 2;
   for (int lm = blockIdx.x * GPBA_K2_WARPS + warp; lm < V.n_lm; lm += gridDim.x * GPBA_K2_WARPS) {
     const int64_t ob = V.lm_obs_begin[lm], oe = V.lm_obs_begin[lm + 1];
-    const int64_t hb = V.lm_hpl_begin[lm];
-    const int d = (int)(V.lm_hpl_begin[lm + 1] - hb);
-    const bool use_tile = d <= GPBA_K2_DMAX;
-    double* tile = use_tile ? sTile[warp] : hpl + (size_t)hb * 36;
-    for (int j = lane; j < d * 36; j += 32) tile[j] = 0.0;
-    __syncwarp();
     const double X0 = pt[3 * (size_t)lm], X1 = pt[3 * (size_t)lm + 1], X2 = pt[3 * (size_t)lm + 2];
     double h[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-    for (int64_t base = ob; base < oe; base += 32) {
-      const int64_t i = base + lane;
-      if (i < oe) {
-        const int r = V.o_rec[i];
-        ObsEval<STEREO> E;
-        double J1[ROWS][6], Jp[ROWS][3];
-        eval_obs<STEREO, true>(V, rec + (size_t)r * GPBA_REC_STRIDE, V.cam[V.rec_cam[r]], X0, X1, X2, V.o_u[i], V.o_v[i],
-                               STEREO ? V.o_ur[i] : -1.0, V.o_w[i], V.o_flags[i], E, J1, Jp);
-        const double wr = E.rho1 * V.o_w[i];  // robustInformation = rho' * Omega (base_edge.h:96-102)
+    for (int64_t i = ob + lane; i < oe; i += 32) {
+      const int r = V.o_rec[i];
+      ObsEval<STEREO> E;
+      double J1[ROWS][6], Jp[ROWS][3];
+      const double w = V.o_w[i];
+      eval_obs<STEREO, true>(V, rec + (size_t)r * GPBA_REC_STRIDE, V.cam[V.rec_cam[r]], X0, X1, X2, V.o_u[i], V.o_v[i],
+                             STEREO ? V.o_ur[i] : -1.0, w, V.o_flags[i], E, J1, Jp);
+      const double wr = E.rho1 * w;  // robustInformation = rho' * Omega (base_edge.h:96-102)
+      double Wo[18];
 #pragma unroll
-        for (int m = 0; m < 6; ++m)
+      for (int m = 0; m < 6; ++m)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            double s = 0.0;
+        for (int c = 0; c < 3; ++c) {
+          double s = 0.0;
 #pragma unroll
-            for (int rr = 0; rr < ROWS; ++rr) s = fma(wr * J1[rr][m], Jp[rr][c], s);
-            sW[warp][lane][m * 3 + c] = s;
-          }
-        sRec[warp][lane] = r;
-        sS1[warp][lane] = V.o_slot1[i];
-        sS2[warp][lane] = V.o_slot2[i];
-#pragma unroll
-        for (int rr = 0; rr < ROWS; ++rr) {
-          const double w0 = wr * Jp[rr][0], w1 = wr * Jp[rr][1], w2 = wr * Jp[rr][2];
-          h[0] = fma(w0, Jp[rr][0], h[0]); h[1] = fma(w0, Jp[rr][1], h[1]); h[2] = fma(w0, Jp[rr][2], h[2]);
-          h[3] = fma(w1, Jp[rr][1], h[3]); h[4] = fma(w1, Jp[rr][2], h[4]); h[5] = fma(w2, Jp[rr][2], h[5]);
-          b[0] = fma(-w0, E.e[rr], b[0]); b[1] = fma(-w1, E.e[rr], b[1]); b[2] = fma(-w2, E.e[rr], b[2]);
+          for (int rr = 0; rr < ROWS; ++rr) s = fma(wr * J1[rr][m], Jp[rr][c], s);
+          Wo[m * 3 + c] = s;
         }
-      }
-      __syncwarp();
-      const int n = (int)((oe - base) < 32 ? (oe - base) : 32);
-      for (int o = 0; o < n; ++o) {
-        const int r = sRec[warp][o];
-        const unsigned s1 = sS1[warp][o], s2 = sS2[warp][o];
-        const bool is_gp = V.rec_kf1[r] >= 0;
-        const double* M = rec + (size_t)r * GPBA_REC_STRIDE + GPBA_REC_M;
-        const double* W = sW[warp][o];
+      double2* out = reinterpret_cast<double2*>(W + (size_t)i * 18);
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const int e = lane + 32 * pass;
-          if (e < 72) {
-            const int ap = e / 3, c = e - 3 * ap;
-            const unsigned slot = ap < 12 ? s1 : s2;
-            if (slot != GPBA_NO_SLOT) {
-              double val;
-              bool live = true;
-              if (is_gp) {
-                val = 0.0;
+      for (int q = 0; q < 9; ++q) out[q] = make_double2(Wo[2 * q], Wo[2 * q + 1]);
 #pragma unroll
-                for (int m = 0; m < 6; ++m) val = fma(M[m * 24 + ap], W[m * 3 + c], val);
-              } else {  // EdgeMono / EdgeStereo: pose block = J1, velocity block = 0 (G2oTypes.cc:465-467)
-                live = ap >= 12 && ap < 18;
-                val = live ? W[(ap - 12) * 3 + c] : 0.0;
-              }
-              if (live) tile[slot * 36 + (ap % 12) * 3 + c] += val;
-            }
-          }
-        }
-        __syncwarp();
+      for (int rr = 0; rr < ROWS; ++rr) {
+        const double w0 = wr * Jp[rr][0], w1 = wr * Jp[rr][1], w2 = wr * Jp[rr][2];
+        h[0] = fma(w0, Jp[rr][0], h[0]); h[1] = fma(w0, Jp[rr][1], h[1]); h[2] = fma(w0, Jp[rr][2], h[2]);
+        h[3] = fma(w1, Jp[rr][1], h[3]); h[4] = fma(w1, Jp[rr][2], h[4]); h[5] = fma(w2, Jp[rr][2], h[5]);
+        b[0] = fma(-w0, E.e[rr], b[0]); b[1] = fma(-w1, E.e[rr], b[1]); b[2] = fma(-w2, E.e[rr], b[2]);
       }
     }
 #pragma unroll
@@ -301,11 +272,6 @@ __global__ void __launch_bounds__(GPBA_K2_WARPS * 32) k_lin_points(DevView V, co
       H[6] = h[2]; H[7] = h[4]; H[8] = h[5];
       bl[3 * (size_t)lm] = b[0]; bl[3 * (size_t)lm + 1] = b[1]; bl[3 * (size_t)lm + 2] = b[2];
     }
-    if (use_tile) {
-      double* out = hpl + (size_t)hb * 36;
-      for (int j = lane; j < d * 36; j += 32) out[j] = tile[j];
-    }
-    __syncwarp();
   }
 }
 
@@ -529,10 +495,11 @@ __global__ void __launch_bounds__(64) k_priors(DevView V, const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ K4
-// K4a: one warp per landmark: D = Hll + lambda I = L L^T, U_il = Hpl_il L^-T (so that Hpl D^-1 Hpl^T = U U^T),
-// z = L^-1 b_l.  ptL[9*lm] = {l00,l10,l11,l20,l21,l22, z0,z1,z2}.  Pure streaming: reads/writes each Hpl block once.
+// K4a: one warp per landmark: D = Hll + lambda I = L L^T, U_o = W_o L^-T (so that W_o D^-1 W_o'^T = U_o U_o'^T),
+// z = L^-1 b_l.  ptL[9*lm] = {l00,l10,l11,l20,l21,l22, z0,z1,z2}.  Pure streaming: each W row is read and each U row
+// written once.
 __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, const double* __restrict__ hll,
-                                                    const double* __restrict__ bl, const double* __restrict__ hpl,
+                                                    const double* __restrict__ bl, const double* __restrict__ W,
                                                     double* __restrict__ U, double* __restrict__ ptL, int* __restrict__ fail) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int lm = blockIdx.x * 4 + warp; lm < V.n_lm; lm += gridDim.x * 4) {
@@ -551,112 +518,158 @@ __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, co
       double* o = ptL + 9 * (size_t)lm;
       o[0] = l00; o[1] = l10; o[2] = l11; o[3] = l20; o[4] = l21; o[5] = l22; o[6] = z0; o[7] = z1; o[8] = z2;
     }
-    const int64_t hb = V.lm_hpl_begin[lm];
-    const int nrow = (int)(V.lm_hpl_begin[lm + 1] - hb) * 12;
-    const double* B = hpl + (size_t)hb * 36;
-    double* Uo = U + (size_t)hb * 36;
+    const int64_t ob = V.lm_obs_begin[lm];
+    const int nrow = (int)(V.lm_obs_begin[lm + 1] - ob) * 6;
+    const double* B = W + (size_t)ob * 18;
+    double* Uo = U + (size_t)ob * 18;
+    const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
     for (int rr = lane; rr < nrow; rr += 32) {
       const double b0 = B[rr * 3], b1 = B[rr * 3 + 1], b2 = B[rr * 3 + 2];
-      const double u0 = b0 / l00;
-      const double u1 = (b1 - u0 * l10) / l11;
-      const double u2 = (b2 - u0 * l20 - u1 * l21) / l22;
+      const double u0 = b0 * i00;
+      const double u1 = (b1 - u0 * l10) * i11;
+      const double u2 = (b2 - u0 * l20 - u1 * l21) * i22;
       Uo[rr * 3] = u0; Uo[rr * 3 + 1] = u1; Uo[rr * 3 + 2] = u2;
     }
   }
 }
 
-// Hschur := Hpp (+ lambda on the diagonal), bschur := b_p.   (block_solver.hpp:373-374, 436-439, 563-589)
-__global__ void k_schur_init(DevView V, double lambda, const double* __restrict__ hpp, const double* __restrict__ bp,
-                             double* __restrict__ hs, double* __restrict__ bs) {
-  const int64_t n = (int64_t)V.n_hs * 144;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-    const int blk = (int)(j / 144), e = (int)(j % 144);
-    const int src = V.hs_from_hpp[blk];
-    double v = src >= 0 ? hpp[(size_t)src * 144 + e] : 0.0;
-    if (V.hs_diag_pose[blk] >= 0 && (e / 12) == (e % 12)) v += lambda;
-    hs[j] = v;
-  }
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < (int64_t)V.n_pose * 12; j += (int64_t)gridDim.x * blockDim.x)
-    bs[j] = bp[j];
-}
-
-// K4b: block-sparse SYRK on the FP64 tensor pipe.  One warp per work item = (Hschur block (i,j), chunk of
-// landmarks seen by both poses).  Hs_ij -= sum_l U_il U_jl^T is a 12 x 12 x 3L GEMM evaluated as 16x16 with
-// mma.sync.m8n8k4.f64 (DMMA); the padding column 12 of diagonal blocks carries z_l, which yields
-// bschur_i -= sum_l U_il z_l for free.
+// K4b: C_(r,r') = sum U_o U_o'^T over the observation pairs (o in r, o' in r') of common landmarks: a 6 x 6 x 3L GEMM
+// per record pair on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA), one warp per work item = (record pair, chunk
+// of its pair list).  Diagonal record pairs hold the self pairs (o, o): there the padding column 6 carries z_l, which
+// yields g'_r = sum_o U_o z_l (the record's share of Hpl D^-1 b_l) for free.  C is stored 6 x 8 row-major.
 GPBA_D void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(128) k_schur_gather(int n_items, const int* __restrict__ item_blk,
-                                                      const int64_t* __restrict__ item_begin,
-                                                      const int* __restrict__ pair_i, const int* __restrict__ pair_j,
-                                                      const int* __restrict__ hpl_lm, const int* __restrict__ hs_diag_pose,
-                                                      const double* __restrict__ U, const double* __restrict__ ptL,
-                                                      double* __restrict__ hs, double* __restrict__ bs) {
+#define GPBA_RP_STRIDE 48
+__global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __restrict__ item_rp,
+                                                     const int64_t* __restrict__ item_begin, const int64_t* __restrict__ item_end,
+                                                     const unsigned char* __restrict__ item_flags /* 1: diagonal, 2: atomic */,
+                                                     const unsigned long long* __restrict__ pairs, const int* __restrict__ o_lm,
+                                                     const double* __restrict__ U, const double* __restrict__ ptL,
+                                                     double* __restrict__ C) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   for (int it = blockIdx.x * 4 + warp; it < n_items; it += gridDim.x * 4) {
-    const int blk = item_blk[it];
     const int64_t pb = item_begin[it];
-    const int kmax = 3 * (int)(item_begin[it + 1] - pb);
-    const int diag = hs_diag_pose[blk];
-    double c[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
-    for (int k0 = 0; k0 < kmax; k0 += 4) {
-      const int kk = k0 + tig;
-      const bool valid = kk < kmax;
-      const int p = kk / 3, cc = kk - 3 * p;
-      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-      if (valid) {
-        const int oi = pair_i[pb + p], oj = pair_j[pb + p];
-        const double* Ui = U + (size_t)oi * 36 + cc;
-        const double* Uj = U + (size_t)oj * 36 + cc;
-        a0 = Ui[gid * 3];
-        b0 = Uj[gid * 3];
-        if (gid < 4) { a1 = Ui[(8 + gid) * 3]; b1 = Uj[(8 + gid) * 3]; }
-        else if (gid == 4 && diag >= 0) b1 = ptL[(size_t)hpl_lm[oi] * 9 + 6 + cc];
-      }
-      dmma884(c[0][0][0], c[0][0][1], a0, b0);
-      dmma884(c[0][1][0], c[0][1][1], a0, b1);
-      dmma884(c[1][0][0], c[1][0][1], a1, b0);
-      dmma884(c[1][1][0], c[1][1][1], a1, b1);
-    }
+    const int kmax = 3 * (int)(item_end[it] - pb);
+    const unsigned fl = item_flags[it];
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: independent DMMA chains
+    for (int k0 = 0; k0 < kmax; k0 += 8) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int row = mt * 8 + gid, col = nt * 8 + 2 * tig + q;
-          if (row < 12) {
-            if (col < 12) atomicAdd(&hs[(size_t)blk * 144 + row * 12 + col], -c[mt][nt][q]);
-            else if (col == 12 && diag >= 0) atomicAdd(&bs[(size_t)diag * 12 + row], -c[mt][nt][q]);
-          }
+      for (int half = 0; half < 2; ++half) {
+        const int kk = k0 + 4 * half + tig;
+        double a = 0.0, b = 0.0;
+        if (kk < kmax) {
+          const int p = kk / 3, cc = kk - 3 * p;
+          const unsigned long long pr = pairs[pb + p];
+          const unsigned oa = (unsigned)(pr >> 32), ob = (unsigned)pr;
+          if (gid < 6) { a = U[(size_t)oa * 18 + gid * 3 + cc]; b = U[(size_t)ob * 18 + gid * 3 + cc]; }
+          else if (gid == 6 && (fl & 1u)) b = ptL[(size_t)o_lm[oa] * 9 + 6 + cc];
         }
+        if (half == 0) dmma884(c0, c1, a, b); else dmma884(e0, e1, a, b);
+      }
+    }
+    c0 += e0; c1 += e1;
+    if (gid < 6) {
+      double* out = C + (size_t)item_rp[it] * GPBA_RP_STRIDE + gid * 8 + 2 * tig;
+      if (fl & 2u) { atomicAdd(out, c0); atomicAdd(out + 1, c1); }
+      else *reinterpret_cast<double2*>(out) = make_double2(c0, c1);
+    }
   }
 }
 
+// K4c: one CTA (144 threads = one per entry) per Hschur block (i, j), i <= j:
+//   Hs_ij = Hpp_ij (+ lambda on the diagonal) - sum over the block's contributions of M_r^(a)T C_(r,r') M_r'^(b)
+// in the fixed order of the contribution list (no atomics: the block is written once).  mode 1 adds the transposed
+// product (the pair was listed with its poses swapped), mode 2 the symmetrised one (both records touch pose i);
+// on diagonal blocks the diagonal record pairs also give bschur_i = b_p,i - sum M_r^(a)T g'_r.
+struct HsContrib { int rp; int r1; int r2; int code; };  // code: bit0 a, bit1 b, bits 2-3 mode, bit 4: diagonal record pair with a == b
+__global__ void __launch_bounds__(144) k_schur_expand(DevView V, double lambda, const double* __restrict__ rec,
+                                                      const double* __restrict__ hpp, const double* __restrict__ bp,
+                                                      const int* __restrict__ con_begin, const HsContrib* __restrict__ con,
+                                                      const double* __restrict__ C, double* __restrict__ hs,
+                                                      double* __restrict__ bs) {
+  __shared__ double sC[48], sMa[72], sMb[72], sT[72];
+  const int blk = blockIdx.x, tid = threadIdx.x;
+  const int i = tid / 12, j = tid % 12;
+  const int src = V.hs_from_hpp[blk];
+  const int diag = V.hs_diag_pose[blk];
+  double acc = src >= 0 ? hpp[(size_t)src * 144 + tid] : 0.0;
+  if (diag >= 0 && i == j) acc += lambda;
+  double bacc = (diag >= 0 && tid < 12) ? bp[(size_t)diag * 12 + tid] : 0.0;
+  for (int e = con_begin[blk]; e < con_begin[blk + 1]; ++e) {
+    const HsContrib cn = con[e];
+    const int a = cn.code & 1, b = (cn.code >> 1) & 1, mode = (cn.code >> 2) & 3;
+    if (tid < 48) sC[tid] = C[(size_t)cn.rp * GPBA_RP_STRIDE + tid];
+    if (tid < 72) sMa[tid] = rec[(size_t)cn.r1 * GPBA_REC_STRIDE + GPBA_REC_M + (tid / 12) * 24 + 12 * a + tid % 12];
+    else sMb[tid - 72] = rec[(size_t)cn.r2 * GPBA_REC_STRIDE + GPBA_REC_M + ((tid - 72) / 12) * 24 + 12 * b + (tid - 72) % 12];
+    __syncthreads();
+    if (tid < 72) {  // T = C M_b  (6 x 12)
+      const int m = tid / 12, c = tid % 12;
+      double s = 0.0;
+#pragma unroll
+      for (int n = 0; n < 6; ++n) s = fma(sC[m * 8 + n], sMb[n * 12 + c], s);
+      sT[tid] = s;
+    }
+    __syncthreads();
+    double p = 0.0, q = 0.0;  // P[i][j] and P[j][i], P = M_a^T T
+#pragma unroll
+    for (int m = 0; m < 6; ++m) { p = fma(sMa[m * 12 + i], sT[m * 12 + j], p); q = fma(sMa[m * 12 + j], sT[m * 12 + i], q); }
+    acc -= mode == 0 ? p : (mode == 1 ? q : p + q);
+    if ((cn.code & 16) && tid < 12) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) s = fma(sMa[m * 12 + tid], sC[m * 8 + 6], s);
+      bacc -= s;
+    }
+    __syncthreads();
+  }
+  hs[(size_t)blk * 144 + tid] = acc;
+  if (diag >= 0 && tid < 12) bs[(size_t)diag * 12 + tid] = bacc;
+}
+
 // ------------------------------------------------------------------------------------------------ K6
-// Landmarks: x_l = D^-1 (b_l - Hpl^T x_p) = L^-T (z - sum_i U_il^T x_i); pt_new = pt + x_l.
+// y_r = M_r [x_kf1; x_kf2]: the pose update seen from record r (6-vector), one thread per (record, row).
+__global__ void k_rec_y(DevView V, const double* __restrict__ rec, const double* __restrict__ xp, double* __restrict__ Y) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V.n_rec * 6) return;
+  const int r = t / 6, m = t % 6;
+  const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
+  const int h1 = k1 >= 0 ? V.kf_h[k1] : -1, h2 = V.kf_h[k2];
+  const double* M = rec + (size_t)r * GPBA_REC_STRIDE + GPBA_REC_M + m * 24;
+  double s = 0.0;
+  if (h1 >= 0) {
+#pragma unroll
+    for (int c = 0; c < 12; ++c) s = fma(M[c], xp[(size_t)h1 * 12 + c], s);
+  }
+  if (h2 >= 0) {
+#pragma unroll
+    for (int c = 0; c < 12; ++c) s = fma(M[12 + c], xp[(size_t)h2 * 12 + c], s);
+  }
+  Y[t] = s;
+}
+
+// Landmarks: x_l = D^-1 (b_l - Hpl^T x_p) = L^-T (z - sum_o U_o^T y_r(o)); pt_new = pt + x_l.
 // partial[] receives sum x_l (lambda x_l + b_l) for computeScale (optimization_algorithm_levenberg.cpp:187-194).
 __global__ void __launch_bounds__(128) k_backsub(DevView V, double lambda, const double* __restrict__ U,
                                                  const double* __restrict__ ptL, const double* __restrict__ bl,
-                                                 const double* __restrict__ xp, const double* __restrict__ pt_cur,
+                                                 const double* __restrict__ Y, const double* __restrict__ pt_cur,
                                                  double* __restrict__ pt_new, double* __restrict__ xl,
                                                  double* __restrict__ partial) {
   __shared__ double red[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double sc = 0.0;
   for (int lm = blockIdx.x * 4 + warp; lm < V.n_lm; lm += gridDim.x * 4) {
-    const int64_t hb = V.lm_hpl_begin[lm];
-    const int d = (int)(V.lm_hpl_begin[lm + 1] - hb);
+    const int64_t ob = V.lm_obs_begin[lm];
+    const int nrow = (int)(V.lm_obs_begin[lm + 1] - ob) * 6;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int rr = lane; rr < d * 12; rr += 32) {
-      const double x = xp[(size_t)V.hpl_pose[hb + rr / 12] * 12 + rr % 12];
-      const double* u = U + (size_t)hb * 36 + rr * 3;
-      a0 = fma(u[0], x, a0); a1 = fma(u[1], x, a1); a2 = fma(u[2], x, a2);
+    for (int rr = lane; rr < nrow; rr += 32) {
+      const double y = Y[(size_t)V.o_rec[ob + rr / 6] * 6 + rr % 6];
+      const double* u = U + (size_t)ob * 18 + rr * 3;
+      a0 = fma(u[0], y, a0); a1 = fma(u[1], y, a1); a2 = fma(u[2], y, a2);
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) {

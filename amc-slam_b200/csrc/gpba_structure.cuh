@@ -1,0 +1,136 @@
+// gpba_structure.cuh -- P0 on the device: the index structures of one optimize() call.
+//
+// BlockSolver::buildStructure (Thirdparty/g2o/g2o/core/block_solver.hpp:142-295) walks every landmark's edge list
+// through std::map / unordered_map on one core; here the O(sum d^2) part -- which pairs of observations of a
+// landmark meet in which block -- is one radix sort.  Everything is integer work and deterministic (cub's radix sort
+// is stable), so the resulting pattern is bit-exact and the summation order of every block is fixed.
+//
+//   observations sorted by landmark  ->  k_emit_pairs      one (record pair key, observation pair) per unordered
+//                                                         pair of observations of a landmark (self pairs included)
+//                                    ->  cub radix sort    by record pair key
+//                                    ->  cub run-length    unique record pairs + their list offsets
+// The host then turns the (few) unique record pairs into the Hschur block pattern (pose pairs) and the per-block
+// contribution lists; see Solver::build_structure.
+#pragma once
+#include <cub/cub.cuh>
+#include "gpba_device.cuh"
+
+namespace gpba {
+
+// sorted (by landmark) copies of the per-observation inputs
+__global__ void k_gather_obs(int64_t n, const int64_t* __restrict__ o_orig, const double* __restrict__ u,
+                             const double* __restrict__ v, const double* __restrict__ ur, const double* __restrict__ w,
+                             const int* __restrict__ rec, const uint8_t* __restrict__ flags, double* __restrict__ su,
+                             double* __restrict__ sv, double* __restrict__ sur, double* __restrict__ sw,
+                             int* __restrict__ srec, uint8_t* __restrict__ sfl) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = o_orig[j];
+    su[j] = u[i]; sv[j] = v[i]; sw[j] = w[i]; srec[j] = rec[i]; sfl[j] = flags[i];
+    if (ur) sur[j] = ur[i];
+  }
+}
+
+__global__ void k_fill_lm(int n_lm, const int64_t* __restrict__ lm_obs_begin, int* __restrict__ o_lm) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int l = warp; l < n_lm; l += nw)
+    for (int64_t j = lm_obs_begin[l] + lane; j < lm_obs_begin[l + 1]; j += 32) o_lm[j] = l;
+}
+
+// One warp per landmark.  Observation pairs (a <= b, positions inside the landmark) are enumerated row by row;
+// the key orders the two records, the value keeps the observation of the smaller record first.
+// dup[0] is raised when two different observations of one landmark share a record (never produced by the reference:
+// a MapPoint holds one observation per keyframe and camera).
+__global__ void k_emit_pairs(int n_lm, const int64_t* __restrict__ lm_obs_begin, const int64_t* __restrict__ lm_pair_begin,
+                             const int* __restrict__ o_rec, unsigned long long n_rec, unsigned long long* __restrict__ keys,
+                             unsigned long long* __restrict__ vals, int* __restrict__ dup) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int l = warp; l < n_lm; l += nw) {
+    const int64_t ob = lm_obs_begin[l];
+    const int n = (int)(lm_obs_begin[l + 1] - ob);
+    const int64_t pb = lm_pair_begin[l];
+    const int np = n * (n + 1) / 2;
+    for (int idx = lane; idx < np; idx += 32) {
+      // idx = b*(b+1)/2 + a with a <= b
+      int b = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+      while ((b + 1) * (b + 2) / 2 <= idx) ++b;
+      while (b * (b + 1) / 2 > idx) --b;
+      const int a = idx - b * (b + 1) / 2;
+      const unsigned long long oa = (unsigned long long)(ob + a), obb = (unsigned long long)(ob + b);
+      const unsigned long long ra = (unsigned long long)o_rec[ob + a], rb = (unsigned long long)o_rec[ob + b];
+      if (a != b && ra == rb) atomicExch(dup, 1);
+      const bool swap = ra > rb;
+      keys[pb + idx] = swap ? rb * n_rec + ra : ra * n_rec + rb;
+      vals[pb + idx] = swap ? (obb << 32) | oa : (oa << 32) | obb;
+    }
+  }
+}
+
+// #(free pose, landmark) blocks of Hpl = _Hpl->nonZeroBlocks() (block_solver.hpp:206-254), only reported through
+// gpba_structure_info: per landmark the number of distinct free poses among its active observations.
+__global__ void k_count_hpl(DevView V, const int* __restrict__ o_rec, unsigned long long* __restrict__ total) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long cnt = 0;
+  for (int l = warp; l < V.n_lm; l += nw) {
+    const int64_t ob = V.lm_obs_begin[l];
+    const int m = 2 * (int)(V.lm_obs_begin[l + 1] - ob);
+    for (int j = lane; j < m; j += 32) {
+      const int r = o_rec[ob + (j >> 1)];
+      const int k = (j & 1) ? V.rec_kf2[r] : V.rec_kf1[r];
+      const int h = k >= 0 ? V.kf_h[k] : -1;
+      if (h < 0) continue;
+      bool first = true;
+      for (int q = 0; q < j && first; ++q) {
+        const int r2 = o_rec[ob + (q >> 1)];
+        const int k2 = (q & 1) ? V.rec_kf2[r2] : V.rec_kf1[r2];
+        if (k2 >= 0 && V.kf_h[k2] == h) first = false;
+      }
+      if (first) ++cnt;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0 && cnt) atomicAdd(total, cnt);
+}
+
+// cub temp storage that grows on demand
+struct CubTemp {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~CubTemp() { if (p) cudaFree(p); }
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+};
+
+static inline int bits_for(unsigned long long max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b)) ++b;
+  return b;
+}
+
+// keys/vals (n entries) -> sorted in place (through the alternate buffers), unique keys + run lengths.
+// Returns the number of unique keys in *h_runs (synchronises the stream).
+static inline cudaError_t sort_and_encode(CubTemp& tmp, unsigned long long*& keys, unsigned long long*& vals,
+                                          unsigned long long*& keys_alt, unsigned long long*& vals_alt, int64_t n, int key_bits,
+                                          unsigned long long* uniq, int* counts, int* d_runs, int* h_runs, cudaStream_t s) {
+  cub::DoubleBuffer<unsigned long long> dk(keys, keys_alt), dv(vals, vals_alt);
+  size_t need = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, key_bits, s);
+  if (e != cudaSuccess) return e;
+  if ((e = tmp.reserve(need)) != cudaSuccess) return e;
+  if ((e = cub::DeviceRadixSort::SortPairs(tmp.p, need, dk, dv, n, 0, key_bits, s)) != cudaSuccess) return e;
+  if (dk.Current() != keys) { std::swap(keys, keys_alt); }
+  if (dv.Current() != vals) { std::swap(vals, vals_alt); }
+  need = 0;
+  if ((e = cub::DeviceRunLengthEncode::Encode(nullptr, need, keys, uniq, counts, d_runs, n, s)) != cudaSuccess) return e;
+  if ((e = tmp.reserve(need)) != cudaSuccess) return e;
+  if ((e = cub::DeviceRunLengthEncode::Encode(tmp.p, need, keys, uniq, counts, d_runs, n, s)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(h_runs, d_runs, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
+}
+
+}  // namespace gpba
