@@ -512,18 +512,34 @@ int Solver::build_structure() {
     CK(cudaStreamSynchronize(stream));
     n_hpl = (int64_t)h;
   }
-  // --- work items of K4b: chunks of every record pair's list
-  const int CH = 256;
+  // --- work items of K4b: chunks of every record pair's list.  Items are issued in (block of 128 first records,
+  //     second record, first record) order: the U rows of a block's first records stay L2 resident while the second
+  //     records stream through once per block (row-major order re-read U ~13x from HBM: ncu dram__bytes_read 9.6 GB
+  //     for 0.7 GB of U at C4).
+  const int CH = 256, RB = 128;
   std::vector<int> item_rp;
   std::vector<int64_t> item_begin, item_end;
   std::vector<unsigned char> item_flags;
   {
-    int64_t off = 0;
-    for (int sidx = 0; sidx < n_rp; ++sidx) {
-      const int64_t c = rp_count[sidx];
+    std::vector<int64_t> rp_begin(n_rp + 1, 0);
+    for (int sidx = 0; sidx < n_rp; ++sidx) rp_begin[sidx + 1] = rp_begin[sidx] + rp_count[sidx];
+    std::vector<int> order(n_rp), cnt2;
+    for (int lo = 0; lo < n_rp;) {   // rp_key is ascending in (r1, r2): a block of first records is a contiguous range
+      const int blk = (int)(rp_key[lo] / (unsigned long long)n_rec) / RB;
+      int hi = lo;
+      while (hi < n_rp && (int)(rp_key[hi] / (unsigned long long)n_rec) / RB == blk) ++hi;
+      // stable bucket sort of [lo, hi) by the second record
+      cnt2.assign(n_rec + 1, 0);
+      for (int sidx = lo; sidx < hi; ++sidx) cnt2[(int)(rp_key[sidx] % (unsigned long long)n_rec) + 1]++;
+      for (int r = 0; r < n_rec; ++r) cnt2[r + 1] += cnt2[r];
+      for (int sidx = lo; sidx < hi; ++sidx) order[lo + cnt2[(int)(rp_key[sidx] % (unsigned long long)n_rec)]++] = sidx;
+      lo = hi;
+    }
+    for (int o = 0; o < n_rp; ++o) {
+      const int sidx = order[o];
+      const int64_t c = rp_count[sidx], off = rp_begin[sidx];
       const unsigned char fl = (unsigned char)(((rp_key[sidx] / (unsigned long long)n_rec == rp_key[sidx] % (unsigned long long)n_rec) ? 1 : 0) | (c > CH ? 2 : 0));
       for (int64_t b = 0; b < c; b += CH) { item_rp.push_back(sidx); item_begin.push_back(off + b); item_end.push_back(off + std::min<int64_t>(b + CH, c)); item_flags.push_back(fl); }
-      off += c;
     }
   }
   n_items = (int)item_rp.size();
@@ -588,13 +604,18 @@ int Solver::build_structure() {
   for (int i = 0; i < n_pose; ++i) pose_diag[i] = pp(i, i);
   for (int k = 0; k < n_hpp; ++k) hs_from[lookup(hs_rows, hs_ids, hpp_row[k], hpp_col[k])] = k;
   for (int k = 0; k < n_hs; ++k) if (hs_row[k] == hs_col[k]) hs_diag[k] = hs_row[k];
-  // --- K4c contribution lists: which record pairs feed which Hschur block (counting sort by block, stable)
+  // --- K4c contribution lists: which record pairs feed which Hschur block, as (left record slice, right record slice,
+  //     transpose flag); bucketed by block, then grouped by left record slice inside a block
   std::vector<int> con_begin(n_hs + 1, 0);
   std::vector<HsContrib> con;
   {
     struct Raw { int blk; HsContrib c; };
     std::vector<Raw> raw;
     raw.reserve((size_t)n_rp * 4);
+    auto emit = [&](int blk, int sidx, int rL, int aL, int rR, int aR, int tr, int gflag) {
+      raw.push_back({blk, HsContrib{sidx, rL, rR, aL | (aR << 1) | (tr << 2) | (gflag << 4)}});
+      con_begin[blk + 1]++;
+    };
     for (int sidx = 0; sidx < n_rp; ++sidx) {
       const int r1 = (int)(rp_key[sidx] / (unsigned long long)n_rec), r2 = (int)(rp_key[sidx] % (unsigned long long)n_rec);
       for (int a = 0; a < 2; ++a)
@@ -602,18 +623,28 @@ int Solver::build_structure() {
           if (r1 == r2 && a > b) continue;  // the mirror image of (b, a)
           const int pa = rec_pose(r1, a), pb = rec_pose(r2, b);
           if (pa < 0 || pb < 0) continue;
-          int mode = 0;
-          if (pa > pb) mode = 1; else if (pa == pb && r1 != r2) mode = 2;
           const int blk = lookup(hs_rows, hs_ids, std::min(pa, pb), std::max(pa, pb));
-          HsContrib c{sidx, r1, r2, a | (b << 1) | (mode << 2) | ((r1 == r2 && a == b) ? 16 : 0)};
-          raw.push_back({blk, c});
-          con_begin[blk + 1]++;
+          if (pa < pb) emit(blk, sidx, r1, a, r2, b, 0, 0);
+          else if (pa > pb) emit(blk, sidx, r2, b, r1, a, 1, 0);          // upper storage holds the transposed product
+          else if (r1 == r2) emit(blk, sidx, r1, a, r2, b, 0, 1);         // a == b: symmetric, carries g'_r for bschur
+          else { emit(blk, sidx, r1, a, r2, b, 0, 0); emit(blk, sidx, r2, b, r1, a, 1, 0); }  // both ordered pairs land in (pa, pa)
         }
     }
     for (int k = 0; k < n_hs; ++k) con_begin[k + 1] += con_begin[k];
     con.resize(raw.size());
     std::vector<int> cursor(con_begin.begin(), con_begin.end() - 1);
     for (const Raw& x : raw) con[cursor[x.blk]++] = x.c;
+    for (int k = 0; k < n_hs; ++k) {
+      HsContrib* lo = con.data() + con_begin[k];
+      HsContrib* hi = con.data() + con_begin[k + 1];
+      std::stable_sort(lo, hi, [](const HsContrib& x, const HsContrib& y) { return x.rL != y.rL ? x.rL < y.rL : (x.code & 1) < (y.code & 1); });
+      for (HsContrib* g = lo; g < hi;) {
+        HsContrib* ge = g;
+        while (ge < hi && ge->rL == g->rL && (ge->code & 1) == (g->code & 1)) ++ge;
+        g->code |= (int)(ge - g) << 8;
+        g = ge;
+      }
+    }
   }
   // --- record-major permutation (K2b): sorted-obs indices grouped by record (stable device sort), split into segments
   CKR(d_rperm.alloc(na));

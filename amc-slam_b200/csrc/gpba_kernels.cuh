@@ -582,53 +582,61 @@ __global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __r
 }
 
 // K4c: one CTA (144 threads = one per entry) per Hschur block (i, j), i <= j:
-//   Hs_ij = Hpp_ij (+ lambda on the diagonal) - sum over the block's contributions of M_r^(a)T C_(r,r') M_r'^(b)
-// in the fixed order of the contribution list (no atomics: the block is written once).  mode 1 adds the transposed
-// product (the pair was listed with its poses swapped), mode 2 the symmetrised one (both records touch pose i);
-// on diagonal blocks the diagonal record pairs also give bschur_i = b_p,i - sum M_r^(a)T g'_r.
-struct HsContrib { int rp; int r1; int r2; int code; };  // code: bit0 a, bit1 b, bits 2-3 mode, bit 4: diagonal record pair with a == b
+//   Hs_ij = Hpp_ij (+ lambda on the diagonal) - sum over the block's contributions of M_L^T C^ M_R
+// where L / R are the records (and their keyframe slice) touching pose i / pose j and C^ = C_(r1,r2) or its transpose
+// when the pair is listed the other way round.  Contributions are grouped by L on the host: T = sum_R C^ M_R (6 x 12)
+// is accumulated in registers (the two half-CTAs take alternate contributions; operands come through L1, only ~24
+// distinct M slices exist per block), and M_L^T T is formed once per group.  The block is written once, in a fixed
+// order: no atomics.  On diagonal blocks the diagonal record pairs also give bschur_i = b_p,i - sum M_L^T g'_r.
+struct HsContrib { int rp; int rL; int rR; int code; };  // code: bit0 slice of L, bit1 slice of R, bit2 transpose C, bit4 g' entry, bits 8.. group size (first entry)
 __global__ void __launch_bounds__(144) k_schur_expand(DevView V, double lambda, const double* __restrict__ rec,
                                                       const double* __restrict__ hpp, const double* __restrict__ bp,
                                                       const int* __restrict__ con_begin, const HsContrib* __restrict__ con,
                                                       const double* __restrict__ C, double* __restrict__ hs,
                                                       double* __restrict__ bs) {
-  __shared__ double sC[48], sMa[72], sMb[72], sT[72];
+  __shared__ double sT[2][72], sB[2][12];
   const int blk = blockIdx.x, tid = threadIdx.x;
+  const int half = tid / 72, t = tid % 72, m = t / 12, c = t % 12;
   const int i = tid / 12, j = tid % 12;
   const int src = V.hs_from_hpp[blk];
   const int diag = V.hs_diag_pose[blk];
   double acc = src >= 0 ? hpp[(size_t)src * 144 + tid] : 0.0;
   if (diag >= 0 && i == j) acc += lambda;
-  double bacc = (diag >= 0 && tid < 12) ? bp[(size_t)diag * 12 + tid] : 0.0;
-  for (int e = con_begin[blk]; e < con_begin[blk + 1]; ++e) {
-    const HsContrib cn = con[e];
-    const int a = cn.code & 1, b = (cn.code >> 1) & 1, mode = (cn.code >> 2) & 3;
-    if (tid < 48) sC[tid] = C[(size_t)cn.rp * GPBA_RP_STRIDE + tid];
-    if (tid < 72) sMa[tid] = rec[(size_t)cn.r1 * GPBA_REC_STRIDE + GPBA_REC_M + (tid / 12) * 24 + 12 * a + tid % 12];
-    else sMb[tid - 72] = rec[(size_t)cn.r2 * GPBA_REC_STRIDE + GPBA_REC_M + ((tid - 72) / 12) * 24 + 12 * b + (tid - 72) % 12];
-    __syncthreads();
-    if (tid < 72) {  // T = C M_b  (6 x 12)
-      const int m = tid / 12, c = tid % 12;
-      double s = 0.0;
+  double bpart = 0.0;
+  const int end = con_begin[blk + 1];
+  for (int e = con_begin[blk]; e < end;) {
+    const HsContrib g = con[e];
+    const int gs = g.code >> 8;
+    double tacc = 0.0;
+    for (int q = e + half; q < e + gs; q += 2) {
+      const HsContrib cn = con[q];
+      const double* Cp = C + (size_t)cn.rp * GPBA_RP_STRIDE;
+      const double* Mb = rec + (size_t)cn.rR * GPBA_REC_STRIDE + GPBA_REC_M + 12 * ((cn.code >> 1) & 1) + c;
+      const int sm = (cn.code & 4) ? 1 : 8, sn = (cn.code & 4) ? 8 : 1;  // C^[m][n] = C[n][m] when transposed
 #pragma unroll
-      for (int n = 0; n < 6; ++n) s = fma(sC[m * 8 + n], sMb[n * 12 + c], s);
-      sT[tid] = s;
+      for (int n = 0; n < 6; ++n) tacc = fma(Cp[m * sm + n * sn], Mb[n * 24], tacc);
+      if ((cn.code & 16) && t < 12) {
+        const double* Ma = rec + (size_t)cn.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (cn.code & 1) + t;
+#pragma unroll
+        for (int mm = 0; mm < 6; ++mm) bpart = fma(Ma[mm * 24], Cp[mm * 8 + 6], bpart);
+      }
     }
+    sT[half][t] = tacc;
     __syncthreads();
-    double p = 0.0, q = 0.0;  // P[i][j] and P[j][i], P = M_a^T T
+    const double* Ma = rec + (size_t)g.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (g.code & 1) + i;
+    double p = 0.0;
 #pragma unroll
-    for (int m = 0; m < 6; ++m) { p = fma(sMa[m * 12 + i], sT[m * 12 + j], p); q = fma(sMa[m * 12 + j], sT[m * 12 + i], q); }
-    acc -= mode == 0 ? p : (mode == 1 ? q : p + q);
-    if ((cn.code & 16) && tid < 12) {
-      double s = 0.0;
-#pragma unroll
-      for (int m = 0; m < 6; ++m) s = fma(sMa[m * 12 + tid], sC[m * 8 + 6], s);
-      bacc -= s;
-    }
+    for (int mm = 0; mm < 6; ++mm) p = fma(Ma[mm * 24], sT[0][mm * 12 + j] + sT[1][mm * 12 + j], p);
+    acc -= p;
     __syncthreads();
+    e += gs;
   }
   hs[(size_t)blk * 144 + tid] = acc;
-  if (diag >= 0 && tid < 12) bs[(size_t)diag * 12 + tid] = bacc;
+  if (diag >= 0) {
+    if (t < 12) sB[half][t] = bpart;
+    __syncthreads();
+    if (tid < 12) bs[(size_t)diag * 12 + tid] = bp[(size_t)diag * 12 + tid] - (sB[0][tid] + sB[1][tid]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K6
