@@ -305,7 +305,7 @@ int Solver::init(const gpba_problem* P, int dev) {
   CKR(d_all_u.upload(P->obs_u, (size_t)n_obs, stream)); CKR(d_all_v.upload(P->obs_v, (size_t)n_obs, stream));
   CKR(d_all_w.upload(P->obs_inv_sigma2, (size_t)n_obs, stream));
   if (stereo) CKR(d_all_ur.upload(P->obs_ur, (size_t)n_obs, stream));
-  CKR(d_scal.alloc(8)); CKR(d_fail.alloc(1));
+  CKR(d_scal.alloc(8)); CKR(d_fail.alloc(2));  // [0] failure flag, [1] work counter of K4b
   CKR(d_rec.alloc((size_t)n_rec * GPBA_REC_STRIDE)); CKR(d_rec_lite.alloc((size_t)n_rec * GPBA_REC_LITE_STRIDE));
   CKR(d_recS.alloc((size_t)n_rec * 27)); CKR(d_Y.alloc((size_t)n_rec * 6));
   CKR(d_prior_rho.alloc((size_t)n_prior + n_velp));
@@ -445,14 +445,18 @@ int Solver::build_structure() {
   for (int l = 0; l < n_lm; ++l) { const int64_t n = lm_obs_begin[l + 1] - lm_obs_begin[l]; lm_pair_begin[l + 1] = lm_pair_begin[l] + n * (n + 1) / 2; }
   n_pairs = lm_pair_begin[n_lm];
   std::vector<unsigned long long> rp_key;   // unique record pairs of the compute list, ascending
-  std::vector<int> rp_count;
-  const int key_bits = bits_for((unsigned long long)n_rec * (unsigned long long)n_rec);
-  auto pair_pass = [&](int nl, const DBuf<int64_t>& d_lob, const std::vector<int64_t>& lpb, const int* d_rec_sorted, bool keep_pairs,
-                       std::vector<unsigned long long>& keys_out, std::vector<int>* counts_out) -> int {
+  const unsigned long long nrec2 = (unsigned long long)n_rec * (unsigned long long)n_rec;
+  const int LM_CHUNK = 8192;                // landmarks per chunk: ~12 MB of U rows at 10 observations per landmark
+  // One pass = emit + sort + run-length encode.  with_items: runs of (chunk, record pair) become the work items of K4b
+  // and the sorted observation pairs are kept; otherwise only the unique record pairs are wanted (pattern).
+  auto pair_pass = [&](int nl, const DBuf<int64_t>& d_lob, const std::vector<int64_t>& lpb, const int* d_rec_sorted, bool with_items,
+                       std::vector<unsigned long long>& keys_out) -> int {
     const int64_t np = lpb[nl];
     keys_out.clear();
-    if (counts_out) counts_out->clear();
+    if (with_items) { n_items = 0; n_rp = 0; }
     if (np == 0) return GPBA_OK;
+    const int chunk = with_items ? LM_CHUNK : 0;
+    const unsigned long long n_chunks = chunk ? (unsigned long long)((nl + chunk - 1) / chunk) : 1ull;
     DBuf<int64_t> d_lpb;
     DBuf<unsigned long long> k0, k1, v0, v1, uq;
     DBuf<int> cnt, runs, dup;
@@ -460,26 +464,56 @@ int Solver::build_structure() {
     CKR(k0.alloc((size_t)np)); CKR(k1.alloc((size_t)np)); CKR(v0.alloc((size_t)np)); CKR(v1.alloc((size_t)np));
     CKR(uq.alloc((size_t)np)); CKR(cnt.alloc((size_t)np)); CKR(runs.alloc(1)); CKR(dup.alloc(1));
     CK(cudaMemsetAsync(dup.p, 0, sizeof(int), stream));
-    k_emit_pairs<<<std::min((nl + 7) / 8, 148 * 16), 256, 0, stream>>>(nl, d_lob.p, d_lpb.p, d_rec_sorted, (unsigned long long)n_rec, k0.p, v0.p, dup.p);
+    k_emit_pairs<<<std::min((nl + 7) / 8, 148 * 16), 256, 0, stream>>>(nl, d_lob.p, d_lpb.p, d_rec_sorted, (unsigned long long)n_rec, chunk, k0.p, v0.p, dup.p);
     CK(cudaGetLastError());
     int h_runs = 0;
     unsigned long long *pk = k0.p, *pv = v0.p, *pka = k1.p, *pva = v1.p;
-    CK(sort_and_encode(cub_tmp, pk, pv, pka, pva, np, key_bits, uq.p, cnt.p, runs.p, &h_runs, stream));
-    keys_out.resize(h_runs);
-    CK(cudaMemcpyAsync(keys_out.data(), uq.p, sizeof(unsigned long long) * h_runs, cudaMemcpyDeviceToHost, stream));
-    if (counts_out) { counts_out->resize(h_runs); CK(cudaMemcpyAsync(counts_out->data(), cnt.p, sizeof(int) * h_runs, cudaMemcpyDeviceToHost, stream)); }
+    CK(sort_and_encode(cub_tmp, pk, pv, pka, pva, np, bits_for(n_chunks * nrec2), uq.p, cnt.p, runs.p, &h_runs, stream));
+    if (!with_items) {
+      keys_out.resize(h_runs);
+      CK(cudaMemcpyAsync(keys_out.data(), uq.p, sizeof(unsigned long long) * h_runs, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      return GPBA_OK;
+    }
     int h_dup = 0;
     CK(cudaMemcpyAsync(&h_dup, dup.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    if (keep_pairs) {
-      CKR(d_pairs.alloc((size_t)np));
-      CK(cudaMemcpyAsync(d_pairs.p, pv, sizeof(unsigned long long) * (size_t)np, cudaMemcpyDeviceToDevice, stream));
-    }
+    CKR(d_pairs.alloc((size_t)np));
+    CK(cudaMemcpyAsync(d_pairs.p, pv, sizeof(unsigned long long) * (size_t)np, cudaMemcpyDeviceToDevice, stream));
+    // items = runs; slot of an item = rank of its record pair among the unique record pairs
+    const int ni = h_runs, gi = (ni + 255) / 256;
+    DBuf<unsigned long long> low, low_s, rpk;
+    DBuf<int> idx, idx_s, head, slot_p1;
+    DBuf<int64_t> beg;
+    CKR(low.alloc(ni)); CKR(low_s.alloc(ni)); CKR(rpk.alloc(ni)); CKR(idx.alloc(ni)); CKR(idx_s.alloc(ni)); CKR(head.alloc(ni)); CKR(slot_p1.alloc(ni)); CKR(beg.alloc(ni));
+    CKR(d_item_rp.alloc(ni)); CKR(d_item_flags.alloc(ni)); CKR(d_item_begin.alloc(ni)); CKR(d_item_end.alloc(ni));
+    k_item_low<<<gi, 256, 0, stream>>>(ni, uq.p, nrec2, low.p, idx.p);
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, low.p, low_s.p, idx.p, idx_s.p, ni, 0, bits_for(nrec2), stream));
+    CK(cub_tmp.reserve(need));
+    CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, low.p, low_s.p, idx.p, idx_s.p, ni, 0, bits_for(nrec2), stream));
+    k_slot_heads<<<gi, 256, 0, stream>>>(ni, low_s.p, head.p);
+    need = 0;
+    CK(cub::DeviceScan::InclusiveSum(nullptr, need, head.p, slot_p1.p, ni, stream));
+    CK(cub_tmp.reserve(need));
+    CK(cub::DeviceScan::InclusiveSum(cub_tmp.p, need, head.p, slot_p1.p, ni, stream));
+    k_slot_assign<<<gi, 256, 0, stream>>>(ni, low_s.p, idx_s.p, head.p, slot_p1.p, (unsigned long long)n_rec, d_item_rp.p, d_item_flags.p, rpk.p);
+    need = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, cnt.p, beg.p, ni, stream));
+    CK(cub_tmp.reserve(need));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, need, cnt.p, beg.p, ni, stream));
+    k_item_ranges<<<gi, 256, 0, stream>>>(ni, beg.p, cnt.p, d_item_begin.p, d_item_end.p);
+    CK(cudaGetLastError());
+    int h_nrp = 0;
+    CK(cudaMemcpyAsync(&h_nrp, slot_p1.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    if (keep_pairs && h_dup) { g_err = "two observations of one landmark share a (keyframe pair, camera) record"; return GPBA_ERR_INVALID; }
+    if (h_dup) { g_err = "two observations of one landmark share a (keyframe pair, camera) record"; return GPBA_ERR_INVALID; }
+    keys_out.resize(h_nrp);
+    CK(cudaMemcpyAsync(keys_out.data(), rpk.p, sizeof(unsigned long long) * h_nrp, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    n_items = ni; n_rp = h_nrp;
     return GPBA_OK;
   };
-  CKR(pair_pass(n_lm, d_lm_obs_begin, lm_pair_begin, d_o_rec.p, true, rp_key, &rp_count));
-  n_rp = (int)rp_key.size();
+  CKR(pair_pass(n_lm, d_lm_obs_begin, lm_pair_begin, d_o_rec.p, true, rp_key));
   // pattern keys: all edges (any level) of all active landmarks (block_solver.hpp:262-288) -- a second, key-only pass
   // when that set differs from the compute list (level-1 edges, or landmarks owned by other ranks)
   std::vector<unsigned long long> pat_key_store;
@@ -497,7 +531,7 @@ int Solver::build_structure() {
     for (int l = 0; l < n_lm_all; ++l) { const int64_t n = lob[l + 1] - lob[l]; lpb[l + 1] = lpb[l] + n * (n + 1) / 2; }
     DBuf<int64_t> d_lob; DBuf<int> d_recs;
     CKR(d_lob.upload(lob, stream)); CKR(d_recs.upload(recs, stream));
-    CKR(pair_pass(n_lm_all, d_lob, lpb, d_recs.p, false, pat_key_store, nullptr));
+    CKR(pair_pass(n_lm_all, d_lob, lpb, d_recs.p, false, pat_key_store));
     pat_key = &pat_key_store;
   }
   // --- #Hpl blocks (reported only)
@@ -512,37 +546,6 @@ int Solver::build_structure() {
     CK(cudaStreamSynchronize(stream));
     n_hpl = (int64_t)h;
   }
-  // --- work items of K4b: chunks of every record pair's list.  Items are issued in (block of 128 first records,
-  //     second record, first record) order: the U rows of a block's first records stay L2 resident while the second
-  //     records stream through once per block (row-major order re-read U ~13x from HBM: ncu dram__bytes_read 9.6 GB
-  //     for 0.7 GB of U at C4).
-  const int CH = 256, RB = 128;
-  std::vector<int> item_rp;
-  std::vector<int64_t> item_begin, item_end;
-  std::vector<unsigned char> item_flags;
-  {
-    std::vector<int64_t> rp_begin(n_rp + 1, 0);
-    for (int sidx = 0; sidx < n_rp; ++sidx) rp_begin[sidx + 1] = rp_begin[sidx] + rp_count[sidx];
-    std::vector<int> order(n_rp), cnt2;
-    for (int lo = 0; lo < n_rp;) {   // rp_key is ascending in (r1, r2): a block of first records is a contiguous range
-      const int blk = (int)(rp_key[lo] / (unsigned long long)n_rec) / RB;
-      int hi = lo;
-      while (hi < n_rp && (int)(rp_key[hi] / (unsigned long long)n_rec) / RB == blk) ++hi;
-      // stable bucket sort of [lo, hi) by the second record
-      cnt2.assign(n_rec + 1, 0);
-      for (int sidx = lo; sidx < hi; ++sidx) cnt2[(int)(rp_key[sidx] % (unsigned long long)n_rec) + 1]++;
-      for (int r = 0; r < n_rec; ++r) cnt2[r + 1] += cnt2[r];
-      for (int sidx = lo; sidx < hi; ++sidx) order[lo + cnt2[(int)(rp_key[sidx] % (unsigned long long)n_rec)]++] = sidx;
-      lo = hi;
-    }
-    for (int o = 0; o < n_rp; ++o) {
-      const int sidx = order[o];
-      const int64_t c = rp_count[sidx], off = rp_begin[sidx];
-      const unsigned char fl = (unsigned char)(((rp_key[sidx] / (unsigned long long)n_rec == rp_key[sidx] % (unsigned long long)n_rec) ? 1 : 0) | (c > CH ? 2 : 0));
-      for (int64_t b = 0; b < c; b += CH) { item_rp.push_back(sidx); item_begin.push_back(off + b); item_end.push_back(off + std::min<int64_t>(b + CH, c)); item_flags.push_back(fl); }
-    }
-  }
-  n_items = (int)item_rp.size();
   // --- Hpp pattern (upper): diagonals + priors + the keyframe pair of every record with an active edge
   std::vector<std::vector<int>> pp_rows(n_pose), hs_rows;
   auto add_pair = [](std::vector<std::vector<int>>& rows, int a, int b) {
@@ -672,8 +675,6 @@ int Solver::build_structure() {
   CKR(d_prior_hpp11.upload(pr11, stream)); CKR(d_prior_hpp12.upload(pr12, stream)); CKR(d_prior_hpp22.upload(pr22, stream));
   CKR(d_pose_hpp_diag.upload(pose_diag, stream)); CKR(d_hs_from_hpp.upload(hs_from, stream)); CKR(d_hs_diag_pose.upload(hs_diag, stream));
   CKR(d_hs_row.upload(hs_row, stream)); CKR(d_hs_col.upload(hs_col, stream));
-  CKR(d_item_rp.upload(item_rp, stream)); CKR(d_item_begin.upload(item_begin, stream)); CKR(d_item_end.upload(item_end, stream));
-  CKR(d_item_flags.upload(item_flags, stream));
   CKR(d_con_begin.upload(con_begin, stream)); CKR(d_con.upload(con, stream));
   // --- storage
   CKR(d_ptS[0].alloc((size_t)n_lm * 3)); CKR(d_ptS[1].alloc((size_t)n_lm * 3));
@@ -933,8 +934,10 @@ int Solver::solve(double lambda, bool* ok) {
   int launches = 0;
   if (n_items > 0) {
     CK(cudaMemsetAsync(d_C.p, 0, sizeof(double) * (size_t)n_rp * GPBA_RP_STRIDE, stream));
-    k_schur_pairs<<<std::min((n_items + 3) / 4, 148 * 16), 128, 0, stream>>>(n_items, d_item_rp.p, d_item_begin.p, d_item_end.p, d_item_flags.p,
-                                                                             d_pairs.p, d_o_lm.p, d_U.p, d_ptL.p, d_C.p);
+    CK(cudaMemsetAsync(d_fail.p + 1, 0, sizeof(int), stream));
+    static const int pairs_ctas_per_sm = getenv("GPBA_PAIRS_CTAS") ? atoi(getenv("GPBA_PAIRS_CTAS")) : 16;
+    k_schur_pairs<<<std::min((n_items + 3) / 4, 148 * pairs_ctas_per_sm), 128, 0, stream>>>(n_items, d_item_rp.p, d_item_begin.p, d_item_end.p, d_item_flags.p,
+                                                                             d_pairs.p, d_o_lm.p, d_U.p, d_ptL.p, d_C.p, d_fail.p + 1);
     CK(cudaGetLastError());
     ++launches;
   }

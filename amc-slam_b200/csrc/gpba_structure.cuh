@@ -40,8 +40,10 @@ __global__ void k_fill_lm(int n_lm, const int64_t* __restrict__ lm_obs_begin, in
 // the key orders the two records, the value keeps the observation of the smaller record first.
 // dup[0] is raised when two different observations of one landmark share a record (never produced by the reference:
 // a MapPoint holds one observation per keyframe and camera).
+// The key is (landmark chunk, record pair): work items of K4b are then (chunk, record pair) runs, so that the U rows
+// of one chunk of landmarks (a few MB) serve all their ~11 uses from L2 before the next chunk is touched.
 __global__ void k_emit_pairs(int n_lm, const int64_t* __restrict__ lm_obs_begin, const int64_t* __restrict__ lm_pair_begin,
-                             const int* __restrict__ o_rec, unsigned long long n_rec, unsigned long long* __restrict__ keys,
+                             const int* __restrict__ o_rec, unsigned long long n_rec, int lm_chunk, unsigned long long* __restrict__ keys,
                              unsigned long long* __restrict__ vals, int* __restrict__ dup) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
   for (int l = warp; l < n_lm; l += nw) {
@@ -59,7 +61,8 @@ __global__ void k_emit_pairs(int n_lm, const int64_t* __restrict__ lm_obs_begin,
       const unsigned long long ra = (unsigned long long)o_rec[ob + a], rb = (unsigned long long)o_rec[ob + b];
       if (a != b && ra == rb) atomicExch(dup, 1);
       const bool swap = ra > rb;
-      keys[pb + idx] = swap ? rb * n_rec + ra : ra * n_rec + rb;
+      const unsigned long long chunk = lm_chunk > 0 ? (unsigned long long)(l / lm_chunk) : 0ull;
+      keys[pb + idx] = chunk * n_rec * n_rec + (swap ? rb * n_rec + ra : ra * n_rec + rb);
       vals[pb + idx] = swap ? (obb << 32) | oa : (oa << 32) | obb;
     }
   }
@@ -89,6 +92,34 @@ __global__ void k_count_hpl(DevView V, const int* __restrict__ o_rec, unsigned l
   }
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0 && cnt) atomicAdd(total, cnt);
+}
+
+// run keys (chunk, r1, r2) -> record pair part; idx = iota
+__global__ void k_item_low(int n, const unsigned long long* __restrict__ run_key, unsigned long long nrec2,
+                           unsigned long long* __restrict__ low, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { low[i] = run_key[i] % nrec2; idx[i] = i; }
+}
+__global__ void k_slot_heads(int n, const unsigned long long* __restrict__ low_sorted, int* __restrict__ head) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) head[p] = (p == 0 || low_sorted[p] != low_sorted[p - 1]) ? 1 : 0;
+}
+// slot of every item (= rank of its record pair among the unique record pairs), the unique record pairs themselves
+__global__ void k_slot_assign(int n, const unsigned long long* __restrict__ low_sorted, const int* __restrict__ idx_sorted,
+                              const int* __restrict__ head, const int* __restrict__ slot_p1, unsigned long long n_rec,
+                              int* __restrict__ item_rp, unsigned char* __restrict__ item_flags, unsigned long long* __restrict__ rp_key) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int slot = slot_p1[p] - 1;
+  const unsigned long long k = low_sorted[p];
+  item_rp[idx_sorted[p]] = slot;
+  item_flags[idx_sorted[p]] = (unsigned char)(((k / n_rec == k % n_rec) ? 1 : 0) | 2);  // several chunks feed one slot: accumulate atomically
+  if (head[p]) rp_key[slot] = k;
+}
+__global__ void k_item_ranges(int n, const int64_t* __restrict__ begin_excl, const int* __restrict__ count, int64_t* __restrict__ item_begin,
+                              int64_t* __restrict__ item_end) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { item_begin[i] = begin_excl[i]; item_end[i] = begin_excl[i] + count[i]; }
 }
 
 // cub temp storage that grows on demand
