@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 #include <dlfcn.h>
+#include <chrono>
 
 using namespace gpba;
 
@@ -39,17 +40,23 @@ static thread_local std::string g_err;
 
 namespace {
 
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync) on the handle's stream: the pool
+// keeps freed blocks, so building the structures of the next optimize() call does not pay cudaMalloc / cudaFree again
+// (they were ~200 ms of a 380 ms build_structure at C4).  g_alloc_stream is set by every entry point of a handle.
+static thread_local cudaStream_t g_alloc_stream = nullptr;
 template <typename T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t owner = nullptr;
   ~DBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) cudaFreeAsync(p, owner); p = nullptr; n = 0; }
   int alloc(size_t count) {
     if (count <= n && p) return GPBA_OK;
     release();
     if (count == 0) count = 1;
-    CK(cudaMalloc(&p, count * sizeof(T)));
+    owner = g_alloc_stream;
+    CK(cudaMallocAsync(&p, count * sizeof(T), owner));
     n = count;
     return GPBA_OK;
   }
@@ -90,8 +97,14 @@ static NcclApi g_nccl;
 struct NcclId { char internal[128]; };
 typedef int (*ncclCommInitRank_t)(ncclComm_t*, int, NcclId, int);
 
+struct StreamHolder {
+  cudaStream_t s = nullptr;
+  ~StreamHolder() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+};
+
 struct Solver {
   int device = 0;
+  StreamHolder stream_holder;   // first member: destroyed after every buffer has been returned to the pool
   cudaStream_t stream = nullptr;
   // ------------------------------------------------------------------ host copy of the problem
   int n_cam = 0, n_kf = 0, n_pt = 0, n_rec = 0, n_prior = 0, n_velp = 0;
@@ -191,7 +204,8 @@ struct Solver {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    if (stream) cudaStreamDestroy(stream);
+    // the DBuf members free into `stream` after this body ran: the stream object itself is released by StreamHolder,
+    // which is declared first and therefore destroyed last
   }
 
   // stage timing helpers
@@ -248,6 +262,14 @@ int Solver::init(const gpba_problem* P, int dev) {
   device = dev;
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  stream_holder.s = stream;
+  g_alloc_stream = stream;
+  {
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;   // never hand memory back to the driver between optimize() calls
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   CK(cudaEventCreate(&ev0));
   CK(cudaEventCreate(&ev1));
   CK(cudaMallocHost(&h_scal, 8 * sizeof(double)));
@@ -353,6 +375,16 @@ __global__ void k_scatter_pts(int n_lm, const int* __restrict__ lm_pt, const dou
 // bucket passes and the (small) pose-level patterns; the O(sum d^2) pairing runs on the device (gpba_structure.cuh).
 int Solver::build_structure() {
   CK(cudaSetDevice(device));
+  g_alloc_stream = stream;
+  const bool verbose = getenv("GPBA_VERBOSE") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    cudaStreamSynchronize(stream);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gpba] build_structure %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tp0).count());
+    tp0 = now;
+  };
   if (structure_ok && n_lm > 0) CKR(scatter_points(cur));  // keep d_pt_full current before re-sorting
   // --- active set (edge active iff level 0; vertex active iff it has an active edge)
   std::vector<char> kf_act(n_kf, 0), pt_act(n_pt, 0), rec_used(n_rec, 0);
@@ -389,6 +421,7 @@ int Solver::build_structure() {
     for (int p = 0; p < n_pt; ++p)
       if (pt_act[p]) { rank_of_pt[p] = g++; const int l = bucket[first_kf[p]]++; all_lm_pt[l] = p; pt_lm_all[p] = l; }  // g2o landmark index = rank among active points
   }
+  lap("active set + landmark order");
   // --- multi-GPU: this rank owns a contiguous range of the sorted landmarks, balanced by observation count;
   //     patterns (Hpp, Hschur) are built from ALL landmarks so that every rank packs the same block list
   int own_lo = 0, own_hi = n_lm_all;
@@ -426,6 +459,7 @@ int Solver::build_structure() {
     }
   }
   for (int r = 0; r < n_rec; ++r) rcount[r + 1] += rcount[r];
+  lap("observation bucket sort");
   // --- device: sorted observation arrays
   CKR(d_kf_h.upload(kf_h, stream));
   CKR(d_o_orig.upload(o_orig, stream)); CKR(d_lm_obs_begin.upload(lm_obs_begin, stream)); CKR(d_lm_pt.upload(lm_pt, stream));
@@ -440,6 +474,7 @@ int Solver::build_structure() {
     k_fill_lm<<<std::min((n_lm + 7) / 8, 148 * 16), 256, 0, stream>>>(n_lm, d_lm_obs_begin.p, d_o_lm.p);
     CK(cudaGetLastError());
   }
+  lap("upload + gather");
   // --- device: observation pairs grouped by record pair
   std::vector<int64_t> lm_pair_begin(n_lm + 1, 0);
   for (int l = 0; l < n_lm; ++l) { const int64_t n = lm_obs_begin[l + 1] - lm_obs_begin[l]; lm_pair_begin[l + 1] = lm_pair_begin[l] + n * (n + 1) / 2; }
@@ -489,17 +524,17 @@ int Solver::build_structure() {
     k_item_low<<<gi, 256, 0, stream>>>(ni, uq.p, nrec2, low.p, idx.p);
     size_t need = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, need, low.p, low_s.p, idx.p, idx_s.p, ni, 0, bits_for(nrec2), stream));
-    CK(cub_tmp.reserve(need));
+    CK(cub_tmp.reserve(need, stream));
     CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, low.p, low_s.p, idx.p, idx_s.p, ni, 0, bits_for(nrec2), stream));
     k_slot_heads<<<gi, 256, 0, stream>>>(ni, low_s.p, head.p);
     need = 0;
     CK(cub::DeviceScan::InclusiveSum(nullptr, need, head.p, slot_p1.p, ni, stream));
-    CK(cub_tmp.reserve(need));
+    CK(cub_tmp.reserve(need, stream));
     CK(cub::DeviceScan::InclusiveSum(cub_tmp.p, need, head.p, slot_p1.p, ni, stream));
     k_slot_assign<<<gi, 256, 0, stream>>>(ni, low_s.p, idx_s.p, head.p, slot_p1.p, (unsigned long long)n_rec, d_item_rp.p, d_item_flags.p, rpk.p);
     need = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, need, cnt.p, beg.p, ni, stream));
-    CK(cub_tmp.reserve(need));
+    CK(cub_tmp.reserve(need, stream));
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, need, cnt.p, beg.p, ni, stream));
     k_item_ranges<<<gi, 256, 0, stream>>>(ni, beg.p, cnt.p, d_item_begin.p, d_item_end.p);
     CK(cudaGetLastError());
@@ -534,6 +569,7 @@ int Solver::build_structure() {
     CKR(pair_pass(n_lm_all, d_lob, lpb, d_recs.p, false, pat_key_store));
     pat_key = &pat_key_store;
   }
+  lap("pair sort");
   // --- #Hpl blocks (reported only)
   fill_view();
   {
@@ -546,6 +582,7 @@ int Solver::build_structure() {
     CK(cudaStreamSynchronize(stream));
     n_hpl = (int64_t)h;
   }
+  lap("hpl count");
   // --- Hpp pattern (upper): diagonals + priors + the keyframe pair of every record with an active edge
   std::vector<std::vector<int>> pp_rows(n_pose), hs_rows;
   auto add_pair = [](std::vector<std::vector<int>>& rows, int a, int b) {
@@ -607,59 +644,67 @@ int Solver::build_structure() {
   for (int i = 0; i < n_pose; ++i) pose_diag[i] = pp(i, i);
   for (int k = 0; k < n_hpp; ++k) hs_from[lookup(hs_rows, hs_ids, hpp_row[k], hpp_col[k])] = k;
   for (int k = 0; k < n_hs; ++k) if (hs_row[k] == hs_col[k]) hs_diag[k] = hs_row[k];
+  lap("patterns");
   // --- K4c contribution lists: which record pairs feed which Hschur block, as (left record slice, right record slice,
   //     transpose flag); bucketed by block, then grouped by left record slice inside a block
   std::vector<int> con_begin(n_hs + 1, 0);
   std::vector<HsContrib> con;
   {
-    struct Raw { int blk; HsContrib c; };
-    std::vector<Raw> raw;
-    raw.reserve((size_t)n_rp * 4);
-    auto emit = [&](int blk, int sidx, int rL, int aL, int rR, int aR, int tr, int gflag) {
-      raw.push_back({blk, HsContrib{sidx, rL, rR, aL | (aR << 1) | (tr << 2) | (gflag << 4)}});
-      con_begin[blk + 1]++;
-    };
-    for (int sidx = 0; sidx < n_rp; ++sidx) {
-      const int r1 = (int)(rp_key[sidx] / (unsigned long long)n_rec), r2 = (int)(rp_key[sidx] % (unsigned long long)n_rec);
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-          if (r1 == r2 && a > b) continue;  // the mirror image of (b, a)
-          const int pa = rec_pose(r1, a), pb = rec_pose(r2, b);
-          if (pa < 0 || pb < 0) continue;
-          const int blk = lookup(hs_rows, hs_ids, std::min(pa, pb), std::max(pa, pb));
-          if (pa < pb) emit(blk, sidx, r1, a, r2, b, 0, 0);
-          else if (pa > pb) emit(blk, sidx, r2, b, r1, a, 1, 0);          // upper storage holds the transposed product
-          else if (r1 == r2) emit(blk, sidx, r1, a, r2, b, 0, 1);         // a == b: symmetric, carries g'_r for bschur
-          else { emit(blk, sidx, r1, a, r2, b, 0, 0); emit(blk, sidx, r2, b, r1, a, 1, 0); }  // both ordered pairs land in (pa, pa)
-        }
+    // pass 0 counts, pass 1 fills (same enumeration)
+    std::vector<int> cursor;
+    for (int pass = 0; pass < 2; ++pass) {
+      auto emit = [&](int blk, int sidx, int rL, int aL, int rR, int aR, int tr, int gflag) {
+        if (pass == 0) con_begin[blk + 1]++;
+        else con[cursor[blk]++] = HsContrib{sidx, rL, rR, aL | (aR << 1) | (tr << 2) | (gflag << 4)};
+      };
+      for (int sidx = 0; sidx < n_rp; ++sidx) {
+        const int r1 = (int)(rp_key[sidx] / (unsigned long long)n_rec), r2 = (int)(rp_key[sidx] % (unsigned long long)n_rec);
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            if (r1 == r2 && a > b) continue;  // the mirror image of (b, a)
+            const int pa = rec_pose(r1, a), pb = rec_pose(r2, b);
+            if (pa < 0 || pb < 0) continue;
+            const int blk = lookup(hs_rows, hs_ids, std::min(pa, pb), std::max(pa, pb));
+            if (pa < pb) emit(blk, sidx, r1, a, r2, b, 0, 0);
+            else if (pa > pb) emit(blk, sidx, r2, b, r1, a, 1, 0);          // upper storage holds the transposed product
+            else if (r1 == r2) emit(blk, sidx, r1, a, r2, b, 0, 1);         // a == b: symmetric, carries g'_r for bschur
+            else { emit(blk, sidx, r1, a, r2, b, 0, 0); emit(blk, sidx, r2, b, r1, a, 1, 0); }  // both ordered pairs land in (pa, pa)
+          }
+      }
+      if (pass == 0) {
+        for (int k = 0; k < n_hs; ++k) con_begin[k + 1] += con_begin[k];
+        con.resize((size_t)con_begin[n_hs]);
+        cursor.assign(con_begin.begin(), con_begin.end() - 1);
+      }
     }
-    for (int k = 0; k < n_hs; ++k) con_begin[k + 1] += con_begin[k];
-    con.resize(raw.size());
-    std::vector<int> cursor(con_begin.begin(), con_begin.end() - 1);
-    for (const Raw& x : raw) con[cursor[x.blk]++] = x.c;
-    for (int k = 0; k < n_hs; ++k) {
+    for (int k = 0; k < n_hs; ++k) {   // group by left record slice (stable insertion sort: the lists are short)
       HsContrib* lo = con.data() + con_begin[k];
-      HsContrib* hi = con.data() + con_begin[k + 1];
-      std::stable_sort(lo, hi, [](const HsContrib& x, const HsContrib& y) { return x.rL != y.rL ? x.rL < y.rL : (x.code & 1) < (y.code & 1); });
-      for (HsContrib* g = lo; g < hi;) {
-        HsContrib* ge = g;
-        while (ge < hi && ge->rL == g->rL && (ge->code & 1) == (g->code & 1)) ++ge;
-        g->code |= (int)(ge - g) << 8;
+      const int n = con_begin[k + 1] - con_begin[k];
+      auto key = [](const HsContrib& x) { return ((long long)x.rL << 1) | (x.code & 1); };
+      for (int q = 1; q < n; ++q) {
+        const HsContrib x = lo[q];
+        int w = q;
+        while (w > 0 && key(lo[w - 1]) > key(x)) { lo[w] = lo[w - 1]; --w; }
+        lo[w] = x;
+      }
+      for (int g = 0; g < n;) {
+        int ge = g;
+        while (ge < n && key(lo[ge]) == key(lo[g])) ++ge;
+        lo[g].code |= (ge - g) << 8;
         g = ge;
       }
     }
   }
+  lap("contribution lists");
   // --- record-major permutation (K2b): sorted-obs indices grouped by record (stable device sort), split into segments
   CKR(d_rperm.alloc(na));
   if (n_aobs > 0) {
-    DBuf<int> kin, kout; DBuf<int64_t> vin;
+    DBuf<int> kout; DBuf<int64_t> vin;
     CKR(kout.alloc(na)); CKR(vin.alloc(na));
-    std::vector<int64_t> iota((size_t)n_aobs);
-    for (int64_t j = 0; j < n_aobs; ++j) iota[j] = j;
-    CKR(vin.upload(iota, stream));
+    k_iota<<<gobs, 256, 0, stream>>>(n_aobs, vin.p);
     size_t need = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, need, d_o_rec.p, kout.p, vin.p, d_rperm.p, n_aobs, 0, bits_for((unsigned long long)n_rec), stream));
-    CK(cub_tmp.reserve(need));
+    CK(cub_tmp.reserve(need, stream));
     CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, d_o_rec.p, kout.p, vin.p, d_rperm.p, n_aobs, 0, bits_for((unsigned long long)n_rec), stream));
     CK(cudaStreamSynchronize(stream));
   }
@@ -669,6 +714,7 @@ int Solver::build_structure() {
     for (int64_t b = rcount[r]; b < rcount[r + 1]; b += SEG) { rseg_rec.push_back(r); rseg_begin.push_back(b); }
   rseg_begin.push_back(n_aobs);
   n_rseg = (int)rseg_rec.size();
+  lap("record-major permutation");
   // --- upload
   CKR(d_rseg_rec.upload(rseg_rec, stream)); CKR(d_rseg_begin.upload(rseg_begin, stream));
   CKR(d_rec_hpp11.upload(rec11, stream)); CKR(d_rec_hpp12.upload(rec12, stream)); CKR(d_rec_hpp22.upload(rec22, stream));
@@ -694,9 +740,11 @@ int Solver::build_structure() {
   // both state buffers must agree on fixed / inactive vertices
   CK(cudaMemcpyAsync(d_pose[1 - cur].p, d_pose[cur].p, sizeof(double) * 7 * (size_t)n_kf, cudaMemcpyDeviceToDevice, stream));
   CK(cudaMemcpyAsync(d_vel[1 - cur].p, d_vel[cur].p, sizeof(double) * 6 * (size_t)n_kf, cudaMemcpyDeviceToDevice, stream));
+  lap("upload + alloc");
   if (linear_solver == GPBA_SOLVER_DENSE_CHOL) CKR(build_cholesky_structure());
   else CKR(pcg.setup(n_pose, n_hs, hs_row, hs_col, stream));
   CK(cudaStreamSynchronize(stream));
+  lap("linear solver structure");
   info.n_free_kf = n_pose; info.n_active_pt = n_lm; info.n_active_obs = n_aobs; info.n_hpl = n_hpl; info.n_hpp = n_hpp; info.n_hschur = n_hs;
   structure_ok = true; system_ok = false; lambda_applied = false; structure_dirty = false;
   last_eval = cur;
@@ -1106,7 +1154,7 @@ int Solver::download_state(double* kf_pose, double* kf_vel, double* pt_xyz) {
 // ===================================================================================== C ABI
 struct gpba_handle { Solver s; };
 #define S(h) ((h)->s)
-#define NEED(h) do { if (!(h)) { g_err = "null handle"; return GPBA_ERR_INVALID; } } while (0)
+#define NEED(h) do { if (!(h)) { g_err = "null handle"; return GPBA_ERR_INVALID; } g_alloc_stream = S(h).stream; } while (0)
 #define NEED_STRUCT(h) do { NEED(h); if (!S(h).structure_ok) { g_err = "call gpba_build_structure first"; return GPBA_ERR_STATE; } if (cudaSetDevice(S(h).device) != cudaSuccess) return GPBA_ERR_CUDA; } while (0)
 
 extern "C" {
@@ -1129,7 +1177,7 @@ int gpba_create(const gpba_problem* prob, int device, gpba_handle** out) {
 }
 
 int gpba_destroy(gpba_handle* h) {
-  if (h) { cudaSetDevice(h->s.device); delete h; }
+  if (h) { cudaSetDevice(h->s.device); g_alloc_stream = h->s.stream; delete h; }
   return GPBA_OK;
 }
 

@@ -30,6 +30,10 @@ __global__ void k_gather_obs(int64_t n, const int64_t* __restrict__ o_orig, cons
   }
 }
 
+__global__ void k_iota(int64_t n, int64_t* __restrict__ out) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) out[j] = j;
+}
+
 __global__ void k_fill_lm(int n_lm, const int64_t* __restrict__ lm_obs_begin, int* __restrict__ o_lm) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
   for (int l = warp; l < n_lm; l += nw)
@@ -126,12 +130,13 @@ __global__ void k_item_ranges(int n, const int64_t* __restrict__ begin_excl, con
 struct CubTemp {
   void* p = nullptr;
   size_t bytes = 0;
-  ~CubTemp() { if (p) cudaFree(p); }
-  cudaError_t reserve(size_t need) {
+  cudaStream_t owner = nullptr;
+  ~CubTemp() { if (p) cudaFreeAsync(p, owner); }
+  cudaError_t reserve(size_t need, cudaStream_t s) {
     if (need <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; bytes = 0;
-    cudaError_t e = cudaMalloc(&p, need);
+    if (p) cudaFreeAsync(p, owner);
+    p = nullptr; bytes = 0; owner = s;
+    cudaError_t e = cudaMallocAsync(&p, need, s);
     if (e == cudaSuccess) bytes = need;
     return e;
   }
@@ -152,13 +157,13 @@ static inline cudaError_t sort_and_encode(CubTemp& tmp, unsigned long long*& key
   size_t need = 0;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, key_bits, s);
   if (e != cudaSuccess) return e;
-  if ((e = tmp.reserve(need)) != cudaSuccess) return e;
+  if ((e = tmp.reserve(need, s)) != cudaSuccess) return e;
   if ((e = cub::DeviceRadixSort::SortPairs(tmp.p, need, dk, dv, n, 0, key_bits, s)) != cudaSuccess) return e;
   if (dk.Current() != keys) { std::swap(keys, keys_alt); }
   if (dv.Current() != vals) { std::swap(vals, vals_alt); }
   need = 0;
   if ((e = cub::DeviceRunLengthEncode::Encode(nullptr, need, keys, uniq, counts, d_runs, n, s)) != cudaSuccess) return e;
-  if ((e = tmp.reserve(need)) != cudaSuccess) return e;
+  if ((e = tmp.reserve(need, s)) != cudaSuccess) return e;
   if ((e = cub::DeviceRunLengthEncode::Encode(tmp.p, need, keys, uniq, counts, d_runs, n, s)) != cudaSuccess) return e;
   if ((e = cudaMemcpyAsync(h_runs, d_runs, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
   return cudaStreamSynchronize(s);
