@@ -136,6 +136,7 @@ struct Solver {
   std::vector<int> hpp_row, hpp_col, hs_row, hs_col;
   int64_t n_aobs = 0;
   int n_lm = 0, n_pose = 0, n_hpp = 0, n_hs = 0, n_items = 0, n_rseg = 0, n_rp = 0;
+  int64_t n_con = 0;
   int64_t n_hpl = 0, n_pairs = 0;
   // ------------------------------------------------------------------ structure (device)
   DBuf<int> d_kf_h, d_o_rec, d_o_lm, d_lm_pt, d_rseg_rec, d_item_rp, d_con_begin;
@@ -677,6 +678,7 @@ int Solver::build_structure() {
         cursor.assign(con_begin.begin(), con_begin.end() - 1);
       }
     }
+    n_con = (int64_t)con.size();
     for (int k = 0; k < n_hs; ++k) {   // group by left record slice (stable insertion sort: the lists are short)
       HsContrib* lo = con.data() + con_begin[k];
       const int n = con_begin[k + 1] - con_begin[k];
@@ -989,6 +991,9 @@ int Solver::solve(double lambda, bool* ok) {
     CK(cudaGetLastError());
     ++launches;
   }
+  t1(5, launches);
+  t0();
+  launches = 0;
   // K4c: rank 0 carries lambda (pose priors / damping must enter the sum exactly once); the GP-edge part of
   // Hpp is a per-rank partial, so every rank adds its own Hpp but only rank 0 adds lambda.
   if (n_hs > 0) {
@@ -996,7 +1001,7 @@ int Solver::solve(double lambda, bool* ok) {
     CK(cudaGetLastError());
     ++launches;
   }
-  t1(5, launches);
+  t1(10, launches);
   CKR(allreduce_system());
   t0();
   launches = 0;
@@ -1537,6 +1542,11 @@ int gpba_stage_stats(gpba_handle* h, double ms_total[GPBA_N_STAGES], int64_t lau
     if (launches) launches[i] = S(h).stage_launches[i];
     if (reset) { S(h).stage_ms[i] = 0; S(h).stage_launches[i] = 0; }
   }
+  return GPBA_OK;
+}
+int gpba_schur_stats(gpba_handle* h, int64_t out[4]) {
+  NEED_STRUCT(h);
+  out[0] = S(h).n_pairs; out[1] = S(h).n_rp; out[2] = S(h).n_items; out[3] = S(h).n_con;
   return GPBA_OK;
 }
 int gpba_set_profiling(gpba_handle* h, int enabled) { NEED(h); S(h).collect_events(); S(h).profiling = enabled != 0; return GPBA_OK; }

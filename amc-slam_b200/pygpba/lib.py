@@ -21,12 +21,12 @@ SYMBOLS = [
     "gpba_get_hschur", "gpba_get_hll", "gpba_get_hpl", "gpba_oplus", "gpba_push", "gpba_pop", "gpba_discard_top",
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
-    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream",
+    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats",
 ]
 
 
-STAGE_NAMES = ["records", "residuals", "lin_landmarks", "lin_poses", "schur_prepare", "schur_gather", "factorize", "tri_solve",
-               "backsub_update", "collective"]
+STAGE_NAMES = ["records", "residuals", "lin_landmarks", "lin_poses", "schur_prepare", "schur_pairs", "factorize", "tri_solve",
+               "backsub_update", "collective", "schur_expand"]
 
 
 class GpbaError(RuntimeError):
@@ -227,6 +227,11 @@ class GpBa:
         self._ck(self.L.gpba_stage_stats(self.h, ms, n, int(reset)), "gpba_stage_stats")
         names = STAGE_NAMES
         return {k: dict(ms=ms[i], launches=n[i]) for i, k in enumerate(names)}
+
+    def schur_stats(self):
+        a = (C.c_int64 * 4)()
+        self._ck(self.L.gpba_schur_stats(self.h, a), "gpba_schur_stats")
+        return dict(n_obs_pairs=a[0], n_record_pairs=a[1], n_items=a[2], n_contrib=a[3])
 
     def stream(self):
         return self.L.gpba_get_stream(self.h)

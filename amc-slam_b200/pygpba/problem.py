@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 GPBA_MAX_ITERS = 64
-GPBA_N_STAGES = 10
+GPBA_N_STAGES = 11
 OBS_CLOSE, OBS_LEVEL1, OBS_NO_KERNEL = 1, 2, 4
 SOLVER_DENSE_CHOL, SOLVER_PCG = 0, 1
 

@@ -40,6 +40,8 @@ CPU_SAMPLE = {
     "c4": dict(n_kf=120, n_pt=60000), "c5": dict(n_kf=120, n_pt=60000),
 }
 LM_ITERS = 10
+KERNEL_OF_STAGE = {"residuals": "k_residual", "lin_landmarks": "k_lin_points", "lin_poses": "k_lin_records", "schur_prepare": "k_schur_prep",
+                   "schur_pairs": "k_schur_pairs", "schur_expand": "k_schur_expand", "backsub_update": "k_backsub"}
 
 
 def load_problem(name, **override):
@@ -117,17 +119,31 @@ def peaks():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def algorithmic_bytes(info, n_kf_free):
-    """Algorithmic bytes per launch of each HBM-bound stage (SURVEY.md §8d figures x this map's counts)."""
-    No, Np, Npl, Nhs, Nk = info.n_active_obs, info.n_active_pt, info.n_hpl, info.n_hschur, n_kf_free
+def algorithmic_bytes(info, sch):
+    """Algorithmic (compulsory) bytes per launch of each HBM-bound stage, from this map's counts.
+    Per observation: u, v, invSigma2 (3 x 8) + record, landmark, flags (3 x 4) = 36 B in; W_o / U_o = 6 x 3 f64 = 144 B.
+    Per landmark: xyz 24 B, Hll 72 B, b_l 24 B, L + z 72 B.  Per record pair: C 6 x 8 f64 = 384 B.  Per Hschur block 1152 B."""
+    No, Np, Nhs, Nk, Nhpp = info.n_active_obs, info.n_active_pt, info.n_hschur, info.n_free_kf, info.n_hpp
+    Npairs, Nrp, Ncon = sch["n_obs_pairs"], sch["n_record_pairs"], sch["n_contrib"]
     return {
         "residuals": 36 * No + 24 * Np,
-        "lin_landmarks": 36 * No + 24 * Np + 288 * Npl + 72 * Np,
+        "lin_landmarks": 36 * No + 24 * Np + 144 * No + 96 * Np,
         "lin_poses": 36 * No + 24 * Np,
-        "schur_prepare": 288 * Npl + 72 * Np + 288 * Npl + 72 * Np,
-        "schur_gather": 288 * Npl + 72 * Np + 1152 * Nhs + 96 * Nk,
-        "backsub_update": 288 * Npl + 72 * Np + 96 * Nk + 48 * Np,
+        "schur_prepare": 144 * No + 96 * Np + 144 * No + 72 * Np,
+        "schur_pairs": 144 * No + 8 * Npairs + 72 * Np + 384 * Nrp,        # U read once, pair list, z, C written
+        "schur_expand": 384 * Nrp + 16 * Ncon + 1152 * Nhpp + 1152 * Nhs + 96 * Nk,
+        "backsub_update": 144 * No + 4 * No + 96 * Np + 48 * Np,
     }
+
+
+def measured_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+    (profiles/r01_dram_traffic.json); None when no capture exists for this workload / kernel."""
+    p = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    try:
+        return json.load(open(p))[workload][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def run_reference(args):
@@ -207,6 +223,7 @@ def run_gpba(args):
     # ---------------- device-resident arm: `value`
     g = gl.GpBa(P, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
     info = g.build_structure()
+    sch = g.schur_stats()
     stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local_rank))
     total_ms, iters_done, trials_done, last = 0.0, 0, 0, None
     sampler = ClockSampler(local_rank)
@@ -239,21 +256,21 @@ def run_gpba(args):
 
     # ---------------- roofline of the dominant HBM-bound kernel (CUDA-event pairs recorded live in the timed region)
     peak, peak_src = peaks()
-    ab = algorithmic_bytes(info, info.n_free_kf)
-    per_launch_count = {"residuals": None}
+    ab = algorithmic_bytes(info, sch)
     cand = {}
     for k, nbytes in ab.items():
         st = stages[k]
         # number of kernel launches of the stage's main kernel in the timed region
         n_main = {"residuals": trials_done + iters_done + args.steps, "lin_landmarks": iters_done, "lin_poses": iters_done,
-                  "schur_prepare": trials_done, "schur_gather": trials_done, "backsub_update": trials_done}[k]
+                  "schur_prepare": trials_done, "schur_pairs": trials_done, "schur_expand": trials_done,
+                  "backsub_update": trials_done}[k]
         if n_main > 0 and st["ms"] > 0:
             cand[k] = dict(ms_per_launch=st["ms"] / n_main, bytes_per_launch=nbytes, gbs=nbytes / (st["ms"] / n_main * 1e-3) / 1e9)
     dom = max(cand, key=lambda k: stages[k]["ms"]) if cand else None
     roof = None
     if dom:
-        roof = {"bound": "hbm", "kernel": dom, "achieved": cand[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": cand[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+        roof = {"bound": "hbm", "kernel": KERNEL_OF_STAGE[dom], "stage": dom, "achieved": cand[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": cand[dom]["gbs"] / peak, "traffic": measured_traffic(args.workload, KERNEL_OF_STAGE[dom]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": cand[dom]["bytes_per_launch"], "ms_per_launch": cand[dom]["ms_per_launch"]}
     g.close()
 
@@ -308,7 +325,7 @@ def run_gpba(args):
                        "n_kf": int(P.n_kf), "lm_iters_executed_per_step": iters_done // max(args.steps, 1),
                        "lm_trials_per_step": trials_done // max(args.steps, 1),
                        "linear_solver": "pcg" if args.pcg else "tile_cholesky_dmma", "parallelism": f"landmark-sharded x{world}",
-                       "l2": "inputs larger than L2 (observation arrays + Hpl blocks >> 126 MB), no flush",
+                       "l2": "inputs larger than L2 (per LM iteration the kernels stream ~2.5 GB of observation / W / U arrays through a 126 MB L2), no flush",
                        "final_chi2": last["chi2_after"][last["n_iters"] - 1] if last else None},
             "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": int(P.input_bytes()),
                     "d2h_bytes_per_step": int(kp.nbytes + kv.nbytes + pt.nbytes), "ms_per_step": e2e_ms / n_e2e},
@@ -316,6 +333,7 @@ def run_gpba(args):
             "roofline": roof,
             "stages_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in stages.items()},
             "stage_gbs": {k: round(v["gbs"], 1) for k, v in cand.items()},
+            "schur_sizes": sch,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -227,13 +227,18 @@ int gpba_rejection_rounds(gpba_handle* h, int n_rounds, int iters, const gpba_th
 /* ---- measurement ------------------------------------------------------------------- */
 /* Total device time (ms, CUDA event pairs recorded on the library stream, read back only here) and
  * launch count per stage since the last reset: 0 records (K0), 1 residuals (K1), 2 linearize landmarks
- * (K2a), 3 linearize poses + priors (K2b/K2c/K3), 4 schur prepare (K4 init + K4a), 5 schur gather (K4b),
- * 6 reduced-system factorization / PCG (K5), 7 triangular solves, 8 back-substitution + update (K6),
- * 9 collective.  Grouping follows G2OBatchStatistics (g2o/core/batch_stats.h:39-78):
- * timeResiduals = 0+1, timeQuadraticForm = 2+3, timeSchurComplement = 4+5, timeLinearSolver = 6+7, timeUpdate = 8. */
-#define GPBA_N_STAGES 10
+ * (K2a), 3 linearize poses + priors (K2b/K2c/K3), 4 schur prepare (K4a), 5 schur record-pair products (K4b),
+ * 6 reduced-system factorization + forward substitution / PCG (K5), 7 backward substitution,
+ * 8 back-substitution + update (K6), 9 collective, 10 schur expansion into Hschur / bschur (K4c).
+ * Grouping follows G2OBatchStatistics (g2o/core/batch_stats.h:39-78): timeResiduals = 0+1,
+ * timeQuadraticForm = 2+3, timeSchurComplement = 4+5+10, timeLinearSolver = 6+7, timeUpdate = 8. */
+#define GPBA_N_STAGES 11
 int gpba_stage_stats(gpba_handle* h, double ms_total[GPBA_N_STAGES], int64_t launches[GPBA_N_STAGES], int reset);
 int gpba_set_profiling(gpba_handle* h, int enabled);
+/* Sizes of the record-space Schur structures (for the algorithmic-byte accounting of bench.py / DESIGN.md):
+ * out[0] observation pairs, out[1] record pairs (6x6 accumulators), out[2] work items of K4b,
+ * out[3] (record pair -> Hschur block) contributions of K4c. */
+int gpba_schur_stats(gpba_handle* h, int64_t out[4]);
 /* cudaStream_t every kernel of this handle is launched on (for CUDA-event timing by the caller). */
 void* gpba_get_stream(gpba_handle* h);
 /* Re-upload estimates only (same structure): lets a benchmark repeat optimize() from the same start. */
