@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 #include <dlfcn.h>
+#include <map>
+#include <mutex>
 #include <chrono>
 
 using namespace gpba;
@@ -197,7 +199,7 @@ struct Solver {
   DevView V{};
 
   ~Solver() {
-    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    // the communicator is shared by every handle created with the same NCCL id (g_comms) and lives until process exit
     if (chol_graph) cudaGraphExecDestroy(chol_graph);
     if (chol_back_graph) cudaGraphExecDestroy(chol_back_graph);
     if (h_scal) cudaFreeHost(h_scal);
@@ -1191,18 +1193,36 @@ int gpba_nccl_unique_id(unsigned char id_out[128]) {
   return g_nccl.GetUniqueId(id_out) == 0 ? GPBA_OK : GPBA_ERR_NCCL;
 }
 
+// One communicator per (NCCL id, rank) and process: an ncclUniqueId can initialise a communicator only once, while a
+// SLAM process runs many BA calls (one handle each, like one g2o::SparseOptimizer each) over the same set of GPUs.
+static std::mutex g_comm_mutex;
+static std::map<std::string, ncclComm_t> g_comms;
+
 int gpba_create_dist(const gpba_problem* prob, int device, int rank, int nranks, const unsigned char id[128], gpba_handle** out) {
+  if (nranks > 1 && (!id || rank < 0 || rank >= nranks)) { g_err = "bad rank / NCCL id"; return GPBA_ERR_INVALID; }
   int rc = gpba_create(prob, device, out);
   if (rc != GPBA_OK) return rc;
   Solver& s = (*out)->s;
   s.rank = rank; s.nranks = nranks;
   if (nranks > 1) {
-    if (!g_nccl.load()) { g_err = "libnccl.so.2 not found"; gpba_destroy(*out); return GPBA_ERR_NCCL; }
-    NcclId nid;
-    std::memcpy(nid.internal, id, 128);
-    ncclCommInitRank_t init = (ncclCommInitRank_t)dlsym(g_nccl.lib, "ncclCommInitRank");
-    int nrc = init(&s.comm, nranks, nid, rank);
-    if (nrc != 0) { g_err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"); gpba_destroy(*out); return GPBA_ERR_NCCL; }
+    if (!g_nccl.load()) { g_err = "libnccl.so.2 not found"; gpba_destroy(*out); *out = nullptr; return GPBA_ERR_NCCL; }
+    std::lock_guard<std::mutex> lock(g_comm_mutex);
+    const std::string key = std::string((const char*)id, 128) + "#" + std::to_string(rank) + "/" + std::to_string(nranks);
+    auto it = g_comms.find(key);
+    if (it == g_comms.end()) {
+      NcclId nid;
+      std::memcpy(nid.internal, id, 128);
+      ncclCommInitRank_t init = (ncclCommInitRank_t)dlsym(g_nccl.lib, "ncclCommInitRank");
+      ncclComm_t c = nullptr;
+      int nrc = init(&c, nranks, nid, rank);
+      if (nrc != 0) {
+        g_err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
+        gpba_destroy(*out); *out = nullptr;
+        return GPBA_ERR_NCCL;
+      }
+      it = g_comms.emplace(key, c).first;
+    }
+    s.comm = it->second;
   }
   return GPBA_OK;
 }

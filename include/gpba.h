@@ -159,7 +159,9 @@ const char* gpba_last_error(void);
 void gpba_default_lm_params(gpba_lm_params* p);
 /* Multi-GPU (global BA): this rank owns the points with (pt % nranks == rank)-style shard
  * given by gpba_shard_points; partial Hschur/bschur/chi2 are summed with ncclAllReduce.
- * nccl_unique_id = 128 bytes from ncclGetUniqueId on rank 0 (gpba_nccl_unique_id). */
+ * nccl_unique_id = 128 bytes from ncclGetUniqueId on rank 0 (gpba_nccl_unique_id).  The communicator is created at
+ * the first gpba_create_dist with a given id and shared by every later handle of the process that passes the same id
+ * (one id per set of GPUs, many BA calls). */
 int gpba_nccl_unique_id(unsigned char id_out[128]);
 int gpba_create_dist(const gpba_problem* prob, int device, int rank, int nranks,
                      const unsigned char nccl_unique_id[128], gpba_handle** out);
