@@ -46,6 +46,15 @@ __device__ __forceinline__ long long* chol_clk_smem() { __shared__ long long b[6
 #define GPBA_TICKP(slot) do { } while (0)
 #endif
 
+// Programmatic dependent launch (PDL): every kernel of the factorization chain first waits for its predecessor
+// (griddepcontrol.wait: predecessor complete, its stores visible), then lets its own successor become resident
+// (griddepcontrol.launch_dependents), so the successor's launch latency is hidden behind this kernel's work.
+// Both are no-ops when the kernel was launched without the PDL attribute.
+GPBA_D void pdl_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 struct CholView {
   int NT;                       // tiles per side
   int n;                        // true dimension (12 * n_pose)
@@ -264,14 +273,14 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, i
   __shared__ double Sy[GPBA_NB];
   const int tid = threadIdx.x;
   GPBA_TICK(0);
-  const double* Tkk = C.tiles + C.tile_off[(size_t)k * C.NT + k];
-  double* A = nullptr;
+  const double* Tkk = C.tiles + C.tile_off[(size_t)k * C.NT + k];   // static index data: may be read before the wait
+  double* A = blockIdx.x == 0 ? nullptr : C.tiles + C.tile_off[(size_t)C.col_rows[C.col_begin[k] + blockIdx.x - 1] * C.NT + k];
+  pdl_wait_then_release();
   if (blockIdx.x == 0) {
     tiles_to_smem<GPBA_PANEL_THREADS, 1>(Tkk, S, nullptr, nullptr);
     for (int j = tid; j < GPBA_NB * GPBA_NB; j += blockDim.x) T[j / GPBA_NB][j % GPBA_NB] = (j / GPBA_NB == j % GPBA_NB) ? 1.0 : 0.0;
     if (tid < GPBA_NB) Sy[tid] = C.work[k * GPBA_NB + tid];
   } else {
-    A = C.tiles + C.tile_off[(size_t)C.col_rows[C.col_begin[k] + blockIdx.x - 1] * C.NT + k];
     tiles_to_smem<GPBA_PANEL_THREADS, 2>(Tkk, S, A, T);
   }
   __syncthreads();
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int m0 = 3 * (warp >> 1), n0 = 3 * (warp & 1);
+  pdl_wait_then_release();
   double2 cin[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -372,6 +382,7 @@ __global__ void __launch_bounds__(192) k_chol_back(CholView C, int i) {
   const double* D = C.dinv + (size_t)i * GPBA_NB * GPBA_NB;  // (L^-T)[c][r] = Linv[r][c], zero for r < c
   const int k = blockIdx.x > 0 ? C.row_cols[C.row_begin[i] + blockIdx.x - 1] : 0;
   const double* L = blockIdx.x > 0 ? C.tiles + C.tile_off[(size_t)i * C.NT + k] : D;
+  pdl_wait_then_release();
   double dv[12], lv[12];
 #pragma unroll
   for (int r = 0; r < 12; ++r) { dv[r] = D[(12 * h + r) * GPBA_NB + c]; lv[r] = L[(12 * h + r) * GPBA_NB + c]; }
@@ -399,6 +410,7 @@ __global__ void __launch_bounds__(192) k_chol_back(CholView C, int i) {
 }
 
 __global__ void k_chol_unpermute(CholView C, double* __restrict__ xout) {
+  pdl_wait_then_release();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < C.n) xout[j] = C.xsol[C.perm[j / 12] * 12 + j % 12];
 }

@@ -838,7 +838,20 @@ int Solver::build_cholesky_structure() {
 
 // The factorization of one structure is a fixed launch sequence (2 kernels per tile column); replaying it as a
 // CUDA graph removes the per-launch host cost from the critical path of every LM trial.
+// launch with the programmatic-stream-serialization attribute (PDL edge when captured into a graph)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 int Solver::capture_cholesky_graph() {
+  static const bool use_pdl = !getenv("GPBA_NO_PDL");
   double* bs = d_hs.p + (size_t)n_hs * 144;
   const CholView C = chol_view();
   auto finish = [&](cudaError_t e, cudaGraphExec_t* exec) -> int {
@@ -864,24 +877,36 @@ int Solver::capture_cholesky_graph() {
     ++launches;
     for (int k = 0; k < NT; ++k) {
       const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
-      k_chol_panel<<<1 + nr, GPBA_PANEL_THREADS, 0, stream>>>(C, k, d_fail.p);
+      if (use_pdl && k > 0) e = launch_pdl(k_chol_panel, 1 + nr, GPBA_PANEL_THREADS, stream, C, k, d_fail.p);
+      else k_chol_panel<<<1 + nr, GPBA_PANEL_THREADS, 0, stream>>>(C, k, d_fail.p);
       ++launches;
-      if (nr > 0) { k_chol_update<<<nr * (nr + 1) / 2, 128, 0, stream>>>(C, k); ++launches; }
+      if (nr > 0) {
+        if (use_pdl) e = launch_pdl(k_chol_update, nr * (nr + 1) / 2, 128, stream, C, k);
+        else k_chol_update<<<nr * (nr + 1) / 2, 128, 0, stream>>>(C, k);
+        ++launches;
+      }
+      if (e != cudaSuccess) break;
     }
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
   }
   CKR(finish(e, &chol_graph));
   chol_graph_launches = launches;
   // ---- graph B: backward substitution
   CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
   launches = 0;
-  for (int i = NT - 1; i >= 0; --i) {
-    k_chol_back<<<1 + chol_row_begin[i + 1] - chol_row_begin[i], 192, 0, stream>>>(C, i);
+  e = cudaSuccess;
+  for (int i = NT - 1; i >= 0 && e == cudaSuccess; --i) {
+    if (use_pdl && i < NT - 1) e = launch_pdl(k_chol_back, 1 + chol_row_begin[i + 1] - chol_row_begin[i], 192, stream, C, i);
+    else k_chol_back<<<1 + chol_row_begin[i + 1] - chol_row_begin[i], 192, 0, stream>>>(C, i);
     ++launches;
   }
-  k_chol_unpermute<<<(n_pose * 12 + 255) / 256, 256, 0, stream>>>(C, d_x.p);
-  ++launches;
-  CKR(finish(cudaGetLastError(), &chol_back_graph));
+  if (e == cudaSuccess) {
+    if (use_pdl) e = launch_pdl(k_chol_unpermute, (n_pose * 12 + 255) / 256, 256, stream, C, d_x.p);
+    else k_chol_unpermute<<<(n_pose * 12 + 255) / 256, 256, 0, stream>>>(C, d_x.p);
+    ++launches;
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  CKR(finish(e, &chol_back_graph));
   chol_back_launches = launches;
   return GPBA_OK;
 }
@@ -929,9 +954,11 @@ int Solver::build_system() {
   CK(cudaMemsetAsync(d_bp.p, 0, sizeof(double) * 12 * (size_t)std::max(n_pose, 1), stream));
   int launches = 0;
   if (n_lm > 0) {
-    const int g = std::min((n_lm + GPBA_K2_WARPS - 1) / GPBA_K2_WARPS, 148 * 16);
-    if (stereo) k_lin_points<true><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
-    else k_lin_points<false><<<g, GPBA_K2_WARPS * 32, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
+    CK(cudaMemsetAsync(d_hll.p, 0, sizeof(double) * 9 * (size_t)n_lm, stream));
+    CK(cudaMemsetAsync(d_bl.p, 0, sizeof(double) * 3 * (size_t)n_lm, stream));
+    const int g = (int)std::min<int64_t>((n_aobs + GPBA_K2_THREADS - 1) / GPBA_K2_THREADS, 148 * 8);
+    if (stereo) k_lin_points<true><<<g, GPBA_K2_THREADS, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
+    else k_lin_points<false><<<g, GPBA_K2_THREADS, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
     CK(cudaGetLastError());
     t1(2, 1);
     t0();

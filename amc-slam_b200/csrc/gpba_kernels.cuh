@@ -45,6 +45,15 @@ GPBA_D double block_sum(double v, double* smem32) {
   return r;
 }
 
+// R_cw | t_cw of a record row (12 doubles, 16-byte aligned rows): six 16-byte loads instead of twelve scattered 8-byte
+// ones -- neighbouring observations belong to different records, so every load instruction of a warp touches up to
+// 32 lines and the load count, not the byte count, is what these kernels pay for.
+GPBA_D void load_rec12(const double* __restrict__ p, double (&R)[12]) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const double2 v = __ldg(q + k); R[2 * k] = v.x; R[2 * k + 1] = v.y; }
+}
+
 // Per-observation geometry shared by K1/K2/K8: residual, chi2, robust weight, J1 (rows x 6), Jp (rows x 3).
 template <bool STEREO>
 struct ObsEval {
@@ -196,7 +205,8 @@ __global__ void __launch_bounds__(256) k_residual(DevView V, const double* __res
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V.n_aobs; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = V.o_rec[i];
     const int lm = V.o_lm[i];
-    const double* R = rec + (size_t)r * rec_stride;
+    double R[12];
+    load_rec12(rec + (size_t)r * rec_stride, R);
     ObsEval<STEREO> E;
     eval_obs<STEREO, false>(V, R, V.cam[V.rec_cam[r]], pt[3 * (size_t)lm], pt[3 * (size_t)lm + 1], pt[3 * (size_t)lm + 2],
                             V.o_u[i], V.o_v[i], STEREO ? V.o_ur[i] : -1.0, V.o_w[i], V.o_flags[i], E, nullptr, nullptr);
@@ -219,28 +229,37 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ a, in
 }
 
 // ------------------------------------------------------------------------------------------------ K2a
-// One warp per landmark, lane = observation: residual, robust weight, J1, Jp; W_o = J1^T (rho' w) Jp goes out as
-// 18 contiguous doubles per observation, Hll / b_l are reduced with warp shuffles (no atomics, no shared memory).
-#define GPBA_K2_WARPS 8
+// One thread per observation (observations are sorted by landmark, so a warp covers ~3 landmarks at 10 observations
+// each; a warp-per-landmark mapping left 2/3 of the lanes idle).  Residual, robust weight, J1, Jp per lane;
+// W_o = J1^T (rho' w) Jp is staged through shared memory and leaves as fully coalesced 256-byte stores; Hll / b_l are
+// reduced over the lanes of equal landmark with a segmented shuffle reduction, one atomicAdd per value and segment
+// (a landmark that straddles two warps gets two commutative adds into the zeroed accumulators).
+#define GPBA_K2_THREADS 256
+#define GPBA_K2_WSTRIDE 19   // padded row stride of the staging tile (18 values per observation)
 template <bool STEREO>
-__global__ void __launch_bounds__(GPBA_K2_WARPS * 32) k_lin_points(DevView V, const double* __restrict__ rec,
-                                                                   const double* __restrict__ pt, double* __restrict__ hll,
-                                                                   double* __restrict__ bl, double* __restrict__ W) {
+__global__ void __launch_bounds__(GPBA_K2_THREADS) k_lin_points(DevView V, const double* __restrict__ rec,
+                                                                const double* __restrict__ pt, double* __restrict__ hll,
+                                                                double* __restrict__ bl, double* __restrict__ W) {
+  __shared__ double sW[GPBA_K2_THREADS / 32][32 * GPBA_K2_WSTRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ROWS = STEREO ? 3 : 2;
-  for (int lm = blockIdx.x * GPBA_K2_WARPS + warp; lm < V.n_lm; lm += gridDim.x * GPBA_K2_WARPS) {
-    const int64_t ob = V.lm_obs_begin[lm], oe = V.lm_obs_begin[lm + 1];
-    const double X0 = pt[3 * (size_t)lm], X1 = pt[3 * (size_t)lm + 1], X2 = pt[3 * (size_t)lm + 2];
+  const int64_t nwarps = (int64_t)gridDim.x * (GPBA_K2_THREADS / 32);
+  for (int64_t base = ((int64_t)blockIdx.x * (GPBA_K2_THREADS / 32) + warp) * 32; base < V.n_aobs; base += nwarps * 32) {
+    const int64_t i = base + lane;
+    const bool live = i < V.n_aobs;
+    int lm = -1;
     double h[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-    for (int64_t i = ob + lane; i < oe; i += 32) {
+    if (live) {
+      lm = V.o_lm[i];
       const int r = V.o_rec[i];
+      double R[12];
+      load_rec12(rec + (size_t)r * GPBA_REC_STRIDE, R);
       ObsEval<STEREO> E;
       double J1[ROWS][6], Jp[ROWS][3];
       const double w = V.o_w[i];
-      eval_obs<STEREO, true>(V, rec + (size_t)r * GPBA_REC_STRIDE, V.cam[V.rec_cam[r]], X0, X1, X2, V.o_u[i], V.o_v[i],
-                             STEREO ? V.o_ur[i] : -1.0, w, V.o_flags[i], E, J1, Jp);
+      eval_obs<STEREO, true>(V, R, V.cam[V.rec_cam[r]], pt[3 * (size_t)lm], pt[3 * (size_t)lm + 1], pt[3 * (size_t)lm + 2],
+                             V.o_u[i], V.o_v[i], STEREO ? V.o_ur[i] : -1.0, w, V.o_flags[i], E, J1, Jp);
       const double wr = E.rho1 * w;  // robustInformation = rho' * Omega (base_edge.h:96-102)
-      double Wo[18];
 #pragma unroll
       for (int m = 0; m < 6; ++m)
 #pragma unroll
@@ -248,11 +267,8 @@ __global__ void __launch_bounds__(GPBA_K2_WARPS * 32) k_lin_points(DevView V, co
           double s = 0.0;
 #pragma unroll
           for (int rr = 0; rr < ROWS; ++rr) s = fma(wr * J1[rr][m], Jp[rr][c], s);
-          Wo[m * 3 + c] = s;
+          sW[warp][lane * GPBA_K2_WSTRIDE + m * 3 + c] = s;
         }
-      double2* out = reinterpret_cast<double2*>(W + (size_t)i * 18);
-#pragma unroll
-      for (int q = 0; q < 9; ++q) out[q] = make_double2(Wo[2 * q], Wo[2 * q + 1]);
 #pragma unroll
       for (int rr = 0; rr < ROWS; ++rr) {
         const double w0 = wr * Jp[rr][0], w1 = wr * Jp[rr][1], w2 = wr * Jp[rr][2];
@@ -261,17 +277,30 @@ __global__ void __launch_bounds__(GPBA_K2_WARPS * 32) k_lin_points(DevView V, co
         b[0] = fma(-w0, E.e[rr], b[0]); b[1] = fma(-w1, E.e[rr], b[1]); b[2] = fma(-w2, E.e[rr], b[2]);
       }
     }
+    __syncwarp();
+    // coalesced copy-out of the warp's W rows
+    const int nlive = (int)((V.n_aobs - base) < 32 ? (V.n_aobs - base) : 32);
+    double* out = W + (size_t)base * 18;
+    for (int j = lane; j < nlive * 18; j += 32) out[j] = sW[warp][(j / 18) * GPBA_K2_WSTRIDE + j % 18];
+    // segmented reduction over equal landmark (segments are contiguous)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) h[k] = warp_sum(h[k]);
+    for (int o = 1; o < 32; o <<= 1) {
+      const int lm_o = __shfl_down_sync(0xffffffffu, lm, o);
+      const bool take = (lane + o < 32) && lm_o == lm;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) b[k] = warp_sum(b[k]);
-    if (lane == 0) {
-      double* H = hll + 9 * (size_t)lm;
-      H[0] = h[0]; H[1] = h[1]; H[2] = h[2];
-      H[3] = h[1]; H[4] = h[3]; H[5] = h[4];
-      H[6] = h[2]; H[7] = h[4]; H[8] = h[5];
-      bl[3 * (size_t)lm] = b[0]; bl[3 * (size_t)lm + 1] = b[1]; bl[3 * (size_t)lm + 2] = b[2];
+      for (int k = 0; k < 6; ++k) { const double t = __shfl_down_sync(0xffffffffu, h[k], o); if (take) h[k] += t; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const double t = __shfl_down_sync(0xffffffffu, b[k], o); if (take) b[k] += t; }
     }
+    const int lm_prev = __shfl_up_sync(0xffffffffu, lm, 1);
+    if (live && (lane == 0 || lm_prev != lm)) {
+      double* H = hll + 9 * (size_t)lm;
+      atomicAdd(H + 0, h[0]); atomicAdd(H + 1, h[1]); atomicAdd(H + 2, h[2]);
+      atomicAdd(H + 3, h[1]); atomicAdd(H + 4, h[3]); atomicAdd(H + 5, h[4]);
+      atomicAdd(H + 6, h[2]); atomicAdd(H + 7, h[4]); atomicAdd(H + 8, h[5]);
+      atomicAdd(bl + 3 * (size_t)lm, b[0]); atomicAdd(bl + 3 * (size_t)lm + 1, b[1]); atomicAdd(bl + 3 * (size_t)lm + 2, b[2]);
+    }
+    __syncwarp();
   }
 }
 
@@ -285,7 +314,8 @@ __global__ void __launch_bounds__(128) k_lin_records(DevView V, const double* __
   constexpr int ROWS = STEREO ? 3 : 2;
   for (int s = blockIdx.x * 4 + warp; s < V.n_rseg; s += gridDim.x * 4) {
     const int r = V.rseg_rec[s];
-    const double* R = rec + (size_t)r * GPBA_REC_STRIDE;
+    double R[12];
+    load_rec12(rec + (size_t)r * GPBA_REC_STRIDE, R);
     const CamConst& cam = V.cam[V.rec_cam[r]];
     double acc[27];
 #pragma unroll
