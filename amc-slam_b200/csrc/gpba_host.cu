@@ -99,6 +99,28 @@ static NcclApi g_nccl;
 struct NcclId { char internal[128]; };
 typedef int (*ncclCommInitRank_t)(ncclComm_t*, int, NcclId, int);
 
+// Pinned scratch for the few scalars a handle reads back per LM trial.  cudaMallocHost / cudaFreeHost synchronise the
+// device and map / unmap pages (tens of ms when memory is busy), so handles borrow 256-byte slots of one block that is
+// allocated once per process.
+struct PinnedSlots {
+  static constexpr int N = 256, BYTES = 256;
+  std::mutex m;
+  char* base = nullptr;
+  bool used[N] = {false};
+  void* take() {
+    std::lock_guard<std::mutex> lock(m);
+    if (!base && cudaMallocHost(&base, (size_t)N * BYTES) != cudaSuccess) { base = nullptr; return nullptr; }
+    for (int i = 0; i < N; ++i) if (!used[i]) { used[i] = true; return base + (size_t)i * BYTES; }
+    return nullptr;
+  }
+  void give(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(m);
+    used[((char*)p - base) / BYTES] = false;
+  }
+};
+static PinnedSlots g_pinned;
+
 struct StreamHolder {
   cudaStream_t s = nullptr;
   ~StreamHolder() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
@@ -114,7 +136,7 @@ struct Solver {
   bool stereo = false;
   std::vector<double> h_pose, h_vel, h_pt, h_time;
   std::vector<uint8_t> kf_fixed, obs_flags;
-  std::vector<int> rec_kf1, rec_kf2, rec_cam, obs_rec, obs_pt, prior_kf1, prior_kf2, velp_kf;
+  std::vector<int> rec_kf1, rec_kf2, rec_cam, prior_kf1, prior_kf2, velp_kf;   // per-observation indices live on the device only
   std::vector<double> rec_t;   // per-observation measurements live on the device only (d_all_*)
   double lambda_init = 0;
   int linear_solver = 0;
@@ -146,6 +168,7 @@ struct Solver {
   DBuf<uint8_t> d_o_flags, d_item_flags;
   DBuf<int64_t> d_o_orig, d_lm_obs_begin, d_rperm, d_rseg_begin, d_item_begin, d_item_end;
   DBuf<unsigned long long> d_pairs;     // observation pairs grouped by record pair (sorted order)
+  DBuf<unsigned long long> d_rp_key;    // unique record pairs (r1 * n_rec + r2), ascending
   DBuf<HsContrib> d_con;
   CubTemp cub_tmp;
   DBuf<int> d_rec_hpp11, d_rec_hpp12, d_rec_hpp22, d_prior_hpp11, d_prior_hpp12, d_prior_hpp22, d_pose_hpp_diag;
@@ -202,8 +225,7 @@ struct Solver {
     // the communicator is shared by every handle created with the same NCCL id (g_comms) and lives until process exit
     if (chol_graph) cudaGraphExecDestroy(chol_graph);
     if (chol_back_graph) cudaGraphExecDestroy(chol_back_graph);
-    if (h_scal) cudaFreeHost(h_scal);
-    if (h_fail) cudaFreeHost(h_fail);
+    g_pinned.give(h_scal);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -275,8 +297,9 @@ int Solver::init(const gpba_problem* P, int dev) {
   }
   CK(cudaEventCreate(&ev0));
   CK(cudaEventCreate(&ev1));
-  CK(cudaMallocHost(&h_scal, 8 * sizeof(double)));
-  CK(cudaMallocHost(&h_fail, sizeof(int)));
+  h_scal = (double*)g_pinned.take();
+  if (!h_scal) { g_err = "out of pinned scratch slots (more than 256 live handles?)"; return GPBA_ERR_CUDA; }
+  h_fail = (int*)(h_scal + 16);
   n_cam = P->n_cam; n_kf = P->n_kf; n_pt = P->n_pt; n_rec = P->n_rec; n_obs = P->n_obs;
   n_prior = P->n_prior; n_velp = P->n_velp;
   if (n_cam <= 0 || n_kf <= 0 || n_pt < 0 || n_obs < 0) { g_err = "empty problem"; return GPBA_ERR_INVALID; }
@@ -291,16 +314,12 @@ int Solver::init(const gpba_problem* P, int dev) {
   stereo = false;
   if (P->obs_ur)
     for (int64_t i = 0; i < n_obs; ++i) if (P->obs_ur[i] >= 0) { stereo = true; break; }
-  obs_rec.assign(P->obs_rec, P->obs_rec + n_obs); obs_pt.assign(P->obs_pt, P->obs_pt + n_obs);
   if (P->obs_flags) obs_flags.assign(P->obs_flags, P->obs_flags + n_obs); else obs_flags.assign(n_obs, 0);
   prior_kf1.assign(P->prior_kf1, P->prior_kf1 + n_prior); prior_kf2.assign(P->prior_kf2, P->prior_kf2 + n_prior);
   velp_kf.assign(P->velp_kf, P->velp_kf + n_velp);
   for (int i = 0; i < 6; ++i) qc[i] = P->qc[i];
   huber_mono = P->huber_mono; huber_stereo = P->huber_stereo; huber_prior = P->huber_prior;
   lambda_init = P->lambda_init; linear_solver = P->linear_solver;
-  for (int64_t i = 0; i < n_obs; ++i) {
-    if (obs_rec[i] < 0 || obs_rec[i] >= n_rec || obs_pt[i] < 0 || obs_pt[i] >= n_pt) { g_err = "observation index out of range"; return GPBA_ERR_INVALID; }
-  }
   for (int r = 0; r < n_rec; ++r)
     if (rec_kf2[r] < 0 || rec_kf2[r] >= n_kf || rec_kf1[r] >= n_kf || rec_cam[r] < 0 || rec_cam[r] >= n_cam) { g_err = "record index out of range"; return GPBA_ERR_INVALID; }
 
@@ -326,11 +345,19 @@ int Solver::init(const gpba_problem* P, int dev) {
   for (int b = 0; b < 2; ++b) { CKR(d_pose[b].upload(h_pose, stream)); CKR(d_vel[b].upload(h_vel, stream)); }
   CKR(d_chi2.alloc((size_t)n_obs));
   CK(cudaMemsetAsync(d_chi2.p, 0, sizeof(double) * (size_t)std::max<int64_t>(n_obs, 1), stream));
-  CKR(d_all_rec.upload(obs_rec, stream)); CKR(d_all_pt.upload(obs_pt, stream));
+  CKR(d_all_rec.upload(P->obs_rec, (size_t)n_obs, stream)); CKR(d_all_pt.upload(P->obs_pt, (size_t)n_obs, stream));
+  CKR(d_scal.alloc(8)); CKR(d_fail.alloc(2));  // [0] failure flag, [1] work counter of K4b
+  if (n_obs > 0) {   // index validation on the device (the host never walks the observation arrays)
+    CK(cudaMemsetAsync(d_fail.p, 0, sizeof(int), stream));
+    k_check_indices<<<(int)std::min<int64_t>((n_obs + 255) / 256, 148 * 8), 256, 0, stream>>>(n_obs, d_all_rec.p, d_all_pt.p, n_rec, n_pt, d_fail.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_fail, d_fail.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (*h_fail) { g_err = "observation index out of range"; return GPBA_ERR_INVALID; }
+  }
   CKR(d_all_u.upload(P->obs_u, (size_t)n_obs, stream)); CKR(d_all_v.upload(P->obs_v, (size_t)n_obs, stream));
   CKR(d_all_w.upload(P->obs_inv_sigma2, (size_t)n_obs, stream));
   if (stereo) CKR(d_all_ur.upload(P->obs_ur, (size_t)n_obs, stream));
-  CKR(d_scal.alloc(8)); CKR(d_fail.alloc(2));  // [0] failure flag, [1] work counter of K4b
   CKR(d_rec.alloc((size_t)n_rec * GPBA_REC_STRIDE)); CKR(d_rec_lite.alloc((size_t)n_rec * GPBA_REC_LITE_STRIDE));
   CKR(d_recS.alloc((size_t)n_rec * 27)); CKR(d_Y.alloc((size_t)n_rec * 6));
   CKR(d_prior_rho.alloc((size_t)n_prior + n_velp));
@@ -389,14 +416,35 @@ int Solver::build_structure() {
     tp0 = now;
   };
   if (structure_ok && n_lm > 0) CKR(scatter_points(cur));  // keep d_pt_full current before re-sorting
-  // --- active set (edge active iff level 0; vertex active iff it has an active edge)
-  std::vector<char> kf_act(n_kf, 0), pt_act(n_pt, 0), rec_used(n_rec, 0);
-  bool any_level1 = false;
-  for (int64_t i = 0; i < n_obs; ++i) {
-    if (obs_flags[i] & GPBA_OBS_LEVEL1) { any_level1 = true; continue; }
-    pt_act[obs_pt[i]] = 1;
-    rec_used[obs_rec[i]] = 1;
+  // exclusive / inclusive scans and sorts below all go through cub on `stream`
+  auto excl_scan64 = [&](const int64_t* in, int64_t* out, int n) -> int {
+    size_t need = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n, stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, need, in, out, n, stream));
+    return GPBA_OK;
+  };
+  const int gall = (int)std::min<int64_t>((n_obs + 255) / 256 + 1, 148 * 16);
+  // --- active set (edge active iff level 0; vertex active iff it has an active edge): one device pass
+  DBuf<unsigned char> d_rec_used;
+  DBuf<int> d_pt_act, d_first_kf, d_flag;
+  CKR(d_rec_used.alloc((size_t)n_rec)); CKR(d_pt_act.alloc((size_t)n_pt)); CKR(d_first_kf.alloc((size_t)n_pt)); CKR(d_flag.alloc(1));
+  CK(cudaMemsetAsync(d_rec_used.p, 0, (size_t)n_rec, stream));
+  CK(cudaMemsetAsync(d_pt_act.p, 0, sizeof(int) * (size_t)n_pt, stream));
+  CK(cudaMemsetAsync(d_first_kf.p, 0x7f, sizeof(int) * (size_t)n_pt, stream));
+  CK(cudaMemsetAsync(d_flag.p, 0, sizeof(int), stream));
+  CKR(d_all_flags.upload(obs_flags, stream));
+  if (n_obs > 0) {
+    k_scan_obs<<<gall, 256, 0, stream>>>(n_obs, d_all_flags.p, d_all_rec.p, d_all_pt.p, d_rec_kf2.p, d_rec_used.p, d_pt_act.p, d_first_kf.p, d_flag.p);
+    CK(cudaGetLastError());
   }
+  std::vector<unsigned char> rec_used((size_t)n_rec, 0);
+  int h_any_level1 = 0;
+  if (n_rec) CK(cudaMemcpyAsync(rec_used.data(), d_rec_used.p, (size_t)n_rec, cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(&h_any_level1, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  const bool any_level1 = h_any_level1 != 0;
+  std::vector<char> kf_act(n_kf, 0);
   for (int r = 0; r < n_rec; ++r)
     if (rec_used[r]) { if (rec_kf1[r] >= 0) kf_act[rec_kf1[r]] = 1; kf_act[rec_kf2[r]] = 1; }
   for (int i = 0; i < n_prior; ++i)
@@ -407,102 +455,138 @@ int Solver::build_structure() {
   n_pose = 0;
   for (int k = 0; k < n_kf; ++k)
     if (kf_act[k] && !kf_fixed[k]) kf_h[k] = n_pose++;
-  // --- landmark order: ascending first keyframe (locality of record / pose accesses), ties by point id (bucket sort)
-  std::vector<int> first_kf(n_pt, n_kf);
-  for (int64_t i = 0; i < n_obs; ++i) {
-    if (obs_flags[i] & GPBA_OBS_LEVEL1) continue;
-    const int k = rec_kf2[obs_rec[i]];
-    if (k < first_kf[obs_pt[i]]) first_kf[obs_pt[i]] = k;
-  }
-  std::vector<int> bucket(n_kf + 2, 0);
+  CKR(d_kf_h.upload(kf_h, stream));
+  // --- landmark order: ascending first keyframe, ties by point id (stable radix sort of the points);
+  //     g2o landmark index = rank among active points in ascending id (exclusive scan of the activity flags)
   int n_lm_all = 0;
-  for (int p = 0; p < n_pt; ++p) if (pt_act[p]) { bucket[first_kf[p] + 1]++; ++n_lm_all; }
-  for (int k = 0; k <= n_kf; ++k) bucket[k + 1] += bucket[k];
-  std::vector<int> all_lm_pt(n_lm_all), rank_of_pt(n_pt, -1), pt_lm_all(n_pt, -1);
-  {
-    int g = 0;
-    for (int p = 0; p < n_pt; ++p)
-      if (pt_act[p]) { rank_of_pt[p] = g++; const int l = bucket[first_kf[p]]++; all_lm_pt[l] = p; pt_lm_all[p] = l; }  // g2o landmark index = rank among active points
+  DBuf<int> d_pkey, d_pkey_s, d_pval, d_sorted_pt, d_pt_lm_all, d_rank_of_pt, d_cnt_all;
+  const size_t npt1 = (size_t)std::max(n_pt, 1);
+  CKR(d_pkey.alloc(npt1)); CKR(d_pkey_s.alloc(npt1)); CKR(d_pval.alloc(npt1)); CKR(d_sorted_pt.alloc(npt1)); CKR(d_pt_lm_all.alloc(npt1)); CKR(d_rank_of_pt.alloc(npt1));
+  if (n_pt > 0) {
+    k_point_keys<<<(n_pt + 255) / 256, 256, 0, stream>>>(n_pt, d_pt_act.p, d_first_kf.p, n_kf, d_pkey.p, d_pval.p);
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, d_pkey.p, d_pkey_s.p, d_pval.p, d_sorted_pt.p, n_pt, 0, bits_for((unsigned long long)n_kf + 1), stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, d_pkey.p, d_pkey_s.p, d_pval.p, d_sorted_pt.p, n_pt, 0, bits_for((unsigned long long)n_kf + 1), stream));
+    need = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, d_pt_act.p, d_rank_of_pt.p, n_pt, stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, need, d_pt_act.p, d_rank_of_pt.p, n_pt, stream));
+    int last_rank = 0, last_act = 0;
+    CK(cudaMemcpyAsync(&last_rank, d_rank_of_pt.p + (n_pt - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&last_act, d_pt_act.p + (n_pt - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    n_lm_all = last_rank + last_act;
+    k_point_index<<<(n_pt + 255) / 256, 256, 0, stream>>>(n_pt, n_lm_all, d_sorted_pt.p, d_pt_lm_all.p);
+    CK(cudaGetLastError());
   }
   lap("active set + landmark order");
   // --- multi-GPU: this rank owns a contiguous range of the sorted landmarks, balanced by observation count;
   //     patterns (Hpp, Hschur) are built from ALL landmarks so that every rank packs the same block list
+  CKR(d_cnt_all.alloc((size_t)n_lm_all + 1));
+  CK(cudaMemsetAsync(d_cnt_all.p, 0, sizeof(int) * ((size_t)n_lm_all + 1), stream));
+  if (n_obs > 0 && n_lm_all > 0) {
+    k_count_lm_obs<<<gall, 256, 0, stream>>>(n_obs, d_all_flags.p, d_all_pt.p, d_pt_lm_all.p, 0, d_cnt_all.p);
+    CK(cudaGetLastError());
+  }
   int own_lo = 0, own_hi = n_lm_all;
   if (nranks > 1) {
+    std::vector<int> c((size_t)n_lm_all + 1, 0);
+    CK(cudaMemcpyAsync(c.data(), d_cnt_all.p, sizeof(int) * (size_t)n_lm_all, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
     std::vector<int64_t> cnt(n_lm_all + 1, 0);
-    for (int64_t i = 0; i < n_obs; ++i) if (!(obs_flags[i] & GPBA_OBS_LEVEL1)) cnt[pt_lm_all[obs_pt[i]] + 1]++;
-    for (int l = 0; l < n_lm_all; ++l) cnt[l + 1] += cnt[l];
+    for (int l = 0; l < n_lm_all; ++l) cnt[l + 1] = cnt[l] + c[l];
     const int64_t total = cnt[n_lm_all];
     auto cut = [&](int r) { return (int)(std::lower_bound(cnt.begin(), cnt.end(), total * r / nranks) - cnt.begin()); };
     own_lo = rank == 0 ? 0 : std::min(cut(rank), n_lm_all);
     own_hi = rank == nranks - 1 ? n_lm_all : std::min(cut(rank + 1), n_lm_all);
     if (own_hi < own_lo) own_hi = own_lo;
   }
-  lm_pt.assign(all_lm_pt.begin() + own_lo, all_lm_pt.begin() + own_hi);
-  n_lm = (int)lm_pt.size();
-  lm_rank.resize(n_lm);
-  for (int l = 0; l < n_lm; ++l) lm_rank[l] = rank_of_pt[lm_pt[l]];
+  n_lm = own_hi - own_lo;
   // --- compute list: active observations of the own landmarks, sorted by landmark (stable: insertion order inside)
-  lm_obs_begin.assign(n_lm + 1, 0);
-  for (int64_t i = 0; i < n_obs; ++i) {
-    if (obs_flags[i] & GPBA_OBS_LEVEL1) continue;
-    const int l = pt_lm_all[obs_pt[i]] - own_lo;
-    if (l >= 0 && l < n_lm) lm_obs_begin[l + 1]++;
+  const size_t nl1 = (size_t)n_lm + 1;
+  DBuf<int> d_okey, d_okey_s, d_rcnt;
+  DBuf<int64_t> d_oval, d_cnt64, d_npair, d_lm_pair_begin;
+  CKR(d_cnt64.alloc(nl1)); CKR(d_lm_obs_begin.alloc(nl1)); CKR(d_npair.alloc(nl1)); CKR(d_lm_pair_begin.alloc(nl1));
+  CKR(d_lm_pt.alloc((size_t)std::max(n_lm, 1)));
+  DBuf<int> d_lm_rank;
+  CKR(d_lm_rank.alloc((size_t)std::max(n_lm, 1)));
+  k_widen<<<(int)((nl1 + 255) / 256), 256, 0, stream>>>(n_lm + 1, d_cnt_all.p + own_lo, d_cnt64.p);
+  if (n_lm > 0) {
+    CK(cudaMemsetAsync(d_cnt64.p + n_lm, 0, sizeof(int64_t), stream));  // the entry after the range belongs to the next rank
+    CK(cudaMemcpyAsync(d_lm_pt.p, d_sorted_pt.p + own_lo, sizeof(int) * (size_t)n_lm, cudaMemcpyDeviceToDevice, stream));
+    k_lm_rank<<<(n_lm + 255) / 256, 256, 0, stream>>>(n_lm, d_lm_pt.p, d_rank_of_pt.p, d_lm_rank.p);
   }
-  for (int l = 0; l < n_lm; ++l) lm_obs_begin[l + 1] += lm_obs_begin[l];
+  CKR(excl_scan64(d_cnt64.p, d_lm_obs_begin.p, n_lm + 1));
+  k_pair_counts<<<(int)((nl1 + 255) / 256), 256, 0, stream>>>(n_lm, d_cnt_all.p + own_lo, d_npair.p);
+  CKR(excl_scan64(d_npair.p, d_lm_pair_begin.p, n_lm + 1));
+  CK(cudaGetLastError());
+  lm_obs_begin.assign(nl1, 0);
+  lm_pt.assign((size_t)n_lm, 0); lm_rank.assign((size_t)n_lm, 0);
+  CK(cudaMemcpyAsync(lm_obs_begin.data(), d_lm_obs_begin.p, sizeof(int64_t) * nl1, cudaMemcpyDeviceToHost, stream));
+  if (n_lm > 0) {
+    CK(cudaMemcpyAsync(lm_pt.data(), d_lm_pt.p, sizeof(int) * (size_t)n_lm, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(lm_rank.data(), d_lm_rank.p, sizeof(int) * (size_t)n_lm, cudaMemcpyDeviceToHost, stream));
+  }
+  CK(cudaMemcpyAsync(&n_pairs, d_lm_pair_begin.p + n_lm, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
   n_aobs = lm_obs_begin[n_lm];
-  o_orig.assign((size_t)n_aobs, 0);
-  std::vector<int64_t> rcount(n_rec + 1, 0);
-  {
-    std::vector<int64_t> cursor(lm_obs_begin.begin(), lm_obs_begin.end() - 1);
-    for (int64_t i = 0; i < n_obs; ++i) {
-      if (obs_flags[i] & GPBA_OBS_LEVEL1) continue;
-      const int l = pt_lm_all[obs_pt[i]] - own_lo;
-      if (l >= 0 && l < n_lm) { o_orig[cursor[l]++] = i; rcount[obs_rec[i] + 1]++; }
-    }
-  }
-  for (int r = 0; r < n_rec; ++r) rcount[r + 1] += rcount[r];
-  lap("observation bucket sort");
-  // --- device: sorted observation arrays
-  CKR(d_kf_h.upload(kf_h, stream));
-  CKR(d_o_orig.upload(o_orig, stream)); CKR(d_lm_obs_begin.upload(lm_obs_begin, stream)); CKR(d_lm_pt.upload(lm_pt, stream));
-  CKR(d_all_flags.upload(obs_flags, stream));
   const size_t na = (size_t)std::max<int64_t>(n_aobs, 1);
-  CKR(d_o_u.alloc(na)); CKR(d_o_v.alloc(na)); CKR(d_o_w.alloc(na)); CKR(d_o_rec.alloc(na)); CKR(d_o_lm.alloc(na)); CKR(d_o_flags.alloc(na));
+  CKR(d_o_orig.alloc(na)); CKR(d_o_lm.alloc(na));
+  if (n_obs > 0) {
+    const size_t no = (size_t)n_obs;
+    CKR(d_okey.alloc(no)); CKR(d_okey_s.alloc(no)); CKR(d_oval.alloc(no));
+    DBuf<int64_t> d_oval_s;
+    CKR(d_oval_s.alloc(no));
+    k_obs_keys<<<gall, 256, 0, stream>>>(n_obs, d_all_flags.p, d_all_pt.p, d_pt_lm_all.p, own_lo, n_lm, 0, d_okey.p, d_oval.p);
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, d_okey.p, d_okey_s.p, d_oval.p, d_oval_s.p, n_obs, 0, bits_for((unsigned long long)n_lm), stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, d_okey.p, d_okey_s.p, d_oval.p, d_oval_s.p, n_obs, 0, bits_for((unsigned long long)n_lm), stream));
+    if (n_aobs > 0) {
+      CK(cudaMemcpyAsync(d_o_orig.p, d_oval_s.p, sizeof(int64_t) * (size_t)n_aobs, cudaMemcpyDeviceToDevice, stream));
+      CK(cudaMemcpyAsync(d_o_lm.p, d_okey_s.p, sizeof(int) * (size_t)n_aobs, cudaMemcpyDeviceToDevice, stream));
+    }
+    CK(cudaStreamSynchronize(stream));   // the temporaries above go back to the pool in stream order anyway
+  }
+  lap("observation sort");
+  // --- device: sorted observation arrays
+  CKR(d_o_u.alloc(na)); CKR(d_o_v.alloc(na)); CKR(d_o_w.alloc(na)); CKR(d_o_rec.alloc(na)); CKR(d_o_flags.alloc(na));
   if (stereo) CKR(d_o_ur.alloc(na));
   const int gobs = (int)std::min<int64_t>((n_aobs + 255) / 256 + 1, 148 * 16);
+  std::vector<int64_t> rcount(n_rec + 1, 0);
   if (n_aobs > 0) {
     k_gather_obs<<<gobs, 256, 0, stream>>>(n_aobs, d_o_orig.p, d_all_u.p, d_all_v.p, stereo ? d_all_ur.p : nullptr, d_all_w.p, d_all_rec.p,
                                            d_all_flags.p, d_o_u.p, d_o_v.p, stereo ? d_o_ur.p : nullptr, d_o_w.p, d_o_rec.p, d_o_flags.p);
-    k_fill_lm<<<std::min((n_lm + 7) / 8, 148 * 16), 256, 0, stream>>>(n_lm, d_lm_obs_begin.p, d_o_lm.p);
+    CKR(d_rcnt.alloc((size_t)n_rec));
+    CK(cudaMemsetAsync(d_rcnt.p, 0, sizeof(int) * (size_t)n_rec, stream));
+    k_hist_int<<<gobs, 256, 0, stream>>>(n_aobs, d_o_rec.p, d_rcnt.p);
     CK(cudaGetLastError());
+    std::vector<int> rc((size_t)n_rec);
+    CK(cudaMemcpyAsync(rc.data(), d_rcnt.p, sizeof(int) * (size_t)n_rec, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int r = 0; r < n_rec; ++r) rcount[r + 1] = rcount[r] + rc[r];
   }
-  lap("upload + gather");
+  lap("gather");
   // --- device: observation pairs grouped by record pair
-  std::vector<int64_t> lm_pair_begin(n_lm + 1, 0);
-  for (int l = 0; l < n_lm; ++l) { const int64_t n = lm_obs_begin[l + 1] - lm_obs_begin[l]; lm_pair_begin[l + 1] = lm_pair_begin[l] + n * (n + 1) / 2; }
-  n_pairs = lm_pair_begin[n_lm];
   std::vector<unsigned long long> rp_key;   // unique record pairs of the compute list, ascending
   const unsigned long long nrec2 = (unsigned long long)n_rec * (unsigned long long)n_rec;
   const int LM_CHUNK = 8192;                // landmarks per chunk: ~12 MB of U rows at 10 observations per landmark
   // One pass = emit + sort + run-length encode.  with_items: runs of (chunk, record pair) become the work items of K4b
   // and the sorted observation pairs are kept; otherwise only the unique record pairs are wanted (pattern).
-  auto pair_pass = [&](int nl, const DBuf<int64_t>& d_lob, const std::vector<int64_t>& lpb, const int* d_rec_sorted, bool with_items,
+  auto pair_pass = [&](int nl, const int64_t* d_lob, const int64_t* d_lpb, int64_t np, const int* d_rec_sorted, bool with_items,
                        std::vector<unsigned long long>& keys_out) -> int {
-    const int64_t np = lpb[nl];
     keys_out.clear();
     if (with_items) { n_items = 0; n_rp = 0; }
     if (np == 0) return GPBA_OK;
     const int chunk = with_items ? LM_CHUNK : 0;
     const unsigned long long n_chunks = chunk ? (unsigned long long)((nl + chunk - 1) / chunk) : 1ull;
-    DBuf<int64_t> d_lpb;
     DBuf<unsigned long long> k0, k1, v0, v1, uq;
     DBuf<int> cnt, runs, dup;
-    CKR(d_lpb.upload(lpb, stream));
     CKR(k0.alloc((size_t)np)); CKR(k1.alloc((size_t)np)); CKR(v0.alloc((size_t)np)); CKR(v1.alloc((size_t)np));
     CKR(uq.alloc((size_t)np)); CKR(cnt.alloc((size_t)np)); CKR(runs.alloc(1)); CKR(dup.alloc(1));
     CK(cudaMemsetAsync(dup.p, 0, sizeof(int), stream));
-    k_emit_pairs<<<std::min((nl + 7) / 8, 148 * 16), 256, 0, stream>>>(nl, d_lob.p, d_lpb.p, d_rec_sorted, (unsigned long long)n_rec, chunk, k0.p, v0.p, dup.p);
+    k_emit_pairs<<<std::min((nl + 7) / 8, 148 * 16), 256, 0, stream>>>(nl, d_lob, d_lpb, d_rec_sorted, (unsigned long long)n_rec, chunk, k0.p, v0.p, dup.p);
     CK(cudaGetLastError());
     int h_runs = 0;
     unsigned long long *pk = k0.p, *pv = v0.p, *pka = k1.p, *pva = v1.p;
@@ -546,30 +630,41 @@ int Solver::build_structure() {
     CK(cudaStreamSynchronize(stream));
     if (h_dup) { g_err = "two observations of one landmark share a (keyframe pair, camera) record"; return GPBA_ERR_INVALID; }
     keys_out.resize(h_nrp);
+    CKR(d_rp_key.alloc((size_t)h_nrp));
+    CK(cudaMemcpyAsync(d_rp_key.p, rpk.p, sizeof(unsigned long long) * h_nrp, cudaMemcpyDeviceToDevice, stream));
     CK(cudaMemcpyAsync(keys_out.data(), rpk.p, sizeof(unsigned long long) * h_nrp, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     n_items = ni; n_rp = h_nrp;
     return GPBA_OK;
   };
-  CKR(pair_pass(n_lm, d_lm_obs_begin, lm_pair_begin, d_o_rec.p, true, rp_key));
+  CKR(pair_pass(n_lm, d_lm_obs_begin.p, d_lm_pair_begin.p, n_pairs, d_o_rec.p, true, rp_key));
   // pattern keys: all edges (any level) of all active landmarks (block_solver.hpp:262-288) -- a second, key-only pass
   // when that set differs from the compute list (level-1 edges, or landmarks owned by other ranks)
   std::vector<unsigned long long> pat_key_store;
   const std::vector<unsigned long long>* pat_key = &rp_key;
-  if (any_level1 || nranks > 1) {
-    std::vector<int64_t> lob(n_lm_all + 1, 0);
-    for (int64_t i = 0; i < n_obs; ++i) { const int l = pt_lm_all[obs_pt[i]]; if (l >= 0) lob[l + 1]++; }
-    for (int l = 0; l < n_lm_all; ++l) lob[l + 1] += lob[l];
-    std::vector<int> recs((size_t)lob[n_lm_all]);
-    {
-      std::vector<int64_t> cursor(lob.begin(), lob.end() - 1);
-      for (int64_t i = 0; i < n_obs; ++i) { const int l = pt_lm_all[obs_pt[i]]; if (l >= 0) recs[cursor[l]++] = obs_rec[i]; }
-    }
-    std::vector<int64_t> lpb(n_lm_all + 1, 0);
-    for (int l = 0; l < n_lm_all; ++l) { const int64_t n = lob[l + 1] - lob[l]; lpb[l + 1] = lpb[l] + n * (n + 1) / 2; }
-    DBuf<int64_t> d_lob; DBuf<int> d_recs;
-    CKR(d_lob.upload(lob, stream)); CKR(d_recs.upload(recs, stream));
-    CKR(pair_pass(n_lm_all, d_lob, lpb, d_recs.p, false, pat_key_store));
+  if ((any_level1 || nranks > 1) && n_lm_all > 0) {
+    const size_t nla1 = (size_t)n_lm_all + 1, no = (size_t)n_obs;
+    DBuf<int> cnt_any, key, key_s, recs;
+    DBuf<int64_t> cnt64, lob, npair, lpb, val, val_s;
+    CKR(cnt_any.alloc(nla1)); CKR(cnt64.alloc(nla1)); CKR(lob.alloc(nla1)); CKR(npair.alloc(nla1)); CKR(lpb.alloc(nla1));
+    CKR(key.alloc(no)); CKR(key_s.alloc(no)); CKR(val.alloc(no)); CKR(val_s.alloc(no)); CKR(recs.alloc(no));
+    CK(cudaMemsetAsync(cnt_any.p, 0, sizeof(int) * nla1, stream));
+    k_count_lm_obs<<<gall, 256, 0, stream>>>(n_obs, d_all_flags.p, d_all_pt.p, d_pt_lm_all.p, 1, cnt_any.p);
+    k_widen<<<(int)((nla1 + 255) / 256), 256, 0, stream>>>(n_lm_all + 1, cnt_any.p, cnt64.p);
+    CKR(excl_scan64(cnt64.p, lob.p, n_lm_all + 1));
+    k_pair_counts<<<(int)((nla1 + 255) / 256), 256, 0, stream>>>(n_lm_all, cnt_any.p, npair.p);
+    CKR(excl_scan64(npair.p, lpb.p, n_lm_all + 1));
+    k_obs_keys<<<gall, 256, 0, stream>>>(n_obs, d_all_flags.p, d_all_pt.p, d_pt_lm_all.p, 0, n_lm_all, 1, key.p, val.p);
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, key.p, key_s.p, val.p, val_s.p, n_obs, 0, bits_for((unsigned long long)n_lm_all), stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, key.p, key_s.p, val.p, val_s.p, n_obs, 0, bits_for((unsigned long long)n_lm_all), stream));
+    int64_t n_any = 0, np_any = 0;
+    CK(cudaMemcpyAsync(&n_any, lob.p + n_lm_all, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&np_any, lpb.p + n_lm_all, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (n_any > 0) { k_gather_int<<<gall, 256, 0, stream>>>(n_any, val_s.p, d_all_rec.p, recs.p); CK(cudaGetLastError()); }
+    CKR(pair_pass(n_lm_all, lob.p, lpb.p, np_any, recs.p, false, pat_key_store));
     pat_key = &pat_key_store;
   }
   lap("pair sort");
@@ -586,8 +681,8 @@ int Solver::build_structure() {
     n_hpl = (int64_t)h;
   }
   lap("hpl count");
-  // --- Hpp pattern (upper): diagonals + priors + the keyframe pair of every record with an active edge
-  std::vector<std::vector<int>> pp_rows(n_pose), hs_rows;
+  // --- Hpp pattern (upper, host: a few thousand blocks): diagonals + priors + the keyframe pair of every used record
+  std::vector<std::vector<int>> pp_rows(n_pose);
   auto add_pair = [](std::vector<std::vector<int>>& rows, int a, int b) {
     if (a < 0 || b < 0) return;
     if (a > b) std::swap(a, b);
@@ -597,43 +692,14 @@ int Solver::build_structure() {
   for (int i = 0; i < n_prior; ++i) add_pair(pp_rows, kf_h[prior_kf1[i]], kf_h[prior_kf2[i]]);
   for (int r = 0; r < n_rec; ++r)
     if (rec_used[r] && rec_kf1[r] >= 0) add_pair(pp_rows, kf_h[rec_kf1[r]], kf_h[rec_kf2[r]]);
-  auto uniq = [](std::vector<std::vector<int>>& rows) {
-    for (auto& v : rows) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
-  };
-  uniq(pp_rows);
-  // --- Hschur pattern: Hpp pattern U pose pairs of all edges of active landmarks
-  hs_rows = pp_rows;
-  auto rec_pose = [&](int r, int which) { const int k = which ? rec_kf2[r] : rec_kf1[r]; return k >= 0 ? kf_h[k] : -1; };
-  for (unsigned long long key : *pat_key) {
-    const int r1 = (int)(key / (unsigned long long)n_rec), r2 = (int)(key % (unsigned long long)n_rec);
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b) add_pair(hs_rows, rec_pose(r1, a), rec_pose(r2, b));
-  }
-  uniq(hs_rows);
-  auto flatten = [&](const std::vector<std::vector<int>>& rows, std::vector<int>& prow, std::vector<int>& pcol,
-                     std::vector<std::vector<int>>& ids) {
-    // order by (col, row) like the columns of a SparseBlockMatrix
-    std::vector<std::pair<int, int>> cr;
-    for (int r = 0; r < (int)rows.size(); ++r) for (int c : rows[r]) cr.push_back({c, r});
-    std::sort(cr.begin(), cr.end());
-    prow.resize(cr.size()); pcol.resize(cr.size());
-    ids.assign(rows.size(), {});
-    for (int r = 0; r < (int)rows.size(); ++r) ids[r].assign(rows[r].size(), -1);
-    for (size_t k = 0; k < cr.size(); ++k) {
-      prow[k] = cr[k].second; pcol[k] = cr[k].first;
-      const std::vector<int>& row = rows[cr[k].second];
-      ids[cr[k].second][std::lower_bound(row.begin(), row.end(), cr[k].first) - row.begin()] = (int)k;
-    }
-  };
-  std::vector<std::vector<int>> pp_ids, hs_ids;
-  flatten(pp_rows, hpp_row, hpp_col, pp_ids);
-  flatten(hs_rows, hs_row, hs_col, hs_ids);
-  n_hpp = (int)hpp_row.size(); n_hs = (int)hs_row.size();
-  auto lookup = [](const std::vector<std::vector<int>>& rows, const std::vector<std::vector<int>>& ids, int r, int c) {
-    const std::vector<int>& row = rows[r];
-    return ids[r][std::lower_bound(row.begin(), row.end(), c) - row.begin()];
-  };
-  auto pp = [&](int a, int b) { return lookup(pp_rows, pp_ids, a, b); };
+  for (auto& v : pp_rows) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+  std::vector<unsigned long long> hpp_key;   // (col << 32 | row), sorted: the order of SparseBlockMatrix columns
+  for (int r = 0; r < n_pose; ++r) for (int c : pp_rows[r]) hpp_key.push_back(((unsigned long long)c << 32) | (unsigned)r);
+  std::sort(hpp_key.begin(), hpp_key.end());
+  n_hpp = (int)hpp_key.size();
+  hpp_row.resize(n_hpp); hpp_col.resize(n_hpp);
+  for (int k = 0; k < n_hpp; ++k) { hpp_row[k] = (int)(unsigned)hpp_key[k]; hpp_col[k] = (int)(hpp_key[k] >> 32); }
+  auto pp = [&](int a, int b) { return (int)(std::lower_bound(hpp_key.begin(), hpp_key.end(), ((unsigned long long)b << 32) | (unsigned)a) - hpp_key.begin()); };
   std::vector<int> rec11(n_rec, -1), rec12(n_rec, -1), rec22(n_rec, -1), pr11(n_prior, -1), pr12(n_prior, -1), pr22(n_prior, -1);
   auto pair_blocks = [&](int h1, int h2, int& b11, int& b12, int& b22) {
     if (h1 >= 0) b11 = pp(h1, h1);
@@ -643,61 +709,91 @@ int Solver::build_structure() {
   for (int r = 0; r < n_rec; ++r)
     if (rec_used[r]) pair_blocks(rec_kf1[r] >= 0 ? kf_h[rec_kf1[r]] : -1, kf_h[rec_kf2[r]], rec11[r], rec12[r], rec22[r]);
   for (int i = 0; i < n_prior; ++i) pair_blocks(kf_h[prior_kf1[i]], kf_h[prior_kf2[i]], pr11[i], pr12[i], pr22[i]);
-  std::vector<int> pose_diag(n_pose), hs_from(n_hs, -1), hs_diag(n_hs, -1);
+  std::vector<int> pose_diag(n_pose);
   for (int i = 0; i < n_pose; ++i) pose_diag[i] = pp(i, i);
-  for (int k = 0; k < n_hpp; ++k) hs_from[lookup(hs_rows, hs_ids, hpp_row[k], hpp_col[k])] = k;
-  for (int k = 0; k < n_hs; ++k) if (hs_row[k] == hs_col[k]) hs_diag[k] = hs_row[k];
-  lap("patterns");
-  // --- K4c contribution lists: which record pairs feed which Hschur block, as (left record slice, right record slice,
-  //     transpose flag); bucketed by block, then grouped by left record slice inside a block
-  std::vector<int> con_begin(n_hs + 1, 0);
-  std::vector<HsContrib> con;
+  // --- Hschur pattern (device): Hpp pattern U pose pairs of all edges of active landmarks = sorted unique block keys
+  DBuf<unsigned long long> d_hs_key;
   {
-    // pass 0 counts, pass 1 fills (same enumeration)
-    std::vector<int> cursor;
-    for (int pass = 0; pass < 2; ++pass) {
-      auto emit = [&](int blk, int sidx, int rL, int aL, int rR, int aR, int tr, int gflag) {
-        if (pass == 0) con_begin[blk + 1]++;
-        else con[cursor[blk]++] = HsContrib{sidx, rL, rR, aL | (aR << 1) | (tr << 2) | (gflag << 4)};
-      };
-      for (int sidx = 0; sidx < n_rp; ++sidx) {
-        const int r1 = (int)(rp_key[sidx] / (unsigned long long)n_rec), r2 = (int)(rp_key[sidx] % (unsigned long long)n_rec);
-        for (int a = 0; a < 2; ++a)
-          for (int b = 0; b < 2; ++b) {
-            if (r1 == r2 && a > b) continue;  // the mirror image of (b, a)
-            const int pa = rec_pose(r1, a), pb = rec_pose(r2, b);
-            if (pa < 0 || pb < 0) continue;
-            const int blk = lookup(hs_rows, hs_ids, std::min(pa, pb), std::max(pa, pb));
-            if (pa < pb) emit(blk, sidx, r1, a, r2, b, 0, 0);
-            else if (pa > pb) emit(blk, sidx, r2, b, r1, a, 1, 0);          // upper storage holds the transposed product
-            else if (r1 == r2) emit(blk, sidx, r1, a, r2, b, 0, 1);         // a == b: symmetric, carries g'_r for bschur
-            else { emit(blk, sidx, r1, a, r2, b, 0, 0); emit(blk, sidx, r2, b, r1, a, 1, 0); }  // both ordered pairs land in (pa, pa)
-          }
-      }
-      if (pass == 0) {
-        for (int k = 0; k < n_hs; ++k) con_begin[k + 1] += con_begin[k];
-        con.resize((size_t)con_begin[n_hs]);
-        cursor.assign(con_begin.begin(), con_begin.end() - 1);
-      }
+    const int npat = (int)pat_key->size();
+    const size_t nk = (size_t)npat * 4 + hpp_key.size();
+    DBuf<unsigned long long> d_patk, kin, kout;
+    DBuf<int> d_nsel;
+    CKR(kin.alloc(nk)); CKR(kout.alloc(nk)); CKR(d_hs_key.alloc(nk)); CKR(d_nsel.alloc(1));
+    if (npat) {
+      const unsigned long long* src = d_rp_key.p;
+      if (pat_key != &rp_key) { CKR(d_patk.upload(*pat_key, stream)); src = d_patk.p; }
+      k_emit_block_keys<<<(npat + 255) / 256, 256, 0, stream>>>(V, npat, src, kin.p);
+      CK(cudaGetLastError());
     }
-    n_con = (int64_t)con.size();
-    for (int k = 0; k < n_hs; ++k) {   // group by left record slice (stable insertion sort: the lists are short)
-      HsContrib* lo = con.data() + con_begin[k];
-      const int n = con_begin[k + 1] - con_begin[k];
-      auto key = [](const HsContrib& x) { return ((long long)x.rL << 1) | (x.code & 1); };
-      for (int q = 1; q < n; ++q) {
-        const HsContrib x = lo[q];
-        int w = q;
-        while (w > 0 && key(lo[w - 1]) > key(x)) { lo[w] = lo[w - 1]; --w; }
-        lo[w] = x;
-      }
-      for (int g = 0; g < n;) {
-        int ge = g;
-        while (ge < n && key(lo[ge]) == key(lo[g])) ++ge;
-        lo[g].code |= (ge - g) << 8;
-        g = ge;
-      }
+    if (!hpp_key.empty()) CK(cudaMemcpyAsync(kin.p + (size_t)npat * 4, hpp_key.data(), sizeof(unsigned long long) * hpp_key.size(), cudaMemcpyHostToDevice, stream));
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, need, kin.p, kout.p, (int)nk, 0, 64, stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceRadixSort::SortKeys(cub_tmp.p, need, kin.p, kout.p, (int)nk, 0, 64, stream));
+    need = 0;
+    CK(cub::DeviceSelect::Unique(nullptr, need, kout.p, d_hs_key.p, d_nsel.p, (int)nk, stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceSelect::Unique(cub_tmp.p, need, kout.p, d_hs_key.p, d_nsel.p, (int)nk, stream));
+    int nsel = 0;
+    CK(cudaMemcpyAsync(&nsel, d_nsel.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));   // also keeps hpp_key alive until its copy is done
+    std::vector<unsigned long long> hs_key(nsel);
+    if (nsel) CK(cudaMemcpyAsync(hs_key.data(), d_hs_key.p, sizeof(unsigned long long) * nsel, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (nsel && hs_key.back() == ~0ull) --nsel;   // the "no block" marker sorts last
+    n_hs = nsel;
+    hs_row.resize(n_hs); hs_col.resize(n_hs);
+    std::vector<int> hs_from(n_hs, -1), hs_diag(n_hs, -1);
+    for (int k = 0; k < n_hs; ++k) { hs_row[k] = (int)(unsigned)hs_key[k]; hs_col[k] = (int)(hs_key[k] >> 32); if (hs_row[k] == hs_col[k]) hs_diag[k] = hs_row[k]; }
+    for (int k = 0; k < n_hpp; ++k) hs_from[(int)(std::lower_bound(hs_key.begin(), hs_key.begin() + n_hs, hpp_key[k]) - hs_key.begin())] = k;
+    CKR(d_hs_from_hpp.upload(hs_from, stream)); CKR(d_hs_diag_pose.upload(hs_diag, stream));
+    CKR(d_hs_row.upload(hs_row, stream)); CKR(d_hs_col.upload(hs_col, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  lap("patterns");
+  // --- K4c contribution lists (device): which record pairs feed which Hschur block, as (left record slice, right record
+  //     slice, transpose flag), sorted by (block, left record slice) -- a stable radix sort keeps record-pair order inside
+  n_con = 0;
+  CKR(d_con_begin.alloc((size_t)n_hs + 1));
+  if (n_rp > 0 && n_hs > 0) {
+    const size_t cap = (size_t)n_rp * GPBA_MAX_CON_PER_RP;
+    DBuf<unsigned long long> kin, kout, guq;
+    DBuf<HsContrib> vin;
+    DBuf<int> nvalid, gcnt, gstart, gruns;
+    CKR(kin.alloc(cap)); CKR(kout.alloc(cap)); CKR(vin.alloc(cap)); CKR(d_con.alloc(cap)); CKR(nvalid.alloc(1));
+    CK(cudaMemsetAsync(nvalid.p, 0, sizeof(int), stream));
+    k_emit_contribs<<<(n_rp + 127) / 128, 128, 0, stream>>>(V, n_rp, d_rp_key.p, d_hs_key.p, n_hs, kin.p, vin.p, nvalid.p);
+    CK(cudaGetLastError());
+    const int kb = bits_for(((unsigned long long)n_hs * (unsigned long long)n_rec + (unsigned long long)n_rec) * 2ull);
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, kin.p, kout.p, vin.p, d_con.p, (int)cap, 0, 64, stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, kin.p, kout.p, vin.p, d_con.p, (int)cap, 0, 64, stream));
+    (void)kb;
+    int h_valid = 0;
+    CK(cudaMemcpyAsync(&h_valid, nvalid.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    n_con = h_valid;
+    CKR(guq.alloc((size_t)std::max(h_valid, 1))); CKR(gcnt.alloc((size_t)std::max(h_valid, 1))); CKR(gstart.alloc((size_t)std::max(h_valid, 1))); CKR(gruns.alloc(1));
+    if (h_valid > 0) {
+      need = 0;
+      CK(cub::DeviceRunLengthEncode::Encode(nullptr, need, kout.p, guq.p, gcnt.p, gruns.p, h_valid, stream));
+      CK(cub_tmp.reserve(need, stream));
+      CK(cub::DeviceRunLengthEncode::Encode(cub_tmp.p, need, kout.p, guq.p, gcnt.p, gruns.p, h_valid, stream));
+      int h_groups = 0;
+      CK(cudaMemcpyAsync(&h_groups, gruns.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      need = 0;
+      CK(cub::DeviceScan::ExclusiveSum(nullptr, need, gcnt.p, gstart.p, h_groups, stream));
+      CK(cub_tmp.reserve(need, stream));
+      CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, need, gcnt.p, gstart.p, h_groups, stream));
+      k_mark_groups<<<(h_groups + 255) / 256, 256, 0, stream>>>(h_groups, gstart.p, gcnt.p, d_con.p);
     }
+    k_con_begin<<<(n_hs + 256) / 256, 256, 0, stream>>>(n_hs, h_valid, 2ull * (unsigned long long)n_rec, kout.p, d_con_begin.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));
+  } else {
+    CK(cudaMemsetAsync(d_con_begin.p, 0, sizeof(int) * ((size_t)n_hs + 1), stream));
   }
   lap("contribution lists");
   // --- record-major permutation (K2b): sorted-obs indices grouped by record (stable device sort), split into segments
@@ -723,9 +819,7 @@ int Solver::build_structure() {
   CKR(d_rseg_rec.upload(rseg_rec, stream)); CKR(d_rseg_begin.upload(rseg_begin, stream));
   CKR(d_rec_hpp11.upload(rec11, stream)); CKR(d_rec_hpp12.upload(rec12, stream)); CKR(d_rec_hpp22.upload(rec22, stream));
   CKR(d_prior_hpp11.upload(pr11, stream)); CKR(d_prior_hpp12.upload(pr12, stream)); CKR(d_prior_hpp22.upload(pr22, stream));
-  CKR(d_pose_hpp_diag.upload(pose_diag, stream)); CKR(d_hs_from_hpp.upload(hs_from, stream)); CKR(d_hs_diag_pose.upload(hs_diag, stream));
-  CKR(d_hs_row.upload(hs_row, stream)); CKR(d_hs_col.upload(hs_col, stream));
-  CKR(d_con_begin.upload(con_begin, stream)); CKR(d_con.upload(con, stream));
+  CKR(d_pose_hpp_diag.upload(pose_diag, stream));
   // --- storage
   CKR(d_ptS[0].alloc((size_t)n_lm * 3)); CKR(d_ptS[1].alloc((size_t)n_lm * 3));
   CKR(d_hll.alloc((size_t)n_lm * 9)); CKR(d_bl.alloc((size_t)n_lm * 3)); CKR(d_ptL.alloc((size_t)n_lm * 9)); CKR(d_xl.alloc((size_t)n_lm * 3));
@@ -1211,7 +1305,17 @@ int gpba_create(const gpba_problem* prob, int device, gpba_handle** out) {
 }
 
 int gpba_destroy(gpba_handle* h) {
-  if (h) { cudaSetDevice(h->s.device); g_alloc_stream = h->s.stream; delete h; }
+  if (h) {
+    cudaSetDevice(h->s.device); g_alloc_stream = h->s.stream;
+    const bool verbose = getenv("GPBA_VERBOSE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    if (h->s.chol_graph) { cudaGraphExecDestroy(h->s.chol_graph); h->s.chol_graph = nullptr; }
+    if (h->s.chol_back_graph) { cudaGraphExecDestroy(h->s.chol_back_graph); h->s.chol_back_graph = nullptr; }
+    auto t1 = std::chrono::steady_clock::now();
+    delete h;
+    auto t2 = std::chrono::steady_clock::now();
+    if (verbose) fprintf(stderr, "[gpba] destroy: graphs %.2f ms, rest %.2f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+  }
   return GPBA_OK;
 }
 

@@ -13,9 +13,78 @@
 // contribution lists; see Solver::build_structure.
 #pragma once
 #include <cub/cub.cuh>
-#include "gpba_device.cuh"
+#include "gpba_kernels.cuh"
 
 namespace gpba {
+
+// ---- active set and orderings (SparseOptimizer::initializeOptimization, sparse_optimizer.cpp:199-267)
+// One pass over the observations: which records / points carry an active (level 0) edge, first keyframe of every
+// point, whether any level-1 edge exists.  Plain stores of the same value and atomicMin: the result is order independent.
+__global__ void k_scan_obs(int64_t n_obs, const uint8_t* __restrict__ flags, const int* __restrict__ rec, const int* __restrict__ pt,
+                           const int* __restrict__ rec_kf2, unsigned char* __restrict__ rec_used, int* __restrict__ pt_act,
+                           int* __restrict__ first_kf, int* __restrict__ any_level1) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    if (flags[i] & 0x2u) { *any_level1 = 1; continue; }
+    const int r = rec[i], p = pt[i];
+    rec_used[r] = 1;
+    pt_act[p] = 1;
+    atomicMin(first_kf + p, rec_kf2[r]);
+  }
+}
+// landmark order key of a point: first keyframe (locality of record / pose accesses); inactive points sort last
+__global__ void k_point_keys(int n_pt, const int* __restrict__ pt_act, const int* __restrict__ first_kf, int n_kf,
+                             int* __restrict__ key, int* __restrict__ val) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pt) { key[p] = pt_act[p] ? first_kf[p] : n_kf + 1; val[p] = p; }
+}
+__global__ void k_point_index(int n_pt, int n_lm_all, const int* __restrict__ sorted_pt, int* __restrict__ pt_lm_all) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n_pt) pt_lm_all[sorted_pt[l]] = l < n_lm_all ? l : -1;
+}
+// observations per landmark (all ranks' landmarks, level 0 only / any level)
+__global__ void k_count_lm_obs(int64_t n_obs, const uint8_t* __restrict__ flags, const int* __restrict__ pt,
+                               const int* __restrict__ pt_lm_all, int any_level, int* __restrict__ cnt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!any_level && (flags[i] & 0x2u)) continue;
+    const int l = pt_lm_all[pt[i]];
+    if (l >= 0) atomicAdd(cnt + l, 1);
+  }
+}
+// sort key of an observation: its landmark relative to the owned range, or the sentinel `n_own` (dropped)
+__global__ void k_obs_keys(int64_t n_obs, const uint8_t* __restrict__ flags, const int* __restrict__ pt, const int* __restrict__ pt_lm_all,
+                           int own_lo, int n_own, int any_level, int* __restrict__ key, int64_t* __restrict__ val) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    int l = -1;
+    if (any_level || !(flags[i] & 0x2u)) l = pt_lm_all[pt[i]];
+    l = l >= 0 ? l - own_lo : -1;
+    key[i] = (l >= 0 && l < n_own) ? l : n_own;
+    val[i] = i;
+  }
+}
+__global__ void k_gather_int(int64_t n, const int64_t* __restrict__ idx, const int* __restrict__ src, int* __restrict__ dst) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) dst[j] = src[idx[j]];
+}
+__global__ void k_hist_int(int64_t n, const int* __restrict__ key, int* __restrict__ cnt) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) atomicAdd(cnt + key[j], 1);
+}
+// n(n+1)/2 observation pairs per landmark
+__global__ void k_pair_counts(int n_lm, const int* __restrict__ cnt, int64_t* __restrict__ np) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n_lm) { const int64_t n = cnt[l]; np[l] = n * (n + 1) / 2; }
+  else if (l == n_lm) np[l] = 0;
+}
+__global__ void k_widen(int n, const int* __restrict__ in, int64_t* __restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n) out[l] = in[l];
+}
+__global__ void k_lm_rank(int n_lm, const int* __restrict__ lm_pt, const int* __restrict__ rank_of_pt, int* __restrict__ lm_rank) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n_lm) lm_rank[l] = rank_of_pt[lm_pt[l]];
+}
+__global__ void k_check_indices(int64_t n_obs, const int* __restrict__ rec, const int* __restrict__ pt, int n_rec, int n_pt, int* __restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x)
+    if (rec[i] < 0 || rec[i] >= n_rec || pt[i] < 0 || pt[i] >= n_pt) *bad = 1;
+}
 
 // sorted (by landmark) copies of the per-observation inputs
 __global__ void k_gather_obs(int64_t n, const int64_t* __restrict__ o_orig, const double* __restrict__ u,
@@ -124,6 +193,78 @@ __global__ void k_item_ranges(int n, const int64_t* __restrict__ begin_excl, con
                               int64_t* __restrict__ item_end) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { item_begin[i] = begin_excl[i]; item_end[i] = begin_excl[i] + count[i]; }
+}
+
+// ---- Hschur block pattern and K4c contribution lists from the unique record pairs (all integer, all on the device)
+GPBA_D int rec_pose(const DevView& V, int r, int which) {
+  const int k = which ? V.rec_kf2[r] : V.rec_kf1[r];
+  return k >= 0 ? V.kf_h[k] : -1;
+}
+GPBA_D unsigned long long block_key(int pa, int pb) {  // (col, row) with row <= col: the order of SparseBlockMatrix columns
+  const unsigned lo = (unsigned)(pa < pb ? pa : pb), hi = (unsigned)(pa < pb ? pb : pa);
+  return ((unsigned long long)hi << 32) | lo;
+}
+// four candidate pose-pair blocks per record pair (~0 = none)
+__global__ void k_emit_block_keys(DevView V, int n, const unsigned long long* __restrict__ rp_key, unsigned long long* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int r1 = (int)(rp_key[t] / (unsigned long long)V.n_rec), r2 = (int)(rp_key[t] % (unsigned long long)V.n_rec);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int pa = rec_pose(V, r1, q >> 1), pb = rec_pose(V, r2, q & 1);
+    out[4 * (size_t)t + q] = (pa >= 0 && pb >= 0) ? block_key(pa, pb) : ~0ull;
+  }
+}
+__global__ void k_split_block_keys(int n, const unsigned long long* __restrict__ key, int* __restrict__ row, int* __restrict__ col) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) { row[t] = (int)(unsigned)key[t]; col[t] = (int)(key[t] >> 32); }
+}
+GPBA_D int find_block(const unsigned long long* __restrict__ hs_key, int n_hs, unsigned long long key) {
+  int lo = 0, hi = n_hs - 1;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (hs_key[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// up to six (block, left record slice, right record slice, transpose) contributions per record pair, see k_schur_expand;
+// sort key = (block, left record, left slice)
+#define GPBA_MAX_CON_PER_RP 6
+__global__ void k_emit_contribs(DevView V, int n_rp, const unsigned long long* __restrict__ rp_key, const unsigned long long* __restrict__ hs_key,
+                                int n_hs, unsigned long long* __restrict__ keys, HsContrib* __restrict__ vals, int* __restrict__ n_valid) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_rp) return;
+  const int r1 = (int)(rp_key[t] / (unsigned long long)V.n_rec), r2 = (int)(rp_key[t] % (unsigned long long)V.n_rec);
+  int w = 0;
+  auto emit = [&](int blk, int rL, int aL, int rR, int aR, int tr, int g) {
+    keys[(size_t)t * GPBA_MAX_CON_PER_RP + w] = ((unsigned long long)blk * (unsigned long long)V.n_rec + (unsigned long long)rL) * 2ull + (unsigned long long)aL;
+    vals[(size_t)t * GPBA_MAX_CON_PER_RP + w] = HsContrib{t, rL, rR, aL | (aR << 1) | (tr << 2) | (g << 4)};
+    ++w;
+  };
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      if (r1 == r2 && a > b) continue;  // the mirror image of (b, a)
+      const int pa = rec_pose(V, r1, a), pb = rec_pose(V, r2, b);
+      if (pa < 0 || pb < 0) continue;
+      const int blk = find_block(hs_key, n_hs, block_key(pa, pb));
+      if (pa < pb) emit(blk, r1, a, r2, b, 0, 0);
+      else if (pa > pb) emit(blk, r2, b, r1, a, 1, 0);       // upper storage holds the transposed product
+      else if (r1 == r2) emit(blk, r1, a, r2, b, 0, 1);      // a == b: symmetric, carries g'_r for bschur
+      else { emit(blk, r1, a, r2, b, 0, 0); emit(blk, r2, b, r1, a, 1, 0); }  // both ordered pairs land in (pa, pa)
+    }
+  if (w) atomicAdd(n_valid, w);
+  for (; w < GPBA_MAX_CON_PER_RP; ++w) keys[(size_t)t * GPBA_MAX_CON_PER_RP + w] = ~0ull;
+}
+// group size into the first entry of every (block, left slice) run
+__global__ void k_mark_groups(int n_groups, const int* __restrict__ start, const int* __restrict__ count, HsContrib* __restrict__ con) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_groups) con[start[t]].code |= count[t] << 8;
+}
+// first contribution of every block (sorted keys)
+__global__ void k_con_begin(int n_hs, int n_con, unsigned long long two_nrec, const unsigned long long* __restrict__ keys, int* __restrict__ con_begin) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_hs) return;
+  const unsigned long long want = (unsigned long long)b * two_nrec;
+  int lo = 0, hi = n_con;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < want) lo = mid + 1; else hi = mid; }
+  con_begin[b] = lo;
 }
 
 // cub temp storage that grows on demand
