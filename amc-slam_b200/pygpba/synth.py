@@ -130,7 +130,9 @@ def make_problem(name="c1", *, seed=None, mode=None, linear_solver=None, **overr
     bf = float(np.float32(501.7))
 
     # ---- ground-truth trajectory: piecewise-constant body twist, closes a lap every `lap` keyframes
-    lap = cfg.get("lap", 500 if is_global and n_kf >= 600 else 8 * n_kf)
+    # global maps drive the same loop twice (second lap = the post-loop-closure revisit): C4 500 + 500
+    # keyframes, C5 5000 + 5000 (a 5 km loop driven twice = 10 km); local windows never close a loop
+    lap = cfg.get("lap", n_kf // 2 if is_global and n_kf >= 600 else 8 * n_kf)
     k = np.arange(n_kf)
     ph = 2 * np.pi * k / lap
     w0 = 2 * np.pi / (lap * dt)
