@@ -601,13 +601,14 @@ int Solver::build_structure() {
     CK(cudaMemcpyAsync(&h_dup, dup.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CKR(d_pairs.alloc((size_t)np));
     CK(cudaMemcpyAsync(d_pairs.p, pv, sizeof(unsigned long long) * (size_t)np, cudaMemcpyDeviceToDevice, stream));
-    // items = runs; slot of an item = rank of its record pair among the unique record pairs
+    // runs -> work items (long runs are cut); slot of a run = rank of its record pair among the unique record pairs
     const int ni = h_runs, gi = (ni + 255) / 256;
     DBuf<unsigned long long> low, low_s, rpk;
-    DBuf<int> idx, idx_s, head, slot_p1;
+    DBuf<int> idx, idx_s, head, slot_p1, run_rp, nsub, sub_begin;
+    DBuf<unsigned char> run_flags;
     DBuf<int64_t> beg;
     CKR(low.alloc(ni)); CKR(low_s.alloc(ni)); CKR(rpk.alloc(ni)); CKR(idx.alloc(ni)); CKR(idx_s.alloc(ni)); CKR(head.alloc(ni)); CKR(slot_p1.alloc(ni)); CKR(beg.alloc(ni));
-    CKR(d_item_rp.alloc(ni)); CKR(d_item_flags.alloc(ni)); CKR(d_item_begin.alloc(ni)); CKR(d_item_end.alloc(ni));
+    CKR(run_rp.alloc(ni)); CKR(run_flags.alloc(ni)); CKR(nsub.alloc((size_t)ni + 1)); CKR(sub_begin.alloc((size_t)ni + 1));
     k_item_low<<<gi, 256, 0, stream>>>(ni, uq.p, nrec2, low.p, idx.p);
     size_t need = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, need, low.p, low_s.p, idx.p, idx_s.p, ni, 0, bits_for(nrec2), stream));
@@ -618,15 +619,24 @@ int Solver::build_structure() {
     CK(cub::DeviceScan::InclusiveSum(nullptr, need, head.p, slot_p1.p, ni, stream));
     CK(cub_tmp.reserve(need, stream));
     CK(cub::DeviceScan::InclusiveSum(cub_tmp.p, need, head.p, slot_p1.p, ni, stream));
-    k_slot_assign<<<gi, 256, 0, stream>>>(ni, low_s.p, idx_s.p, head.p, slot_p1.p, (unsigned long long)n_rec, d_item_rp.p, d_item_flags.p, rpk.p);
+    k_slot_assign<<<gi, 256, 0, stream>>>(ni, low_s.p, idx_s.p, head.p, slot_p1.p, (unsigned long long)n_rec, run_rp.p, run_flags.p, rpk.p);
     need = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, need, cnt.p, beg.p, ni, stream));
     CK(cub_tmp.reserve(need, stream));
     CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, need, cnt.p, beg.p, ni, stream));
-    k_item_ranges<<<gi, 256, 0, stream>>>(ni, beg.p, cnt.p, d_item_begin.p, d_item_end.p);
-    CK(cudaGetLastError());
-    int h_nrp = 0;
+    CK(cudaMemsetAsync(nsub.p + ni, 0, sizeof(int), stream));
+    k_run_items<<<gi, 256, 0, stream>>>(ni, cnt.p, nsub.p);
+    need = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, nsub.p, sub_begin.p, ni + 1, stream));
+    CK(cub_tmp.reserve(need, stream));
+    CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, need, nsub.p, sub_begin.p, ni + 1, stream));
+    int h_nrp = 0, h_items = 0;
     CK(cudaMemcpyAsync(&h_nrp, slot_p1.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&h_items, sub_begin.p + ni, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CKR(d_item_rp.alloc(h_items)); CKR(d_item_flags.alloc(h_items)); CKR(d_item_begin.alloc(h_items)); CKR(d_item_end.alloc(h_items));
+    k_item_ranges<<<gi, 256, 0, stream>>>(ni, beg.p, cnt.p, sub_begin.p, run_rp.p, run_flags.p, d_item_begin.p, d_item_end.p, d_item_rp.p, d_item_flags.p);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(stream));
     if (h_dup) { g_err = "two observations of one landmark share a (keyframe pair, camera) record"; return GPBA_ERR_INVALID; }
     keys_out.resize(h_nrp);
@@ -634,7 +644,7 @@ int Solver::build_structure() {
     CK(cudaMemcpyAsync(d_rp_key.p, rpk.p, sizeof(unsigned long long) * h_nrp, cudaMemcpyDeviceToDevice, stream));
     CK(cudaMemcpyAsync(keys_out.data(), rpk.p, sizeof(unsigned long long) * h_nrp, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    n_items = ni; n_rp = h_nrp;
+    n_items = h_items; n_rp = h_nrp;
     return GPBA_OK;
   };
   CKR(pair_pass(n_lm, d_lm_obs_begin.p, d_lm_pair_begin.p, n_pairs, d_o_rec.p, true, rp_key));

@@ -189,10 +189,26 @@ __global__ void k_slot_assign(int n, const unsigned long long* __restrict__ low_
   item_flags[idx_sorted[p]] = (unsigned char)(((k / n_rec == k % n_rec) ? 1 : 0) | 2);  // several chunks feed one slot: accumulate atomically
   if (head[p]) rp_key[slot] = k;
 }
-__global__ void k_item_ranges(int n, const int64_t* __restrict__ begin_excl, const int* __restrict__ count, int64_t* __restrict__ item_begin,
-                              int64_t* __restrict__ item_end) {
+// a run of the sorted pair list longer than GPBA_ITEM_PAIRS is cut into several work items (the diagonal runs hold one
+// self pair per observation of a record inside the chunk -- hundreds -- and would otherwise be the kernel's critical path)
+#define GPBA_ITEM_PAIRS 64
+__global__ void k_run_items(int n, const int* __restrict__ count, int* __restrict__ n_sub) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { item_begin[i] = begin_excl[i]; item_end[i] = begin_excl[i] + count[i]; }
+  if (i < n) n_sub[i] = (count[i] + GPBA_ITEM_PAIRS - 1) / GPBA_ITEM_PAIRS;
+}
+__global__ void k_item_ranges(int n, const int64_t* __restrict__ begin_excl, const int* __restrict__ count, const int* __restrict__ sub_begin,
+                              const int* __restrict__ run_rp, const unsigned char* __restrict__ run_flags, int64_t* __restrict__ item_begin,
+                              int64_t* __restrict__ item_end, int* __restrict__ item_rp, unsigned char* __restrict__ item_flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t b = begin_excl[i], e = b + count[i];
+  int it = sub_begin[i];
+  for (int64_t q = b; q < e; q += GPBA_ITEM_PAIRS, ++it) {
+    item_begin[it] = q;
+    item_end[it] = q + GPBA_ITEM_PAIRS < e ? q + GPBA_ITEM_PAIRS : e;
+    item_rp[it] = run_rp[i];
+    item_flags[it] = run_flags[i];
+  }
 }
 
 // ---- Hschur block pattern and K4c contribution lists from the unique record pairs (all integer, all on the device)
