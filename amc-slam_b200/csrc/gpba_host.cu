@@ -164,7 +164,8 @@ struct Solver {
   int64_t n_hpl = 0, n_pairs = 0;
   // ------------------------------------------------------------------ structure (device)
   DBuf<int> d_kf_h, d_o_rec, d_o_lm, d_lm_pt, d_rseg_rec, d_item_rp, d_con_begin;
-  DBuf<double> d_o_u, d_o_v, d_o_ur, d_o_w;
+  DBuf<double> d_o_u, d_o_v, d_o_ur, d_o_w, d_r_u, d_r_v, d_r_ur, d_r_w;   // landmark-major and record-major copies
+  DBuf<int> d_r_lm; DBuf<uint8_t> d_r_flags;
   DBuf<uint8_t> d_o_flags, d_item_flags;
   DBuf<int64_t> d_o_orig, d_lm_obs_begin, d_rperm, d_rseg_begin, d_item_begin, d_item_end;
   DBuf<unsigned long long> d_pairs;     // observation pairs grouped by record pair (sorted order)
@@ -816,6 +817,11 @@ int Solver::build_structure() {
     CK(cub::DeviceRadixSort::SortPairs(nullptr, need, d_o_rec.p, kout.p, vin.p, d_rperm.p, n_aobs, 0, bits_for((unsigned long long)n_rec), stream));
     CK(cub_tmp.reserve(need, stream));
     CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, d_o_rec.p, kout.p, vin.p, d_rperm.p, n_aobs, 0, bits_for((unsigned long long)n_rec), stream));
+    CKR(d_r_u.alloc(na)); CKR(d_r_v.alloc(na)); CKR(d_r_w.alloc(na)); CKR(d_r_lm.alloc(na)); CKR(d_r_flags.alloc(na));
+    if (stereo) CKR(d_r_ur.alloc(na));
+    k_gather_recmajor<<<gobs, 256, 0, stream>>>(n_aobs, d_rperm.p, d_o_u.p, d_o_v.p, stereo ? d_o_ur.p : nullptr, d_o_w.p, d_o_lm.p, d_o_flags.p,
+                                                d_r_u.p, d_r_v.p, stereo ? d_r_ur.p : nullptr, d_r_w.p, d_r_lm.p, d_r_flags.p);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(stream));
   }
   const int SEG = 512;
@@ -1067,8 +1073,8 @@ int Solver::build_system() {
     t1(2, 1);
     t0();
     const int g2 = std::min((n_rseg + 3) / 4, 148 * 16);
-    if (stereo) k_lin_records<true><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p);
-    else k_lin_records<false><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p);
+    if (stereo) k_lin_records<true><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p, d_r_u.p, d_r_v.p, d_r_ur.p, d_r_w.p, d_r_lm.p, d_r_flags.p);
+    else k_lin_records<false><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p, d_r_u.p, d_r_v.p, nullptr, d_r_w.p, d_r_lm.p, d_r_flags.p);
     CK(cudaGetLastError());
     k_rec_to_hpp<<<n_rec, 128, 0, stream>>>(V, d_rec.p, d_recS.p, d_hpp.p, d_bp.p);
     CK(cudaGetLastError());

@@ -309,7 +309,10 @@ __global__ void __launch_bounds__(GPBA_K2_THREADS) k_lin_points(DevView V, const
 // (upper, 21 values) and g_r = -sum w J1^T e in registers, warp-shuffle reduces, one atomicAdd per value.
 template <bool STEREO>
 __global__ void __launch_bounds__(128) k_lin_records(DevView V, const double* __restrict__ rec,
-                                                     const double* __restrict__ pt, double* __restrict__ recS) {
+                                                     const double* __restrict__ pt, double* __restrict__ recS,
+                                                     const double* __restrict__ r_u, const double* __restrict__ r_v,
+                                                     const double* __restrict__ r_ur, const double* __restrict__ r_w,
+                                                     const int* __restrict__ r_lm, const uint8_t* __restrict__ r_flags) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ROWS = STEREO ? 3 : 2;
   for (int s = blockIdx.x * 4 + warp; s < V.n_rseg; s += gridDim.x * 4) {
@@ -320,14 +323,16 @@ __global__ void __launch_bounds__(128) k_lin_records(DevView V, const double* __
     double acc[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+    // record-major copies of the per-observation inputs (made once per structure): coalesced streams, only the
+    // landmark position is gathered
     for (int64_t j = V.rseg_begin[s] + lane; j < V.rseg_begin[s + 1]; j += 32) {
-      const int64_t i = V.rperm[j];
-      const int lm = V.o_lm[i];
+      const int lm = r_lm[j];
+      const double w = r_w[j];
       ObsEval<STEREO> E;
       double J1[ROWS][6], Jp[ROWS][3];
-      eval_obs<STEREO, true>(V, R, cam, pt[3 * (size_t)lm], pt[3 * (size_t)lm + 1], pt[3 * (size_t)lm + 2], V.o_u[i],
-                             V.o_v[i], STEREO ? V.o_ur[i] : -1.0, V.o_w[i], V.o_flags[i], E, J1, Jp);
-      const double wr = E.rho1 * V.o_w[i];
+      eval_obs<STEREO, true>(V, R, cam, pt[3 * (size_t)lm], pt[3 * (size_t)lm + 1], pt[3 * (size_t)lm + 2], r_u[j],
+                             r_v[j], STEREO ? r_ur[j] : -1.0, w, r_flags[j], E, J1, Jp);
+      const double wr = E.rho1 * w;
 #pragma unroll
       for (int rr = 0; rr < ROWS; ++rr) {
         int k = 0;

@@ -99,6 +99,18 @@ __global__ void k_gather_obs(int64_t n, const int64_t* __restrict__ o_orig, cons
   }
 }
 
+// record-major copies of the landmark-sorted observation inputs (K2b streams them)
+__global__ void k_gather_recmajor(int64_t n, const int64_t* __restrict__ rperm, const double* __restrict__ u, const double* __restrict__ v,
+                                  const double* __restrict__ ur, const double* __restrict__ w, const int* __restrict__ lm,
+                                  const uint8_t* __restrict__ flags, double* __restrict__ ru, double* __restrict__ rv,
+                                  double* __restrict__ rur, double* __restrict__ rw, int* __restrict__ rlm, uint8_t* __restrict__ rfl) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = rperm[j];
+    ru[j] = u[i]; rv[j] = v[i]; rw[j] = w[i]; rlm[j] = lm[i]; rfl[j] = flags[i];
+    if (ur) rur[j] = ur[i];
+  }
+}
+
 __global__ void k_iota(int64_t n, int64_t* __restrict__ out) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) out[j] = j;
 }

@@ -280,12 +280,14 @@ def make_problem(name="c1", *, seed=None, mode=None, linear_solver=None, **overr
     return prob
 
 
-def add_stereo(prob, fraction=0.5, seed=0):
-    """Turn a fraction of the synchronous (reference camera) observations into EdgeStereo (ur >= 0)."""
+def add_stereo(prob, fraction=0.5, seed=0, gp_fraction=0.0):
+    """Turn a fraction of the synchronous (reference camera) observations into EdgeStereo (ur >= 0) and, with
+    gp_fraction > 0, a fraction of the asynchronous ones into EdgeStereoGP (src/G2oTypes.cc:369-443)."""
     rng = np.random.default_rng(seed)
     ur = -np.ones(prob.n_obs)
     sync = prob.rec_kf1[prob.obs_rec] < 0
-    pick = sync & (rng.uniform(size=prob.n_obs) < fraction)
+    draw = rng.uniform(size=prob.n_obs)
+    pick = (sync & (draw < fraction)) | (~sync & (draw < gp_fraction))
     # ur = u - bf / z with z from the true geometry approximated through the current estimate is not needed for
     # parity tests: any plausible value works, use a depth of 8..40 m.
     z = rng.uniform(8.0, 40.0, prob.n_obs)

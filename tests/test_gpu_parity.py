@@ -164,6 +164,25 @@ def test_stereo_edges(G, oracle_mod):
     assert_trace_equal(g.optimize(6), o.optimize(6))
 
 
+def test_stereo_gp_edges(G, oracle_mod):
+    """EdgeStereoGP (3-d residual on an interpolated record, src/G2oTypes.cc:369-443): only reachable through the dead
+    GPObs path in the reference, implemented for completeness."""
+    P = synth.add_stereo(synth.make_problem("c1", n_pt=500, seed=39), 0.3, gp_fraction=0.4)
+    gp_stereo = (P.obs_ur >= 0) & (P.rec_kf1[P.obs_rec] >= 0)
+    assert gp_stereo.sum() > 500
+    g = G.GpBa(P); o = oracle_mod.Oracle(P)
+    g.build_structure(); o.build_structure()
+    assert abs(g.compute_errors() - o.compute_errors()) <= 1e-10 * o.compute_errors()
+    np.testing.assert_allclose(g.edge_chi2(), o.edge_chi2(), rtol=1e-9, atol=1e-12)
+    g.build_system(); o.build_system()
+    sc = np.abs(o.hpp()).max()
+    np.testing.assert_allclose(g.hpp(), o.hpp(), rtol=1e-9, atol=1e-12 * sc)
+    (bg, pg, Bg), (bo, po, Bo) = g.hpl(), o.hpl()
+    np.testing.assert_allclose(Bg, Bo, rtol=1e-9, atol=1e-12 * sc)
+    assert_trace_equal(g.optimize(6), o.optimize(6))
+    assert_state_close(g.state(), o.state())
+
+
 def test_edge_cases(G, oracle_mod):
     # a keyframe-only graph (no landmarks at all) and a landmark seen from fixed keyframes only
     P = synth.make_problem("tiny")
