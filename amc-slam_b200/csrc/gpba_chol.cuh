@@ -36,10 +36,10 @@ namespace gpba {
 __device__ long long g_chol_clk[64];
 __device__ __forceinline__ long long* chol_clk_smem() { __shared__ long long b[64]; return b; }
 // ticks go to shared memory and are dumped at the end: a global store in front of a barrier stalls ~900 cycles
-#define GPBA_TICK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 1 && k == 100) chol_clk_smem()[slot] = clock64(); } while (0)
-#define GPBA_TICK_DUMP() do { if (threadIdx.x == 0 && blockIdx.x == 1 && k == 100) for (int q_ = 0; q_ < 64; ++q_) g_chol_clk[q_] = chol_clk_smem()[q_]; } while (0)
+#define GPBA_TICK(slot) do { if (threadIdx.x == 0 && q_ == 1 && k == 100) chol_clk_smem()[slot] = clock64(); } while (0)
+#define GPBA_TICK_DUMP() do { if (threadIdx.x == 0 && q_ == 1 && k == 100) for (int q_ = 0; q_ < 64; ++q_) g_chol_clk[q_] = chol_clk_smem()[q_]; } while (0)
 #define GPBA_TICKP(slot) do { GPBA_TICK(16 + pb * 4 + (slot) - 5); \
-  if (blockIdx.x == 1 && k == 100 && pb == 5) { if (threadIdx.x == 74) chol_clk_smem()[40 + (slot) - 5] = clock64(); if (threadIdx.x == 160) chol_clk_smem()[44 + (slot) - 5] = clock64(); if (threadIdx.x == 64) chol_clk_smem()[48 + (slot) - 5] = clock64(); } } while (0)
+  if (q_ == 1 && k == 100 && pb == 5) { if (threadIdx.x == 74) chol_clk_smem()[40 + (slot) - 5] = clock64(); if (threadIdx.x == 160) chol_clk_smem()[44 + (slot) - 5] = clock64(); if (threadIdx.x == 64) chol_clk_smem()[48 + (slot) - 5] = clock64(); } } while (0)
 #else
 #define GPBA_TICK(slot) do { } while (0)
 #define GPBA_TICK_DUMP() do { } while (0)
@@ -156,7 +156,7 @@ GPBA_D void diag_block_inverse(const double (*S)[GPBA_LD], int b, int lane, doub
 // own row of the panel with it.  Meanwhile warp 3 inverts the previous panel's diagonal block for the blocked
 // triangular solves; the other warps stay off the FP64 pipe.  The trailing tile is then updated with DMMA by all
 // warps.  On exit S = L, D8[b] = (b-th 8x8 diagonal block of L)^-1.
-GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], int* fail, int k = -1) {
+GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], int* fail, int k = -1, int q_ = -1) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int r = tid;
 #pragma unroll 1
@@ -265,8 +265,10 @@ GPBA_D void trsm48(double (*T)[GPBA_LD], const double (*S)[GPBA_LD], const doubl
   }
 }
 
-// Panel step of tile column k.  grid = 1 + (#non-zero tiles below the diagonal).
-__global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, int k, int* __restrict__ fail) {
+// Panel step of the tile columns of one level.  One CTA per table entry (k, q): q = 0 is the diagonal CTA of column k,
+// q > 0 its q-th non-zero tile below the diagonal.
+__global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, const int2* __restrict__ tab, int* __restrict__ fail) {
+  const int k = tab[blockIdx.x].x, q_ = tab[blockIdx.x].y;
   __shared__ __align__(16) double S[GPBA_NB][GPBA_LD];
   __shared__ __align__(16) double T[GPBA_NB][GPBA_LD];
   __shared__ double D8[GPBA_NB / 8][8][8];
@@ -274,9 +276,9 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, i
   const int tid = threadIdx.x;
   GPBA_TICK(0);
   const double* Tkk = C.tiles + C.tile_off[(size_t)k * C.NT + k];   // static index data: may be read before the wait
-  double* A = blockIdx.x == 0 ? nullptr : C.tiles + C.tile_off[(size_t)C.col_rows[C.col_begin[k] + blockIdx.x - 1] * C.NT + k];
+  double* A = q_ == 0 ? nullptr : C.tiles + C.tile_off[(size_t)C.col_rows[C.col_begin[k] + q_ - 1] * C.NT + k];
   pdl_wait_then_release();
-  if (blockIdx.x == 0) {
+  if (q_ == 0) {
     tiles_to_smem<GPBA_PANEL_THREADS, 1>(Tkk, S, nullptr, nullptr);
     for (int j = tid; j < GPBA_NB * GPBA_NB; j += blockDim.x) T[j / GPBA_NB][j % GPBA_NB] = (j / GPBA_NB == j % GPBA_NB) ? 1.0 : 0.0;
     if (tid < GPBA_NB) Sy[tid] = C.work[k * GPBA_NB + tid];
@@ -285,12 +287,12 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, i
   }
   __syncthreads();
   GPBA_TICK(1);
-  potrf48(S, D8, fail, k);
+  potrf48(S, D8, fail, k, q_);
   GPBA_TICK(2);
   trsm48(T, S, D8);
   __syncthreads();
   GPBA_TICK(3);
-  if (blockIdx.x == 0) {
+  if (q_ == 0) {
     // T = L_kk^-T.  dinv[k] = L_kk^-1 = T^T (row-major), y_k = L_kk^-1 b_k
     double* D = C.dinv + (size_t)k * GPBA_NB * GPBA_NB;
     for (int j = tid; j < GPBA_NB * GPBA_NB; j += blockDim.x) D[j] = T[j % GPBA_NB][j / GPBA_NB];
@@ -313,15 +315,15 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, i
 // One CTA (4 warps) per pair; both L tiles staged in shared memory, the C tile prefetched into registers while
 // they arrive; each warp owns a 24 x 24 corner = 3 x 3 DMMA tiles (9 independent accumulator chains).
 // The CTA of a diagonal pair (a == b) also applies its tile to the right-hand side: b_i -= L_ik y_k.
-__global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
+// ATOMIC: the level holds several columns, whose updates may meet in one tile (e.g. two independent interiors of the
+// nested-dissection order both update a separator tile): accumulate with red.global.add.f64.
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) k_chol_update(CholView C, const int2* __restrict__ tab) {
   __shared__ __align__(16) double La[GPBA_NB][GPBA_LD], Lb[GPBA_NB][GPBA_LD];
   __shared__ double yk[GPBA_NB];
+  const int k = tab[blockIdx.x].x;
   const int cb = C.col_begin[k];
-  // decode the triangular pair index: blockIdx.x = a*(a+1)/2 + b, a >= b
-  int a = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
-  while ((a + 1) * (a + 2) / 2 <= (int)blockIdx.x) ++a;
-  while (a * (a + 1) / 2 > (int)blockIdx.x) --a;
-  const int b = blockIdx.x - a * (a + 1) / 2;
+  const int a = tab[blockIdx.x].y >> 16, b = tab[blockIdx.x].y & 0xffff;   // pair of the column's non-zero rows, a >= b
   const int ra = C.col_rows[cb + a], rb = C.col_rows[cb + b];
   const double* Ta = C.tiles + C.tile_off[(size_t)ra * C.NT + k];
   const double* Tb = C.tiles + C.tile_off[(size_t)rb * C.NT + k];
@@ -331,11 +333,13 @@ __global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
   const int m0 = 3 * (warp >> 1), n0 = 3 * (warp & 1);
   pdl_wait_then_release();
   double2 cin[3][3];
+  if (!ATOMIC) {
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      cin[i][j] = *reinterpret_cast<const double2*>(Tc + (8 * (m0 + i) + gid) * GPBA_NB + 8 * (n0 + j) + 2 * tig);
+      for (int j = 0; j < 3; ++j)
+        cin[i][j] = *reinterpret_cast<const double2*>(Tc + (8 * (m0 + i) + gid) * GPBA_NB + 8 * (n0 + j) + 2 * tig);
+  }
   if (a == b && threadIdx.x < GPBA_NB) yk[threadIdx.x] = C.work[k * GPBA_NB + threadIdx.x];
   tiles_to_smem<128, 2>(Ta, La, Tb, Lb);
   __syncthreads();
@@ -358,16 +362,21 @@ __global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      double2 o = cin[i][j];
-      o.x -= acc[i][j].x; o.y -= acc[i][j].y;
-      *reinterpret_cast<double2*>(Tc + (8 * (m0 + i) + gid) * GPBA_NB + 8 * (n0 + j) + 2 * tig) = o;
+      double* out = Tc + (8 * (m0 + i) + gid) * GPBA_NB + 8 * (n0 + j) + 2 * tig;
+      if (ATOMIC) { atomicAdd(out, -acc[i][j].x); atomicAdd(out + 1, -acc[i][j].y); }
+      else {
+        double2 o = cin[i][j];
+        o.x -= acc[i][j].x; o.y -= acc[i][j].y;
+        *reinterpret_cast<double2*>(out) = o;
+      }
     }
   if (a == b && threadIdx.x < GPBA_NB) {  // forward substitution: b_i -= L_ik y_k with the tile already staged
     const int r = threadIdx.x;
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll 4
     for (int c = 0; c < GPBA_NB; c += 2) { s0 = fma(La[r][c], yk[c], s0); s1 = fma(La[r][c + 1], yk[c + 1], s1); }
-    C.work[ra * GPBA_NB + r] -= s0 + s1;
+    if (ATOMIC) atomicAdd(&C.work[ra * GPBA_NB + r], -(s0 + s1));
+    else C.work[ra * GPBA_NB + r] -= s0 + s1;
   }
 }
 
@@ -375,18 +384,20 @@ __global__ void __launch_bounds__(128) k_chol_update(CholView C, int k) {
 // (y_i has received the contributions of all later rows); CTA 0 stores it, CTA q > 0 applies one tile of
 // row i to an earlier segment: y_k -= L_ik^T x_i.  Distinct k per CTA and rows are stream ordered, so the
 // result is deterministic without atomics.
-__global__ void __launch_bounds__(192) k_chol_back(CholView C, int i) {
+template <bool ATOMIC>
+__global__ void __launch_bounds__(192) k_chol_back(CholView C, const int2* __restrict__ tab) {
   __shared__ double yi[GPBA_NB], xi[GPBA_NB], part[4][GPBA_NB];
+  const int i = tab[blockIdx.x].x, q_ = tab[blockIdx.x].y;   // tile row i; q_ = 0: store x_i, q_ > 0: its q_-th tile
   const int tid = threadIdx.x, c = tid % GPBA_NB, h = tid / GPBA_NB;  // 4 row-quarters x 48 columns
   // all global operands are requested up front (they do not depend on x_i): one memory round trip per launch
   const double* D = C.dinv + (size_t)i * GPBA_NB * GPBA_NB;  // (L^-T)[c][r] = Linv[r][c], zero for r < c
-  const int k = blockIdx.x > 0 ? C.row_cols[C.row_begin[i] + blockIdx.x - 1] : 0;
-  const double* L = blockIdx.x > 0 ? C.tiles + C.tile_off[(size_t)i * C.NT + k] : D;
+  const int k = q_ > 0 ? C.row_cols[C.row_begin[i] + q_ - 1] : 0;
+  const double* L = q_ > 0 ? C.tiles + C.tile_off[(size_t)i * C.NT + k] : D;
   pdl_wait_then_release();
   double dv[12], lv[12];
 #pragma unroll
   for (int r = 0; r < 12; ++r) { dv[r] = D[(12 * h + r) * GPBA_NB + c]; lv[r] = L[(12 * h + r) * GPBA_NB + c]; }
-  const double yk_old = (blockIdx.x > 0 && tid < GPBA_NB) ? C.work[k * GPBA_NB + tid] : 0.0;
+  const double yk_old = (!ATOMIC && q_ > 0 && tid < GPBA_NB) ? C.work[k * GPBA_NB + tid] : 0.0;
   if (tid < GPBA_NB) yi[tid] = C.work[i * GPBA_NB + tid];
   __syncthreads();
   double s = 0.0;
@@ -397,16 +408,20 @@ __global__ void __launch_bounds__(192) k_chol_back(CholView C, int i) {
   if (tid < GPBA_NB) {
     const double x = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
     xi[tid] = x;
-    if (blockIdx.x == 0) C.xsol[i * GPBA_NB + tid] = x;  // not in place: the other CTAs of this launch still read y_i
+    if (q_ == 0) C.xsol[i * GPBA_NB + tid] = x;  // not in place: the other CTAs of this launch still read y_i
   }
-  if (blockIdx.x == 0) return;
+  if (q_ == 0) return;
   __syncthreads();
   s = 0.0;
 #pragma unroll
   for (int r = 0; r < 12; ++r) s = fma(lv[r], xi[12 * h + r], s);
   part[h][c] = s;
   __syncthreads();
-  if (tid < GPBA_NB) C.work[k * GPBA_NB + tid] = yk_old - ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]));
+  if (tid < GPBA_NB) {
+    const double sum = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    if (ATOMIC) atomicAdd(&C.work[k * GPBA_NB + tid], -sum);   // rows of one level may feed the same earlier segment
+    else C.work[k * GPBA_NB + tid] = yk_old - sum;
+  }
 }
 
 __global__ void k_chol_unpermute(CholView C, double* __restrict__ xout) {

@@ -189,6 +189,10 @@ struct Solver {
   DBuf<double> d_tiles, d_chol_work, d_chol_dinv, d_chol_x;
   DBuf<int> d_row_begin, d_row_cols;
   std::vector<int> chol_row_begin;
+  // level schedule of the tile columns (columns of one level are independent) and the CTA tables of its launches
+  std::vector<int> lvl_pan_begin, lvl_upd_begin, lvl_back_begin, lvl_ncols;
+  DBuf<int2> d_pan_tab, d_upd_tab, d_back_tab;
+  int chol_parts = 1;
   cudaGraphExec_t chol_graph = nullptr;       // load + (panel, update) x NT, captured once per structure
   cudaGraphExec_t chol_back_graph = nullptr;  // backward substitution, one launch per tile row
   int chol_graph_launches = 0, chol_back_launches = 0;
@@ -901,6 +905,36 @@ int Solver::build_cholesky_structure() {
       bfs(far, order);
     }
     for (int i = 0; i < n_pose; ++i) perm[order[n_pose - 1 - i]] = i;  // reversed
+    // Nested dissection on top of the RCM order for long trajectories: with bandwidth bw (pose blocks) no edge spans
+    // more than bw positions, so the last bw positions of every segment separate its interior from the next one.
+    // Interiors are eliminated first (independent of each other: their tile columns share levels below and run in
+    // the same launches), the separators last.  Pays when the system is many bandwidths long (C5: ~400); a system
+    // that is only ~12 bandwidths long (C4) keeps the plain banded order.
+    int bw = 1;
+    for (int k = 0; k < n_hs; ++k) bw = std::max(bw, std::abs(perm[hs_row[k]] - perm[hs_col[k]]));
+    const int bwT = (bw + bpt - 1) / bpt * bpt;
+    int P = std::min(64, n_pose / (16 * bwT));
+    if (getenv("GPBA_CHOL_PARTS")) P = atoi(getenv("GPBA_CHOL_PARTS"));
+    chol_parts = 1;
+    if (P >= 2) {
+      const int L = ((n_pose + P - 1) / P + bpt - 1) / bpt * bpt;
+      if (L > 2 * bwT) {
+        std::vector<int> newpos(n_pose, -1);
+        int cursor = 0;
+        for (int s0 = 0; s0 < P; ++s0) {       // interiors
+          const int lo = s0 * L, hi = std::min(n_pose, (s0 + 1) * L);
+          const int sep_lo = (s0 < P - 1 && hi == (s0 + 1) * L) ? hi - bwT : hi;
+          for (int q = lo; q < sep_lo; ++q) newpos[q] = cursor++;
+        }
+        for (int s0 = 0; s0 < P - 1; ++s0) {   // separators
+          const int hi = std::min(n_pose, (s0 + 1) * L);
+          if (hi != (s0 + 1) * L) continue;
+          for (int q = hi - bwT; q < hi; ++q) newpos[q] = cursor++;
+        }
+        for (int i = 0; i < n_pose; ++i) perm[i] = newpos[perm[i]];
+        chol_parts = P;
+      }
+    }
   }
   std::vector<char> nz((size_t)NT * NT, 0);
   for (int t = 0; t < NT; ++t) nz[(size_t)t * NT + t] = 1;
@@ -940,6 +974,33 @@ int Solver::build_cholesky_structure() {
   for (int k = 0; k < NT; ++k)
     for (int e = chol_col_begin[k]; e < chol_col_begin[k + 1]; ++e) row_cols[cur_r[col_rows[e]]++] = k;
   CKR(d_row_begin.upload(chol_row_begin, stream)); CKR(d_row_cols.upload(row_cols, stream));
+  // level schedule: column r depends on column j < r iff tile (r, j) is non-zero; columns of equal level are independent
+  std::vector<int> level(NT, 0);
+  int n_levels = 0;
+  for (int j = 0; j < NT; ++j) {
+    for (int e = chol_col_begin[j]; e < chol_col_begin[j + 1]; ++e) level[col_rows[e]] = std::max(level[col_rows[e]], level[j] + 1);
+    n_levels = std::max(n_levels, level[j] + 1);
+  }
+  std::vector<std::vector<int>> lvl_cols(n_levels);
+  for (int k = 0; k < NT; ++k) lvl_cols[level[k]].push_back(k);
+  std::vector<int2> pan_tab, upd_tab, back_tab;
+  lvl_pan_begin.assign(n_levels + 1, 0); lvl_upd_begin.assign(n_levels + 1, 0); lvl_back_begin.assign(n_levels + 1, 0);
+  lvl_ncols.assign(n_levels, 0);
+  for (int l = 0; l < n_levels; ++l) {
+    lvl_ncols[l] = (int)lvl_cols[l].size();
+    for (int k : lvl_cols[l]) {
+      const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
+      for (int q = 0; q <= nr; ++q) pan_tab.push_back(make_int2(k, q));
+      for (int a = 0; a < nr; ++a) for (int b = 0; b <= a; ++b) upd_tab.push_back(make_int2(k, (a << 16) | b));
+      const int nrow = chol_row_begin[k + 1] - chol_row_begin[k];
+      for (int q = 0; q <= nrow; ++q) back_tab.push_back(make_int2(k, q));
+      if (nr >= 65536) { g_err = "tile column with more than 65535 rows"; return GPBA_ERR_INVALID; }
+    }
+    lvl_pan_begin[l + 1] = (int)pan_tab.size(); lvl_upd_begin[l + 1] = (int)upd_tab.size(); lvl_back_begin[l + 1] = (int)back_tab.size();
+  }
+  if (upd_tab.empty()) upd_tab.push_back(make_int2(0, 0));
+  CKR(d_pan_tab.upload(pan_tab, stream)); CKR(d_upd_tab.upload(upd_tab, stream)); CKR(d_back_tab.upload(back_tab, stream));
+  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns\n", chol_parts, n_levels, NT);
   CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
   if (chol_graph) { cudaGraphExecDestroy(chol_graph); chol_graph = nullptr; }
   if (chol_back_graph) { cudaGraphExecDestroy(chol_back_graph); chol_back_graph = nullptr; }
@@ -985,14 +1046,23 @@ int Solver::capture_cholesky_graph() {
     const int64_t work = std::max((int64_t)n_hs * 144, (int64_t)NT * GPBA_NB);
     k_chol_load<<<(int)std::min((work + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(C, n_hs, d_hs_row.p, d_hs_col.p, d_hs.p, bs);
     ++launches;
-    for (int k = 0; k < NT; ++k) {
-      const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
-      if (use_pdl && k > 0) e = launch_pdl(k_chol_panel, 1 + nr, GPBA_PANEL_THREADS, stream, C, k, d_fail.p);
-      else k_chol_panel<<<1 + nr, GPBA_PANEL_THREADS, 0, stream>>>(C, k, d_fail.p);
+    const int n_levels = (int)lvl_ncols.size();
+    for (int l = 0; l < n_levels; ++l) {
+      const int npan = lvl_pan_begin[l + 1] - lvl_pan_begin[l], nupd = lvl_upd_begin[l + 1] - lvl_upd_begin[l];
+      const bool shared = lvl_ncols[l] > 1;   // several columns may update one tile: accumulate atomically
+      const int2* pt = d_pan_tab.p + lvl_pan_begin[l];
+      const int2* ut = d_upd_tab.p + lvl_upd_begin[l];
+      if (use_pdl && l > 0) e = launch_pdl(k_chol_panel, npan, GPBA_PANEL_THREADS, stream, C, pt, d_fail.p);
+      else k_chol_panel<<<npan, GPBA_PANEL_THREADS, 0, stream>>>(C, pt, d_fail.p);
       ++launches;
-      if (nr > 0) {
-        if (use_pdl) e = launch_pdl(k_chol_update, nr * (nr + 1) / 2, 128, stream, C, k);
-        else k_chol_update<<<nr * (nr + 1) / 2, 128, 0, stream>>>(C, k);
+      if (nupd > 0 && e == cudaSuccess) {
+        if (shared) {
+          if (use_pdl) e = launch_pdl(k_chol_update<true>, nupd, 128, stream, C, ut);
+          else k_chol_update<true><<<nupd, 128, 0, stream>>>(C, ut);
+        } else {
+          if (use_pdl) e = launch_pdl(k_chol_update<false>, nupd, 128, stream, C, ut);
+          else k_chol_update<false><<<nupd, 128, 0, stream>>>(C, ut);
+        }
         ++launches;
       }
       if (e != cudaSuccess) break;
@@ -1005,9 +1075,17 @@ int Solver::capture_cholesky_graph() {
   CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
   launches = 0;
   e = cudaSuccess;
-  for (int i = NT - 1; i >= 0 && e == cudaSuccess; --i) {
-    if (use_pdl && i < NT - 1) e = launch_pdl(k_chol_back, 1 + chol_row_begin[i + 1] - chol_row_begin[i], 192, stream, C, i);
-    else k_chol_back<<<1 + chol_row_begin[i + 1] - chol_row_begin[i], 192, 0, stream>>>(C, i);
+  for (int l = (int)lvl_ncols.size() - 1; l >= 0 && e == cudaSuccess; --l) {
+    const int nb = lvl_back_begin[l + 1] - lvl_back_begin[l];
+    const int2* bt = d_back_tab.p + lvl_back_begin[l];
+    const bool first = l == (int)lvl_ncols.size() - 1;
+    if (lvl_ncols[l] > 1) {
+      if (use_pdl && !first) e = launch_pdl(k_chol_back<true>, nb, 192, stream, C, bt);
+      else k_chol_back<true><<<nb, 192, 0, stream>>>(C, bt);
+    } else {
+      if (use_pdl && !first) e = launch_pdl(k_chol_back<false>, nb, 192, stream, C, bt);
+      else k_chol_back<false><<<nb, 192, 0, stream>>>(C, bt);
+    }
     ++launches;
   }
   if (e == cudaSuccess) {
