@@ -1794,6 +1794,11 @@ int gpba_schur_stats(gpba_handle* h, int64_t out[4]) {
   out[0] = S(h).n_pairs; out[1] = S(h).n_rp; out[2] = S(h).n_items; out[3] = S(h).n_con;
   return GPBA_OK;
 }
+int gpba_solver_stats(gpba_handle* h, int64_t out[4]) {
+  NEED_STRUCT(h);
+  out[0] = S(h).NT; out[1] = (int64_t)S(h).lvl_ncols.size(); out[2] = S(h).chol_parts; out[3] = S(h).chol_doubles / (GPBA_NB * GPBA_NB);
+  return GPBA_OK;
+}
 int gpba_set_profiling(gpba_handle* h, int enabled) { NEED(h); S(h).collect_events(); S(h).profiling = enabled != 0; return GPBA_OK; }
 void* gpba_get_stream(gpba_handle* h) { return h ? (void*)S(h).stream : nullptr; }
 

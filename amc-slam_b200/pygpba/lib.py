@@ -21,7 +21,7 @@ SYMBOLS = [
     "gpba_get_hschur", "gpba_get_hll", "gpba_get_hpl", "gpba_oplus", "gpba_push", "gpba_pop", "gpba_discard_top",
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
-    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats",
+    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats",
 ]
 
 
@@ -232,6 +232,11 @@ class GpBa:
         a = (C.c_int64 * 4)()
         self._ck(self.L.gpba_schur_stats(self.h, a), "gpba_schur_stats")
         return dict(n_obs_pairs=a[0], n_record_pairs=a[1], n_items=a[2], n_contrib=a[3])
+
+    def solver_stats(self):
+        a = (C.c_int64 * 4)()
+        self._ck(self.L.gpba_solver_stats(self.h, a), "gpba_solver_stats")
+        return dict(tile_columns=a[0], levels=a[1], partitions=a[2], tiles=a[3])
 
     def stream(self):
         return self.L.gpba_get_stream(self.h)

@@ -241,6 +241,10 @@ int gpba_set_profiling(gpba_handle* h, int enabled);
  * out[0] observation pairs, out[1] record pairs (6x6 accumulators), out[2] work items of K4b,
  * out[3] (record pair -> Hschur block) contributions of K4c. */
 int gpba_schur_stats(gpba_handle* h, int64_t out[4]);
+/* Shape of the reduced-system factorization (the analyzePattern of linear_solver_eigen.h:147-201): out[0] tile columns,
+ * out[1] levels of the schedule (independent tile columns share a level), out[2] partitions of the nested-dissection
+ * order (1 = plain banded order), out[3] non-zero 48x48 tiles of the factor. */
+int gpba_solver_stats(gpba_handle* h, int64_t out[4]);
 /* cudaStream_t every kernel of this handle is launched on (for CUDA-event timing by the caller). */
 void* gpba_get_stream(gpba_handle* h);
 /* Re-upload estimates only (same structure): lets a benchmark repeat optimize() from the same start. */

@@ -183,6 +183,22 @@ def test_stereo_gp_edges(G, oracle_mod):
     assert_state_close(g.state(), o.state())
 
 
+def test_nested_dissection_order_matches_oracle(G, oracle_mod, monkeypatch):
+    """Long trajectory: the tile Cholesky switches to the nested-dissection order with level-scheduled (concurrent,
+    atomically accumulated) tile columns; the LM run must still match the oracle's sequential factorization."""
+    P = synth.make_problem("tiny_global", n_kf=200, n_pt=2500, obs_per_pt=6, seed=41)
+    ref = oracle_mod.Oracle(P)
+    tc = ref.optimize(3)
+    for parts in ("1", "4"):
+        monkeypatch.setenv("GPBA_CHOL_PARTS", parts)
+        g = G.GpBa(P)
+        assert_trace_equal(g.optimize(3), tc)
+        assert_state_close(g.state(), ref.state())
+        st = g.solver_stats()
+        assert st["partitions"] == int(parts)
+        assert (st["levels"] < st["tile_columns"]) == (parts != "1")
+
+
 def test_edge_cases(G, oracle_mod):
     # a keyframe-only graph (no landmarks at all) and a landmark seen from fixed keyframes only
     P = synth.make_problem("tiny")
