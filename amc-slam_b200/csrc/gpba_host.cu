@@ -913,6 +913,7 @@ int Solver::build_cholesky_structure() {
     int bw = 1;
     for (int k = 0; k < n_hs; ++k) bw = std::max(bw, std::abs(perm[hs_row[k]] - perm[hs_col[k]]));
     const int bwT = (bw + bpt - 1) / bpt * bpt;
+    if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: RCM bandwidth %d pose blocks of %d\n", bw, n_pose);
     int P = std::min(64, n_pose / (16 * bwT));
     if (getenv("GPBA_CHOL_PARTS")) P = atoi(getenv("GPBA_CHOL_PARTS"));
     chol_parts = 1;
@@ -1000,7 +1001,7 @@ int Solver::build_cholesky_structure() {
   }
   if (upd_tab.empty()) upd_tab.push_back(make_int2(0, 0));
   CKR(d_pan_tab.upload(pan_tab, stream)); CKR(d_upd_tab.upload(upd_tab, stream)); CKR(d_back_tab.upload(back_tab, stream));
-  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns\n", chol_parts, n_levels, NT);
+  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns, %zu panel CTAs, %zu update CTAs\n", chol_parts, n_levels, NT, pan_tab.size(), upd_tab.size());
   CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
   if (chol_graph) { cudaGraphExecDestroy(chol_graph); chol_graph = nullptr; }
   if (chol_back_graph) { cudaGraphExecDestroy(chol_back_graph); chol_back_graph = nullptr; }
