@@ -596,25 +596,36 @@ __global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __r
     it = __shfl_sync(0xffffffffu, it, 0);
     if (it >= n_items) break;
     const int64_t pb = item_begin[it];
-    const int kmax = 3 * (int)(item_end[it] - pb);
+    const int np = (int)(item_end[it] - pb);
     const unsigned fl = item_flags[it];
-    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: independent DMMA chains
-    for (int k0 = 0; k0 < kmax; k0 += 8) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int kk = k0 + 4 * half + tig;
-        double a = 0.0, b = 0.0;
-        if (kk < kmax) {
-          const int p = kk / 3, cc = kk - 3 * p;
-          const unsigned long long pr = pairs[pb + p];
-          const unsigned oa = (unsigned)(pr >> 32), ob = (unsigned)pr;
-          if (gid < 6) { a = U[(size_t)oa * 18 + gid * 3 + cc]; b = U[(size_t)ob * 18 + gid * 3 + cc]; }
-          else if (gid == 6 && (fl & 1u)) b = ptL[(size_t)o_lm[oa] * 9 + 6 + cc];
+    // Four pairs per trip: K slot `tig` of the three DMMAs (one per column cc of the 6 x 3 blocks) belongs to pair
+    // 4 j + tig, so a lane reads one pair index and three consecutive doubles of each block per trip (no div / mod,
+    // one index load per three DMMAs); three accumulator pairs = independent DMMA chains.  The next trip's pair index
+    // is fetched before this trip's gathers so the dependent loads overlap.
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+    unsigned long long pr = tig < np ? pairs[pb + tig] : 0ull;
+    for (int j = 0; j < np; j += 4) {
+      const bool live = j + tig < np;
+      const unsigned long long cur = pr;
+      if (j + 4 + tig < np) pr = pairs[pb + j + 4 + tig];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+      if (live) {
+        const unsigned oa = (unsigned)(cur >> 32), ob = (unsigned)cur;
+        if (gid < 6) {
+          const double* pa = U + (size_t)oa * 18 + gid * 3;
+          const double* pbb = U + (size_t)ob * 18 + gid * 3;
+          a0 = pa[0]; a1 = pa[1]; a2 = pa[2];
+          b0 = pbb[0]; b1 = pbb[1]; b2 = pbb[2];
+        } else if (gid == 6 && (fl & 1u)) {
+          const double* z = ptL + (size_t)o_lm[oa] * 9 + 6;
+          b0 = z[0]; b1 = z[1]; b2 = z[2];
         }
-        if (half == 0) dmma884(c0, c1, a, b); else dmma884(e0, e1, a, b);
       }
+      dmma884(c0, c1, a0, b0);
+      dmma884(e0, e1, a1, b1);
+      dmma884(f0, f1, a2, b2);
     }
-    c0 += e0; c1 += e1;
+    c0 += e0 + f0; c1 += e1 + f1;
     if (gid < 6) {
       double* out = C + (size_t)item_rp[it] * GPBA_RP_STRIDE + gid * 8 + 2 * tig;
       if (fl & 2u) { atomicAdd(out, c0); atomicAdd(out + 1, c1); }
