@@ -151,6 +151,9 @@ struct Solver {
   DBuf<double> d_pose[2], d_vel[2], d_ptS[2];   // d_ptS: landmarks in sorted order
   int cur = 0;
   int last_eval = 0;                            // buffer the last error evaluation ran on
+  double* chi2_store_override = nullptr;
+  bool pts_gathered = false;                    // multi-GPU: d_pt_full holds all ranks' landmarks (valid until the state changes)
+         // multi-GPU: per-edge chi2 goes to the staging buffer first
   std::vector<std::vector<double>> stack_pose, stack_vel, stack_pt;  // push/pop (L1)
   // ------------------------------------------------------------------ structure (host)
   bool structure_ok = false, system_ok = false;
@@ -159,7 +162,7 @@ struct Solver {
   std::vector<int64_t> lm_obs_begin, o_orig;
   std::vector<int> hpp_row, hpp_col, hs_row, hs_col;
   int64_t n_aobs = 0;
-  int n_lm = 0, n_pose = 0, n_hpp = 0, n_hs = 0, n_items = 0, n_rseg = 0, n_rp = 0;
+  int n_lm = 0, n_lm_all = 0, n_pose = 0, n_hpp = 0, n_hs = 0, n_items = 0, n_rseg = 0, n_rp = 0;   // n_lm: own landmarks, n_lm_all: all ranks'
   int64_t n_con = 0;
   int64_t n_hpl = 0, n_pairs = 0;
   // ------------------------------------------------------------------ structure (device)
@@ -170,6 +173,8 @@ struct Solver {
   DBuf<int64_t> d_o_orig, d_lm_obs_begin, d_rperm, d_rseg_begin, d_item_begin, d_item_end;
   DBuf<unsigned long long> d_pairs;     // observation pairs grouped by record pair (sorted order)
   DBuf<unsigned long long> d_rp_key;    // unique record pairs (r1 * n_rec + r2), ascending
+  DBuf<int> d_pt_act;                   // [n_pt] point carries an active edge (on any rank)
+  DBuf<double> d_gather;                // multi-GPU: staging buffer of the end-of-optimize all-reduces
   DBuf<HsContrib> d_con;
   CubTemp cub_tmp;
   DBuf<int> d_rec_hpp11, d_rec_hpp12, d_rec_hpp22, d_prior_hpp11, d_prior_hpp12, d_prior_hpp22, d_pose_hpp_diag;
@@ -404,6 +409,16 @@ __global__ void k_scatter_pts(int n_lm, const int* __restrict__ lm_pt, const dou
   full[3 * (size_t)lm_pt[i / 3] + i % 3] = s[i];
 }
 
+// multi-GPU: after the all-reduce (sum of zero-initialised staging buffers, every entry owned by exactly one rank)
+__global__ void k_merge_pts(int n_pt, const int* __restrict__ pt_act, const double* __restrict__ g, double* __restrict__ full) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pt * 3 && pt_act[i / 3]) full[i] = g[i];
+}
+__global__ void k_merge_chi2(int64_t n_obs, const uint8_t* __restrict__ flags, const double* __restrict__ g, double* __restrict__ chi2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x)
+    if (!(flags[i] & 0x2u)) chi2[i] = g[i];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // P0: SparseOptimizer::initializeOptimization + buildIndexMapping + BlockSolver::buildStructure
 // (sparse_optimizer.cpp:199-267,166-190; block_solver.hpp:142-295), integer and bit-exact.  The host does the O(n_obs)
@@ -432,7 +447,7 @@ int Solver::build_structure() {
   const int gall = (int)std::min<int64_t>((n_obs + 255) / 256 + 1, 148 * 16);
   // --- active set (edge active iff level 0; vertex active iff it has an active edge): one device pass
   DBuf<unsigned char> d_rec_used;
-  DBuf<int> d_pt_act, d_first_kf, d_flag;
+  DBuf<int> d_first_kf, d_flag;
   CKR(d_rec_used.alloc((size_t)n_rec)); CKR(d_pt_act.alloc((size_t)n_pt)); CKR(d_first_kf.alloc((size_t)n_pt)); CKR(d_flag.alloc(1));
   CK(cudaMemsetAsync(d_rec_used.p, 0, (size_t)n_rec, stream));
   CK(cudaMemsetAsync(d_pt_act.p, 0, sizeof(int) * (size_t)n_pt, stream));
@@ -463,7 +478,7 @@ int Solver::build_structure() {
   CKR(d_kf_h.upload(kf_h, stream));
   // --- landmark order: ascending first keyframe, ties by point id (stable radix sort of the points);
   //     g2o landmark index = rank among active points in ascending id (exclusive scan of the activity flags)
-  int n_lm_all = 0;
+  n_lm_all = 0;
   DBuf<int> d_pkey, d_pkey_s, d_pval, d_sorted_pt, d_pt_lm_all, d_rank_of_pt, d_cnt_all;
   const size_t npt1 = (size_t)std::max(n_pt, 1);
   CKR(d_pkey.alloc(npt1)); CKR(d_pkey_s.alloc(npt1)); CKR(d_pval.alloc(npt1)); CKR(d_sorted_pt.alloc(npt1)); CKR(d_pt_lm_all.alloc(npt1)); CKR(d_rank_of_pt.alloc(npt1));
@@ -1113,7 +1128,7 @@ int Solver::compute_records(int buf, bool full) {
 int Solver::compute_errors(int buf, bool store, double* chi2) {
   CKR(compute_records(buf, false));
   t0();
-  double* out = store ? d_chi2.p : nullptr;
+  double* out = store ? (chi2_store_override ? chi2_store_override : d_chi2.p) : nullptr;
   if (stereo) k_residual<true><<<grid_obs, 256, 0, stream>>>(V, d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
   else k_residual<false><<<grid_obs, 256, 0, stream>>>(V, d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
   CK(cudaGetLastError());
@@ -1355,8 +1370,32 @@ int Solver::optimize(int iters, const volatile unsigned char* stop, const gpba_l
     // stale-error quirk: edge errors are those of the LAST EVALUATED trial, even if it was rejected
     double dummy;
     const int ev = last_eval;
-    CKR(compute_errors(ev, true, &dummy));
-    CKR(scatter_points(cur));
+    if (nranks > 1) {
+      // every rank ends with the full state: stored edge errors and landmark positions of the other ranks' shards
+      // arrive through two all-reduces of zero-initialised staging buffers (each entry is owned by exactly one rank)
+      const size_t ng = (size_t)std::max<int64_t>(std::max<int64_t>(n_obs, (int64_t)n_pt * 3), 1);
+      CKR(d_gather.alloc(ng));
+      CK(cudaMemsetAsync(d_gather.p, 0, sizeof(double) * (size_t)std::max<int64_t>(n_obs, 1), stream));
+      chi2_store_override = d_gather.p;
+      const int rc = compute_errors(ev, true, &dummy);
+      chi2_store_override = nullptr;
+      CKR(rc);
+      if (n_obs > 0) {
+        if (g_nccl.AllReduce(d_gather.p, d_gather.p, (size_t)n_obs, 8, 0, comm, stream) != 0) { g_err = "ncclAllReduce(edge chi2) failed"; return GPBA_ERR_NCCL; }
+        k_merge_chi2<<<(int)std::min<int64_t>((n_obs + 255) / 256, 148 * 8), 256, 0, stream>>>(n_obs, d_all_flags.p, d_gather.p, d_chi2.p);
+      }
+      CK(cudaMemsetAsync(d_gather.p, 0, sizeof(double) * 3 * (size_t)std::max(n_pt, 1), stream));
+      if (n_lm > 0) k_scatter_pts<<<(n_lm * 3 + 255) / 256, 256, 0, stream>>>(n_lm, d_lm_pt.p, d_ptS[cur].p, d_gather.p);
+      if (n_pt > 0) {
+        if (g_nccl.AllReduce(d_gather.p, d_gather.p, (size_t)n_pt * 3, 8, 0, comm, stream) != 0) { g_err = "ncclAllReduce(points) failed"; return GPBA_ERR_NCCL; }
+        k_merge_pts<<<(n_pt * 3 + 255) / 256, 256, 0, stream>>>(n_pt, d_pt_act.p, d_gather.p, d_pt_full.p);
+      }
+      CK(cudaGetLastError());
+      pts_gathered = true;
+    } else {
+      CKR(compute_errors(ev, true, &dummy));
+      CKR(scatter_points(cur));
+    }
     CK(cudaStreamSynchronize(stream));
   }
   return GPBA_OK;
@@ -1496,13 +1535,15 @@ int gpba_solve(gpba_handle* h, int* ok) {
   if (ok) *ok = k ? 1 : 0;
   return GPBA_OK;
 }
-int gpba_vector_size(gpba_handle* h, int64_t* n) { NEED_STRUCT(h); *n = (int64_t)S(h).n_pose * 12 + (int64_t)S(h).n_lm * 3; return GPBA_OK; }
+// poses (12 each) then ALL active landmarks in g2o order (3 each); a rank of a multi-GPU run fills only its own landmarks
+int gpba_vector_size(gpba_handle* h, int64_t* n) { NEED_STRUCT(h); *n = (int64_t)S(h).n_pose * 12 + (int64_t)S(h).n_lm_all * 3; return GPBA_OK; }
 int gpba_get_x(gpba_handle* h, double* x) {
   NEED_STRUCT(h);
   Solver& s = S(h);
   CK(cudaMemcpy(x, s.d_x.p, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost));
   std::vector<double> xl((size_t)s.n_lm * 3);
   if (s.n_lm) CK(cudaMemcpy(xl.data(), s.d_xl.p, xl.size() * 8, cudaMemcpyDeviceToHost));
+  std::fill(x + (size_t)s.n_pose * 12, x + (size_t)s.n_pose * 12 + (size_t)s.n_lm_all * 3, 0.0);
   for (int l = 0; l < s.n_lm; ++l) for (int c = 0; c < 3; ++c) x[(size_t)s.n_pose * 12 + (size_t)s.lm_rank[l] * 3 + c] = xl[(size_t)l * 3 + c];
   return GPBA_OK;
 }
@@ -1513,6 +1554,7 @@ int gpba_get_b(gpba_handle* h, double* b) {
   CK(cudaMemcpy(b, s.d_bp.p, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost));
   std::vector<double> bl((size_t)s.n_lm * 3);
   if (s.n_lm) CK(cudaMemcpy(bl.data(), s.d_bl.p, bl.size() * 8, cudaMemcpyDeviceToHost));
+  std::fill(b + (size_t)s.n_pose * 12, b + (size_t)s.n_pose * 12 + (size_t)s.n_lm_all * 3, 0.0);
   for (int l = 0; l < s.n_lm; ++l) for (int c = 0; c < 3; ++c) b[(size_t)s.n_pose * 12 + (size_t)s.lm_rank[l] * 3 + c] = bl[(size_t)l * 3 + c];
   return GPBA_OK;
 }
@@ -1536,6 +1578,7 @@ int gpba_get_hschur(gpba_handle* h, double* blocks, double* bschur) {
 int gpba_get_hll(gpba_handle* h, double* blocks) {
   NEED_STRUCT(h);
   Solver& s = S(h);
+  if (s.nranks > 1) { g_err = "gpba_get_hll is a single-GPU parity accessor (landmarks are sharded)"; return GPBA_ERR_STATE; }
   CK(cudaStreamSynchronize(s.stream));
   std::vector<double> hl((size_t)s.n_lm * 9);
   if (s.n_lm) CK(cudaMemcpy(hl.data(), s.d_hll.p, hl.size() * 8, cudaMemcpyDeviceToHost));
@@ -1550,6 +1593,7 @@ int gpba_get_hpl(gpba_handle* h, int64_t* lm_begin, int32_t* pose, double* block
   // record touches the pose of (M_r^(pose))^T W_o, assembled here on the host from W and the record table.
   NEED_STRUCT(h);
   Solver& s = S(h);
+  if (s.nranks > 1) { g_err = "gpba_get_hpl is a single-GPU parity accessor (landmarks are sharded)"; return GPBA_ERR_STATE; }
   CK(cudaStreamSynchronize(s.stream));
   std::vector<double> W((size_t)s.n_aobs * 18), R((size_t)s.n_rec * GPBA_REC_STRIDE);
   std::vector<int> orec((size_t)s.n_aobs);

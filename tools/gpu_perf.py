@@ -28,10 +28,28 @@ def run(name, solver=SOLVER_DENSE_CHOL, iters=10, reps=3, **kw):
     return g
 
 
+def run_rejection_rounds(name="c3", reps=3):
+    """C3: 4 x (initializeOptimization(0) + optimize(10)) with re-flagging after every round (Optimizer.cc:548-675 structure)."""
+    P = synth.make_problem(name)
+    print(f"===== {name} rejection rounds n_obs={P.n_obs} n_pt={P.n_pt} n_kf={P.n_kf} outliers={P.meta['outliers']}", flush=True)
+    for rep in range(reps):
+        g = G.GpBa(P)
+        t = time.time(); flags, traces = g.rejection_rounds(4, 10); dt = time.time() - t
+        its = sum(tr.n_iters for tr in traces)
+        truth = P.truth["is_outlier"] if P.truth is not None else None
+        msg = ""
+        if truth is not None:
+            msg = f" flagged {int(flags.sum())} (true outliers {int(truth.sum())}, recall {float((flags[truth] > 0).mean()):.3f}, false positives {float((flags[~truth] > 0).mean()):.4f})"
+        print(f" rep{rep}: 4 rounds {dt*1e3:.2f} ms, {its} LM iterations, obs/s {P.n_obs*its/dt:.3e}{msg}", flush=True)
+        g.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c3", "c4"]
     for w in which:
         if w == "c4pcg":
             run("c4", SOLVER_PCG)
+        elif w == "c3rr":
+            run_rejection_rounds("c3")
         else:
             run(w)
