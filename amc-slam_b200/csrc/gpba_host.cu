@@ -9,6 +9,7 @@
 #include "gpba_chol.cuh"
 #include "gpba_pcg.cuh"
 #include "gpba_structure.cuh"
+#include "gpba_pose.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1861,6 +1862,91 @@ int gpba_reset_state(gpba_handle* h, const double* kf_pose, const double* kf_vel
     }
   }
   CK(cudaStreamSynchronize(s.stream));
+  return GPBA_OK;
+}
+
+// ---- pose-only GP optimisation (Optimizer::PoseGPOptimizationFromeLastFrame, src/Optimizer.cc:369-686)
+int gpba_pose_optimize(const gpba_pose_batch* B, int device, double* cur_pose_out, double* cur_vel_out, double* prev_pose_out,
+                       double* prev_vel_out, uint8_t* outlier_out, int32_t* n_inliers_out, gpba_lm_trace* traces) {
+  if (!B || B->n_cam < 1 || B->n_cam > GPBA_POSE_MAX_CAM || B->n_frames < 0 || !B->cam_intr || !B->cam_Tbc) { g_err = "invalid pose batch"; return GPBA_ERR_INVALID; }
+  const int nf = B->n_frames;
+  if (nf == 0) return GPBA_OK;
+  if (!B->prev_pose || !B->prev_vel || !B->prev_time || !B->prev_fixed || !B->cur_pose || !B->cur_vel || !B->cur_time || !B->cam_time || !B->obs_begin) { g_err = "invalid pose batch"; return GPBA_ERR_INVALID; }
+  const int64_t n_obs = B->obs_begin[nf];
+  for (int f = 0; f < nf; ++f) if (B->obs_begin[f + 1] < B->obs_begin[f] || B->obs_begin[f] < 0) { g_err = "obs_begin not monotone"; return GPBA_ERR_INVALID; }
+  if (n_obs > 0 && (!B->obs_u || !B->obs_v || !B->obs_inv_sigma2 || !B->obs_xw || !B->obs_cam)) { g_err = "invalid pose batch"; return GPBA_ERR_INVALID; }
+  for (int64_t i = 0; i < n_obs; ++i) if (B->obs_cam[i] < 0 || B->obs_cam[i] >= B->n_cam) { g_err = "camera index out of range"; return GPBA_ERR_INVALID; }
+  for (int f = 0; f < nf; ++f) if (!(B->cur_time[f] > B->prev_time[f])) { g_err = "frame times not increasing"; return GPBA_ERR_INVALID; }
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device (libgpba has no CPU fallback)"; return GPBA_ERR_NO_DEVICE; }
+  }
+  if (device < 0) CK(cudaGetDevice(&device));
+  CK(cudaSetDevice(device));
+  StreamHolder sh;   // declared before the buffers: destroyed after they went back to the pool
+  CK(cudaStreamCreateWithFlags(&sh.s, cudaStreamNonBlocking));
+  cudaStream_t st = sh.s;
+  g_alloc_stream = st;
+  {
+    cudaMemPool_t pool; uint64_t thr = UINT64_MAX;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  std::vector<CamConst> cams(B->n_cam);
+  for (int c = 0; c < B->n_cam; ++c) {
+    CamConst& cc = cams[c];
+    cc.fx = B->cam_intr[4 * c]; cc.fy = B->cam_intr[4 * c + 1]; cc.cx = B->cam_intr[4 * c + 2]; cc.cy = B->cam_intr[4 * c + 3];
+    SE3 Tbc = load_se3(B->cam_Tbc + 7 * c);
+    SE3 Tcb = se3_inv(Tbc);
+    M3 Rcb = quat_to_R(Tcb.q), Rbc = quat_to_R(Tbc.q);
+    for (int i = 0; i < 9; ++i) { cc.Rcb[i] = Rcb.a[i]; cc.Rbc[i] = Rbc.a[i]; }
+    for (int i = 0; i < 3; ++i) { cc.tcb[i] = Tcb.t[i]; cc.tbc[i] = Tbc.t[i]; }
+    cc.qbc[0] = Tbc.q.x; cc.qbc[1] = Tbc.q.y; cc.qbc[2] = Tbc.q.z; cc.qbc[3] = Tbc.q.w;
+  }
+  DBuf<CamConst> d_cam;
+  DBuf<double> d_pp, d_pv, d_pt, d_cp, d_cv, d_ct, d_camt, d_u, d_v, d_ur, d_w, d_xw, d_chi2, d_ocp, d_ocv, d_opp, d_opv;
+  DBuf<uint8_t> d_fix, d_fl, d_level, d_koff;
+  DBuf<int64_t> d_ob;
+  DBuf<int> d_cam_of, d_inl;
+  DBuf<gpba_lm_trace> d_tr;
+  CKR(d_cam.upload(cams, st));
+  CKR(d_pp.upload(B->prev_pose, (size_t)7 * nf, st)); CKR(d_pv.upload(B->prev_vel, (size_t)6 * nf, st)); CKR(d_pt.upload(B->prev_time, nf, st));
+  CKR(d_cp.upload(B->cur_pose, (size_t)7 * nf, st)); CKR(d_cv.upload(B->cur_vel, (size_t)6 * nf, st)); CKR(d_ct.upload(B->cur_time, nf, st));
+  CKR(d_camt.upload(B->cam_time, (size_t)nf * B->n_cam, st)); CKR(d_fix.upload(B->prev_fixed, nf, st));
+  CKR(d_ob.upload(B->obs_begin, (size_t)nf + 1, st));
+  CKR(d_u.upload(B->obs_u, (size_t)n_obs, st)); CKR(d_v.upload(B->obs_v, (size_t)n_obs, st)); CKR(d_w.upload(B->obs_inv_sigma2, (size_t)n_obs, st));
+  if (B->obs_ur) CKR(d_ur.upload(B->obs_ur, (size_t)n_obs, st));
+  CKR(d_xw.upload(B->obs_xw, (size_t)3 * n_obs, st)); CKR(d_cam_of.upload(B->obs_cam, (size_t)n_obs, st));
+  if (B->obs_flags) CKR(d_fl.upload(B->obs_flags, (size_t)n_obs, st));
+  else { CKR(d_fl.alloc((size_t)n_obs)); CK(cudaMemsetAsync(d_fl.p, 0, (size_t)std::max<int64_t>(n_obs, 1), st)); }
+  CKR(d_level.alloc((size_t)n_obs)); CKR(d_koff.alloc((size_t)n_obs)); CKR(d_chi2.alloc((size_t)n_obs));
+  CKR(d_ocp.alloc((size_t)7 * nf)); CKR(d_ocv.alloc((size_t)6 * nf)); CKR(d_opp.alloc((size_t)7 * nf)); CKR(d_opv.alloc((size_t)6 * nf));
+  CKR(d_inl.alloc(nf));
+  if (traces) CKR(d_tr.alloc((size_t)nf * GPBA_POSE_ROUNDS));
+
+  DevView V;
+  std::memset(&V, 0, sizeof(V));
+  for (int i = 0; i < 6; ++i) V.qc_inv[i] = 1.0 / B->qc[i];
+  V.bf = B->bf;
+  V.hub_mono_delta = B->huber_mono; V.hub_mono_dsqr = f32sq(B->huber_mono);
+  V.hub_stereo_delta = B->huber_stereo; V.hub_stereo_dsqr = f32sq(B->huber_stereo);
+  PoseBatchView P;
+  P.n_cam = B->n_cam; P.n_frames = nf; P.cam = d_cam.p;
+  P.prev_pose = d_pp.p; P.prev_vel = d_pv.p; P.prev_time = d_pt.p; P.cur_pose = d_cp.p; P.cur_vel = d_cv.p; P.cur_time = d_ct.p;
+  P.cam_time = d_camt.p; P.prev_fixed = d_fix.p; P.obs_begin = d_ob.p;
+  P.obs_u = d_u.p; P.obs_v = d_v.p; P.obs_ur = B->obs_ur ? d_ur.p : nullptr; P.obs_w = d_w.p; P.obs_xw = d_xw.p; P.obs_cam = d_cam_of.p;
+  P.obs_flags = d_fl.p; P.level = d_level.p; P.kernel_off = d_koff.p; P.chi2 = d_chi2.p;
+  P.out_cur_pose = d_ocp.p; P.out_cur_vel = d_ocv.p; P.out_prev_pose = d_opp.p; P.out_prev_vel = d_opv.p; P.out_inliers = d_inl.p;
+  P.traces = traces ? d_tr.p : nullptr;
+  k_pose_only<<<nf, GPBA_POSE_THREADS, 0, st>>>(P, V);
+  CK(cudaGetLastError());
+  if (cur_pose_out) CK(cudaMemcpyAsync(cur_pose_out, d_ocp.p, sizeof(double) * 7 * nf, cudaMemcpyDeviceToHost, st));
+  if (cur_vel_out) CK(cudaMemcpyAsync(cur_vel_out, d_ocv.p, sizeof(double) * 6 * nf, cudaMemcpyDeviceToHost, st));
+  if (prev_pose_out) CK(cudaMemcpyAsync(prev_pose_out, d_opp.p, sizeof(double) * 7 * nf, cudaMemcpyDeviceToHost, st));
+  if (prev_vel_out) CK(cudaMemcpyAsync(prev_vel_out, d_opv.p, sizeof(double) * 6 * nf, cudaMemcpyDeviceToHost, st));
+  if (outlier_out && n_obs) CK(cudaMemcpyAsync(outlier_out, d_level.p, (size_t)n_obs, cudaMemcpyDeviceToHost, st));
+  if (n_inliers_out) CK(cudaMemcpyAsync(n_inliers_out, d_inl.p, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
+  if (traces) CK(cudaMemcpyAsync(traces, d_tr.p, sizeof(gpba_lm_trace) * (size_t)nf * GPBA_POSE_ROUNDS, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return GPBA_OK;
 }
 

@@ -128,20 +128,18 @@ GPBA_D void eval_obs(const DevView& V, const double* __restrict__ R /* R_cw[9], 
 }
 
 // ------------------------------------------------------------------------------------------------ K0
+// One record row: interpolated camera pose (R_cw | t_cw) and, if FULL, the 6 x 24 chain matrix M.
+// pose1 / vel1 == nullptr marks a synchronous record.
 template <bool FULL>
-__global__ void k_records(DevView V, const double* __restrict__ pose, const double* __restrict__ vel,
-                          double* __restrict__ rec_out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= V.n_rec) return;
-  const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
-  const CamConst& cam = V.cam[V.rec_cam[r]];
-  double* out = rec_out + (size_t)r * (FULL ? GPBA_REC_STRIDE : GPBA_REC_LITE_STRIDE);
-  const SE3 T2 = load_se3(pose + 7 * k2);
+GPBA_D void record_row(const double* __restrict__ pose1, const double* __restrict__ vel1, double t1,
+                       const double* __restrict__ pose2, const double* __restrict__ vel2, double t2, double t,
+                       const CamConst& cam, double* __restrict__ out) {
+  const SE3 T2 = load_se3(pose2);
   SE3 Twb = T2;
-  if (k1 >= 0) {
-    const SE3 T1 = load_se3(pose + 7 * k1);
-    const V6 v1 = load_v6(vel + 6 * k1), v2 = load_v6(vel + 6 * k2);
-    const GpWeights gw = gp_weights(V.kf_time[k1], V.kf_time[k2], V.rec_t[r]);
+  if (pose1) {
+    const SE3 T1 = load_se3(pose1);
+    const V6 v1 = load_v6(vel1), v2 = load_v6(vel2);
+    const GpWeights gw = gp_weights(t1, t2, t);
     const V6 xi12 = se3_log(se3_mul(se3_inv(T1), T2));
     const M6 K = RightJacobianPose3Inv(xi12);
     const V6 Kv2 = mul(K, v2);
@@ -191,6 +189,17 @@ __global__ void k_records(DevView V, const double* __restrict__ pose, const doub
 #pragma unroll
   for (int i = 0; i < 9; ++i) out[i] = R.a[i];
   out[9] = Tcw.t[0]; out[10] = Tcw.t[1]; out[11] = Tcw.t[2];
+}
+
+template <bool FULL>
+__global__ void k_records(DevView V, const double* __restrict__ pose, const double* __restrict__ vel,
+                          double* __restrict__ rec_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= V.n_rec) return;
+  const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
+  record_row<FULL>(k1 >= 0 ? pose + 7 * k1 : nullptr, k1 >= 0 ? vel + 6 * k1 : nullptr, k1 >= 0 ? V.kf_time[k1] : 0.0,
+                   pose + 7 * k2, vel + 6 * k2, V.kf_time[k2], V.rec_t[r], V.cam[V.rec_cam[r]],
+                   rec_out + (size_t)r * (FULL ? GPBA_REC_STRIDE : GPBA_REC_LITE_STRIDE));
 }
 
 // ------------------------------------------------------------------------------------------------ K1

@@ -21,7 +21,7 @@ SYMBOLS = [
     "gpba_get_hschur", "gpba_get_hll", "gpba_get_hpl", "gpba_oplus", "gpba_push", "gpba_pop", "gpba_discard_top",
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
-    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats",
+    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_pose_optimize",
 ]
 
 
@@ -41,6 +41,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.gpba_last_error.restype = C.c_char_p
         L.gpba_get_stream.restype = C.c_void_p
+        L.gpba_pose_optimize.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
         L.gpba_create.argtypes = [C.POINTER(CProblem), C.c_int, C.POINTER(C.c_void_p)]
         L.gpba_create_dist.argtypes = [C.POINTER(CProblem), C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
         _LIB = L

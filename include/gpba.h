@@ -226,6 +226,48 @@ int gpba_compute_errors_inactive(gpba_handle* h);
 int gpba_rejection_rounds(gpba_handle* h, int n_rounds, int iters, const gpba_thresholds* th,
                           const gpba_lm_params* params, uint8_t* flags_out, gpba_lm_trace* traces /* [n_rounds] */);
 
+/* ---- pose-only GP optimisation ---------------------------------- */
+/* Optimizer::PoseGPOptimizationFromeLastFrame (src/Optimizer.cc:369-686) for a batch of independent frames: per frame
+ * two VertexPoseVel (previous frame, fixed iff prev_fixed; current frame, free), one EdgeMonoGPOnlyPose per match of an
+ * asynchronous camera, EdgeMonoOnlyPose / EdgeStereoOnlyPose per match of the reference camera (the world point is a
+ * constant of the edge, src/G2oTypes.cc:120-223), one EdgeGaussianPrior without kernel (:526-533) and an EdgeVelocity on
+ * both vertices (:535-543).  Four rounds of initializeOptimization(0) + optimize(10) with default lambda
+ * (tau * max diag), re-flagging after every round with float-typed chi2 and thresholds chi2Mono = 5.991 (x1.5 for close
+ * points), chi2Stereo = {15.6, 9.8, 7.815, 7.815}, kernels removed after the third round (:545-670). */
+#define GPBA_POSE_ROUNDS 4
+typedef struct gpba_pose_batch {
+  int32_t n_cam;                 /* async cameras + the reference camera (last)                              */
+  const double* cam_intr;        /* [n_cam][4] fx fy cx cy (float-rounded)                                   */
+  const double* cam_Tbc;         /* [n_cam][7] qx qy qz qw tx ty tz of MultiKeyFrame::mTbc                   */
+  double bf;
+  double qc[6];                  /* diagonal of GaussianProcess::mQc                                         */
+  int32_t n_frames;
+  const double* prev_pose;       /* [n_frames][7] Twb of pFrame->mpPrevFrame                                 */
+  const double* prev_vel;        /* [n_frames][6]                                                            */
+  const double* prev_time;       /* [n_frames]                                                               */
+  const uint8_t* prev_fixed;     /* [n_frames] the `fix` argument                                            */
+  const double* cur_pose;        /* [n_frames][7] Twb of pFrame (initial estimate)                           */
+  const double* cur_vel;         /* [n_frames][6]                                                            */
+  const double* cur_time;        /* [n_frames] pFrame->mTimeStamp                                            */
+  const double* cam_time;        /* [n_frames][n_cam] pFrame->mvTimeStamps                                   */
+  const int64_t* obs_begin;      /* [n_frames+1] matches of frame f = [obs_begin[f], obs_begin[f+1])         */
+  const double* obs_u;           /* kpUn.pt.x                                                                */
+  const double* obs_v;
+  const double* obs_ur;          /* mvuRight (reference camera only), < 0 => monocular; NULL => all mono     */
+  const double* obs_inv_sigma2;  /* mvInvLevelSigma2[octave] / uncertainty2 (float-rounded)                  */
+  const double* obs_xw;          /* [n_obs][3] pMP->GetWorldPos(), constant                                  */
+  const int32_t* obs_cam;        /* mmpKeyToCam                                                              */
+  const uint8_t* obs_flags;      /* GPBA_OBS_CLOSE (mvTrackDepth < 10 m), GPBA_OBS_LEVEL1 (mvbOutlier on entry) */
+  double huber_mono;             /* (float)sqrt(5.991)                                                       */
+  double huber_stereo;           /* (float)sqrt(7.815)                                                       */
+} gpba_pose_batch;
+/* One CTA per frame runs the whole 4 x 10 LM schedule on the device.  Outputs (any may be NULL): optimised states,
+ * mvbOutlier per match, nInitialCorrespondences - nBad per frame (the return value of the reference function) and the
+ * LM trace of every round ([n_frames][GPBA_POSE_ROUNDS]). */
+int gpba_pose_optimize(const gpba_pose_batch* batch, int device, double* cur_pose_out, double* cur_vel_out,
+                       double* prev_pose_out, double* prev_vel_out, uint8_t* outlier_out, int32_t* n_inliers_out,
+                       gpba_lm_trace* traces);
+
 /* ---- measurement ------------------------------------------------------------------- */
 /* Total device time (ms, CUDA event pairs recorded on the library stream, read back only here) and
  * launch count per stage since the last reset: 0 records (K0), 1 residuals (K1), 2 linearize landmarks

@@ -266,6 +266,10 @@ struct BlockSparseChol {
 };
 
 // ----------------------------------------------------------------------------- the optimizer
+}  // namespace
+#include "pose_only.h"
+namespace {
+
 struct Oracle {
   // ---- problem (deep copy)
   int n_cam = 0, n_kf = 0, n_pt = 0, n_rec = 0, n_prior = 0, n_velp = 0;
@@ -1056,6 +1060,20 @@ int oracle_rejection_rounds(void* h, int n_rounds, int iters, const gpba_thresho
 static SE3 se3_from7(const double* p) { SE3 T; T.q = {p[0], p[1], p[2], p[3]}; T.t[0] = p[4]; T.t[1] = p[5]; T.t[2] = p[6]; return T; }
 static void se3_to7(const SE3& T, double* p) { p[0] = T.q.x; p[1] = T.q.y; p[2] = T.q.z; p[3] = T.q.w; p[4] = T.t[0]; p[5] = T.t[1]; p[6] = T.t[2]; }
 static V6 v6(const double* p) { V6 v; for (int i = 0; i < 6; ++i) v[i] = p[i]; return v; }
+// Optimizer::PoseGPOptimizationFromeLastFrame for every frame of the batch (oracle/pose_only.h)
+int oracle_pose_optimize(const gpba_pose_batch* B, double* cur_pose_out, double* cur_vel_out, double* prev_pose_out, double* prev_vel_out,
+                         uint8_t* outlier_out, int32_t* n_inliers_out, gpba_lm_trace* traces) {
+  for (int f = 0; f < B->n_frames; ++f) {
+    ora::PoseOnlyFrame F(B, f);
+    const int inl = F.run(traces ? traces + (size_t)f * GPBA_POSE_ROUNDS : nullptr, outlier_out);
+    if (n_inliers_out) n_inliers_out[f] = inl;
+    if (cur_pose_out) se3_to7(F.s2.Twb, cur_pose_out + 7 * f);
+    if (cur_vel_out) std::memcpy(cur_vel_out + 6 * f, F.s2.vel.a, 48);
+    if (prev_pose_out) se3_to7(F.s1.Twb, prev_pose_out + 7 * f);
+    if (prev_vel_out) std::memcpy(prev_vel_out + 6 * f, F.s1.vel.a, 48);
+  }
+  return 0;
+}
 void oracle_se3_exp(const double* xi, double* out7) { se3_to7(se3_exp(v6(xi)), out7); }
 void oracle_se3_log(const double* T7, double* xi) { V6 v = se3_log(se3_from7(T7)); std::memcpy(xi, v.a, 48); }
 void oracle_se3_mul(const double* a, const double* b, double* out7) { se3_to7(se3_mul(se3_from7(a), se3_from7(b)), out7); }

@@ -19,7 +19,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libgpba_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("gpba_oracle.cc", "gp_edges.h", "lie.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("gpba_oracle.cc", "gp_edges.h", "lie.h", "pose_only.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -253,3 +253,12 @@ def ldlt_dense(A, b):
     n = len(b); x = np.zeros(n)
     ok = lib().oracle_ldlt_dense(n, _p(_d(A)), _p(_d(b)), _p(x))
     return bool(ok), x
+
+
+def pose_optimize(B):
+    """CPU restatement of Optimizer::PoseGPOptimizationFromeLastFrame on a pygpba.pose.PoseBatch (oracle/pose_only.h)."""
+    from pygpba.pose import PoseResult
+    c = B.to_c()
+    R = PoseResult(B)
+    lib().oracle_pose_optimize(C.byref(c), *R.args())
+    return R
