@@ -12,14 +12,14 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 
 def sources():
-    return [os.path.join(SRC, f) for f in sorted(os.listdir(SRC))] + [os.path.join(os.path.dirname(HERE), "include", "gpba.h")]
+    return [os.path.join(SRC, f) for f in sorted(os.listdir(SRC))] + [os.path.join(os.path.dirname(HERE), "include", h) for h in ("gpba.h", "gpba_map.h")]
 
 
 def build(force=False, verbose=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(s) <= os.path.getmtime(OUT) for s in sources()):
         return OUT
     flags = [f for f in FLAGS if f != "--use_fast_math=false"]
-    cmd = [NVCC] + flags + ["-o", OUT, os.path.join(SRC, "gpba_host.cu"), "-ldl"]
+    cmd = [NVCC] + flags + ["-o", OUT, os.path.join(SRC, "gpba_host.cu"), os.path.join(SRC, "gpba_map.cc"), "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
