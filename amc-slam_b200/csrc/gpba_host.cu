@@ -1937,8 +1937,12 @@ int gpba_pose_optimize(const gpba_pose_batch* B, int device, double* cur_pose_ou
   P.obs_flags = d_fl.p; P.level = d_level.p; P.kernel_off = d_koff.p; P.chi2 = d_chi2.p;
   P.out_cur_pose = d_ocp.p; P.out_cur_vel = d_ocv.p; P.out_prev_pose = d_opp.p; P.out_prev_vel = d_opv.p; P.out_inliers = d_inl.p;
   P.traces = traces ? d_tr.p : nullptr;
+  const bool verbose = getenv("GPBA_VERBOSE") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (verbose) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, st)); }
   k_pose_only<<<nf, GPBA_POSE_THREADS, 0, st>>>(P, V);
   CK(cudaGetLastError());
+  if (verbose) CK(cudaEventRecord(e1, st));
   if (cur_pose_out) CK(cudaMemcpyAsync(cur_pose_out, d_ocp.p, sizeof(double) * 7 * nf, cudaMemcpyDeviceToHost, st));
   if (cur_vel_out) CK(cudaMemcpyAsync(cur_vel_out, d_ocv.p, sizeof(double) * 6 * nf, cudaMemcpyDeviceToHost, st));
   if (prev_pose_out) CK(cudaMemcpyAsync(prev_pose_out, d_opp.p, sizeof(double) * 7 * nf, cudaMemcpyDeviceToHost, st));
@@ -1947,6 +1951,12 @@ int gpba_pose_optimize(const gpba_pose_batch* B, int device, double* cur_pose_ou
   if (n_inliers_out) CK(cudaMemcpyAsync(n_inliers_out, d_inl.p, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
   if (traces) CK(cudaMemcpyAsync(traces, d_tr.p, sizeof(gpba_lm_trace) * (size_t)nf * GPBA_POSE_ROUNDS, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (verbose) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    fprintf(stderr, "[gpba] pose-only: %d frames, %lld matches, kernel %.3f ms\n", nf, (long long)n_obs, ms);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   return GPBA_OK;
 }
 

@@ -231,9 +231,13 @@ def test_flattened_window_optimizes_like_the_oracle(oracle_mod):
     from pygpba import lib as G
     from pygpba.problem import Thresholds
     P, M = geometric_map("c1", n_kf=16, n_pt=600, outliers=0.05, seed=21)
+    for k in range(6):   # the keyframes that will be fixed have been optimised before: true state
+        M.set_keyframe_state(10 + 2 * k, np.concatenate([P.truth["kf_q"][k], P.truth["kf_t"][k]]), P.truth["kf_vel"][k])
     W = M.local_window(10 + 2 * 15)
     Q = W.problem
+    assert Q.kf_fixed.sum() == 6 and Q.n_obs > 5000
     g = G.GpBa(Q)
+    g.build_structure()
     chi0 = g.compute_errors()
     tr = g.optimize(W.iterations)
     o = oracle_mod.Oracle(Q)
@@ -253,4 +257,5 @@ def test_flattened_window_optimizes_like_the_oracle(oracle_mod):
     W2 = M.local_window(10 + 2 * 15)
     assert W2.problem.n_obs == Q.n_obs - len(erased)
     g2 = G.GpBa(W2.problem)
-    assert g2.compute_errors() < 0.5 * chi0
+    g2.build_structure()
+    assert g2.compute_errors() < 0.1 * chi0     # the wrong associations are gone

@@ -20,6 +20,11 @@ its = sum(R.trace(f, r)["n_iters"] for f in range(B.n_frames) for r in range(4))
 trials = sum(sum(R.trace(f, r)["trials"]) for f in range(B.n_frames) for r in range(4))
 truth = B.truth_outlier
 print(f" LM iterations {its} trials {trials}  recall {(R.outlier[truth] > 0).mean():.3f}  false positives {(R.outlier[~truth] > 0).mean():.3f}")
+one = B.slice(0)
+lat = 1e9
+for rep in range(20):
+    t = time.time(); PO.pose_optimize(one); lat = min(lat, time.time() - t)
+print(f" single frame ({one.n_obs} matches): {lat * 1e3:.3f} ms per call (host buffers in/out)")
 import oracle_py
 ns = min(16, B.n_frames)
 sub = [B.slice(f) for f in range(ns)]
@@ -28,4 +33,4 @@ for s in sub:
     oracle_py.pose_optimize(s)
 dc = time.time() - t
 print(json.dumps({"metric": "pose_only_frames_per_s", "gpu_e2e": B.n_frames / best, "cpu_port_1core": ns / dc, "frames": B.n_frames,
-                  "matches_per_frame": B.n_obs / B.n_frames, "gpu_ms": best * 1e3, "cpu_sample_frames": ns, "cpu_ms_per_frame": dc * 1e3 / ns}))
+                  "matches_per_frame": B.n_obs / B.n_frames, "gpu_ms": best * 1e3, "single_frame_ms": lat * 1e3, "cpu_sample_frames": ns, "cpu_ms_per_frame": dc * 1e3 / ns}))
