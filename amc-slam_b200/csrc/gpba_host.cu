@@ -10,6 +10,7 @@
 #include "gpba_pcg.cuh"
 #include "gpba_structure.cuh"
 #include "gpba_pose.cuh"
+#include "gpba_vel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -130,7 +131,10 @@ struct StreamHolder {
 struct Solver {
   int device = 0;
   StreamHolder stream_holder;   // first member: destroyed after every buffer has been returned to the pool
+  StreamHolder copy_holder;     // second stream of the asynchronous measurement upload (GPBA_CREATE_ASYNC_UPLOAD)
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev_meas = nullptr;
+  bool meas_pending = false;    // the measurement copies have been enqueued on copy_holder.s and not yet waited for
   // ------------------------------------------------------------------ host copy of the problem
   int n_cam = 0, n_kf = 0, n_pt = 0, n_rec = 0, n_prior = 0, n_velp = 0;
   int64_t n_obs = 0;
@@ -271,7 +275,7 @@ struct Solver {
     ev_used = 0;
   }
 
-  int init(const gpba_problem* P, int dev);
+  int init(const gpba_problem* P, int dev, bool async_upload);
   int build_structure();
   int build_cholesky_structure();
   int capture_cholesky_graph();
@@ -291,12 +295,20 @@ struct Solver {
 
 static double f32sq(double d) { return (double)(float)(d * d); }  // RobustKernelHuber::setDelta: float dsqr
 
-int Solver::init(const gpba_problem* P, int dev) {
+int Solver::init(const gpba_problem* P, int dev, bool async_upload) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device (libgpba has no CPU fallback)"; return GPBA_ERR_NO_DEVICE; }
   if (dev < 0) CK(cudaGetDevice(&dev));
   device = dev;
   CK(cudaSetDevice(device));
+  const bool verbose_init = getenv("GPBA_VERBOSE") != nullptr;
+  auto ti0 = std::chrono::steady_clock::now();
+  auto ilap = [&](const char* what) {
+    if (!verbose_init) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gpba] create %-32s %6.2f ms\n", what, std::chrono::duration<double, std::milli>(t - ti0).count());
+    ti0 = t;
+  };
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   stream_holder.s = stream;
   g_alloc_stream = stream;
@@ -366,13 +378,34 @@ int Solver::init(const gpba_problem* P, int dev) {
     CK(cudaStreamSynchronize(stream));
     if (*h_fail) { g_err = "observation index out of range"; return GPBA_ERR_INVALID; }
   }
-  CKR(d_all_u.upload(P->obs_u, (size_t)n_obs, stream)); CKR(d_all_v.upload(P->obs_v, (size_t)n_obs, stream));
-  CKR(d_all_w.upload(P->obs_inv_sigma2, (size_t)n_obs, stream));
-  if (stereo) CKR(d_all_ur.upload(P->obs_ur, (size_t)n_obs, stream));
+  ilap("host copies + index upload + check");
+  if (async_upload && n_obs > 0) {
+    // allocate in stream order on the main stream, copy on the second stream: build_structure works on the index
+    // arrays meanwhile and waits for ev_meas right before it needs the measurements
+    CKR(d_all_u.alloc((size_t)n_obs)); CKR(d_all_v.alloc((size_t)n_obs)); CKR(d_all_w.alloc((size_t)n_obs));
+    if (stereo) CKR(d_all_ur.alloc((size_t)n_obs));
+    CK(cudaStreamCreateWithFlags(&copy_holder.s, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_meas, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_meas, stream));
+    CK(cudaStreamWaitEvent(copy_holder.s, ev_meas, 0));
+    const size_t nb = sizeof(double) * (size_t)n_obs;
+    CK(cudaMemcpyAsync(d_all_u.p, P->obs_u, nb, cudaMemcpyHostToDevice, copy_holder.s));
+    CK(cudaMemcpyAsync(d_all_v.p, P->obs_v, nb, cudaMemcpyHostToDevice, copy_holder.s));
+    CK(cudaMemcpyAsync(d_all_w.p, P->obs_inv_sigma2, nb, cudaMemcpyHostToDevice, copy_holder.s));
+    if (stereo) CK(cudaMemcpyAsync(d_all_ur.p, P->obs_ur, nb, cudaMemcpyHostToDevice, copy_holder.s));
+    CK(cudaEventRecord(ev_meas, copy_holder.s));
+    meas_pending = true;
+  } else {
+    CKR(d_all_u.upload(P->obs_u, (size_t)n_obs, stream)); CKR(d_all_v.upload(P->obs_v, (size_t)n_obs, stream));
+    CKR(d_all_w.upload(P->obs_inv_sigma2, (size_t)n_obs, stream));
+    if (stereo) CKR(d_all_ur.upload(P->obs_ur, (size_t)n_obs, stream));
+  }
   CKR(d_rec.alloc((size_t)n_rec * GPBA_REC_STRIDE)); CKR(d_rec_lite.alloc((size_t)n_rec * GPBA_REC_LITE_STRIDE));
   CKR(d_recS.alloc((size_t)n_rec * 27)); CKR(d_Y.alloc((size_t)n_rec * 6));
   CKR(d_prior_rho.alloc((size_t)n_prior + n_velp));
+  ilap("measurement upload enqueued");
   CK(cudaStreamSynchronize(stream));
+  ilap("final sync");
   return GPBA_OK;
 }
 
@@ -577,8 +610,7 @@ int Solver::build_structure() {
   const int gobs = (int)std::min<int64_t>((n_aobs + 255) / 256 + 1, 148 * 16);
   std::vector<int64_t> rcount(n_rec + 1, 0);
   if (n_aobs > 0) {
-    k_gather_obs<<<gobs, 256, 0, stream>>>(n_aobs, d_o_orig.p, d_all_u.p, d_all_v.p, stereo ? d_all_ur.p : nullptr, d_all_w.p, d_all_rec.p,
-                                           d_all_flags.p, d_o_u.p, d_o_v.p, stereo ? d_o_ur.p : nullptr, d_o_w.p, d_o_rec.p, d_o_flags.p);
+    k_gather_obs_idx<<<gobs, 256, 0, stream>>>(n_aobs, d_o_orig.p, d_all_rec.p, d_all_flags.p, d_o_rec.p, d_o_flags.p);
     CKR(d_rcnt.alloc((size_t)n_rec));
     CK(cudaMemsetAsync(d_rcnt.p, 0, sizeof(int) * (size_t)n_rec, stream));
     k_hist_int<<<gobs, 256, 0, stream>>>(n_aobs, d_o_rec.p, d_rcnt.p);
@@ -839,11 +871,16 @@ int Solver::build_structure() {
     CK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, need, d_o_rec.p, kout.p, vin.p, d_rperm.p, n_aobs, 0, bits_for((unsigned long long)n_rec), stream));
     CKR(d_r_u.alloc(na)); CKR(d_r_v.alloc(na)); CKR(d_r_w.alloc(na)); CKR(d_r_lm.alloc(na)); CKR(d_r_flags.alloc(na));
     if (stereo) CKR(d_r_ur.alloc(na));
+    // the measurements are first needed here: everything above worked on indices and flags only
+    if (meas_pending) { CK(cudaStreamWaitEvent(stream, ev_meas, 0)); }
+    k_gather_obs_meas<<<gobs, 256, 0, stream>>>(n_aobs, d_o_orig.p, d_all_u.p, d_all_v.p, stereo ? d_all_ur.p : nullptr, d_all_w.p,
+                                                d_o_u.p, d_o_v.p, stereo ? d_o_ur.p : nullptr, d_o_w.p);
     k_gather_recmajor<<<gobs, 256, 0, stream>>>(n_aobs, d_rperm.p, d_o_u.p, d_o_v.p, stereo ? d_o_ur.p : nullptr, d_o_w.p, d_o_lm.p, d_o_flags.p,
                                                 d_r_u.p, d_r_v.p, stereo ? d_r_ur.p : nullptr, d_r_w.p, d_r_lm.p, d_r_flags.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(stream));
   }
+  if (meas_pending) { CK(cudaStreamSynchronize(copy_holder.s)); meas_pending = false; }   // the caller's arrays are free again
   const int SEG = 512;
   std::vector<int> rseg_rec; std::vector<int64_t> rseg_begin;
   for (int r = 0; r < n_rec; ++r)
@@ -1429,19 +1466,22 @@ void gpba_default_lm_params(gpba_lm_params* p) {
   p->pcg_tolerance = 1e-12; p->pcg_max_iterations = 4000;
 }
 
-int gpba_create(const gpba_problem* prob, int device, gpba_handle** out) {
+static int create_impl(const gpba_problem* prob, int device, bool async_upload, gpba_handle** out) {
   if (!prob || !out) { g_err = "null argument"; return GPBA_ERR_INVALID; }
   gpba_handle* h = new (std::nothrow) gpba_handle();
   if (!h) return GPBA_ERR_INVALID;
-  int rc = h->s.init(prob, device);
-  if (rc != GPBA_OK) { delete h; return rc; }
+  int rc = h->s.init(prob, device, async_upload);
+  if (rc != GPBA_OK) { if (h->s.copy_holder.s) cudaStreamSynchronize(h->s.copy_holder.s); delete h; return rc; }
   *out = h;
   return GPBA_OK;
 }
+int gpba_create(const gpba_problem* prob, int device, gpba_handle** out) { return create_impl(prob, device, false, out); }
 
 int gpba_destroy(gpba_handle* h) {
   if (h) {
     cudaSetDevice(h->s.device); g_alloc_stream = h->s.stream;
+    if (h->s.copy_holder.s) cudaStreamSynchronize(h->s.copy_holder.s);   // no copy may be in flight when the buffers go
+    if (h->s.ev_meas) { cudaEventDestroy(h->s.ev_meas); h->s.ev_meas = nullptr; }
     const bool verbose = getenv("GPBA_VERBOSE") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
     if (h->s.chol_graph) { cudaGraphExecDestroy(h->s.chol_graph); h->s.chol_graph = nullptr; }
@@ -1465,11 +1505,20 @@ static std::mutex g_comm_mutex;
 static std::map<std::string, ncclComm_t> g_comms;
 
 int gpba_create_dist(const gpba_problem* prob, int device, int rank, int nranks, const unsigned char id[128], gpba_handle** out) {
+  gpba_create_options o;
+  o.device = device; o.rank = rank; o.nranks = nranks; o.nccl_id = id; o.flags = 0;
+  return gpba_create_ex(prob, &o, out);
+}
+
+int gpba_create_ex(const gpba_problem* prob, const gpba_create_options* opt, gpba_handle** out) {
+  if (!opt) { g_err = "null argument"; return GPBA_ERR_INVALID; }
+  const int device = opt->device, rank = opt->rank, nranks = opt->nranks;
+  const unsigned char* id = opt->nccl_id;
   if (nranks > 1 && (!id || rank < 0 || rank >= nranks)) { g_err = "bad rank / NCCL id"; return GPBA_ERR_INVALID; }
-  int rc = gpba_create(prob, device, out);
+  int rc = create_impl(prob, device, (opt->flags & GPBA_CREATE_ASYNC_UPLOAD) != 0, out);
   if (rc != GPBA_OK) return rc;
   Solver& s = (*out)->s;
-  s.rank = rank; s.nranks = nranks;
+  s.rank = nranks > 1 ? rank : 0; s.nranks = nranks > 1 ? nranks : 1;
   if (nranks > 1) {
     if (!g_nccl.load()) { g_err = "libnccl.so.2 not found"; gpba_destroy(*out); *out = nullptr; return GPBA_ERR_NCCL; }
     std::lock_guard<std::mutex> lock(g_comm_mutex);
@@ -1957,6 +2006,75 @@ int gpba_pose_optimize(const gpba_pose_batch* B, int device, double* cur_pose_ou
     fprintf(stderr, "[gpba] pose-only: %d frames, %lld matches, kernel %.3f ms\n", nf, (long long)n_obs, ms);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
+  return GPBA_OK;
+}
+
+// ---- velocity RANSAC (Tracking::MCRansac / Optimizer::OptimizeVel, src/Tracking.cc:1939-2002, src/Optimizer.cc:2364-2447)
+int gpba_vel_ransac(const gpba_vel_batch* B, int device, double* vel_out, int32_t* inliers_out, uint8_t* inlier_mask_out,
+                    int32_t* best_out, gpba_lm_trace* traces) {
+  if (!B || B->n_cam < 1 || B->n_cam > GPBA_VEL_MAX_CAM || !B->cam_intr || !B->cam_Tbc || !B->cam_dt || B->n_match < 0 || B->n_hyp < 0 ||
+      B->set_size < 1 || B->set_size > GPBA_VEL_MAX_SET || B->iterations < 0 || B->iterations > GPBA_MAX_ITERS) { g_err = "invalid velocity batch"; return GPBA_ERR_INVALID; }
+  if (best_out) *best_out = -1;
+  if (B->n_hyp == 0) return GPBA_OK;
+  if (!B->samples || (B->n_match > 0 && (!B->obs_u || !B->obs_v || !B->obs_inv_sigma2 || !B->obs_xw || !B->obs_cam))) { g_err = "invalid velocity batch"; return GPBA_ERR_INVALID; }
+  for (int i = 0; i < B->n_match; ++i) if (B->obs_cam[i] < 0 || B->obs_cam[i] >= B->n_cam) { g_err = "camera index out of range"; return GPBA_ERR_INVALID; }
+  for (int64_t i = 0; i < (int64_t)B->n_hyp * B->set_size; ++i) if (B->samples[i] < 0 || B->samples[i] >= B->n_match) { g_err = "sample index out of range"; return GPBA_ERR_INVALID; }
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device (libgpba has no CPU fallback)"; return GPBA_ERR_NO_DEVICE; }
+  }
+  if (device < 0) CK(cudaGetDevice(&device));
+  CK(cudaSetDevice(device));
+  StreamHolder sh;   // declared before the buffers: destroyed after they went back to the pool
+  CK(cudaStreamCreateWithFlags(&sh.s, cudaStreamNonBlocking));
+  cudaStream_t st = sh.s;
+  g_alloc_stream = st;
+  std::vector<CamConst> cams(B->n_cam);
+  for (int c = 0; c < B->n_cam; ++c) {
+    CamConst& cc = cams[c];
+    cc.fx = B->cam_intr[4 * c]; cc.fy = B->cam_intr[4 * c + 1]; cc.cx = B->cam_intr[4 * c + 2]; cc.cy = B->cam_intr[4 * c + 3];
+    SE3 Tbc = load_se3(B->cam_Tbc + 7 * c);
+    SE3 Tcb = se3_inv(Tbc);
+    M3 Rcb = quat_to_R(Tcb.q), Rbc = quat_to_R(Tbc.q);
+    for (int i = 0; i < 9; ++i) { cc.Rcb[i] = Rcb.a[i]; cc.Rbc[i] = Rbc.a[i]; }
+    for (int i = 0; i < 3; ++i) { cc.tcb[i] = Tcb.t[i]; cc.tbc[i] = Tbc.t[i]; }
+    cc.qbc[0] = Tbc.q.x; cc.qbc[1] = Tbc.q.y; cc.qbc[2] = Tbc.q.z; cc.qbc[3] = Tbc.q.w;
+  }
+  const size_t nm = (size_t)B->n_match, nh = (size_t)B->n_hyp;
+  DBuf<CamConst> d_cam;
+  DBuf<double> d_dt, d_u, d_v, d_w, d_xw, d_vel;
+  DBuf<int> d_camof, d_samples, d_inl;
+  DBuf<uint8_t> d_mask;
+  DBuf<gpba_lm_trace> d_tr;
+  CKR(d_cam.upload(cams, st)); CKR(d_dt.upload(B->cam_dt, (size_t)B->n_cam, st));
+  CKR(d_u.upload(B->obs_u, nm, st)); CKR(d_v.upload(B->obs_v, nm, st)); CKR(d_w.upload(B->obs_inv_sigma2, nm, st));
+  CKR(d_xw.upload(B->obs_xw, 3 * nm, st)); CKR(d_camof.upload(B->obs_cam, nm, st));
+  CKR(d_samples.upload(B->samples, nh * B->set_size, st));
+  CKR(d_vel.alloc(6 * nh)); CKR(d_inl.alloc(nh));
+  if (inlier_mask_out) CKR(d_mask.alloc(nh * std::max<size_t>(nm, 1)));
+  if (traces) CKR(d_tr.alloc(nh));
+  VelView V;
+  V.n_cam = B->n_cam; V.n_match = B->n_match; V.n_hyp = B->n_hyp; V.set_size = B->set_size; V.iterations = B->iterations;
+  V.cam = d_cam.p; V.cam_dt = d_dt.p;
+  store_se3(se3_inv(load_se3(B->last_pose)), V.Tinv);
+  for (int i = 0; i < 6; ++i) V.vel_init[i] = B->vel_init[i];
+  V.obs_u = d_u.p; V.obs_v = d_v.p; V.obs_w = d_w.p; V.obs_xw = d_xw.p; V.obs_cam = d_camof.p; V.samples = d_samples.p;
+  V.hub_delta = B->huber_delta; V.hub_dsqr = f32sq(B->huber_delta); V.threshold = B->threshold;
+  V.vel_out = d_vel.p; V.inliers_out = d_inl.p; V.mask_out = inlier_mask_out ? d_mask.p : nullptr; V.traces = traces ? d_tr.p : nullptr;
+  k_vel_ransac<<<B->n_hyp, GPBA_VEL_THREADS, 0, st>>>(V);
+  CK(cudaGetLastError());
+  std::vector<int> inl(nh);
+  CK(cudaMemcpyAsync(inl.data(), d_inl.p, sizeof(int) * nh, cudaMemcpyDeviceToHost, st));
+  if (vel_out) CK(cudaMemcpyAsync(vel_out, d_vel.p, sizeof(double) * 6 * nh, cudaMemcpyDeviceToHost, st));
+  if (inlier_mask_out && nm) CK(cudaMemcpyAsync(inlier_mask_out, d_mask.p, nh * nm, cudaMemcpyDeviceToHost, st));
+  if (traces) CK(cudaMemcpyAsync(traces, d_tr.p, sizeof(gpba_lm_trace) * nh, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int best = -1, best_inl = 0;
+  for (size_t h = 0; h < nh; ++h) {
+    if (inliers_out) inliers_out[h] = inl[h];
+    if (inl[h] > best_inl) { best_inl = inl[h]; best = (int)h; }   // `inliers > bestInliers` (Tracking.cc:1973)
+  }
+  if (best_out) *best_out = best;
   return GPBA_OK;
 }
 

@@ -86,15 +86,21 @@ __global__ void k_check_indices(int64_t n_obs, const int* __restrict__ rec, cons
     if (rec[i] < 0 || rec[i] >= n_rec || pt[i] < 0 || pt[i] >= n_pt) *bad = 1;
 }
 
-// sorted (by landmark) copies of the per-observation inputs
-__global__ void k_gather_obs(int64_t n, const int64_t* __restrict__ o_orig, const double* __restrict__ u,
-                             const double* __restrict__ v, const double* __restrict__ ur, const double* __restrict__ w,
-                             const int* __restrict__ rec, const uint8_t* __restrict__ flags, double* __restrict__ su,
-                             double* __restrict__ sv, double* __restrict__ sur, double* __restrict__ sw,
-                             int* __restrict__ srec, uint8_t* __restrict__ sfl) {
+// gather of the landmark-sorted observation arrays, split in two for the asynchronous upload: indices first, measurements
+// when their copy has landed
+__global__ void k_gather_obs_idx(int64_t n, const int64_t* __restrict__ o_orig, const int* __restrict__ rec,
+                                 const uint8_t* __restrict__ flags, int* __restrict__ srec, uint8_t* __restrict__ sfl) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = o_orig[j];
-    su[j] = u[i]; sv[j] = v[i]; sw[j] = w[i]; srec[j] = rec[i]; sfl[j] = flags[i];
+    srec[j] = rec[i]; sfl[j] = flags[i];
+  }
+}
+__global__ void k_gather_obs_meas(int64_t n, const int64_t* __restrict__ o_orig, const double* __restrict__ u,
+                                  const double* __restrict__ v, const double* __restrict__ ur, const double* __restrict__ w,
+                                  double* __restrict__ su, double* __restrict__ sv, double* __restrict__ sur, double* __restrict__ sw) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = o_orig[j];
+    su[j] = u[i]; sv[j] = v[i]; sw[j] = w[i];
     if (ur) sur[j] = ur[i];
   }
 }

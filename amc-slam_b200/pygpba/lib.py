@@ -15,13 +15,13 @@ _LIB = None
 
 # every symbol include/gpba.h declares
 SYMBOLS = [
-    "gpba_create", "gpba_destroy", "gpba_last_error", "gpba_default_lm_params", "gpba_nccl_unique_id", "gpba_create_dist",
+    "gpba_create", "gpba_destroy", "gpba_last_error", "gpba_default_lm_params", "gpba_nccl_unique_id", "gpba_create_dist", "gpba_create_ex",
     "gpba_build_structure", "gpba_get_hpp_pattern", "gpba_get_hschur_pattern", "gpba_compute_errors", "gpba_build_system",
     "gpba_set_lambda", "gpba_restore_diagonal", "gpba_solve", "gpba_vector_size", "gpba_get_x", "gpba_get_b", "gpba_get_hpp",
     "gpba_get_hschur", "gpba_get_hll", "gpba_get_hpl", "gpba_oplus", "gpba_push", "gpba_pop", "gpba_discard_top",
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
-    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_pose_optimize",
+    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_pose_optimize", "gpba_vel_ransac",
 ]
 
 
@@ -42,6 +42,7 @@ def lib():
         L.gpba_last_error.restype = C.c_char_p
         L.gpba_get_stream.restype = C.c_void_p
         L.gpba_pose_optimize.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        L.gpba_vel_ransac.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.gpba_create.argtypes = [C.POINTER(CProblem), C.c_int, C.POINTER(C.c_void_p)]
         L.gpba_create_dist.argtypes = [C.POINTER(CProblem), C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
         _LIB = L
@@ -69,12 +70,16 @@ def nccl_unique_id():
 class GpBa:
     """One handle == one g2o::SparseOptimizer + BlockSolverX + OptimizationAlgorithmLevenberg instance."""
 
-    def __init__(self, prob, device=-1, rank=0, nranks=1, nccl_id=None):
-        self.prob = prob
+    def __init__(self, prob, device=-1, rank=0, nranks=1, nccl_id=None, async_upload=False):
+        self.prob = prob      # keeps the host arrays alive (required until build_structure with async_upload)
         self._c = prob.to_c()
         self.L = lib()
         self.h = C.c_void_p()
-        if nranks > 1:
+        if async_upload:
+            from .problem import CreateOptions, CREATE_ASYNC_UPLOAD
+            o = CreateOptions(int(device), int(rank), int(nranks), nccl_id if nranks > 1 else None, CREATE_ASYNC_UPLOAD)
+            rc = self.L.gpba_create_ex(C.byref(self._c), C.byref(o), C.byref(self.h))
+        elif nranks > 1:
             rc = self.L.gpba_create_dist(C.byref(self._c), device, rank, nranks, nccl_id, C.byref(self.h))
         else:
             rc = self.L.gpba_create(C.byref(self._c), device, C.byref(self.h))

@@ -67,6 +67,13 @@ class Thresholds(C.Structure):
         return Thresholds(float(m), float(np.float32(1.5) * m), float(np.float32(7.815)))
 
 
+CREATE_ASYNC_UPLOAD = 0x1
+
+
+class CreateOptions(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_id", C.c_char_p), ("flags", C.c_uint32)]
+
+
 class StructureInfo(C.Structure):
     _fields_ = [("n_free_kf", C.c_int32), ("n_active_pt", C.c_int32), ("n_active_obs", C.c_int64),
                 ("n_hpl", C.c_int64), ("n_hpp", C.c_int32), ("n_hschur", C.c_int32)]

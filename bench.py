@@ -284,7 +284,7 @@ def run_gpba(args):
     for s in range(1 + n_e2e):
         barrier()
         t = time.perf_counter()
-        h = gl.GpBa(P, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+        h = gl.GpBa(P, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id, async_upload=True)
         tr = h.optimize(LM_ITERS, params)
         h.download_into(kp, kv, pt)
         h.close()

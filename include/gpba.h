@@ -166,6 +166,20 @@ int gpba_nccl_unique_id(unsigned char id_out[128]);
 int gpba_create_dist(const gpba_problem* prob, int device, int rank, int nranks,
                      const unsigned char nccl_unique_id[128], gpba_handle** out);
 
+/* General form of the two calls above.  GPBA_CREATE_ASYNC_UPLOAD: the per-observation measurement arrays (obs_u, obs_v,
+ * obs_ur, obs_inv_sigma2 -- two thirds of the upload) are copied on a second stream while gpba_build_structure already
+ * sorts and pairs the index arrays; with this flag those four arrays must stay valid and unchanged until the first
+ * gpba_build_structure / gpba_optimize / gpba_destroy call on the handle returns (without it every array may be freed
+ * as soon as gpba_create returns).  Pinned host memory is needed for the copies to overlap. */
+#define GPBA_CREATE_ASYNC_UPLOAD 0x1u
+typedef struct gpba_create_options {
+  int32_t device;                /* < 0: current device                         */
+  int32_t rank, nranks;          /* nranks <= 1: single GPU                     */
+  const unsigned char* nccl_id;  /* [128], required when nranks > 1             */
+  uint32_t flags;                /* GPBA_CREATE_*                               */
+} gpba_create_options;
+int gpba_create_ex(const gpba_problem* prob, const gpba_create_options* opt, gpba_handle** out);
+
 /* ---- L1: g2o::Solver / BlockSolver-shaped --------------------------------------- */
 /* BlockSolver::buildStructure (block_solver.hpp:142-295) + SparseOptimizer::initializeOptimization
  * (sparse_optimizer.cpp:199-267): active set, index mapping, Hpp/Hpl/Hschur block pattern. */
@@ -267,6 +281,40 @@ typedef struct gpba_pose_batch {
 int gpba_pose_optimize(const gpba_pose_batch* batch, int device, double* cur_pose_out, double* cur_vel_out,
                        double* prev_pose_out, double* prev_vel_out, uint8_t* outlier_out, int32_t* n_inliers_out,
                        gpba_lm_trace* traces);
+
+/* ---- velocity RANSAC -------------------------------------------- */
+/* Tracking::MCRansac (src/Tracking.cc:1939-2002) = maxIt x Optimizer::OptimizeVel (src/Optimizer.cc:2364-2447) over one
+ * frame pair, as ONE call: every hypothesis is a g2o graph with a single VertexVel (6-dim body twist, additive oplus,
+ * include/G2oTypes.h:128-145) and one EdgeVelReproj per matched feature (G2oTypes.h:521-547, src/G2oTypes.cc:497-510:
+ * e = obs - project((T_last exp(v dt_cam) T_bc)^-1 X_w), Huber delta = 5.991, information = I * invSigma2), of which only
+ * the `set_size` sampled edges are active (level 0); optimize(40) with the default lambda; afterwards every edge is
+ * re-evaluated and counted as inlier when |e| <= threshold.  The caller draws the sample sets (std::mt19937 in the
+ * reference) and keeps the best hypothesis: best_out = first hypothesis with the largest inlier count (`inliers >
+ * bestInliers`, Tracking.cc:1973). */
+typedef struct gpba_vel_batch {
+  int32_t n_cam;
+  const double* cam_intr;        /* [n_cam][4] fx fy cx cy                                              */
+  const double* cam_Tbc;         /* [n_cam][7] MultiFrame::mTbc                                         */
+  const double* cam_dt;          /* [n_cam] pF1->mvTimeStamps[cam] - pF2->mTimeStamp                    */
+  double last_pose[7];           /* pF2->GetPoseW(): Twb of the last frame                              */
+  double vel_init[6];            /* pF1->GetVelocity(): initial estimate of every hypothesis            */
+  int32_t n_match;               /* vMatchedFeatures.size()                                             */
+  const double* obs_u;           /* [n_match] kpUn.pt.x                                                 */
+  const double* obs_v;
+  const double* obs_inv_sigma2;  /* [n_match] mvInvLevelSigma2[octave]                                  */
+  const double* obs_xw;          /* [n_match][3] pMP->GetWorldPos()                                     */
+  const int32_t* obs_cam;        /* [n_match] mmpKeyToCam                                               */
+  int32_t n_hyp;                 /* maxIt (23 at Tracking.cc:2029)                                      */
+  int32_t set_size;              /* min_set = 3 (Tracking.cc:1947); <= 8                                */
+  const int32_t* samples;        /* [n_hyp][set_size] indices into the match arrays, distinct per row   */
+  double huber_delta;            /* 5.991 (Optimizer.cc:2410)                                           */
+  double threshold;              /* 2.0 px (include/Optimizer.h:86)                                     */
+  int32_t iterations;            /* 40 (Optimizer.cc:2423)                                              */
+} gpba_vel_batch;
+/* Outputs (any may be NULL): vel_out [n_hyp][6], inliers_out [n_hyp], inlier_mask_out [n_hyp][n_match] (vbInliers),
+ * best_out (index of the winning hypothesis, -1 if no hypothesis has an inlier), traces [n_hyp]. */
+int gpba_vel_ransac(const gpba_vel_batch* batch, int device, double* vel_out, int32_t* inliers_out,
+                    uint8_t* inlier_mask_out, int32_t* best_out, gpba_lm_trace* traces);
 
 /* ---- measurement ------------------------------------------------------------------- */
 /* Total device time (ms, CUDA event pairs recorded on the library stream, read back only here) and

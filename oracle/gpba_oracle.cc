@@ -268,6 +268,7 @@ struct BlockSparseChol {
 // ----------------------------------------------------------------------------- the optimizer
 }  // namespace
 #include "pose_only.h"
+#include "vel_ransac.h"
 namespace {
 
 struct Oracle {
@@ -1072,6 +1073,19 @@ int oracle_pose_optimize(const gpba_pose_batch* B, double* cur_pose_out, double*
     if (prev_pose_out) se3_to7(F.s1.Twb, prev_pose_out + 7 * f);
     if (prev_vel_out) std::memcpy(prev_vel_out + 6 * f, F.s1.vel.a, 48);
   }
+  return 0;
+}
+// Tracking::MCRansac's hypotheses, one Optimizer::OptimizeVel each (oracle/vel_ransac.h)
+int oracle_vel_ransac(const gpba_vel_batch* B, double* vel_out, int32_t* inliers_out, uint8_t* mask_out, int32_t* best_out, gpba_lm_trace* traces) {
+  int best = -1, best_inl = 0;
+  for (int h = 0; h < B->n_hyp; ++h) {
+    ora::VelHypothesis H(B);
+    const int inl = H.run(B->samples + (size_t)h * B->set_size, vel_out ? vel_out + 6 * h : nullptr,
+                          mask_out ? mask_out + (size_t)h * B->n_match : nullptr, traces ? traces + h : nullptr);
+    if (inliers_out) inliers_out[h] = inl;
+    if (inl > best_inl) { best_inl = inl; best = h; }
+  }
+  if (best_out) *best_out = best;
   return 0;
 }
 void oracle_se3_exp(const double* xi, double* out7) { se3_to7(se3_exp(v6(xi)), out7); }

@@ -262,3 +262,13 @@ def pose_optimize(B):
     R = PoseResult(B)
     lib().oracle_pose_optimize(C.byref(c), *R.args())
     return R
+
+
+def vel_ransac(B):
+    """CPU restatement of Tracking::MCRansac's hypotheses (Optimizer::OptimizeVel each) on a pygpba.velransac.VelBatch
+    (oracle/vel_ransac.h)."""
+    from pygpba.velransac import VelResult
+    c = B.to_c()
+    R = VelResult(B)
+    lib().oracle_vel_ransac(C.byref(c), *R.args())
+    return R

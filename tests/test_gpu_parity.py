@@ -237,3 +237,21 @@ def test_l1_stepping_equals_l2(G):
                 break
         chis.append(cur)
     np.testing.assert_allclose(chis, tr["chi2_after"][:4], rtol=1e-10)
+
+
+def test_async_upload_equals_sync(G):
+    """gpba_create_ex(GPBA_CREATE_ASYNC_UPLOAD): the measurement arrays travel on a second stream while the structure is
+    built from the index arrays."""
+    P = synth.make_problem("c2")
+    a = G.GpBa(P)
+    b = G.GpBa(P, async_upload=True)
+    ta, tb = a.optimize(10).summary(), b.optimize(10).summary()
+    # same kernels on the same data; the atomically accumulated sums (Hll, C) make any two runs differ in the last bits
+    assert ta["n_iters"] == tb["n_iters"] and ta["trials"] == tb["trials"]
+    np.testing.assert_allclose(ta["chi2_after"], tb["chi2_after"], rtol=1e-12)
+    for x, y in zip(a.state(), b.state()):
+        np.testing.assert_allclose(x, y, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(a.edge_chi2(), b.edge_chi2(), rtol=1e-9, atol=1e-12)
+    # a handle destroyed before its structure was ever built must wait for its copies
+    c = G.GpBa(P, async_upload=True)
+    c.close()
