@@ -2061,14 +2061,24 @@ int gpba_vel_ransac(const gpba_vel_batch* B, int device, double* vel_out, int32_
   V.obs_u = d_u.p; V.obs_v = d_v.p; V.obs_w = d_w.p; V.obs_xw = d_xw.p; V.obs_cam = d_camof.p; V.samples = d_samples.p;
   V.hub_delta = B->huber_delta; V.hub_dsqr = f32sq(B->huber_delta); V.threshold = B->threshold;
   V.vel_out = d_vel.p; V.inliers_out = d_inl.p; V.mask_out = inlier_mask_out ? d_mask.p : nullptr; V.traces = traces ? d_tr.p : nullptr;
+  const bool verbose = getenv("GPBA_VERBOSE") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (verbose) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, st)); }
   k_vel_ransac<<<B->n_hyp, GPBA_VEL_THREADS, 0, st>>>(V);
   CK(cudaGetLastError());
+  if (verbose) CK(cudaEventRecord(e1, st));
   std::vector<int> inl(nh);
   CK(cudaMemcpyAsync(inl.data(), d_inl.p, sizeof(int) * nh, cudaMemcpyDeviceToHost, st));
   if (vel_out) CK(cudaMemcpyAsync(vel_out, d_vel.p, sizeof(double) * 6 * nh, cudaMemcpyDeviceToHost, st));
   if (inlier_mask_out && nm) CK(cudaMemcpyAsync(inlier_mask_out, d_mask.p, nh * nm, cudaMemcpyDeviceToHost, st));
   if (traces) CK(cudaMemcpyAsync(traces, d_tr.p, sizeof(gpba_lm_trace) * nh, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (verbose) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    fprintf(stderr, "[gpba] velocity ransac: %d hypotheses, %d matches, kernel %.3f ms\n", B->n_hyp, B->n_match, ms);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   int best = -1, best_inl = 0;
   for (size_t h = 0; h < nh; ++h) {
     if (inliers_out) inliers_out[h] = inl[h];

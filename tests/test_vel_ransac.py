@@ -8,10 +8,18 @@ fits exactly (6 equations, 6 unknowns) drives chi2 to ~1e-26; from there on the 
 the comparison is on what the reference function returns: the twist (1e-7), the inlier mask (identical except matches
 within 1e-6 px of the threshold) and the winning hypothesis.
 """
+import importlib.util
+import os
+
 import numpy as np
 import pytest
 
 from pygpba import velransac as VR
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location("make_golden_vel", os.path.join(HERE, "golden", "make_golden_vel.py"))
+mgv = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mgv)
 
 
 def test_vel_oracle_converges_quadratically_on_exact_samples(oracle_mod):
@@ -44,6 +52,29 @@ def test_vel_oracle_selects_first_best_hypothesis(oracle_mod):
 def test_vel_oracle_no_hypothesis(oracle_mod):
     B = VR.make_vel_batch(n_match=50, n_hyp=0)
     assert oracle_mod.vel_ransac(B).best.value == -1
+
+
+@pytest.mark.parametrize("key", sorted(mgv.CASES))
+def test_vel_oracle_reproduces_golden(oracle_mod, key):
+    G = np.load(os.path.join(HERE, "golden", "vel_" + key + ".npz"))
+    B = VR.make_vel_batch(**mgv.CASES[key])
+    assert mgv.input_checksum(B) == str(G["input_sha256"])
+    out = mgv.pack(B, oracle_mod.vel_ransac(B))
+    for f in ("inliers", "mask", "best", "n_iters"):
+        assert np.array_equal(out[f], G[f]), f
+    np.testing.assert_allclose(out["vel"], G["vel"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(mgv.CASES))
+def test_vel_ransac_matches_golden(key):
+    G = np.load(os.path.join(HERE, "golden", "vel_" + key + ".npz"))
+    B = VR.make_vel_batch(**mgv.CASES[key])
+    R = VR.vel_ransac(B)
+    well = G["inliers"] >= 30
+    assert np.abs(R.vel[well] - G["vel"][well]).max() <= 1e-7
+    assert (R.mask[well] != G["mask"][well]).sum() <= 1
+    assert int(R.best.value) == int(G["best"])
 
 
 @pytest.mark.gpu
