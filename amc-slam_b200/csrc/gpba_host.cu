@@ -123,6 +123,19 @@ struct PinnedSlots {
 };
 static PinnedSlots g_pinned;
 
+// The frame-rate entry points (gpba_pose_optimize, gpba_vel_ransac) are called a few times per frame from one tracking
+// thread: they keep one stream per (host thread, device) instead of creating and destroying one per call.  The streams
+// live as long as the process (destroying CUDA objects from thread-exit handlers races with runtime teardown).
+static cudaStream_t small_call_stream(int device) {
+  static thread_local std::map<int, cudaStream_t> streams;
+  auto it = streams.find(device);
+  if (it != streams.end()) return it->second;
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  streams.emplace(device, s);
+  return s;
+}
+
 struct StreamHolder {
   cudaStream_t s = nullptr;
   ~StreamHolder() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
@@ -1932,9 +1945,8 @@ int gpba_pose_optimize(const gpba_pose_batch* B, int device, double* cur_pose_ou
   }
   if (device < 0) CK(cudaGetDevice(&device));
   CK(cudaSetDevice(device));
-  StreamHolder sh;   // declared before the buffers: destroyed after they went back to the pool
-  CK(cudaStreamCreateWithFlags(&sh.s, cudaStreamNonBlocking));
-  cudaStream_t st = sh.s;
+  cudaStream_t st = small_call_stream(device);
+  if (!st) { g_err = "cudaStreamCreate failed"; return GPBA_ERR_CUDA; }
   g_alloc_stream = st;
   {
     cudaMemPool_t pool; uint64_t thr = UINT64_MAX;
@@ -1970,7 +1982,10 @@ int gpba_pose_optimize(const gpba_pose_batch* B, int device, double* cur_pose_ou
   CKR(d_level.alloc((size_t)n_obs)); CKR(d_koff.alloc((size_t)n_obs)); CKR(d_chi2.alloc((size_t)n_obs));
   CKR(d_ocp.alloc((size_t)7 * nf)); CKR(d_ocv.alloc((size_t)6 * nf)); CKR(d_opp.alloc((size_t)7 * nf)); CKR(d_opv.alloc((size_t)6 * nf));
   CKR(d_inl.alloc(nf));
-  if (traces) CKR(d_tr.alloc((size_t)nf * GPBA_POSE_ROUNDS));
+  if (traces) {   // rounds that are never run (edges().size() < 10) report an empty trace
+    CKR(d_tr.alloc((size_t)nf * GPBA_POSE_ROUNDS));
+    CK(cudaMemsetAsync(d_tr.p, 0, sizeof(gpba_lm_trace) * (size_t)nf * GPBA_POSE_ROUNDS, st));
+  }
 
   DevView V;
   std::memset(&V, 0, sizeof(V));
@@ -2025,9 +2040,8 @@ int gpba_vel_ransac(const gpba_vel_batch* B, int device, double* vel_out, int32_
   }
   if (device < 0) CK(cudaGetDevice(&device));
   CK(cudaSetDevice(device));
-  StreamHolder sh;   // declared before the buffers: destroyed after they went back to the pool
-  CK(cudaStreamCreateWithFlags(&sh.s, cudaStreamNonBlocking));
-  cudaStream_t st = sh.s;
+  cudaStream_t st = small_call_stream(device);
+  if (!st) { g_err = "cudaStreamCreate failed"; return GPBA_ERR_CUDA; }
   g_alloc_stream = st;
   std::vector<CamConst> cams(B->n_cam);
   for (int c = 0; c < B->n_cam; ++c) {
@@ -2052,7 +2066,7 @@ int gpba_vel_ransac(const gpba_vel_batch* B, int device, double* vel_out, int32_
   CKR(d_samples.upload(B->samples, nh * B->set_size, st));
   CKR(d_vel.alloc(6 * nh)); CKR(d_inl.alloc(nh));
   if (inlier_mask_out) CKR(d_mask.alloc(nh * std::max<size_t>(nm, 1)));
-  if (traces) CKR(d_tr.alloc(nh));
+  if (traces) { CKR(d_tr.alloc(nh)); CK(cudaMemsetAsync(d_tr.p, 0, sizeof(gpba_lm_trace) * nh, st)); }
   VelView V;
   V.n_cam = B->n_cam; V.n_match = B->n_match; V.n_hyp = B->n_hyp; V.set_size = B->set_size; V.iterations = B->iterations;
   V.cam = d_cam.p; V.cam_dt = d_dt.p;

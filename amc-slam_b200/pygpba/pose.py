@@ -63,6 +63,20 @@ class PoseBatch:
                          obs_flags=self.obs_flags[a:b], huber_mono=self.huber_mono, huber_stereo=self.huber_stereo,
                          truth_outlier=None if self.truth_outlier is None else self.truth_outlier[a:b])
 
+    def subset(self, keep):
+        """the batch with only the matches selected by the boolean mask `keep` (frames may end up empty)"""
+        keep = np.asarray(keep, bool)
+        cnt = np.add.reduceat(np.concatenate([keep, [False]]).astype(np.int64), self.obs_begin[:-1].clip(max=len(keep)))
+        cnt[np.diff(self.obs_begin) == 0] = 0
+        return PoseBatch(cam_intr=self.cam_intr, cam_Tbc=self.cam_Tbc, bf=self.bf, qc=self.qc, prev_pose=self.prev_pose,
+                         prev_vel=self.prev_vel, prev_time=self.prev_time, prev_fixed=self.prev_fixed, cur_pose=self.cur_pose,
+                         cur_vel=self.cur_vel, cur_time=self.cur_time, cam_time=self.cam_time,
+                         obs_begin=np.concatenate([[0], np.cumsum(cnt)]), obs_u=self.obs_u[keep], obs_v=self.obs_v[keep],
+                         obs_ur=None if self.obs_ur is None else self.obs_ur[keep], obs_inv_sigma2=self.obs_inv_sigma2[keep],
+                         obs_xw=self.obs_xw[keep], obs_cam=self.obs_cam[keep], obs_flags=self.obs_flags[keep],
+                         huber_mono=self.huber_mono, huber_stereo=self.huber_stereo,
+                         truth_outlier=None if self.truth_outlier is None else self.truth_outlier[keep])
+
     def to_c(self):
         def p(a, t):
             return a.ctypes.data_as(t) if a is not None and a.size else C.cast(None, t)

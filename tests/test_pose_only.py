@@ -142,6 +142,35 @@ def test_pose_optimize_large_batch_is_frame_independent():
     assert (R.outlier[truth] > 0).mean() >= 0.95 and (R.outlier[~truth] > 0).mean() <= 0.10
 
 
+def ragged_batch():
+    """frame 0 without any match (prior and velocity edges only), frame 1 with three, frame 2 complete"""
+    B = PO.make_pose_batch(n_frames=3, n_pt=300, A=2, outliers=0.1, seed=58, fix_prev=True)
+    keep = np.ones(B.n_obs, bool)
+    keep[B.obs_begin[0]:B.obs_begin[1]] = False
+    keep[B.obs_begin[1] + 3:B.obs_begin[2]] = False
+    R = B.subset(keep)
+    assert list(np.diff(R.obs_begin)[:2]) == [0, 3]
+    return R
+
+
+def test_pose_oracle_ragged_and_empty_frames(oracle_mod):
+    B = ragged_batch()
+    R = oracle_mod.pose_optimize(B)
+    assert R.n_inliers[0] == 0 and R.trace(0, 0)["n_iters"] >= 1 and R.trace(0, 1)["n_iters"] == 0   # 3 edges < 10: one round
+    assert np.isfinite(R.cur_pose).all() and np.isfinite(R.cur_vel).all()
+    # with no match the frame is pulled towards the constant-velocity prediction of the fixed previous frame
+    assert np.abs(R.cur_pose[0] - B.cur_pose[0]).max() > 0
+
+
+@pytest.mark.gpu
+def test_pose_optimize_ragged_and_empty_frames(oracle_mod):
+    B = ragged_batch()
+    assert_same(B, PO.pose_optimize(B), oracle_mod.pose_optimize(B))
+    E = B.subset(np.zeros(B.n_obs, bool))            # no match at all in the whole batch
+    assert E.n_obs == 0
+    assert_same(E, PO.pose_optimize(E), oracle_mod.pose_optimize(E))
+
+
 @pytest.mark.gpu
 def test_pose_optimize_rejects_bad_input():
     from pygpba import lib as gl

@@ -101,6 +101,16 @@ def test_vel_ransac_matches_oracle(oracle_mod, kw):
 
 
 @pytest.mark.gpu
+def test_vel_ransac_minimal_and_empty_batches(oracle_mod):
+    B = VR.make_vel_batch(n_match=3, n_hyp=1, outliers=0.0, seed=75)     # the matches ARE the sample
+    a, b = VR.vel_ransac(B), oracle_mod.vel_ransac(B)
+    assert np.abs(a.vel - b.vel).max() <= 1e-7 and np.array_equal(a.mask, b.mask) and a.best.value == b.best.value == 0
+    assert a.inliers[0] == 3
+    E = VR.make_vel_batch(n_match=40, n_hyp=0)
+    assert VR.vel_ransac(E).best.value == -1
+
+
+@pytest.mark.gpu
 def test_vel_ransac_rejects_bad_input():
     from pygpba import lib as gl
     B = VR.make_vel_batch()
