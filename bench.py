@@ -179,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -337,10 +337,22 @@ def run_gpba(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def emit(out):
+    line = (json.dumps(out) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, line)
 
 
 def main():
@@ -355,6 +367,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # stdout carries exactly one JSON line: library banners written to fd 1 while the job runs (e.g. "NCCL version ...")
+    # go to stderr instead
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpba(args)
