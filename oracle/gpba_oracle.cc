@@ -1075,6 +1075,23 @@ int oracle_pose_optimize(const gpba_pose_batch* B, double* cur_pose_out, double*
   }
   return 0;
 }
+// Test hooks of the pose-only restatement: the linear system of frame f at the initial estimate, and the robust chi2 after
+// the tangent step `delta` (n = 12 or 24) -- tests/test_pose_only.py checks b against central differences of chi2.
+int oracle_pose_system(const gpba_pose_batch* B, int f, double* H, double* b, double* chi2) {
+  ora::PoseOnlyFrame F(B, f);
+  const double c = F.compute_errors();
+  F.build_system();
+  if (chi2) *chi2 = c;
+  if (H) std::memcpy(H, F.H.data(), sizeof(double) * F.H.size());
+  if (b) std::memcpy(b, F.b.data(), sizeof(double) * F.b.size());
+  return F.n;
+}
+double oracle_pose_chi2_at(const gpba_pose_batch* B, int f, const double* delta) {
+  ora::PoseOnlyFrame F(B, f);
+  if (!F.fix1) { ora::PoseOnlyFrame::oplus(F.s1, delta); ora::PoseOnlyFrame::oplus(F.s2, delta + 12); }
+  else ora::PoseOnlyFrame::oplus(F.s2, delta);
+  return F.compute_errors();
+}
 // Tracking::MCRansac's hypotheses, one Optimizer::OptimizeVel each (oracle/vel_ransac.h)
 int oracle_vel_ransac(const gpba_vel_batch* B, double* vel_out, int32_t* inliers_out, uint8_t* mask_out, int32_t* best_out, gpba_lm_trace* traces) {
   int best = -1, best_inl = 0;

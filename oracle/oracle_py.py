@@ -272,3 +272,20 @@ def vel_ransac(B):
     R = VelResult(B)
     lib().oracle_vel_ransac(C.byref(c), *R.args())
     return R
+
+
+def pose_system(B, f):
+    """(H, b, chi2) of frame f of a PoseBatch at its initial estimate (oracle/pose_only.h build_system)"""
+    c = B.to_c()
+    H = np.zeros(24 * 24); b = np.zeros(24); chi2 = C.c_double(0)
+    L = lib()
+    n = L.oracle_pose_system(C.byref(c), int(f), H.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.byref(chi2))
+    return H[:n * n].reshape(n, n).copy(), b[:n].copy(), chi2.value
+
+
+def pose_chi2_at(B, f, delta):
+    c = B.to_c()
+    d = np.ascontiguousarray(delta, np.float64)
+    L = lib()
+    L.oracle_pose_chi2_at.restype = C.c_double
+    return L.oracle_pose_chi2_at(C.byref(c), int(f), d.ctypes.data_as(C.c_void_p))

@@ -77,6 +77,30 @@ def test_pose_oracle_recovers_pose_and_rejects_outliers(oracle_mod):
     assert (moved > 1e-4).all()
 
 
+@pytest.mark.parametrize("fix_prev", [True, False])
+def test_pose_oracle_gradient_matches_central_differences(oracle_mod, fix_prev):
+    """Independent pin of every Jacobian on the pose-only path (reprojection edges through the GP interpolation, prior,
+    velocity edges, Huber weights): b = -J^T rho' Omega e against -1/2 of the central-difference gradient of the robust
+    chi2 over the 12 / 24 tangent directions; H must be symmetric positive definite."""
+    B = PO.make_pose_batch(n_frames=2, n_pt=300, A=2, outliers=0.1, seed=57, fix_prev=fix_prev)
+    for f in range(B.n_frames):
+        H, b, chi0 = oracle_mod.pose_system(B, f)
+        n = len(b)
+        assert n == (12 if fix_prev else 24)
+        assert np.abs(H - H.T).max() <= 1e-9 * np.abs(H).max() and np.linalg.eigvalsh(H).min() > 0
+        g = np.zeros(n)
+        for i in range(n):
+            h = 1e-6
+            d = np.zeros(n); d[i] = h
+            g[i] = (oracle_mod.pose_chi2_at(B, f, d) - oracle_mod.pose_chi2_at(B, f, -d)) / (2 * h)
+        assert abs(oracle_mod.pose_chi2_at(B, f, np.zeros(n)) - chi0) <= 1e-9 * chi0
+        # velocity rows: exact derivatives.  Pose rows carry the reference's first-order approximation of
+        # d(J_r^-1(xi) v2)/d(xi) (-0.5 ad(v2), src/G2oTypes.cc:351-357, SURVEY fact 0.7): reproduced, not corrected.
+        vel = (np.arange(n) % 12) >= 6
+        np.testing.assert_allclose((-0.5 * g)[vel], b[vel], rtol=2e-5, atol=1e-6 * np.abs(b).max())
+        np.testing.assert_allclose((-0.5 * g)[~vel], b[~vel], rtol=2e-2, atol=2e-3 * np.abs(b).max())
+
+
 def test_pose_oracle_free_previous_frame_moves(oracle_mod):
     B = PO.make_pose_batch(**CASES["free_prev"])
     R = oracle_mod.pose_optimize(B)
