@@ -32,15 +32,21 @@ def test_struct_layouts_match_header():
     code = textwrap.dedent("""
         #include <stdio.h>
         #include "gpba.h"
-        int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(gpba_problem), sizeof(gpba_lm_trace), sizeof(gpba_lm_params),
-                                sizeof(gpba_thresholds), sizeof(gpba_structure_info)); return 0; }
+        #include "gpba_map.h"
+        int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gpba_problem), sizeof(gpba_lm_trace), sizeof(gpba_lm_params),
+                                sizeof(gpba_thresholds), sizeof(gpba_structure_info), sizeof(gpba_pose_batch), sizeof(gpba_vel_batch),
+                                sizeof(gpba_create_options), sizeof(gpba_map_config)); return 0; }
     """)
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(code)
         subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         sizes = list(map(int, subprocess.check_output([os.path.join(d, "t")]).split()))
-    from pygpba.problem import CProblem, LmTrace, LmParams, Thresholds, StructureInfo
-    assert sizes == [C.sizeof(CProblem), C.sizeof(LmTrace), C.sizeof(LmParams), C.sizeof(Thresholds), C.sizeof(StructureInfo)]
+    from pygpba.problem import CProblem, LmTrace, LmParams, Thresholds, StructureInfo, CreateOptions
+    from pygpba.pose import CPoseBatch
+    from pygpba.velransac import CVelBatch
+    from pygpba.mapmirror import CMapConfig
+    assert sizes == [C.sizeof(CProblem), C.sizeof(LmTrace), C.sizeof(LmParams), C.sizeof(Thresholds), C.sizeof(StructureInfo),
+                     C.sizeof(CPoseBatch), C.sizeof(CVelBatch), C.sizeof(CreateOptions), C.sizeof(CMapConfig)]
 
 
 def test_no_cpu_fallback():
