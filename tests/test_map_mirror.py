@@ -226,6 +226,29 @@ def test_geometric_local_window_has_reference_shape():
     assert np.all((t1 < Q.rec_t[Q.rec_kf1 >= 0]) & (Q.rec_t[Q.rec_kf1 >= 0] < t2))
 
 
+def test_global_window_round_trips_a_full_size_problem():
+    """Size-independent property at C2 size (294 k observations): a problem replayed into the mirror through the mutation
+    hooks and flattened again is the same problem -- same keyframes, points, the same multiset of edges with the same
+    measurements, every GP edge on the (previous keyframe, keyframe, camera, capture time) record it came from."""
+    P, M = geometric_map("c2")
+    W = M.global_window(10)
+    Q = W.problem
+    assert Q.n_kf == P.n_kf and Q.n_pt == P.n_pt and Q.n_obs == P.n_obs and Q.n_rec == P.n_rec
+    assert np.array_equal(Q.kf_pose, P.kf_pose) and np.array_equal(Q.kf_time, P.kf_time) and np.array_equal(Q.pt_xyz, P.pt_xyz)
+    assert np.array_equal(Q.kf_fixed, P.kf_fixed)
+
+    def edge_table(X):
+        k2, k1, c = X.rec_kf2[X.obs_rec], X.rec_kf1[X.obs_rec], X.rec_cam[X.obs_rec]
+        t = X.rec_t[X.obs_rec]
+        tab = np.stack([k2.astype(float), k1.astype(float), c.astype(float), X.obs_pt.astype(float), t, X.obs_u, X.obs_v, X.obs_inv_sigma2,
+                        (X.obs_flags & 1).astype(float)], 1)
+        return tab[np.lexsort((tab[:, 2], tab[:, 0], tab[:, 3]))]
+    assert np.array_equal(edge_table(Q), edge_table(P))
+    assert sorted(zip(Q.prior_kf1, Q.prior_kf2)) == sorted(zip(P.prior_kf1, P.prior_kf2))
+    assert sorted(Q.velp_kf) == sorted(P.velp_kf)
+    assert Q.huber_mono == P.huber_mono and Q.huber_prior == 21.026 and Q.lambda_init == 1e-5   # BundleAdjustment's parameters
+
+
 @pytest.mark.gpu
 def test_flattened_window_optimizes_like_the_oracle(oracle_mod):
     from pygpba import lib as G

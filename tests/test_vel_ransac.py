@@ -111,6 +111,24 @@ def test_vel_ransac_minimal_and_empty_batches(oracle_mod):
 
 
 @pytest.mark.gpu
+def test_vel_ransac_hypotheses_are_independent_at_scale():
+    """Size-independent property on a large batch (2 048 hypotheses x 4 000 matches): a hypothesis does not depend on the
+    batch it travels in (one CTA each, no shared state) -- reversed order and single-hypothesis calls give the same bits."""
+    B = VR.make_vel_batch(n_match=4000, n_hyp=2048, A=4, outliers=0.3, seed=77)
+    R = VR.vel_ransac(B)
+    rev = VR.VelBatch(**{**{k: getattr(B, k) for k in ("cam_intr", "cam_Tbc", "cam_dt", "last_pose", "vel_init", "obs_u", "obs_v", "obs_inv_sigma2",
+                                                     "obs_xw", "obs_cam")}, "samples": B.samples[::-1].copy(), "set_size": B.set_size})
+    Rr = VR.vel_ransac(rev)
+    assert np.array_equal(R.vel, Rr.vel[::-1]) and np.array_equal(R.inliers, Rr.inliers[::-1]) and np.array_equal(R.mask, Rr.mask[::-1])
+    for h in (0, 777, 2047):
+        one = VR.VelBatch(**{**{k: getattr(B, k) for k in ("cam_intr", "cam_Tbc", "cam_dt", "last_pose", "vel_init", "obs_u", "obs_v",
+                                                         "obs_inv_sigma2", "obs_xw", "obs_cam")}, "samples": B.samples[h:h + 1].copy(), "set_size": B.set_size})
+        r1 = VR.vel_ransac(one)
+        assert np.array_equal(r1.vel[0], R.vel[h]) and r1.inliers[0] == R.inliers[h] and np.array_equal(r1.mask[0], R.mask[h])
+    assert R.best.value == int(np.argmax(R.inliers)) and R.inliers.max() >= 0.5 * (~B.truth_outlier).sum()
+
+
+@pytest.mark.gpu
 def test_vel_ransac_rejects_bad_input():
     from pygpba import lib as gl
     B = VR.make_vel_batch()
