@@ -1281,7 +1281,7 @@ int Solver::solve(double lambda, bool* ok) {
   // K4c: rank 0 carries lambda (pose priors / damping must enter the sum exactly once); the GP-edge part of
   // Hpp is a per-rank partial, so every rank adds its own Hpp but only rank 0 adds lambda.
   if (n_hs > 0) {
-    k_schur_expand<<<n_hs, 144, 0, stream>>>(V, rank == 0 ? lambda : 0.0, d_rec.p, d_hpp.p, d_bp.p, d_con_begin.p, d_con.p, d_C.p, d_hs.p, bs);
+    k_schur_expand<<<(n_hs + GPBA_K4C_WARPS - 1) / GPBA_K4C_WARPS, 32 * GPBA_K4C_WARPS, 0, stream>>>(V, rank == 0 ? lambda : 0.0, d_rec.p, d_hpp.p, d_bp.p, d_con_begin.p, d_con.p, d_C.p, d_hs.p, bs);
     CK(cudaGetLastError());
     ++launches;
   }

@@ -643,62 +643,99 @@ __global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __r
   }
 }
 
-// K4c: one CTA (144 threads = one per entry) per Hschur block (i, j), i <= j:
+// K4c: one WARP per Hschur block (i, j), i <= j:
 //   Hs_ij = Hpp_ij (+ lambda on the diagonal) - sum over the block's contributions of M_L^T C^ M_R
 // where L / R are the records (and their keyframe slice) touching pose i / pose j and C^ = C_(r1,r2) or its transpose
-// when the pair is listed the other way round.  Contributions are grouped by L on the host: T = sum_R C^ M_R (6 x 12)
-// is accumulated in registers (the two half-CTAs take alternate contributions; operands come through L1, only ~24
-// distinct M slices exist per block), and M_L^T T is formed once per group.  The block is written once, in a fixed
-// order: no atomics.  On diagonal blocks the diagonal record pairs also give bschur_i = b_p,i - sum M_L^T g'_r.
+// when the pair is listed the other way round.  Contributions are grouped by L on the device (build_structure):
+// T = sum_R C^ M_R (6 x 12) accumulates in DMMA accumulator fragments (m8n8k4: C^ padded to 8 x 8, M_R to 8 x 16), and
+// M_L^T T (12 x 12, four 8 x 8 tiles) is formed once per group with T moved from accumulator to B-operand layout by
+// warp shuffles.  Per contribution a lane issues 6 loads and 4 DMMAs (the scalar version issued 12 loads per thread of a
+// 72-thread half CTA and was L1-bound: ncu l1tex throughput 81 %, 0.83 ms at C4).  The block is written once, in a
+// fixed order: no atomics.  On diagonal blocks the diagonal record pairs also give bschur_i = b_p,i - sum M_L^T g'_r.
 struct HsContrib { int rp; int rL; int rR; int code; };  // code: bit0 slice of L, bit1 slice of R, bit2 transpose C, bit4 g' entry, bits 8.. group size (first entry)
-__global__ void __launch_bounds__(144) k_schur_expand(DevView V, double lambda, const double* __restrict__ rec,
-                                                      const double* __restrict__ hpp, const double* __restrict__ bp,
-                                                      const int* __restrict__ con_begin, const HsContrib* __restrict__ con,
-                                                      const double* __restrict__ C, double* __restrict__ hs,
-                                                      double* __restrict__ bs) {
-  __shared__ double sT[2][72], sB[2][12];
-  const int blk = blockIdx.x, tid = threadIdx.x;
-  const int half = tid / 72, t = tid % 72, m = t / 12, c = t % 12;
-  const int i = tid / 12, j = tid % 12;
+#define GPBA_K4C_WARPS 4
+__global__ void __launch_bounds__(32 * GPBA_K4C_WARPS) k_schur_expand(DevView V, double lambda, const double* __restrict__ rec,
+                                                                     const double* __restrict__ hpp, const double* __restrict__ bp,
+                                                                     const int* __restrict__ con_begin, const HsContrib* __restrict__ con,
+                                                                     const double* __restrict__ C, double* __restrict__ hs,
+                                                                     double* __restrict__ bs) {
+  const int blk = blockIdx.x * GPBA_K4C_WARPS + (threadIdx.x >> 5);
+  if (blk >= V.n_hs) return;
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   const int src = V.hs_from_hpp[blk];
   const int diag = V.hs_diag_pose[blk];
-  double acc = src >= 0 ? hpp[(size_t)src * 144 + tid] : 0.0;
-  if (diag >= 0 && i == j) acc += lambda;
-  double bpart = 0.0;
+  // accumulator tiles of the 12 x 12 block: acc[mt][nt] = rows 8 mt + gid, columns 8 nt + 2 tig + {0, 1}
+  double2 acc[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int r = 8 * mt + gid, c = 8 * nt + 2 * tig;
+      double2 v = make_double2(0.0, 0.0);
+      if (src >= 0 && r < 12 && c < 12) v = *reinterpret_cast<const double2*>(hpp + (size_t)src * 144 + r * 12 + c);
+      if (diag >= 0 && r < 12) { if (r == c) v.x += lambda; if (r == c + 1) v.y += lambda; }
+      acc[mt][nt] = v;
+    }
+  double bpart = 0.0;   // lanes < 12
   const int end = con_begin[blk + 1];
+#pragma unroll 1
   for (int e = con_begin[blk]; e < end;) {
     const HsContrib g = con[e];
     const int gs = g.code >> 8;
-    double tacc = 0.0;
-    for (int q = e + half; q < e + gs; q += 2) {
-      const HsContrib cn = con[q];
+    double2 T[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};   // T[gid][8 nt + 2 tig + {0,1}], rows 6, 7 stay zero
+#pragma unroll 1
+    for (int q = e; q < e + gs; ++q) {
+      const HsContrib cn = q == e ? g : con[q];
       const double* Cp = C + (size_t)cn.rp * GPBA_RP_STRIDE;
-      const double* Mb = rec + (size_t)cn.rR * GPBA_REC_STRIDE + GPBA_REC_M + 12 * ((cn.code >> 1) & 1) + c;
+      const double* Mb = rec + (size_t)cn.rR * GPBA_REC_STRIDE + GPBA_REC_M + 12 * ((cn.code >> 1) & 1);
       const int sm = (cn.code & 4) ? 1 : 8, sn = (cn.code & 4) ? 8 : 1;  // C^[m][n] = C[n][m] when transposed
+      double a[2], b[2][2];
 #pragma unroll
-      for (int n = 0; n < 6; ++n) tacc = fma(Cp[m * sm + n * sn], Mb[n * 24], tacc);
-      if ((cn.code & 16) && t < 12) {
-        const double* Ma = rec + (size_t)cn.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (cn.code & 1) + t;
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = 4 * kk + tig;
+        a[kk] = (gid < 6 && k < 6) ? Cp[gid * sm + k * sn] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) b[kk][nt] = (k < 6 && 8 * nt + gid < 12) ? Mb[k * 24 + 8 * nt + gid] : 0.0;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) dmma884(T[nt].x, T[nt].y, a[kk], b[kk][nt]);
+      if ((cn.code & 16) && lane < 12) {
+        const double* Ma = rec + (size_t)cn.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (cn.code & 1) + lane;
 #pragma unroll
         for (int mm = 0; mm < 6; ++mm) bpart = fma(Ma[mm * 24], Cp[mm * 8 + 6], bpart);
       }
     }
-    sT[half][t] = tacc;
-    __syncthreads();
-    const double* Ma = rec + (size_t)g.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (g.code & 1) + i;
-    double p = 0.0;
+    // acc -= M_L^T T : A[m'][k] = -M_L[k][m'], B[k][n] = T[k][n] (accumulator layout -> B-operand layout by shuffles)
+    const double* Ma = rec + (size_t)g.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (g.code & 1);
 #pragma unroll
-    for (int mm = 0; mm < 6; ++mm) p = fma(Ma[mm * 24], sT[0][mm * 12 + j] + sT[1][mm * 12 + j], p);
-    acc -= p;
-    __syncthreads();
+    for (int kk = 0; kk < 2; ++kk) {
+      const int k = 4 * kk + tig;
+      const int srcl = (k << 2) | (gid >> 1);   // lane holding T[k][8 nt + gid] in its T[nt].x / .y (gid even / odd)
+      double bt[2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const double x = __shfl_sync(0xffffffffu, T[nt].x, srcl), y = __shfl_sync(0xffffffffu, T[nt].y, srcl);
+        bt[nt] = (gid & 1) ? y : x;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const double am = (k < 6 && 8 * mt + gid < 12) ? -Ma[k * 24 + 8 * mt + gid] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt].x, acc[mt][nt].y, am, bt[nt]);
+      }
+    }
     e += gs;
   }
-  hs[(size_t)blk * 144 + tid] = acc;
-  if (diag >= 0) {
-    if (t < 12) sB[half][t] = bpart;
-    __syncthreads();
-    if (tid < 12) bs[(size_t)diag * 12 + tid] = bp[(size_t)diag * 12 + tid] - (sB[0][tid] + sB[1][tid]);
-  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int r = 8 * mt + gid, c = 8 * nt + 2 * tig;
+      if (r < 12 && c < 12) *reinterpret_cast<double2*>(hs + (size_t)blk * 144 + r * 12 + c) = acc[mt][nt];
+    }
+  if (diag >= 0 && lane < 12) bs[(size_t)diag * 12 + lane] = bp[(size_t)diag * 12 + lane] - bpart;
 }
 
 // ------------------------------------------------------------------------------------------------ K6
