@@ -150,18 +150,39 @@ GPBA_D void diag_block_inverse(const double (*S)[GPBA_LD], int b, int lane, doub
 }
 
 // Cholesky of the 48x48 tile in S (lower part; the upper part is never read), GPBA_PANEL_THREADS threads.
-// Six panels of 8 columns.  Warps 0-1 own the 48 rows: every one of their threads factorizes the 8x8 diagonal
-// block of the panel redundantly in registers (LDL^T form: the pivot chain is one reciprocal + one FMA per pivot
-// and needs no communication -- a shared-memory + barrier round trip per pivot cost ~380 cycles) and solves its
-// own row of the panel with it.  Meanwhile warp 3 inverts the previous panel's diagonal block for the blocked
-// triangular solves; the other warps stay off the FP64 pipe.  The trailing tile is then updated with DMMA by all
-// warps.  On exit S = L, D8[b] = (b-th 8x8 diagonal block of L)^-1.
+// Six panels of 8 columns, left-looking: before a panel is factorized its (48 - 8 pb) x 8 column strip receives the
+// updates of all previous panels in one go -- one 8x8 tile per warp, two DMMA accumulator chains of depth pb each
+// (a right-looking trailing update touched m(m+1)/2 tiles per panel in up to three rounds per warp and cost 470-940
+// cycles per panel against ~150-400 here; same flops, fewer and longer chains, one shared-memory round trip per tile).
+// Then warps 0-1, which own the 48 rows, factorize: every one of their threads factorizes the 8x8 diagonal block of the
+// panel redundantly in registers (LDL^T form: the pivot chain is one reciprocal + one FMA per pivot and needs no
+// communication -- a shared-memory + barrier round trip per pivot cost ~380 cycles) and solves its own row of the panel
+// with it.  Meanwhile warp 3 inverts the previous panel's diagonal block for the blocked triangular solves; the other
+// warps stay off the FP64 pipe.  On exit S = L, D8[b] = (b-th 8x8 diagonal block of L)^-1.
 GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], int* fail, int k = -1, int q_ = -1) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int r = tid;
 #pragma unroll 1
   for (int pb = 0; pb < GPBA_NB / 8; ++pb) {
     const int c0 = 8 * pb;
+    if (pb > 0) {
+      // S[8 mt + gid][c0 + 2 tig ..] -= sum over previous columns kc of L[8 mt + gid][kc] L[c0 + n][kc], mt = pb + warp
+      const int mt = pb + warp;
+      if (mt < GPBA_NB / 8) {
+        double* cp = &S[8 * mt + gid][c0 + 2 * tig];
+        double2 c = *reinterpret_cast<double2*>(cp);
+        double e0 = 0.0, e1 = 0.0;   // second accumulator pair: two independent DMMA chains
+#pragma unroll 1
+        for (int kp = 0; kp < pb; ++kp) {
+          dmma884(c.x, c.y, -S[8 * mt + gid][8 * kp + tig], S[c0 + gid][8 * kp + tig]);
+          dmma884(e0, e1, -S[8 * mt + gid][8 * kp + 4 + tig], S[c0 + gid][8 * kp + 4 + tig]);
+        }
+        c.x += e0; c.y += e1;
+        *reinterpret_cast<double2*>(cp) = c;   // columns >= c0: nobody reads them in this phase (operands are columns < c0)
+      }
+      __syncthreads();
+    }
+    GPBA_TICKP(7);
     if (warp < 2) {
       double u[8][8], p[8], is[8];
       const bool mine = r >= c0 && r < GPBA_NB;
@@ -200,36 +221,6 @@ GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], int* fail, int k =
     } else if (warp == 3 && pb > 0) {
       diag_block_inverse(S, pb - 1, lane, D8);
     }
-    __syncthreads();
-    GPBA_TICKP(7);
-    // trailing update S[mt][nt] -= P[mt] P[nt]^T over the tiles pb < nt <= mt < 6: up to three tiles per warp,
-    // interleaved so that the DMMA latencies overlap
-    const int m = GPBA_NB / 8 - 1 - pb, cnt = m * (m + 1) / 2;
-    double2 c[3];
-    double* cp[3];
-    double af[3][2], bf[3][2];
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int t = warp + s * (GPBA_PANEL_THREADS / 32);
-      cp[s] = nullptr;
-      if (t < cnt) {
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= t) ++a;
-        const int mt = pb + 1 + a, nt = pb + 1 + (t - a * (a + 1) / 2);
-        cp[s] = &S[8 * mt + gid][8 * nt + 2 * tig];
-        c[s] = *reinterpret_cast<double2*>(cp[s]);
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) { af[s][kk] = -S[8 * mt + gid][c0 + 4 * kk + tig]; bf[s][kk] = S[8 * nt + gid][c0 + 4 * kk + tig]; }
-      }
-    }
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-      for (int s = 0; s < 3; ++s)
-        if (cp[s]) dmma884(c[s].x, c[s].y, af[s][kk], bf[s][kk]);
-#pragma unroll
-    for (int s = 0; s < 3; ++s)
-      if (cp[s]) *reinterpret_cast<double2*>(cp[s]) = c[s];
     __syncthreads();
     GPBA_TICKP(8);
   }
