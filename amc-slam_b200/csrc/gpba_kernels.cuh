@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(GPBA_K2_THREADS) k_lin_points(DevView V, const
 // One warp per record segment (observations grouped by record).  Accumulates the 6x6 S_r = sum w J1^T J1
 // (upper, 21 values) and g_r = -sum w J1^T e in registers, warp-shuffle reduces, one atomicAdd per value.
 template <bool STEREO>
-__global__ void __launch_bounds__(128) k_lin_records(DevView V, const double* __restrict__ rec,
+__global__ void __launch_bounds__(128, 3) k_lin_records(DevView V, const double* __restrict__ rec,
                                                      const double* __restrict__ pt, double* __restrict__ recS,
                                                      const double* __restrict__ r_u, const double* __restrict__ r_v,
                                                      const double* __restrict__ r_ur, const double* __restrict__ r_w,
