@@ -69,3 +69,34 @@ def test_product_does_not_reference_oracle():
                 if re.search(r"oracle_py|libgpba_oracle|oracle/|numpy_mirror", txt):
                     bad.append(os.path.join(base, f))
     assert not bad, bad
+
+
+def _build_c_example(tmpdir):
+    import subprocess
+    exe = os.path.join(tmpdir, "gpba_c_example")
+    libdir = os.path.join(ROOT, "amc-slam_b200")
+    gl.lib()   # make sure libgpba.so exists
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "gpba_c_example.c"), "-L", libdir, "-lgpba", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe])
+    return exe
+
+
+def test_c_example_links_and_fails_loudly_without_a_device(tmp_path):
+    """The boundary is usable from plain C (no torch, no Python): examples/gpba_c_example.c compiles with -Wall -Werror
+    against include/gpba.h, links libgpba.so, and on a box without a GPU reports GPBA_ERR_NO_DEVICE (exit code 3)."""
+    import subprocess
+    import torch
+    exe = _build_c_example(str(tmp_path))
+    if torch.cuda.is_available():
+        pytest.skip("device present: covered by the gpu test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_example_optimizes_on_the_gpu(tmp_path):
+    import subprocess
+    exe = _build_c_example(str(tmp_path))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "LM iterations" in r.stdout
