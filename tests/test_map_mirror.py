@@ -144,6 +144,19 @@ def test_local_windows_match_restatement(flat, seed):
                 W.close()
 
 
+@pytest.mark.parametrize("n_kf", [1, 2, 3, 4])
+def test_tiny_maps_match_restatement(flat, n_kf):
+    """Degenerate windows: Nd = min(KeyFramesInMap - 2, 10) <= 1, a first keyframe without predecessor that becomes the
+    fixed one (Optimizer.cc:776-782), no covisible keyframe, points seen once."""
+    M, ids, pids, rng = random_map(flat, 20 + n_kf, n_kf=n_kf, n_pt=30)
+    for kid in ids:
+        for large in (False, True):
+            W, R = M.a.local_window(kid, large, []), M.b.local_window(kid, large, [])
+            assert_same_window(W, R)
+            assert (W.kf_role == 2).sum() >= 1
+    assert_same_window(M.a.global_window(ids[0]), M.b.global_window(ids[0]))
+
+
 @pytest.mark.parametrize("seed", [4, 5])
 def test_global_window_matches_restatement(flat, seed):
     M, ids, pids, rng = random_map(flat, seed)
