@@ -388,6 +388,18 @@ int gpba_map_add_observation(gpba_map* m, int64_t kf, int32_t cam, int64_t pt, d
   return GPBA_OK;
 }
 
+int gpba_map_add_observations(gpba_map* m, int64_t n, const int64_t* kf, const int32_t* cam, const int64_t* pt, const double* u,
+                              const double* v, const double* ur, const double* w, const uint8_t* close_flag, int64_t* n_done) {
+  if (n_done) *n_done = 0;
+  if (!m || n < 0 || (n > 0 && (!kf || !cam || !pt || !u || !v || !w))) return fail("null argument");
+  for (int64_t i = 0; i < n; ++i) {
+    const int rc = gpba_map_add_observation(m, kf[i], cam[i], pt[i], u[i], v[i], ur ? ur[i] : -1.0, w[i], close_flag ? close_flag[i] : 0);
+    if (rc != GPBA_OK) return rc;
+    if (n_done) *n_done = i + 1;
+  }
+  return GPBA_OK;
+}
+
 int gpba_map_erase_observation(gpba_map* m, int64_t kf, int32_t cam, int64_t pt) {
   if (!m) return fail("null argument");
   auto ip = m->pt_of.find(pt);

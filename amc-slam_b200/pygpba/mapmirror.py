@@ -10,7 +10,7 @@ from .problem import CProblem, Problem
 SYMBOLS = [
     "gpba_map_last_error", "gpba_map_create", "gpba_map_destroy", "gpba_map_add_keyframe", "gpba_map_set_keyframe_state",
     "gpba_map_set_keyframe_bad", "gpba_map_add_point", "gpba_map_set_point", "gpba_map_set_point_bad",
-    "gpba_map_add_observation", "gpba_map_erase_observation", "gpba_map_stats", "gpba_map_local_window",
+    "gpba_map_add_observation", "gpba_map_add_observations", "gpba_map_erase_observation", "gpba_map_stats", "gpba_map_local_window",
     "gpba_map_global_window", "gpba_window_destroy", "gpba_window_problem", "gpba_window_iterations", "gpba_window_ids",
     "gpba_window_cam_obs", "gpba_window_apply",
 ]
@@ -41,6 +41,7 @@ def _lib():
         L.gpba_map_set_point.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.gpba_map_set_point_bad.argtypes = [C.c_void_p, C.c_int64]
         L.gpba_map_add_observation.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32]
+        L.gpba_map_add_observations.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 9
         L.gpba_map_erase_observation.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64]
         L.gpba_map_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.gpba_map_local_window.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
@@ -144,6 +145,17 @@ class MapMirror:
 
     def add_observation(self, kf, cam, pt, u, v, ur, inv_sigma2, close):
         self._ck(self.L.gpba_map_add_observation(self.h, int(kf), int(cam), int(pt), float(u), float(v), float(ur), float(inv_sigma2), int(close)))
+
+    def add_observations(self, kf, cam, pt, u, v, ur, inv_sigma2, close):
+        """bulk form of add_observation (array order); ur / close may be None"""
+        kf = np.ascontiguousarray(kf, np.int64); cam = np.ascontiguousarray(cam, np.int32); pt = np.ascontiguousarray(pt, np.int64)
+        u = np.ascontiguousarray(u, np.float64); v = np.ascontiguousarray(v, np.float64); w = np.ascontiguousarray(inv_sigma2, np.float64)
+        ur = None if ur is None else np.ascontiguousarray(ur, np.float64)
+        cl = None if close is None else np.ascontiguousarray(close, np.uint8)
+        assert len(cam) == len(pt) == len(u) == len(v) == len(w) == len(kf)
+        done = C.c_int64(0)
+        self._ck(self.L.gpba_map_add_observations(self.h, len(kf), _p(kf), _p(cam), _p(pt), _p(u), _p(v), _p(ur), _p(w), _p(cl), C.byref(done)))
+        return int(done.value)
 
     def erase_observation(self, kf, cam, pt):
         self._ck(self.L.gpba_map_erase_observation(self.h, int(kf), int(cam), int(pt)))

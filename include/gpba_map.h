@@ -62,6 +62,11 @@ int gpba_map_set_point_bad(gpba_map* m, int64_t id);
  * A second observation of the same (kf, cam, pt) replaces the first (the reference's vector<int> slot is overwritten). */
 int gpba_map_add_observation(gpba_map* m, int64_t kf, int32_t cam, int64_t pt, double u, double v, double ur,
                              double inv_sigma2, int32_t close_flag);
+/* n calls of gpba_map_add_observation in array order (initial fill of the mirror from an existing map, Atlas load).
+ * ur / close_flag may be NULL (monocular / not close).  Stops at the first invalid entry and reports its index. */
+int gpba_map_add_observations(gpba_map* m, int64_t n, const int64_t* kf, const int32_t* cam, const int64_t* pt,
+                              const double* u, const double* v, const double* ur, const double* inv_sigma2,
+                              const uint8_t* close_flag, int64_t* n_done);
 /* MapPoint::EraseObservation(pKF, cam) + MultiKeyFrame::EraseMapPointMatch */
 int gpba_map_erase_observation(gpba_map* m, int64_t kf, int32_t cam, int64_t pt);
 /* counts: [0] keyframes (not bad) [1] points (not bad) [2] observations */

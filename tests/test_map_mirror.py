@@ -228,6 +228,27 @@ def geometric_map(name="c1", **kw):
     return P, M
 
 
+def test_bulk_observation_load_equals_one_by_one():
+    P, A = geometric_map("c1", n_kf=12, n_pt=400)
+    B = MM.MapMirror(P.cam_intr, P.cam_Tbc, P.bf, P.qc)
+    cam_time = np.tile(P.kf_time[:, None], (1, P.n_cam)); cam_time[P.rec_kf2, P.rec_cam] = P.rec_t
+    for k in range(P.n_kf):
+        B.add_keyframe(10 + 2 * k, 10 + 2 * (k - 1) if k else -1, P.kf_pose[k], P.kf_vel[k], P.kf_time[k], cam_time[k])
+    for j in range(P.n_pt):
+        B.add_point(1000 + j, P.pt_xyz[j])
+    order = np.argsort(P.rec_kf2[P.obs_rec], kind="stable")
+    r = P.obs_rec[order]
+    n = B.add_observations(10 + 2 * P.rec_kf2[r], P.rec_cam[r], 1000 + P.obs_pt[order], P.obs_u[order], P.obs_v[order], None,
+                           P.obs_inv_sigma2[order], P.obs_flags[order] & 1)
+    assert n == P.n_obs and A.stats() == B.stats()
+    Wa, Wb = A.local_window(10 + 2 * 11), B.local_window(10 + 2 * 11)
+    for f in ARRAYS:
+        assert np.array_equal(getattr(Wa.problem, f), getattr(Wb.problem, f)), f
+    from pygpba import lib as gl
+    with pytest.raises(gl.GpbaError):
+        B.add_observations([10, 99999], [0, 0], [1000, 1000], [1.0, 1.0], [1.0, 1.0], None, [1.0, 1.0], None)   # unknown keyframe in entry 1
+
+
 def test_geometric_local_window_has_reference_shape():
     P, M = geometric_map("c1", n_kf=16, n_pt=600)
     W = M.local_window(10 + 2 * 15)
