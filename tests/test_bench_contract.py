@@ -29,7 +29,7 @@ def test_product_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():
         pytest.skip("device present")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu", "--workload", "c1"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu", "--workload", "c2"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert r.returncode != 0
+    assert r.returncode != 0 and "usage:" not in r.stderr          # a real refusal, not an argument error
     assert not [l for l in r.stdout.splitlines() if l.strip().startswith("{")]    # no number without a device
