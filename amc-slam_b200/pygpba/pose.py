@@ -96,6 +96,24 @@ class PoseBatch:
         return int(sum(getattr(self, f).nbytes for f in self.FIELDS if getattr(self, f) is not None))
 
 
+def shard_frames(B, rank, world):
+    """Multi-GPU use of the pose-only path: frames are independent, so a batch shards without any data-path collective
+    ("replicas" in DESIGN terms).  Contiguous frame ranges balanced by match count; returns (sub-batch, frame indices)."""
+    cnt = np.concatenate([[0], np.cumsum(np.diff(B.obs_begin))]).astype(np.int64)
+    total = int(cnt[-1])
+    cuts = [0] + [int(np.searchsorted(cnt, total * r // world, side="left")) for r in range(1, world)] + [B.n_frames]
+    cuts = np.maximum.accumulate(np.clip(cuts, 0, B.n_frames))
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    a, b = int(B.obs_begin[lo]), int(B.obs_begin[hi])
+    sub = PoseBatch(cam_intr=B.cam_intr, cam_Tbc=B.cam_Tbc, bf=B.bf, qc=B.qc, prev_pose=B.prev_pose[lo:hi], prev_vel=B.prev_vel[lo:hi],
+                    prev_time=B.prev_time[lo:hi], prev_fixed=B.prev_fixed[lo:hi], cur_pose=B.cur_pose[lo:hi], cur_vel=B.cur_vel[lo:hi],
+                    cur_time=B.cur_time[lo:hi], cam_time=B.cam_time[lo:hi], obs_begin=B.obs_begin[lo:hi + 1] - a, obs_u=B.obs_u[a:b],
+                    obs_v=B.obs_v[a:b], obs_ur=None if B.obs_ur is None else B.obs_ur[a:b], obs_inv_sigma2=B.obs_inv_sigma2[a:b],
+                    obs_xw=B.obs_xw[a:b], obs_cam=B.obs_cam[a:b], obs_flags=B.obs_flags[a:b], huber_mono=B.huber_mono,
+                    huber_stereo=B.huber_stereo, truth_outlier=None if B.truth_outlier is None else B.truth_outlier[a:b])
+    return sub, np.arange(lo, hi)
+
+
 def make_pose_batch(n_frames=4, n_pt=600, A=2, outliers=0.15, seed=51, fix_prev=True, stereo_fraction=0.0, obs_per_pt=None):
     """Frames cut out of a seeded synthetic map (synth.make_problem): frame f = keyframe f+1 of the map with keyframe f as
     the previous frame; its matches are the map's observations of that keyframe against the (noisy, then frozen) map

@@ -107,3 +107,47 @@ def test_shards_are_balanced_and_disjoint():
         assert np.all(np.sum(masks, axis=0) <= 1)
         obs = np.array([m[P.obs_pt].sum() for m in masks])
         assert obs.sum() == P.n_obs and obs.max() <= 1.25 * obs.mean() + 64
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The frame-rate paths shard without a data-path collective: frames (pose-only) and hypotheses (velocity RANSAC) are
+# independent.  world_size 2 over gloo: every rank runs the oracle on its contiguous share of the frames, the results are
+# gathered, and the union must be the unsharded result bit for bit.
+def _pose_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_py
+    from pygpba import pose as PO
+    B = PO.make_pose_batch(n_frames=7, n_pt=500, A=2, outliers=0.1, seed=63, fix_prev=True)
+    sub, frames = PO.shard_frames(B, rank, world)
+    R = oracle_py.pose_optimize(sub)
+    pose = torch.zeros(B.n_frames, 7, dtype=torch.float64); inl = torch.zeros(B.n_frames, dtype=torch.int64)
+    pose[torch.from_numpy(frames)] = torch.from_numpy(R.cur_pose)
+    inl[torch.from_numpy(frames)] = torch.from_numpy(R.n_inliers.astype(np.int64))
+    covered = torch.zeros(B.n_frames, dtype=torch.int64); covered[torch.from_numpy(frames)] = 1
+    for t in (pose, inl, covered):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)   # disjoint shards: the sum is the gather
+    if rank == 0:
+        full = oracle_py.pose_optimize(B)
+        out.put((bool(np.array_equal(pose.numpy(), full.cur_pose)), bool(np.array_equal(inl.numpy(), full.n_inliers)),
+                 covered.tolist(), [int(x) for x in np.diff(sub.obs_begin)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pose_frames_shard_without_collectives(oracle_mod):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_pose_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same_pose, same_inl, covered, _ = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same_pose and same_inl
+    assert covered == [1] * 7          # every frame on exactly one rank
