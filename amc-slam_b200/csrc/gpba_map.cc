@@ -42,6 +42,8 @@ struct Kf {
   int n_dead = 0;
   int64_t local_stamp = -1, fixed_stamp = -1;
   int widx = -1;          // index in the window being built
+  std::unordered_map<int, int> conn;            // mConnectedKeyFrameWeights: keyframe slot -> shared map points
+  std::vector<std::pair<int, int> > ordered;    // mvpOrderedConnectedKeyFrames / mvOrderedWeights: (slot, weight)
 };
 struct Pt {
   int64_t id = 0;
@@ -85,6 +87,22 @@ struct gpba_map {
     }
     Kf& k = kfs[o.kf];
     if (++k.n_dead > 64 && (size_t)k.n_dead * 2 > k.obs.size() && may_compact) compact(k);
+  }
+  // MultiKeyFrame::UpdateBestCovisibles (KeyFrame.cc:265-287): all connected, not bad, by (weight, id) descending
+  void update_best_covisibles(Kf& k) {
+    std::vector<std::pair<std::pair<int, int64_t>, int> > v;
+    v.reserve(k.conn.size());
+    for (const auto& c : k.conn) if (!kfs[c.first].bad) v.push_back({{c.second, kfs[c.first].id}, c.first});
+    std::sort(v.begin(), v.end());
+    k.ordered.clear();
+    for (size_t i = v.size(); i-- > 0;) k.ordered.push_back({v[i].second, v[i].first.first});
+  }
+  void add_connection(int to, int from, int weight) {   // kfs[to].AddConnection(kfs[from], weight) (:250-263)
+    Kf& k = kfs[to];
+    auto it = k.conn.find(from);
+    if (it != k.conn.end() && it->second == weight) return;
+    k.conn[from] = weight;
+    update_best_covisibles(k);
   }
   void compact(Kf& k) {
     size_t w = 0;
@@ -326,6 +344,12 @@ int gpba_map_set_keyframe_bad(gpba_map* m, int64_t id) {
     m->kfs[k.prev].next = k.next;
     k.next = -1; k.prev = -1;
   }
+  const int self = it->second;
+  for (const auto& c : k.conn) {                                        // EraseConnection on every neighbour (:663-666, :763-777)
+    Kf& o = m->kfs[c.first];
+    if (o.conn.erase(self)) m->update_best_covisibles(o);
+  }
+  k.conn.clear(); k.ordered.clear();
   for (int s : k.obs) if (m->obs[s].alive) m->kill_obs(s, true, false);   // k.obs is being walked: compact afterwards
   m->compact(k);
   k.bad = true;
@@ -410,6 +434,59 @@ int gpba_map_erase_observation(gpba_map* m, int64_t kf, int32_t cam, int64_t pt)
   return GPBA_OK;
 }
 
+int gpba_map_update_connections(gpba_map* m, int64_t kf_id) {
+  if (!m) return fail("null argument");
+  auto it = m->kf_of.find(kf_id);
+  if (it == m->kf_of.end() || m->kfs[it->second].bad) return fail("keyframe unknown");
+  const int self = it->second;
+  std::unordered_map<int, int> counter;                                 // KFcounter (:457-487)
+  for (int s : m->kfs[self].obs) {
+    const Obs& o = m->obs[s];
+    if (!o.alive) continue;
+    const Pt& p = m->pts[o.pt];
+    if (p.bad) continue;
+    int last = -1;
+    for (const PObs& q : p.obs) {                                       // one count per observing keyframe
+      if (q.kf == last) continue;
+      last = q.kf;
+      if (q.kf == self || m->kfs[q.kf].bad) continue;
+      ++counter[q.kf];
+    }
+  }
+  if (counter.empty()) return GPBA_OK;                                  // :490-491
+  std::vector<std::pair<int64_t, int> > byid;                           // the reference walks a pointer-keyed map: by id here
+  for (const auto& c : counter) byid.push_back({m->kfs[c.first].id, c.first});
+  std::sort(byid.begin(), byid.end());
+  const int th = 15;
+  int nmax = 0, kmax = -1;
+  std::vector<std::pair<std::pair<int, int64_t>, int> > pairs;
+  for (const auto& e : byid) {
+    const int w = counter[e.second];
+    if (w > nmax) { nmax = w; kmax = e.second; }
+    if (w >= th) { pairs.push_back({{w, e.first}, e.second}); m->add_connection(e.second, self, w); }
+  }
+  if (pairs.empty()) { pairs.push_back({{nmax, m->kfs[kmax].id}, kmax}); m->add_connection(kmax, self, nmax); }
+  std::sort(pairs.begin(), pairs.end());
+  Kf& k = m->kfs[self];
+  k.conn = std::move(counter);                                          // ALL counted keyframes (:537)
+  k.ordered.clear();
+  for (size_t i = pairs.size(); i-- > 0;) k.ordered.push_back({pairs[i].second, pairs[i].first.first});
+  return GPBA_OK;
+}
+
+int gpba_map_covisibles(const gpba_map* m, int64_t kf_id, int64_t* ids, int32_t* weights, int32_t capacity, int32_t* n_out) {
+  if (!m || !n_out) return fail("null argument");
+  auto it = m->kf_of.find(kf_id);
+  if (it == m->kf_of.end()) return fail("keyframe unknown");
+  const Kf& k = m->kfs[it->second];
+  *n_out = (int32_t)k.ordered.size();
+  for (int32_t i = 0; i < capacity && i < *n_out; ++i) {
+    if (ids) ids[i] = m->kfs[k.ordered[i].first].id;
+    if (weights) weights[i] = k.ordered[i].second;
+  }
+  return GPBA_OK;
+}
+
 int gpba_map_stats(const gpba_map* m, int64_t out[3]) {
   if (!m || !out) return fail("null argument");
   out[0] = m->n_kf_alive; out[1] = m->n_pt_alive; out[2] = m->n_obs_alive;
@@ -463,6 +540,11 @@ int gpba_map_local_window(gpba_map* m, int64_t kf_id, int32_t large, const int64
       fixed.push_back(last);
       opt.pop_back();
     }
+  }
+  std::vector<int64_t> own_cov;
+  if (n_cov < 0) {                                                      // pKF->GetVectorCovisibleKeyFrames() from the mirror
+    for (const auto& c : m->kfs[it0->second].ordered) own_cov.push_back(m->kfs[c.first].id);
+    covisible = own_cov.data(); n_cov = (int32_t)own_cov.size();
   }
   for (int i = 0; i < n_cov; ++i) {                                     // :784-812 (maxCovKF = 0: one keyframe at most)
     if (!vis.empty()) break;

@@ -10,7 +10,7 @@ from .problem import CProblem, Problem
 SYMBOLS = [
     "gpba_map_last_error", "gpba_map_create", "gpba_map_destroy", "gpba_map_add_keyframe", "gpba_map_set_keyframe_state",
     "gpba_map_set_keyframe_bad", "gpba_map_add_point", "gpba_map_set_point", "gpba_map_set_point_bad",
-    "gpba_map_add_observation", "gpba_map_add_observations", "gpba_map_erase_observation", "gpba_map_stats", "gpba_map_local_window",
+    "gpba_map_add_observation", "gpba_map_add_observations", "gpba_map_erase_observation", "gpba_map_update_connections", "gpba_map_covisibles", "gpba_map_stats", "gpba_map_local_window",
     "gpba_map_global_window", "gpba_window_destroy", "gpba_window_problem", "gpba_window_iterations", "gpba_window_ids",
     "gpba_window_cam_obs", "gpba_window_apply",
 ]
@@ -44,6 +44,8 @@ def _lib():
         L.gpba_map_add_observations.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 9
         L.gpba_map_erase_observation.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64]
         L.gpba_map_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.gpba_map_update_connections.argtypes = [C.c_void_p, C.c_int64]
+        L.gpba_map_covisibles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.gpba_map_local_window.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.gpba_map_global_window.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
         L.gpba_window_ids.argtypes = [C.c_void_p] + [C.c_void_p] * 6
@@ -160,14 +162,29 @@ class MapMirror:
     def erase_observation(self, kf, cam, pt):
         self._ck(self.L.gpba_map_erase_observation(self.h, int(kf), int(cam), int(pt)))
 
+    def update_connections(self, kf):
+        self._ck(self.L.gpba_map_update_connections(self.h, int(kf)))
+
+    def covisibles(self, kf):
+        """(ids, weights) of MultiKeyFrame::GetVectorCovisibleKeyFrames as the mirror maintains it"""
+        n = C.c_int32(0)
+        self._ck(self.L.gpba_map_covisibles(self.h, int(kf), None, None, 0, C.byref(n)))
+        ids = np.zeros(max(n.value, 1), np.int64); w = np.zeros(max(n.value, 1), np.int32)
+        self._ck(self.L.gpba_map_covisibles(self.h, int(kf), _p(ids), _p(w), n.value, C.byref(n)))
+        return ids[:n.value].copy(), w[:n.value].copy()
+
     def stats(self):
         a = np.zeros(3, np.int64)
         self._ck(self.L.gpba_map_stats(self.h, _p(a)))
         return dict(keyframes=int(a[0]), points=int(a[1]), observations=int(a[2]))
 
     def local_window(self, kf_id, large=False, covisible=()):
-        cov = np.ascontiguousarray(covisible, np.int64)
+        """covisible=None: use the mirror's own covisibility list (update_connections)"""
         h = C.c_void_p()
+        if covisible is None:
+            self._ck(self.L.gpba_map_local_window(self.h, int(kf_id), int(bool(large)), None, -1, C.byref(h)))
+            return Window(self.L, h, self.n_cam)
+        cov = np.ascontiguousarray(covisible, np.int64)
         self._ck(self.L.gpba_map_local_window(self.h, int(kf_id), int(bool(large)), _p(cov), len(cov), C.byref(h)))
         return Window(self.L, h, self.n_cam)
 

@@ -69,13 +69,24 @@ int gpba_map_add_observations(gpba_map* m, int64_t n, const int64_t* kf, const i
                               const uint8_t* close_flag, int64_t* n_done);
 /* MapPoint::EraseObservation(pKF, cam) + MultiKeyFrame::EraseMapPointMatch */
 int gpba_map_erase_observation(gpba_map* m, int64_t kf, int32_t cam, int64_t pt);
+/* MultiKeyFrame::UpdateConnections (src/KeyFrame.cc:455-550) at the places the reference calls it (LocalMapping.cc:261,694,
+ * LoopClosing.cc:840,952,995, Tracking.cc:1613-1614): counts, for every other keyframe, the map points it shares with
+ * `kf` (one count per keypoint of `kf`, so a point matched in two cameras counts twice, as in the reference); keyframes
+ * with >= 15 shared points (or the best one if none reaches 15) become the ordered covisible list of `kf` and get the
+ * symmetric AddConnection + UpdateBestCovisibles (:250-287) -- including the reference's quirk that a list rebuilt by
+ * UpdateBestCovisibles holds ALL counted keyframes, not only those above the threshold.  gpba_map_set_keyframe_bad erases
+ * the connections like SetBadFlag does (:663-666, EraseConnection :763-777).  Ties are ordered by keyframe id where the
+ * reference orders them by pointer. */
+int gpba_map_update_connections(gpba_map* m, int64_t kf);
+/* MultiKeyFrame::GetVectorCovisibleKeyFrames: ids in decreasing weight; *n_out = list length (may exceed capacity). */
+int gpba_map_covisibles(const gpba_map* m, int64_t kf, int64_t* ids, int32_t* weights, int32_t capacity, int32_t* n_out);
 /* counts: [0] keyframes (not bad) [1] points (not bad) [2] observations */
 int gpba_map_stats(const gpba_map* m, int64_t out[3]);
 
 /* ---- flattening ----------------------------------------------------------------------------------------------- */
 /* Optimizer::LocalGPBA(pKF, ..., bLarge, ...) window selection and graph construction (src/Optimizer.cc:718-1211).
- * covisible = pKF->GetVectorCovisibleKeyFrames() ids in that order (the mirror does not keep the covisibility graph;
- * at most one of them joins the window, maxCovKF = 0 at :784). */
+ * covisible = pKF->GetVectorCovisibleKeyFrames() ids in that order; n_covisible < 0: use the mirror's own covisibility
+ * list of kf_id (gpba_map_update_connections).  At most one of them joins the window (maxCovKF = 0 at :784). */
 int gpba_map_local_window(gpba_map* m, int64_t kf_id, int32_t large, const int64_t* covisible, int32_t n_covisible,
                           gpba_window** out);
 /* Optimizer::BundleAdjustment(vpKFs = all keyframes, vpMP = all points, ...) graph construction (:85-315);

@@ -20,6 +20,29 @@ class KF:
         self.bad = False
         self.matches = {}            # (cam, point id) -> MapPoint, insertion order = GetMapPointMatches order
         self.mnBALocalForKF = self.mnBAFixedForKF = -1
+        self.mConnectedKeyFrameWeights = {}      # KF -> weight
+        self.mvpOrderedConnectedKeyFrames, self.mvOrderedWeights = [], []
+
+    # src/KeyFrame.cc:250-287
+    def AddConnection(self, pKF, weight):
+        if pKF not in self.mConnectedKeyFrameWeights or self.mConnectedKeyFrameWeights[pKF] != weight:
+            self.mConnectedKeyFrameWeights[pKF] = weight
+        else:
+            return
+        self.UpdateBestCovisibles()
+
+    def UpdateBestCovisibles(self):
+        vPairs = sorted(((w, k.mnId, k) for k, w in self.mConnectedKeyFrameWeights.items()), key=lambda t: (t[0], t[1]))
+        lKFs, lWs = [], []
+        for w, _, k in vPairs:
+            if not k.bad:
+                lKFs.insert(0, k); lWs.insert(0, w)
+        self.mvpOrderedConnectedKeyFrames, self.mvOrderedWeights = lKFs, lWs
+
+    def EraseConnection(self, pKF):
+        if pKF in self.mConnectedKeyFrameWeights:
+            del self.mConnectedKeyFrameWeights[pKF]
+            self.UpdateBestCovisibles()
 
 
 class MP:
@@ -57,6 +80,9 @@ class RefMap:
             k.mNextKF.mPrevKF = k.mPrevKF
             k.mPrevKF.mNextKF = k.mNextKF
             k.mNextKF = k.mPrevKF = None
+        for other in list(k.mConnectedKeyFrameWeights):       # SetBadFlag (KeyFrame.cc:663-666)
+            other.EraseConnection(k)
+        k.mConnectedKeyFrameWeights.clear(); k.mvpOrderedConnectedKeyFrames = []; k.mvOrderedWeights = []
         for (cam, pid), p in list(k.matches.items()):
             del p.obs[id][cam]
             if not p.obs[id]:
@@ -92,6 +118,40 @@ class RefMap:
         if not p.obs[kf]:
             del p.obs[kf]
         del self.kfs[kf].matches[(cam, pt)]
+
+    # MultiKeyFrame::UpdateConnections (src/KeyFrame.cc:455-550); the pointer-keyed maps are walked by keyframe id here
+    def update_connections(self, kf_id):
+        this = self.kfs[kf_id]
+        KFcounter = {}
+        for p in this.matches.values():                      # vpMP = mvpMapPoints: one entry per keypoint
+            if p.bad:
+                continue
+            for oid in p.obs:                                # GetObservations(): one entry per keyframe
+                o = self.kfs[oid]
+                if o.mnId == this.mnId or o.bad:
+                    continue
+                KFcounter[o] = KFcounter.get(o, 0) + 1
+        if not KFcounter:
+            return
+        nmax, pKFmax, th, vPairs = 0, None, 15, []
+        for o in sorted(KFcounter, key=lambda k: k.mnId):
+            w = KFcounter[o]
+            if w > nmax:
+                nmax, pKFmax = w, o
+            if w >= th:
+                vPairs.append((w, o.mnId, o))
+                o.AddConnection(this, w)
+        if not vPairs:
+            vPairs.append((nmax, pKFmax.mnId, pKFmax))
+            pKFmax.AddConnection(this, nmax)
+        vPairs.sort(key=lambda t: (t[0], t[1]))
+        this.mConnectedKeyFrameWeights = dict(KFcounter)
+        this.mvpOrderedConnectedKeyFrames = [t[2] for t in reversed(vPairs)]
+        this.mvOrderedWeights = [t[0] for t in reversed(vPairs)]
+
+    def covisibles(self, kf_id):
+        k = self.kfs[kf_id]
+        return [o.mnId for o in k.mvpOrderedConnectedKeyFrames], list(k.mvOrderedWeights)
 
     def n_alive(self):
         return sum(1 for k in self.kfs.values() if not k.bad)
@@ -150,6 +210,8 @@ class RefMap:
             huber_prior=huber_prior, lambda_init=lambda_init)
 
     def local_window(self, kf_id, large=False, covisible=()):
+        if covisible is None:
+            covisible = [o.mnId for o in self.kfs[kf_id].mvpOrderedConnectedKeyFrames]
         self.stamp += 1
         S = self.stamp
         pKF = self.kfs[kf_id]

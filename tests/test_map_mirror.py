@@ -144,6 +144,26 @@ def test_local_windows_match_restatement(flat, seed):
                 W.close()
 
 
+@pytest.mark.parametrize("seed", [11, 12])
+def test_covisibility_graph_matches_restatement(flat, seed):
+    """gpba_map_update_connections against the restatement of MultiKeyFrame::UpdateConnections / AddConnection /
+    UpdateBestCovisibles / EraseConnection, interleaved with keyframe culling, point removal and observation changes; then
+    local windows that take the covisible keyframe from the mirror's own list."""
+    M, ids, pids, rng = random_map(flat, seed, n_kf=30, n_pt=900)
+    alive = list(ids)
+    for rnd in range(4):
+        for kid in rng.permutation(alive)[:12]:
+            M.update_connections(kid)
+        for kid in alive:
+            ia, wa = M.a.covisibles(kid)
+            ib, wb = M.b.covisibles(kid)
+            assert list(ia) == ib and list(wa) == wb, (rnd, kid)
+        assert any(len(M.a.covisibles(k)[0]) > 1 for k in alive)
+        for kid in (alive[-1], alive[len(alive) // 2]):
+            assert_same_window(M.a.local_window(kid, False, None), M.b.local_window(kid, False, None))
+        alive = mutate(M, alive, pids, rng, n_ops=150)
+
+
 @pytest.mark.parametrize("n_kf", [1, 2, 3, 4])
 def test_tiny_maps_match_restatement(flat, n_kf):
     """Degenerate windows: Nd = min(KeyFramesInMap - 2, 10) <= 1, a first keyframe without predecessor that becomes the
