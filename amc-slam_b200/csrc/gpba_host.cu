@@ -83,6 +83,7 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, unsigned char[128], int) = nullptr;  // ncclUniqueId passed by value (128 B)
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load() {
@@ -92,12 +93,14 @@ struct NcclApi {
     if (!lib) return false;
     GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclBroadcast");
     CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    return GetUniqueId && AllReduce && CommDestroy && dlsym(lib, "ncclCommInitRank");
+    return GetUniqueId && AllReduce && Broadcast && CommDestroy && dlsym(lib, "ncclCommInitRank");
   }
 };
 static NcclApi g_nccl;
+enum { kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2 };   // ncclDataType_t / ncclRedOp_t values of nccl.h
 struct NcclId { char internal[128]; };
 typedef int (*ncclCommInitRank_t)(ncclComm_t*, int, NcclId, int);
 
@@ -294,16 +297,23 @@ struct Solver {
   int capture_cholesky_graph();
   void fill_view();
   int compute_records(int buf, bool full);
-  int compute_errors(int buf, bool store, double* chi2);
+  int compute_errors(int buf, bool store, double* chi2, bool trial = false, const volatile unsigned char* stop = nullptr);
   int build_system();
-  int solve(double lambda, bool* ok);
+  int solve(double lambda);
+  int read_fail(bool* ok);
   int apply_update(double lambda, double* scale);
+  // what the last trial evaluation (compute_errors with trial = true) brought back in its one host read
+  double trial_scale = 0;       // computeScale: sum over all ranks of x (lambda x + b)
+  bool trial_failed = false;    // any rank saw a non-positive pivot (landmark block or reduced system)
+  bool stop_seen = false;       // the force-stop flag as ALL ranks agreed to see it
+  bool chi_cache_valid = false; // chi_cache is the robust chi2 of state buffer `cur` (the last trial was accepted)
+  double chi_cache = 0;
   int lm_solve(int iteration, const gpba_lm_params& P, const volatile unsigned char* stop, gpba_lm_trace* tr, int* result);
   int optimize(int iters, const volatile unsigned char* stop, const gpba_lm_params& P, gpba_lm_trace* tr);
   int scatter_points(int buf);
   int download_state(double* kf_pose, double* kf_vel, double* pt_xyz);
   int allreduce_system();
-  int allreduce_scalar(double* v);
+  int allreduce_scalar(double* v, int count = 1, int op = kNcclSum);
 };
 
 static double f32sq(double d) { return (double)(float)(d * d); }  // RobustKernelHuber::setDelta: float dsqr
@@ -338,7 +348,17 @@ int Solver::init(const gpba_problem* P, int dev, bool async_upload) {
   h_fail = (int*)(h_scal + 16);
   n_cam = P->n_cam; n_kf = P->n_kf; n_pt = P->n_pt; n_rec = P->n_rec; n_obs = P->n_obs;
   n_prior = P->n_prior; n_velp = P->n_velp;
-  if (n_cam <= 0 || n_kf <= 0 || n_pt < 0 || n_obs < 0) { g_err = "empty problem"; return GPBA_ERR_INVALID; }
+  if (n_cam <= 0 || n_kf <= 0 || n_pt < 0 || n_obs < 0 || n_rec < 0 || n_prior < 0 || n_velp < 0) { g_err = "empty problem / negative count"; return GPBA_ERR_INVALID; }
+  // nothing malformed crosses the boundary: every array a count promises must be there, every index in range
+  if (!P->cam_intr || !P->cam_Tbc || !P->kf_pose || !P->kf_vel || !P->kf_time || !P->kf_fixed || (n_pt > 0 && !P->pt_xyz) ||
+      (n_rec > 0 && (!P->rec_kf1 || !P->rec_kf2 || !P->rec_cam || !P->rec_t)) ||
+      (n_obs > 0 && (!P->obs_u || !P->obs_v || !P->obs_inv_sigma2 || !P->obs_rec || !P->obs_pt)) ||
+      (n_prior > 0 && (!P->prior_kf1 || !P->prior_kf2)) || (n_velp > 0 && !P->velp_kf)) { g_err = "null array with a non-zero count"; return GPBA_ERR_INVALID; }
+  if (n_obs > 0 && (n_rec == 0 || n_pt == 0)) { g_err = "observations without records / points"; return GPBA_ERR_INVALID; }
+  for (int i = 0; i < n_prior; ++i)
+    if (P->prior_kf1[i] < 0 || P->prior_kf1[i] >= n_kf || P->prior_kf2[i] < 0 || P->prior_kf2[i] >= n_kf) { g_err = "prior keyframe index out of range"; return GPBA_ERR_INVALID; }
+  for (int i = 0; i < n_velp; ++i)
+    if (P->velp_kf[i] < 0 || P->velp_kf[i] >= n_kf) { g_err = "velocity-prior keyframe index out of range"; return GPBA_ERR_INVALID; }
   bf = P->bf;
   h_pose.assign(P->kf_pose, P->kf_pose + 7 * (size_t)n_kf);
   h_vel.assign(P->kf_vel, P->kf_vel + 6 * (size_t)n_kf);
@@ -357,7 +377,7 @@ int Solver::init(const gpba_problem* P, int dev, bool async_upload) {
   huber_mono = P->huber_mono; huber_stereo = P->huber_stereo; huber_prior = P->huber_prior;
   lambda_init = P->lambda_init; linear_solver = P->linear_solver;
   for (int r = 0; r < n_rec; ++r)
-    if (rec_kf2[r] < 0 || rec_kf2[r] >= n_kf || rec_kf1[r] >= n_kf || rec_cam[r] < 0 || rec_cam[r] >= n_cam) { g_err = "record index out of range"; return GPBA_ERR_INVALID; }
+    if (rec_kf2[r] < 0 || rec_kf2[r] >= n_kf || rec_kf1[r] < -1 || rec_kf1[r] >= n_kf || rec_cam[r] < 0 || rec_cam[r] >= n_cam) { g_err = "record index out of range"; return GPBA_ERR_INVALID; }
 
   // per-camera constants
   std::vector<CamConst> cams(n_cam);
@@ -925,7 +945,7 @@ int Solver::build_structure() {
   CK(cudaMemcpyAsync(d_pose[1 - cur].p, d_pose[cur].p, sizeof(double) * 7 * (size_t)n_kf, cudaMemcpyDeviceToDevice, stream));
   CK(cudaMemcpyAsync(d_vel[1 - cur].p, d_vel[cur].p, sizeof(double) * 6 * (size_t)n_kf, cudaMemcpyDeviceToDevice, stream));
   lap("upload + alloc");
-  if (linear_solver == GPBA_SOLVER_DENSE_CHOL) CKR(build_cholesky_structure());
+  if (linear_solver != GPBA_SOLVER_PCG) CKR(build_cholesky_structure());
   else CKR(pcg.setup(n_pose, n_hs, hs_row, hs_col, stream));
   CK(cudaStreamSynchronize(stream));
   lap("linear solver structure");
@@ -1166,6 +1186,22 @@ int Solver::capture_cholesky_graph() {
   return GPBA_OK;
 }
 
+// computeLambdaInit helpers: diagonal of the pose blocks, max |diagonal| of the landmark blocks
+__global__ void k_hpp_diag(int n_pose, const int* __restrict__ pose_diag, const double* __restrict__ hpp, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pose * 12) out[i] = hpp[(size_t)pose_diag[i / 12] * 144 + (i % 12) * 13];
+}
+__global__ void __launch_bounds__(256) k_hll_absmax(int n_lm, const double* __restrict__ hll, double* __restrict__ partial) {
+  __shared__ double red[256];
+  double m = 0.0;
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n_lm; l += gridDim.x * blockDim.x)
+    m = fmax(m, fmax(fabs(hll[9 * (size_t)l]), fmax(fabs(hll[9 * (size_t)l + 4]), fabs(hll[9 * (size_t)l + 8]))));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]); __syncthreads(); }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
 int Solver::compute_records(int buf, bool full) {
   t0();
   if (full) k_records<true><<<(n_rec + 63) / 64, 64, 0, stream>>>(V, d_pose[buf].p, d_vel[buf].p, d_rec.p);
@@ -1175,8 +1211,20 @@ int Solver::compute_records(int buf, bool full) {
   return GPBA_OK;
 }
 
-// SparseOptimizer::computeActiveErrors + activeRobustChi2 on state buffer `buf`.
-int Solver::compute_errors(int buf, bool store, double* chi2) {
+// [chi2, scale, fail, stop] of one LM trial leave the device in ONE copy (and, on several GPUs, ONE all-reduce): the
+// failure flag of the solve and the caller's stop flag ride along as doubles, so every rank takes the same accept /
+// reject / stop decision from the same four sums (a rank-local flag would let the replicated LM loops diverge).
+__global__ void k_pack_trial(double* __restrict__ scal, const int* __restrict__ fail, int trial, double stop) {
+  if (threadIdx.x == 0) {
+    if (!trial) scal[1] = 0.0;
+    scal[2] = trial && fail[0] ? 1.0 : 0.0;
+    scal[3] = stop;
+  }
+}
+
+// SparseOptimizer::computeActiveErrors + activeRobustChi2 on state buffer `buf`.  trial: the evaluation closes an LM
+// trial (solve + apply_update were enqueued before): the same host read also brings computeScale and the failure flag.
+int Solver::compute_errors(int buf, bool store, double* chi2, bool trial, const volatile unsigned char* stop) {
   CKR(compute_records(buf, false));
   t0();
   double* out = store ? (chi2_store_override ? chi2_store_override : d_chi2.p) : nullptr;
@@ -1191,11 +1239,14 @@ int Solver::compute_errors(int buf, bool store, double* chi2) {
   }
   k_reduce<<<1, 256, 0, stream>>>(d_partial.p, n_aobs > 0 ? grid_obs : 0, d_prior_rho.p, priors_here ? n_prior + n_velp : 0, d_scal.p);
   CK(cudaGetLastError());
-  t1(1, 3);
-  if (nranks > 1) CKR(allreduce_scalar(d_scal.p));
-  CK(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  k_pack_trial<<<1, 32, 0, stream>>>(d_scal.p, d_fail.p, trial ? 1 : 0, (stop && *stop) ? 1.0 : 0.0);
+  CK(cudaGetLastError());
+  t1(1, 4);
+  if (nranks > 1) CKR(allreduce_scalar(d_scal.p, 4));
+  CK(cudaMemcpyAsync(h_scal, d_scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   *chi2 = h_scal[0];
+  trial_scale = h_scal[1]; trial_failed = h_scal[2] != 0.0; stop_seen = h_scal[3] != 0.0;
   last_eval = buf;
   return GPBA_OK;
 }
@@ -1245,16 +1296,16 @@ int Solver::allreduce_system() {
   t1(9, 1);
   return GPBA_OK;
 }
-int Solver::allreduce_scalar(double* v) {
+int Solver::allreduce_scalar(double* v, int count, int op) {
   t0();
-  int rc = g_nccl.AllReduce(v, v, 1, 8, 0, comm, stream);
+  int rc = g_nccl.AllReduce(v, v, (size_t)count, kNcclDouble, op, comm, stream);
   if (rc != 0) { g_err = "ncclAllReduce(scalar) failed"; return GPBA_ERR_NCCL; }
   t1(9, 1);
   return GPBA_OK;
 }
 
 // BlockSolver::solve with lambda on the diagonals of Hpp and Hll (setLambda folded in: block_solver.hpp:563-589,353-486).
-int Solver::solve(double lambda, bool* ok) {
+int Solver::solve(double lambda) {
   double* bs = d_hs.p + (size_t)n_hs * 144;  // bschur lives right behind the Hschur values (one allreduce)
   CK(cudaMemsetAsync(d_fail.p, 0, sizeof(int), stream));
   t0();
@@ -1289,7 +1340,7 @@ int Solver::solve(double lambda, bool* ok) {
   CKR(allreduce_system());
   t0();
   launches = 0;
-  if (linear_solver == GPBA_SOLVER_DENSE_CHOL) {
+  if (linear_solver != GPBA_SOLVER_PCG) {
     if (!chol_graph) CKR(capture_cholesky_graph());
     CK(cudaGraphLaunch(chol_graph, stream));
     t1(6, chol_graph_launches);
@@ -1301,6 +1352,28 @@ int Solver::solve(double lambda, bool* ok) {
     CKR(pcg.solve(n_pose, n_hs, d_hs.p, bs, d_x.p, stream, &it, d_fail.p));
     launches += 1;
     t1(6, launches);
+  }
+  // Levels that hold several tile columns accumulate with floating-point atomics, whose order is not fixed: the ranks
+  // of a multi-GPU run would keep replicated poses that differ in the last bits.  Rank 0's solution is everybody's.
+  if (nranks > 1 && n_pose > 0) {
+    t0();
+    if (g_nccl.Broadcast(d_x.p, d_x.p, (size_t)n_pose * 12, kNcclDouble, 0, comm, stream) != 0) { g_err = "ncclBroadcast(x) failed"; return GPBA_ERR_NCCL; }
+    t1(9, 1);
+  }
+  return GPBA_OK;
+}
+
+// solve()'s failure flag (a non-positive landmark block or reduced system), agreed on by all ranks: used by the L1 path;
+// the LM loop gets the same flag with the trial's chi2 (compute_errors).
+int Solver::read_fail(bool* ok) {
+  if (nranks > 1) {
+    k_pack_trial<<<1, 32, 0, stream>>>(d_scal.p + 4, d_fail.p, 1, 0.0);
+    CK(cudaGetLastError());
+    CKR(allreduce_scalar(d_scal.p + 6, 1));
+    CK(cudaMemcpyAsync(h_scal + 6, d_scal.p + 6, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    *ok = h_scal[6] == 0.0;
+    return GPBA_OK;
   }
   CK(cudaMemcpyAsync(h_fail, d_fail.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
@@ -1319,18 +1392,15 @@ int Solver::apply_update(double lambda, double* scale) {
     k_backsub<<<gp, 128, 0, stream>>>(V, lambda, d_U.p, d_ptL.p, d_bl.p, d_Y.p, d_ptS[cur].p, d_ptS[nb].p, d_xl.p, d_partial.p);
     CK(cudaGetLastError());
   }
-  k_update_poses<<<(n_kf + 63) / 64, 64, 0, stream>>>(V, lambda, d_x.p, d_bp.p, d_pose[cur].p, d_vel[cur].p, d_pose[nb].p, d_vel[nb].p, d_pose_scale.p);
+  // computeScale = sum x (lambda x + b) over poses and landmarks (optimization_algorithm_levenberg.cpp:187-194).  Under
+  // sharding b_p is a per-rank partial (the GP-edge part of the rank's own landmarks; the priors live on rank 0), so every
+  // rank contributes x_p . b_p^(rank) and rank 0 alone adds lambda |x_p|^2: the all-reduced sum is x_p . (lambda x_p + b_p).
+  k_update_poses<<<(n_kf + 63) / 64, 64, 0, stream>>>(V, rank == 0 ? lambda : 0.0, d_x.p, d_bp.p, d_pose[cur].p, d_vel[cur].p, d_pose[nb].p, d_vel[nb].p, d_pose_scale.p);
   CK(cudaGetLastError());
-  // pose part of computeScale is replicated on every rank; landmark part is per-rank
-  k_reduce<<<1, 256, 0, stream>>>(d_partial.p, gp, d_pose_scale.p, rank == 0 ? n_pose : 0, d_scal.p + 1);
+  k_reduce<<<1, 256, 0, stream>>>(d_partial.p, gp, d_pose_scale.p, n_pose, d_scal.p + 1);
   CK(cudaGetLastError());
   t1(8, 4);
-  if (nranks > 1) CKR(allreduce_scalar(d_scal.p + 1));
-  if (scale) {
-    CK(cudaMemcpyAsync(h_scal + 1, d_scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    *scale = h_scal[1];
-  }
+  (void)scale;   // read back together with the trial's chi2 (compute_errors(trial = true))
   return GPBA_OK;
 }
 
@@ -1338,37 +1408,60 @@ int Solver::apply_update(double lambda, double* scale) {
 int Solver::lm_solve(int iteration, const gpba_lm_params& P, const volatile unsigned char* stop, gpba_lm_trace* tr, int* result) {
   if (iteration == 0 && structure_dirty) CKR(build_structure());
   double currentChi = 0;
-  CKR(compute_errors(cur, false, &currentChi));
+  // computeActiveErrors + activeRobustChi2 at the estimate (:72-73).  After an accepted trial the estimate IS the state
+  // that trial evaluated, so the value is already known and the pass over the observations is skipped.
+  if (chi_cache_valid && last_eval == cur) currentChi = chi_cache;
+  else CKR(compute_errors(cur, false, &currentChi));
+  chi_cache_valid = false;
   double tempChi = currentChi;
   const double iniChi = currentChi;
   CKR(build_system());
   if (iteration == 0) {
     if (lambda_init > 0) lambda_cur = lambda_init;
     else {  // computeLambdaInit: tau * max |H_jj| over poses and landmarks (:171-185)
-      std::vector<double> hp((size_t)n_hpp * 144), hl((size_t)n_lm * 9);
-      CK(cudaMemcpyAsync(hp.data(), d_hpp.p, hp.size() * 8, cudaMemcpyDeviceToHost, stream));
-      if (n_lm) CK(cudaMemcpyAsync(hl.data(), d_hll.p, hl.size() * 8, cudaMemcpyDeviceToHost, stream));
+      // the pose diagonal of a multi-GPU run is the SUM of the ranks' partial Hpp, the landmark diagonal is rank-local:
+      // sum-reduce the first, max-reduce the result, so every rank starts from the same lambda
+      std::vector<double> hd((size_t)std::max(n_pose, 1) * 12, 0.0);
+      DBuf<double> d_diag;
+      CKR(d_diag.alloc(hd.size() + 1));
+      const int gl = n_lm > 0 ? std::min((n_lm + 255) / 256, 148 * 8) : 0;
+      if (n_pose > 0) { k_hpp_diag<<<(n_pose * 12 + 255) / 256, 256, 0, stream>>>(n_pose, d_pose_hpp_diag.p, d_hpp.p, d_diag.p); CK(cudaGetLastError()); }
+      if (gl > 0) { k_hll_absmax<<<gl, 256, 0, stream>>>(n_lm, d_hll.p, d_partial.p); CK(cudaGetLastError()); }
+      if (nranks > 1 && n_pose > 0) CKR(allreduce_scalar(d_diag.p, n_pose * 12, kNcclSum));
+      std::vector<double> part((size_t)std::max(gl, 1), 0.0);
+      if (n_pose > 0) CK(cudaMemcpyAsync(hd.data(), d_diag.p, sizeof(double) * 12 * (size_t)n_pose, cudaMemcpyDeviceToHost, stream));
+      if (gl > 0) CK(cudaMemcpyAsync(part.data(), d_partial.p, sizeof(double) * gl, cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
       double mx = 0;
-      for (int k = 0; k < n_hpp; ++k) if (hpp_row[k] == hpp_col[k]) for (int j = 0; j < 12; ++j) mx = std::max(mx, std::fabs(hp[(size_t)k * 144 + j * 13]));
-      for (int l = 0; l < n_lm; ++l) for (int j = 0; j < 3; ++j) mx = std::max(mx, std::fabs(hl[(size_t)l * 9 + j * 4]));
+      for (double v : hd) mx = std::max(mx, std::fabs(v));
+      for (double v : part) mx = std::max(mx, v);
+      if (nranks > 1) {
+        h_scal[8] = mx;
+        CK(cudaMemcpyAsync(d_scal.p + 7, h_scal + 8, sizeof(double), cudaMemcpyHostToDevice, stream));
+        CKR(allreduce_scalar(d_scal.p + 7, 1, kNcclMax));
+        CK(cudaMemcpyAsync(h_scal + 8, d_scal.p + 7, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        mx = h_scal[8];
+      }
       lambda_cur = P.tau * mx;
     }
     ni = 2; nBad = 0;
   }
   double rho = 0;
   int qmax = 0;
+  bool accepted = false;
   do {
-    bool ok2 = false;
-    CKR(solve(lambda_cur, &ok2));
-    double scale = 0;
-    CKR(apply_update(lambda_cur, &scale));
-    CKR(compute_errors(1 - cur, false, &tempChi));
-    if (!ok2) tempChi = std::numeric_limits<double>::max();
+    // one trial = solve + update + evaluation enqueued back to back, ONE host synchronisation at its end
+    CKR(solve(lambda_cur));
+    CKR(apply_update(lambda_cur, nullptr));
+    CKR(compute_errors(1 - cur, false, &tempChi, true, stop));
+    if (trial_failed) tempChi = std::numeric_limits<double>::max();   // solve() == false (:110-113)
+    double scale = trial_scale;
     rho = (currentChi - tempChi);
     scale += 1e-3;
     rho /= scale;
-    if (rho > 0 && std::isfinite(tempChi)) {
+    accepted = rho > 0 && std::isfinite(tempChi);
+    if (accepted) {
       double alpha = 1. - std::pow((2 * rho - 1), 3);
       alpha = (std::min)(alpha, P.good_step_upper);
       const double scaleFactor = (std::max)(P.good_step_lower, alpha);
@@ -1381,7 +1474,8 @@ int Solver::lm_solve(int iteration, const gpba_lm_params& P, const volatile unsi
       ni *= 2;       // pop(): the estimate buffer is untouched
     }
     qmax++;
-  } while (rho < 0 && qmax < P.max_trials_after_failure && !(stop && *stop));
+  } while (rho < 0 && qmax < P.max_trials_after_failure && !stop_seen);
+  if (accepted) { chi_cache_valid = true; chi_cache = currentChi; }
   if (tr && iteration < GPBA_MAX_ITERS) {
     tr->levenberg_iterations[iteration] = qmax;
     tr->chi2_before[iteration] = iniChi;
@@ -1411,7 +1505,20 @@ int Solver::optimize(int iters, const volatile unsigned char* stop, const gpba_l
   pcg.total_iterations = 0;
   int cj = 0, result = GPBA_RESULT_OK;
   bool ok = true;
-  for (int i = 0; i < iters && !(stop && *stop) && ok; ++i) {
+  chi_cache_valid = false;
+  // terminate() (sparse_optimizer.h:188) is polled where the reference polls it -- between outer iterations and in the
+  // trial loop -- but on several GPUs every rank must see the same answer: the flag is sampled when a trial's scalars are
+  // packed and summed over the ranks with them (stop_seen); before the first trial a one-scalar all-reduce does the same.
+  stop_seen = stop && *stop;
+  if (nranks > 1 && stop) {
+    h_scal[8] = stop_seen ? 1.0 : 0.0;
+    CK(cudaMemcpyAsync(d_scal.p + 7, h_scal + 8, sizeof(double), cudaMemcpyHostToDevice, stream));
+    CKR(allreduce_scalar(d_scal.p + 7, 1));
+    CK(cudaMemcpyAsync(h_scal + 8, d_scal.p + 7, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    stop_seen = h_scal[8] != 0.0;
+  }
+  for (int i = 0; i < iters && !stop_seen && ok; ++i) {
     CKR(lm_solve(i, P, stop, tr, &result));
     ok = (result == GPBA_RESULT_OK);
     ++cj;
@@ -1591,10 +1698,10 @@ int gpba_solve(gpba_handle* h, int* ok) {
   bool k = false;
   Solver& s = S(h);
   const double lam = s.lambda_applied ? s.lambda_set : 0.0;
-  CKR(s.solve(lam, &k));
+  CKR(s.solve(lam));
   // landmark part of x (no state change): run the back-substitution into the scratch buffer
   CKR(s.apply_update(lam, nullptr));
-  CK(cudaStreamSynchronize(s.stream));
+  CKR(s.read_fail(&k));
   if (ok) *ok = k ? 1 : 0;
   return GPBA_OK;
 }
@@ -1603,9 +1710,10 @@ int gpba_vector_size(gpba_handle* h, int64_t* n) { NEED_STRUCT(h); *n = (int64_t
 int gpba_get_x(gpba_handle* h, double* x) {
   NEED_STRUCT(h);
   Solver& s = S(h);
-  CK(cudaMemcpy(x, s.d_x.p, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(x, s.d_x.p, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost, s.stream));
   std::vector<double> xl((size_t)s.n_lm * 3);
-  if (s.n_lm) CK(cudaMemcpy(xl.data(), s.d_xl.p, xl.size() * 8, cudaMemcpyDeviceToHost));
+  if (s.n_lm) CK(cudaMemcpyAsync(xl.data(), s.d_xl.p, xl.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   std::fill(x + (size_t)s.n_pose * 12, x + (size_t)s.n_pose * 12 + (size_t)s.n_lm_all * 3, 0.0);
   for (int l = 0; l < s.n_lm; ++l) for (int c = 0; c < 3; ++c) x[(size_t)s.n_pose * 12 + (size_t)s.lm_rank[l] * 3 + c] = xl[(size_t)l * 3 + c];
   return GPBA_OK;
@@ -1614,9 +1722,10 @@ int gpba_get_b(gpba_handle* h, double* b) {
   NEED_STRUCT(h);
   Solver& s = S(h);
   CK(cudaStreamSynchronize(s.stream));
-  CK(cudaMemcpy(b, s.d_bp.p, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(b, s.d_bp.p, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost, s.stream));
   std::vector<double> bl((size_t)s.n_lm * 3);
-  if (s.n_lm) CK(cudaMemcpy(bl.data(), s.d_bl.p, bl.size() * 8, cudaMemcpyDeviceToHost));
+  if (s.n_lm) CK(cudaMemcpyAsync(bl.data(), s.d_bl.p, bl.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   std::fill(b + (size_t)s.n_pose * 12, b + (size_t)s.n_pose * 12 + (size_t)s.n_lm_all * 3, 0.0);
   for (int l = 0; l < s.n_lm; ++l) for (int c = 0; c < 3; ++c) b[(size_t)s.n_pose * 12 + (size_t)s.lm_rank[l] * 3 + c] = bl[(size_t)l * 3 + c];
   return GPBA_OK;
@@ -1625,7 +1734,8 @@ int gpba_get_hpp(gpba_handle* h, double* blocks) {
   NEED_STRUCT(h);
   Solver& s = S(h);
   CK(cudaStreamSynchronize(s.stream));
-  CK(cudaMemcpy(blocks, s.d_hpp.p, sizeof(double) * 144 * (size_t)s.n_hpp, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(blocks, s.d_hpp.p, sizeof(double) * 144 * (size_t)s.n_hpp, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   if (s.lambda_applied)
     for (int k = 0; k < s.n_hpp; ++k) if (s.hpp_row[k] == s.hpp_col[k]) for (int j = 0; j < 12; ++j) blocks[(size_t)k * 144 + j * 13] += s.lambda_set;
   return GPBA_OK;
@@ -1634,8 +1744,9 @@ int gpba_get_hschur(gpba_handle* h, double* blocks, double* bschur) {
   NEED_STRUCT(h);
   Solver& s = S(h);
   CK(cudaStreamSynchronize(s.stream));
-  if (blocks) CK(cudaMemcpy(blocks, s.d_hs.p, sizeof(double) * 144 * (size_t)s.n_hs, cudaMemcpyDeviceToHost));
-  if (bschur) CK(cudaMemcpy(bschur, s.d_hs.p + (size_t)s.n_hs * 144, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost));
+  if (blocks) CK(cudaMemcpyAsync(blocks, s.d_hs.p, sizeof(double) * 144 * (size_t)s.n_hs, cudaMemcpyDeviceToHost, s.stream));
+  if (bschur) CK(cudaMemcpyAsync(bschur, s.d_hs.p + (size_t)s.n_hs * 144, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   return GPBA_OK;
 }
 int gpba_get_hll(gpba_handle* h, double* blocks) {
@@ -1644,7 +1755,8 @@ int gpba_get_hll(gpba_handle* h, double* blocks) {
   if (s.nranks > 1) { g_err = "gpba_get_hll is a single-GPU parity accessor (landmarks are sharded)"; return GPBA_ERR_STATE; }
   CK(cudaStreamSynchronize(s.stream));
   std::vector<double> hl((size_t)s.n_lm * 9);
-  if (s.n_lm) CK(cudaMemcpy(hl.data(), s.d_hll.p, hl.size() * 8, cudaMemcpyDeviceToHost));
+  if (s.n_lm) CK(cudaMemcpyAsync(hl.data(), s.d_hll.p, hl.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   for (int l = 0; l < s.n_lm; ++l) {
     for (int c = 0; c < 9; ++c) blocks[(size_t)s.lm_rank[l] * 9 + c] = hl[(size_t)l * 9 + c];
     if (s.lambda_applied) for (int j = 0; j < 3; ++j) blocks[(size_t)s.lm_rank[l] * 9 + j * 4] += s.lambda_set;
@@ -1661,10 +1773,11 @@ int gpba_get_hpl(gpba_handle* h, int64_t* lm_begin, int32_t* pose, double* block
   std::vector<double> W((size_t)s.n_aobs * 18), R((size_t)s.n_rec * GPBA_REC_STRIDE);
   std::vector<int> orec((size_t)s.n_aobs);
   if (s.n_aobs) {
-    CK(cudaMemcpy(W.data(), s.d_W.p, W.size() * 8, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(orec.data(), s.d_o_rec.p, orec.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(W.data(), s.d_W.p, W.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(orec.data(), s.d_o_rec.p, orec.size() * 4, cudaMemcpyDeviceToHost, s.stream));
   }
-  if (s.n_rec) CK(cudaMemcpy(R.data(), s.d_rec.p, R.size() * 8, cudaMemcpyDeviceToHost));
+  if (s.n_rec) CK(cudaMemcpyAsync(R.data(), s.d_rec.p, R.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   std::vector<int> inv(s.n_lm);
   for (int l = 0; l < s.n_lm; ++l) inv[s.lm_rank[l]] = l;
   int64_t cursor = 0;
@@ -1710,16 +1823,17 @@ int gpba_oplus(gpba_handle* h, const double* x) {
   NEED_STRUCT(h);
   Solver& s = S(h);
   if (x) {  // caller-provided update in g2o order
-    CK(cudaMemcpy(s.d_x.p, x, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(s.d_x.p, x, sizeof(double) * 12 * (size_t)s.n_pose, cudaMemcpyHostToDevice, s.stream));
     std::vector<double> xl((size_t)s.n_lm * 3);
     for (int l = 0; l < s.n_lm; ++l) for (int c = 0; c < 3; ++c) xl[(size_t)l * 3 + c] = x[(size_t)s.n_pose * 12 + (size_t)s.lm_rank[l] * 3 + c];
-    if (s.n_lm) CK(cudaMemcpy(s.d_xl.p, xl.data(), xl.size() * 8, cudaMemcpyHostToDevice));
+    if (s.n_lm) CK(cudaMemcpyAsync(s.d_xl.p, xl.data(), xl.size() * 8, cudaMemcpyHostToDevice, s.stream));
     // landmarks: plain addition of the provided update
     std::vector<double> pt((size_t)s.n_lm * 3);
     if (s.n_lm) {
-      CK(cudaMemcpy(pt.data(), s.d_ptS[s.cur].p, pt.size() * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpyAsync(pt.data(), s.d_ptS[s.cur].p, pt.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
       for (size_t i = 0; i < pt.size(); ++i) pt[i] += xl[i];
-      CK(cudaMemcpy(s.d_ptS[1 - s.cur].p, pt.data(), pt.size() * 8, cudaMemcpyHostToDevice));
+      CK(cudaMemcpyAsync(s.d_ptS[1 - s.cur].p, pt.data(), pt.size() * 8, cudaMemcpyHostToDevice, s.stream));
     }
     k_update_poses<<<(s.n_kf + 63) / 64, 64, 0, s.stream>>>(s.V, 0.0, s.d_x.p, s.d_bp.p, s.d_pose[s.cur].p, s.d_vel[s.cur].p,
                                                            s.d_pose[1 - s.cur].p, s.d_vel[1 - s.cur].p, s.d_pose_scale.p);
@@ -1735,9 +1849,10 @@ int gpba_push(gpba_handle* h) {
   Solver& s = S(h);
   std::vector<double> p((size_t)s.n_kf * 7), v((size_t)s.n_kf * 6), q((size_t)s.n_lm * 3);
   CK(cudaStreamSynchronize(s.stream));
-  CK(cudaMemcpy(p.data(), s.d_pose[s.cur].p, p.size() * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(v.data(), s.d_vel[s.cur].p, v.size() * 8, cudaMemcpyDeviceToHost));
-  if (s.n_lm) CK(cudaMemcpy(q.data(), s.d_ptS[s.cur].p, q.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(p.data(), s.d_pose[s.cur].p, p.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaMemcpyAsync(v.data(), s.d_vel[s.cur].p, v.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+  if (s.n_lm) CK(cudaMemcpyAsync(q.data(), s.d_ptS[s.cur].p, q.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   s.stack_pose.push_back(p); s.stack_vel.push_back(v); s.stack_pt.push_back(q);
   return GPBA_OK;
 }
@@ -1746,10 +1861,11 @@ int gpba_pop(gpba_handle* h) {
   Solver& s = S(h);
   if (s.stack_pose.empty()) { g_err = "pop on empty stack"; return GPBA_ERR_STATE; }
   for (int b = 0; b < 2; ++b) {
-    CK(cudaMemcpy(s.d_pose[b].p, s.stack_pose.back().data(), s.stack_pose.back().size() * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.d_vel[b].p, s.stack_vel.back().data(), s.stack_vel.back().size() * 8, cudaMemcpyHostToDevice));
-    if (s.n_lm) CK(cudaMemcpy(s.d_ptS[b].p, s.stack_pt.back().data(), s.stack_pt.back().size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(s.d_pose[b].p, s.stack_pose.back().data(), s.stack_pose.back().size() * 8, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_vel[b].p, s.stack_vel.back().data(), s.stack_vel.back().size() * 8, cudaMemcpyHostToDevice, s.stream));
+    if (s.n_lm) CK(cudaMemcpyAsync(s.d_ptS[b].p, s.stack_pt.back().data(), s.stack_pt.back().size() * 8, cudaMemcpyHostToDevice, s.stream));
   }
+  CK(cudaStreamSynchronize(s.stream));
   s.stack_pose.pop_back(); s.stack_vel.pop_back(); s.stack_pt.pop_back();
   return GPBA_OK;
 }
@@ -1775,7 +1891,8 @@ int gpba_edge_chi2(gpba_handle* h, double* chi2) {
   Solver& s = S(h);
   CK(cudaSetDevice(s.device));
   CK(cudaStreamSynchronize(s.stream));
-  if (s.n_obs) CK(cudaMemcpy(chi2, s.d_chi2.p, sizeof(double) * (size_t)s.n_obs, cudaMemcpyDeviceToHost));
+  if (s.n_obs) CK(cudaMemcpyAsync(chi2, s.d_chi2.p, sizeof(double) * (size_t)s.n_obs, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   return GPBA_OK;
 }
 

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgView P) {
   double rz = grid_partial_sum(part0, gridDim.x);
   const double bb = grid_partial_sum(part1, gridDim.x);
   const double thresh = P.tol * P.tol * bb;
-  int it = 0, converged = (bb == 0.0) ? 1 : 0;
+  int it = 0, converged = (bb == 0.0) ? 1 : 0, indefinite = 0;
   grid.sync();
   while (!converged && it < P.max_it) {
     // ---- Ap = H p (one thread per scalar row), pAp
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgView P) {
     if (tid == 0) part0[blockIdx.x] = lp;
     grid.sync();
     const double pAp = grid_partial_sum(part0, gridDim.x);
+    if (!(pAp > 0.0)) { indefinite = 1; break; }   // every thread reads the same partials: a uniform exit
     const double alpha = rz / pAp;
     // ---- x += alpha p ; r -= alpha Ap
     for (int i = gtid; i < n; i += nthr) { P.x[i] = fma(alpha, P.p[i], P.x[i]); P.r[i] = fma(-alpha, P.Ap[i], P.r[i]); }
@@ -141,7 +142,10 @@ __global__ void __launch_bounds__(256) k_pcg(PcgView P) {
     for (int i = gtid; i < n; i += nthr) P.p[i] = fma(beta, P.p[i], P.z[i]);
     grid.sync();
   }
-  if (gtid == 0) { P.out_it[0] = it; P.out_it[1] = converged; if (!isfinite(rz)) atomicExch(P.fail, 1); }
+  // An inexact or meaningless x must not reach the LM step as a valid solution: the reference's LDLT solve is exact and
+  // returns false on a non-positive system (linear_solver_eigen.h:113-118), so a run that hit max_it, met p^T A p <= 0
+  // (indefinite reduced system) or produced a non-finite residual reports failure and the LM controller rejects the trial.
+  if (gtid == 0) { P.out_it[0] = it; P.out_it[1] = converged; if (!converged || indefinite || !isfinite(rz)) atomicExch(P.fail, 1); }
 }
 
 struct PcgBuffers {

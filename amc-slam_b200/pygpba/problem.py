@@ -10,7 +10,7 @@ import numpy as np
 GPBA_MAX_ITERS = 64
 GPBA_N_STAGES = 11
 OBS_CLOSE, OBS_LEVEL1, OBS_NO_KERNEL = 1, 2, 4
-SOLVER_DENSE_CHOL, SOLVER_PCG = 0, 1
+SOLVER_DENSE_CHOL, SOLVER_PCG, SOLVER_SPARSE_CHOL = 0, 1, 2
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)

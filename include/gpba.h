@@ -38,11 +38,13 @@ typedef enum gpba_status {
 /* g2o::OptimizationAlgorithm::SolverResult (optimization_algorithm.h) */
 typedef enum gpba_solver_result { GPBA_TERMINATE = 2, GPBA_RESULT_OK = 1, GPBA_FAIL = -1 } gpba_solver_result;
 
-/* Reduced-camera-system solver.  DENSE_CHOL replaces LinearSolverDense (Eigen::LDLT,
- * g2o/solvers/linear_solver_dense.h:65-113, LocalGPBA Optimizer.cc:841); PCG is the
- * block-Jacobi preconditioned CG used for the sparse global systems (replaces
- * LinearSolverEigen / SimplicialLDLT, linear_solver_eigen.h:94-124, Optimizer.cc:70). */
-typedef enum gpba_linear_solver { GPBA_SOLVER_DENSE_CHOL = 0, GPBA_SOLVER_PCG = 1 } gpba_linear_solver;
+/* Reduced-camera-system solver = which g2o::LinearSolver the caller would have constructed.
+ *   DENSE_CHOL   LinearSolverDense (Eigen::LDLT, g2o/solvers/linear_solver_dense.h:65-113; LocalGPBA, Optimizer.cc:841)
+ *   SPARSE_CHOL  LinearSolverEigen (SimplicialLDLT + AMD, linear_solver_eigen.h:94-124; BundleAdjustment, Optimizer.cc:70)
+ *   PCG          block-Jacobi preconditioned CG on the Hschur blocks (an inexact alternative, no reference counterpart)
+ * On the device DENSE_CHOL and SPARSE_CHOL run the same tile-sparse DMMA Cholesky (a dense system is the case where
+ * every tile is present); the distinction matters to the CPU oracle, which restates the two Eigen solvers separately. */
+typedef enum gpba_linear_solver { GPBA_SOLVER_DENSE_CHOL = 0, GPBA_SOLVER_PCG = 1, GPBA_SOLVER_SPARSE_CHOL = 2 } gpba_linear_solver;
 
 /* obs_flags bits */
 #define GPBA_OBS_CLOSE 0x1u   /* MapPoint::mvTrackDepth[cam] < 10 m  (Optimizer.cc:1273)     */

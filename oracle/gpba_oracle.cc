@@ -318,7 +318,11 @@ struct Oracle {
   std::vector<double> b, x, bschur, coeff;
   std::vector<double> diag_backup_pose, diag_backup_lm;
   BlockSparseChol sparse;
+#ifdef _OPENMP
+  std::vector<omp_lock_t> row_locks;
+#endif
   bool structure_ok = false, system_ok = false;
+  bool structure_fresh = false;   // build_structure() ran and neither levels nor kernels changed since
 
   // ---- backup stack (BaseVertex::push/pop)
   struct Snapshot { std::vector<KfState> kf; std::vector<V3> pt; };
@@ -328,6 +332,15 @@ struct Oracle {
   double currentLambda = -1, ni = 2;
   int nBad = 0, levenbergIterations = 0;
   double last_trial_chi2 = 0;
+  // ---- per-stage wall time, field names of G2OBatchStatistics (g2o/core/batch_stats.h:39-78)
+  double timeResiduals = 0, timeQuadraticForm = 0, timeSchurComplement = 0, timeLinearSolver = 0, timeUpdate = 0;
+  static double now() {
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return (double)clock() / CLOCKS_PER_SEC;
+#endif
+  }
 
   bool obs_is_gp(int64_t i) const { return rec_kf1[obs_rec[i]] >= 0; }
   int obs_dim(int64_t i) const { return obs_ur[i] >= 0 ? 3 : 2; }
@@ -524,6 +537,7 @@ struct Oracle {
   double velp_chi2(int i) const { return velp_err[i] * (G.QcInv(2, 2) * velp_err[i]); }
 
   void compute_errors() {  // SparseOptimizer::computeActiveErrors
+    const double t_res = now();
     for (int i = 0; i < n_velp; ++i)
       if (velp_active[i]) velp_err[i] = kf[velp_kf[i]].vel[2];
     for (int i = 0; i < n_prior; ++i)
@@ -531,6 +545,7 @@ struct Oracle {
     const int64_t na = (int64_t)active_obs.size();
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
     for (int64_t k = 0; k < na; ++k) compute_obs_error(active_obs[k]);
+    timeResiduals += now() - t_res;
   }
   double robust_chi2() const {  // SparseOptimizer::activeRobustChi2
     double chi = 0.0, rho[3];
@@ -679,6 +694,7 @@ struct Oracle {
   }
 
   void build_system() {
+    const double t_qf = now();
     std::fill(b.begin(), b.end(), 0.0);
     for (auto& m : hpp) m = M12::Zero();
     for (auto& m : hll) m = M3::Zero();
@@ -713,6 +729,7 @@ struct Oracle {
       }
     }
     system_ok = true;
+    timeQuadraticForm += now() - t_qf;
   }
 
   void set_lambda(double lambda, bool backup) {
@@ -739,6 +756,17 @@ struct Oracle {
     for (auto& m : hs) m = M12::Zero();
     for (size_t i = 0; i < hpp_rc.size(); ++i) { M12& t = hs[hs_idx.find(hpp_rc[i])->second]; t = t + hpp[i]; }  // _Hpp->add(_Hschur)
     std::fill(coeff.begin(), coeff.begin() + sizePoses, 0.0);
+    const double t_schur = now();
+    // G2O_OPENMP build of the reference: "#pragma omp parallel for schedule(dynamic, 10)" over the landmarks with one
+    // mutex per pose row (block_solver.hpp:378-380, 397-399).  threads == 1 is the reference's actual configuration.
+#ifdef _OPENMP
+    if (threads > 1 && (int)row_locks.size() != numPoses) {
+      for (auto& lk : row_locks) omp_destroy_lock(&lk);
+      row_locks.resize(numPoses);
+      for (auto& lk : row_locks) omp_init_lock(&lk);
+    }
+#pragma omp parallel for schedule(dynamic, 10) num_threads(threads) if (threads > 1)
+#endif
     for (int l = 0; l < numLandmarks; ++l) {
       M3 Dinv = inverse<3>(hll[l]);
       dinv[l] = Dinv;
@@ -750,6 +778,9 @@ struct Oracle {
         const M12x3& Bi = hpl[s];
         M12x3 BDinv = Bi * Dinv;
         V12 Bb = Bi * db;
+#ifdef _OPENMP
+        if (threads > 1) omp_set_lock(&row_locks[i1]);
+#endif
         for (int k = 0; k < 12; ++k) coeff[(size_t)i1 * 12 + k] += Bb[k];
         size_t it = 0;
         const std::vector<int>& cols = hs_row_cols[i1];
@@ -765,9 +796,14 @@ struct Oracle {
               H(r, c) -= t;
             }
         }
+#ifdef _OPENMP
+        if (threads > 1) omp_unset_lock(&row_locks[i1]);
+#endif
       }
     }
     for (size_t i = 0; i < sizePoses; ++i) bschur[i] = b[i] - coeff[i];
+    timeSchurComplement += now() - t_schur;
+    const double t_lin = now();
     bool ok;
     if (linear_solver == GPBA_SOLVER_DENSE_CHOL) {
       int n = (int)sizePoses;
@@ -785,8 +821,10 @@ struct Oracle {
       if (!sparse.analyzed) sparse.analyze(numPoses, hs_rc);
       ok = sparse.factor_solve(hs_rc, hs, bschur.data(), x.data());
     }
+    timeLinearSolver += now() - t_lin;
     if (!ok) return false;
-    // landmarks: xl = Dinv * (bl - Hpl^T xp)
+    // landmarks: xl = Dinv * (bl - Hpl^T xp)   (block_solver.hpp:459-483; under G2O_OPENMP the two products run in parallel, sparse_block_matrix_ccs.h:117, sparse_block_matrix_diagonal.h:90)
+#pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
     for (int l = 0; l < numLandmarks; ++l) {
       V3 cl;
       for (int j = 0; j < 3; ++j) cl[j] = b[sizePoses + (size_t)l * 3 + j];
@@ -807,6 +845,7 @@ struct Oracle {
 
   // ------------------------------------------------------------------ state
   void oplus(const double* upd) {  // SparseOptimizer::update
+    const double t_up = now();
     for (int k = 0; k < n_kf; ++k) {
       if (kf_h[k] < 0) continue;
       const double* u = upd + (size_t)kf_h[k] * 12;
@@ -818,6 +857,7 @@ struct Oracle {
     const double* ul = upd + (size_t)numPoses * 12;
     for (int l = 0; l < numLandmarks; ++l)
       for (int c = 0; c < 3; ++c) pt[lm_pt[l]][c] += ul[(size_t)l * 3 + c];  // VertexSBAPointXYZ::oplusImpl
+    timeUpdate += now() - t_up;
   }
   void push() { stack.push_back({kf, pt}); }
   void pop() { kf = stack.back().kf; pt = stack.back().pt; stack.pop_back(); }
@@ -841,7 +881,10 @@ struct Oracle {
     return scale;
   }
   int lm_solve(int iteration, const gpba_lm_params& P, const volatile unsigned char* stop, gpba_lm_trace* tr) {
-    if (iteration == 0) build_structure();
+    // buildStructure belongs to the first solve() (optimization_algorithm_levenberg.cpp:65-70); a structure built by the
+    // caller right before (same levels, nothing changed since) is the same structure and is used as it is
+    if (iteration == 0 && !structure_fresh) build_structure();
+    structure_fresh = false;
     compute_errors();
     double currentChi = robust_chi2();
     double tempChi = currentChi;
@@ -958,6 +1001,13 @@ void* oracle_create(const gpba_problem* p) {
 }
 void oracle_destroy(void* h) { delete ORA(h); }
 void oracle_set_threads(void* h, int n) { ORA(h)->threads = n < 1 ? 1 : n; }
+// seconds per stage since the last reset: timeResiduals, timeQuadraticForm (linearize + quadratic form), timeSchurComplement,
+// timeLinearSolver, timeUpdate -- the G2OBatchStatistics fields (g2o/core/batch_stats.h:39-78)
+void oracle_batch_stats(void* h, double out[5], int reset) {
+  auto* o = ORA(h);
+  out[0] = o->timeResiduals; out[1] = o->timeQuadraticForm; out[2] = o->timeSchurComplement; out[3] = o->timeLinearSolver; out[4] = o->timeUpdate;
+  if (reset) o->timeResiduals = o->timeQuadraticForm = o->timeSchurComplement = o->timeLinearSolver = o->timeUpdate = 0;
+}
 void oracle_default_lm_params(gpba_lm_params* p) {
   p->max_trials_after_failure = 10; p->tau = 1e-5; p->good_step_lower = 1. / 3.; p->good_step_upper = 2. / 3.;
   p->pcg_tolerance = 1e-12; p->pcg_max_iterations = 2000;
@@ -965,6 +1015,7 @@ void oracle_default_lm_params(gpba_lm_params* p) {
 int oracle_build_structure(void* h, gpba_structure_info* info) {
   Oracle* o = ORA(h);
   o->build_structure();
+  o->structure_fresh = true;
   if (info) {
     info->n_free_kf = o->numPoses; info->n_active_pt = o->numLandmarks; info->n_active_obs = (int64_t)o->active_obs.size();
     info->n_hpl = (int64_t)o->hpl_pose.size(); info->n_hpp = (int)o->hpp_rc.size(); info->n_hschur = (int)o->hs_rc.size();
@@ -1036,11 +1087,13 @@ int oracle_active_robust_chi2(void* h, double* chi2) { *chi2 = ORA(h)->robust_ch
 int oracle_outlier_flags(void* h, const gpba_thresholds* th, uint8_t* flags) { ORA(h)->outlier_flags(*th, flags); return 0; }
 int oracle_set_levels(void* h, const uint8_t* level) {
   Oracle* o = ORA(h);
+  o->structure_fresh = false;
   for (int64_t i = 0; i < o->n_obs; ++i) { if (level[i]) o->obs_flags[i] |= GPBA_OBS_LEVEL1; else o->obs_flags[i] &= ~GPBA_OBS_LEVEL1; }
   return 0;
 }
 int oracle_set_robust_kernel(void* h, int enabled) {
   Oracle* o = ORA(h);
+  o->structure_fresh = false;
   for (int64_t i = 0; i < o->n_obs; ++i) { if (!enabled) o->obs_flags[i] |= GPBA_OBS_NO_KERNEL; else o->obs_flags[i] &= ~GPBA_OBS_NO_KERNEL; }
   return 0;
 }

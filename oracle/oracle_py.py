@@ -62,6 +62,12 @@ class Oracle:
         except Exception:
             pass
 
+    def batch_stats(self, reset=False):
+        """seconds per stage under the G2OBatchStatistics names (g2o/core/batch_stats.h:39-78)"""
+        a = (C.c_double * 5)()
+        self.L.oracle_batch_stats(self.h, a, int(reset))
+        return dict(zip(("timeResiduals", "timeQuadraticForm", "timeSchurComplement", "timeLinearSolver", "timeUpdate"), [float(v) for v in a]))
+
     def build_structure(self):
         info = StructureInfo()
         self.L.oracle_build_structure(self.h, C.byref(info))
