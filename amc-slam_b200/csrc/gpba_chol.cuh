@@ -8,17 +8,26 @@
 // pattern costs O(n b^2) while a fully dense system degenerates to the classic right-looking blocked
 // algorithm.  Every GEMM-shaped part runs on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA).
 //
-// Schedule (captured once per structure in two CUDA graphs and replayed per LM trial):
-//   graph A  k_chol_load                Hschur blocks -> tiles, bschur -> permuted rhs
-//            for every tile column k:
-//              k_chol_panel(k)  every CTA: potrf(k,k) in shared memory (redundant: saves a launch on the
-//                               critical path); CTA 0: L_kk^-1 (kept for the backward solve), y_k = L_kk^-1 b_k;
-//                               CTA q>0: L_ik = A_ik L_kk^-T for one tile below the diagonal
-//              k_chol_update(k) one CTA per tile pair (a >= b) of column k: A_ab -= L_ak L_bk^T;
-//                               last CTA: b_i -= L_ik y_k  (the forward substitution rides along)
-//   graph B  for every tile row i, last to first:
-//              k_chol_back(i)   x_i = L_ii^-T y_i; one CTA per tile (i,k): y_k -= L_ik^T x_i
+// Schedule (captured once per structure in two CUDA graphs and replayed per LM trial).  Tile columns are grouped in
+// LEVELS (a column depends on column k iff tile (j, k) != 0; the nested-dissection order of gpba_order.h makes the levels
+// few and wide); the columns of a level are independent and share launches through CTA tables:
+//   graph A  k_chol_load                  Hschur blocks -> tiles, bschur -> permuted rhs
+//            for every level:
+//              k_chol_lupdate(level)  LEFT-LOOKING: one CTA per tile (i, j) of the level's columns:
+//                                     A_ij -= sum_k L_ik L_jk^T over the finished columns k that touch both rows, the
+//                                     operand tiles streamed by TMA bulk copies (cp.async.bulk + mbarrier, 3 stages)
+//                                     while the products accumulate in DMMA fragments; the tile is written ONCE, by one
+//                                     CTA, in a fixed order (deterministic, no atomics; a right-looking update re-read
+//                                     and re-wrote the target tile for every product: 72 KB of L2 traffic per product
+//                                     against 36 KB here).  Diagonal CTAs also do b_j -= sum_k L_jk y_k.
+//              k_chol_panel(level)    every CTA: potrf(j,j) in shared memory (redundant: saves a launch on the
+//                                     critical path); CTA 0: L_jj^-1 (kept for the backward solve), y_j = L_jj^-1 b_j;
+//                                     CTA q>0: L_ij = A_ij L_jj^-T for one tile below the diagonal
+//   graph B  for every level, last to first:
+//              k_chol_back(level)     x_i = L_ii^-T y_i; one CTA per tile (i,k): y_k -= L_ik^T x_i
 //            k_chol_unpermute
+// A tile is stored in global memory as its shared-memory image (48 rows padded to 52 doubles: DMMA fragment loads are
+// bank-conflict free), so one 1-D bulk copy moves a tile and no thread touches it on the way.
 // The code is loop-structured on purpose: these kernels run one short CTA per launch, so straight-line
 // unrolled substitutions (~100 KB of SASS) were instruction-fetch bound (ncu: stalled_no_instruction 7/issue).
 // A non-positive pivot sets *fail (=> solve() returns false => LM rejects the trial, like
@@ -29,8 +38,11 @@
 namespace gpba {
 
 #define GPBA_NB 48
-#define GPBA_LD 52   // shared-memory row stride: DMMA fragment loads are bank-conflict free, rows 16-byte aligned
+#define GPBA_LD 52   // row stride of a tile (global and shared): DMMA fragment loads are bank-conflict free, rows 16-byte aligned
+#define GPBA_TILE (GPBA_NB * GPBA_LD)            // doubles per stored tile
+#define GPBA_TILE_BYTES (GPBA_TILE * 8)          // 19 968 B: a multiple of 16, as cp.async.bulk requires
 #define GPBA_PANEL_THREADS 192
+#define GPBA_LU_STAGES 3
 
 #ifdef GPBA_CHOL_TIMING
 __device__ long long g_chol_clk[64];
@@ -64,13 +76,14 @@ struct CholView {
   const int* row_begin;         // [NT+1] into row_cols
   const int* row_cols;          // columns k<i with L_ik != 0, ascending
   double* tiles;
-  const int* perm;              // [n/12] fill-reducing order of the pose blocks: permuted index of block b
+  const int* perm;              // [n/12] fill-reducing order of the pose blocks: permuted position of block b
+  const unsigned char* pos_used; // [NT*NB/12] the position holds a pose block (parts of the order start on tile boundaries)
   double* dinv;                 // [NT][NB*NB] inverse of the diagonal factor tiles (lower, row-major)
   double* work;                 // [NT*NB] rhs -> y in permuted order
   double* xsol;                 // [NT*NB] solution in permuted order
 };
 
-// Pad the diagonal, scatter the upper Hschur blocks (row-major 12x12, block (bi,bj), bi<=bj) into the lower
+// Pad the unused positions, scatter the upper Hschur blocks (row-major 12x12, block (bi,bj), bi<=bj) into the lower
 // tiles and load the permuted right-hand side.  The tiles were zeroed by a memset node before.
 __global__ void k_chol_load(CholView C, int n_hs, const int* __restrict__ hs_row, const int* __restrict__ hs_col,
                             const double* __restrict__ hs, const double* __restrict__ rhs) {
@@ -88,37 +101,38 @@ __global__ void k_chol_load(CholView C, int n_hs, const int* __restrict__ hs_row
     else if (pi > pj) { R = pi * 12 + r; Cc = pj * 12 + c; }
     else { R = pj * 12 + c; Cc = pi * 12 + r; }
     const int ti = R / GPBA_NB, tj = Cc / GPBA_NB;
-    C.tiles[C.tile_off[(size_t)ti * C.NT + tj] + (R % GPBA_NB) * GPBA_NB + (Cc % GPBA_NB)] = hs[j];
+    C.tiles[C.tile_off[(size_t)ti * C.NT + tj] + (R % GPBA_NB) * GPBA_LD + (Cc % GPBA_NB)] = hs[j];
   }
   const int NTNB = C.NT * GPBA_NB;
   for (int64_t j = t0; j < NTNB; j += stride) {
-    if (j < C.n) continue;
+    if (C.pos_used[j / 12]) continue;
     const int t = (int)j / GPBA_NB, o = (int)j % GPBA_NB;
-    C.tiles[C.tile_off[(size_t)t * C.NT + t] + o * GPBA_NB + o] = 1.0;  // identity on the padding
+    C.tiles[C.tile_off[(size_t)t * C.NT + t] + o * GPBA_LD + o] = 1.0;  // identity on the padding positions
     C.work[j] = 0.0;
   }
   for (int64_t j = t0; j < C.n; j += stride) C.work[C.perm[j / 12] * 12 + j % 12] = rhs[j];
 }
 
-// global 48x48 row-major tile(s) -> shared [48][GPBA_LD]: all 16-byte loads are issued before the first store,
-// so a CTA pays one memory round trip for both tiles.  NTHR must divide 1152.
-template <int NTHR, int NTILES>
-GPBA_D void tiles_to_smem(const double* __restrict__ T0, double (*S0)[GPBA_LD], const double* __restrict__ T1,
-                          double (*S1)[GPBA_LD]) {
-  constexpr int PER = GPBA_NB * GPBA_NB / 2 / NTHR;
-  double2 v0[PER], v1[PER];
-#pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    v0[q] = reinterpret_cast<const double2*>(T0)[threadIdx.x + q * NTHR];
-    if (NTILES > 1) v1[q] = reinterpret_cast<const double2*>(T1)[threadIdx.x + q * NTHR];
-  }
-#pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const int j = threadIdx.x + q * NTHR;
-    const int r = j / (GPBA_NB / 2), c = 2 * (j % (GPBA_NB / 2));
-    *reinterpret_cast<double2*>(&S0[r][c]) = v0[q];
-    if (NTILES > 1) *reinterpret_cast<double2*>(&S1[r][c]) = v1[q];
-  }
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier
+GPBA_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+GPBA_D void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+GPBA_D void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+GPBA_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+GPBA_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` on the barrier
+GPBA_D void bulk_g2s(void* dst_smem, const void* src_global, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // reciprocal for the pivot chain: MUFU seed + two Newton steps (55 cycles dependent vs 85 for the IEEE division,
@@ -265,18 +279,23 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, c
   __shared__ double D8[GPBA_NB / 8][8][8];
   __shared__ double Sy[GPBA_NB];
   const int tid = threadIdx.x;
+  __shared__ __align__(8) unsigned long long bar;
   GPBA_TICK(0);
   const double* Tkk = C.tiles + C.tile_off[(size_t)k * C.NT + k];   // static index data: may be read before the wait
   double* A = q_ == 0 ? nullptr : C.tiles + C.tile_off[(size_t)C.col_rows[C.col_begin[k] + q_ - 1] * C.NT + k];
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
   pdl_wait_then_release();
+  if (tid == 0) {   // the tiles are stored as their shared-memory image: one bulk copy each, no thread touches the data
+    mbar_expect_tx(&bar, (q_ == 0 ? 1u : 2u) * GPBA_TILE_BYTES);
+    bulk_g2s(&S[0][0], Tkk, GPBA_TILE_BYTES, &bar);
+    if (q_ != 0) bulk_g2s(&T[0][0], A, GPBA_TILE_BYTES, &bar);
+  }
   if (q_ == 0) {
-    tiles_to_smem<GPBA_PANEL_THREADS, 1>(Tkk, S, nullptr, nullptr);
     for (int j = tid; j < GPBA_NB * GPBA_NB; j += blockDim.x) T[j / GPBA_NB][j % GPBA_NB] = (j / GPBA_NB == j % GPBA_NB) ? 1.0 : 0.0;
     if (tid < GPBA_NB) Sy[tid] = C.work[k * GPBA_NB + tid];
-  } else {
-    tiles_to_smem<GPBA_PANEL_THREADS, 2>(Tkk, S, A, T);
   }
-  __syncthreads();
+  __syncthreads();   // the barrier's initialisation is visible to every waiter
+  mbar_wait(&bar, 0);
   GPBA_TICK(1);
   potrf48(S, D8, fail, k, q_);
   GPBA_TICK(2);
@@ -294,80 +313,127 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, c
       C.work[k * GPBA_NB + tid] = y0 + y1;
     }
   } else {
-    double2* A2 = reinterpret_cast<double2*>(A);
-    for (int j = tid; j < GPBA_NB * GPBA_NB / 2; j += blockDim.x)
-      A2[j] = *reinterpret_cast<double2*>(&T[j / (GPBA_NB / 2)][2 * (j % (GPBA_NB / 2))]);
+    for (int j = tid; j < GPBA_NB * GPBA_NB / 2; j += blockDim.x) {
+      const int r = j / (GPBA_NB / 2), c = 2 * (j % (GPBA_NB / 2));
+      *reinterpret_cast<double2*>(A + r * GPBA_LD + c) = *reinterpret_cast<double2*>(&T[r][c]);
+    }
   }
   GPBA_TICK(4);
   GPBA_TICK_DUMP();
 }
 
-// Trailing update of step k: A_ab -= L_ak L_bk^T for all pairs a >= b of column k's non-zero rows.
-// One CTA (4 warps) per pair; both L tiles staged in shared memory, the C tile prefetched into registers while
-// they arrive; each warp owns a 24 x 24 corner = 3 x 3 DMMA tiles (9 independent accumulator chains).
-// The CTA of a diagonal pair (a == b) also applies its tile to the right-hand side: b_i -= L_ik y_k.
-// ATOMIC: the level holds several columns, whose updates may meet in one tile (e.g. two independent interiors of the
-// nested-dissection order both update a separator tile): accumulate with red.global.add.f64.
-template <bool ATOMIC>
-__global__ void __launch_bounds__(128) k_chol_update(CholView C, const int2* __restrict__ tab) {
-  __shared__ __align__(16) double La[GPBA_NB][GPBA_LD], Lb[GPBA_NB][GPBA_LD];
-  __shared__ double yk[GPBA_NB];
-  const int k = tab[blockIdx.x].x;
-  const int cb = C.col_begin[k];
-  const int a = tab[blockIdx.x].y >> 16, b = tab[blockIdx.x].y & 0xffff;   // pair of the column's non-zero rows, a >= b
-  const int ra = C.col_rows[cb + a], rb = C.col_rows[cb + b];
-  const double* Ta = C.tiles + C.tile_off[(size_t)ra * C.NT + k];
-  const double* Tb = C.tiles + C.tile_off[(size_t)rb * C.NT + k];
-  double* Tc = C.tiles + C.tile_off[(size_t)ra * C.NT + rb];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Left-looking update of the tile columns of one level: tile (i, j) of a column of the level receives
+//     A_ij -= sum_k L_ik L_jk^T                 diagonal tiles also:  b_j -= sum_k L_jk y_k
+// over the finished columns k < j with L_ik != 0 and L_jk != 0 (klist: the symbolic phase intersected the two row
+// patterns).  The host cuts the lists into CHUNKS of <= GPBA_LU_CHUNK products, table entry {j, q, kb, ke} (q = 0: the
+// diagonal tile, q > 0: the q-th non-zero row below it).  One SM needs 0.88 us of DMMA issue per 48^3 product at the
+// measured 37 TFLOP/s, so what matters is that all SMs stay busy for the whole launch: PERSISTENT CTAs (one per SM) draw
+// chunks from an atomic counter, and the operand stream never drains -- thread 0 is the producer and keeps GPBA_LU_STAGES
+// operand pairs in flight with cp.async.bulk (one bulk copy per tile, completing on the stage's mbarrier) ACROSS chunk
+// boundaries, a small descriptor per stage telling the consumers where a chunk begins and ends.  The four warps consume a
+// stage when its barrier flips -- each owns a 24 x 24 corner = 3 x 3 DMMA tiles (9 independent accumulator chains) -- and
+// hand it back at a CTA barrier.  A chunk's partial sum leaves with red.global.add.f64 (fire and forget: no read of the
+// target tile on the way; several chunks, possibly on different SMs, may feed one tile).
+#define GPBA_LU_CHUNK 4
+struct LuDesc { double* target; int j; int flags; };   // flags: 1 first product of its chunk, 2 last product, 4 stop, 8 diagonal tile
+__global__ void __launch_bounds__(128) k_chol_lupdate(CholView C, const int4* __restrict__ tab, int n_chunks,
+                                                      const int* __restrict__ klist, int* __restrict__ counter) {
+  extern __shared__ __align__(128) unsigned char lu_smem[];
+  __shared__ __align__(8) unsigned long long full[GPBA_LU_STAGES];
+  __shared__ LuDesc desc[GPBA_LU_STAGES];
+  typedef double (*TileP)[GPBA_LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int m0 = 3 * (warp >> 1), n0 = 3 * (warp & 1);
-  pdl_wait_then_release();
-  double2 cin[3][3];
-  if (!ATOMIC) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        cin[i][j] = *reinterpret_cast<const double2*>(Tc + (8 * (m0 + i) + gid) * GPBA_NB + 8 * (n0 + j) + 2 * tig);
-  }
-  if (a == b && threadIdx.x < GPBA_NB) yk[threadIdx.x] = C.work[k * GPBA_NB + threadIdx.x];
-  tiles_to_smem<128, 2>(Ta, La, Tb, Lb);
-  __syncthreads();
-  double2 acc[3][3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) acc[i][j] = make_double2(0.0, 0.0);
-#pragma unroll 2
-  for (int k0 = 0; k0 < GPBA_NB; k0 += 4) {
-    double af[3], bf[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { af[i] = La[8 * (m0 + i) + gid][k0 + tig]; bf[i] = Lb[8 * (n0 + i) + gid][k0 + tig]; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) dmma884(acc[i][j].x, acc[i][j].y, af[i], bf[j]);
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      double* out = Tc + (8 * (m0 + i) + gid) * GPBA_NB + 8 * (n0 + j) + 2 * tig;
-      if (ATOMIC) { atomicAdd(out, -acc[i][j].x); atomicAdd(out + 1, -acc[i][j].y); }
-      else {
-        double2 o = cin[i][j];
-        o.x -= acc[i][j].x; o.y -= acc[i][j].y;
-        *reinterpret_cast<double2*>(out) = o;
+  // stage s: [La | Lb | y_k]
+  constexpr int STAGE_BYTES = 2 * GPBA_TILE_BYTES + GPBA_NB * 8;
+  auto stage_a = [&](int s) { return reinterpret_cast<TileP>(lu_smem + (size_t)s * STAGE_BYTES); };
+  auto stage_b = [&](int s) { return reinterpret_cast<TileP>(lu_smem + (size_t)s * STAGE_BYTES + GPBA_TILE_BYTES); };
+  auto stage_y = [&](int s) { return reinterpret_cast<double*>(lu_smem + (size_t)s * STAGE_BYTES + 2 * GPBA_TILE_BYTES); };
+  // ---- producer state (thread 0)
+  int p_pos = 0, p_begin = 0, p_end = 0, p_i = 0, p_j = 0;
+  double* p_target = nullptr;
+  bool p_diag = false, p_done = false;
+  auto produce = [&](int s) {   // fill stage s with the next product of the stream (thread 0 only)
+    if (p_pos == p_end) {
+      const int c = atomicAdd(counter, 1);
+      if (c >= n_chunks) {
+        desc[s].target = nullptr; desc[s].j = -1; desc[s].flags = 4;
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+        p_done = true;
+        return;
       }
+      const int4 e = tab[c];
+      p_j = e.x; p_diag = e.y == 0;
+      p_i = p_diag ? e.x : C.col_rows[C.col_begin[e.x] + e.y - 1];
+      p_target = C.tiles + C.tile_off[(size_t)p_i * C.NT + p_j];   // resolved here, off the consumers' path
+      p_begin = p_pos = e.z; p_end = e.w;
     }
-  if (a == b && threadIdx.x < GPBA_NB) {  // forward substitution: b_i -= L_ik y_k with the tile already staged
-    const int r = threadIdx.x;
-    double s0 = 0.0, s1 = 0.0;
+    const int k = klist[p_pos];
+    desc[s].target = p_target; desc[s].j = p_j;
+    desc[s].flags = (p_pos == p_begin ? 1 : 0) | (p_pos + 1 == p_end ? 2 : 0) | (p_diag ? 8 : 0);
+    mbar_expect_tx(&full[s], p_diag ? GPBA_TILE_BYTES + GPBA_NB * 8u : 2u * GPBA_TILE_BYTES);
+    bulk_g2s(stage_a(s), C.tiles + C.tile_off[(size_t)p_i * C.NT + k], GPBA_TILE_BYTES, &full[s]);
+    if (!p_diag) bulk_g2s(stage_b(s), C.tiles + C.tile_off[(size_t)p_j * C.NT + k], GPBA_TILE_BYTES, &full[s]);
+    else bulk_g2s(stage_y(s), C.work + (size_t)k * GPBA_NB, GPBA_NB * 8, &full[s]);
+    ++p_pos;
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GPBA_LU_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_init_fence();
+  }
+  pdl_wait_then_release();   // everything below reads what the previous launches wrote
+  if (tid == 0) {
+    for (int s = 0; s < GPBA_LU_STAGES && !p_done; ++s) produce(s);
+  }
+  __syncthreads();             // barrier initialisation visible to every waiter
+  double2 acc[3][3];
+  double s0 = 0.0, s1 = 0.0;   // rhs row of thread tid < 48 (diagonal tiles)
+  for (int n = 0;; ++n) {
+    const int s = n % GPBA_LU_STAGES;
+    mbar_wait(&full[s], (unsigned)(n / GPBA_LU_STAGES) & 1u);
+    const LuDesc d = desc[s];
+    if (d.flags & 4) break;    // the stream is exhausted (the stages behind this one were never filled)
+    const bool diag = (d.flags & 8) != 0;
+    if (d.flags & 1) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) acc[a][b] = make_double2(0.0, 0.0);
+      s0 = s1 = 0.0;
+    }
+    const TileP La = stage_a(s);
+    const TileP Lb = diag ? La : stage_b(s);
+#pragma unroll 2
+    for (int k0 = 0; k0 < GPBA_NB; k0 += 4) {
+      double af[3], bf[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { af[a] = La[8 * (m0 + a) + gid][k0 + tig]; bf[a] = Lb[8 * (n0 + a) + gid][k0 + tig]; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) dmma884(acc[a][b].x, acc[a][b].y, af[a], bf[b]);
+    }
+    if (diag && tid < GPBA_NB) {   // forward substitution with the tile already staged
+      const double* yk = stage_y(s);
 #pragma unroll 4
-    for (int c = 0; c < GPBA_NB; c += 2) { s0 = fma(La[r][c], yk[c], s0); s1 = fma(La[r][c + 1], yk[c + 1], s1); }
-    if (ATOMIC) atomicAdd(&C.work[ra * GPBA_NB + r], -(s0 + s1));
-    else C.work[ra * GPBA_NB + r] -= s0 + s1;
+      for (int c = 0; c < GPBA_NB; c += 2) { s0 = fma(La[tid][c], yk[c], s0); s1 = fma(La[tid][c + 1], yk[c + 1], s1); }
+    }
+    if (d.flags & 2) {   // the chunk is complete: its partial sum joins the target tile
+      const int j = d.j;
+      double* Tc = d.target;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          double* out = Tc + (8 * (m0 + a) + gid) * GPBA_LD + 8 * (n0 + b) + 2 * tig;
+          atomicAdd(out, -acc[a][b].x); atomicAdd(out + 1, -acc[a][b].y);
+        }
+      if (diag && tid < GPBA_NB) atomicAdd(&C.work[(size_t)j * GPBA_NB + tid], -(s0 + s1));
+    }
+    __syncthreads();   // every warp is done with stage s and its descriptor: it may be refilled
+    if (tid == 0 && !p_done) produce(s);
   }
 }
 
@@ -384,10 +450,11 @@ __global__ void __launch_bounds__(192) k_chol_back(CholView C, const int2* __res
   const double* D = C.dinv + (size_t)i * GPBA_NB * GPBA_NB;  // (L^-T)[c][r] = Linv[r][c], zero for r < c
   const int k = q_ > 0 ? C.row_cols[C.row_begin[i] + q_ - 1] : 0;
   const double* L = q_ > 0 ? C.tiles + C.tile_off[(size_t)i * C.NT + k] : D;
+  const int ldl = q_ > 0 ? GPBA_LD : GPBA_NB;   // factor tiles are stored padded, the inverses of the diagonal tiles dense
   pdl_wait_then_release();
   double dv[12], lv[12];
 #pragma unroll
-  for (int r = 0; r < 12; ++r) { dv[r] = D[(12 * h + r) * GPBA_NB + c]; lv[r] = L[(12 * h + r) * GPBA_NB + c]; }
+  for (int r = 0; r < 12; ++r) { dv[r] = D[(12 * h + r) * GPBA_NB + c]; lv[r] = L[(12 * h + r) * ldl + c]; }
   const double yk_old = (!ATOMIC && q_ > 0 && tid < GPBA_NB) ? C.work[k * GPBA_NB + tid] : 0.0;
   if (tid < GPBA_NB) yi[tid] = C.work[i * GPBA_NB + tid];
   __syncthreads();

@@ -9,6 +9,7 @@
 #include "gpba_chol.cuh"
 #include "gpba_pcg.cuh"
 #include "gpba_structure.cuh"
+#include "gpba_order.h"
 #include "gpba_pose.cuh"
 #include "gpba_vel.cuh"
 
@@ -21,6 +22,7 @@
 #include <string>
 #include <vector>
 #include <dlfcn.h>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <chrono>
@@ -212,19 +214,23 @@ struct Solver {
   int64_t chol_doubles = 0;
   DBuf<int64_t> d_tile_off;
   DBuf<int> d_col_begin, d_col_rows, d_chol_perm;
+  DBuf<unsigned char> d_chol_pos_used;   // [NT * 4] position (pose block slot) of the permuted system holds a pose block
   DBuf<double> d_tiles, d_chol_work, d_chol_dinv, d_chol_x;
   DBuf<int> d_row_begin, d_row_cols;
   std::vector<int> chol_row_begin;
   // level schedule of the tile columns (columns of one level are independent) and the CTA tables of its launches
   std::vector<int> lvl_pan_begin, lvl_upd_begin, lvl_back_begin, lvl_ncols;
-  DBuf<int2> d_pan_tab, d_upd_tab, d_back_tab;
+  DBuf<int2> d_pan_tab, d_back_tab;
+  DBuf<int4> d_upd_tab;
+  DBuf<int> d_klist, d_lu_counter;   // d_lu_counter: one chunk counter per level of the left-looking update
   int chol_parts = 1;
+  int64_t chol_products = 0, chol_update_ctas = 0;
   cudaGraphExec_t chol_graph = nullptr;       // load + (panel, update) x NT, captured once per structure
   cudaGraphExec_t chol_back_graph = nullptr;  // backward substitution, one launch per tile row
   int chol_graph_launches = 0, chol_back_launches = 0;
   CholView chol_view() {
     return CholView{NT, n_pose * 12, d_tile_off.p, d_col_begin.p, d_col_rows.p, d_row_begin.p, d_row_cols.p, d_tiles.p,
-                    d_chol_perm.p, d_chol_dinv.p, d_chol_work.p, d_chol_x.p};
+                    d_chol_perm.p, d_chol_pos_used.p, d_chol_dinv.p, d_chol_work.p, d_chol_x.p};
   }
   std::vector<int> chol_col_begin;
   // ------------------------------------------------------------------ PCG
@@ -958,119 +964,30 @@ int Solver::build_structure() {
 // tile-level symbolic factorization (the analyzePattern of the sparse path)
 int Solver::build_cholesky_structure() {
   const int n = n_pose * 12;
-  NT = (n + GPBA_NB - 1) / GPBA_NB;
-  if (NT == 0) NT = 1;
   const int bpt = GPBA_NB / 12;  // pose blocks per tile
-  // fill-reducing order of the pose blocks: reverse Cuthill-McKee on the Hschur block graph (the role AMD plays
-  // for SimplicialLDLT, linear_solver_eigen.h:147-201); a revisited place then sits next to its first visit and
-  // the factor stays banded instead of filling the whole loop.
-  std::vector<int> perm(n_pose, 0);
-  {
-    std::vector<std::vector<int>> adj(n_pose);
-    for (int k = 0; k < n_hs; ++k) if (hs_row[k] != hs_col[k]) { adj[hs_row[k]].push_back(hs_col[k]); adj[hs_col[k]].push_back(hs_row[k]); }
-    std::vector<int> order; order.reserve(n_pose);
-    std::vector<char> seen(n_pose, 0);
-    auto bfs = [&](int start, std::vector<int>& out) {
-      size_t head = out.size();
-      out.push_back(start); seen[start] = 1;
-      while (head < out.size()) {
-        const int v = out[head++];
-        std::vector<int> nb;
-        for (int w : adj[v]) if (!seen[w]) { seen[w] = 1; nb.push_back(w); }
-        std::sort(nb.begin(), nb.end(), [&](int a, int b) { return adj[a].size() != adj[b].size() ? adj[a].size() < adj[b].size() : a < b; });
-        out.insert(out.end(), nb.begin(), nb.end());
-      }
-    };
-    for (int s0 = 0; s0 < n_pose; ++s0) {
-      if (seen[s0]) continue;
-      // pseudo-peripheral start: BFS from s0, restart from the last (farthest, lowest-degree) node
-      std::vector<int> probe;
-      bfs(s0, probe);
-      const int far = probe.back();
-      for (int v : probe) seen[v] = 0;
-      bfs(far, order);
-    }
-    for (int i = 0; i < n_pose; ++i) perm[order[n_pose - 1 - i]] = i;  // reversed
-    // Nested dissection on top of the RCM order for long trajectories: with bandwidth bw (pose blocks) no edge spans
-    // more than bw positions, so the last bw positions of every segment separate its interior from the next one.
-    // Interiors are eliminated first (independent of each other: their tile columns share levels below and run in
-    // the same launches), the separators last.  Pays when the system is many bandwidths long (C5: ~400); a system
-    // that is only ~12 bandwidths long (C4) keeps the plain banded order.
-    int bw = 1;
-    for (int k = 0; k < n_hs; ++k) bw = std::max(bw, std::abs(perm[hs_row[k]] - perm[hs_col[k]]));
-    const int bwT = (bw + bpt - 1) / bpt * bpt;
-    if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: RCM bandwidth %d pose blocks of %d\n", bw, n_pose);
-    int P = std::min(64, n_pose / (16 * bwT));
-    if (getenv("GPBA_CHOL_PARTS")) P = atoi(getenv("GPBA_CHOL_PARTS"));
-    chol_parts = 1;
-    if (P >= 2) {
-      const int L = ((n_pose + P - 1) / P + bpt - 1) / bpt * bpt;
-      if (L > 2 * bwT) {
-        std::vector<int> newpos(n_pose, -1);
-        int cursor = 0;
-        for (int s0 = 0; s0 < P; ++s0) {       // interiors
-          const int lo = s0 * L, hi = std::min(n_pose, (s0 + 1) * L);
-          const int sep_lo = (s0 < P - 1 && hi == (s0 + 1) * L) ? hi - bwT : hi;
-          for (int q = lo; q < sep_lo; ++q) newpos[q] = cursor++;
-        }
-        for (int s0 = 0; s0 < P - 1; ++s0) {   // separators
-          const int hi = std::min(n_pose, (s0 + 1) * L);
-          if (hi != (s0 + 1) * L) continue;
-          for (int q = hi - bwT; q < hi; ++q) newpos[q] = cursor++;
-        }
-        for (int i = 0; i < n_pose; ++i) perm[i] = newpos[perm[i]];
-        chol_parts = P;
-      }
-    }
-  }
-  std::vector<char> nz((size_t)NT * NT, 0);
-  for (int t = 0; t < NT; ++t) nz[(size_t)t * NT + t] = 1;
-  for (int k = 0; k < n_hs; ++k) {
-    int ti = perm[hs_col[k]] / bpt, tj = perm[hs_row[k]] / bpt;
-    if (ti < tj) std::swap(ti, tj);  // lower triangle
-    nz[(size_t)ti * NT + tj] = 1;
-  }
-  std::vector<int> col_rows;
-  chol_col_begin.assign(NT + 1, 0);
-  std::vector<int> rows;
-  for (int k = 0; k < NT; ++k) {
-    rows.clear();
-    for (int i = k + 1; i < NT; ++i) if (nz[(size_t)i * NT + k]) rows.push_back(i);
-    for (size_t a = 0; a < rows.size(); ++a)
-      for (size_t b = 0; b <= a; ++b) nz[(size_t)rows[a] * NT + rows[b]] = 1;  // fill
-    chol_col_begin[k] = (int)col_rows.size();
-    col_rows.insert(col_rows.end(), rows.begin(), rows.end());
-  }
-  chol_col_begin[NT] = (int)col_rows.size();
-  std::vector<int64_t> off((size_t)NT * NT, -1);
-  int64_t cursor = 0;
-  for (int i = 0; i < NT; ++i)
-    for (int j = 0; j <= i; ++j)
-      if (nz[(size_t)i * NT + j]) { off[(size_t)i * NT + j] = cursor; cursor += GPBA_NB * GPBA_NB; }
-  chol_doubles = cursor;
-  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: n=%d NT=%d tiles=%lld (dense lower would be %d), %.1f MB\n", n, NT, (long long)(cursor / (GPBA_NB * GPBA_NB)), NT * (NT + 1) / 2, cursor * 8 / 1e6);
+  // symbolic phase on the host (gpba_order.h): nested-dissection order, tile-level fill, level schedule
+  CholSymbolic sym;
+  chol_symbolic(n_pose, n_hs, hs_row.data(), hs_col.data(), bpt, GPBA_TILE, getenv("GPBA_CHOL_ND_DEPTH") ? atoi(getenv("GPBA_CHOL_ND_DEPTH")) : -1,
+                getenv("GPBA_VERBOSE") != nullptr, sym);
+  NT = sym.NT; chol_parts = sym.n_parts; chol_doubles = sym.doubles;
+  chol_col_begin = sym.col_begin; chol_row_begin = sym.row_begin;
+  const std::vector<int>& col_rows = sym.col_rows;
+  const std::vector<int>& perm = sym.perm;
+  const std::vector<int64_t>& off = sym.tile_off;
+  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: n=%d NT=%d tiles=%lld (dense lower would be %d), %.1f MB\n", n, NT, (long long)(chol_doubles / GPBA_TILE), NT * (NT + 1) / 2, chol_doubles * 8 / 1e6);
+  CKR(d_chol_pos_used.upload(sym.pos_used, stream));
   CKR(d_tile_off.upload(off, stream)); CKR(d_col_begin.upload(chol_col_begin, stream)); CKR(d_col_rows.upload(col_rows, stream));
   CKR(d_chol_perm.upload(perm, stream));
   CKR(d_tiles.alloc((size_t)chol_doubles)); CKR(d_chol_work.alloc((size_t)NT * GPBA_NB));
   CKR(d_chol_dinv.alloc((size_t)NT * GPBA_NB * GPBA_NB)); CKR(d_chol_x.alloc((size_t)NT * GPBA_NB));
-  // row-wise view of the factor pattern for the backward substitution
-  chol_row_begin.assign(NT + 1, 0);
-  for (int r : col_rows) chol_row_begin[r + 1]++;
-  for (int i = 0; i < NT; ++i) chol_row_begin[i + 1] += chol_row_begin[i];
-  std::vector<int> row_cols(col_rows.size()), cur_r(chol_row_begin.begin(), chol_row_begin.end() - 1);
-  for (int k = 0; k < NT; ++k)
-    for (int e = chol_col_begin[k]; e < chol_col_begin[k + 1]; ++e) row_cols[cur_r[col_rows[e]]++] = k;
-  CKR(d_row_begin.upload(chol_row_begin, stream)); CKR(d_row_cols.upload(row_cols, stream));
-  // level schedule: column r depends on column j < r iff tile (r, j) is non-zero; columns of equal level are independent
-  std::vector<int> level(NT, 0);
-  int n_levels = 0;
-  for (int j = 0; j < NT; ++j) {
-    for (int e = chol_col_begin[j]; e < chol_col_begin[j + 1]; ++e) level[col_rows[e]] = std::max(level[col_rows[e]], level[j] + 1);
-    n_levels = std::max(n_levels, level[j] + 1);
-  }
+  CKR(d_row_begin.upload(chol_row_begin, stream)); CKR(d_row_cols.upload(sym.row_cols, stream));
+  const int n_levels = sym.n_levels;
+  const std::vector<int>& level = sym.level;
   std::vector<std::vector<int>> lvl_cols(n_levels);
   for (int k = 0; k < NT; ++k) lvl_cols[level[k]].push_back(k);
-  std::vector<int2> pan_tab, upd_tab, back_tab;
+  std::vector<int2> pan_tab, back_tab;
+  std::vector<int4> upd_tab;     // left-looking update: {column j, tile slot q (| GPBA_LU_SPLIT), klist begin, klist end}
+  std::vector<int> klist;        // finished columns k with L_ik != 0 and L_jk != 0, ascending, per tile (i, j)
   lvl_pan_begin.assign(n_levels + 1, 0); lvl_upd_begin.assign(n_levels + 1, 0); lvl_back_begin.assign(n_levels + 1, 0);
   lvl_ncols.assign(n_levels, 0);
   for (int l = 0; l < n_levels; ++l) {
@@ -1078,16 +995,33 @@ int Solver::build_cholesky_structure() {
     for (int k : lvl_cols[l]) {
       const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
       for (int q = 0; q <= nr; ++q) pan_tab.push_back(make_int2(k, q));
-      for (int a = 0; a < nr; ++a) for (int b = 0; b <= a; ++b) upd_tab.push_back(make_int2(k, (a << 16) | b));
+      // tile (i, k) of column k receives L_ic L_kc^T from every finished column c that touches both rows: the
+      // intersection of the two row patterns (both ascending)
+      for (int q = 0; q <= nr; ++q) {
+        const int i = q == 0 ? k : col_rows[chol_col_begin[k] + q - 1];
+        const int *pa = sym.row_cols.data() + chol_row_begin[i], *pae = sym.row_cols.data() + chol_row_begin[i + 1];
+        const int *pb = sym.row_cols.data() + chol_row_begin[k], *pbe = sym.row_cols.data() + chol_row_begin[k + 1];
+        const int kb = (int)klist.size();
+        while (pa < pae && pb < pbe) { if (*pa < *pb) ++pa; else if (*pb < *pa) ++pb; else { klist.push_back(*pa); ++pa; ++pb; } }
+        const int cnt = (int)klist.size() - kb;
+        if (cnt == 0) continue;
+        const int nch = (cnt + GPBA_LU_CHUNK - 1) / GPBA_LU_CHUNK;
+        for (int c = 0; c < nch; ++c)
+          upd_tab.push_back(make_int4(k, q, kb + (int)((int64_t)cnt * c / nch), kb + (int)((int64_t)cnt * (c + 1) / nch)));
+      }
       const int nrow = chol_row_begin[k + 1] - chol_row_begin[k];
       for (int q = 0; q <= nrow; ++q) back_tab.push_back(make_int2(k, q));
       if (nr >= 65536) { g_err = "tile column with more than 65535 rows"; return GPBA_ERR_INVALID; }
     }
     lvl_pan_begin[l + 1] = (int)pan_tab.size(); lvl_upd_begin[l + 1] = (int)upd_tab.size(); lvl_back_begin[l + 1] = (int)back_tab.size();
   }
-  if (upd_tab.empty()) upd_tab.push_back(make_int2(0, 0));
+  chol_products = (int64_t)klist.size(); chol_update_ctas = (int64_t)upd_tab.size();
+  if (upd_tab.empty()) upd_tab.push_back(make_int4(0, 0, 0, 0));
+  if (klist.empty()) klist.push_back(0);
   CKR(d_pan_tab.upload(pan_tab, stream)); CKR(d_upd_tab.upload(upd_tab, stream)); CKR(d_back_tab.upload(back_tab, stream));
-  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns, %zu panel CTAs, %zu update CTAs\n", chol_parts, n_levels, NT, pan_tab.size(), upd_tab.size());
+  CKR(d_klist.upload(klist, stream));
+  CKR(d_lu_counter.alloc((size_t)std::max(n_levels, 1)));
+  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns, %zu panel CTAs, %zu update CTAs for %zu tile products\n", chol_parts, n_levels, NT, pan_tab.size(), upd_tab.size(), klist.size());
   CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
   if (chol_graph) { cudaGraphExecDestroy(chol_graph); chol_graph = nullptr; }
   if (chol_back_graph) { cudaGraphExecDestroy(chol_back_graph); chol_back_graph = nullptr; }
@@ -1097,6 +1031,16 @@ int Solver::build_cholesky_structure() {
 // The factorization of one structure is a fixed launch sequence (2 kernels per tile column); replaying it as a
 // CUDA graph removes the per-launch host cost from the critical path of every LM trial.
 // launch with the programmatic-stream-serialization attribute (PDL edge when captured into a graph)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_smem(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -1129,30 +1073,32 @@ int Solver::capture_cholesky_graph() {
   CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
   int launches = 0;
   cudaError_t e = cudaMemsetAsync(d_tiles.p, 0, sizeof(double) * (size_t)chol_doubles, stream);
+  // chunk counters of the left-looking update: reset by every replay of the graph (a memset node in front of the kernels)
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_lu_counter.p, 0, sizeof(int) * (size_t)std::max<size_t>(lvl_ncols.size(), 1), stream);
   if (e == cudaSuccess) {
     const int64_t work = std::max((int64_t)n_hs * 144, (int64_t)NT * GPBA_NB);
     k_chol_load<<<(int)std::min((work + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(C, n_hs, d_hs_row.p, d_hs_col.p, d_hs.p, bs);
     ++launches;
     const int n_levels = (int)lvl_ncols.size();
-    for (int l = 0; l < n_levels; ++l) {
+    const size_t lu_smem = (size_t)GPBA_LU_STAGES * (2 * GPBA_TILE_BYTES + GPBA_NB * 8);
+    e = cudaFuncSetAttribute(k_chol_lupdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_smem);
+    int lu_ctas = 148;
+    cudaDeviceGetAttribute(&lu_ctas, cudaDevAttrMultiProcessorCount, device);
+    for (int l = 0; l < n_levels && e == cudaSuccess; ++l) {
       const int npan = lvl_pan_begin[l + 1] - lvl_pan_begin[l], nupd = lvl_upd_begin[l + 1] - lvl_upd_begin[l];
-      const bool shared = lvl_ncols[l] > 1;   // several columns may update one tile: accumulate atomically
       const int2* pt = d_pan_tab.p + lvl_pan_begin[l];
-      const int2* ut = d_upd_tab.p + lvl_upd_begin[l];
+      const int4* ut = d_upd_tab.p + lvl_upd_begin[l];
+      // left-looking: the level's tiles first receive the products of all finished columns, then the panel step
+      if (nupd > 0) {
+        const int grid = std::min(nupd, lu_ctas);   // persistent CTAs, one per SM, drawing chunks from the level's counter
+        if (use_pdl) e = launch_pdl_smem(k_chol_lupdate, grid, 128, lu_smem, stream, C, ut, nupd, (const int*)d_klist.p, d_lu_counter.p + l);
+        else k_chol_lupdate<<<grid, 128, lu_smem, stream>>>(C, ut, nupd, d_klist.p, d_lu_counter.p + l);
+        ++launches;
+        if (e != cudaSuccess) break;
+      }
       if (use_pdl && l > 0) e = launch_pdl(k_chol_panel, npan, GPBA_PANEL_THREADS, stream, C, pt, d_fail.p);
       else k_chol_panel<<<npan, GPBA_PANEL_THREADS, 0, stream>>>(C, pt, d_fail.p);
       ++launches;
-      if (nupd > 0 && e == cudaSuccess) {
-        if (shared) {
-          if (use_pdl) e = launch_pdl(k_chol_update<true>, nupd, 128, stream, C, ut);
-          else k_chol_update<true><<<nupd, 128, 0, stream>>>(C, ut);
-        } else {
-          if (use_pdl) e = launch_pdl(k_chol_update<false>, nupd, 128, stream, C, ut);
-          else k_chol_update<false><<<nupd, 128, 0, stream>>>(C, ut);
-        }
-        ++launches;
-      }
-      if (e != cudaSuccess) break;
     }
     if (e == cudaSuccess) e = cudaGetLastError();
   }
@@ -1321,8 +1267,9 @@ int Solver::solve(double lambda) {
     CK(cudaMemsetAsync(d_C.p, 0, sizeof(double) * (size_t)n_rp * GPBA_RP_STRIDE, stream));
     CK(cudaMemsetAsync(d_fail.p + 1, 0, sizeof(int), stream));
     static const int pairs_ctas_per_sm = getenv("GPBA_PAIRS_CTAS") ? atoi(getenv("GPBA_PAIRS_CTAS")) : 16;
+    static const int pairs_batch = getenv("GPBA_PAIRS_BATCH") ? std::max(1, atoi(getenv("GPBA_PAIRS_BATCH"))) : 32;
     k_schur_pairs<<<std::min((n_items + 3) / 4, 148 * pairs_ctas_per_sm), 128, 0, stream>>>(n_items, d_item_rp.p, d_item_begin.p, d_item_end.p, d_item_flags.p,
-                                                                             d_pairs.p, d_o_lm.p, d_U.p, d_ptL.p, d_C.p, d_fail.p + 1);
+                                                                             d_pairs.p, d_o_lm.p, d_U.p, d_ptL.p, d_C.p, d_fail.p + 1, pairs_batch);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -2019,9 +1966,23 @@ int gpba_schur_stats(gpba_handle* h, int64_t out[4]) {
   out[0] = S(h).n_pairs; out[1] = S(h).n_rp; out[2] = S(h).n_items; out[3] = S(h).n_con;
   return GPBA_OK;
 }
-int gpba_solver_stats(gpba_handle* h, int64_t out[4]) {
+int gpba_solver_stats(gpba_handle* h, int64_t out[6]) {
   NEED_STRUCT(h);
-  out[0] = S(h).NT; out[1] = (int64_t)S(h).lvl_ncols.size(); out[2] = S(h).chol_parts; out[3] = S(h).chol_doubles / (GPBA_NB * GPBA_NB);
+  out[0] = S(h).NT; out[1] = (int64_t)S(h).lvl_ncols.size(); out[2] = S(h).chol_parts; out[3] = S(h).chol_doubles / GPBA_TILE;
+  out[4] = S(h).chol_products; out[5] = S(h).chol_update_ctas;
+  return GPBA_OK;
+}
+int gpba_symbolic_analyze(int32_t n_pose, int32_t n_hs, const int32_t* hs_row, const int32_t* hs_col, int32_t nd_depth,
+                          int32_t* perm_out, int64_t out[5]) {
+  if (n_pose < 0 || n_hs < 0 || (n_hs > 0 && (!hs_row || !hs_col)) || !out) { g_err = "invalid argument"; return GPBA_ERR_INVALID; }
+  for (int k = 0; k < n_hs; ++k)
+    if (hs_row[k] < 0 || hs_col[k] < hs_row[k] || hs_col[k] >= n_pose) { g_err = "block index out of range (upper pattern expected)"; return GPBA_ERR_INVALID; }
+  CholSymbolic sym;
+  chol_symbolic(n_pose, n_hs, hs_row, hs_col, GPBA_NB / 12, GPBA_TILE, nd_depth, false, sym);
+  int64_t pairs = 0;
+  for (int k = 0; k < sym.NT; ++k) { const int64_t nr = sym.col_begin[k + 1] - sym.col_begin[k]; pairs += nr * (nr + 1) / 2; }
+  out[0] = sym.NT; out[1] = sym.n_levels; out[2] = sym.n_parts; out[3] = sym.doubles / GPBA_TILE; out[4] = pairs;
+  if (perm_out) for (int i = 0; i < n_pose; ++i) perm_out[i] = sym.perm[i];
   return GPBA_OK;
 }
 int gpba_set_profiling(gpba_handle* h, int enabled) { NEED(h); S(h).collect_events(); S(h).profiling = enabled != 0; return GPBA_OK; }

@@ -593,17 +593,28 @@ __global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __r
                                                      const unsigned char* __restrict__ item_flags /* 1: diagonal, 2: atomic */,
                                                      const unsigned long long* __restrict__ pairs, const int* __restrict__ o_lm,
                                                      const double* __restrict__ U, const double* __restrict__ ptL,
-                                                     double* __restrict__ C, int* __restrict__ next_item) {
+                                                     double* __restrict__ C, int* __restrict__ next_item, int batch) {
   const int lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
-  // items are handed out in list order through a counter: the warps in flight then always work on one tight window
+  __shared__ int s_base, s_taken;
+  // Items are handed out in list order through a counter: the warps in flight then always work on one tight window
   // of the (landmark chunk, record pair) list, whose U rows stay L2 resident.  (With a static grid-stride assignment
   // the warps drift apart -- item lengths differ 100x -- and every L1 miss went to HBM: ncu lts hit rate 20 %.)
+  // A CTA takes `batch` CONSECUTIVE items at a time and its warps share them: the list is sorted by (chunk, first record,
+  // second record), so the items of a batch mostly pair the same first-side rows with different partners, and those rows
+  // are then served by this SM's L1 instead of crossing the L2 -> SM fabric once per pair (round 1: 9.0 GB per launch).
   for (;;) {
+    __syncthreads();   // the previous batch is consumed
+    if (threadIdx.x == 0) { s_base = atomicAdd(next_item, batch); s_taken = 0; }
+    __syncthreads();
+    const int base = s_base;
+    if (base >= n_items) break;
+   for (;;) {
     int it = 0;
-    if (lane == 0) it = atomicAdd(next_item, 1);
+    if (lane == 0) it = atomicAdd(&s_taken, 1);
     it = __shfl_sync(0xffffffffu, it, 0);
-    if (it >= n_items) break;
+    if (it >= batch || base + it >= n_items) break;
+    it += base;
     const int64_t pb = item_begin[it];
     const int np = (int)(item_end[it] - pb);
     const unsigned fl = item_flags[it];
@@ -640,6 +651,7 @@ __global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __r
       if (fl & 2u) { atomicAdd(out, c0); atomicAdd(out + 1, c1); }
       else *reinterpret_cast<double2*>(out) = make_double2(c0, c1);
     }
+   }
   }
 }
 

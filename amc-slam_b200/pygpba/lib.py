@@ -21,7 +21,7 @@ SYMBOLS = [
     "gpba_get_hschur", "gpba_get_hll", "gpba_get_hpl", "gpba_oplus", "gpba_push", "gpba_pop", "gpba_discard_top",
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
-    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_pose_optimize", "gpba_vel_ransac",
+    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_symbolic_analyze", "gpba_pose_optimize", "gpba_vel_ransac",
 ]
 
 
@@ -57,6 +57,16 @@ def default_lm_params():
     p = LmParams()
     lib().gpba_default_lm_params(C.byref(p))
     return p
+
+
+def symbolic_analyze(n_pose, hs_row, hs_col, nd_depth=-1):
+    """Host-only symbolic phase of the reduced-system factorization (no device needed): (perm, stats dict)."""
+    r = np.ascontiguousarray(hs_row, np.int32); c = np.ascontiguousarray(hs_col, np.int32)
+    perm = np.zeros(n_pose, np.int32); out = (C.c_int64 * 5)()
+    rc = lib().gpba_symbolic_analyze(C.c_int32(n_pose), C.c_int32(len(r)), _p(r), _p(c), C.c_int32(nd_depth), _p(perm), out)
+    if rc != 0:
+        raise GpbaError(f"gpba_symbolic_analyze: {lib().gpba_last_error().decode()}")
+    return perm, dict(tile_columns=out[0], levels=out[1], parts=out[2], tiles=out[3], update_pairs=out[4])
 
 
 def nccl_unique_id():
@@ -240,9 +250,9 @@ class GpBa:
         return dict(n_obs_pairs=a[0], n_record_pairs=a[1], n_items=a[2], n_contrib=a[3])
 
     def solver_stats(self):
-        a = (C.c_int64 * 4)()
+        a = (C.c_int64 * 6)()
         self._ck(self.L.gpba_solver_stats(self.h, a), "gpba_solver_stats")
-        return dict(tile_columns=a[0], levels=a[1], partitions=a[2], tiles=a[3])
+        return dict(tile_columns=a[0], levels=a[1], parts=a[2], tiles=a[3], tile_products=a[4], update_ctas=a[5])
 
     def stream(self):
         return self.L.gpba_get_stream(self.h)

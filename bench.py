@@ -11,9 +11,13 @@ reduced camera systems are summed with ncclAllReduce.
 
 value   = observations x executed LM iterations / device time, problem + structure already resident in HBM.
 e2e     = same metric through the C ABI from host buffers: gpba_create (H2D) + structure + optimize +
-          gpba_download_state (D2H) + destroy inside the timed region.
---impl reference times the CPU restatement of the reference's g2o path (oracle/, all host cores) on a bounded
-sample of the same workload.
+          gpba_download_state (D2H) + destroy inside the timed region (median of >= 10 calls; the host arrays are
+          page-locked with cudaHostRegister BEFORE the timed region, as a caller that reuses its buffers would).
+--impl reference times the CPU restatement of the reference's g2o path (oracle/, all host cores, OpenMP over the loops
+g2o annotates) on the SAME workload (same generator, same sizes), its structure built before the timed region like the
+device arm's, 2 LM iterations per step; per-stage seconds are printed under the G2OBatchStatistics names.
+Both arms print the same `config` object.  The device arm also compares its result with the committed oracle fixture of the
+workload (tests/golden/baseline_<name>.npz) and prints `parity_check` -- at every N, so the sharded path is checked too.
 """
 import argparse
 import json
@@ -34,12 +38,31 @@ WORKLOADS = {
     "c4": "post-loop-closure global GP-BA: 5 async cameras, 1k keyframes, 500k points, ~5M observations",
     "c5": "10 km global GP-BA: 5 async cameras, 10k keyframes, 2M points, ~20M observations",
 }
-# bounded CPU sample of each workload (same generator family, fewer keyframes / points)
+# bounded CPU sample of each workload for the 1-core `cpu_baseline` leg of the device arm (same generator family, fewer
+# keyframes / points); the reference arm (--impl reference) runs the full workload
 CPU_SAMPLE = {
     "c2": dict(n_kf=30, n_pt=6000), "c3": dict(n_kf=50, n_pt=6000),
     "c4": dict(n_kf=120, n_pt=60000), "c5": dict(n_kf=120, n_pt=60000),
 }
 LM_ITERS = 10
+REF_LM_ITERS = 2          # LM iterations per step of the reference arm (">= 2 iterations")
+L2_NOTE = "inputs larger than L2 (per LM iteration the kernels stream ~2.5 GB of observation / W / U arrays through a 126 MB L2), no flush"
+
+
+def workload_config(name, P):
+    """The `config` object: the workload only, identical in both arms."""
+    return {"workload": WORKLOADS[name], "name": name, "n_obs": int(P.n_obs), "n_pt": int(P.n_pt), "n_kf": int(P.n_kf),
+            "n_cam": int(P.n_cam), "mode": P.meta.get("mode"), "seed": P.meta.get("seed"), "l2": L2_NOTE}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 KERNEL_OF_STAGE = {"residuals": "k_residual", "lin_landmarks": "k_lin_points", "lin_poses": "k_lin_records", "schur_prepare": "k_schur_prep",
                    "schur_pairs": "k_schur_pairs", "schur_expand": "k_schur_expand", "backsub_update": "k_backsub"}
 
@@ -150,46 +173,85 @@ def algorithmic_bytes(info, sch):
 
 def measured_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
-    (profiles/r01_dram_traffic.json); None when no capture exists for this workload / kernel."""
-    p = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    (profiles/r02_dram_traffic.json, else round 1's); None when no capture exists for this workload / kernel."""
+    for f in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", f)))[workload][kernel]["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
+
+
+def fp64_peaks():
+    """Measured FP64 peaks of this pool's B200 (tools/fp64_peak.cu, run under gpurun, committed as
+    profiles/r02_fp64_peaks.json): DFMA and DMMA (mma.sync m8n8k4.f64) TFLOP/s.  Fallback: nominal 40 TFLOP/s."""
     try:
-        return json.load(open(p))[workload][kernel]["dram_bytes_per_launch"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_fp64_peaks.json")))
+        return float(d["fp64_tensor_tflops"]), float(d["dfma_tflops"]), "profiles/r02_fp64_peaks.json (tools/fp64_peak.cu, of measured)"
     except Exception:
+        return 40.0, 40.0, "nominal B200 FP64 (no measurement committed: of nominal)"
+
+
+def parity_check(workload, trace_summary, state):
+    """Compare the last timed step with the committed oracle fixture of this workload (north-star tolerances)."""
+    from pygpba import fixtures as FX
+    if not os.path.exists(FX.fixture_path(workload)):
         return None
+    F = FX.load(workload)
+    if int(F["tr_n_iters"].shape[0]) != 1:       # a rejection-round fixture (C3): covered by the -m gpu tests, not by optimize()
+        return None
+    r = FX.compare(F, [trace_summary], state)
+    return {"fixture": f"tests/golden/baseline_{workload}.npz (CPU oracle, {int(F['oracle_threads'])} threads, {float(F['oracle_seconds']):.0f} s)",
+            "ok": r["ok"], "iters_equal": r["iters_equal"], "trials_equal": r["trials_equal"], "cost_rel": r["cost_rel"],
+            "lambda_rel": r["lambda_rel"], "pos_m": r.get("pos_m"), "rot_rad": r.get("rot_rad"), "vel": r.get("vel"),
+            "pt_m_sampled": r.get("pt_m"), "tolerance": r["tolerance"]}
 
 
 def run_reference(args):
-    """CPU arm: the oracle (C++ restatement of the reference's g2o path) on the host cores, bounded sample."""
+    """CPU arm: the oracle (C++ restatement of the reference's g2o path) on the host cores, on the SAME workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
+    from pygpba.problem import SOLVER_SPARSE_CHOL
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    sample = CPU_SAMPLE[args.workload]
-    P = load_problem(args.workload, **sample)
-    iters = 2
+    P = load_problem(args.workload)
+    if P.meta.get("mode") == "global":
+        P.linear_solver = SOLVER_SPARSE_CHOL      # LinearSolverEigen (src/Optimizer.cc:70); local windows keep LinearSolverDense (:841)
+    o = oracle_py.Oracle(P, threads=cores)
+    state0 = (P.kf_pose.copy(), P.kf_vel.copy(), P.pt_xyz.copy())
     times, its = [], 0
+    stats = None
     for s in range(args.warmup + args.steps):
-        o = oracle_py.Oracle(P, threads=cores)
+        o.reset_state(*state0)
+        o.build_structure()                       # outside the timed region, like the device arm's `value`
+        if s == args.warmup:
+            o.batch_stats(reset=True)
         t = time.perf_counter()
-        tr = o.optimize(iters)
+        tr = o.optimize(REF_LM_ITERS)
         dt = time.perf_counter() - t
         if s >= args.warmup:
             times.append(dt); its += tr.n_iters
-        o.close()
+    stats = o.batch_stats()
+    o.close()
     total = sum(times)
     value = P.n_obs * its / total
-    desc = f"{args.workload} family, {sample['n_kf']} keyframes, {P.n_pt} points, {P.n_obs} observations, {iters} LM iterations per step"
+    desc = (f"full {args.workload} workload ({P.n_kf} keyframes, {P.n_pt} points, {P.n_obs} observations), {REF_LM_ITERS} LM iterations per step, "
+            f"structure prebuilt, {cores} OpenMP threads on {cpu_model()}")
     out = {
         "impl": "reference", "metric": "gpba_observations_per_sec", "value": value, "unit": "obs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "lm_iters_per_sec": its / total,
-        "config": {"workload": WORKLOADS[args.workload], "name": args.workload, "sample": desc},
+        "lm_iters_per_sec": its / total, "ms_per_lm_iter": 1e3 * total / max(its, 1),
+        "config": workload_config(args.workload, P),
         "cpu_baseline": {"value": value, "unit": "obs/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "host": {"nproc": cores, "cpu_model": cpu_model()},
+        # seconds per stage over the timed steps, field names of G2OBatchStatistics (g2o/core/batch_stats.h:39-78)
+        "g2o_batch_stats_s_per_step": {k: round(v / max(args.steps, 1), 4) for k, v in stats.items()},
+        "lm_iters_per_step": REF_LM_ITERS,
     }
     emit(out)
     return 0
@@ -259,6 +321,12 @@ def run_gpba(args):
     clocks = sampler.stop()
     stages = g.stage_stats(reset=True)
     g.set_profiling(False)
+    solver = g.solver_stats()
+    parity = None
+    try:
+        parity = parity_check(args.workload, last, g.state()) if last else None
+    except Exception as ex:     # never lose the headline line to the checker
+        parity = {"ok": False, "error": repr(ex)}
     t_max = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
@@ -273,8 +341,9 @@ def run_gpba(args):
     cand = {}
     for k, nbytes in ab.items():
         st = stages[k]
-        # number of kernel launches of the stage's main kernel in the timed region
-        n_main = {"residuals": trials_done + iters_done + args.steps, "lin_landmarks": iters_done, "lin_poses": iters_done,
+        # number of launches of the stage's main kernel in the timed region (the library counts every launch of a stage;
+        # a residual pass is 4 launches: K1 + priors + reduce + pack, a back-substitution 4, the others 1 main kernel)
+        n_main = {"residuals": st["launches"] // 4, "lin_landmarks": iters_done, "lin_poses": iters_done,
                   "schur_prepare": trials_done, "schur_pairs": trials_done, "schur_expand": trials_done,
                   "backsub_update": trials_done}[k]
         if n_main > 0 and st["ms"] > 0:
@@ -285,6 +354,21 @@ def run_gpba(args):
         roof = {"bound": "hbm", "kernel": KERNEL_OF_STAGE[dom], "stage": dom, "achieved": cand[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": cand[dom]["gbs"] / peak, "traffic": measured_traffic(args.workload, KERNEL_OF_STAGE[dom]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": cand[dom]["bytes_per_launch"], "ms_per_launch": cand[dom]["ms_per_launch"]}
+    # ---------------- roofline of the reduced-system factorization (FP64 tensor pipe, DMMA)
+    tpeak, dfma_peak, tpeak_src = fp64_peaks()
+    roof_f = None
+    if trials_done > 0 and stages["factorize"]["ms"] > 0 and not args.pcg:
+        NB = 48
+        tiles_below = solver["tiles"] - solver["tile_columns"]
+        # left-looking products 2*48^3 each (the diagonal ones are full-tile syrk), one triangular solve 48^3 per tile below the
+        # diagonal, one 48^3/3 potrf + one 48^3/3 inverse per tile column
+        flops = solver["tile_products"] * 2.0 * NB ** 3 + tiles_below * float(NB ** 3) + solver["tile_columns"] * (2.0 / 3.0) * NB ** 3
+        ms = stages["factorize"]["ms"] / trials_done
+        roof_f = {"bound": "fp64_tensor", "kernel": "k_chol_lupdate + k_chol_panel (CUDA graph of one factorization)", "achieved": flops / (ms * 1e-3) / 1e12,
+                  "peak": tpeak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / tpeak, "peak_source": tpeak_src, "dfma_peak_tflops": dfma_peak,
+                  "algorithmic_flops_per_factorization": flops, "ms_per_factorization": ms, "levels": solver["levels"],
+                  "us_per_level": 1e3 * ms / max(solver["levels"], 1),
+                  "note": "bound by the dependency chain of tile-column levels (one 48-pivot potrf + two kernel boundaries each), not by the pipe"}
     g.close()
 
     # ---------------- end-to-end arm through the C ABI from host buffers: `e2e`
@@ -293,8 +377,9 @@ def run_gpba(args):
     for a in (kp, kv, pt):
         if a.nbytes >= 1 << 16 and int(cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
             pinned.append(a)
-    n_e2e = max(1, min(args.steps, 3))
-    for s in range(1 + n_e2e):
+    n_e2e = max(10, min(args.steps, 20))
+    e2e_times, e2e_its = [], 0
+    for s in range(2 + n_e2e):
         barrier()
         t = time.perf_counter()
         h = gl.GpBa(P, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id, async_upload=True)
@@ -303,13 +388,14 @@ def run_gpba(args):
         h.close()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
-        if s >= 1:
-            e2e_ms += dt * 1e3; e2e_iters += tr.n_iters
-    t_max = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        if s >= 2:
+            e2e_times.append(dt * 1e3); e2e_its = tr.n_iters
+    t_all = torch.tensor(e2e_times, dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t_max.item())
-    e2e_value = n_obs_total * e2e_iters / (e2e_ms * 1e-3)
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)       # per call: the slowest rank
+    e2e_times = [float(x) for x in t_all.cpu().tolist()]
+    e2e_ms = float(np.median(e2e_times))                    # median call
+    e2e_value = n_obs_total * e2e_its / (e2e_ms * 1e-3)
     for a in pinned:
         cudart.cudaHostUnregister(a.ctypes.data)
 
@@ -343,16 +429,19 @@ def run_gpba(args):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "lm_iters_per_sec": iters_done / (total_ms * 1e-3), "ms_per_lm_iter": total_ms / max(iters_done, 1),
-            "config": {"workload": WORKLOADS[args.workload], "name": args.workload, "n_obs": int(P.n_obs), "n_pt": int(P.n_pt),
-                       "n_kf": int(P.n_kf), "lm_iters_executed_per_step": iters_done // max(args.steps, 1),
-                       "lm_trials_per_step": trials_done // max(args.steps, 1),
-                       "linear_solver": "pcg" if args.pcg else "tile_cholesky_dmma", "parallelism": f"landmark-sharded x{world}",
-                       "l2": "inputs larger than L2 (per LM iteration the kernels stream ~2.5 GB of observation / W / U arrays through a 126 MB L2), no flush",
-                       "final_chi2": last["chi2_after"][last["n_iters"] - 1] if last else None},
+            "config": workload_config(args.workload, P),
+            "run": {"lm_iters_executed_per_step": iters_done // max(args.steps, 1), "lm_trials_per_step": trials_done // max(args.steps, 1),
+                    "linear_solver": "pcg" if args.pcg else "tile_cholesky_dmma", "parallelism": f"landmark-sharded x{world}",
+                    "final_chi2": last["chi2_after"][last["n_iters"] - 1] if last else None, "solver": solver},
             "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": int(P.input_bytes()),
-                    "d2h_bytes_per_step": int(kp.nbytes + kv.nbytes + pt.nbytes), "ms_per_step": e2e_ms / n_e2e},
+                    "d2h_bytes_per_step": int(kp.nbytes + kv.nbytes + pt.nbytes), "ms_per_step": e2e_ms,
+                    "calls": n_e2e, "statistic": "median call (max over ranks per call)", "ms_min": min(e2e_times), "ms_max": max(e2e_times),
+                    "host_buffers": "page-locked with cudaHostRegister before the timed region; gpba_create(GPBA_CREATE_ASYNC_UPLOAD) + "
+                                    "gpba_optimize + gpba_download_state + gpba_destroy inside it"},
             "gpu_launches": launches,
+            "parity_check": parity,
             "roofline": roof,
+            "roofline_factorize": roof_f,
             "stages_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in stages.items()},
             "stage_gbs": {k: round(v["gbs"], 1) for k, v in cand.items()},
             "schur_sizes": sch,

@@ -334,9 +334,18 @@ int gpba_set_profiling(gpba_handle* h, int enabled);
  * out[3] (record pair -> Hschur block) contributions of K4c. */
 int gpba_schur_stats(gpba_handle* h, int64_t out[4]);
 /* Shape of the reduced-system factorization (the analyzePattern of linear_solver_eigen.h:147-201): out[0] tile columns,
- * out[1] levels of the schedule (independent tile columns share a level), out[2] partitions of the nested-dissection
- * order (1 = plain banded order), out[3] non-zero 48x48 tiles of the factor. */
-int gpba_solver_stats(gpba_handle* h, int64_t out[4]);
+ * out[1] levels of the schedule (independent tile columns share a level), out[2] parts (leaves + separators) of the
+ * nested-dissection order (1 = plain banded order), out[3] non-zero 48x48 tiles of the factor, out[4] 48x48x48 tile
+ * products of the left-looking update (x 2 * 48^3 = its flops), out[5] CTAs of the update launches. */
+int gpba_solver_stats(gpba_handle* h, int64_t out[6]);
+/* The symbolic phase alone, on the host (no device needed): nested-dissection order of the pose blocks by BFS level
+ * structures, tile-level symbolic factorization and level schedule, for an upper block pattern (row <= col) such as the one
+ * gpba_get_hschur_pattern returns.  nd_depth < 0: the default (8 for >= 256 pose blocks, else the plain banded order);
+ * 0 switches the dissection off.  perm_out[b] (optional) = position of pose block b, in pose-block slots: every part of
+ * the order starts on a tile boundary, so positions may skip slots.  out[0] tile columns, out[1] levels, out[2] parts,
+ * out[3] non-zero tiles of the factor, out[4] tile pairs of the trailing updates (x 2 * 48^3 = their flops). */
+int gpba_symbolic_analyze(int32_t n_pose, int32_t n_hs, const int32_t* hs_row, const int32_t* hs_col, int32_t nd_depth,
+                          int32_t* perm_out, int64_t out[5]);
 /* cudaStream_t every kernel of this handle is launched on (for CUDA-event timing by the caller). */
 void* gpba_get_stream(gpba_handle* h);
 /* Re-upload estimates only (same structure): lets a benchmark repeat optimize() from the same start. */

@@ -1000,6 +1000,20 @@ void* oracle_create(const gpba_problem* p) {
   return o;
 }
 void oracle_destroy(void* h) { delete ORA(h); }
+// Re-load the estimates only (same graph): lets the benchmark repeat optimize() from the same start on one instance.
+void oracle_reset_state(void* h, const double* kf_pose, const double* kf_vel, const double* pt_xyz) {
+  Oracle* o = ORA(h);
+  for (int k = 0; k < o->n_kf; ++k) {
+    if (kf_pose) {
+      const double* q = kf_pose + 7 * k;
+      o->kf[k].Twb.q = {q[0], q[1], q[2], q[3]};
+      o->kf[k].Twb.t[0] = q[4]; o->kf[k].Twb.t[1] = q[5]; o->kf[k].Twb.t[2] = q[6];
+    }
+    if (kf_vel) for (int i = 0; i < 6; ++i) o->kf[k].vel[i] = kf_vel[6 * k + i];
+  }
+  if (pt_xyz) for (int i = 0; i < o->n_pt; ++i) for (int c = 0; c < 3; ++c) o->pt[i][c] = pt_xyz[3 * (size_t)i + c];
+  o->stack.clear();
+}
 void oracle_set_threads(void* h, int n) { ORA(h)->threads = n < 1 ? 1 : n; }
 // seconds per stage since the last reset: timeResiduals, timeQuadraticForm (linearize + quadratic form), timeSchurComplement,
 // timeLinearSolver, timeUpdate -- the G2OBatchStatistics fields (g2o/core/batch_stats.h:39-78)

@@ -62,6 +62,10 @@ class Oracle:
         except Exception:
             pass
 
+    def reset_state(self, kf_pose, kf_vel, pt_xyz):
+        self.L.oracle_reset_state(self.h, _p(np.ascontiguousarray(kf_pose, np.float64)), _p(np.ascontiguousarray(kf_vel, np.float64)),
+                                  _p(np.ascontiguousarray(pt_xyz, np.float64)))
+
     def batch_stats(self, reset=False):
         """seconds per stage under the G2OBatchStatistics names (g2o/core/batch_stats.h:39-78)"""
         a = (C.c_double * 5)()

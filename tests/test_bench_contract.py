@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    # C2 keeps the CPU suite short; the driver runs the default workload (C4, all ~5M observations) on the GPU box's host
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "c2"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -23,6 +24,13 @@ def test_reference_arm_prints_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert "workload" in d["config"]
+    # the reference arm runs the workload itself, not a sample: the config object is the one the device arm prints
+    sys.path.insert(0, ROOT)
+    import bench
+    P = bench.load_problem("c2")
+    assert d["config"] == bench.workload_config("c2", P) and d["config"]["n_obs"] == P.n_obs
+    assert set(d["g2o_batch_stats_s_per_step"]) == {"timeResiduals", "timeQuadraticForm", "timeSchurComplement", "timeLinearSolver", "timeUpdate"}
+    assert d["host"]["nproc"] == cb["cores"] and d["lm_iters_per_step"] == 2
 
 
 def test_product_arm_needs_a_gpu():

@@ -184,19 +184,26 @@ def test_stereo_gp_edges(G, oracle_mod):
 
 
 def test_nested_dissection_order_matches_oracle(G, oracle_mod, monkeypatch):
-    """Long trajectory: the tile Cholesky switches to the nested-dissection order with level-scheduled (concurrent,
-    atomically accumulated) tile columns; the LM run must still match the oracle's sequential factorization."""
-    P = synth.make_problem("tiny_global", n_kf=200, n_pt=2500, obs_per_pt=6, seed=41)
+    """Long trajectory: the tile Cholesky orders the pose blocks by nested dissection, the independent parts share levels
+    of the schedule (concurrent, atomically accumulated tile columns); the LM run must still match the oracle's sequential
+    factorization, whatever the depth of the dissection."""
+    P = synth.make_problem("tiny_global", n_kf=400, n_pt=12000, obs_per_pt=8, seed=41)   # well-posed: the oracle moves 4e-9 m under an edge-order permutation
     ref = oracle_mod.Oracle(P)
     tc = ref.optimize(3)
-    for parts in ("1", "4"):
-        monkeypatch.setenv("GPBA_CHOL_PARTS", parts)
+    seen = {}
+    for depth in ("0", "1", "3", None):
+        if depth is None:
+            monkeypatch.delenv("GPBA_CHOL_ND_DEPTH", raising=False)
+        else:
+            monkeypatch.setenv("GPBA_CHOL_ND_DEPTH", depth)
         g = G.GpBa(P)
         assert_trace_equal(g.optimize(3), tc)
         assert_state_close(g.state(), ref.state())
-        st = g.solver_stats()
-        assert st["partitions"] == int(parts)
-        assert (st["levels"] < st["tile_columns"]) == (parts != "1")
+        seen[depth] = g.solver_stats()
+    assert seen["0"]["parts"] == 1 and seen["0"]["levels"] == seen["0"]["tile_columns"]
+    assert seen["1"]["parts"] == 3 and seen["1"]["levels"] < seen["0"]["levels"]
+    assert seen["3"]["levels"] < seen["1"]["levels"]
+    assert seen[None]["levels"] <= seen["3"]["levels"]          # the default dissects a 400-keyframe system
 
 
 def test_edge_cases(G, oracle_mod):
