@@ -328,73 +328,81 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, c
 // patterns).  The host cuts the lists into CHUNKS of <= GPBA_LU_CHUNK products, table entry {j, q, kb, ke} (q = 0: the
 // diagonal tile, q > 0: the q-th non-zero row below it).  One SM needs 0.88 us of DMMA issue per 48^3 product at the
 // measured 37 TFLOP/s, so what matters is that all SMs stay busy for the whole launch: PERSISTENT CTAs (one per SM) draw
-// chunks from an atomic counter, and the operand stream never drains -- thread 0 is the producer and keeps GPBA_LU_STAGES
-// operand pairs in flight with cp.async.bulk (one bulk copy per tile, completing on the stage's mbarrier) ACROSS chunk
-// boundaries, a small descriptor per stage telling the consumers where a chunk begins and ends.  The four warps consume a
-// stage when its barrier flips -- each owns a 24 x 24 corner = 3 x 3 DMMA tiles (9 independent accumulator chains) -- and
-// hand it back at a CTA barrier.  A chunk's partial sum leaves with red.global.add.f64 (fire and forget: no read of the
-// target tile on the way; several chunks, possibly on different SMs, may feed one tile).
+// chunks from an atomic counter, and the operand stream never drains: a PRODUCER WARP (one thread) walks the chunk
+// stream and keeps GPBA_LU_STAGES operand pairs in flight with cp.async.bulk (one bulk copy per tile, completing on the
+// stage's `full` mbarrier) ACROSS chunk boundaries -- its index loads and the atomic never sit on the consumers' path -- and
+// leaves a small descriptor per stage telling the consumers where a chunk begins and ends and where it goes.  Four
+// CONSUMER WARPS take a stage when its barrier flips -- each owns a 24 x 24 corner = 3 x 3 DMMA tiles (9 independent
+// accumulator chains) -- and hand it back through the stage's `empty` mbarrier (no CTA-wide barrier in the loop).  A chunk's
+// partial sum leaves with red.global.add.f64 (fire and forget: no read of the target tile on the way; several chunks,
+// possibly on different SMs, may feed one tile).
 #define GPBA_LU_CHUNK 4
+#define GPBA_LU_THREADS 160   // warps 0-3 consume (DMMA), warp 4 produces (TMA)
 struct LuDesc { double* target; int j; int flags; };   // flags: 1 first product of its chunk, 2 last product, 4 stop, 8 diagonal tile
-__global__ void __launch_bounds__(128) k_chol_lupdate(CholView C, const int4* __restrict__ tab, int n_chunks,
-                                                      const int* __restrict__ klist, int* __restrict__ counter) {
+GPBA_D void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__global__ void __launch_bounds__(GPBA_LU_THREADS) k_chol_lupdate(CholView C, const int4* __restrict__ tab, int n_chunks,
+                                                                  const int* __restrict__ klist, int* __restrict__ counter) {
   extern __shared__ __align__(128) unsigned char lu_smem[];
-  __shared__ __align__(8) unsigned long long full[GPBA_LU_STAGES];
+  __shared__ __align__(8) unsigned long long full[GPBA_LU_STAGES], empty[GPBA_LU_STAGES];
   __shared__ LuDesc desc[GPBA_LU_STAGES];
   typedef double (*TileP)[GPBA_LD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int gid = lane >> 2, tig = lane & 3;
-  const int m0 = 3 * (warp >> 1), n0 = 3 * (warp & 1);
   // stage s: [La | Lb | y_k]
   constexpr int STAGE_BYTES = 2 * GPBA_TILE_BYTES + GPBA_NB * 8;
   auto stage_a = [&](int s) { return reinterpret_cast<TileP>(lu_smem + (size_t)s * STAGE_BYTES); };
   auto stage_b = [&](int s) { return reinterpret_cast<TileP>(lu_smem + (size_t)s * STAGE_BYTES + GPBA_TILE_BYTES); };
   auto stage_y = [&](int s) { return reinterpret_cast<double*>(lu_smem + (size_t)s * STAGE_BYTES + 2 * GPBA_TILE_BYTES); };
-  // ---- producer state (thread 0)
-  int p_pos = 0, p_begin = 0, p_end = 0, p_i = 0, p_j = 0;
-  double* p_target = nullptr;
-  bool p_diag = false, p_done = false;
-  auto produce = [&](int s) {   // fill stage s with the next product of the stream (thread 0 only)
-    if (p_pos == p_end) {
-      const int c = atomicAdd(counter, 1);
-      if (c >= n_chunks) {
-        desc[s].target = nullptr; desc[s].j = -1; desc[s].flags = 4;
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
-        p_done = true;
-        return;
-      }
-      const int4 e = tab[c];
-      p_j = e.x; p_diag = e.y == 0;
-      p_i = p_diag ? e.x : C.col_rows[C.col_begin[e.x] + e.y - 1];
-      p_target = C.tiles + C.tile_off[(size_t)p_i * C.NT + p_j];   // resolved here, off the consumers' path
-      p_begin = p_pos = e.z; p_end = e.w;
-    }
-    const int k = klist[p_pos];
-    desc[s].target = p_target; desc[s].j = p_j;
-    desc[s].flags = (p_pos == p_begin ? 1 : 0) | (p_pos + 1 == p_end ? 2 : 0) | (p_diag ? 8 : 0);
-    mbar_expect_tx(&full[s], p_diag ? GPBA_TILE_BYTES + GPBA_NB * 8u : 2u * GPBA_TILE_BYTES);
-    bulk_g2s(stage_a(s), C.tiles + C.tile_off[(size_t)p_i * C.NT + k], GPBA_TILE_BYTES, &full[s]);
-    if (!p_diag) bulk_g2s(stage_b(s), C.tiles + C.tile_off[(size_t)p_j * C.NT + k], GPBA_TILE_BYTES, &full[s]);
-    else bulk_g2s(stage_y(s), C.work + (size_t)k * GPBA_NB, GPBA_NB * 8, &full[s]);
-    ++p_pos;
-  };
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < GPBA_LU_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < GPBA_LU_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
     mbar_init_fence();
   }
   pdl_wait_then_release();   // everything below reads what the previous launches wrote
-  if (tid == 0) {
-    for (int s = 0; s < GPBA_LU_STAGES && !p_done; ++s) produce(s);
+  __syncthreads();           // barrier initialisation visible to both roles
+  if (warp == 4) {
+    // ---------------------------------------------------------------- producer (one thread): the operand stream
+    if (lane != 0) return;
+    int pos = 0, begin = 0, end = 0, pi = 0, pj = 0;
+    double* target = nullptr;
+    bool diag = false;
+    for (int n = 0;; ++n) {
+      const int s = n % GPBA_LU_STAGES;
+      if (n >= GPBA_LU_STAGES) mbar_wait(&empty[s], (unsigned)(n / GPBA_LU_STAGES - 1) & 1u);   // the four warps released the stage
+      if (pos == end) {
+        const int c = atomicAdd(counter, 1);
+        if (c >= n_chunks) {
+          desc[s].target = nullptr; desc[s].j = -1; desc[s].flags = 4;
+          mbar_arrive(&full[s]);
+          return;
+        }
+        const int4 e = tab[c];
+        pj = e.x; diag = e.y == 0;
+        pi = diag ? e.x : C.col_rows[C.col_begin[e.x] + e.y - 1];
+        target = C.tiles + C.tile_off[(size_t)pi * C.NT + pj];
+        begin = pos = e.z; end = e.w;
+      }
+      const int k = klist[pos];
+      desc[s].target = target; desc[s].j = pj;
+      desc[s].flags = (pos == begin ? 1 : 0) | (pos + 1 == end ? 2 : 0) | (diag ? 8 : 0);
+      mbar_expect_tx(&full[s], diag ? GPBA_TILE_BYTES + GPBA_NB * 8u : 2u * GPBA_TILE_BYTES);
+      bulk_g2s(stage_a(s), C.tiles + C.tile_off[(size_t)pi * C.NT + k], GPBA_TILE_BYTES, &full[s]);
+      if (!diag) bulk_g2s(stage_b(s), C.tiles + C.tile_off[(size_t)pj * C.NT + k], GPBA_TILE_BYTES, &full[s]);
+      else bulk_g2s(stage_y(s), C.work + (size_t)k * GPBA_NB, GPBA_NB * 8, &full[s]);
+      ++pos;
+    }
   }
-  __syncthreads();             // barrier initialisation visible to every waiter
+  // ------------------------------------------------------------------ consumers (warps 0-3)
+  const int gid = lane >> 2, tig = lane & 3;
+  const int m0 = 3 * (warp >> 1), n0 = 3 * (warp & 1);
   double2 acc[3][3];
-  double s0 = 0.0, s1 = 0.0;   // rhs row of thread tid < 48 (diagonal tiles)
+  double s0 = 0.0, s1 = 0.0;   // rhs rows (diagonal tiles): warp w owns rows 12 w .. 12 w + 11, lanes 0..11
   for (int n = 0;; ++n) {
     const int s = n % GPBA_LU_STAGES;
     mbar_wait(&full[s], (unsigned)(n / GPBA_LU_STAGES) & 1u);
     const LuDesc d = desc[s];
-    if (d.flags & 4) break;    // the stream is exhausted (the stages behind this one were never filled)
+    if (d.flags & 4) break;    // the stream is exhausted
     const bool diag = (d.flags & 8) != 0;
     if (d.flags & 1) {
 #pragma unroll
@@ -415,13 +423,15 @@ __global__ void __launch_bounds__(128) k_chol_lupdate(CholView C, const int4* __
 #pragma unroll
         for (int b = 0; b < 3; ++b) dmma884(acc[a][b].x, acc[a][b].y, af[a], bf[b]);
     }
-    if (diag && tid < GPBA_NB) {   // forward substitution with the tile already staged
+    const int rrow = 12 * warp + lane;   // forward substitution with the tile already staged
+    if (diag && lane < 12) {
       const double* yk = stage_y(s);
 #pragma unroll 4
-      for (int c = 0; c < GPBA_NB; c += 2) { s0 = fma(La[tid][c], yk[c], s0); s1 = fma(La[tid][c + 1], yk[c + 1], s1); }
+      for (int c = 0; c < GPBA_NB; c += 2) { s0 = fma(La[rrow][c], yk[c], s0); s1 = fma(La[rrow][c + 1], yk[c + 1], s1); }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done with stage s (and its descriptor, held in registers)
     if (d.flags & 2) {   // the chunk is complete: its partial sum joins the target tile
-      const int j = d.j;
       double* Tc = d.target;
 #pragma unroll
       for (int a = 0; a < 3; ++a)
@@ -430,10 +440,8 @@ __global__ void __launch_bounds__(128) k_chol_lupdate(CholView C, const int4* __
           double* out = Tc + (8 * (m0 + a) + gid) * GPBA_LD + 8 * (n0 + b) + 2 * tig;
           atomicAdd(out, -acc[a][b].x); atomicAdd(out + 1, -acc[a][b].y);
         }
-      if (diag && tid < GPBA_NB) atomicAdd(&C.work[(size_t)j * GPBA_NB + tid], -(s0 + s1));
+      if (diag && lane < 12) atomicAdd(&C.work[(size_t)d.j * GPBA_NB + rrow], -(s0 + s1));
     }
-    __syncthreads();   // every warp is done with stage s and its descriptor: it may be refilled
-    if (tid == 0 && !p_done) produce(s);
   }
 }
 

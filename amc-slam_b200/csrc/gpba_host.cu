@@ -1005,7 +1005,8 @@ int Solver::build_cholesky_structure() {
         while (pa < pae && pb < pbe) { if (*pa < *pb) ++pa; else if (*pb < *pa) ++pb; else { klist.push_back(*pa); ++pa; ++pb; } }
         const int cnt = (int)klist.size() - kb;
         if (cnt == 0) continue;
-        const int nch = (cnt + GPBA_LU_CHUNK - 1) / GPBA_LU_CHUNK;
+        static const int lu_chunk = getenv("GPBA_LU_CHUNK") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK"))) : GPBA_LU_CHUNK;
+        const int nch = (cnt + lu_chunk - 1) / lu_chunk;
         for (int c = 0; c < nch; ++c)
           upd_tab.push_back(make_int4(k, q, kb + (int)((int64_t)cnt * c / nch), kb + (int)((int64_t)cnt * (c + 1) / nch)));
       }
@@ -1091,8 +1092,8 @@ int Solver::capture_cholesky_graph() {
       // left-looking: the level's tiles first receive the products of all finished columns, then the panel step
       if (nupd > 0) {
         const int grid = std::min(nupd, lu_ctas);   // persistent CTAs, one per SM, drawing chunks from the level's counter
-        if (use_pdl) e = launch_pdl_smem(k_chol_lupdate, grid, 128, lu_smem, stream, C, ut, nupd, (const int*)d_klist.p, d_lu_counter.p + l);
-        else k_chol_lupdate<<<grid, 128, lu_smem, stream>>>(C, ut, nupd, d_klist.p, d_lu_counter.p + l);
+        if (use_pdl) e = launch_pdl_smem(k_chol_lupdate, grid, GPBA_LU_THREADS, lu_smem, stream, C, ut, nupd, (const int*)d_klist.p, d_lu_counter.p + l);
+        else k_chol_lupdate<<<grid, GPBA_LU_THREADS, lu_smem, stream>>>(C, ut, nupd, d_klist.p, d_lu_counter.p + l);
         ++launches;
         if (e != cudaSuccess) break;
       }
