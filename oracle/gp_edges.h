@@ -112,7 +112,7 @@ inline void reproj_error(const GaussianProcess& G, bool gp, int dim, const KfSta
 // J2kf (dim x 12) wrt KF_cur, Jpt (dim x 3).  Row-major, leading dimension 12 / 3.
 inline void reproj_jacobian(const GaussianProcess& G, bool gp, int dim, const KfState* f1, const KfState& f2, double t,
                             const SE3& Tbc, const Pinhole& cam, double bf, const V3& Xw, double* J1kf, double* J2kf,
-                            double* Jpt) {
+                            double* Jpt, double* Jext = nullptr /* dim x 6: EdgeMonoGPExtrinsic's fourth block */) {
   M6x12 At1, Pt1;
   SE3 dT, Twb;
   V6 xi12;
@@ -140,6 +140,14 @@ inline void reproj_jacobian(const GaussianProcess& G, bool gp, int dim, const Kf
   Mat<3, 3> Jp = -(P * Rcb * Rbw);
   for (int r = 0; r < dim; ++r)
     for (int c = 0; c < 3; ++c) Jpt[r * 3 + c] = Jp(r, c);
+  if (Jext) {  // _jacobianOplus[3] = -proj_jac * [-I, Skew(Xc)]   (src/G2oTypes.cc:311-313)
+    Mat<3, 6> SE3deriv2;
+    SE3deriv2.set_block(0, 0, -M3::Identity());
+    SE3deriv2.set_block(0, 3, hat(Xc));
+    Mat<3, 6> Je = -(P * SE3deriv2);
+    for (int r = 0; r < dim; ++r)
+      for (int c = 0; c < 6; ++c) Jext[r * 6 + c] = Je(r, c);
+  }
   if (!gp) {  // EdgeMono / EdgeStereo: pose block = J1, velocity block = 0
     for (int r = 0; r < dim; ++r)
       for (int c = 0; c < 12; ++c) J2kf[r * 12 + c] = c < 6 ? J1(r, c) : 0.0;
@@ -206,6 +214,27 @@ inline void prior_jacobian(const KfState& f1, const KfState& f2, M12* Ji, M12* J
 }
 
 // RobustKernelHuber with the reference's float-typed dsqr (robust_kernel_impl.h:84, .cpp:65-91)
+// EdgeExtrinsicPrior (include/G2oTypes.h:470-494): e = Log(R_ini^-1 R_bc), J = [0 | RightJacobianSO3(e)^-1] wrt the
+// 6-dim tangent [translation; rotation] of VertexExtrinsic (oplus: Tbc <- Tbc exp(delta), :98-100).
+// RightJacobianSO3 (src/G2oTypes.cc:575-590, ORB-SLAM3's): I - W (1 - cos d) / d^2 + W^2 (d - sin d) / d^3, identity below d = 1e-5;
+// `.inverse()` is Eigen's fixed-size 3 x 3 inverse (cofactors).
+inline M3 RightJacobianSO3_orb(const V3& v) {
+  const double d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  const double d = std::sqrt(d2);
+  M3 W = hat(v);
+  if (d < 1e-5) return M3::Identity();
+  return M3::Identity() - W * ((1.0 - std::cos(d)) / d2) + (W * W) * ((d - std::sin(d)) / (d2 * d));
+}
+inline M3 inverse3_cofactor(const M3& A) {
+  M3 C;
+  C(0, 0) = A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1); C(0, 1) = A(0, 2) * A(2, 1) - A(0, 1) * A(2, 2); C(0, 2) = A(0, 1) * A(1, 2) - A(0, 2) * A(1, 1);
+  C(1, 0) = A(1, 2) * A(2, 0) - A(1, 0) * A(2, 2); C(1, 1) = A(0, 0) * A(2, 2) - A(0, 2) * A(2, 0); C(1, 2) = A(0, 2) * A(1, 0) - A(0, 0) * A(1, 2);
+  C(2, 0) = A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0); C(2, 1) = A(0, 1) * A(2, 0) - A(0, 0) * A(2, 1); C(2, 2) = A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0);
+  const double det = A(0, 0) * C(0, 0) + A(0, 1) * C(1, 0) + A(0, 2) * C(2, 0);
+  return C * (1.0 / det);
+}
+inline V3 ext_prior_error(const Quat& q_ini_inv, const SE3& Tbc) { double theta; return so3_log(quat_mul(q_ini_inv, Tbc.q), &theta); }
+
 struct Huber {
   double delta;
   float dsqr;

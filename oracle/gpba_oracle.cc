@@ -325,7 +325,18 @@ struct Oracle {
   bool structure_fresh = false;   // build_structure() ran and neither levels nor kernels changed since
 
   // ---- backup stack (BaseVertex::push/pop)
-  struct Snapshot { std::vector<KfState> kf; std::vector<V3> pt; };
+  struct Snapshot { std::vector<KfState> kf; std::vector<V3> pt; std::vector<SE3> Tbc; };
+  // ---- extrinsic self-calibration: VertexExtrinsic + EdgeExtrinsicPrior of LocalGPBA (src/Optimizer.cc:983-995, 1228-1240).
+  // An extrinsic is a non-marginalized 6-dim vertex whose id follows every keyframe id (:986), so its Hessian block follows
+  // the keyframes' (sparse_optimizer.cpp:166-190).  Here it occupies a 12-slot whose last six dimensions are padding (zero
+  // Jacobian, unit diagonal in the reduced system, zero update): the solution is the one of the 6-dim block.
+  std::vector<uint8_t> ext_free, ext_prior_on, ext_prior_active;
+  std::vector<Quat> ext_prior_qinv;     // R_ini^-1 (EdgeExtrinsicPrior::R_, G2oTypes.h:474)
+  std::vector<M3> ext_prior_info;       // MultiFrame::mRbc_ini_cov[c]
+  std::vector<V3> ext_prior_err;
+  std::vector<int> ext_h;               // Hessian index of camera c's extrinsic or -1
+  std::vector<int> obs_slot3;           // Hpl slot of (extrinsic, landmark) or -1
+  int numPosesKf = 0;
   std::vector<Snapshot> stack;
 
   // ---- LM state
@@ -387,6 +398,8 @@ struct Oracle {
     if (has_prior_k) hub_prior.setDelta(p->huber_prior);
     lambda_init = p->lambda_init; linear_solver = p->linear_solver;
     obs_err.assign((size_t)n_obs * 3, 0.0); prior_err.assign((size_t)n_prior * 12, 0.0); velp_err.assign(n_velp, 0.0);
+    ext_free.assign(n_cam, 0); ext_prior_on.assign(n_cam, 0); ext_prior_active.assign(n_cam, 0); ext_h.assign(n_cam, -1);
+    ext_prior_qinv.assign(n_cam, Quat{0, 0, 0, 1}); ext_prior_info.assign(n_cam, M3::Zero()); ext_prior_err.assign(n_cam, V3());
   }
 
   // ------------------------------------------------------------------ structure
@@ -414,6 +427,18 @@ struct Oracle {
     numPoses = 0;
     for (int k = 0; k < n_kf; ++k)
       if (kf_act[k] && !kf_fixed[k]) kf_h[k] = numPoses++;
+    numPosesKf = numPoses;
+    // free extrinsic vertices follow the keyframes (their ids are larger, Optimizer.cc:986); active iff they carry an active
+    // edge: the prior (active iff the vertex is not fixed) or an active EdgeMonoGPExtrinsic of their camera
+    {
+      std::vector<char> cam_act(n_cam, 0);
+      for (int64_t i : active_obs) if (rec_kf1[obs_rec[i]] >= 0) cam_act[rec_cam[obs_rec[i]]] = 1;
+      for (int c = 0; c < n_cam; ++c) {
+        ext_prior_active[c] = ext_free[c] && ext_prior_on[c];
+        ext_h[c] = (ext_free[c] && (ext_prior_on[c] || cam_act[c])) ? numPoses++ : -1;
+      }
+    }
+    auto obs_ext = [&](int64_t i) { const int r = obs_rec[i]; return rec_kf1[r] >= 0 ? ext_h[rec_cam[r]] : -1; };
     numLandmarks = 0; lm_pt.clear();
     for (int i = 0; i < n_pt; ++i)
       if (pt_act[i]) { pt_h[i] = numLandmarks++; lm_pt.push_back(i); }
@@ -431,6 +456,8 @@ struct Oracle {
     for (int64_t i : active_obs) {
       int r = obs_rec[i];
       if (rec_kf1[r] >= 0) add_pair(pp, kf_h[rec_kf1[r]], kf_h[rec_kf2[r]]);
+      const int he = obs_ext(i);   // EdgeMonoGPExtrinsic: (kf1, ext), (kf2, ext) (base_multi_edge.hpp:60-90 maps every vertex pair)
+      if (he >= 0) { add_pair(pp, kf_h[rec_kf1[r]], he); add_pair(pp, kf_h[rec_kf2[r]], he); }
     }
     // Hschur pattern = Hpp pattern U pairs of free poses attached to ANY edge (active or not) of an
     // active landmark (block_solver.hpp:262-288 walks v->edges()).
@@ -443,6 +470,7 @@ struct Oracle {
         int r = obs_rec[i];
         if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0) lm_poses[l].push_back(kf_h[rec_kf1[r]]);
         if (kf_h[rec_kf2[r]] >= 0) lm_poses[l].push_back(kf_h[rec_kf2[r]]);
+        if (obs_ext(i) >= 0) lm_poses[l].push_back(obs_ext(i));
       }
       for (int l = 0; l < numLandmarks; ++l) {
         std::vector<int>& v = lm_poses[l];
@@ -475,6 +503,7 @@ struct Oracle {
         int r = obs_rec[i];
         if (rec_kf1[r] >= 0 && kf_h[rec_kf1[r]] >= 0) lm_poses[l].push_back(kf_h[rec_kf1[r]]);
         if (kf_h[rec_kf2[r]] >= 0) lm_poses[l].push_back(kf_h[rec_kf2[r]]);
+        if (obs_ext(i) >= 0) lm_poses[l].push_back(obs_ext(i));
       }
       lm_begin.assign(numLandmarks + 1, 0); hpl_pose.clear();
       for (int l = 0; l < numLandmarks; ++l) {
@@ -486,18 +515,20 @@ struct Oracle {
       }
       lm_begin[numLandmarks] = (int64_t)hpl_pose.size();
       hpl.assign(hpl_pose.size(), M12x3::Zero());
-      obs_slot1.assign(n_obs, -1); obs_slot2.assign(n_obs, -1);
+      obs_slot1.assign(n_obs, -1); obs_slot2.assign(n_obs, -1); obs_slot3.assign(n_obs, -1);
       for (int64_t i : active_obs) {
         int l = pt_h[obs_pt[i]];
         int r = obs_rec[i];
-        auto slot = [&](int kfi) -> int {
-          if (kfi < 0 || kf_h[kfi] < 0) return -1;
+        auto slot_h = [&](int h) -> int {
+          if (h < 0) return -1;
           const int* bgn = &hpl_pose[lm_begin[l]];
           const int* end = &hpl_pose[0] + lm_begin[l + 1];
-          return (int)(lm_begin[l] + (std::lower_bound(bgn, end, kf_h[kfi]) - bgn));
+          return (int)(lm_begin[l] + (std::lower_bound(bgn, end, h) - bgn));
         };
+        auto slot = [&](int kfi) -> int { return kfi < 0 ? -1 : slot_h(kf_h[kfi]); };
         obs_slot1[i] = slot(rec_kf1[r]);
         obs_slot2[i] = slot(rec_kf2[r]);
+        obs_slot3[i] = slot_h(obs_ext(i));
       }
     }
     hll.assign(numLandmarks, M3::Zero()); dinv.assign(numLandmarks, M3::Zero());
@@ -535,6 +566,13 @@ struct Oracle {
     return s;
   }
   double velp_chi2(int i) const { return velp_err[i] * (G.QcInv(2, 2) * velp_err[i]); }
+  double ext_prior_chi2(int c) const {
+    const V3& e = ext_prior_err[c];
+    const M3& O = ext_prior_info[c];
+    double s = 0;
+    for (int r = 0; r < 3; ++r) { double t = 0; for (int k = 0; k < 3; ++k) t += O(r, k) * e[k]; s += e[r] * t; }
+    return s;
+  }
 
   void compute_errors() {  // SparseOptimizer::computeActiveErrors
     const double t_res = now();
@@ -542,6 +580,8 @@ struct Oracle {
       if (velp_active[i]) velp_err[i] = kf[velp_kf[i]].vel[2];
     for (int i = 0; i < n_prior; ++i)
       if (prior_active[i]) prior_error(kf[prior_kf1[i]], kf[prior_kf2[i]], &prior_err[(size_t)i * 12]);
+    for (int c = 0; c < n_cam; ++c)
+      if (ext_prior_active[c]) ext_prior_err[c] = ext_prior_error(ext_prior_qinv[c], Tbc[c]);   // EdgeExtrinsicPrior::computeError
     const int64_t na = (int64_t)active_obs.size();
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
     for (int64_t k = 0; k < na; ++k) compute_obs_error(active_obs[k]);
@@ -556,6 +596,8 @@ struct Oracle {
         if (has_prior_k) { hub_prior.robustify(prior_chi2(i), rho); chi += rho[0]; }
         else chi += prior_chi2(i);
       }
+    for (int c = 0; c < n_cam; ++c)
+      if (ext_prior_active[c]) chi += ext_prior_chi2(c);   // no robust kernel (Optimizer.cc:990-994)
     for (int64_t i : active_obs) {
       if (obs_has_kernel(i)) { obs_kernel(i).robustify(obs_chi2(i), rho); chi += rho[0]; }
       else chi += obs_chi2(i);
@@ -593,9 +635,13 @@ struct Oracle {
     int r = obs_rec[i];
     const bool gp = rec_kf1[r] >= 0;
     const int dim = obs_dim(i);
-    double J1[36], J2[36], Jp[9];
+    double J1[36], J2[36], Jp[9], Je[18], J3[36];
+    const int h3 = gp ? ext_h[rec_cam[r]] : -1;
     reproj_jacobian(G, gp, dim, gp ? &kf[rec_kf1[r]] : nullptr, kf[rec_kf2[r]], rec_t[r], Tbc[rec_cam[r]],
-                    cams[rec_cam[r]], bf, pt[obs_pt[i]], J1, J2, Jp);
+                    cams[rec_cam[r]], bf, pt[obs_pt[i]], J1, J2, Jp, h3 >= 0 ? Je : nullptr);
+    if (h3 >= 0)   // the extrinsic's 12-slot: [J_ext | 0]
+      for (int d = 0; d < dim; ++d)
+        for (int c = 0; c < 12; ++c) J3[d * 12 + c] = c < 6 ? Je[d * 6 + c] : 0.0;
     // constructQuadraticForm (base_multi_edge.hpp:36-48 / base_binary_edge.hpp:55-120)
     const double* e = &obs_err[(size_t)i * 3];
     double w = obs_w[i];
@@ -642,6 +688,13 @@ struct Oracle {
       add_b(bp + (size_t)h2 * 12, J2, 12, 12);
       add_hpl(obs_slot2[i], J2);
     }
+    if (h3 >= 0) {   // the extrinsic follows every keyframe: (kf, ext) blocks are stored as they are
+      AtOB(Hpp[hpp_at(h3, h3)], J3, J3, false);
+      add_b(bp + (size_t)h3 * 12, J3, 12, 12);
+      if (h1 >= 0) AtOB(Hpp[hpp_at(h1, h3)], J1, J3, false);
+      if (h2 >= 0) AtOB(Hpp[hpp_at(h2, h3)], J2, J3, false);
+      add_hpl(obs_slot3[i], J3);
+    }
     M3& Hl = hll[l];
     for (int a = 0; a < 3; ++a)
       for (int c = 0; c < 3; ++c) {
@@ -659,6 +712,22 @@ struct Oracle {
       double O = G.QcInv(2, 2);
       hpp_block(h, h)(8, 8) += O;           // J = [0_6 | 0 0 1 0 0 0]  (G2oTypes.h:509-513)
       b[(size_t)h * 12 + 8] += -(O * velp_err[i]);
+    }
+    for (int c = 0; c < n_cam; ++c) {   // EdgeExtrinsicPrior (G2oTypes.h:470-494): J = [0 | Jr(e)^-1], no kernel
+      if (!ext_prior_active[c]) continue;
+      const int h = ext_h[c];
+      const M3 Ji3 = inverse3_cofactor(RightJacobianSO3_orb(ext_prior_err[c]));
+      const M3& O = ext_prior_info[c];
+      const M3 JtO = transpose(Ji3) * O;
+      const M3 H3 = JtO * Ji3;
+      M12& B = hpp_block(h, h);
+      for (int a = 0; a < 3; ++a)
+        for (int k = 0; k < 3; ++k) B(3 + a, 3 + k) += H3(a, k);
+      for (int a = 0; a < 3; ++a) {
+        double t = 0;
+        for (int k = 0; k < 3; ++k) t += JtO(a, k) * ext_prior_err[c][k];
+        b[(size_t)h * 12 + 3 + a] += -t;
+      }
     }
     for (int i = 0; i < n_prior; ++i) {
       if (!prior_active[i]) continue;
@@ -755,6 +824,10 @@ struct Oracle {
     const size_t sizePoses = (size_t)numPoses * 12;
     for (auto& m : hs) m = M12::Zero();
     for (size_t i = 0; i < hpp_rc.size(); ++i) { M12& t = hs[hs_idx.find(hpp_rc[i])->second]; t = t + hpp[i]; }  // _Hpp->add(_Hschur)
+    for (int h = numPosesKf; h < numPoses; ++h) {   // padding of the extrinsics' 12-slots: identity rows, zero right-hand side
+      M12& t = hs[hs_idx.find({h, h})->second];
+      for (int k = 6; k < 12; ++k) t(k, k) += 1.0;
+    }
     std::fill(coeff.begin(), coeff.begin() + sizePoses, 0.0);
     const double t_schur = now();
     // G2O_OPENMP build of the reference: "#pragma omp parallel for schedule(dynamic, 10)" over the landmarks with one
@@ -854,13 +927,20 @@ struct Oracle {
       kf[k].Twb = se3_mul(kf[k].Twb, se3_exp(du));  // PoseVelocity::Update, G2oTypes.cc:41-46
       for (int i = 0; i < 6; ++i) kf[k].vel[i] += u[6 + i];
     }
+    for (int c = 0; c < n_cam; ++c) {   // VertexExtrinsic::oplusImpl (G2oTypes.h:98-100)
+      if (ext_h[c] < 0) continue;
+      const double* u = upd + (size_t)ext_h[c] * 12;
+      V6 du;
+      for (int i = 0; i < 6; ++i) du[i] = u[i];
+      Tbc[c] = se3_mul(Tbc[c], se3_exp(du));
+    }
     const double* ul = upd + (size_t)numPoses * 12;
     for (int l = 0; l < numLandmarks; ++l)
       for (int c = 0; c < 3; ++c) pt[lm_pt[l]][c] += ul[(size_t)l * 3 + c];  // VertexSBAPointXYZ::oplusImpl
     timeUpdate += now() - t_up;
   }
-  void push() { stack.push_back({kf, pt}); }
-  void pop() { kf = stack.back().kf; pt = stack.back().pt; stack.pop_back(); }
+  void push() { stack.push_back({kf, pt, Tbc}); }
+  void pop() { kf = stack.back().kf; pt = stack.back().pt; Tbc = stack.back().Tbc; stack.pop_back(); }
   void discard_top() { stack.pop_back(); }
 
   // ------------------------------------------------------------------ LM (optimization_algorithm_levenberg.cpp)
@@ -1013,6 +1093,37 @@ void oracle_reset_state(void* h, const double* kf_pose, const double* kf_vel, co
   }
   if (pt_xyz) for (int i = 0; i < o->n_pt; ++i) for (int c = 0; c < 3; ++c) o->pt[i][c] = pt_xyz[3 * (size_t)i + c];
   o->stack.clear();
+}
+// LocalGPBA's extrinsic vertices (src/Optimizer.cc:983-995): which are free (setFixed(false), :1236) and their
+// EdgeExtrinsicPrior (R_ini as quaternion xyzw, information 3 x 3 row-major); prior_q == NULL: no prior edges.
+int oracle_set_extrinsics(void* h, const uint8_t* free_, const double* prior_q, const double* prior_info) {
+  Oracle* o = ORA(h);
+  o->structure_fresh = false;
+  for (int c = 0; c < o->n_cam; ++c) {
+    o->ext_free[c] = free_ ? free_[c] : 0;
+    o->ext_prior_on[c] = prior_q != nullptr;
+    if (prior_q) {
+      o->ext_prior_qinv[c] = quat_inv(Quat{prior_q[4 * c], prior_q[4 * c + 1], prior_q[4 * c + 2], prior_q[4 * c + 3]});
+      for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) o->ext_prior_info[c](r, k) = prior_info[9 * c + 3 * r + k];
+    }
+  }
+  return 0;
+}
+int oracle_get_extrinsics(void* h, double* Tbc7) {
+  Oracle* o = ORA(h);
+  for (int c = 0; c < o->n_cam; ++c) {
+    double* q = Tbc7 + 7 * c;
+    q[0] = o->Tbc[c].q.x; q[1] = o->Tbc[c].q.y; q[2] = o->Tbc[c].q.z; q[3] = o->Tbc[c].q.w;
+    q[4] = o->Tbc[c].t[0]; q[5] = o->Tbc[c].t[1]; q[6] = o->Tbc[c].t[2];
+  }
+  return 0;
+}
+// cam_obs[c]++ for every EdgeMonoGPExtrinsic of camera c, whatever its level (src/Optimizer.cc:1129)
+int oracle_count_camera_observations(void* h, int64_t* cam_obs) {
+  Oracle* o = ORA(h);
+  for (int c = 0; c < o->n_cam; ++c) cam_obs[c] = 0;
+  for (int64_t i = 0; i < o->n_obs; ++i) if (o->rec_kf1[o->obs_rec[i]] >= 0) cam_obs[o->rec_cam[o->obs_rec[i]]]++;
+  return 0;
 }
 void oracle_set_threads(void* h, int n) { ORA(h)->threads = n < 1 ? 1 : n; }
 // seconds per stage since the last reset: timeResiduals, timeQuadraticForm (linearize + quadratic form), timeSchurComplement,
@@ -1224,6 +1335,29 @@ void oracle_edge_eval(const double* qc, int gp, const double* T1, const double* 
     std::memcpy(J2, j2, dim * 12 * 8);
     if (Jp) std::memcpy(Jp, jp, dim * 3 * 8);
   }
+}
+// the fourth Jacobian block of EdgeMonoGPExtrinsic (wrt VertexExtrinsic), dim x 6
+void oracle_edge_jext(const double* qc, int gp, const double* T1, const double* v1, double t1, const double* T2,
+                      const double* v2, double t2, double t, const double* Tbc7, const double* intr, double bf,
+                      const double* Xw, const double* obs3, double* Jext) {
+  GaussianProcess G;
+  G.set_diag(qc);
+  KfState f1, f2;
+  if (gp) { f1.Twb = se3_from7(T1); f1.vel = v6(v1); f1.time = t1; }
+  f2.Twb = se3_from7(T2); f2.vel = v6(v2); f2.time = t2;
+  Pinhole cam = {intr[0], intr[1], intr[2], intr[3]};
+  V3 X; X[0] = Xw[0]; X[1] = Xw[1]; X[2] = Xw[2];
+  int dim = obs3[2] >= 0 ? 3 : 2;
+  double j1[36] = {0}, j2[36] = {0}, jp[9] = {0}, je[18] = {0};
+  reproj_jacobian(G, gp != 0, dim, gp ? &f1 : nullptr, f2, t, se3_from7(Tbc7), cam, bf, X, j1, j2, jp, je);
+  std::memcpy(Jext, je, dim * 6 * 8);
+}
+// EdgeExtrinsicPrior: error (3) and Jacobian wrt the rotation part of the tangent (3 x 3)
+void oracle_ext_prior_eval(const double* q_ini, const double* Tbc7, double* err3, double* J9) {
+  const Quat qi = quat_inv(Quat{q_ini[0], q_ini[1], q_ini[2], q_ini[3]});
+  const V3 e = ext_prior_error(qi, se3_from7(Tbc7));
+  const M3 J = inverse3_cofactor(RightJacobianSO3_orb(e));
+  for (int i = 0; i < 3; ++i) { err3[i] = e[i]; for (int k = 0; k < 3; ++k) J9[3 * i + k] = J(i, k); }
 }
 void oracle_prior_eval(const double* T1, const double* v1, double t1, const double* T2, const double* v2, double t2,
                        double* err12, double* Ji144, double* Jj144) {

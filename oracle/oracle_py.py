@@ -62,6 +62,19 @@ class Oracle:
         except Exception:
             pass
 
+    def set_extrinsics(self, free, prior_q=None, prior_info=None):
+        """free [n_cam] uint8; prior_q [n_cam][4] (R_ini, xyzw) + prior_info [n_cam][3][3], or None for no EdgeExtrinsicPrior"""
+        f = np.ascontiguousarray(free, np.uint8)
+        q = None if prior_q is None else np.ascontiguousarray(prior_q, np.float64)
+        w = None if prior_info is None else np.ascontiguousarray(prior_info, np.float64)
+        self.L.oracle_set_extrinsics(self.h, _p(f), None if q is None else _p(q), None if w is None else _p(w))
+
+    def extrinsics(self):
+        a = np.zeros((self.prob.n_cam, 7)); self.L.oracle_get_extrinsics(self.h, _p(a)); return a
+
+    def count_camera_observations(self):
+        a = np.zeros(self.prob.n_cam, np.int64); self.L.oracle_count_camera_observations(self.h, _p(a)); return a
+
     def reset_state(self, kf_pose, kf_vel, pt_xyz):
         self.L.oracle_reset_state(self.h, _p(np.ascontiguousarray(kf_pose, np.float64)), _p(np.ascontiguousarray(kf_vel, np.float64)),
                                   _p(np.ascontiguousarray(pt_xyz, np.float64)))
@@ -246,6 +259,20 @@ def edge_eval(qc, gp, T1, v1, t1, T2, v2, t2, t, Tbc, intr, bf, Xw, obs3, jac=Tr
                            _p(_d(obs3)), _p(err), _p(J1) if jac else None, _p(J2) if jac else None,
                            _p(Jp) if jac else None)
     return err[:dim], J1, J2, Jp
+
+
+def edge_jext(qc, gp, T1, v1, t1, T2, v2, t2, t, Tbc, intr, bf, Xw, obs3):
+    dim = 3 if obs3[2] >= 0 else 2
+    J = np.zeros((dim, 6))
+    lib().oracle_edge_jext(_p(_d(qc)), int(gp), _p(_d(T1)), _p(_d(v1)), C.c_double(t1), _p(_d(T2)), _p(_d(v2)), C.c_double(t2),
+                           C.c_double(t), _p(_d(Tbc)), _p(_d(intr)), C.c_double(bf), _p(_d(Xw)), _p(_d(obs3)), _p(J))
+    return J
+
+
+def ext_prior_eval(q_ini, Tbc):
+    e = np.zeros(3); J = np.zeros((3, 3))
+    lib().oracle_ext_prior_eval(_p(_d(q_ini)), _p(_d(Tbc)), _p(e), _p(J))
+    return e, J
 
 
 def prior_eval(T1, v1, t1, T2, v2, t2):
