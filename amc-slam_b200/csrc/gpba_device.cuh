@@ -11,13 +11,17 @@ struct CamConst {
   double Rcb[9], tcb[3];  // Tcb = Tbc^-1
   double Rbc[9], tbc[3];
   double qbc[4];          // Tbc quaternion xyzw (for se3 products in K0)
+  double AdjTbc[36];      // Adj(T_bc) = [[R_bc, t_bc^ R_bc], [0, R_bc]]: J_ext = J1 Adj(T_bc) (src/G2oTypes.cc:311-313)
 };
 
 // Record table (output of K0), one row per (KF_prev, KF_cur, cam, t) record:
 //   [0..8]  R_cw   [9..11] t_cw      so that X_c = R_cw X_w + t_cw with T_cw = (T_wb(t) T_bc)^-1
-//   [12..155] M (6 x 24, row-major): [M_T1 | M_V1 | M_T2 | M_V2]  (SURVEY Appendix A.3); [0 | 0 | I | 0] for a
-//             synchronous record
-#define GPBA_REC_STRIDE 156
+//   [12..227] M (6 x 36, row-major): [M_T1 | M_V1 | M_T2 | M_V2 | A_c 0]  (SURVEY Appendix A.3); [0 | 0 | I | 0 | 0 0] for a
+//             synchronous record.  The three 12-column slices belong to the record's three pose-like vertices: previous
+//             keyframe, current keyframe, and (GP records of a camera whose VertexExtrinsic is free) the extrinsic, whose
+//             12-slot holds the 6-dim tangent in front of six padding dimensions; A_c = Adj(T_bc).
+#define GPBA_REC_MS 36
+#define GPBA_REC_STRIDE (12 + 6 * GPBA_REC_MS)
 #define GPBA_REC_M 12
 #define GPBA_REC_LITE_STRIDE 12
 
@@ -51,9 +55,15 @@ struct DevView {
   int n_rseg;
   const int* rseg_rec; const int64_t* rseg_begin;  // [n_rseg], [n_rseg+1]
   // ---- Hessian storage
-  int n_pose;                                 // free keyframes
+  int n_pose;                                 // free keyframes + free extrinsics (the extrinsics follow the keyframes)
+  int n_pose_kf;                              // free keyframes
+  const int* ext_h;                           // [n_cam] hessian index of the camera's extrinsic or -1 (fixed / absent)
+  const unsigned char* ext_prior_on;          // [n_cam] EdgeExtrinsicPrior active
+  const double* ext_prior_qinv;               // [n_cam][4] R_ini^-1 (xyzw)
+  const double* ext_prior_info;               // [n_cam][9]
   int n_hpp, n_hs;
   const int* rec_hpp11; const int* rec_hpp12; const int* rec_hpp22;  // Hpp block index per record (-1 if n/a); hpp12 < 0 => none, bit30 set => transposed
+  const int* rec_hpp13; const int* rec_hpp23; const int* rec_hpp33;  // blocks with the record's extrinsic (never transposed: it follows the keyframes)
   const int* prior_hpp11; const int* prior_hpp12; const int* prior_hpp22;
   const int* pose_hpp_diag;                   // [n_pose]
   const int* hs_from_hpp;                     // [n_hs] index into Hpp or -1

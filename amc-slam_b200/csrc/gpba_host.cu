@@ -164,7 +164,19 @@ struct Solver {
   double lambda_init = 0;
   int linear_solver = 0;
   // ------------------------------------------------------------------ device: static
-  DBuf<CamConst> d_cam;
+  DBuf<CamConst> d_cam[2];                      // per state buffer: the extrinsics are part of the state when they are free
+  DBuf<double> d_ext[2];                        // [n_cam][7] Tbc (VertexExtrinsic estimate), double buffered like the poses
+  std::vector<double> h_ext0;                   // the extrinsics the handle was created with
+  std::vector<CamConst> h_cam0;
+  // extrinsic self-calibration (LocalGPBA's second stage, src/Optimizer.cc:983-995, 1228-1240)
+  std::vector<uint8_t> ext_free, ext_prior_on;  // [n_cam]
+  std::vector<double> ext_prior_qinv, ext_prior_info;
+  std::vector<int> ext_h;                       // [n_cam] hessian index (after the keyframes) or -1
+  DBuf<int> d_ext_h;
+  DBuf<unsigned char> d_ext_prior_on;
+  DBuf<double> d_ext_prior_qinv, d_ext_prior_info;
+  std::vector<std::vector<double>> stack_ext;
+  int n_pose_kf = 0;
   DBuf<double> d_time, d_rec_t;
   DBuf<int> d_rec_kf1, d_rec_kf2, d_rec_cam, d_prior_kf1, d_prior_kf2, d_velp_kf;
   DBuf<double> d_pt_full;                       // [n_pt*3] always-current copy in original order
@@ -200,6 +212,7 @@ struct Solver {
   DBuf<double> d_gather;                // multi-GPU: staging buffer of the end-of-optimize all-reduces
   DBuf<HsContrib> d_con;
   CubTemp cub_tmp;
+  DBuf<int> d_rec_hpp13, d_rec_hpp23, d_rec_hpp33;
   DBuf<int> d_rec_hpp11, d_rec_hpp12, d_rec_hpp22, d_prior_hpp11, d_prior_hpp12, d_prior_hpp22, d_pose_hpp_diag;
   DBuf<int> d_hs_from_hpp, d_hs_diag_pose, d_hs_row, d_hs_col;
   // ------------------------------------------------------------------ Hessian storage (device)
@@ -317,6 +330,9 @@ struct Solver {
   int lm_solve(int iteration, const gpba_lm_params& P, const volatile unsigned char* stop, gpba_lm_trace* tr, int* result);
   int optimize(int iters, const volatile unsigned char* stop, const gpba_lm_params& P, gpba_lm_trace* tr);
   int scatter_points(int buf);
+  DevView Vb(int buf) { DevView v = V; v.cam = d_cam[buf].p; return v; }   // the view of state buffer `buf`
+  int refresh_cams();
+  bool any_ext_free() const { for (uint8_t f : ext_free) if (f) return true; return false; }
   int download_state(double* kf_pose, double* kf_vel, double* pt_xyz);
   int allreduce_system();
   int allreduce_scalar(double* v, int count = 1, int op = kNcclSum);
@@ -396,8 +412,16 @@ int Solver::init(const gpba_problem* P, int dev, bool async_upload) {
     for (int i = 0; i < 9; ++i) { cc.Rcb[i] = Rcb.a[i]; cc.Rbc[i] = Rbc.a[i]; }
     for (int i = 0; i < 3; ++i) { cc.tcb[i] = Tcb.t[i]; cc.tbc[i] = Tbc.t[i]; }
     cc.qbc[0] = Tbc.q.x; cc.qbc[1] = Tbc.q.y; cc.qbc[2] = Tbc.q.z; cc.qbc[3] = Tbc.q.w;
+    const M6 A = se3_Adj(Tbc);
+    for (int r = 0; r < 6; ++r) for (int k = 0; k < 6; ++k) cc.AdjTbc[r * 6 + k] = A(r, k);
   }
-  CKR(d_cam.upload(cams, stream));
+  h_cam0 = cams;
+  h_ext0.assign(P->cam_Tbc, P->cam_Tbc + 7 * (size_t)n_cam);
+  ext_free.assign(n_cam, 0); ext_prior_on.assign(n_cam, 0); ext_h.assign(n_cam, -1);
+  ext_prior_qinv.assign(4 * (size_t)n_cam, 0.0); ext_prior_info.assign(9 * (size_t)n_cam, 0.0);
+  for (int b = 0; b < 2; ++b) { CKR(d_cam[b].upload(cams, stream)); CKR(d_ext[b].upload(h_ext0, stream)); }
+  CKR(d_ext_h.upload(ext_h, stream)); CKR(d_ext_prior_on.upload(ext_prior_on, stream));
+  CKR(d_ext_prior_qinv.upload(ext_prior_qinv, stream)); CKR(d_ext_prior_info.upload(ext_prior_info, stream));
   CKR(d_time.upload(h_time, stream));
   CKR(d_rec_kf1.upload(rec_kf1, stream)); CKR(d_rec_kf2.upload(rec_kf2, stream));
   CKR(d_rec_cam.upload(rec_cam, stream)); CKR(d_rec_t.upload(rec_t, stream));
@@ -441,7 +465,7 @@ int Solver::init(const gpba_problem* P, int dev, bool async_upload) {
   }
   CKR(d_rec.alloc((size_t)n_rec * GPBA_REC_STRIDE)); CKR(d_rec_lite.alloc((size_t)n_rec * GPBA_REC_LITE_STRIDE));
   CKR(d_recS.alloc((size_t)n_rec * 27)); CKR(d_Y.alloc((size_t)n_rec * 6));
-  CKR(d_prior_rho.alloc((size_t)n_prior + n_velp));
+  CKR(d_prior_rho.alloc((size_t)n_prior + n_velp + n_cam));
   ilap("measurement upload enqueued");
   CK(cudaStreamSynchronize(stream));
   ilap("final sync");
@@ -450,7 +474,10 @@ int Solver::init(const gpba_problem* P, int dev, bool async_upload) {
 
 void Solver::fill_view() {
   V.n_cam = n_cam; V.n_kf = n_kf; V.n_pt = n_pt; V.n_rec = n_rec; V.n_prior = n_prior; V.n_velp = n_velp;
-  V.cam = d_cam.p; V.kf_time = d_time.p; V.kf_h = d_kf_h.p;
+  V.cam = d_cam[cur].p; V.kf_time = d_time.p; V.kf_h = d_kf_h.p;
+  V.n_pose_kf = n_pose_kf; V.ext_h = d_ext_h.p; V.ext_prior_on = d_ext_prior_on.p;
+  V.ext_prior_qinv = d_ext_prior_qinv.p; V.ext_prior_info = d_ext_prior_info.p;
+  V.rec_hpp13 = d_rec_hpp13.p; V.rec_hpp23 = d_rec_hpp23.p; V.rec_hpp33 = d_rec_hpp33.p;
   V.rec_kf1 = d_rec_kf1.p; V.rec_kf2 = d_rec_kf2.p; V.rec_cam = d_rec_cam.p; V.rec_t = d_rec_t.p;
   V.prior_kf1 = d_prior_kf1.p; V.prior_kf2 = d_prior_kf2.p; V.velp_kf = d_velp_kf.p;
   for (int i = 0; i < 6; ++i) V.qc_inv[i] = 1.0 / qc[i];  // GaussianProcess::mQcInv of a diagonal Qc
@@ -548,6 +575,21 @@ int Solver::build_structure() {
   n_pose = 0;
   for (int k = 0; k < n_kf; ++k)
     if (kf_act[k] && !kf_fixed[k]) kf_h[k] = n_pose++;
+  n_pose_kf = n_pose;
+  // free extrinsic vertices follow the keyframes (their vertex ids are larger, Optimizer.cc:986); a vertex is active iff it
+  // carries an active edge: its EdgeExtrinsicPrior (active iff the vertex is not fixed) or an active GP edge of its camera
+  {
+    std::vector<char> cam_act(n_cam, 0);
+    for (int r = 0; r < n_rec; ++r) if (rec_used[r] && rec_kf1[r] >= 0) cam_act[rec_cam[r]] = 1;
+    std::vector<unsigned char> prior_act(n_cam, 0);
+    for (int c = 0; c < n_cam; ++c) {
+      ext_h[c] = (ext_free[c] && (ext_prior_on[c] || cam_act[c])) ? n_pose++ : -1;
+      prior_act[c] = ext_h[c] >= 0 && ext_prior_on[c];
+    }
+    CKR(d_ext_h.upload(ext_h, stream)); CKR(d_ext_prior_on.upload(prior_act, stream));
+    CKR(d_ext_prior_qinv.upload(ext_prior_qinv, stream)); CKR(d_ext_prior_info.upload(ext_prior_info, stream));
+    CK(cudaStreamSynchronize(stream));   // prior_act goes out of scope
+  }
   CKR(d_kf_h.upload(kf_h, stream));
   // --- landmark order: ascending first keyframe, ties by point id (stable radix sort of the points);
   //     g2o landmark index = rank among active points in ascending id (exclusive scan of the activity flags)
@@ -793,7 +835,11 @@ int Solver::build_structure() {
   for (int i = 0; i < n_pose; ++i) pp_rows[i].push_back(i);
   for (int i = 0; i < n_prior; ++i) add_pair(pp_rows, kf_h[prior_kf1[i]], kf_h[prior_kf2[i]]);
   for (int r = 0; r < n_rec; ++r)
-    if (rec_used[r] && rec_kf1[r] >= 0) add_pair(pp_rows, kf_h[rec_kf1[r]], kf_h[rec_kf2[r]]);
+    if (rec_used[r] && rec_kf1[r] >= 0) {
+      add_pair(pp_rows, kf_h[rec_kf1[r]], kf_h[rec_kf2[r]]);
+      const int h3 = ext_h[rec_cam[r]];   // EdgeMonoGPExtrinsic also links both keyframes to the extrinsic
+      if (h3 >= 0) { add_pair(pp_rows, kf_h[rec_kf1[r]], h3); add_pair(pp_rows, kf_h[rec_kf2[r]], h3); }
+    }
   for (auto& v : pp_rows) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
   std::vector<unsigned long long> hpp_key;   // (col << 32 | row), sorted: the order of SparseBlockMatrix columns
   for (int r = 0; r < n_pose; ++r) for (int c : pp_rows[r]) hpp_key.push_back(((unsigned long long)c << 32) | (unsigned)r);
@@ -808,8 +854,17 @@ int Solver::build_structure() {
     if (h2 >= 0) b22 = pp(h2, h2);
     if (h1 >= 0 && h2 >= 0) b12 = h1 <= h2 ? pp(h1, h2) : (pp(h2, h1) | 0x40000000);
   };
+  std::vector<int> rec13(n_rec, -1), rec23(n_rec, -1), rec33(n_rec, -1);
   for (int r = 0; r < n_rec; ++r)
-    if (rec_used[r]) pair_blocks(rec_kf1[r] >= 0 ? kf_h[rec_kf1[r]] : -1, kf_h[rec_kf2[r]], rec11[r], rec12[r], rec22[r]);
+    if (rec_used[r]) {
+      pair_blocks(rec_kf1[r] >= 0 ? kf_h[rec_kf1[r]] : -1, kf_h[rec_kf2[r]], rec11[r], rec12[r], rec22[r]);
+      const int h3 = rec_kf1[r] >= 0 ? ext_h[rec_cam[r]] : -1;
+      if (h3 >= 0) {
+        rec33[r] = pp(h3, h3);
+        if (kf_h[rec_kf1[r]] >= 0) rec13[r] = pp(kf_h[rec_kf1[r]], h3);
+        if (kf_h[rec_kf2[r]] >= 0) rec23[r] = pp(kf_h[rec_kf2[r]], h3);
+      }
+    }
   for (int i = 0; i < n_prior; ++i) pair_blocks(kf_h[prior_kf1[i]], kf_h[prior_kf2[i]], pr11[i], pr12[i], pr22[i]);
   std::vector<int> pose_diag(n_pose);
   for (int i = 0; i < n_pose; ++i) pose_diag[i] = pp(i, i);
@@ -817,7 +872,7 @@ int Solver::build_structure() {
   DBuf<unsigned long long> d_hs_key;
   {
     const int npat = (int)pat_key->size();
-    const size_t nk = (size_t)npat * 4 + hpp_key.size();
+    const size_t nk = (size_t)npat * GPBA_KEYS_PER_RP + hpp_key.size();
     DBuf<unsigned long long> d_patk, kin, kout;
     DBuf<int> d_nsel;
     CKR(kin.alloc(nk)); CKR(kout.alloc(nk)); CKR(d_hs_key.alloc(nk)); CKR(d_nsel.alloc(1));
@@ -827,7 +882,7 @@ int Solver::build_structure() {
       k_emit_block_keys<<<(npat + 255) / 256, 256, 0, stream>>>(V, npat, src, kin.p);
       CK(cudaGetLastError());
     }
-    if (!hpp_key.empty()) CK(cudaMemcpyAsync(kin.p + (size_t)npat * 4, hpp_key.data(), sizeof(unsigned long long) * hpp_key.size(), cudaMemcpyHostToDevice, stream));
+    if (!hpp_key.empty()) CK(cudaMemcpyAsync(kin.p + (size_t)npat * GPBA_KEYS_PER_RP, hpp_key.data(), sizeof(unsigned long long) * hpp_key.size(), cudaMemcpyHostToDevice, stream));
     size_t need = 0;
     CK(cub::DeviceRadixSort::SortKeys(nullptr, need, kin.p, kout.p, (int)nk, 0, 64, stream));
     CK(cub_tmp.reserve(need, stream));
@@ -891,7 +946,7 @@ int Solver::build_structure() {
       CK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, need, gcnt.p, gstart.p, h_groups, stream));
       k_mark_groups<<<(h_groups + 255) / 256, 256, 0, stream>>>(h_groups, gstart.p, gcnt.p, d_con.p);
     }
-    k_con_begin<<<(n_hs + 256) / 256, 256, 0, stream>>>(n_hs, h_valid, 2ull * (unsigned long long)n_rec, kout.p, d_con_begin.p);
+    k_con_begin<<<(n_hs + 256) / 256, 256, 0, stream>>>(n_hs, h_valid, 4ull * (unsigned long long)n_rec, kout.p, d_con_begin.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(stream));
   } else {
@@ -930,6 +985,7 @@ int Solver::build_structure() {
   // --- upload
   CKR(d_rseg_rec.upload(rseg_rec, stream)); CKR(d_rseg_begin.upload(rseg_begin, stream));
   CKR(d_rec_hpp11.upload(rec11, stream)); CKR(d_rec_hpp12.upload(rec12, stream)); CKR(d_rec_hpp22.upload(rec22, stream));
+  CKR(d_rec_hpp13.upload(rec13, stream)); CKR(d_rec_hpp23.upload(rec23, stream)); CKR(d_rec_hpp33.upload(rec33, stream));
   CKR(d_prior_hpp11.upload(pr11, stream)); CKR(d_prior_hpp12.upload(pr12, stream)); CKR(d_prior_hpp22.upload(pr22, stream));
   CKR(d_pose_hpp_diag.upload(pose_diag, stream));
   // --- storage
@@ -1133,6 +1189,19 @@ int Solver::capture_cholesky_graph() {
   return GPBA_OK;
 }
 
+// per-camera constants of a state buffer from its extrinsics (after a state reload: pop, reset)
+__global__ void k_refresh_cams(int n_cam, const double* __restrict__ ext, CamConst* __restrict__ cam) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cam) return;
+  CamConst cc = cam[c];
+  cam_from_tbc(load_se3(ext + 7 * c), cc);
+  cam[c] = cc;
+}
+int Solver::refresh_cams() {
+  for (int b = 0; b < 2; ++b) { k_refresh_cams<<<(n_cam + 31) / 32, 32, 0, stream>>>(n_cam, d_ext[b].p, d_cam[b].p); CK(cudaGetLastError()); }
+  return GPBA_OK;
+}
+
 // computeLambdaInit helpers: diagonal of the pose blocks, max |diagonal| of the landmark blocks
 __global__ void k_hpp_diag(int n_pose, const int* __restrict__ pose_diag, const double* __restrict__ hpp, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1151,8 +1220,8 @@ __global__ void __launch_bounds__(256) k_hll_absmax(int n_lm, const double* __re
 
 int Solver::compute_records(int buf, bool full) {
   t0();
-  if (full) k_records<true><<<(n_rec + 63) / 64, 64, 0, stream>>>(V, d_pose[buf].p, d_vel[buf].p, d_rec.p);
-  else k_records<false><<<(n_rec + 63) / 64, 64, 0, stream>>>(V, d_pose[buf].p, d_vel[buf].p, d_rec_lite.p);
+  if (full) k_records<true><<<(n_rec + 63) / 64, 64, 0, stream>>>(Vb(buf), d_pose[buf].p, d_vel[buf].p, d_rec.p);
+  else k_records<false><<<(n_rec + 63) / 64, 64, 0, stream>>>(Vb(buf), d_pose[buf].p, d_vel[buf].p, d_rec_lite.p);
   CK(cudaGetLastError());
   t1(0, 1);
   return GPBA_OK;
@@ -1175,8 +1244,8 @@ int Solver::compute_errors(int buf, bool store, double* chi2, bool trial, const 
   CKR(compute_records(buf, false));
   t0();
   double* out = store ? (chi2_store_override ? chi2_store_override : d_chi2.p) : nullptr;
-  if (stereo) k_residual<true><<<grid_obs, 256, 0, stream>>>(V, d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
-  else k_residual<false><<<grid_obs, 256, 0, stream>>>(V, d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
+  if (stereo) k_residual<true><<<grid_obs, 256, 0, stream>>>(Vb(buf), d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
+  else k_residual<false><<<grid_obs, 256, 0, stream>>>(Vb(buf), d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
   CK(cudaGetLastError());
   const int np = n_prior + (n_velp + 63) / 64;
   const bool priors_here = rank == 0;  // priors are replicated: counted once
@@ -1184,11 +1253,15 @@ int Solver::compute_errors(int buf, bool store, double* chi2, bool trial, const 
     k_priors<<<np, 64, 0, stream>>>(V, d_pose[buf].p, d_vel[buf].p, 0, d_prior_rho.p, nullptr, nullptr);
     CK(cudaGetLastError());
   }
-  k_reduce<<<1, 256, 0, stream>>>(d_partial.p, n_aobs > 0 ? grid_obs : 0, d_prior_rho.p, priors_here ? n_prior + n_velp : 0, d_scal.p);
+  if (priors_here) {   // EdgeExtrinsicPrior of the free extrinsics (zero for the others)
+    k_ext_prior<<<(n_cam + 31) / 32, 32, 0, stream>>>(V, d_ext[buf].p, 0, d_prior_rho.p + n_prior + n_velp, nullptr, nullptr);
+    CK(cudaGetLastError());
+  }
+  k_reduce<<<1, 256, 0, stream>>>(d_partial.p, n_aobs > 0 ? grid_obs : 0, d_prior_rho.p, priors_here ? n_prior + n_velp + n_cam : 0, d_scal.p);
   CK(cudaGetLastError());
   k_pack_trial<<<1, 32, 0, stream>>>(d_scal.p, d_fail.p, trial ? 1 : 0, (stop && *stop) ? 1.0 : 0.0);
   CK(cudaGetLastError());
-  t1(1, 4);
+  t1(1, 5);
   if (nranks > 1) CKR(allreduce_scalar(d_scal.p, 4));
   CK(cudaMemcpyAsync(h_scal, d_scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
@@ -1210,14 +1283,14 @@ int Solver::build_system() {
     CK(cudaMemsetAsync(d_hll.p, 0, sizeof(double) * 9 * (size_t)n_lm, stream));
     CK(cudaMemsetAsync(d_bl.p, 0, sizeof(double) * 3 * (size_t)n_lm, stream));
     const int g = (int)std::min<int64_t>((n_aobs + GPBA_K2_THREADS - 1) / GPBA_K2_THREADS, 148 * 8);
-    if (stereo) k_lin_points<true><<<g, GPBA_K2_THREADS, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
-    else k_lin_points<false><<<g, GPBA_K2_THREADS, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
+    if (stereo) k_lin_points<true><<<g, GPBA_K2_THREADS, 0, stream>>>(Vb(cur), d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
+    else k_lin_points<false><<<g, GPBA_K2_THREADS, 0, stream>>>(Vb(cur), d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
     CK(cudaGetLastError());
     t1(2, 1);
     t0();
     const int g2 = std::min((n_rseg + 3) / 4, 148 * 16);
-    if (stereo) k_lin_records<true><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p, d_r_u.p, d_r_v.p, d_r_ur.p, d_r_w.p, d_r_lm.p, d_r_flags.p);
-    else k_lin_records<false><<<g2, 128, 0, stream>>>(V, d_rec.p, d_ptS[cur].p, d_recS.p, d_r_u.p, d_r_v.p, nullptr, d_r_w.p, d_r_lm.p, d_r_flags.p);
+    if (stereo) k_lin_records<true><<<g2, 128, 0, stream>>>(Vb(cur), d_rec.p, d_ptS[cur].p, d_recS.p, d_r_u.p, d_r_v.p, d_r_ur.p, d_r_w.p, d_r_lm.p, d_r_flags.p);
+    else k_lin_records<false><<<g2, 128, 0, stream>>>(Vb(cur), d_rec.p, d_ptS[cur].p, d_recS.p, d_r_u.p, d_r_v.p, nullptr, d_r_w.p, d_r_lm.p, d_r_flags.p);
     CK(cudaGetLastError());
     k_rec_to_hpp<<<n_rec, 128, 0, stream>>>(V, d_rec.p, d_recS.p, d_hpp.p, d_bp.p);
     CK(cudaGetLastError());
@@ -1226,6 +1299,11 @@ int Solver::build_system() {
   const int np = n_prior + (n_velp + 63) / 64;
   if (np > 0 && rank == 0) {
     k_priors<<<np, 64, 0, stream>>>(V, d_pose[cur].p, d_vel[cur].p, 1, nullptr, d_hpp.p, d_bp.p);
+    CK(cudaGetLastError());
+    launches++;
+  }
+  if (rank == 0 && n_pose > n_pose_kf) {
+    k_ext_prior<<<(n_cam + 31) / 32, 32, 0, stream>>>(V, d_ext[cur].p, 1, nullptr, d_hpp.p, d_bp.p);
     CK(cudaGetLastError());
     launches++;
   }
@@ -1345,6 +1423,10 @@ int Solver::apply_update(double lambda, double* scale) {
   // rank contributes x_p . b_p^(rank) and rank 0 alone adds lambda |x_p|^2: the all-reduced sum is x_p . (lambda x_p + b_p).
   k_update_poses<<<(n_kf + 63) / 64, 64, 0, stream>>>(V, rank == 0 ? lambda : 0.0, d_x.p, d_bp.p, d_pose[cur].p, d_vel[cur].p, d_pose[nb].p, d_vel[nb].p, d_pose_scale.p);
   CK(cudaGetLastError());
+  if (n_pose > n_pose_kf) {   // free extrinsics: Tbc (+) x and the per-camera constants of the trial state
+    k_update_ext<<<(n_cam + 31) / 32, 32, 0, stream>>>(V, rank == 0 ? lambda : 0.0, d_x.p, d_bp.p, d_ext[cur].p, d_ext[nb].p, d_cam[cur].p, d_cam[nb].p, d_pose_scale.p);
+    CK(cudaGetLastError());
+  }
   k_reduce<<<1, 256, 0, stream>>>(d_partial.p, gp, d_pose_scale.p, n_pose, d_scal.p + 1);
   CK(cudaGetLastError());
   t1(8, 4);
@@ -1738,6 +1820,7 @@ int gpba_get_hpl(gpba_handle* h, int64_t* lm_begin, int32_t* pose, double* block
       const int r = orec[j];
       if (s.rec_kf1[r] >= 0 && s.kf_h[s.rec_kf1[r]] >= 0) poses.push_back(s.kf_h[s.rec_kf1[r]]);
       if (s.kf_h[s.rec_kf2[r]] >= 0) poses.push_back(s.kf_h[s.rec_kf2[r]]);
+      if (s.rec_kf1[r] >= 0 && s.ext_h[s.rec_cam[r]] >= 0) poses.push_back(s.ext_h[s.rec_cam[r]]);
     }
     std::sort(poses.begin(), poses.end());
     poses.erase(std::unique(poses.begin(), poses.end()), poses.end());
@@ -1749,15 +1832,15 @@ int gpba_get_hpl(gpba_handle* h, int64_t* lm_begin, int32_t* pose, double* block
       for (int64_t j = s.lm_obs_begin[l]; j < s.lm_obs_begin[l + 1]; ++j) {
         const int r = orec[j];
         const double* M = R.data() + (size_t)r * GPBA_REC_STRIDE + GPBA_REC_M;
-        for (int which = 0; which < 2; ++which) {
-          const int k = which ? s.rec_kf2[r] : s.rec_kf1[r];
-          const int hh = k >= 0 ? s.kf_h[k] : -1;
+        for (int which = 0; which < 3; ++which) {
+          const int k = which == 1 ? s.rec_kf2[r] : s.rec_kf1[r];
+          const int hh = which == 2 ? (k >= 0 ? s.ext_h[s.rec_cam[r]] : -1) : (k >= 0 ? s.kf_h[k] : -1);
           if (hh < 0) continue;
           const size_t slot = cursor + (std::lower_bound(poses.begin(), poses.end(), hh) - poses.begin());
           for (int c12 = 0; c12 < 12; ++c12)
             for (int c = 0; c < 3; ++c) {
               double acc = 0.0;
-              for (int m = 0; m < 6; ++m) acc += M[m * 24 + 12 * which + c12] * W[(size_t)j * 18 + m * 3 + c];
+              for (int m = 0; m < 6; ++m) acc += M[m * GPBA_REC_MS + 12 * which + c12] * W[(size_t)j * 18 + m * 3 + c];
               blocks[slot * 36 + c12 * 3 + c] += acc;
             }
         }
@@ -1786,6 +1869,11 @@ int gpba_oplus(gpba_handle* h, const double* x) {
     k_update_poses<<<(s.n_kf + 63) / 64, 64, 0, s.stream>>>(s.V, 0.0, s.d_x.p, s.d_bp.p, s.d_pose[s.cur].p, s.d_vel[s.cur].p,
                                                            s.d_pose[1 - s.cur].p, s.d_vel[1 - s.cur].p, s.d_pose_scale.p);
     CK(cudaGetLastError());
+    if (s.n_pose > s.n_pose_kf) {
+      k_update_ext<<<(s.n_cam + 31) / 32, 32, 0, s.stream>>>(s.V, 0.0, s.d_x.p, s.d_bp.p, s.d_ext[s.cur].p, s.d_ext[1 - s.cur].p,
+                                                            s.d_cam[s.cur].p, s.d_cam[1 - s.cur].p, s.d_pose_scale.p);
+      CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(s.stream));
   }
   // x == NULL: gpba_solve already wrote state (+) x into the other buffer
@@ -1795,13 +1883,14 @@ int gpba_oplus(gpba_handle* h, const double* x) {
 int gpba_push(gpba_handle* h) {
   NEED_STRUCT(h);
   Solver& s = S(h);
-  std::vector<double> p((size_t)s.n_kf * 7), v((size_t)s.n_kf * 6), q((size_t)s.n_lm * 3);
+  std::vector<double> p((size_t)s.n_kf * 7), v((size_t)s.n_kf * 6), q((size_t)s.n_lm * 3), x((size_t)s.n_cam * 7);
   CK(cudaStreamSynchronize(s.stream));
+  CK(cudaMemcpyAsync(x.data(), s.d_ext[s.cur].p, x.size() * 8, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaMemcpyAsync(p.data(), s.d_pose[s.cur].p, p.size() * 8, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaMemcpyAsync(v.data(), s.d_vel[s.cur].p, v.size() * 8, cudaMemcpyDeviceToHost, s.stream));
   if (s.n_lm) CK(cudaMemcpyAsync(q.data(), s.d_ptS[s.cur].p, q.size() * 8, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
-  s.stack_pose.push_back(p); s.stack_vel.push_back(v); s.stack_pt.push_back(q);
+  s.stack_pose.push_back(p); s.stack_vel.push_back(v); s.stack_pt.push_back(q); s.stack_ext.push_back(x);
   return GPBA_OK;
 }
 int gpba_pop(gpba_handle* h) {
@@ -1812,16 +1901,18 @@ int gpba_pop(gpba_handle* h) {
     CK(cudaMemcpyAsync(s.d_pose[b].p, s.stack_pose.back().data(), s.stack_pose.back().size() * 8, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_vel[b].p, s.stack_vel.back().data(), s.stack_vel.back().size() * 8, cudaMemcpyHostToDevice, s.stream));
     if (s.n_lm) CK(cudaMemcpyAsync(s.d_ptS[b].p, s.stack_pt.back().data(), s.stack_pt.back().size() * 8, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_ext[b].p, s.stack_ext.back().data(), s.stack_ext.back().size() * 8, cudaMemcpyHostToDevice, s.stream));
   }
+  CKR(s.refresh_cams());
   CK(cudaStreamSynchronize(s.stream));
-  s.stack_pose.pop_back(); s.stack_vel.pop_back(); s.stack_pt.pop_back();
+  s.stack_pose.pop_back(); s.stack_vel.pop_back(); s.stack_pt.pop_back(); s.stack_ext.pop_back();
   return GPBA_OK;
 }
 int gpba_discard_top(gpba_handle* h) {
   NEED_STRUCT(h);
   Solver& s = S(h);
   if (s.stack_pose.empty()) { g_err = "discardTop on empty stack"; return GPBA_ERR_STATE; }
-  s.stack_pose.pop_back(); s.stack_vel.pop_back(); s.stack_pt.pop_back();
+  s.stack_pose.pop_back(); s.stack_vel.pop_back(); s.stack_pt.pop_back(); s.stack_ext.pop_back();
   return GPBA_OK;
 }
 
@@ -1867,7 +1958,9 @@ int gpba_active_robust_chi2(gpba_handle* h, double* chi2) {
   CK(cudaGetLastError());
   const int np = s.n_prior + (s.n_velp + 63) / 64;
   if (np > 0) { k_priors<<<np, 64, 0, s.stream>>>(s.V, s.d_pose[s.last_eval].p, s.d_vel[s.last_eval].p, 0, s.d_prior_rho.p, nullptr, nullptr); CK(cudaGetLastError()); }
-  k_reduce<<<1, 256, 0, s.stream>>>(s.d_partial.p, g, s.d_prior_rho.p, s.n_prior + s.n_velp, s.d_scal.p + 2);
+  k_ext_prior<<<(s.n_cam + 31) / 32, 32, 0, s.stream>>>(s.V, s.d_ext[s.last_eval].p, 0, s.d_prior_rho.p + s.n_prior + s.n_velp, nullptr, nullptr);
+  CK(cudaGetLastError());
+  k_reduce<<<1, 256, 0, s.stream>>>(s.d_partial.p, g, s.d_prior_rho.p, s.n_prior + s.n_velp + s.n_cam, s.d_scal.p + 2);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(s.h_scal + 2, s.d_scal.p + 2, 8, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
@@ -1883,7 +1976,7 @@ int gpba_outlier_flags(gpba_handle* h, const gpba_thresholds* th, uint8_t* flags
   DBuf<uint8_t> d_flags;
   CKR(d_flags.alloc((size_t)s.n_obs));
   const int g = (int)std::min<int64_t>((s.n_obs + 255) / 256 + 1, 148 * 8);
-  k_flags<<<g, 256, 0, s.stream>>>(s.V, s.n_obs, s.d_chi2.p, s.stereo ? s.d_all_ur.p : nullptr, s.d_all_rec.p, s.d_all_flags.p, nullptr,
+  k_flags<<<g, 256, 0, s.stream>>>(s.Vb(s.cur), s.n_obs, s.d_chi2.p, s.stereo ? s.d_all_ur.p : nullptr, s.d_all_rec.p, s.d_all_flags.p, nullptr,
                                    s.d_all_pt.p, s.d_pt_full.p, s.d_pose[s.cur].p, th->chi2_mono, th->chi2_mono_close, th->chi2_stereo, d_flags.p);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(flags, d_flags.p, (size_t)s.n_obs, cudaMemcpyDeviceToHost, s.stream));
@@ -1928,7 +2021,7 @@ int gpba_compute_errors_inactive(gpba_handle* h) {
   CKR(s.scatter_points(s.cur));
   CKR(s.compute_records(s.cur, false));
   const int g = (int)std::min<int64_t>((s.n_obs + 255) / 256 + 1, 148 * 8);
-  k_chi2_inactive<<<g, 256, 0, s.stream>>>(s.V, s.n_obs, s.d_all_flags.p, s.d_all_rec.p, s.d_all_pt.p, s.d_all_u.p, s.d_all_v.p,
+  k_chi2_inactive<<<g, 256, 0, s.stream>>>(s.Vb(s.cur), s.n_obs, s.d_all_flags.p, s.d_all_rec.p, s.d_all_pt.p, s.d_all_u.p, s.d_all_v.p,
                                            s.stereo ? s.d_all_ur.p : nullptr, s.d_all_w.p, s.d_rec_lite.p, s.d_pt_full.p, s.d_chi2.p);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s.stream));
@@ -1950,6 +2043,78 @@ int gpba_rejection_rounds(gpba_handle* h, int n_rounds, int iters, const gpba_th
   }
   if (flags_out) std::memcpy(flags_out, fl.data(), fl.size());
   return GPBA_OK;
+}
+
+// ---- extrinsic self-calibration (LocalGPBA's second stage, src/Optimizer.cc:983-995, 1228-1240, 1419-1428)
+int gpba_set_extrinsics(gpba_handle* h, const gpba_extrinsics* e) {
+  NEED(h);
+  Solver& s = S(h);
+  if (!e || !e->free_mask) { g_err = "null argument"; return GPBA_ERR_INVALID; }
+  if ((e->prior_R == nullptr) != (e->prior_info == nullptr)) { g_err = "prior_R and prior_info go together"; return GPBA_ERR_INVALID; }
+  bool any = false;
+  for (int c = 0; c < s.n_cam; ++c) any = any || e->free_mask[c];
+  if (any && s.nranks > 1) { g_err = "extrinsic self-calibration belongs to the local BA: single GPU only"; return GPBA_ERR_INVALID; }
+  for (int c = 0; c < s.n_cam; ++c) {
+    s.ext_free[c] = e->free_mask[c] ? 1 : 0;
+    s.ext_prior_on[c] = e->prior_R ? 1 : 0;
+    if (e->prior_R) {
+      Quat q; q.x = e->prior_R[4 * c]; q.y = e->prior_R[4 * c + 1]; q.z = e->prior_R[4 * c + 2]; q.w = e->prior_R[4 * c + 3];
+      const Quat qi = quat_inv(q);   // EdgeExtrinsicPrior keeps R_ini^-1 (G2oTypes.h:474)
+      s.ext_prior_qinv[4 * c] = qi.x; s.ext_prior_qinv[4 * c + 1] = qi.y; s.ext_prior_qinv[4 * c + 2] = qi.z; s.ext_prior_qinv[4 * c + 3] = qi.w;
+      for (int k = 0; k < 9; ++k) s.ext_prior_info[9 * c + k] = e->prior_info[9 * c + k];
+    }
+  }
+  s.structure_dirty = true;   // takes effect at the next build_structure / optimize (initializeOptimization, :1238)
+  return GPBA_OK;
+}
+int gpba_get_extrinsics(gpba_handle* h, double* cam_Tbc) {
+  NEED(h);
+  Solver& s = S(h);
+  if (!cam_Tbc) { g_err = "null argument"; return GPBA_ERR_INVALID; }
+  CK(cudaSetDevice(s.device));
+  CK(cudaMemcpyAsync(cam_Tbc, s.d_ext[s.cur].p, sizeof(double) * 7 * (size_t)s.n_cam, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return GPBA_OK;
+}
+__global__ void k_count_cam_obs(int64_t n_obs, const int* __restrict__ obs_rec, const int* __restrict__ rec_kf1, const int* __restrict__ rec_cam,
+                                unsigned long long* __restrict__ cnt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = obs_rec[i];
+    if (rec_kf1[r] >= 0) atomicAdd(&cnt[rec_cam[r]], 1ull);
+  }
+}
+int gpba_count_camera_observations(gpba_handle* h, int64_t* cam_obs) {
+  NEED(h);
+  Solver& s = S(h);
+  if (!cam_obs) { g_err = "null argument"; return GPBA_ERR_INVALID; }
+  CK(cudaSetDevice(s.device));
+  DBuf<unsigned long long> d_cnt;
+  CKR(d_cnt.alloc((size_t)s.n_cam));
+  CK(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long) * (size_t)s.n_cam, s.stream));
+  if (s.n_obs > 0) {
+    k_count_cam_obs<<<(int)std::min<int64_t>((s.n_obs + 255) / 256, 148 * 8), 256, 0, s.stream>>>(s.n_obs, s.d_all_rec.p, s.d_rec_kf1.p, s.d_rec_cam.p, d_cnt.p);
+    CK(cudaGetLastError());
+  }
+  std::vector<unsigned long long> c((size_t)s.n_cam);
+  CK(cudaMemcpyAsync(c.data(), d_cnt.p, sizeof(unsigned long long) * (size_t)s.n_cam, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  for (int i = 0; i < s.n_cam; ++i) cam_obs[i] = (int64_t)c[i];
+  return GPBA_OK;
+}
+int gpba_calibrate_extrinsics(gpba_handle* h, const gpba_extrinsics* candidates, int min_obs, int iters, const gpba_lm_params* params,
+                              gpba_lm_trace* trace, uint8_t* freed_out) {
+  NEED(h);
+  Solver& s = S(h);
+  if (!candidates || !candidates->free_mask) { g_err = "null argument"; return GPBA_ERR_INVALID; }
+  std::vector<int64_t> cam_obs((size_t)s.n_cam);
+  CKR(gpba_count_camera_observations(h, cam_obs.data()));
+  std::vector<uint8_t> fr((size_t)s.n_cam, 0);
+  for (int c = 0; c < s.n_cam; ++c) fr[c] = candidates->free_mask[c] && cam_obs[c] >= min_obs;   // "if (cam_obs[i] < extrin_thresh) continue" (:1232)
+  gpba_extrinsics e = *candidates;
+  e.free_mask = fr.data();
+  CKR(gpba_set_extrinsics(h, &e));
+  if (freed_out) std::memcpy(freed_out, fr.data(), fr.size());
+  return gpba_optimize(h, iters, nullptr, params, trace);   // initializeOptimization + computeActiveErrors + optimize(opt_it2) (:1238-1240)
 }
 
 int gpba_stage_stats(gpba_handle* h, double ms_total[GPBA_N_STAGES], int64_t launches[GPBA_N_STAGES], int reset) {
@@ -1995,6 +2160,12 @@ int gpba_reset_state(gpba_handle* h, const double* kf_pose, const double* kf_vel
   CK(cudaSetDevice(s.device));
   if (kf_pose) for (int b = 0; b < 2; ++b) CK(cudaMemcpyAsync(s.d_pose[b].p, kf_pose, sizeof(double) * 7 * (size_t)s.n_kf, cudaMemcpyHostToDevice, s.stream));
   if (kf_vel) for (int b = 0; b < 2; ++b) CK(cudaMemcpyAsync(s.d_vel[b].p, kf_vel, sizeof(double) * 6 * (size_t)s.n_kf, cudaMemcpyHostToDevice, s.stream));
+  if (s.any_ext_free()) {   // the extrinsics are part of the state: back to the ones the handle was created with
+    for (int b = 0; b < 2; ++b) {
+      CK(cudaMemcpyAsync(s.d_ext[b].p, s.h_ext0.data(), sizeof(double) * 7 * (size_t)s.n_cam, cudaMemcpyHostToDevice, s.stream));
+      CK(cudaMemcpyAsync(s.d_cam[b].p, s.h_cam0.data(), sizeof(CamConst) * (size_t)s.n_cam, cudaMemcpyHostToDevice, s.stream));
+    }
+  }
   if (pt_xyz) {
     CK(cudaMemcpyAsync(s.d_pt_full.p, pt_xyz, sizeof(double) * 3 * (size_t)s.n_pt, cudaMemcpyHostToDevice, s.stream));
     if (s.structure_ok && s.n_lm > 0) {

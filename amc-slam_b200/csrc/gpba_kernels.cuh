@@ -130,7 +130,7 @@ GPBA_D void eval_obs(const DevView& V, const double* __restrict__ R /* R_cw[9], 
 // ------------------------------------------------------------------------------------------------ K0
 // One record row: interpolated camera pose (R_cw | t_cw) and, if FULL, the 6 x 24 chain matrix M.
 // pose1 / vel1 == nullptr marks a synchronous record.
-template <bool FULL>
+template <bool FULL, int MS = GPBA_REC_MS>
 GPBA_D void record_row(const double* __restrict__ pose1, const double* __restrict__ vel1, double t1,
                        const double* __restrict__ pose2, const double* __restrict__ vel2, double t2, double t,
                        const CamConst& cam, double* __restrict__ out) {
@@ -166,10 +166,10 @@ GPBA_D void record_row(const double* __restrict__ pose1, const double* __restric
       for (int m = 0; m < 6; ++m)
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          M[m * 24 + c] = MT1(m, c);
-          M[m * 24 + 6 + c] = MV1(m, c);
-          M[m * 24 + 12 + c] = MT2(m, c);
-          M[m * 24 + 18 + c] = MV2(m, c);
+          M[m * MS + c] = MT1(m, c);
+          M[m * MS + 6 + c] = MV1(m, c);
+          M[m * MS + 12 + c] = MT2(m, c);
+          M[m * MS + 18 + c] = MV2(m, c);
         }
     }
   } else if (FULL) {
@@ -179,7 +179,7 @@ GPBA_D void record_row(const double* __restrict__ pose1, const double* __restric
 #pragma unroll
     for (int m = 0; m < 6; ++m)
 #pragma unroll
-      for (int c = 0; c < 24; ++c) M[m * 24 + c] = (c == 12 + m) ? 1.0 : 0.0;
+      for (int c = 0; c < 24; ++c) M[m * MS + c] = (c == 12 + m) ? 1.0 : 0.0;
   }
   SE3 Tbc;
   Tbc.q.x = cam.qbc[0]; Tbc.q.y = cam.qbc[1]; Tbc.q.z = cam.qbc[2]; Tbc.q.w = cam.qbc[3];
@@ -197,9 +197,18 @@ __global__ void k_records(DevView V, const double* __restrict__ pose, const doub
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= V.n_rec) return;
   const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
+  double* out = rec_out + (size_t)r * (FULL ? GPBA_REC_STRIDE : GPBA_REC_LITE_STRIDE);
+  const CamConst& cam = V.cam[V.rec_cam[r]];
   record_row<FULL>(k1 >= 0 ? pose + 7 * k1 : nullptr, k1 >= 0 ? vel + 6 * k1 : nullptr, k1 >= 0 ? V.kf_time[k1] : 0.0,
-                   pose + 7 * k2, vel + 6 * k2, V.kf_time[k2], V.rec_t[r], V.cam[V.rec_cam[r]],
-                   rec_out + (size_t)r * (FULL ? GPBA_REC_STRIDE : GPBA_REC_LITE_STRIDE));
+                   pose + 7 * k2, vel + 6 * k2, V.kf_time[k2], V.rec_t[r], cam, out);
+  if (FULL) {   // third slice: the extrinsic's 12-slot [Adj(T_bc) | 0] (EdgeMonoGPExtrinsic, src/G2oTypes.cc:311-313)
+    const bool ext = k1 >= 0 && V.ext_h[V.rec_cam[r]] >= 0;
+    double* M = out + GPBA_REC_M;
+#pragma unroll
+    for (int m = 0; m < 6; ++m)
+#pragma unroll
+      for (int c = 0; c < 12; ++c) M[m * GPBA_REC_MS + 24 + c] = (ext && c < 6) ? cam.AdjTbc[m * 6 + c] : 0.0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -364,15 +373,17 @@ __global__ void __launch_bounds__(128, 3) k_lin_records(DevView V, const double*
 }
 
 // ------------------------------------------------------------------------------------------------ K2c
-// One CTA per record: Hpp blocks += M_r^T S_r M_r, b_p += M_r^T g_r.
+// One CTA per record: Hpp blocks += M_r^T S_r M_r, b_p += M_r^T g_r, over the record's (up to) three pose-like vertices:
+// previous keyframe, current keyframe, extrinsic (12-column slices 0, 1, 2 of M_r).
 __global__ void __launch_bounds__(128) k_rec_to_hpp(DevView V, const double* __restrict__ rec,
                                                     const double* __restrict__ recS, double* __restrict__ hpp,
                                                     double* __restrict__ bp) {
-  __shared__ double S[36], g[6], M[144], T[144];
+  __shared__ double S[36], g[6], M[6 * GPBA_REC_MS], T[6 * GPBA_REC_MS];
   const int r = blockIdx.x;
   const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
   const int h1 = k1 >= 0 ? V.kf_h[k1] : -1, h2 = V.kf_h[k2];
-  if (h1 < 0 && h2 < 0) return;
+  const int h3 = k1 >= 0 ? V.ext_h[V.rec_cam[r]] : -1;
+  if (h1 < 0 && h2 < 0 && h3 < 0) return;
   const int tid = threadIdx.x;
   if (tid < 27) {
     const double v = recS[(size_t)r * 27 + tid];
@@ -385,45 +396,51 @@ __global__ void __launch_bounds__(128) k_rec_to_hpp(DevView V, const double* __r
       g[tid - 21] = v;
     }
   }
-  const int b11 = V.rec_hpp11[r], b12 = V.rec_hpp12[r], b22 = V.rec_hpp22[r];
+  const int b22 = V.rec_hpp22[r];
   if (k1 < 0) {  // synchronous record: pose block = S, velocity rows/cols = 0
     __syncthreads();
+    if (h2 < 0) return;
     if (tid < 36) atomicAdd(&hpp[(size_t)b22 * 144 + (tid / 6) * 12 + (tid % 6)], S[tid]);
     if (tid < 6) atomicAdd(&bp[(size_t)h2 * 12 + tid], g[tid]);
     return;
   }
-  for (int j = tid; j < 144; j += blockDim.x) M[j] = rec[(size_t)r * GPBA_REC_STRIDE + GPBA_REC_M + j];
+  const int NC = h3 >= 0 ? 36 : 24;   // columns of M in use
+  for (int j = tid; j < 6 * GPBA_REC_MS; j += blockDim.x) M[j] = rec[(size_t)r * GPBA_REC_STRIDE + GPBA_REC_M + j];
   __syncthreads();
-  for (int j = tid; j < 144; j += blockDim.x) {
-    const int m = j / 24, c = j % 24;
+  for (int j = tid; j < 6 * GPBA_REC_MS; j += blockDim.x) {
+    const int m = j / GPBA_REC_MS, c = j % GPBA_REC_MS;
     double s = 0.0;
 #pragma unroll
-    for (int n = 0; n < 6; ++n) s = fma(S[m * 6 + n], M[n * 24 + c], s);
+    for (int n = 0; n < 6; ++n) s = fma(S[m * 6 + n], M[n * GPBA_REC_MS + c], s);
     T[j] = s;
   }
   __syncthreads();
-  for (int j = tid; j < 576; j += blockDim.x) {
-    const int ap = j / 24, bpp = j % 24;
+  const int hh[3] = {h1, h2, h3};
+  // block of slice pair (A, B), A <= B: 11, 12, 22, 13, 23, 33
+  const int blk_of[3][3] = {{V.rec_hpp11[r], V.rec_hpp12[r], V.rec_hpp13[r]}, {-1, b22, V.rec_hpp23[r]}, {-1, -1, V.rec_hpp33[r]}};
+  for (int j = tid; j < NC * NC; j += blockDim.x) {
+    const int ap = j / NC, bpp = j % NC;
     const int A = ap / 12, B = bpp / 12;
-    if (A > B) continue;
-    double s = 0.0;
-#pragma unroll
-    for (int m = 0; m < 6; ++m) s = fma(M[m * 24 + ap], T[m * 24 + bpp], s);
+    if (A > B || hh[A] < 0 || hh[B] < 0) continue;
     const int ra = ap % 12, cb = bpp % 12;
-    if (A == 0 && B == 0) { if (h1 >= 0) atomicAdd(&hpp[(size_t)b11 * 144 + ra * 12 + cb], s); }
-    else if (A == 1) { if (h2 >= 0) atomicAdd(&hpp[(size_t)b22 * 144 + ra * 12 + cb], s); }
-    else if (b12 >= 0) {
-      const int blk = b12 & 0x3fffffff;
-      if (b12 & 0x40000000) atomicAdd(&hpp[(size_t)blk * 144 + cb * 12 + ra], s);  // stored transposed
-      else atomicAdd(&hpp[(size_t)blk * 144 + ra * 12 + cb], s);
-    }
-  }
-  if (tid < 24) {
+    if ((A == 2 && ra >= 6) || (B == 2 && cb >= 6)) continue;   // padding of the extrinsic's slot
     double s = 0.0;
 #pragma unroll
-    for (int m = 0; m < 6; ++m) s = fma(M[m * 24 + tid], g[m], s);
-    const int hh = tid < 12 ? h1 : h2;
-    if (hh >= 0) atomicAdd(&bp[(size_t)hh * 12 + (tid % 12)], s);
+    for (int m = 0; m < 6; ++m) s = fma(M[m * GPBA_REC_MS + ap], T[m * GPBA_REC_MS + bpp], s);
+    const int b = blk_of[A][B];
+    if (b < 0) continue;
+    const int blk = b & 0x3fffffff;
+    if (b & 0x40000000) atomicAdd(&hpp[(size_t)blk * 144 + cb * 12 + ra], s);  // stored transposed
+    else atomicAdd(&hpp[(size_t)blk * 144 + ra * 12 + cb], s);
+  }
+  if (tid < NC) {
+    const int A = tid / 12;
+    if (hh[A] >= 0 && !(A == 2 && tid % 12 >= 6)) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) s = fma(M[m * GPBA_REC_MS + tid], g[m], s);
+      atomicAdd(&bp[(size_t)hh[A] * 12 + (tid % 12)], s);
+    }
   }
 }
 
@@ -664,7 +681,7 @@ __global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __r
 // warp shuffles.  Per contribution a lane issues 6 loads and 4 DMMAs (the scalar version issued 12 loads per thread of a
 // 72-thread half CTA and was L1-bound: ncu l1tex throughput 81 %, 0.83 ms at C4).  The block is written once, in a
 // fixed order: no atomics.  On diagonal blocks the diagonal record pairs also give bschur_i = b_p,i - sum M_L^T g'_r.
-struct HsContrib { int rp; int rL; int rR; int code; };  // code: bit0 slice of L, bit1 slice of R, bit2 transpose C, bit4 g' entry, bits 8.. group size (first entry)
+struct HsContrib { int rp; int rL; int rR; int code; };  // code: bits 0-1 slice of L, bits 2-3 slice of R (0 previous keyframe, 1 current keyframe, 2 extrinsic), bit 4 transpose C, bit 5 g' entry, bits 8.. group size (first entry)
 #define GPBA_K4C_WARPS 4
 __global__ void __launch_bounds__(32 * GPBA_K4C_WARPS) k_schur_expand(DevView V, double lambda, const double* __restrict__ rec,
                                                                      const double* __restrict__ hpp, const double* __restrict__ bp,
@@ -685,7 +702,12 @@ __global__ void __launch_bounds__(32 * GPBA_K4C_WARPS) k_schur_expand(DevView V,
       const int r = 8 * mt + gid, c = 8 * nt + 2 * tig;
       double2 v = make_double2(0.0, 0.0);
       if (src >= 0 && r < 12 && c < 12) v = *reinterpret_cast<const double2*>(hpp + (size_t)src * 144 + r * 12 + c);
-      if (diag >= 0 && r < 12) { if (r == c) v.x += lambda; if (r == c + 1) v.y += lambda; }
+      if (diag >= 0 && r < 12) {
+        // lambda on the diagonal; the padding dimensions of an extrinsic's 12-slot get a unit diagonal (zero rows otherwise)
+        const double pad = (diag >= V.n_pose_kf) ? 1.0 : 0.0;
+        if (r == c) v.x += lambda + (r >= 6 ? pad : 0.0);
+        if (r == c + 1) v.y += lambda + (r >= 6 ? pad : 0.0);
+      }
       acc[mt][nt] = v;
     }
   double bpart = 0.0;   // lanes < 12
@@ -699,28 +721,28 @@ __global__ void __launch_bounds__(32 * GPBA_K4C_WARPS) k_schur_expand(DevView V,
     for (int q = e; q < e + gs; ++q) {
       const HsContrib cn = q == e ? g : con[q];
       const double* Cp = C + (size_t)cn.rp * GPBA_RP_STRIDE;
-      const double* Mb = rec + (size_t)cn.rR * GPBA_REC_STRIDE + GPBA_REC_M + 12 * ((cn.code >> 1) & 1);
-      const int sm = (cn.code & 4) ? 1 : 8, sn = (cn.code & 4) ? 8 : 1;  // C^[m][n] = C[n][m] when transposed
+      const double* Mb = rec + (size_t)cn.rR * GPBA_REC_STRIDE + GPBA_REC_M + 12 * ((cn.code >> 2) & 3);
+      const int sm = (cn.code & 16) ? 1 : 8, sn = (cn.code & 16) ? 8 : 1;  // C^[m][n] = C[n][m] when transposed
       double a[2], b[2][2];
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         const int k = 4 * kk + tig;
         a[kk] = (gid < 6 && k < 6) ? Cp[gid * sm + k * sn] : 0.0;
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) b[kk][nt] = (k < 6 && 8 * nt + gid < 12) ? Mb[k * 24 + 8 * nt + gid] : 0.0;
+        for (int nt = 0; nt < 2; ++nt) b[kk][nt] = (k < 6 && 8 * nt + gid < 12) ? Mb[k * GPBA_REC_MS + 8 * nt + gid] : 0.0;
       }
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) dmma884(T[nt].x, T[nt].y, a[kk], b[kk][nt]);
-      if ((cn.code & 16) && lane < 12) {
-        const double* Ma = rec + (size_t)cn.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (cn.code & 1) + lane;
+      if ((cn.code & 32) && lane < 12) {
+        const double* Ma = rec + (size_t)cn.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (cn.code & 3) + lane;
 #pragma unroll
-        for (int mm = 0; mm < 6; ++mm) bpart = fma(Ma[mm * 24], Cp[mm * 8 + 6], bpart);
+        for (int mm = 0; mm < 6; ++mm) bpart = fma(Ma[mm * GPBA_REC_MS], Cp[mm * 8 + 6], bpart);
       }
     }
     // acc -= M_L^T T : A[m'][k] = -M_L[k][m'], B[k][n] = T[k][n] (accumulator layout -> B-operand layout by shuffles)
-    const double* Ma = rec + (size_t)g.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (g.code & 1);
+    const double* Ma = rec + (size_t)g.rL * GPBA_REC_STRIDE + GPBA_REC_M + 12 * (g.code & 3);
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       const int k = 4 * kk + tig;
@@ -733,7 +755,7 @@ __global__ void __launch_bounds__(32 * GPBA_K4C_WARPS) k_schur_expand(DevView V,
       }
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        const double am = (k < 6 && 8 * mt + gid < 12) ? -Ma[k * 24 + 8 * mt + gid] : 0.0;
+        const double am = (k < 6 && 8 * mt + gid < 12) ? -Ma[k * GPBA_REC_MS + 8 * mt + gid] : 0.0;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt].x, acc[mt][nt].y, am, bt[nt]);
       }
@@ -758,7 +780,8 @@ __global__ void k_rec_y(DevView V, const double* __restrict__ rec, const double*
   const int r = t / 6, m = t % 6;
   const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
   const int h1 = k1 >= 0 ? V.kf_h[k1] : -1, h2 = V.kf_h[k2];
-  const double* M = rec + (size_t)r * GPBA_REC_STRIDE + GPBA_REC_M + m * 24;
+  const int h3 = k1 >= 0 ? V.ext_h[V.rec_cam[r]] : -1;
+  const double* M = rec + (size_t)r * GPBA_REC_STRIDE + GPBA_REC_M + m * GPBA_REC_MS;
   double s = 0.0;
   if (h1 >= 0) {
 #pragma unroll
@@ -767,6 +790,10 @@ __global__ void k_rec_y(DevView V, const double* __restrict__ rec, const double*
   if (h2 >= 0) {
 #pragma unroll
     for (int c = 0; c < 12; ++c) s = fma(M[12 + c], xp[(size_t)h2 * 12 + c], s);
+  }
+  if (h3 >= 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s = fma(M[24 + c], xp[(size_t)h3 * 12 + c], s);
   }
   Y[t] = s;
 }
@@ -825,6 +852,88 @@ __global__ void k_update_poses(DevView V, double lambda, const double* __restric
   for (int i = 0; i < 6; ++i) vel_new[6 * k + i] = vel_cur[6 * k + i] + x[6 + i];
   for (int i = 0; i < 12; ++i) sc += x[i] * (lambda * x[i] + bp[(size_t)h * 12 + i]);
   pose_scale[h] = sc;
+}
+
+// Extrinsics: Tbc <- Tbc * exp(x[0:6])  (VertexExtrinsic::oplusImpl, include/G2oTypes.h:98-100); fixed ones are copied.
+// One thread per camera; also derives the per-camera constants of the new state.
+GPBA_D void cam_from_tbc(const SE3& Tbc, CamConst& cc) {
+  const SE3 Tcb = se3_inv(Tbc);
+  const M3 Rcb = quat_to_R(Tcb.q), Rbc = quat_to_R(Tbc.q);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { cc.Rcb[i] = Rcb.a[i]; cc.Rbc[i] = Rbc.a[i]; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { cc.tcb[i] = Tcb.t[i]; cc.tbc[i] = Tbc.t[i]; }
+  cc.qbc[0] = Tbc.q.x; cc.qbc[1] = Tbc.q.y; cc.qbc[2] = Tbc.q.z; cc.qbc[3] = Tbc.q.w;
+  const M6 A = se3_Adj(Tbc);
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) cc.AdjTbc[r * 6 + c] = A(r, c);
+}
+__global__ void k_update_ext(DevView V, double lambda, const double* __restrict__ xp, const double* __restrict__ bp,
+                             const double* __restrict__ ext_cur, double* __restrict__ ext_new, const CamConst* __restrict__ cam_cur,
+                             CamConst* __restrict__ cam_new, double* __restrict__ pose_scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= V.n_cam) return;
+  const int h = V.ext_h[c];
+  SE3 T = load_se3(ext_cur + 7 * c);
+  if (h >= 0) {
+    const double* x = xp + (size_t)h * 12;
+    T = se3_mul(T, se3_exp(load_v6(x)));
+    double sc = 0.0;
+    for (int i = 0; i < 6; ++i) sc += x[i] * (lambda * x[i] + bp[(size_t)h * 12 + i]);
+    pose_scale[h] = sc;   // the padding dimensions carry x = 0
+  }
+  store_se3(T, ext_new + 7 * c);
+  CamConst cc = cam_cur[c];
+  if (h >= 0) cam_from_tbc(T, cc);
+  cam_new[c] = cc;
+}
+
+// EdgeExtrinsicPrior (include/G2oTypes.h:470-494): e = Log(R_ini^-1 R_bc), J = [0 | Jr(e)^-1] (RightJacobianSO3 of
+// src/G2oTypes.cc:575-590, inverted like Eigen's fixed 3 x 3 inverse), information = MultiFrame::mRbc_ini_cov[c], no kernel.
+// One thread per camera.  mode 0: chi2 -> rho[c]; mode 1: Hpp / b of the extrinsic's rotation block.
+__global__ void k_ext_prior(DevView V, const double* __restrict__ ext, int mode, double* __restrict__ rho,
+                            double* __restrict__ hpp, double* __restrict__ bp) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= V.n_cam) return;
+  const int h = V.ext_h[c];
+  if (h < 0 || !V.ext_prior_on[c]) { if (mode == 0) rho[c] = 0.0; return; }
+  const SE3 T = load_se3(ext + 7 * c);
+  Quat qi; qi.x = V.ext_prior_qinv[4 * c]; qi.y = V.ext_prior_qinv[4 * c + 1]; qi.z = V.ext_prior_qinv[4 * c + 2]; qi.w = V.ext_prior_qinv[4 * c + 3];
+  double theta_;
+  const V3 e = so3_log(quat_mul(qi, T.q), &theta_);
+  const double* O = V.ext_prior_info + 9 * c;
+  double Oe[3];
+  for (int r = 0; r < 3; ++r) Oe[r] = O[3 * r] * e[0] + O[3 * r + 1] * e[1] + O[3 * r + 2] * e[2];
+  if (mode == 0) { rho[c] = e[0] * Oe[0] + e[1] * Oe[1] + e[2] * Oe[2]; return; }
+  // Jr(e) = I - W (1 - cos d) / d^2 + W^2 (d - sin d) / d^3, identity below d = 1e-5
+  const double d2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2], d = sqrt(d2);
+  double Jr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (!(d < 1e-5)) {
+    const double W[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+    const double a = (1.0 - cos(d)) / d2, b2 = (d - sin(d)) / (d2 * d);
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) {
+        double ww = 0.0;
+        for (int q = 0; q < 3; ++q) ww += W[3 * r + q] * W[3 * q + k];
+        Jr[3 * r + k] += -a * W[3 * r + k] + b2 * ww;
+      }
+  }
+  double Cf[9];   // cofactor inverse
+  Cf[0] = Jr[4] * Jr[8] - Jr[5] * Jr[7]; Cf[1] = Jr[2] * Jr[7] - Jr[1] * Jr[8]; Cf[2] = Jr[1] * Jr[5] - Jr[2] * Jr[4];
+  Cf[3] = Jr[5] * Jr[6] - Jr[3] * Jr[8]; Cf[4] = Jr[0] * Jr[8] - Jr[2] * Jr[6]; Cf[5] = Jr[2] * Jr[3] - Jr[0] * Jr[5];
+  Cf[6] = Jr[3] * Jr[7] - Jr[4] * Jr[6]; Cf[7] = Jr[1] * Jr[6] - Jr[0] * Jr[7]; Cf[8] = Jr[0] * Jr[4] - Jr[1] * Jr[3];
+  const double idet = 1.0 / (Jr[0] * Cf[0] + Jr[1] * Cf[3] + Jr[2] * Cf[6]);
+  double J[9], JtO[9];
+  for (int i = 0; i < 9; ++i) J[i] = Cf[i] * idet;
+  for (int a2 = 0; a2 < 3; ++a2)
+    for (int k = 0; k < 3; ++k) JtO[3 * a2 + k] = J[a2] * O[k] + J[3 + a2] * O[3 + k] + J[6 + a2] * O[6 + k];
+  double* B = hpp + (size_t)V.pose_hpp_diag[h] * 144;
+  for (int a2 = 0; a2 < 3; ++a2) {
+    for (int k = 0; k < 3; ++k) atomicAdd(&B[(3 + a2) * 12 + 3 + k], JtO[3 * a2] * J[k] + JtO[3 * a2 + 1] * J[3 + k] + JtO[3 * a2 + 2] * J[6 + k]);
+    atomicAdd(&bp[(size_t)h * 12 + 3 + a2], -(JtO[3 * a2] * e[0] + JtO[3 * a2 + 1] * e[1] + JtO[3 * a2 + 2] * e[2]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K8

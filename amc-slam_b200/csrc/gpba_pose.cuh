@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(GPBA_POSE_THREADS) k_pose_only(PoseBatchView B
     const double* st = sState[s];
     if (tid < n_cam) {
       const bool gp = tid != n_cam - 1;
-      if (full) record_row<true>(gp ? st : nullptr, gp ? st + 7 : nullptr, t1, st + 13, st + 20, t2, B.cam_time[(size_t)f * n_cam + tid], B.cam[tid], sRec[tid]);
-      else record_row<false>(gp ? st : nullptr, gp ? st + 7 : nullptr, t1, st + 13, st + 20, t2, B.cam_time[(size_t)f * n_cam + tid], B.cam[tid], sRec[tid]);
+      if (full) record_row<true, 24>(gp ? st : nullptr, gp ? st + 7 : nullptr, t1, st + 13, st + 20, t2, B.cam_time[(size_t)f * n_cam + tid], B.cam[tid], sRec[tid]);
+      else record_row<false, 24>(gp ? st : nullptr, gp ? st + 7 : nullptr, t1, st + 13, st + 20, t2, B.cam_time[(size_t)f * n_cam + tid], B.cam[tid], sRec[tid]);
     }
     if (with_prior && tid == 32) {
       const SE3 T1 = load_se3(st), T2 = load_se3(st + 13);

@@ -164,20 +164,20 @@ __global__ void k_emit_pairs(int n_lm, const int64_t* __restrict__ lm_obs_begin,
 __global__ void k_count_hpl(DevView V, const int* __restrict__ o_rec, unsigned long long* __restrict__ total) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
   unsigned long long cnt = 0;
+  auto pose_of = [&](int r, int which) -> int {   // 0 previous keyframe, 1 current keyframe, 2 extrinsic
+    if (which == 2) return V.rec_kf1[r] >= 0 ? V.ext_h[V.rec_cam[r]] : -1;
+    const int k = which ? V.rec_kf2[r] : V.rec_kf1[r];
+    return k >= 0 ? V.kf_h[k] : -1;
+  };
   for (int l = warp; l < V.n_lm; l += nw) {
     const int64_t ob = V.lm_obs_begin[l];
-    const int m = 2 * (int)(V.lm_obs_begin[l + 1] - ob);
+    const int m = 3 * (int)(V.lm_obs_begin[l + 1] - ob);
     for (int j = lane; j < m; j += 32) {
-      const int r = o_rec[ob + (j >> 1)];
-      const int k = (j & 1) ? V.rec_kf2[r] : V.rec_kf1[r];
-      const int h = k >= 0 ? V.kf_h[k] : -1;
+      const int h = pose_of(o_rec[ob + j / 3], j % 3);
       if (h < 0) continue;
       bool first = true;
-      for (int q = 0; q < j && first; ++q) {
-        const int r2 = o_rec[ob + (q >> 1)];
-        const int k2 = (q & 1) ? V.rec_kf2[r2] : V.rec_kf1[r2];
-        if (k2 >= 0 && V.kf_h[k2] == h) first = false;
-      }
+      for (int q = 0; q < j && first; ++q)
+        if (pose_of(o_rec[ob + q / 3], q % 3) == h) first = false;
       if (first) ++cnt;
     }
   }
@@ -230,7 +230,9 @@ __global__ void k_item_ranges(int n, const int64_t* __restrict__ begin_excl, con
 }
 
 // ---- Hschur block pattern and K4c contribution lists from the unique record pairs (all integer, all on the device)
+// pose-like vertex `which` of record r: 0 previous keyframe, 1 current keyframe, 2 the camera's extrinsic (GP records only)
 GPBA_D int rec_pose(const DevView& V, int r, int which) {
+  if (which == 2) return V.rec_kf1[r] >= 0 ? V.ext_h[V.rec_cam[r]] : -1;
   const int k = which ? V.rec_kf2[r] : V.rec_kf1[r];
   return k >= 0 ? V.kf_h[k] : -1;
 }
@@ -238,15 +240,16 @@ GPBA_D unsigned long long block_key(int pa, int pb) {  // (col, row) with row <=
   const unsigned lo = (unsigned)(pa < pb ? pa : pb), hi = (unsigned)(pa < pb ? pb : pa);
   return ((unsigned long long)hi << 32) | lo;
 }
-// four candidate pose-pair blocks per record pair (~0 = none)
+// nine candidate pose-pair blocks per record pair (~0 = none)
+#define GPBA_KEYS_PER_RP 9
 __global__ void k_emit_block_keys(DevView V, int n, const unsigned long long* __restrict__ rp_key, unsigned long long* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int r1 = (int)(rp_key[t] / (unsigned long long)V.n_rec), r2 = (int)(rp_key[t] % (unsigned long long)V.n_rec);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int pa = rec_pose(V, r1, q >> 1), pb = rec_pose(V, r2, q & 1);
-    out[4 * (size_t)t + q] = (pa >= 0 && pb >= 0) ? block_key(pa, pb) : ~0ull;
+  for (int q = 0; q < GPBA_KEYS_PER_RP; ++q) {
+    const int pa = rec_pose(V, r1, q / 3), pb = rec_pose(V, r2, q % 3);
+    out[GPBA_KEYS_PER_RP * (size_t)t + q] = (pa >= 0 && pb >= 0) ? block_key(pa, pb) : ~0ull;
   }
 }
 __global__ void k_split_block_keys(int n, const unsigned long long* __restrict__ key, int* __restrict__ row, int* __restrict__ col) {
@@ -258,9 +261,10 @@ GPBA_D int find_block(const unsigned long long* __restrict__ hs_key, int n_hs, u
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (hs_key[mid] < key) lo = mid + 1; else hi = mid; }
   return lo;
 }
-// up to six (block, left record slice, right record slice, transpose) contributions per record pair, see k_schur_expand;
+// up to twelve (block, left record slice, right record slice, transpose) contributions per record pair, see k_schur_expand
+// (nine slice pairs; a pair whose two poses coincide across two different records lands twice in the diagonal block);
 // sort key = (block, left record, left slice)
-#define GPBA_MAX_CON_PER_RP 6
+#define GPBA_MAX_CON_PER_RP 12
 __global__ void k_emit_contribs(DevView V, int n_rp, const unsigned long long* __restrict__ rp_key, const unsigned long long* __restrict__ hs_key,
                                 int n_hs, unsigned long long* __restrict__ keys, HsContrib* __restrict__ vals, int* __restrict__ n_valid) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,12 +272,13 @@ __global__ void k_emit_contribs(DevView V, int n_rp, const unsigned long long* _
   const int r1 = (int)(rp_key[t] / (unsigned long long)V.n_rec), r2 = (int)(rp_key[t] % (unsigned long long)V.n_rec);
   int w = 0;
   auto emit = [&](int blk, int rL, int aL, int rR, int aR, int tr, int g) {
-    keys[(size_t)t * GPBA_MAX_CON_PER_RP + w] = ((unsigned long long)blk * (unsigned long long)V.n_rec + (unsigned long long)rL) * 2ull + (unsigned long long)aL;
-    vals[(size_t)t * GPBA_MAX_CON_PER_RP + w] = HsContrib{t, rL, rR, aL | (aR << 1) | (tr << 2) | (g << 4)};
+    if (w >= GPBA_MAX_CON_PER_RP) return;   // cannot happen: at most 9 slice pairs + 3 coinciding poses
+    keys[(size_t)t * GPBA_MAX_CON_PER_RP + w] = ((unsigned long long)blk * (unsigned long long)V.n_rec + (unsigned long long)rL) * 4ull + (unsigned long long)aL;
+    vals[(size_t)t * GPBA_MAX_CON_PER_RP + w] = HsContrib{t, rL, rR, aL | (aR << 2) | (tr << 4) | (g << 5)};
     ++w;
   };
-  for (int a = 0; a < 2; ++a)
-    for (int b = 0; b < 2; ++b) {
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
       if (r1 == r2 && a > b) continue;  // the mirror image of (b, a)
       const int pa = rec_pose(V, r1, a), pb = rec_pose(V, r2, b);
       if (pa < 0 || pb < 0) continue;
@@ -292,10 +297,10 @@ __global__ void k_mark_groups(int n_groups, const int* __restrict__ start, const
   if (t < n_groups) con[start[t]].code |= count[t] << 8;
 }
 // first contribution of every block (sorted keys)
-__global__ void k_con_begin(int n_hs, int n_con, unsigned long long two_nrec, const unsigned long long* __restrict__ keys, int* __restrict__ con_begin) {
+__global__ void k_con_begin(int n_hs, int n_con, unsigned long long keys_per_block, const unsigned long long* __restrict__ keys, int* __restrict__ con_begin) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > n_hs) return;
-  const unsigned long long want = (unsigned long long)b * two_nrec;
+  const unsigned long long want = (unsigned long long)b * keys_per_block;
   int lo = 0, hi = n_con;
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < want) lo = mid + 1; else hi = mid; }
   con_begin[b] = lo;

@@ -21,6 +21,7 @@ SYMBOLS = [
     "gpba_get_hschur", "gpba_get_hll", "gpba_get_hpl", "gpba_oplus", "gpba_push", "gpba_pop", "gpba_discard_top",
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
+    "gpba_set_extrinsics", "gpba_get_extrinsics", "gpba_count_camera_observations", "gpba_calibrate_extrinsics",
     "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_symbolic_analyze", "gpba_pose_optimize", "gpba_vel_ransac",
 ]
 
@@ -233,6 +234,37 @@ class GpBa:
                                               C.byref(params) if params is not None else None, _p(f), traces),
                  "gpba_rejection_rounds")
         return f, list(traces)
+
+    # ---- extrinsic self-calibration
+    def _ext_struct(self, free, prior_q, prior_info):
+        from .problem import Extrinsics
+        self._ext_keep = (np.ascontiguousarray(free, np.uint8),
+                          None if prior_q is None else np.ascontiguousarray(prior_q, np.float64),
+                          None if prior_info is None else np.ascontiguousarray(prior_info, np.float64))
+        f, q, w = self._ext_keep
+        return Extrinsics(f.ctypes.data_as(C.POINTER(C.c_uint8)),
+                          None if q is None else q.ctypes.data_as(C.POINTER(C.c_double)),
+                          None if w is None else w.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def set_extrinsics(self, free, prior_q=None, prior_info=None):
+        e = self._ext_struct(free, prior_q, prior_info)
+        self._ck(self.L.gpba_set_extrinsics(self.h, C.byref(e)), "gpba_set_extrinsics")
+
+    def extrinsics(self):
+        a = np.zeros((self.prob.n_cam, 7)); self._ck(self.L.gpba_get_extrinsics(self.h, _p(a)), "gpba_get_extrinsics"); return a
+
+    def count_camera_observations(self):
+        a = np.zeros(self.prob.n_cam, np.int64)
+        self._ck(self.L.gpba_count_camera_observations(self.h, _p(a)), "gpba_count_camera_observations")
+        return a
+
+    def calibrate_extrinsics(self, candidates, prior_q=None, prior_info=None, min_obs=50, iters=10, params=None):
+        e = self._ext_struct(candidates, prior_q, prior_info)
+        tr = LmTrace()
+        freed = np.zeros(self.prob.n_cam, np.uint8)
+        self._ck(self.L.gpba_calibrate_extrinsics(self.h, C.byref(e), int(min_obs), int(iters), C.byref(params) if params is not None else None,
+                                                  C.byref(tr), _p(freed)), "gpba_calibrate_extrinsics")
+        return tr, freed
 
     # ---- measurement
     def set_profiling(self, on):

@@ -74,6 +74,11 @@ class CreateOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_id", C.c_char_p), ("flags", C.c_uint32)]
 
 
+class Extrinsics(C.Structure):
+    """gpba_extrinsics (include/gpba.h)"""
+    _fields_ = [("free_mask", C.POINTER(C.c_uint8)), ("prior_R", C.POINTER(C.c_double)), ("prior_info", C.POINTER(C.c_double))]
+
+
 class StructureInfo(C.Structure):
     _fields_ = [("n_free_kf", C.c_int32), ("n_active_pt", C.c_int32), ("n_active_obs", C.c_int64),
                 ("n_hpl", C.c_int64), ("n_hpp", C.c_int32), ("n_hschur", C.c_int32)]

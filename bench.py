@@ -342,8 +342,8 @@ def run_gpba(args):
     for k, nbytes in ab.items():
         st = stages[k]
         # number of launches of the stage's main kernel in the timed region (the library counts every launch of a stage;
-        # a residual pass is 4 launches: K1 + priors + reduce + pack, a back-substitution 4, the others 1 main kernel)
-        n_main = {"residuals": st["launches"] // 4, "lin_landmarks": iters_done, "lin_poses": iters_done,
+        # a residual pass counts 5 launches: K1 + priors + extrinsic priors + reduce + pack; the others 1 main kernel)
+        n_main = {"residuals": st["launches"] // 5, "lin_landmarks": iters_done, "lin_poses": iters_done,
                   "schur_prepare": trials_done, "schur_pairs": trials_done, "schur_expand": trials_done,
                   "backsub_update": trials_done}[k]
         if n_main > 0 and st["ms"] > 0:

@@ -242,6 +242,30 @@ int gpba_compute_errors_inactive(gpba_handle* h);
 int gpba_rejection_rounds(gpba_handle* h, int n_rounds, int iters, const gpba_thresholds* th,
                           const gpba_lm_params* params, uint8_t* flags_out, gpba_lm_trace* traces /* [n_rounds] */);
 
+/* ---- extrinsic self-calibration ---------------------------------- */
+/* LocalGPBA's second stage (src/Optimizer.cc:983-995, 1228-1240, 1419-1428): every asynchronous camera carries a
+ * VertexExtrinsic (6-dim, Tbc <- Tbc exp(delta), include/G2oTypes.h:83-102), fixed during the first optimize(); cameras
+ * with at least extrin_thresh = 50 EdgeMonoGPExtrinsic are then un-fixed and the graph is optimised again, with an
+ * EdgeExtrinsicPrior (e = Log(R_ini^-1 R_bc), information MultiFrame::mRbc_ini_cov[c], G2oTypes.h:470-494) on every free
+ * extrinsic.  A free extrinsic is a non-marginalized vertex whose id follows every keyframe id (:986): in every vector and
+ * block pattern of this library it is a pose block AFTER the keyframes' -- a 12-slot whose first six entries are the
+ * extrinsic's tangent [translation; rotation] and whose last six are padding (zero). */
+typedef struct gpba_extrinsics {
+  const uint8_t* free_mask;  /* [n_cam] 1 = VertexExtrinsic::setFixed(false) (:1236)                                   */
+  const double* prior_R;     /* [n_cam][4] qx qy qz qw of MultiFrame::mRbc_ini[c]; NULL = no EdgeExtrinsicPrior edges  */
+  const double* prior_info;  /* [n_cam][9] MultiFrame::mRbc_ini_cov[c], row-major; NULL iff prior_R is NULL            */
+} gpba_extrinsics;
+/* Takes effect at the next gpba_build_structure / gpba_optimize (= initializeOptimization, :1238).  Single GPU only. */
+int gpba_set_extrinsics(gpba_handle* h, const gpba_extrinsics* ext);
+/* VertexExtrinsic::estimate() read-back (:1419-1428): [n_cam][7] qx qy qz qw tx ty tz of the current estimate. */
+int gpba_get_extrinsics(gpba_handle* h, double* cam_Tbc);
+/* cam_obs[c]: EdgeMonoGPExtrinsic of camera c in the graph, whatever their level (`cam_obs[c]++`, :1129). */
+int gpba_count_camera_observations(gpba_handle* h, int64_t* cam_obs /* [n_cam] */);
+/* The whole second stage (:1226-1240): un-fix the candidates with cam_obs >= min_obs (50 in the reference), then
+ * initializeOptimization + optimize(iters).  freed_out [n_cam] (optional) reports which extrinsics were un-fixed. */
+int gpba_calibrate_extrinsics(gpba_handle* h, const gpba_extrinsics* candidates, int min_obs, int iters,
+                              const gpba_lm_params* params, gpba_lm_trace* trace, uint8_t* freed_out);
+
 /* ---- pose-only GP optimisation ---------------------------------- */
 /* Optimizer::PoseGPOptimizationFromeLastFrame (src/Optimizer.cc:369-686) for a batch of independent frames: per frame
  * two VertexPoseVel (previous frame, fixed iff prev_fixed; current frame, free), one EdgeMonoGPOnlyPose per match of an
