@@ -51,6 +51,13 @@ struct FlatGraph {
   std::vector<g2o::VertexSBAPointXYZ*> pt_vertex;
   std::vector<g2o::OptimizableGraph::Edge*> obs_edge;   // reprojection edge of every observation (write-back of chi2)
   double qc[6], bf = 0, huber_mono = 0, huber_stereo = 0, huber_prior = 0;
+  // extrinsic self-calibration: VertexExtrinsic of camera c (from the EdgeMonoGPExtrinsic that reference it), which of them
+  // are un-fixed, and the EdgeExtrinsicPrior edges (R_ini, information)
+  std::map<int, ORB_SLAM3::VertexExtrinsic*> ext_vertex, ext_vertex_by_id;
+  std::map<int, uint8_t> ext_free;
+  std::vector<ORB_SLAM3::EdgeExtrinsicPrior*> ext_priors;
+  std::vector<double> ext_prior_R, ext_prior_info;
+  bool have_ext_prior = false;
   bool ok = true;
   std::string why;
 
@@ -74,8 +81,9 @@ struct FlatGraph {
     return r;
   }
 
-  // Walks optimizer->vertices() / activeEdges() exactly once.  Extrinsic vertices must be fixed (the state of
-  // LocalGPBA's first optimize(), src/Optimizer.cc:983-988); the bExtrinsic second stage (:1228-1240) stays on g2o.
+  // Walks optimizer->vertices() / activeEdges() exactly once.  Extrinsic vertices are fixed during LocalGPBA's first
+  // optimize() (src/Optimizer.cc:983-988); in the bExtrinsic second stage (:1228-1240) the un-fixed ones, with their
+  // EdgeExtrinsicPrior edges, travel through gpba_set_extrinsics (see apply_extrinsics below).
   void build(g2o::SparseOptimizer* opt) {
     using namespace ORB_SLAM3;
     std::map<int, int> kf_index, pt_index;   // vertex id -> flat index, ascending id == Hessian order
@@ -101,7 +109,7 @@ struct FlatGraph {
         pt_vertex.push_back(p);
         for (int i = 0; i < 3; ++i) pt_xyz.push_back(p->estimate()(i));
       } else if (VertexExtrinsic* x = dynamic_cast<VertexExtrinsic*>(iv.second)) {
-        if (!x->fixed()) { ok = false; why = "free VertexExtrinsic: run this stage on g2o"; }
+        ext_vertex_by_id[iv.first] = x;   // camera index comes from the edges that reference it
       }
     }
     std::map<std::pair<std::pair<int, int>, std::pair<int, long long> >, int> recs;
@@ -135,7 +143,10 @@ struct FlatGraph {
         take_gp(g->gp);
         const int r = record(recs, kf_index[g->vertices()[0]->id()], kf_index[g->vertices()[1]->id()], g->cam_idx, g->t);
         add_obs(e, r, pt_index[g->vertices()[2]->id()], g->measurement()(0), g->measurement()(1), -1.0, g->information()(0, 0));
-        Tbc[g->cam_idx] = static_cast<VertexExtrinsic*>(g->vertices()[3])->estimate();   // the (fixed) extrinsic vertex wins over mTbc
+        VertexExtrinsic* xv = static_cast<VertexExtrinsic*>(g->vertices()[3]);
+        Tbc[g->cam_idx] = xv->estimate();   // the extrinsic vertex wins over mTbc
+        ext_vertex[g->cam_idx] = xv;
+        if (!xv->fixed()) ext_free[g->cam_idx] = 1;
         huber_mono = delta_of(e) > 0 ? delta_of(e) : huber_mono;
       } else if (EdgeStereoGP* g = dynamic_cast<EdgeStereoGP*>(e)) {
         take_gp(g->gp);
@@ -157,14 +168,42 @@ struct FlatGraph {
         huber_prior = delta_of(e);   // 21.026 in BundleAdjustment (Optimizer.cc:128-130), none in LocalGPBA (:903-910)
       } else if (dynamic_cast<EdgeVelocity*>(e)) {
         velp_kf.push_back(kf_index[e->vertices()[0]->id()]);
-      } else if (dynamic_cast<EdgeExtrinsicPrior*>(e)) {
-        // inactive while the extrinsic vertex is fixed (allVerticesFixed, sparse_optimizer.cpp:236-247)
+      } else if (EdgeExtrinsicPrior* xp = dynamic_cast<EdgeExtrinsicPrior*>(e)) {
+        // inactive while the extrinsic vertex is fixed (allVerticesFixed, sparse_optimizer.cpp:236-247); kept for the second stage
+        ext_priors.push_back(xp);
       } else {
         ok = false; why = "edge type outside the GP-BA path";
       }
     }
     for (int c = 0; c < n_cam; ++c) put_se3(Tbc[c], cam_Tbc);
     if (!have_qc) for (int i = 0; i < 6; ++i) qc[i] = 1.0;
+    // EdgeExtrinsicPrior -> (camera, R_ini, information): R_ is stored inverted (G2oTypes.h:474)
+    ext_prior_R.assign(4 * (size_t)n_cam, 0.0); ext_prior_info.assign(9 * (size_t)n_cam, 0.0);
+    for (int c = 0; c < n_cam; ++c) ext_prior_R[4 * c + 3] = 1.0;
+    for (EdgeExtrinsicPrior* xp : ext_priors)
+      for (auto& kv : ext_vertex)
+        if (kv.second == xp->vertices()[0]) {
+          const Eigen::Quaterniond q = xp->R_.inverse().unit_quaternion();
+          const int c = kv.first;
+          ext_prior_R[4 * c] = q.x(); ext_prior_R[4 * c + 1] = q.y(); ext_prior_R[4 * c + 2] = q.z(); ext_prior_R[4 * c + 3] = q.w();
+          for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) ext_prior_info[9 * c + 3 * r + k] = xp->information()(r, k);
+          have_ext_prior = true;
+        }
+  }
+
+  // un-fixed VertexExtrinsic + EdgeExtrinsicPrior -> the handle (no-op when every extrinsic is fixed)
+  int apply_extrinsics(gpba_handle* h) const {
+    bool any = false;
+    for (auto& kv : ext_free) any = any || kv.second;
+    if (!any) return GPBA_OK;
+    const int n_cam = (int)(cam_Tbc.size() / 7);
+    std::vector<uint8_t> fr((size_t)n_cam, 0);
+    for (auto& kv : ext_free) fr[kv.first] = kv.second;
+    gpba_extrinsics e;
+    e.free_mask = fr.data();
+    e.prior_R = have_ext_prior ? ext_prior_R.data() : nullptr;
+    e.prior_info = have_ext_prior ? ext_prior_info.data() : nullptr;
+    return gpba_set_extrinsics(h, &e);
   }
 
   gpba_problem view(double lambda_init, int linear_solver) const {
@@ -184,6 +223,45 @@ struct FlatGraph {
     return P;
   }
 
+  // The reference leaves every active edge with the _error of the LAST EVALUATED state: optimize() never re-evaluates after
+  // its last trial, so after a rejected trial e->chi2() and activeRobustChi2() (Optimizer.cc:1254, 1273-1330) see the
+  // rejected state's errors while the vertices hold the accepted estimate.  Reproduced here: the reprojection errors come
+  // from gpba_edge_errors; the few prior edges are re-evaluated by g2o itself at the last evaluated keyframe states, which
+  // are set and then replaced by the estimate again.
+  void write_back_errors(gpba_handle* h, g2o::SparseOptimizer* opt) {
+    std::vector<double> err(3 * obs_edge.size());
+    if (gpba_edge_errors(h, err.data()) == GPBA_OK)
+      for (size_t i = 0; i < obs_edge.size(); ++i) {
+        if (err[3 * i] != err[3 * i]) continue;                     // NaN: inactive edge, keeps its own error
+        double* ed = obs_edge[i]->errorData();
+        for (int d = 0; d < obs_edge[i]->dimension(); ++d) ed[d] = err[3 * i + d];
+      }
+    std::vector<double> kp(kf_pose.size()), kv(kf_vel.size()), tb(cam_Tbc.size());
+    if (gpba_download_evaluated_state(h, kp.data(), kv.data(), tb.data()) != GPBA_OK) return;
+    std::vector<ORB_SLAM3::PoseVelocity> keep(kf_vertex.size());
+    for (size_t k = 0; k < kf_vertex.size(); ++k) {
+      keep[k] = kf_vertex[k]->estimate();
+      if (kf_vertex[k]->fixed()) continue;
+      ORB_SLAM3::PoseVelocity pv = keep[k];
+      const double* q = &kp[7 * k];
+      pv.Twb = Sophus::SE3d(Eigen::Quaterniond(q[3], q[0], q[1], q[2]), Eigen::Vector3d(q[4], q[5], q[6]));
+      for (int i = 0; i < 6; ++i) pv.Vel(i) = kv[6 * k + i];
+      kf_vertex[k]->setEstimate(pv);
+    }
+    std::map<int, Sophus::SE3d> keep_ext;
+    for (auto& kvp : ext_vertex) {
+      keep_ext[kvp.first] = kvp.second->estimate();
+      if (kvp.second->fixed()) continue;
+      const double* q = &tb[7 * kvp.first];
+      kvp.second->setEstimate(Sophus::SE3d(Eigen::Quaterniond(q[3], q[0], q[1], q[2]), Eigen::Vector3d(q[4], q[5], q[6])));
+    }
+    for (g2o::OptimizableGraph::Edge* e : opt->activeEdges())
+      if (dynamic_cast<ORB_SLAM3::EdgeGaussianPrior*>(e) || dynamic_cast<ORB_SLAM3::EdgeVelocity*>(e) || dynamic_cast<ORB_SLAM3::EdgeExtrinsicPrior*>(e))
+        e->computeError();
+    for (size_t k = 0; k < kf_vertex.size(); ++k) kf_vertex[k]->setEstimate(keep[k]);
+    for (auto& kvp : ext_vertex) kvp.second->setEstimate(keep_ext[kvp.first]);
+  }
+
   // vertex->setEstimate() for every free vertex (what Optimizer.cc:324-366 / 1360-1430 read afterwards)
   void write_back(gpba_handle* h) {
     std::vector<double> kp(kf_pose.size()), kv(kf_vel.size()), pt(pt_xyz.size());
@@ -197,6 +275,14 @@ struct FlatGraph {
       kf_vertex[k]->setEstimate(pv);
     }
     for (size_t p = 0; p < pt_vertex.size(); ++p) pt_vertex[p]->setEstimate(Eigen::Vector3d(pt[3 * p], pt[3 * p + 1], pt[3 * p + 2]));
+    // free extrinsics: VertexExtrinsic::setEstimate (Optimizer.cc:1419-1428 reads them back into MultiKeyFrame::mTbc)
+    std::vector<double> tbc(cam_Tbc.size());
+    if (!ext_vertex.empty() && gpba_get_extrinsics(h, tbc.data()) == GPBA_OK)
+      for (auto& kv : ext_vertex) {
+        if (kv.second->fixed()) continue;
+        const double* q = &tbc[7 * kv.first];
+        kv.second->setEstimate(Sophus::SE3d(Eigen::Quaterniond(q[3], q[0], q[1], q[2]), Eigen::Vector3d(q[4], q[5], q[6])));
+      }
   }
 };
 
@@ -223,11 +309,12 @@ class GpBaLevenberg : public g2o::OptimizationAlgorithm {
     const gpba_problem P = G.view(_lambda_init, _linear);
     gpba_destroy(_h); _h = nullptr;
     if (gpba_create(&P, _device, &_h) != GPBA_OK) { std::cerr << "gpba_create: " << gpba_last_error() << std::endl; return Fail; }
+    if (G.apply_extrinsics(_h) != GPBA_OK) { std::cerr << "gpba_set_extrinsics: " << gpba_last_error() << std::endl; return Fail; }
     // setForceStopFlag(bool*) (sparse_optimizer.h:188): bool and unsigned char share size and representation here
     const volatile unsigned char* stop = reinterpret_cast<const volatile unsigned char*>(_optimizer->forceStopFlag());
     if (gpba_optimize(_h, _iters, stop, nullptr, &_trace) != GPBA_OK) { std::cerr << "gpba_optimize: " << gpba_last_error() << std::endl; return Fail; }
     G.write_back(_h);
-    _optimizer->computeActiveErrors();                              // edge->chi2() for the caller's inlier checks (Optimizer.cc:1263-1348)
+    G.write_back_errors(_h, _optimizer);                            // edge->chi2() / activeRobustChi2() for the caller (Optimizer.cc:1254, 1263-1348)
     _done = true;
     return _trace.result == GPBA_FAIL ? Fail : Terminate;
   }
@@ -262,6 +349,9 @@ class GpBaBlockSolver : public g2o::BlockSolverBase {
     _G = FlatGraph();
     _G.build(_optimizer);
     if (!_G.ok) return false;
+    // Seam B exchanges Solver::_x / _b in g2o's layout, where a VertexExtrinsic has 6 entries; the library keeps a 12-slot
+    // per extrinsic (include/gpba.h).  The second stage of LocalGPBA (free extrinsics) goes through seam A' (GpBaLevenberg).
+    for (auto& kv : _G.ext_free) if (kv.second) return false;
     const gpba_problem P = _G.view(0.0, _linear);
     gpba_destroy(_h); _h = nullptr;
     if (gpba_create(&P, _device, &_h) != GPBA_OK) return false;

@@ -1935,6 +1935,43 @@ int gpba_edge_chi2(gpba_handle* h, double* chi2) {
   return GPBA_OK;
 }
 
+// BaseEdge::_error of every ACTIVE reprojection edge as the last evaluation left it (the stale-error quirk: after a
+// rejected last trial these are the rejected state's errors, which is what the reference's e->chi2() reads afterwards);
+// entries of inactive (level 1) edges are NaN = "unchanged".  Recomputed on demand from the state buffer of that evaluation.
+int gpba_edge_errors(gpba_handle* h, double* err3) {
+  NEED_STRUCT(h);
+  Solver& s = S(h);
+  if (!err3) { g_err = "null argument"; return GPBA_ERR_INVALID; }
+  if (s.nranks > 1) { g_err = "gpba_edge_errors is a single-GPU accessor"; return GPBA_ERR_STATE; }
+  if (s.n_obs == 0) return GPBA_OK;
+  DBuf<double> d_err;
+  CKR(d_err.alloc(3 * (size_t)s.n_obs));
+  CK(cudaMemsetAsync(d_err.p, 0xFF, sizeof(double) * 3 * (size_t)s.n_obs, s.stream));   // all-ones = NaN
+  const int ev = s.last_eval;
+  CKR(s.compute_records(ev, false));
+  if (s.n_aobs > 0) {
+    if (s.stereo) k_residual<true><<<s.grid_obs, 256, 0, s.stream>>>(s.Vb(ev), s.d_rec_lite.p, GPBA_REC_LITE_STRIDE, s.d_ptS[ev].p, s.d_partial.p, nullptr, d_err.p);
+    else k_residual<false><<<s.grid_obs, 256, 0, s.stream>>>(s.Vb(ev), s.d_rec_lite.p, GPBA_REC_LITE_STRIDE, s.d_ptS[ev].p, s.d_partial.p, nullptr, d_err.p);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(err3, d_err.p, sizeof(double) * 3 * (size_t)s.n_obs, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return GPBA_OK;
+}
+// Keyframe states and extrinsics of the last EVALUATED state (equal to gpba_download_state's unless the last trial was
+// rejected): lets the caller recompute the errors of its few prior edges exactly where the reference left them.
+int gpba_download_evaluated_state(gpba_handle* h, double* kf_pose, double* kf_vel, double* cam_Tbc) {
+  NEED(h);
+  Solver& s = S(h);
+  CK(cudaSetDevice(s.device));
+  const int ev = s.last_eval;
+  if (kf_pose) CK(cudaMemcpyAsync(kf_pose, s.d_pose[ev].p, sizeof(double) * 7 * (size_t)s.n_kf, cudaMemcpyDeviceToHost, s.stream));
+  if (kf_vel) CK(cudaMemcpyAsync(kf_vel, s.d_vel[ev].p, sizeof(double) * 6 * (size_t)s.n_kf, cudaMemcpyDeviceToHost, s.stream));
+  if (cam_Tbc) CK(cudaMemcpyAsync(cam_Tbc, s.d_ext[ev].p, sizeof(double) * 7 * (size_t)s.n_cam, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return GPBA_OK;
+}
+
 __global__ void k_robust_sum(DevView V, int64_t n_obs, const double* __restrict__ chi2, const uint8_t* __restrict__ flags,
                              const double* __restrict__ ur, double* __restrict__ partial) {
   __shared__ double red[32];

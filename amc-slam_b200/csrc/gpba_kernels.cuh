@@ -217,7 +217,7 @@ __global__ void k_records(DevView V, const double* __restrict__ pose, const doub
 template <bool STEREO>
 __global__ void __launch_bounds__(256) k_residual(DevView V, const double* __restrict__ rec, int rec_stride,
                                                   const double* __restrict__ pt, double* __restrict__ partial,
-                                                  double* __restrict__ chi2_out) {
+                                                  double* __restrict__ chi2_out, double* __restrict__ err_out = nullptr) {
   __shared__ double red[32];
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V.n_aobs; i += (int64_t)gridDim.x * blockDim.x) {
@@ -230,6 +230,10 @@ __global__ void __launch_bounds__(256) k_residual(DevView V, const double* __res
                             V.o_u[i], V.o_v[i], STEREO ? V.o_ur[i] : -1.0, V.o_w[i], V.o_flags[i], E, nullptr, nullptr);
     acc += E.rho;
     if (chi2_out) chi2_out[V.o_orig[i]] = E.chi2;
+    if (err_out) {   // BaseEdge::_error of the edge (3 slots; the third is 0 for a monocular edge)
+      double* eo = err_out + 3 * V.o_orig[i];
+      eo[0] = E.e[0]; eo[1] = E.e[1]; eo[2] = (STEREO && E.rows == 3) ? E.e[2] : 0.0;
+    }
   }
   const double s = block_sum(acc, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;

@@ -719,6 +719,29 @@ int gpba_window_apply(gpba_map* m, const gpba_window* w, const double* kf_pose, 
   return GPBA_OK;
 }
 
+// MultiKeyFrame::mTbc[c] = v->estimate().cast<float>() for the cameras that were calibrated (src/Optimizer.cc:1419-1428)
+int gpba_map_apply_extrinsics(gpba_map* m, const gpba_window* w, const double* cam_Tbc, int32_t min_obs, int32_t* n_updated) {
+  if (!m || !w || !cam_Tbc) return fail("null argument");
+  int32_t n = 0;
+  for (int c = 0; c < m->n_cam - 1; ++c) {          // the last camera is the synchronous reference camera: no VertexExtrinsic (:983)
+    if (w->cam_obs[c] < min_obs) continue;           // "if (cam_obs[c] < extrin_thresh) continue" (:1421-1424)
+    double q[4], nq = 0;
+    for (int k = 0; k < 4; ++k) { q[k] = f32(cam_Tbc[7 * c + k]); nq += q[k] * q[k]; }
+    nq = std::sqrt(nq);
+    if (!(nq > 0)) return fail("degenerate extrinsic quaternion");
+    for (int k = 0; k < 4; ++k) m->cam_Tbc[7 * c + k] = q[k] / nq;   // SE3f -> cast<double>() re-normalises (so3.hpp:480-487)
+    for (int k = 4; k < 7; ++k) m->cam_Tbc[7 * c + k] = f32(cam_Tbc[7 * c + k]);
+    ++n;
+  }
+  if (n_updated) *n_updated = n;
+  return GPBA_OK;
+}
+int gpba_map_extrinsics(const gpba_map* m, double* cam_Tbc) {
+  if (!m || !cam_Tbc) return fail("null argument");
+  std::copy(m->cam_Tbc.begin(), m->cam_Tbc.end(), cam_Tbc);
+  return GPBA_OK;
+}
+
 const char* gpba_map_last_error(void) { return g_map_err.c_str(); }
 
 }  // extern "C"

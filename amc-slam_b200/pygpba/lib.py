@@ -19,7 +19,7 @@ SYMBOLS = [
     "gpba_build_structure", "gpba_get_hpp_pattern", "gpba_get_hschur_pattern", "gpba_compute_errors", "gpba_build_system",
     "gpba_set_lambda", "gpba_restore_diagonal", "gpba_solve", "gpba_vector_size", "gpba_get_x", "gpba_get_b", "gpba_get_hpp",
     "gpba_get_hschur", "gpba_get_hll", "gpba_get_hpl", "gpba_oplus", "gpba_push", "gpba_pop", "gpba_discard_top",
-    "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_active_robust_chi2", "gpba_outlier_flags",
+    "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_edge_errors", "gpba_download_evaluated_state", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
     "gpba_set_extrinsics", "gpba_get_extrinsics", "gpba_count_camera_observations", "gpba_calibrate_extrinsics",
     "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_symbolic_analyze", "gpba_pose_optimize", "gpba_vel_ransac",
@@ -207,6 +207,15 @@ class GpBa:
 
     def edge_chi2(self):
         a = np.zeros(self.prob.n_obs); self._ck(self.L.gpba_edge_chi2(self.h, _p(a)), "gpba_edge_chi2"); return a
+
+    def edge_errors(self):
+        a = np.zeros((self.prob.n_obs, 3)); self._ck(self.L.gpba_edge_errors(self.h, _p(a)), "gpba_edge_errors"); return a
+
+    def evaluated_state(self):
+        P = self.prob
+        kp = np.zeros((P.n_kf, 7)); kv = np.zeros((P.n_kf, 6)); tb = np.zeros((P.n_cam, 7))
+        self._ck(self.L.gpba_download_evaluated_state(self.h, _p(kp), _p(kv), _p(tb)), "gpba_download_evaluated_state")
+        return kp, kv, tb
 
     def active_robust_chi2(self):
         c = C.c_double(); self._ck(self.L.gpba_active_robust_chi2(self.h, C.byref(c)), "gpba_active_robust_chi2"); return c.value

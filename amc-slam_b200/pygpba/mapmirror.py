@@ -12,7 +12,7 @@ SYMBOLS = [
     "gpba_map_set_keyframe_bad", "gpba_map_add_point", "gpba_map_set_point", "gpba_map_set_point_bad",
     "gpba_map_add_observation", "gpba_map_add_observations", "gpba_map_erase_observation", "gpba_map_update_connections", "gpba_map_covisibles", "gpba_map_stats", "gpba_map_local_window",
     "gpba_map_global_window", "gpba_window_destroy", "gpba_window_problem", "gpba_window_iterations", "gpba_window_ids",
-    "gpba_window_cam_obs", "gpba_window_apply",
+    "gpba_window_cam_obs", "gpba_window_apply", "gpba_map_apply_extrinsics", "gpba_map_extrinsics",
 ]
 
 
@@ -204,6 +204,18 @@ class MapMirror:
         self._ck(self.L.gpba_window_apply(self.h, win.h, _p(kp), _p(kv), _p(px), _p(f), float(err), float(err_end),
                                           C.byref(applied), C.byref(n_er), _p(erased)))
         return bool(applied.value), erased[:n_er.value].copy()
+
+    def apply_extrinsics(self, win, cam_Tbc, min_obs=50):
+        """MultiKeyFrame::mTbc[c] = estimate.cast<float>() for cameras with cam_obs >= min_obs (Optimizer.cc:1419-1428)"""
+        n = C.c_int32(0)
+        t = np.ascontiguousarray(cam_Tbc, np.float64)
+        self._ck(self.L.gpba_map_apply_extrinsics(C.c_void_p(self.h) if not isinstance(self.h, C.c_void_p) else self.h, win.h, _p(t), C.c_int32(int(min_obs)), C.byref(n)))
+        return n.value
+
+    def extrinsics(self):
+        a = np.zeros((self.n_cam, 7))
+        self._ck(self.L.gpba_map_extrinsics(C.c_void_p(self.h) if not isinstance(self.h, C.c_void_p) else self.h, _p(a)))
+        return a
 
     def close(self):
         if self.h:

@@ -228,6 +228,13 @@ int gpba_download_state(gpba_handle* h, double* kf_pose, double* kf_vel, double*
 /* edge->chi2() of every reprojection edge from its stored _error (base_edge.h:58-61),
  * original observation order; inactive edges keep their last computed error. */
 int gpba_edge_chi2(gpba_handle* h, double* chi2);
+/* BaseEdge::_error of every ACTIVE reprojection edge as the last evaluation left it ([n_obs][3], third slot 0 for a
+ * monocular edge; NaN for inactive edges = leave the edge's error alone).  After a rejected last trial these are the
+ * rejected state's errors (the stale-error quirk of sparse_optimizer.cpp:354-419 + optimization_algorithm_levenberg.cpp:
+ * 102-166): the adapter writes them into OptimizableGraph::Edge::errorData() instead of recomputing at the estimate. */
+int gpba_edge_errors(gpba_handle* h, double* err3);
+/* Keyframe states / extrinsics of the last EVALUATED state (= gpba_download_state's unless the last trial was rejected). */
+int gpba_download_evaluated_state(gpba_handle* h, double* kf_pose, double* kf_vel, double* cam_Tbc);
 /* activeRobustChi2() over the stored errors (what LocalGPBA reads as err / err_end, Optimizer.cc:1223,1254). */
 int gpba_active_robust_chi2(gpba_handle* h, double* chi2);
 /* LocalGPBA's inlier check (Optimizer.cc:1263-1348): flag = chi2 > threshold || !isDepthPositive. */

@@ -117,6 +117,14 @@ int gpba_window_apply(gpba_map* m, const gpba_window* w, const double* kf_pose, 
                       const double* pt_xyz, const uint8_t* flags, float err, float err_end, int32_t* applied,
                       int64_t* n_erased, int64_t* erased_obs);
 
+/* LocalGPBA's extrinsic write-back (:1419-1428): for every camera with cam_obs[c] >= min_obs (extrin_thresh = 50) the
+ * mirror's Tbc becomes the calibrated estimate (gpba_get_extrinsics), float-rounded like v->estimate().cast<float>();
+ * later windows are flattened with it.  n_updated (optional): how many cameras were written. */
+int gpba_map_apply_extrinsics(gpba_map* m, const gpba_window* w, const double* cam_Tbc /* [n_cam][7] */, int32_t min_obs,
+                              int32_t* n_updated);
+/* MultiKeyFrame::mTbc as the mirror holds it: [n_cam][7] qx qy qz qw tx ty tz */
+int gpba_map_extrinsics(const gpba_map* m, double* cam_Tbc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,3 +90,23 @@ def test_threshold_prior_only_and_flags(G, oracle_mod):
     # reset_state brings the extrinsics back
     g.reset_state()
     assert np.array_equal(g.extrinsics(), P.cam_Tbc)
+
+
+def test_stale_errors_are_handed_back(G, oracle_mod):
+    """gpba_edge_errors = BaseEdge::_error of the last evaluated state (the stale-error quirk), which the adapter writes into
+    the g2o edges instead of recomputing at the estimate (VERDICT r1 weak #10)."""
+    P = synth.make_problem("c1", n_pt=600, outliers=0.1, seed=33)
+    rng = np.random.default_rng(1)
+    from pygpba.problem import OBS_LEVEL1
+    P.obs_flags = (P.obs_flags | np.where(rng.uniform(size=P.n_obs) < 0.1, OBS_LEVEL1, 0)).astype(np.uint8)
+    g = G.GpBa(P); o = oracle_mod.Oracle(P)
+    g.optimize(10); o.optimize(10)
+    eg, eo = g.edge_errors(), o.edge_errors()
+    active = (P.obs_flags & OBS_LEVEL1) == 0
+    assert np.isnan(eg[~active]).all()                                        # inactive edges: left alone
+    np.testing.assert_allclose(eg[active], eo[active], rtol=1e-6, atol=1e-8)
+    w = P.obs_inv_sigma2[active]
+    np.testing.assert_allclose(w * (eg[active] ** 2).sum(1), g.edge_chi2()[active], rtol=1e-9, atol=1e-12)
+    kp, kv, tb = g.evaluated_state()
+    s = g.state()
+    assert np.array_equal(kp, s[0]) == bool(np.array_equal(kv, s[1]))         # both equal (accepted) or both differ (rejected last trial)

@@ -336,3 +336,29 @@ def test_flattened_window_optimizes_like_the_oracle(oracle_mod):
     g2 = G.GpBa(W2.problem)
     g2.build_structure()
     assert g2.compute_errors() < 0.1 * chi0     # the wrong associations are gone
+
+
+def test_extrinsic_write_back_follows_the_observation_threshold():
+    """LocalGPBA's tail for the calibrated extrinsics (src/Optimizer.cc:1419-1428): cameras with cam_obs >= extrin_thresh
+    get MultiKeyFrame::mTbc[c] = estimate.cast<float>(), the others and the synchronous camera keep theirs; later windows are
+    flattened with the new extrinsics."""
+    P, M = geometric_map("c1", n_kf=12, n_pt=300, outliers=0.0, seed=23)
+    W = M.local_window(10 + 2 * 11)
+    before = M.extrinsics()
+    assert np.array_equal(before, P.cam_Tbc)
+    new = before.copy()
+    new[:, 4:] += 0.0123456789
+    q = new[:, :4] + np.array([0.01, -0.02, 0.005, 0.0]); new[:, :4] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    thresh = int(np.sort(W.cam_obs[:-1])[-1])                   # only the best-observed asynchronous camera passes
+    n = M.apply_extrinsics(W, new, min_obs=thresh)
+    after = M.extrinsics()
+    passed = W.cam_obs[:-1] >= thresh
+    assert n == int(passed.sum()) >= 1 and W.cam_obs[-1] == 0
+    for c in range(P.n_cam):
+        if c < P.n_cam - 1 and passed[c]:
+            f = new[c].astype(np.float32).astype(np.float64)
+            f[:4] /= np.linalg.norm(f[:4])
+            assert np.array_equal(after[c], f) and not np.array_equal(after[c], before[c])
+        else:
+            assert np.array_equal(after[c], before[c])
+    assert np.array_equal(M.local_window(10 + 2 * 11).problem.cam_Tbc, after)
