@@ -113,28 +113,6 @@ __global__ void k_chol_load(CholView C, int n_hs, const int* __restrict__ hs_row
   for (int64_t j = t0; j < C.n; j += stride) C.work[C.perm[j / 12] * 12 + j % 12] = rhs[j];
 }
 
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier
-GPBA_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-GPBA_D void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-GPBA_D void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-GPBA_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-GPBA_D void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` on the barrier
-GPBA_D void bulk_g2s(void* dst_smem, const void* src_global, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // reciprocal for the pivot chain: MUFU seed + two Newton steps (55 cycles dependent vs 85 for the IEEE division,
 // tools/microbench.cu); relative error ~1 ulp, far below what the factorization needs
 GPBA_D double fast_rcp(double d) {
@@ -339,9 +317,6 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, c
 #define GPBA_LU_CHUNK 4
 #define GPBA_LU_THREADS 160   // warps 0-3 consume (DMMA), warp 4 produces (TMA)
 struct LuDesc { double* target; int j; int flags; };   // flags: 1 first product of its chunk, 2 last product, 4 stop, 8 diagonal tile
-GPBA_D void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __global__ void __launch_bounds__(GPBA_LU_THREADS) k_chol_lupdate(CholView C, const int4* __restrict__ tab, int n_chunks,
                                                                   const int* __restrict__ klist, int* __restrict__ counter) {
   extern __shared__ __align__(128) unsigned char lu_smem[];

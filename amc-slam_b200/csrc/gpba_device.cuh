@@ -26,6 +26,8 @@ struct CamConst {
 #define GPBA_REC_LITE_STRIDE 12
 
 #define GPBA_NO_SLOT 0xFFFFu
+#define GPBA_TILE_OBS 1024     // observations per tile (a tile ends where a landmark ends)
+#define GPBA_WIN_ROWS 224      // record rows a tile can stage: 224 x 96 B = 21 KB (a 1024-observation tile of C4 touches ~126)
 
 struct DevView {
   // ---- static problem
@@ -50,6 +52,10 @@ struct DevView {
   int n_lm;
   const int* lm_pt;                           // sorted landmark -> point index
   const int64_t* lm_obs_begin;                // [n_lm+1] into sorted obs
+  // ---- landmark-aligned observation tiles of the streaming kernels (K1 / K2a): tile t covers the sorted landmarks
+  //      [tile_lm[t], tile_lm[t+1]) and stages the record rows [tile_rlo[t], tile_rlo[t] + tile_rcnt[t]) in shared memory
+  int n_tiles;
+  const int* tile_lm; const int* tile_rlo; const int* tile_rcnt;
   // ---- record-major permutation (K2b)
   const int64_t* rperm;                       // [n_aobs] sorted-obs indices grouped by record
   int n_rseg;

@@ -235,6 +235,8 @@ struct Solver {
   std::vector<int> lvl_pan_begin, lvl_upd_begin, lvl_back_begin, lvl_ncols;
   DBuf<int2> d_pan_tab, d_back_tab;
   DBuf<int4> d_upd_tab;
+  DBuf<int> d_tile_lm, d_tile_rlo, d_tile_rcnt;   // landmark-aligned observation tiles + their record windows (K1 / K2a)
+  int n_tiles = 0;
   DBuf<int> d_klist, d_lu_counter;   // d_lu_counter: one chunk counter per level of the left-looking update
   int chol_parts = 1;
   int64_t chol_products = 0, chol_update_ctas = 0;
@@ -489,6 +491,7 @@ void Solver::fill_view() {
   V.o_u = d_o_u.p; V.o_v = d_o_v.p; V.o_ur = d_o_ur.p; V.o_w = d_o_w.p; V.o_rec = d_o_rec.p; V.o_lm = d_o_lm.p;
   V.o_flags = d_o_flags.p; V.o_orig = d_o_orig.p;
   V.n_lm = n_lm; V.lm_pt = d_lm_pt.p; V.lm_obs_begin = d_lm_obs_begin.p;
+  V.n_tiles = n_tiles; V.tile_lm = d_tile_lm.p; V.tile_rlo = d_tile_rlo.p; V.tile_rcnt = d_tile_rcnt.p;
   V.rperm = d_rperm.p; V.n_rseg = n_rseg; V.rseg_rec = d_rseg_rec.p; V.rseg_begin = d_rseg_begin.p;
   V.n_pose = n_pose; V.n_hpp = n_hpp; V.n_hs = n_hs;
   V.rec_hpp11 = d_rec_hpp11.p; V.rec_hpp12 = d_rec_hpp12.p; V.rec_hpp22 = d_rec_hpp22.p;
@@ -700,6 +703,24 @@ int Solver::build_structure() {
     CK(cudaMemcpyAsync(rc.data(), d_rcnt.p, sizeof(int) * (size_t)n_rec, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     for (int r = 0; r < n_rec; ++r) rcount[r + 1] = rcount[r] + rc[r];
+  }
+  // --- landmark-aligned observation tiles (<= GPBA_TILE_OBS observations, a tile ends where a landmark ends) and the
+  //     window of record rows each of them touches
+  {
+    std::vector<int> tile_lm;
+    tile_lm.push_back(0);
+    int64_t start = 0;
+    for (int l = 0; l < n_lm; ++l)
+      if (lm_obs_begin[l + 1] - start > GPBA_TILE_OBS && l > tile_lm.back()) { tile_lm.push_back(l); start = lm_obs_begin[l]; }
+    if (n_lm > 0) tile_lm.push_back(n_lm);
+    n_tiles = (int)tile_lm.size() - 1;
+    CKR(d_tile_lm.upload(tile_lm, stream));
+    CKR(d_tile_rlo.alloc((size_t)std::max(n_tiles, 1))); CKR(d_tile_rcnt.alloc((size_t)std::max(n_tiles, 1)));
+    if (n_tiles > 0) {
+      k_tile_windows<<<(n_tiles * 32 + 255) / 256, 256, 0, stream>>>(n_tiles, d_tile_lm.p, d_lm_obs_begin.p, d_o_rec.p, n_rec, d_tile_rlo.p, d_tile_rcnt.p);
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(stream));   // tile_lm goes out of scope
   }
   lap("gather");
   // --- device: observation pairs grouped by record pair
@@ -1220,7 +1241,7 @@ __global__ void __launch_bounds__(256) k_hll_absmax(int n_lm, const double* __re
 
 int Solver::compute_records(int buf, bool full) {
   t0();
-  if (full) k_records<true><<<(n_rec + 63) / 64, 64, 0, stream>>>(Vb(buf), d_pose[buf].p, d_vel[buf].p, d_rec.p);
+  if (full) k_records<true><<<(n_rec + 63) / 64, 64, 0, stream>>>(Vb(buf), d_pose[buf].p, d_vel[buf].p, d_rec.p, d_rec_lite.p);
   else k_records<false><<<(n_rec + 63) / 64, 64, 0, stream>>>(Vb(buf), d_pose[buf].p, d_vel[buf].p, d_rec_lite.p);
   CK(cudaGetLastError());
   t1(0, 1);
@@ -1244,8 +1265,8 @@ int Solver::compute_errors(int buf, bool store, double* chi2, bool trial, const 
   CKR(compute_records(buf, false));
   t0();
   double* out = store ? (chi2_store_override ? chi2_store_override : d_chi2.p) : nullptr;
-  if (stereo) k_residual<true><<<grid_obs, 256, 0, stream>>>(Vb(buf), d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
-  else k_residual<false><<<grid_obs, 256, 0, stream>>>(Vb(buf), d_rec_lite.p, GPBA_REC_LITE_STRIDE, d_ptS[buf].p, d_partial.p, out);
+  if (stereo) k_residual<true><<<grid_obs, 256, 0, stream>>>(Vb(buf), d_rec_lite.p, d_ptS[buf].p, d_partial.p, out);
+  else k_residual<false><<<grid_obs, 256, 0, stream>>>(Vb(buf), d_rec_lite.p, d_ptS[buf].p, d_partial.p, out);
   CK(cudaGetLastError());
   const int np = n_prior + (n_velp + 63) / 64;
   const bool priors_here = rank == 0;  // priors are replicated: counted once
@@ -1282,9 +1303,9 @@ int Solver::build_system() {
   if (n_lm > 0) {
     CK(cudaMemsetAsync(d_hll.p, 0, sizeof(double) * 9 * (size_t)n_lm, stream));
     CK(cudaMemsetAsync(d_bl.p, 0, sizeof(double) * 3 * (size_t)n_lm, stream));
-    const int g = (int)std::min<int64_t>((n_aobs + GPBA_K2_THREADS - 1) / GPBA_K2_THREADS, 148 * 8);
-    if (stereo) k_lin_points<true><<<g, GPBA_K2_THREADS, 0, stream>>>(Vb(cur), d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
-    else k_lin_points<false><<<g, GPBA_K2_THREADS, 0, stream>>>(Vb(cur), d_rec.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
+    const int g = std::max(1, std::min(n_tiles, 148 * 5));
+    if (stereo) k_lin_points<true><<<g, GPBA_K2_THREADS, 0, stream>>>(Vb(cur), d_rec_lite.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
+    else k_lin_points<false><<<g, GPBA_K2_THREADS, 0, stream>>>(Vb(cur), d_rec_lite.p, d_ptS[cur].p, d_hll.p, d_bl.p, d_W.p);
     CK(cudaGetLastError());
     t1(2, 1);
     t0();
@@ -1950,8 +1971,8 @@ int gpba_edge_errors(gpba_handle* h, double* err3) {
   const int ev = s.last_eval;
   CKR(s.compute_records(ev, false));
   if (s.n_aobs > 0) {
-    if (s.stereo) k_residual<true><<<s.grid_obs, 256, 0, s.stream>>>(s.Vb(ev), s.d_rec_lite.p, GPBA_REC_LITE_STRIDE, s.d_ptS[ev].p, s.d_partial.p, nullptr, d_err.p);
-    else k_residual<false><<<s.grid_obs, 256, 0, s.stream>>>(s.Vb(ev), s.d_rec_lite.p, GPBA_REC_LITE_STRIDE, s.d_ptS[ev].p, s.d_partial.p, nullptr, d_err.p);
+    if (s.stereo) k_residual<true><<<s.grid_obs, 256, 0, s.stream>>>(s.Vb(ev), s.d_rec_lite.p, s.d_ptS[ev].p, s.d_partial.p, nullptr, d_err.p);
+    else k_residual<false><<<s.grid_obs, 256, 0, s.stream>>>(s.Vb(ev), s.d_rec_lite.p, s.d_ptS[ev].p, s.d_partial.p, nullptr, d_err.p);
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync(err3, d_err.p, sizeof(double) * 3 * (size_t)s.n_obs, cudaMemcpyDeviceToHost, s.stream));

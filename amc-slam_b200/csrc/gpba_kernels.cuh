@@ -54,6 +54,54 @@ GPBA_D void load_rec12(const double* __restrict__ p, double (&R)[12]) {
   for (int k = 0; k < 6; ++k) { const double2 v = __ldg(q + k); R[2 * k] = v.x; R[2 * k + 1] = v.y; }
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier
+GPBA_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+GPBA_D void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+GPBA_D void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+GPBA_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+GPBA_D void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+GPBA_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` on the barrier
+GPBA_D void bulk_g2s(void* dst_smem, const void* src_global, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Record window of an observation tile: the tile's observations belong to landmarks first seen by neighbouring
+// keyframes, so the records they touch form a short contiguous run of the (keyframe, camera)-ordered record table
+// (C4: ~126 rows per 1024 observations).  One thread stages the run with a single cp.async.bulk (TMA) while the others
+// fetch their observation scalars; afterwards a row is 6 LDS.128 away instead of 6 scattered LDG.128 (ncu, round 1 and
+// profiles/r02_ncu_streaming.txt: these kernels were bound by L1 tag throughput, l1tex 89-90 %, DRAM 20-45 %).
+// Observations of a revisited place (records far from the run) fall back to the global row.
+struct RecWindow {
+  const double* smem;   // staged rows (12 doubles each)
+  const double* global; // the lite record table
+  int lo, cnt;
+  GPBA_D void load12(int r, double (&R)[12]) const {
+    const unsigned d = (unsigned)(r - lo);
+    const double2* q = reinterpret_cast<const double2*>(d < (unsigned)cnt ? smem + (size_t)d * 12 : global + (size_t)r * GPBA_REC_LITE_STRIDE);
+    if (d < (unsigned)cnt) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const double2 v = q[k]; R[2 * k] = v.x; R[2 * k + 1] = v.y; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const double2 v = __ldg(q + k); R[2 * k] = v.x; R[2 * k + 1] = v.y; }
+    }
+  }
+};
+
 // Per-observation geometry shared by K1/K2/K8: residual, chi2, robust weight, J1 (rows x 6), Jp (rows x 3).
 template <bool STEREO>
 struct ObsEval {
@@ -193,7 +241,7 @@ GPBA_D void record_row(const double* __restrict__ pose1, const double* __restric
 
 template <bool FULL>
 __global__ void k_records(DevView V, const double* __restrict__ pose, const double* __restrict__ vel,
-                          double* __restrict__ rec_out) {
+                          double* __restrict__ rec_out, double* __restrict__ lite_out = nullptr) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= V.n_rec) return;
   const int k1 = V.rec_kf1[r], k2 = V.rec_kf2[r];
@@ -208,14 +256,21 @@ __global__ void k_records(DevView V, const double* __restrict__ pose, const doub
     for (int m = 0; m < 6; ++m)
 #pragma unroll
       for (int c = 0; c < 12; ++c) M[m * GPBA_REC_MS + 24 + c] = (ext && c < 6) ? cam.AdjTbc[m * 6 + c] : 0.0;
+    if (lite_out) {   // the compact (R_cw | t_cw) table the streaming kernels stage in shared memory
+#pragma unroll
+      for (int c = 0; c < 12; ++c) lite_out[(size_t)r * GPBA_REC_LITE_STRIDE + c] = out[c];
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ K1
-// One thread per observation (sorted by landmark: u/v/w/rec/lm loads are coalesced, the landmark
-// and record rows come from L1/L2).  Writes nothing per observation unless chi2_out != nullptr.
+// One thread per observation (sorted by landmark: u/v/w/rec/lm loads are coalesced, the landmark and record rows come
+// from L1/L2).  Writes nothing per observation unless chi2_out / err_out are given.  A TMA-staged variant of this kernel
+// (record window per observation tile, as K2a has) was measured and not kept: with only 36 B of HBM traffic per
+// observation the per-tile barrier + bulk-copy latency cost as much as the scattered row loads it removed
+// (profiles/r02_ncu_streaming.txt).
 template <bool STEREO>
-__global__ void __launch_bounds__(256) k_residual(DevView V, const double* __restrict__ rec, int rec_stride,
+__global__ void __launch_bounds__(256) k_residual(DevView V, const double* __restrict__ rec_lite,
                                                   const double* __restrict__ pt, double* __restrict__ partial,
                                                   double* __restrict__ chi2_out, double* __restrict__ err_out = nullptr) {
   __shared__ double red[32];
@@ -224,7 +279,7 @@ __global__ void __launch_bounds__(256) k_residual(DevView V, const double* __res
     const int r = V.o_rec[i];
     const int lm = V.o_lm[i];
     double R[12];
-    load_rec12(rec + (size_t)r * rec_stride, R);
+    load_rec12(rec_lite + (size_t)r * GPBA_REC_LITE_STRIDE, R);
     ObsEval<STEREO> E;
     eval_obs<STEREO, false>(V, R, V.cam[V.rec_cam[r]], pt[3 * (size_t)lm], pt[3 * (size_t)lm + 1], pt[3 * (size_t)lm + 2],
                             V.o_u[i], V.o_v[i], STEREO ? V.o_ur[i] : -1.0, V.o_w[i], V.o_flags[i], E, nullptr, nullptr);
@@ -256,26 +311,41 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ a, in
 // W_o = J1^T (rho' w) Jp is staged through shared memory and leaves as fully coalesced 256-byte stores; Hll / b_l are
 // reduced over the lanes of equal landmark with a segmented shuffle reduction, one atomicAdd per value and segment
 // (a landmark that straddles two warps gets two commutative adds into the zeroed accumulators).
-#define GPBA_K2_THREADS 256
+#define GPBA_K2_THREADS 128
 #define GPBA_K2_WSTRIDE 19   // padded row stride of the staging tile (18 values per observation)
 template <bool STEREO>
 __global__ void __launch_bounds__(GPBA_K2_THREADS) k_lin_points(DevView V, const double* __restrict__ rec,
                                                                 const double* __restrict__ pt, double* __restrict__ hll,
                                                                 double* __restrict__ bl, double* __restrict__ W) {
   __shared__ double sW[GPBA_K2_THREADS / 32][32 * GPBA_K2_WSTRIDE];
+  __shared__ __align__(16) double win[GPBA_WIN_ROWS * 12];
+  __shared__ __align__(8) unsigned long long bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ROWS = STEREO ? 3 : 2;
-  const int64_t nwarps = (int64_t)gridDim.x * (GPBA_K2_THREADS / 32);
-  for (int64_t base = ((int64_t)blockIdx.x * (GPBA_K2_THREADS / 32) + warp) * 32; base < V.n_aobs; base += nwarps * 32) {
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+  __syncthreads();
+  unsigned phase = 0;
+  // persistent CTAs over the landmark-aligned tiles: the tile's record rows are staged by one TMA bulk copy (RecWindow)
+  for (int t = blockIdx.x; t < V.n_tiles; t += gridDim.x) {
+   const int wlo = V.tile_rlo[t], wcnt = V.tile_rcnt[t];
+   if (threadIdx.x == 0) {
+     mbar_expect_tx(&bar, (unsigned)wcnt * 96u);
+     bulk_g2s(win, rec + (size_t)wlo * GPBA_REC_LITE_STRIDE, (unsigned)wcnt * 96u, &bar);
+   }
+   const RecWindow RW{win, rec, wlo, wcnt};
+   const int64_t t_ob = V.lm_obs_begin[V.tile_lm[t]], t_oe = V.lm_obs_begin[V.tile_lm[t + 1]];
+   mbar_wait(&bar, phase);
+   phase ^= 1u;
+   for (int64_t base = t_ob + warp * 32; base < t_oe; base += GPBA_K2_THREADS) {
     const int64_t i = base + lane;
-    const bool live = i < V.n_aobs;
+    const bool live = i < t_oe;
     int lm = -1;
     double h[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
     if (live) {
       lm = V.o_lm[i];
       const int r = V.o_rec[i];
       double R[12];
-      load_rec12(rec + (size_t)r * GPBA_REC_STRIDE, R);
+      RW.load12(r, R);
       ObsEval<STEREO> E;
       double J1[ROWS][6], Jp[ROWS][3];
       const double w = V.o_w[i];
@@ -301,7 +371,7 @@ __global__ void __launch_bounds__(GPBA_K2_THREADS) k_lin_points(DevView V, const
     }
     __syncwarp();
     // coalesced copy-out of the warp's W rows
-    const int nlive = (int)((V.n_aobs - base) < 32 ? (V.n_aobs - base) : 32);
+    const int nlive = (int)((t_oe - base) < 32 ? (t_oe - base) : 32);
     double* out = W + (size_t)base * 18;
     for (int j = lane; j < nlive * 18; j += 32) out[j] = sW[warp][(j / 18) * GPBA_K2_WSTRIDE + j % 18];
     // segmented reduction over equal landmark (segments are contiguous)
@@ -323,6 +393,8 @@ __global__ void __launch_bounds__(GPBA_K2_THREADS) k_lin_points(DevView V, const
       atomicAdd(bl + 3 * (size_t)lm, b[0]); atomicAdd(bl + 3 * (size_t)lm + 1, b[1]); atomicAdd(bl + 3 * (size_t)lm + 2, b[2]);
     }
     __syncwarp();
+   }
+   __syncthreads();   // every warp is done with the window: the next tile may overwrite it
   }
 }
 

@@ -185,6 +185,21 @@ __global__ void k_count_hpl(DevView V, const int* __restrict__ o_rec, unsigned l
   if (lane == 0 && cnt) atomicAdd(total, cnt);
 }
 
+// Record window of every observation tile: [min record, min record + GPBA_WIN_ROWS) clipped to what the tile touches.
+// One warp per tile.
+__global__ void k_tile_windows(int n_tiles, const int* __restrict__ tile_lm, const int64_t* __restrict__ lm_obs_begin,
+                               const int* __restrict__ o_rec, int n_rec, int* __restrict__ rlo, int* __restrict__ rcnt) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= n_tiles) return;
+  int mn = 0x7fffffff, mx = -1;
+  for (int64_t i = lm_obs_begin[tile_lm[t]] + lane; i < lm_obs_begin[tile_lm[t + 1]]; i += 32) { const int r = o_rec[i]; mn = min(mn, r); mx = max(mx, r); }
+  for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if (lane == 0) {
+    if (mx < 0) { rlo[t] = 0; rcnt[t] = 0; }
+    else { rlo[t] = mn; rcnt[t] = min(min(mx - mn + 1, GPBA_WIN_ROWS), n_rec - mn); }
+  }
+}
+
 // run keys (chunk, r1, r2) -> record pair part; idx = iota
 __global__ void k_item_low(int n, const unsigned long long* __restrict__ run_key, unsigned long long nrec2,
                            unsigned long long* __restrict__ low, int* __restrict__ idx) {
