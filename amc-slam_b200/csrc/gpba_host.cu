@@ -12,6 +12,7 @@
 #include "gpba_order.h"
 #include "gpba_pose.cuh"
 #include "gpba_vel.cuh"
+#include "gpba_posegraph.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -24,6 +25,7 @@
 #include <dlfcn.h>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <chrono>
 
@@ -2329,6 +2331,206 @@ int gpba_pose_optimize(const gpba_pose_batch* B, int device, double* cur_pose_ou
     fprintf(stderr, "[gpba] pose-only: %d frames, %lld matches, kernel %.3f ms\n", nf, (long long)n_obs, ms);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
+  return GPBA_OK;
+}
+
+// ---- essential-graph optimisation (the solve inside Optimizer::OptimizeEssentialGraph, src/Optimizer.cc:1434-1717)
+int gpba_pose_graph_optimize(const gpba_pose_graph* G, int device, int iters, const gpba_lm_params* params, double* sim3_out, gpba_lm_trace* trace) {
+  if (!G || G->n_kf < 0 || G->n_edge < 0 || iters < 0 || (G->n_kf > 0 && (!G->sim3 || !G->fixed)) ||
+      (G->n_edge > 0 && (!G->edge_i || !G->edge_j || !G->edge_meas))) { g_err = "invalid pose graph"; return GPBA_ERR_INVALID; }
+  const int n = G->n_kf;
+  const int64_t ne = G->n_edge;
+  for (int64_t k = 0; k < ne; ++k)
+    if (G->edge_i[k] < 0 || G->edge_i[k] >= n || G->edge_j[k] < 0 || G->edge_j[k] >= n || G->edge_i[k] == G->edge_j[k]) { g_err = "edge vertex index out of range"; return GPBA_ERR_INVALID; }
+  if (trace) { std::memset(trace, 0, sizeof(*trace)); trace->result = GPBA_RESULT_OK; }
+  if (n == 0) return GPBA_OK;
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device (libgpba has no CPU fallback)"; return GPBA_ERR_NO_DEVICE; }
+  }
+  if (device < 0) CK(cudaGetDevice(&device));
+  CK(cudaSetDevice(device));
+  gpba_lm_params P;
+  gpba_default_lm_params(&P);
+  if (params) P = *params;
+  // The reduced-system machinery (symbolic phase, tile Cholesky, its CUDA graphs) is the BA solver's: an otherwise empty
+  // Solver serves as the factorization engine of this call.
+  std::unique_ptr<gpba_handle> eng(new (std::nothrow) gpba_handle());
+  if (!eng) return GPBA_ERR_INVALID;
+  Solver& c = eng->s;
+  c.device = device;
+  CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.stream_holder.s = c.stream;
+  cudaStream_t st = c.stream;
+  g_alloc_stream = st;
+  // ---- structure (host: the graph is tiny next to a BA): active vertices, Hessian order, block pattern
+  std::vector<char> act(n, 0);
+  for (int64_t k = 0; k < ne; ++k) if (!(G->fixed[G->edge_i[k]] && G->fixed[G->edge_j[k]])) { act[G->edge_i[k]] = 1; act[G->edge_j[k]] = 1; }
+  std::vector<int> h(n, -1);
+  int np = 0;
+  for (int i = 0; i < n; ++i) if (act[i] && !G->fixed[i]) h[i] = np++;
+  if (np == 0 || iters == 0) {   // nothing to optimise
+    if (sim3_out) std::memcpy(sim3_out, G->sim3, sizeof(double) * 8 * (size_t)n);
+    return GPBA_OK;
+  }
+  std::vector<unsigned long long> keys;
+  keys.reserve((size_t)np + (size_t)ne);
+  for (int i = 0; i < np; ++i) keys.push_back(((unsigned long long)i << 32) | (unsigned)i);
+  for (int64_t k = 0; k < ne; ++k) {
+    const int a = h[G->edge_i[k]], b = h[G->edge_j[k]];
+    if (a < 0 || b < 0) continue;
+    keys.push_back(((unsigned long long)std::max(a, b) << 32) | (unsigned)std::min(a, b));   // (col, row), row <= col
+  }
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  const int nb = (int)keys.size();
+  c.n_pose = np; c.n_pose_kf = np; c.n_hs = nb; c.linear_solver = GPBA_SOLVER_SPARSE_CHOL;
+  c.hs_row.resize(nb); c.hs_col.resize(nb);
+  std::vector<int> diag_of(nb, -1);
+  for (int q = 0; q < nb; ++q) { c.hs_row[q] = (int)(unsigned)keys[q]; c.hs_col[q] = (int)(keys[q] >> 32); if (c.hs_row[q] == c.hs_col[q]) diag_of[q] = c.hs_row[q]; }
+  auto blk = [&](int a, int b) { return (int)(std::lower_bound(keys.begin(), keys.end(), ((unsigned long long)b << 32) | (unsigned)a) - keys.begin()); };
+  std::vector<int> bii((size_t)ne, -1), bjj((size_t)ne, -1), bij((size_t)ne, -1);
+  for (int64_t k = 0; k < ne; ++k) {
+    const int a = h[G->edge_i[k]], b = h[G->edge_j[k]];
+    if (a >= 0) bii[k] = blk(a, a);
+    if (b >= 0) bjj[k] = blk(b, b);
+    if (a >= 0 && b >= 0) bij[k] = a < b ? blk(a, b) : (blk(b, a) | 0x40000000);
+  }
+  DBuf<double> d_S[2], d_meas, d_hpp, d_bp, d_partial, d_pscale, d_scal;
+  DBuf<int> d_ei, d_ej, d_h, d_bii, d_bjj, d_bij, d_diag;
+  DBuf<unsigned char> d_fixed;
+  for (int b = 0; b < 2; ++b) CKR(d_S[b].upload(G->sim3, (size_t)8 * n, st));
+  CKR(d_meas.upload(G->edge_meas, (size_t)8 * ne, st)); CKR(d_ei.upload(G->edge_i, (size_t)ne, st)); CKR(d_ej.upload(G->edge_j, (size_t)ne, st));
+  CKR(d_fixed.upload(G->fixed, (size_t)n, st)); CKR(d_h.upload(h, st));
+  CKR(d_bii.upload(bii, st)); CKR(d_bjj.upload(bjj, st)); CKR(d_bij.upload(bij, st)); CKR(d_diag.upload(diag_of, st));
+  CKR(d_hpp.alloc((size_t)nb * 144)); CKR(d_bp.alloc((size_t)np * 12)); CKR(d_pscale.alloc((size_t)np)); CKR(d_scal.alloc(8));
+  CKR(c.d_hs.alloc((size_t)nb * 144 + (size_t)np * 12 + 8)); CKR(c.d_x.alloc((size_t)np * 12)); CKR(c.d_fail.alloc(2));
+  CKR(c.d_hs_row.upload(c.hs_row, st)); CKR(c.d_hs_col.upload(c.hs_col, st));
+  CKR(c.build_cholesky_structure());
+  CKR(c.capture_cholesky_graph());
+  const int ge = (int)std::min<int64_t>((ne + 127) / 128, 148 * 8);
+  CKR(d_partial.alloc((size_t)std::max(ge, 1)));
+  PgView V;
+  V.n_kf = n; V.fix_scale = G->fix_scale; V.n_edge = ne; V.ei = d_ei.p; V.ej = d_ej.p; V.meas = d_meas.p; V.fixed = d_fixed.p; V.h = d_h.p;
+  V.blk_ii = d_bii.p; V.blk_jj = d_bjj.p; V.blk_ij = d_bij.p;
+  double* h_scal = (double*)g_pinned.take();
+  if (!h_scal) { g_err = "out of pinned scratch slots"; return GPBA_ERR_CUDA; }
+  struct Give { double* p; ~Give() { g_pinned.give(p); } } give{h_scal};
+  int cur = 0;
+  auto errors = [&](int buf, double* chi) -> int {   // computeActiveErrors + activeRobustChi2
+    k_pg_errors<<<std::max(ge, 1), 128, 0, st>>>(V, d_S[buf].p, d_partial.p);
+    k_reduce<<<1, 256, 0, st>>>(d_partial.p, ne > 0 ? ge : 0, nullptr, 0, d_scal.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_scal, d_scal.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_scal + 4, c.d_fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *chi = h_scal[0];
+    return GPBA_OK;
+  };
+  double lambda = -1, ni = 2;
+  int nBad = 0, cj = 0, result = GPBA_RESULT_OK;
+  bool ok = true;
+  double* bs = c.d_hs.p + (size_t)nb * 144;
+  for (int it = 0; it < iters && ok; ++it) {
+    double currentChi = 0;
+    CKR(errors(cur, &currentChi));
+    double tempChi = currentChi;
+    const double iniChi = currentChi;
+    // buildSystem
+    CK(cudaMemsetAsync(d_hpp.p, 0, sizeof(double) * 144 * (size_t)nb, st));
+    CK(cudaMemsetAsync(d_bp.p, 0, sizeof(double) * 12 * (size_t)np, st));
+    if (ne > 0) { k_pg_linearize<<<(int)((ne + 63) / 64), 64, 0, st>>>(V, d_S[cur].p, d_hpp.p, d_bp.p); CK(cudaGetLastError()); }
+    if (it == 0) {
+      if (G->lambda_init > 0) lambda = G->lambda_init;
+      else {   // computeLambdaInit: tau * max |H_jj|
+        std::vector<double> hd((size_t)np * 12);
+        DBuf<double> d_diagv;
+        CKR(d_diagv.alloc(hd.size()));
+        DBuf<int> d_pd;
+        std::vector<int> pd(np);
+        for (int q = 0; q < nb; ++q) if (diag_of[q] >= 0) pd[diag_of[q]] = q;
+        CKR(d_pd.upload(pd, st));
+        k_hpp_diag<<<(np * 12 + 255) / 256, 256, 0, st>>>(np, d_pd.p, d_hpp.p, d_diagv.p);
+        CK(cudaMemcpyAsync(hd.data(), d_diagv.p, sizeof(double) * hd.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        double mx = 0;
+        for (double v : hd) mx = std::max(mx, std::fabs(v));
+        lambda = P.tau * mx;
+      }
+      ni = 2; nBad = 0;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      const int nbuf = 1 - cur;
+      CK(cudaMemsetAsync(c.d_fail.p, 0, sizeof(int), st));
+      k_pg_damp<<<(std::max(nb * 144, np * 12) + 255) / 256, 256, 0, st>>>(nb, d_diag.p, d_hpp.p, lambda, c.d_hs.p, np, d_bp.p, bs);
+      CK(cudaGetLastError());
+      CK(cudaGraphLaunch(c.chol_graph, st));
+      CK(cudaGraphLaunch(c.chol_back_graph, st));
+      k_pg_update<<<(n + 63) / 64, 64, 0, st>>>(V, lambda, c.d_x.p, d_bp.p, d_S[cur].p, d_S[nbuf].p, d_pscale.p);
+      k_reduce<<<1, 256, 0, st>>>(d_pscale.p, np, nullptr, 0, d_scal.p + 1);
+      CK(cudaGetLastError());
+      CKR(errors(nbuf, &tempChi));
+      const bool ok2 = *(int*)(h_scal + 4) == 0;
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      double scale = h_scal[1];
+      rho = currentChi - tempChi;
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = (std::min)(alpha, P.good_step_upper);
+        lambda *= (std::max)(P.good_step_lower, alpha);
+        ni = 2;
+        currentChi = tempChi;
+        cur = nbuf;
+      } else {
+        lambda *= ni;
+        ni *= 2;
+      }
+      qmax++;
+    } while (rho < 0 && qmax < P.max_trials_after_failure);
+    if (trace && it < GPBA_MAX_ITERS) {
+      trace->levenberg_iterations[it] = qmax; trace->chi2_before[it] = iniChi; trace->chi2_after[it] = currentChi;
+      trace->lambda[it] = lambda; trace->total_trials += qmax; trace->last_trial_chi2 = tempChi;
+    }
+    ++cj;
+    if (qmax == P.max_trials_after_failure || rho == 0) { result = GPBA_TERMINATE; ok = false; }
+    else {
+      if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+      if (nBad >= 3) { result = GPBA_TERMINATE; ok = false; }
+    }
+  }
+  if (trace) { trace->n_iters = cj; trace->result = result; }
+  if (sim3_out) CK(cudaMemcpyAsync(sim3_out, d_S[cur].p, sizeof(double) * 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return GPBA_OK;
+}
+
+int gpba_correct_points(int device, int64_t n_pt, const double* xyz, const int32_t* ref_kf, int32_t n_kf, const double* sim3_before,
+                        const double* sim3_after, double* xyz_out) {
+  if (n_pt < 0 || n_kf < 0 || (n_pt > 0 && (!xyz || !ref_kf || !sim3_before || !sim3_after || !xyz_out))) { g_err = "invalid argument"; return GPBA_ERR_INVALID; }
+  for (int64_t i = 0; i < n_pt; ++i) if (ref_kf[i] < 0 || ref_kf[i] >= n_kf) { g_err = "reference keyframe index out of range"; return GPBA_ERR_INVALID; }
+  if (n_pt == 0) return GPBA_OK;
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device (libgpba has no CPU fallback)"; return GPBA_ERR_NO_DEVICE; }
+  }
+  if (device < 0) CK(cudaGetDevice(&device));
+  CK(cudaSetDevice(device));
+  cudaStream_t st = small_call_stream(device);
+  if (!st) { g_err = "cudaStreamCreate failed"; return GPBA_ERR_CUDA; }
+  g_alloc_stream = st;
+  DBuf<double> d_x, d_a, d_b, d_o;
+  DBuf<int> d_r;
+  CKR(d_x.upload(xyz, (size_t)3 * n_pt, st)); CKR(d_r.upload(ref_kf, (size_t)n_pt, st));
+  CKR(d_a.upload(sim3_before, (size_t)8 * n_kf, st)); CKR(d_b.upload(sim3_after, (size_t)8 * n_kf, st));
+  CKR(d_o.alloc((size_t)3 * n_pt));
+  k_correct_points<<<(int)std::min<int64_t>((n_pt + 255) / 256, 148 * 8), 256, 0, st>>>(n_pt, d_x.p, d_r.p, d_a.p, d_b.p, d_o.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(xyz_out, d_o.p, sizeof(double) * 3 * (size_t)n_pt, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return GPBA_OK;
 }
 

@@ -22,7 +22,7 @@ SYMBOLS = [
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_edge_errors", "gpba_download_evaluated_state", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
     "gpba_set_extrinsics", "gpba_get_extrinsics", "gpba_count_camera_observations", "gpba_calibrate_extrinsics",
-    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_symbolic_analyze", "gpba_pose_optimize", "gpba_vel_ransac",
+    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_symbolic_analyze", "gpba_pose_optimize", "gpba_vel_ransac", "gpba_pose_graph_optimize", "gpba_correct_points",
 ]
 
 

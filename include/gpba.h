@@ -349,6 +349,34 @@ typedef struct gpba_vel_batch {
 int gpba_vel_ransac(const gpba_vel_batch* batch, int device, double* vel_out, int32_t* inliers_out,
                     uint8_t* inlier_mask_out, int32_t* best_out, gpba_lm_trace* traces);
 
+/* ---- essential-graph optimisation ------------------------------- */
+/* The optimisation inside Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:1434-1717), the step right before the global
+ * BA: a pose graph of VertexSim3Expmap (7-dim, S <- Sim3(update) S, update = [omega; upsilon; sigma], sigma forced to 0 when
+ * fix_scale; Thirdparty/g2o/g2o/types/types_seven_dof_expmap.h:48-96, sim3.h) joined by EdgeSim3 (e = Log(S_ji S_i S_j^-1),
+ * information = I_7, :99-126, Optimizer.cc:1505, 1535-1541), solved with BlockSolver_7_3 + LinearSolverEigen and
+ * Levenberg-Marquardt, lambda_0 = 1e-16 (:1441-1448), optimize(20) (:1667).  EdgeSim3 has no analytic Jacobian: g2o
+ * differentiates numerically (central differences, delta = 1e-9, core/base_binary_edge.hpp:131-200) and so does the kernel.
+ * WHICH edges exist (loop connections, spanning tree, loop edges, covisibility >= 100, :1507-1640) is the caller's map
+ * logic; the call takes the flattened graph.  Keyframes in ascending id (= Hessian order). */
+typedef struct gpba_pose_graph {
+  int32_t n_kf;
+  const double* sim3;        /* [n_kf][8] qx qy qz qw tx ty tz s: VertexSim3Expmap estimate S_iw (:1468-1482)        */
+  const uint8_t* fixed;      /* [n_kf] setFixed(true) for the map's initial keyframe (:1484-1485)                    */
+  int32_t fix_scale;         /* VertexSim3Expmap::_fix_scale = bFixScale (:1489)                                     */
+  int64_t n_edge;
+  const int32_t* edge_i;     /* [n_edge] vertex 0 of the edge (setVertex(0, ...nIDi), :1533)                         */
+  const int32_t* edge_j;     /* [n_edge] vertex 1 (:1532)                                                            */
+  const double* edge_meas;   /* [n_edge][8] measurement S_ji (:1534)                                                 */
+  double lambda_init;        /* setUserLambdaInit(1e-16) (:1447); <= 0: tau * max diagonal                           */
+} gpba_pose_graph;
+/* sim3_out [n_kf][8]: the optimised S_iw (CorrectedSiw, :1677); trace may be NULL. */
+int gpba_pose_graph_optimize(const gpba_pose_graph* graph, int device, int iters, const gpba_lm_params* params,
+                             double* sim3_out, gpba_lm_trace* trace);
+/* Map point correction after the pose graph (:1687-1712): P <- S_wr' (S_rw P), r = ref_kf[p] the point's reference
+ * keyframe, S_rw from sim3_before, S_wr' the inverse of sim3_after[r].  xyz_out may alias xyz. */
+int gpba_correct_points(int device, int64_t n_pt, const double* xyz, const int32_t* ref_kf, int32_t n_kf,
+                        const double* sim3_before, const double* sim3_after, double* xyz_out);
+
 /* ---- measurement ------------------------------------------------------------------- */
 /* Total device time (ms, CUDA event pairs recorded on the library stream, read back only here) and
  * launch count per stage since the last reset: 0 records (K0), 1 residuals (K1), 2 linearize landmarks

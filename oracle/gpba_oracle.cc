@@ -24,6 +24,7 @@
 //   src/Optimizer.cc:548-675               chi2 rejection rounds structure          -> rejection_rounds()
 #include "../include/gpba.h"
 #include "gp_edges.h"
+#include "pose_graph.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -1125,6 +1126,32 @@ int oracle_count_camera_observations(void* h, int64_t* cam_obs) {
   for (int64_t i = 0; i < o->n_obs; ++i) if (o->rec_kf1[o->obs_rec[i]] >= 0) cam_obs[o->rec_cam[o->obs_rec[i]]]++;
   return 0;
 }
+// ---- essential-graph optimisation (oracle/pose_graph.h; src/Optimizer.cc:1434-1717)
+int oracle_pose_graph_optimize(const gpba_pose_graph* g, int iters, const gpba_lm_params* params, double* sim3_out, gpba_lm_trace* trace) {
+  PoseGraphOracle o;
+  o.load(g);
+  gpba_lm_params P;
+  P.max_trials_after_failure = 10; P.tau = 1e-5; P.good_step_lower = 1. / 3.; P.good_step_upper = 2. / 3.; P.pcg_tolerance = 0; P.pcg_max_iterations = 0;
+  if (params) P = *params;
+  o.optimize(iters, P, trace, ldlt_dense);
+  if (sim3_out) for (int i = 0; i < o.n; ++i) sim3_to8(o.S[i], sim3_out + 8 * i);
+  return 0;
+}
+// src/Optimizer.cc:1687-1712: P <- correctedSwr.map(Srw.map(P)) with r the point's reference keyframe
+int oracle_correct_points(int64_t n_pt, const double* xyz, const int32_t* ref_kf, const double* sim3_before, const double* sim3_after, double* xyz_out) {
+  for (int64_t i = 0; i < n_pt; ++i) {
+    const Sim3 Srw = sim3_from8(sim3_before + 8 * (size_t)ref_kf[i]);
+    const Sim3 Swr = sim3_inv(sim3_from8(sim3_after + 8 * (size_t)ref_kf[i]));
+    V3 p; p[0] = xyz[3 * i]; p[1] = xyz[3 * i + 1]; p[2] = xyz[3 * i + 2];
+    const V3 q = sim3_map(Swr, sim3_map(Srw, p));
+    xyz_out[3 * i] = q[0]; xyz_out[3 * i + 1] = q[1]; xyz_out[3 * i + 2] = q[2];
+  }
+  return 0;
+}
+void oracle_sim3_exp(const double* u7, double* S8) { sim3_to8(sim3_exp(u7), S8); }
+void oracle_sim3_log(const double* S8, double* u7) { sim3_log(sim3_from8(S8), u7); }
+void oracle_sim3_mul(const double* a, const double* b, double* o8) { sim3_to8(sim3_mul(sim3_from8(a), sim3_from8(b)), o8); }
+void oracle_sim3_inv(const double* a, double* o8) { sim3_to8(sim3_inv(sim3_from8(a)), o8); }
 void oracle_set_threads(void* h, int n) { ORA(h)->threads = n < 1 ? 1 : n; }
 // seconds per stage since the last reset: timeResiduals, timeQuadraticForm (linearize + quadratic form), timeSchurComplement,
 // timeLinearSolver, timeUpdate -- the G2OBatchStatistics fields (g2o/core/batch_stats.h:39-78)

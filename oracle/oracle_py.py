@@ -311,6 +311,36 @@ def vel_ransac(B):
     return R
 
 
+def pose_graph_optimize(G, iters=20, params=None):
+    """CPU restatement of the optimisation inside Optimizer::OptimizeEssentialGraph on a pygpba.posegraph.PoseGraph"""
+    c = G.to_c()
+    out = np.zeros((G.n_kf, 8)); tr = LmTrace()
+    lib().oracle_pose_graph_optimize(C.byref(c), int(iters), C.byref(params) if params is not None else None, _p(out), C.byref(tr))
+    return out, tr
+
+
+def correct_points(xyz, ref_kf, sim3_before, sim3_after):
+    x = _d(xyz); r = np.ascontiguousarray(ref_kf, np.int32); out = np.zeros_like(x)
+    lib().oracle_correct_points(C.c_int64(len(x)), _p(x), _p(r), _p(_d(sim3_before)), _p(_d(sim3_after)), _p(out))
+    return out
+
+
+def sim3_exp(u):
+    o = np.zeros(8); lib().oracle_sim3_exp(_p(_d(u)), _p(o)); return o
+
+
+def sim3_log(S):
+    o = np.zeros(7); lib().oracle_sim3_log(_p(_d(S)), _p(o)); return o
+
+
+def sim3_mul(a, b):
+    o = np.zeros(8); lib().oracle_sim3_mul(_p(_d(a)), _p(_d(b)), _p(o)); return o
+
+
+def sim3_inv(a):
+    o = np.zeros(8); lib().oracle_sim3_inv(_p(_d(a)), _p(o)); return o
+
+
 def pose_system(B, f):
     """(H, b, chi2) of frame f of a PoseBatch at its initial estimate (oracle/pose_only.h build_system)"""
     c = B.to_c()
