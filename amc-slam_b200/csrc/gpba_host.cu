@@ -52,19 +52,69 @@ namespace {
 // keeps freed blocks, so building the structures of the next optimize() call does not pay cudaMalloc / cudaFree again
 // (they were ~200 ms of a 380 ms build_structure at C4).  g_alloc_stream is set by every entry point of a handle.
 static thread_local cudaStream_t g_alloc_stream = nullptr;
+
+// A SLAM process runs one BA after the other, each with a fresh handle (like a fresh g2o::SparseOptimizer) and nearly the same
+// buffer sizes.  cudaMallocAsync's pool re-uses freed memory, but a create / destroy cycle of ~4 GB in ~150 blocks made it
+// re-map physical memory unpredictably (measured: gpba_build_structure 17 .. 46 ms for the same problem, one call of 967 ms).
+// Freed blocks are therefore parked in a process-wide best-fit cache; a block taken on another stream than the one it was
+// released on first waits for the event recorded at release time, so the cache is as stream-ordered as cudaFreeAsync is.
+// Total parked memory is capped; beyond the cap blocks go back to the driver pool.
+struct BlockCache {
+  struct Block { void* p; size_t bytes; int device; cudaStream_t stream; cudaEvent_t ev; };
+  std::mutex m;
+  std::multimap<size_t, Block> free_blocks;   // by capacity
+  size_t parked = 0;
+  static constexpr size_t kCap = 24ull << 30;   // parked bytes per process
+  static size_t round_up(size_t b) { return b < (1u << 20) ? ((b + 511) & ~size_t(511)) : ((b + (1u << 20) - 1) & ~size_t((1u << 20) - 1)); }
+  cudaError_t get(void** out, size_t bytes, size_t* capacity, cudaStream_t s) {
+    bytes = round_up(bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lock(m);
+      for (auto it = free_blocks.lower_bound(bytes); it != free_blocks.end() && it->first <= bytes + bytes / 4 + (1u << 20); ++it) {
+        if (it->second.device != dev) continue;
+        Block b = it->second;
+        free_blocks.erase(it);
+        parked -= b.bytes;
+        if (b.stream != s) cudaStreamWaitEvent(s, b.ev, 0);
+        cudaEventDestroy(b.ev);
+        *out = b.p; *capacity = b.bytes;
+        return cudaSuccess;
+      }
+    }
+    *capacity = bytes;
+    return cudaMallocAsync(out, bytes, s);
+  }
+  void put(void* p, size_t bytes, cudaStream_t s) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaEvent_t ev = nullptr;
+    std::unique_lock<std::mutex> lock(m);
+    if (parked + bytes > kCap || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { lock.unlock(); cudaFreeAsync(p, s); return; }
+    cudaEventRecord(ev, s);
+    free_blocks.emplace(bytes, Block{p, bytes, dev, s, ev});
+    parked += bytes;
+  }
+};
+static BlockCache g_blocks;
+
 template <typename T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  size_t cap_bytes = 0;
   cudaStream_t owner = nullptr;
   ~DBuf() { release(); }
-  void release() { if (p) cudaFreeAsync(p, owner); p = nullptr; n = 0; }
+  void release() { if (p) g_blocks.put(p, cap_bytes, owner); p = nullptr; n = 0; cap_bytes = 0; }
   int alloc(size_t count) {
     if (count <= n && p) return GPBA_OK;
     release();
     if (count == 0) count = 1;
     owner = g_alloc_stream;
-    CK(cudaMallocAsync(&p, count * sizeof(T), owner));
+    void* q = nullptr;
+    CK(g_blocks.get(&q, count * sizeof(T), &cap_bytes, owner));
+    p = (T*)q;
     n = count;
     return GPBA_OK;
   }
