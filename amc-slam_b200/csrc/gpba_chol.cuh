@@ -250,7 +250,8 @@ GPBA_D void trsm48(double (*T)[GPBA_LD], const double (*S)[GPBA_LD], const doubl
 
 // Panel step of the tile columns of one level.  One CTA per table entry (k, q): q = 0 is the diagonal CTA of column k,
 // q > 0 its q-th non-zero tile below the diagonal.
-__global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, const int2* __restrict__ tab, int* __restrict__ fail) {
+__global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, const int2* __restrict__ tab, int* __restrict__ fail,
+                                                                   int* __restrict__ level_done) {
   const int k = tab[blockIdx.x].x, q_ = tab[blockIdx.x].y;
   __shared__ __align__(16) double S[GPBA_NB][GPBA_LD];
   __shared__ __align__(16) double T[GPBA_NB][GPBA_LD];
@@ -298,6 +299,11 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, c
   }
   GPBA_TICK(4);
   GPBA_TICK_DUMP();
+  // The next level's left-looking update already runs (it was launched when this grid became resident) and consumes the
+  // older columns; its producers wait for this counter before they touch a column of THIS level.
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) atomicAdd(level_done, 1);
 }
 
 // Left-looking update of the tile columns of one level: tile (i, j) of a column of the level receives
@@ -317,8 +323,10 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, c
 #define GPBA_LU_CHUNK 4
 #define GPBA_LU_THREADS 160   // warps 0-3 consume (DMMA), warp 4 produces (TMA)
 struct LuDesc { double* target; int j; int flags; };   // flags: 1 first product of its chunk, 2 last product, 4 stop, 8 diagonal tile
+#define GPBA_LU_LATE 0x80000000u   // klist entry: the source column belongs to the level whose panel step is still in flight
 __global__ void __launch_bounds__(GPBA_LU_THREADS) k_chol_lupdate(CholView C, const int4* __restrict__ tab, int n_chunks,
-                                                                  const int* __restrict__ klist, int* __restrict__ counter) {
+                                                                  const unsigned* __restrict__ klist, int* __restrict__ counter,
+                                                                  const int* __restrict__ prev_done, int prev_count, int* __restrict__ fail) {
   extern __shared__ __align__(128) unsigned char lu_smem[];
   __shared__ __align__(8) unsigned long long full[GPBA_LU_STAGES], empty[GPBA_LU_STAGES];
   __shared__ LuDesc desc[GPBA_LU_STAGES];
@@ -334,14 +342,21 @@ __global__ void __launch_bounds__(GPBA_LU_THREADS) k_chol_lupdate(CholView C, co
     for (int s = 0; s < GPBA_LU_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
     mbar_init_fence();
   }
-  pdl_wait_then_release();   // everything below reads what the previous launches wrote
+  // LOOK-AHEAD.  This grid is the programmatic dependent of the previous level's panel grid and deliberately does NOT wait
+  // for it (no griddepcontrol.wait): that grid executed its own wait -- everything older than it is complete and visible --
+  // before it let this one start, so only the previous level's columns are still being written.  Products whose source is
+  // such a column (GPBA_LU_LATE, sorted to the end of every list and of the chunk table) wait for the panel grid's completion
+  // counter; all others (the bulk: contributions of columns finished long ago) overlap with the panel step.  The panel grid
+  // is resident in full before this grid exists (that is when a programmatic dependent may start), so the wait cannot
+  // deadlock.  Without programmatic launches the grids run in stream order and the counter is already there.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();           // barrier initialisation visible to both roles
   if (warp == 4) {
     // ---------------------------------------------------------------- producer (one thread): the operand stream
     if (lane != 0) return;
     int pos = 0, begin = 0, end = 0, pi = 0, pj = 0;
     double* target = nullptr;
-    bool diag = false;
+    bool diag = false, prev_ready = prev_count <= 0;
     for (int n = 0;; ++n) {
       const int s = n % GPBA_LU_STAGES;
       if (n >= GPBA_LU_STAGES) mbar_wait(&empty[s], (unsigned)(n / GPBA_LU_STAGES - 1) & 1u);   // the four warps released the stage
@@ -358,7 +373,20 @@ __global__ void __launch_bounds__(GPBA_LU_THREADS) k_chol_lupdate(CholView C, co
         target = C.tiles + C.tile_off[(size_t)pi * C.NT + pj];
         begin = pos = e.z; end = e.w;
       }
-      const int k = klist[pos];
+      const unsigned ke = klist[pos];
+      const int k = (int)(ke & ~GPBA_LU_LATE);
+      if ((ke & GPBA_LU_LATE) && !prev_ready) {
+        // the source column is being written by the panel grid in flight: wait for its last CTA (bounded: a grid that
+        // never completes is reported as a failed factorization instead of a hang)
+        unsigned spins = 0;
+        int seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(prev_done) : "memory");
+        } while (seen < prev_count && ++spins < (1u << 26));
+        if (seen < prev_count) atomicExch(fail, 1);
+        asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies below (async proxy) read what that grid wrote
+        prev_ready = true;
+      }
       desc[s].target = target; desc[s].j = pj;
       desc[s].flags = (pos == begin ? 1 : 0) | (pos + 1 == end ? 2 : 0) | (diag ? 8 : 0);
       mbar_expect_tx(&full[s], diag ? GPBA_TILE_BYTES + GPBA_NB * 8u : 2u * GPBA_TILE_BYTES);

@@ -289,7 +289,8 @@ struct Solver {
   DBuf<int4> d_upd_tab;
   DBuf<int> d_tile_lm, d_tile_rlo, d_tile_rcnt;   // landmark-aligned observation tiles + their record windows (K1 / K2a)
   int n_tiles = 0;
-  DBuf<int> d_klist, d_lu_counter;   // d_lu_counter: one chunk counter per level of the left-looking update
+  DBuf<unsigned> d_klist;
+  DBuf<int> d_lu_counter;            // [2 * levels]: chunk counter of every level's update, then completion counter of every level's panel grid
   int chol_parts = 1;
   int64_t chol_products = 0, chol_update_ctas = 0;
   cudaGraphExec_t chol_graph = nullptr;       // load + (panel, update) x NT, captured once per structure
@@ -1116,11 +1117,14 @@ int Solver::build_cholesky_structure() {
   for (int k = 0; k < NT; ++k) lvl_cols[level[k]].push_back(k);
   std::vector<int2> pan_tab, back_tab;
   std::vector<int4> upd_tab;     // left-looking update: {column j, tile slot q (| GPBA_LU_SPLIT), klist begin, klist end}
-  std::vector<int> klist;        // finished columns k with L_ik != 0 and L_jk != 0, ascending, per tile (i, j)
+  std::vector<unsigned> klist;   // finished columns k with L_ik != 0 and L_jk != 0 per tile (i, j); bit 31: column of the previous level
   lvl_pan_begin.assign(n_levels + 1, 0); lvl_upd_begin.assign(n_levels + 1, 0); lvl_back_begin.assign(n_levels + 1, 0);
   lvl_ncols.assign(n_levels, 0);
+  std::vector<unsigned> late_scratch;
+  std::vector<int4> early_chunks, late_chunks;
   for (int l = 0; l < n_levels; ++l) {
     lvl_ncols[l] = (int)lvl_cols[l].size();
+    early_chunks.clear(); late_chunks.clear();
     for (int k : lvl_cols[l]) {
       const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
       for (int q = 0; q <= nr; ++q) pan_tab.push_back(make_int2(k, q));
@@ -1131,18 +1135,33 @@ int Solver::build_cholesky_structure() {
         const int *pa = sym.row_cols.data() + chol_row_begin[i], *pae = sym.row_cols.data() + chol_row_begin[i + 1];
         const int *pb = sym.row_cols.data() + chol_row_begin[k], *pbe = sym.row_cols.data() + chol_row_begin[k + 1];
         const int kb = (int)klist.size();
-        while (pa < pae && pb < pbe) { if (*pa < *pb) ++pa; else if (*pb < *pa) ++pb; else { klist.push_back(*pa); ++pa; ++pb; } }
+        // sources of older levels first, sources of the previous level (whose panel step overlaps with this update) last
+        size_t n_late = 0;
+        std::vector<unsigned>& late = late_scratch;
+        late.clear();
+        while (pa < pae && pb < pbe) {
+          if (*pa < *pb) ++pa; else if (*pb < *pa) ++pb;
+          else { if (level[*pa] == l - 1) late.push_back((unsigned)*pa | GPBA_LU_LATE); else klist.push_back((unsigned)*pa); ++pa; ++pb; }
+        }
+        n_late = late.size();
+        klist.insert(klist.end(), late.begin(), late.end());
         const int cnt = (int)klist.size() - kb;
         if (cnt == 0) continue;
         static const int lu_chunk = getenv("GPBA_LU_CHUNK") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK"))) : GPBA_LU_CHUNK;
         const int nch = (cnt + lu_chunk - 1) / lu_chunk;
-        for (int c = 0; c < nch; ++c)
-          upd_tab.push_back(make_int4(k, q, kb + (int)((int64_t)cnt * c / nch), kb + (int)((int64_t)cnt * (c + 1) / nch)));
+        for (int c = 0; c < nch; ++c) {
+          const int cb = kb + (int)((int64_t)cnt * c / nch), ce = kb + (int)((int64_t)cnt * (c + 1) / nch);
+          const bool is_late = ce > kb + cnt - (int)n_late;   // the chunk reaches into the late tail
+          (is_late ? late_chunks : early_chunks).push_back(make_int4(k, q, cb, ce));
+        }
       }
       const int nrow = chol_row_begin[k + 1] - chol_row_begin[k];
       for (int q = 0; q <= nrow; ++q) back_tab.push_back(make_int2(k, q));
       if (nr >= 65536) { g_err = "tile column with more than 65535 rows"; return GPBA_ERR_INVALID; }
     }
+    // chunks that only need finished levels are handed out first: they overlap with the previous level's panel step
+    upd_tab.insert(upd_tab.end(), early_chunks.begin(), early_chunks.end());
+    upd_tab.insert(upd_tab.end(), late_chunks.begin(), late_chunks.end());
     lvl_pan_begin[l + 1] = (int)pan_tab.size(); lvl_upd_begin[l + 1] = (int)upd_tab.size(); lvl_back_begin[l + 1] = (int)back_tab.size();
   }
   chol_products = (int64_t)klist.size(); chol_update_ctas = (int64_t)upd_tab.size();
@@ -1150,7 +1169,7 @@ int Solver::build_cholesky_structure() {
   if (klist.empty()) klist.push_back(0);
   CKR(d_pan_tab.upload(pan_tab, stream)); CKR(d_upd_tab.upload(upd_tab, stream)); CKR(d_back_tab.upload(back_tab, stream));
   CKR(d_klist.upload(klist, stream));
-  CKR(d_lu_counter.alloc((size_t)std::max(n_levels, 1)));
+  CKR(d_lu_counter.alloc(2 * (size_t)std::max(n_levels, 1)));
   if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns, %zu panel CTAs, %zu update CTAs for %zu tile products\n", chol_parts, n_levels, NT, pan_tab.size(), upd_tab.size(), klist.size());
   CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
   if (chol_graph) { cudaGraphExecDestroy(chol_graph); chol_graph = nullptr; }
@@ -1204,7 +1223,7 @@ int Solver::capture_cholesky_graph() {
   int launches = 0;
   cudaError_t e = cudaMemsetAsync(d_tiles.p, 0, sizeof(double) * (size_t)chol_doubles, stream);
   // chunk counters of the left-looking update: reset by every replay of the graph (a memset node in front of the kernels)
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_lu_counter.p, 0, sizeof(int) * (size_t)std::max<size_t>(lvl_ncols.size(), 1), stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_lu_counter.p, 0, sizeof(int) * 2 * (size_t)std::max<size_t>(lvl_ncols.size(), 1), stream);
   if (e == cudaSuccess) {
     const int64_t work = std::max((int64_t)n_hs * 144, (int64_t)NT * GPBA_NB);
     k_chol_load<<<(int)std::min((work + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(C, n_hs, d_hs_row.p, d_hs_col.p, d_hs.p, bs);
@@ -1221,13 +1240,16 @@ int Solver::capture_cholesky_graph() {
       // left-looking: the level's tiles first receive the products of all finished columns, then the panel step
       if (nupd > 0) {
         const int grid = std::min(nupd, lu_ctas);   // persistent CTAs, one per SM, drawing chunks from the level's counter
-        if (use_pdl) e = launch_pdl_smem(k_chol_lupdate, grid, GPBA_LU_THREADS, lu_smem, stream, C, ut, nupd, (const int*)d_klist.p, d_lu_counter.p + l);
-        else k_chol_lupdate<<<grid, GPBA_LU_THREADS, lu_smem, stream>>>(C, ut, nupd, d_klist.p, d_lu_counter.p + l);
+        // completion counter of the previous level's panel grid and the number of its CTAs (l >= 1 here: level 0 has no sources)
+        int* prev_done = d_lu_counter.p + n_levels + (l - 1);
+        const int prev_count = lvl_pan_begin[l] - lvl_pan_begin[l - 1];
+        if (use_pdl) e = launch_pdl_smem(k_chol_lupdate, grid, GPBA_LU_THREADS, lu_smem, stream, C, ut, nupd, (const unsigned*)d_klist.p, d_lu_counter.p + l, (const int*)prev_done, prev_count, d_fail.p);
+        else k_chol_lupdate<<<grid, GPBA_LU_THREADS, lu_smem, stream>>>(C, ut, nupd, d_klist.p, d_lu_counter.p + l, prev_done, prev_count, d_fail.p);
         ++launches;
         if (e != cudaSuccess) break;
       }
-      if (use_pdl && l > 0) e = launch_pdl(k_chol_panel, npan, GPBA_PANEL_THREADS, stream, C, pt, d_fail.p);
-      else k_chol_panel<<<npan, GPBA_PANEL_THREADS, 0, stream>>>(C, pt, d_fail.p);
+      if (use_pdl && l > 0) e = launch_pdl(k_chol_panel, npan, GPBA_PANEL_THREADS, stream, C, pt, d_fail.p, d_lu_counter.p + n_levels + l);
+      else k_chol_panel<<<npan, GPBA_PANEL_THREADS, 0, stream>>>(C, pt, d_fail.p, d_lu_counter.p + n_levels + l);
       ++launches;
     }
     if (e == cudaSuccess) e = cudaGetLastError();
