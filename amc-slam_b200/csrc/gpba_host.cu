@@ -1065,7 +1065,7 @@ int Solver::build_structure() {
   // --- storage
   CKR(d_ptS[0].alloc((size_t)n_lm * 3)); CKR(d_ptS[1].alloc((size_t)n_lm * 3));
   CKR(d_hll.alloc((size_t)n_lm * 9)); CKR(d_bl.alloc((size_t)n_lm * 3)); CKR(d_ptL.alloc((size_t)n_lm * 9)); CKR(d_xl.alloc((size_t)n_lm * 3));
-  CKR(d_W.alloc(na * 18)); CKR(d_U.alloc(na * 18)); CKR(d_C.alloc((size_t)std::max(n_rp, 1) * GPBA_RP_STRIDE));
+  CKR(d_W.alloc(na * 18)); CKR(d_U.alloc(na * GPBA_U_STRIDE)); CKR(d_C.alloc((size_t)std::max(n_rp, 1) * GPBA_RP_STRIDE));
   CKR(d_hpp.alloc((size_t)n_hpp * 144)); CKR(d_bp.alloc((size_t)n_pose * 12));
   CKR(d_hs.alloc((size_t)n_hs * 144 + (size_t)n_pose * 12 + 8)); CKR(d_x.alloc((size_t)n_pose * 12)); CKR(d_pose_scale.alloc((size_t)n_pose));
   d_bs.release();
@@ -1441,7 +1441,7 @@ int Solver::solve(double lambda) {
     CK(cudaMemsetAsync(d_C.p, 0, sizeof(double) * (size_t)n_rp * GPBA_RP_STRIDE, stream));
     CK(cudaMemsetAsync(d_fail.p + 1, 0, sizeof(int), stream));
     static const int pairs_ctas_per_sm = getenv("GPBA_PAIRS_CTAS") ? atoi(getenv("GPBA_PAIRS_CTAS")) : 16;
-    static const int pairs_batch = getenv("GPBA_PAIRS_BATCH") ? std::max(1, atoi(getenv("GPBA_PAIRS_BATCH"))) : 32;
+    static const int pairs_batch = getenv("GPBA_PAIRS_BATCH") ? std::max(1, atoi(getenv("GPBA_PAIRS_BATCH"))) : 16;   // measured at C4: 8 -> 7.9, 16 -> 7.4, 32 -> 8.4, 64 -> 11.2 ms per optimize
     k_schur_pairs<<<std::min((n_items + 3) / 4, 148 * pairs_ctas_per_sm), 128, 0, stream>>>(n_items, d_item_rp.p, d_item_begin.p, d_item_end.p, d_item_flags.p,
                                                                              d_pairs.p, d_o_lm.p, d_U.p, d_ptL.p, d_C.p, d_fail.p + 1, pairs_batch);
     CK(cudaGetLastError());

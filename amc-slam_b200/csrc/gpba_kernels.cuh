@@ -635,6 +635,12 @@ __global__ void __launch_bounds__(64) k_priors(DevView V, const double* __restri
 // K4a: one warp per landmark: D = Hll + lambda I = L L^T, U_o = W_o L^-T (so that W_o D^-1 W_o'^T = U_o U_o'^T),
 // z = L^-1 b_l.  ptL[9*lm] = {l00,l10,l11,l20,l21,l22, z0,z1,z2}.  Pure streaming: each W row is read and each U row
 // written once.
+// U layout (GPBA_U_STRIDE = 24 doubles per observation): three k-slices of eight, U[k][m] = (U_o)_(m,k) for m < 6,
+// U[k][6] = z_k of the observation's landmark, U[k][7] = 0.  A k-slice is one aligned 64-byte segment, which is exactly what
+// a DMMA operand fetch of K4b wants (8 rows x one k per pair): the 6 x 3 row-major layout of round 1 made every fetch straddle
+// two 128-byte lines and kept K4b on the L1 tag limit (ncu l1tex 98 %, profiles/r02_ncu_streaming.txt).  The z slot hands K4b
+// the g'_r = sum U_o z_l column without a second gather.
+#define GPBA_U_STRIDE 24
 __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, const double* __restrict__ hll,
                                                     const double* __restrict__ bl, const double* __restrict__ W,
                                                     double* __restrict__ U, double* __restrict__ ptL, int* __restrict__ fail) {
@@ -647,25 +653,32 @@ __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, co
     const double l11 = sqrt(d11 - l10 * l10);
     const double l21 = (d21 - l20 * l10) / l11;
     const double l22 = sqrt(d22 - l20 * l20 - l21 * l21);
+    const double z0 = bl[3 * (size_t)lm] / l00;
+    const double z1 = (bl[3 * (size_t)lm + 1] - l10 * z0) / l11;
+    const double z2 = (bl[3 * (size_t)lm + 2] - l20 * z0 - l21 * z1) / l22;
     if (lane == 0) {
       if (!(l00 > 0.0) || !(l11 > 0.0) || !(l22 > 0.0)) atomicExch(fail, 1);
-      const double z0 = bl[3 * (size_t)lm] / l00;
-      const double z1 = (bl[3 * (size_t)lm + 1] - l10 * z0) / l11;
-      const double z2 = (bl[3 * (size_t)lm + 2] - l20 * z0 - l21 * z1) / l22;
       double* o = ptL + 9 * (size_t)lm;
       o[0] = l00; o[1] = l10; o[2] = l11; o[3] = l20; o[4] = l21; o[5] = l22; o[6] = z0; o[7] = z1; o[8] = z2;
     }
     const int64_t ob = V.lm_obs_begin[lm];
-    const int nrow = (int)(V.lm_obs_begin[lm + 1] - ob) * 6;
+    const int nobs = (int)(V.lm_obs_begin[lm + 1] - ob);
     const double* B = W + (size_t)ob * 18;
-    double* Uo = U + (size_t)ob * 18;
+    double* Uo = U + (size_t)ob * GPBA_U_STRIDE;
     const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
-    for (int rr = lane; rr < nrow; rr += 32) {
-      const double b0 = B[rr * 3], b1 = B[rr * 3 + 1], b2 = B[rr * 3 + 2];
-      const double u0 = b0 * i00;
-      const double u1 = (b1 - u0 * l10) * i11;
-      const double u2 = (b2 - u0 * l20 - u1 * l21) * i22;
-      Uo[rr * 3] = u0; Uo[rr * 3 + 1] = u1; Uo[rr * 3 + 2] = u2;
+    // eight slots per observation: rows 0..5 of the block, the z slot and the zero slot
+    for (int rr = lane; rr < nobs * 8; rr += 32) {
+      const int o = rr >> 3, m = rr & 7;
+      double u0, u1, u2;
+      if (m < 6) {
+        const double b0 = B[(o * 6 + m) * 3], b1 = B[(o * 6 + m) * 3 + 1], b2 = B[(o * 6 + m) * 3 + 2];
+        u0 = b0 * i00;
+        u1 = (b1 - u0 * l10) * i11;
+        u2 = (b2 - u0 * l20 - u1 * l21) * i22;
+      } else if (m == 6) { u0 = z0; u1 = z1; u2 = z2; }
+      else { u0 = 0.0; u1 = 0.0; u2 = 0.0; }
+      double* d = Uo + (size_t)o * GPBA_U_STRIDE + m;
+      d[0] = u0; d[8] = u1; d[16] = u2;
     }
   }
 }
@@ -723,16 +736,13 @@ __global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __r
       if (j + 4 + tig < np) pr = pairs[pb + j + 4 + tig];
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
       if (live) {
+        // eight lanes fetch one aligned 64-byte k-slice of a row: slots 0..5 the block's column k, slot 6 z_k (so that
+        // column 6 of a diagonal record pair accumulates g'_r; ignored elsewhere), slot 7 zero
         const unsigned oa = (unsigned)(cur >> 32), ob = (unsigned)cur;
-        if (gid < 6) {
-          const double* pa = U + (size_t)oa * 18 + gid * 3;
-          const double* pbb = U + (size_t)ob * 18 + gid * 3;
-          a0 = pa[0]; a1 = pa[1]; a2 = pa[2];
-          b0 = pbb[0]; b1 = pbb[1]; b2 = pbb[2];
-        } else if (gid == 6 && (fl & 1u)) {
-          const double* z = ptL + (size_t)o_lm[oa] * 9 + 6;
-          b0 = z[0]; b1 = z[1]; b2 = z[2];
-        }
+        const double* pa = U + (size_t)oa * GPBA_U_STRIDE + gid;
+        const double* pbb = U + (size_t)ob * GPBA_U_STRIDE + gid;
+        a0 = pa[0]; a1 = pa[8]; a2 = pa[16];
+        b0 = pbb[0]; b1 = pbb[8]; b2 = pbb[16];
       }
       dmma884(c0, c1, a0, b0);
       dmma884(e0, e1, a1, b1);
@@ -890,8 +900,8 @@ __global__ void __launch_bounds__(128) k_backsub(DevView V, double lambda, const
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     for (int rr = lane; rr < nrow; rr += 32) {
       const double y = Y[(size_t)V.o_rec[ob + rr / 6] * 6 + rr % 6];
-      const double* u = U + (size_t)ob * 18 + rr * 3;
-      a0 = fma(u[0], y, a0); a1 = fma(u[1], y, a1); a2 = fma(u[2], y, a2);
+      const double* u = U + (size_t)(ob + rr / 6) * GPBA_U_STRIDE + rr % 6;
+      a0 = fma(u[0], y, a0); a1 = fma(u[8], y, a1); a2 = fma(u[16], y, a2);
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) {
