@@ -151,6 +151,14 @@ GPBA_D void diag_block_inverse(const double (*S)[GPBA_LD], int b, int lane, doub
 // communication -- a shared-memory + barrier round trip per pivot cost ~380 cycles) and solves its own row of the panel
 // with it.  Meanwhile warp 3 inverts the previous panel's diagonal block for the blocked triangular solves; the other
 // warps stay off the FP64 pipe.  On exit S = L, D8[b] = (b-th 8x8 diagonal block of L)^-1.
+// CTA-wide barrier of the 192 factorizing threads: the whole CTA in k_chol_panel, the six consumer warps (named barrier 2)
+// in the persistent kernel, whose producer warp must not take part
+template <bool NAMED> GPBA_D void tile_sync() {
+  if (NAMED) asm volatile("barrier.sync 2, 192;" ::: "memory");
+  else __syncthreads();
+}
+
+template <bool NAMED = false>
 GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], int* fail, int k = -1, int q_ = -1) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int r = tid;
@@ -172,7 +180,7 @@ GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], int* fail, int k =
         c.x += e0; c.y += e1;
         *reinterpret_cast<double2*>(cp) = c;   // columns >= c0: nobody reads them in this phase (operands are columns < c0)
       }
-      __syncthreads();
+      tile_sync<NAMED>();
     }
     GPBA_TICKP(7);
     if (warp < 2) {
@@ -213,11 +221,11 @@ GPBA_D void potrf48(double (*S)[GPBA_LD], double (*D8)[8][8], int* fail, int k =
     } else if (warp == 3 && pb > 0) {
       diag_block_inverse(S, pb - 1, lane, D8);
     }
-    __syncthreads();
+    tile_sync<NAMED>();
     GPBA_TICKP(8);
   }
   if (warp == 3) diag_block_inverse(S, GPBA_NB / 8 - 1, lane, D8);
-  __syncthreads();
+  tile_sync<NAMED>();
 }
 
 // X = T L^-T in place (T: 48 x 48 in shared memory), blocked by 8: warp w owns the 8 rows of row-tile w, so the
@@ -320,9 +328,9 @@ __global__ void __launch_bounds__(GPBA_PANEL_THREADS) k_chol_panel(CholView C, c
 // accumulator chains) -- and hand it back through the stage's `empty` mbarrier (no CTA-wide barrier in the loop).  A chunk's
 // partial sum leaves with red.global.add.f64 (fire and forget: no read of the target tile on the way; several chunks,
 // possibly on different SMs, may feed one tile).
-#define GPBA_LU_CHUNK 4
+#define GPBA_LU_CHUNK 2
 #define GPBA_LU_THREADS 160   // warps 0-3 consume (DMMA), warp 4 produces (TMA)
-struct LuDesc { double* target; int j; int flags; };   // flags: 1 first product of its chunk, 2 last product, 4 stop, 8 diagonal tile
+struct LuDesc { double* target; int j; int flags; int task; };   // flags: 1 first product of its chunk, 2 last product, 4 stop, 8 diagonal tile
 #define GPBA_LU_LATE 0x80000000u   // klist entry: the source column belongs to the level whose panel step is still in flight
 __global__ void __launch_bounds__(GPBA_LU_THREADS) k_chol_lupdate(CholView C, const int4* __restrict__ tab, int n_chunks,
                                                                   const unsigned* __restrict__ klist, int* __restrict__ counter,
@@ -445,6 +453,300 @@ __global__ void __launch_bounds__(GPBA_LU_THREADS) k_chol_lupdate(CholView C, co
         }
       if (diag && lane < 12) atomicAdd(&C.work[(size_t)d.j * GPBA_NB + rrow], -(s0 + s1));
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_chol_factor: the WHOLE factorization (and forward substitution) as one persistent dataflow kernel.
+//
+// The level-by-level schedule above pays two kernel boundaries per level on the critical path (~25 us per level at C4
+// against ~8 us of dependent work).  Here the CTAs stay resident (as many as fit: the host sizes the grid with the
+// occupancy calculator, so every CTA is resident from the start) and draw TASKS from one list in level order through an
+// atomic counter:
+//   update chunk {j, q, kb, ke}   A_ij -= sum_k L_ik L_jk^T over klist[kb..ke) (and b_j -= L_jk y_k on diagonal tiles)
+//   panel task   {j, q, -1, 0}    potrf(A_jj); q = 0: L_jj^-1 and y_j; q > 0: L_ij = A_ij L_jj^-T
+// Dependencies are per tile COLUMN and travel through two completion counters in global memory:
+//   upd_cnt[j]  += 1 per consumer warp and chunk once its partial sum has been added to column j   (panel tasks of j wait)
+//   pan_cnt[k]  += 1 per finished panel task of column k                                            (products reading k wait)
+// A task only depends on tasks in front of it in the list; tasks are claimed in list order and every claimed task is held by
+// a resident CTA that executes its tasks in order, so the waits cannot deadlock (induction over the task index).  The
+// waits are bounded anyway: a counter that never arrives is reported as a failed factorization instead of a hang.
+// Inside a CTA the producer warp (one thread) claims tasks, performs the waits (ld.acquire.gpu, then fence.proxy.async
+// because the operands are fetched by the async proxy) and streams the operands with cp.async.bulk into a ring of stages;
+// six consumer warps execute the items in order: an update product on 24 x 24 corners (four of the warps), or a
+// panel item with the 192-thread potrf48 / trsm48 above, IN the stage buffers.
+#define GPBA_CF_THREADS 256   // warps 0-5 consume, warp 6 produces, warp 7 publishes finished chunks
+#define GPBA_CF_SIG 4          // ring of finished-chunk messages between the accumulating warps and the publishing thread
+#define GPBA_CF_D8_BYTES (GPBA_NB / 8 * 64 * 8)   // the six inverted 8 x 8 diagonal blocks of a factorized diagonal tile
+#define GPBA_CF_STAGE_BYTES (2 * GPBA_TILE_BYTES + GPBA_NB * 8 + GPBA_CF_D8_BYTES)
+struct ChFactorArgs {
+  const int4* tab; int n_tasks;   // chunk {j | DIAG, target tile, pb, pe}; panel task {j | DIAG, target tile, -1 / -2 / -3, diagonal tile of j}
+                                  //   -1: potrf + solve (every task of the column factorizes the diagonal tile itself: shortest chain)
+                                  //   -2: diagonal task that also PUBLISHES L_jj and its inverted diagonal blocks; -3: solve only, with the
+                                  //       published factor (levels with more panel tasks than CTAs: 5.3 us of potrf per task saved)
+  const int4* prod;               // per product {tile of L_ik, tile of L_jk, k, -}: everything the producer needs in one load
+  const int* upd_need;   // [NT] chunks that target column j
+  const int* pan_need;   // [NT] panel tasks of column k
+  int* task_counter;     // zeroed by a memset node of the graph, like the two arrays below
+  int* upd_cnt;          // [NT]
+  int* pan_cnt;          // [NT]
+  int* diag_cnt;         // [NT] 1 once the published factor of the diagonal tile is in place
+  double* d8;            // [NT][6][8][8] published inverted diagonal blocks
+  int* fail;
+  long long* trace;      // optional [4 n_tasks] ns: claimed, dependencies met (last wait), first item consumed, done (tools only)
+};
+#define GPBA_CF_DIAG 0x40000000
+GPBA_D long long cf_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+GPBA_D void cf_wait_counter(const int* cnt, int need, int* fail) {
+  unsigned spins = 0;
+  int seen;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+  } while (seen < need && ++spins < (1u << 26));
+  if (seen < need) atomicExch(fail, 1);
+  asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies (async proxy) read what the counted tasks wrote
+}
+#define GPBA_CF_STAGES 3
+__global__ void __launch_bounds__(GPBA_CF_THREADS, 1) k_chol_factor(CholView C, ChFactorArgs F) {
+  extern __shared__ __align__(128) unsigned char cf_smem[];
+  __shared__ __align__(8) unsigned long long full[GPBA_CF_STAGES], empty[GPBA_CF_STAGES];
+  __shared__ LuDesc desc[GPBA_CF_STAGES];
+  __shared__ double D8[GPBA_NB / 8][8][8];
+  __shared__ __align__(8) unsigned long long sig_full[GPBA_CF_SIG], sig_empty[GPBA_CF_SIG];
+  __shared__ int sig_j[GPBA_CF_SIG], sig_task[GPBA_CF_SIG];
+  typedef double (*TileP)[GPBA_LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto stage_a = [&](int s) { return reinterpret_cast<TileP>(cf_smem + (size_t)s * GPBA_CF_STAGE_BYTES); };
+  auto stage_b = [&](int s) { return reinterpret_cast<TileP>(cf_smem + (size_t)s * GPBA_CF_STAGE_BYTES + GPBA_TILE_BYTES); };
+  auto stage_y = [&](int s) { return reinterpret_cast<double*>(cf_smem + (size_t)s * GPBA_CF_STAGE_BYTES + 2 * GPBA_TILE_BYTES); };
+  auto stage_d8 = [&](int s) { return reinterpret_cast<double(*)[8][8]>(cf_smem + (size_t)s * GPBA_CF_STAGE_BYTES + 2 * GPBA_TILE_BYTES + GPBA_NB * 8); };
+  // columns this CTA has already seen complete (completion is final, so a positive answer can be cached): one bit per column
+  unsigned* ready_bits = reinterpret_cast<unsigned*>(cf_smem + (size_t)GPBA_CF_STAGES * GPBA_CF_STAGE_BYTES);
+  for (int j = tid; j < (C.NT + 31) / 32; j += blockDim.x) ready_bits[j] = 0u;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GPBA_CF_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 6); }
+#pragma unroll
+    for (int s = 0; s < GPBA_CF_SIG; ++s) { mbar_init(&sig_full[s], 4); mbar_init(&sig_empty[s], 1); }
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (warp == 7) {
+    // ---------------------------------------------------------------- publisher (one thread)
+    // A finished chunk ends with 36 reductions per thread into the target tile.  Making them visible (a gpu-scope fence that
+    // waits for all of them) and counting the chunk took 2 us per chunk on the accumulating warps; they now only announce
+    // the chunk on a shared-memory barrier (release at CTA scope) and go on, and this thread observes the barrier (acquire),
+    // fences at gpu scope -- cumulative: it covers the reductions it has observed through the barrier, the pattern of a
+    // grid-wide barrier (__syncthreads, then ONE thread fences and signals) -- and counts.
+    if (lane != 0) return;
+    for (int m = 0;; ++m) {
+      const int q = m % GPBA_CF_SIG;
+      mbar_wait(&sig_full[q], (unsigned)(m / GPBA_CF_SIG) & 1u);
+      const int j = sig_j[q], task = sig_task[q];
+      mbar_arrive(&sig_empty[q]);
+      if (j < 0) return;
+      __threadfence();
+      atomicAdd(F.upd_cnt + j, 1);
+      if (F.trace) F.trace[8 * (size_t)task + 3] = cf_now();
+    }
+  }
+  if (warp == 6) {
+    // ---------------------------------------------------------------- producer (one thread)
+    // Everything it needs per item comes from one record (no dependent index chains), and the NEXT task is claimed while
+    // the current one is being streamed: the atomic's round trip and the record loads are off the consumers' path.
+    if (lane != 0) return;
+    int pos = 0, begin = 0, end = 0, pj = 0, task = 0;
+    double* target = nullptr;
+    bool diag = false;
+    int next_c = atomicAdd(F.task_counter, 1);
+    int4 next_e = make_int4(0, 0, 0, 0);
+    bool next_loaded = false;
+    int4 rec = make_int4(0, 0, 0, 0);   // record of product `pos` (prefetched one item ahead inside a chunk)
+    for (int n = 0;; ++n) {
+      const int s = n % GPBA_CF_STAGES;
+      {
+        const long long tw = F.trace ? cf_now() : 0;
+        if (n >= GPBA_CF_STAGES) mbar_wait(&empty[s], (unsigned)(n / GPBA_CF_STAGES - 1) & 1u);
+        if (F.trace && pos != end) F.trace[8 * (size_t)task + 6] += cf_now() - tw;
+      }
+      if (pos == end) {
+        if (next_c >= F.n_tasks) {
+          desc[s].target = nullptr; desc[s].j = -1; desc[s].flags = 4;
+          mbar_arrive(&full[s]);
+          return;
+        }
+        const int4 e = next_loaded ? next_e : F.tab[next_c];
+        task = next_c;
+        next_c = atomicAdd(F.task_counter, 1);   // claim ahead: the result is not needed before the next item
+        next_loaded = false;
+        if (F.trace) F.trace[8 * (size_t)task] = cf_now();
+        pj = e.x & ~GPBA_CF_DIAG; diag = (e.x & GPBA_CF_DIAG) != 0;
+        target = C.tiles + (size_t)e.y * GPBA_TILE;
+        if (e.z < 0) {
+          // panel item: the column has received all its updates (solve-only tasks: and its diagonal tile is factorized)
+          const bool solve_only = e.z == -3;
+          if (solve_only) cf_wait_counter(F.diag_cnt + pj, 1, F.fail);
+          else cf_wait_counter(F.upd_cnt + pj, F.upd_need[pj], F.fail);
+          if (F.trace) F.trace[8 * (size_t)task + 1] = cf_now();
+          desc[s].target = target; desc[s].j = pj; desc[s].task = task;
+          desc[s].flags = 16 | (diag ? 8 : 0) | (e.z == -2 ? 32 : 0) | (solve_only ? 64 : 0);
+          mbar_expect_tx(&full[s], diag ? GPBA_TILE_BYTES + GPBA_NB * 8u : 2u * GPBA_TILE_BYTES + (solve_only ? (unsigned)GPBA_CF_D8_BYTES : 0u));
+          bulk_g2s(stage_a(s), C.tiles + (size_t)e.w * GPBA_TILE, GPBA_TILE_BYTES, &full[s]);
+          if (!diag) bulk_g2s(stage_b(s), target, GPBA_TILE_BYTES, &full[s]);
+          else bulk_g2s(stage_y(s), C.work + (size_t)pj * GPBA_NB, GPBA_NB * 8, &full[s]);
+          if (solve_only) bulk_g2s(stage_d8(s), F.d8 + (size_t)pj * (GPBA_CF_D8_BYTES / 8), GPBA_CF_D8_BYTES, &full[s]);
+          continue;
+        }
+        begin = pos = e.z; end = e.w;
+        rec = F.prod[pos];
+      }
+      const int k = rec.z;
+      if (!(ready_bits[k >> 5] >> (k & 31) & 1u)) {
+        cf_wait_counter(F.pan_cnt + k, F.pan_need[k], F.fail);   // the source column is final (its y_k too)
+        ready_bits[k >> 5] |= 1u << (k & 31);
+      }
+      if (F.trace) F.trace[8 * (size_t)task + 1] = cf_now();
+      desc[s].target = target; desc[s].j = pj; desc[s].task = task;
+      desc[s].flags = (pos == begin ? 1 : 0) | (pos + 1 == end ? 2 : 0) | (diag ? 8 : 0);
+      mbar_expect_tx(&full[s], diag ? GPBA_TILE_BYTES + GPBA_NB * 8u : 2u * GPBA_TILE_BYTES);
+      bulk_g2s(stage_a(s), C.tiles + (size_t)rec.x * GPBA_TILE, GPBA_TILE_BYTES, &full[s]);
+      if (!diag) bulk_g2s(stage_b(s), C.tiles + (size_t)rec.y * GPBA_TILE, GPBA_TILE_BYTES, &full[s]);
+      else bulk_g2s(stage_y(s), C.work + (size_t)k * GPBA_NB, GPBA_NB * 8, &full[s]);
+      ++pos;
+      if (pos < end) rec = F.prod[pos];   // in flight while the consumers work on this stage
+      else if (next_c < F.n_tasks) { next_e = F.tab[next_c]; next_loaded = true; }   // the claim issued at the start of this chunk has returned
+    }
+  }
+  // ------------------------------------------------------------------ consumers (warps 0-5)
+  const int gid = lane >> 2, tig = lane & 3;
+  const int m0 = 3 * ((warp & 3) >> 1), n0 = 3 * (warp & 1);
+  int cn = 0;   // finished chunks of this CTA (message ring position)
+  auto announce = [&](int j, int task) {   // warps 0-3, after their reductions have been issued
+    const int q = cn % GPBA_CF_SIG;
+    if (cn >= GPBA_CF_SIG) mbar_wait(&sig_empty[q], (unsigned)(cn / GPBA_CF_SIG - 1) & 1u);
+    if (tid == 0) { sig_j[q] = j; sig_task[q] = task; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sig_full[q]);
+    ++cn;
+  };
+  for (int n = 0;;) {
+    int s = n % GPBA_CF_STAGES;
+    mbar_wait(&full[s], (unsigned)(n / GPBA_CF_STAGES) & 1u);
+    LuDesc d = desc[s];
+    if (d.flags & 4) { if (warp < 4) announce(-1, 0); break; }
+    const bool diag = (d.flags & 8) != 0;
+    if (F.trace && tid == 0) F.trace[8 * (size_t)d.task + 2] = cf_now();
+    if (d.flags & 16) {
+      // ---- panel item: S = A_jj, T = A_ij (or the identity for the diagonal task), both in the stage
+      const TileP S = stage_a(s), T = stage_b(s);
+      double* Sy = stage_y(s);
+      if (d.flags & 64) {
+        trsm48(T, S, stage_d8(s));   // the column's diagonal task has published L_jj and its inverted diagonal blocks
+      } else {
+        if (diag)
+          for (int j = tid; j < GPBA_NB * GPBA_NB; j += 192) T[j / GPBA_NB][j % GPBA_NB] = (j / GPBA_NB == j % GPBA_NB) ? 1.0 : 0.0;
+        tile_sync<true>();
+        potrf48<true>(S, D8, F.fail);
+        if (F.trace && tid == 0) F.trace[8 * (size_t)d.task + 4] = cf_now();
+        if (d.flags & 32) {
+          // publish the factor first: the solve-only tasks of the column are waiting for it
+          double* A = d.target;   // the diagonal tile itself
+          for (int j = tid; j < GPBA_TILE / 2; j += 192) reinterpret_cast<double2*>(A)[j] = reinterpret_cast<const double2*>(&S[0][0])[j];
+          double* G = F.d8 + (size_t)d.j * (GPBA_CF_D8_BYTES / 8);
+          for (int j = tid; j < GPBA_CF_D8_BYTES / 8; j += 192) G[j] = (&D8[0][0][0])[j];
+          __threadfence();
+          tile_sync<true>();
+          if (tid == 0) { __threadfence(); atomicAdd(F.diag_cnt + d.j, 1); }
+        }
+        trsm48(T, S, D8);
+      }
+      tile_sync<true>();
+      if (F.trace && tid == 0) F.trace[8 * (size_t)d.task + 5] = cf_now();
+      if (diag) {
+        double* D = C.dinv + (size_t)d.j * GPBA_NB * GPBA_NB;
+        for (int j = tid; j < GPBA_NB * GPBA_NB; j += 192) D[j] = T[j % GPBA_NB][j / GPBA_NB];
+        if (tid < GPBA_NB) {
+          double y0 = 0.0, y1 = 0.0;
+#pragma unroll 4
+          for (int c = 0; c < GPBA_NB; c += 2) { y0 = fma(T[c][tid], Sy[c], y0); y1 = fma(T[c + 1][tid], Sy[c + 1], y1); }
+          C.work[d.j * GPBA_NB + tid] = y0 + y1;
+        }
+      } else {
+        double* A = d.target;
+        for (int j = tid; j < GPBA_NB * GPBA_NB / 2; j += 192) {
+          const int r = j / (GPBA_NB / 2), c = 2 * (j % (GPBA_NB / 2));
+          *reinterpret_cast<double2*>(A + r * GPBA_LD + c) = *reinterpret_cast<double2*>(&T[r][c]);
+        }
+      }
+      __threadfence();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes to the stage before the next bulk copy into it
+      tile_sync<true>();
+      if (tid == 0) { __threadfence(); atomicAdd(F.pan_cnt + d.j, 1); if (F.trace) F.trace[8 * (size_t)d.task + 3] = cf_now(); }
+      if (lane == 0) mbar_arrive(&empty[s]);
+      ++n;
+      continue;
+    }
+    // ---- update chunk: its products arrive back to back (the accumulators live only here, not across panel items).
+    // Warps 0-3 -- one per SM sub-partition, so the four FP64 tensor pipes carry equal shares -- own a 24 x 24 corner each
+    // (3 x 3 DMMA tiles, 9 independent accumulator chains); warps 4-5 only take part in panel items and hand the stage back.
+    if (warp >= 4) {
+      for (;;) {
+        if (lane == 0) mbar_arrive(&empty[s]);
+        ++n;
+        if (d.flags & 2) break;
+        s = n % GPBA_CF_STAGES;
+        mbar_wait(&full[s], (unsigned)(n / GPBA_CF_STAGES) & 1u);
+        d = desc[s];
+      }
+      continue;
+    }
+    double2 acc[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) acc[a][b] = make_double2(0.0, 0.0);
+    double s0 = 0.0, s1 = 0.0;   // rhs rows (diagonal tiles): warp w owns rows 12 w .. 12 w + 11, lanes 0..11
+    const int rrow = 12 * warp + lane;
+    long long twait = 0;
+    for (;;) {
+      const TileP La = stage_a(s);
+      const TileP Lb = diag ? La : stage_b(s);
+#pragma unroll 2
+      for (int k0 = 0; k0 < GPBA_NB; k0 += 4) {
+        double af[3], bf[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { af[a] = La[8 * (m0 + a) + gid][k0 + tig]; bf[a] = Lb[8 * (n0 + a) + gid][k0 + tig]; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) dmma884(acc[a][b].x, acc[a][b].y, af[a], bf[b]);
+      }
+      if (diag && lane < 12) {
+        const double* yk = stage_y(s);
+#pragma unroll 4
+        for (int c = 0; c < GPBA_NB; c += 2) { s0 = fma(La[rrow][c], yk[c], s0); s1 = fma(La[rrow][c + 1], yk[c + 1], s1); }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      ++n;
+      if (d.flags & 2) break;
+      s = n % GPBA_CF_STAGES;
+      const long long tw = (F.trace && tid == 0) ? cf_now() : 0;
+      mbar_wait(&full[s], (unsigned)(n / GPBA_CF_STAGES) & 1u);
+      if (F.trace && tid == 0) twait += cf_now() - tw;
+      d = desc[s];
+    }
+    if (F.trace && tid == 0) { F.trace[8 * (size_t)d.task + 4] = twait; F.trace[8 * (size_t)d.task + 5] = cf_now(); }
+    double* Tc = d.target;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        double* out = Tc + (8 * (m0 + a) + gid) * GPBA_LD + 8 * (n0 + b) + 2 * tig;
+        atomicAdd(out, -acc[a][b].x); atomicAdd(out + 1, -acc[a][b].y);
+      }
+    if (diag && lane < 12) atomicAdd(&C.work[(size_t)d.j * GPBA_NB + rrow], -(s0 + s1));
+    announce(d.j, d.task);   // the publisher makes the partial sum visible and counts the chunk
   }
 }
 

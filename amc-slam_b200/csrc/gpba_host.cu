@@ -287,6 +287,13 @@ struct Solver {
   std::vector<int> lvl_pan_begin, lvl_upd_begin, lvl_back_begin, lvl_ncols;
   DBuf<int2> d_pan_tab, d_back_tab;
   DBuf<int4> d_upd_tab;
+  DBuf<int4> d_cf_prod;              // persistent factorization: one record per tile product
+  DBuf<int4> d_cf_tab;               // persistent factorization: all tasks in level order (update chunks, then panel tasks, per level)
+  DBuf<int> d_cf_need;               // [2 NT]: upd_need | pan_need
+  DBuf<int> d_cf_cnt;                // [2 NT + 1]: upd_cnt | pan_cnt | task counter (zeroed by the graph)
+  int cf_tasks = 0;
+  DBuf<double> d_cf_d8;              // [NT][6][8][8] inverted diagonal blocks published by the diagonal tasks of wide levels
+  DBuf<long long> d_cf_trace;        // GPBA_CF_TRACE=<file>: per-task timestamps of the last factorization (tools/cf_trace.py)
   DBuf<int> d_tile_lm, d_tile_rlo, d_tile_rcnt;   // landmark-aligned observation tiles + their record windows (K1 / K2a)
   int n_tiles = 0;
   DBuf<unsigned> d_klist;
@@ -779,7 +786,7 @@ int Solver::build_structure() {
   // --- device: observation pairs grouped by record pair
   std::vector<unsigned long long> rp_key;   // unique record pairs of the compute list, ascending
   const unsigned long long nrec2 = (unsigned long long)n_rec * (unsigned long long)n_rec;
-  const int LM_CHUNK = 8192;                // landmarks per chunk: ~12 MB of U rows at 10 observations per landmark
+  static const int LM_CHUNK = getenv("GPBA_LM_CHUNK") ? std::max(256, atoi(getenv("GPBA_LM_CHUNK"))) : 16384;   // landmarks per chunk: ~31 MB of U rows at 10 observations per landmark (measured at C4: 2048 -> 8.2, 4096 -> 7.7, 8192 -> 7.4, 16384 -> 7.3 ms of K4b per optimize)
   // One pass = emit + sort + run-length encode.  with_items: runs of (chunk, record pair) become the work items of K4b
   // and the sorted observation pairs are kept; otherwise only the unique record pairs are wanted (pattern).
   auto pair_pass = [&](int nl, const int64_t* d_lob, const int64_t* d_lpb, int64_t np, const int* d_rec_sorted, bool with_items,
@@ -1122,9 +1129,13 @@ int Solver::build_cholesky_structure() {
   lvl_ncols.assign(n_levels, 0);
   std::vector<unsigned> late_scratch;
   std::vector<int4> early_chunks, late_chunks;
+  std::vector<int4> cf_tab;
+  std::vector<int> cf_need(2 * (size_t)NT, 0);
   for (int l = 0; l < n_levels; ++l) {
     lvl_ncols[l] = (int)lvl_cols[l].size();
     early_chunks.clear(); late_chunks.clear();
+    struct TileList { int k, q, kb, cnt, n_late; };
+    std::vector<TileList> lists;
     for (int k : lvl_cols[l]) {
       const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
       for (int q = 0; q <= nr; ++q) pan_tab.push_back(make_int2(k, q));
@@ -1147,21 +1158,64 @@ int Solver::build_cholesky_structure() {
         klist.insert(klist.end(), late.begin(), late.end());
         const int cnt = (int)klist.size() - kb;
         if (cnt == 0) continue;
-        static const int lu_chunk = getenv("GPBA_LU_CHUNK") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK"))) : GPBA_LU_CHUNK;
-        const int nch = (cnt + lu_chunk - 1) / lu_chunk;
-        for (int c = 0; c < nch; ++c) {
-          const int cb = kb + (int)((int64_t)cnt * c / nch), ce = kb + (int)((int64_t)cnt * (c + 1) / nch);
-          const bool is_late = ce > kb + cnt - (int)n_late;   // the chunk reaches into the late tail
-          (is_late ? late_chunks : early_chunks).push_back(make_int4(k, q, cb, ce));
-        }
+        lists.push_back({k, q, kb, cnt, (int)n_late});
       }
       const int nrow = chol_row_begin[k + 1] - chol_row_begin[k];
       for (int q = 0; q <= nrow; ++q) back_tab.push_back(make_int2(k, q));
       if (nr >= 65536) { g_err = "tile column with more than 65535 rows"; return GPBA_ERR_INVALID; }
     }
+    // Chunk size: at least GPBA_LU_CHUNK products (a chunk ends with 12 reductions per thread, a fence and a counter
+    // update), more where the level has enough products to keep every SM busy with fewer, longer chunks.
+    {
+      static const int lu_chunk = getenv("GPBA_LU_CHUNK") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK"))) : GPBA_LU_CHUNK;
+      static const int lu_chunk_max = getenv("GPBA_LU_CHUNK_MAX") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK_MAX"))) : 12;
+      int64_t total = 0;
+      for (const TileList& t : lists) total += t.cnt;
+      const int chunk = (int)std::min<int64_t>(std::max<int64_t>(lu_chunk, total / (2 * 148)), std::max(lu_chunk, lu_chunk_max));
+      // products whose source column belongs to the previous level sit on the critical path (panel -> product -> next
+      // panel): they get short chunks of their own so that several SMs work on one tile's late tail at once
+      static const int late_chunk = getenv("GPBA_LU_LATE_CHUNK") ? std::max(0, atoi(getenv("GPBA_LU_LATE_CHUNK"))) : 1;
+      auto cut = [&](const TileList& t, int b, int cnt, int size, bool late) {
+        const int nch = (cnt + size - 1) / size;
+        for (int c = 0; c < nch; ++c)
+          (late ? late_chunks : early_chunks).push_back(make_int4(t.k, t.q, b + (int)((int64_t)cnt * c / nch), b + (int)((int64_t)cnt * (c + 1) / nch)));
+      };
+      for (const TileList& t : lists) {
+        if (late_chunk > 0) {
+          if (t.cnt > t.n_late) cut(t, t.kb, t.cnt - t.n_late, chunk, false);
+          if (t.n_late > 0) cut(t, t.kb + t.cnt - t.n_late, t.n_late, late_chunk, true);
+          continue;
+        }
+        const int nch = (t.cnt + chunk - 1) / chunk;
+        for (int c = 0; c < nch; ++c) {
+          const int cb = t.kb + (int)((int64_t)t.cnt * c / nch), ce = t.kb + (int)((int64_t)t.cnt * (c + 1) / nch);
+          const bool is_late = ce > t.kb + t.cnt - t.n_late;   // the chunk reaches into the late tail
+          (is_late ? late_chunks : early_chunks).push_back(make_int4(t.k, t.q, cb, ce));
+        }
+      }
+    }
     // chunks that only need finished levels are handed out first: they overlap with the previous level's panel step
     upd_tab.insert(upd_tab.end(), early_chunks.begin(), early_chunks.end());
     upd_tab.insert(upd_tab.end(), late_chunks.begin(), late_chunks.end());
+    // the same work as one task list for the persistent kernel: this level's chunks, then its panel tasks
+    auto tile_of = [&](int i, int j) { return (int)(off[(size_t)i * NT + j] / GPBA_TILE); };
+    auto row_of = [&](int k, int q) { return q == 0 ? k : col_rows[chol_col_begin[k] + q - 1]; };
+    for (const std::vector<int4>* v : {&early_chunks, &late_chunks})
+      for (const int4& c : *v) {
+        cf_tab.push_back(make_int4(c.x | (c.y == 0 ? GPBA_CF_DIAG : 0), tile_of(row_of(c.x, c.y), c.x), c.z, c.w));
+        cf_need[c.x] += 1;
+      }
+    // Wide levels (more panel tasks than resident CTAs can take at once) are throughput bound: one task per column
+    // factorizes the diagonal tile and publishes it, the others only solve.  Narrow levels are latency bound: every task
+    // factorizes the diagonal tile itself, which saves a publish / wait / reload hop on the critical path.
+    static const int split_min = getenv("GPBA_CF_SPLIT_MIN") ? atoi(getenv("GPBA_CF_SPLIT_MIN")) : 120;
+    const bool split = lvl_pan_begin.size() > 0 && ((int)pan_tab.size() - lvl_pan_begin[l]) >= split_min;
+    for (int pass = 0; pass < 2; ++pass)   // diagonal tasks first
+      for (int k : lvl_cols[l]) {
+        const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
+        if (pass == 0) { cf_tab.push_back(make_int4(k | GPBA_CF_DIAG, tile_of(k, k), split && nr > 0 ? -2 : -1, tile_of(k, k))); cf_need[(size_t)NT + k] = nr + 1; }
+        else for (int q = 1; q <= nr; ++q) cf_tab.push_back(make_int4(k, tile_of(row_of(k, q), k), split ? -3 : -1, tile_of(k, k)));
+      }
     lvl_pan_begin[l + 1] = (int)pan_tab.size(); lvl_upd_begin[l + 1] = (int)upd_tab.size(); lvl_back_begin[l + 1] = (int)back_tab.size();
   }
   chol_products = (int64_t)klist.size(); chol_update_ctas = (int64_t)upd_tab.size();
@@ -1170,6 +1224,21 @@ int Solver::build_cholesky_structure() {
   CKR(d_pan_tab.upload(pan_tab, stream)); CKR(d_upd_tab.upload(upd_tab, stream)); CKR(d_back_tab.upload(back_tab, stream));
   CKR(d_klist.upload(klist, stream));
   CKR(d_lu_counter.alloc(2 * (size_t)std::max(n_levels, 1)));
+  cf_tasks = (int)cf_tab.size();
+  {
+    // one record per product: the tiles of L_ik and L_jk and the source column k
+    std::vector<int4> prod(klist.size(), make_int4(0, 0, 0, 0));
+    for (const int4& c : upd_tab) {
+      if (c.z >= c.w) continue;
+      const int j = c.x, i = c.y == 0 ? j : col_rows[chol_col_begin[j] + c.y - 1];
+      for (int p = c.z; p < c.w; ++p) {
+        const int k = (int)(klist[p] & ~GPBA_LU_LATE);
+        prod[p] = make_int4((int)(off[(size_t)i * NT + k] / GPBA_TILE), (int)(off[(size_t)j * NT + k] / GPBA_TILE), k, 0);
+      }
+    }
+    CKR(d_cf_prod.upload(prod, stream));
+  }
+  CKR(d_cf_tab.upload(cf_tab, stream)); CKR(d_cf_need.upload(cf_need, stream)); CKR(d_cf_cnt.alloc(3 * (size_t)NT + 1)); CKR(d_cf_d8.alloc((size_t)NT * (GPBA_CF_D8_BYTES / 8)));
   if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns, %zu panel CTAs, %zu update CTAs for %zu tile products\n", chol_parts, n_levels, NT, pan_tab.size(), upd_tab.size(), klist.size());
   CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
   if (chol_graph) { cudaGraphExecDestroy(chol_graph); chol_graph = nullptr; }
@@ -1229,11 +1298,46 @@ int Solver::capture_cholesky_graph() {
     k_chol_load<<<(int)std::min((work + 255) / 256, (int64_t)148 * 8), 256, 0, stream>>>(C, n_hs, d_hs_row.p, d_hs_col.p, d_hs.p, bs);
     ++launches;
     const int n_levels = (int)lvl_ncols.size();
+    static const bool per_level = getenv("GPBA_CHOL_LEVELS") != nullptr;   // the level-by-level launch sequence (A/B comparisons)
+    if (!per_level) {
+      // one persistent dataflow kernel: as many CTAs as are resident at once (the waits inside rely on that)
+      void (*kern)(CholView, ChFactorArgs) = k_chol_factor;
+      const size_t cf_smem = (size_t)GPBA_CF_STAGES * GPBA_CF_STAGE_BYTES + 4 * (((size_t)NT + 31) / 32);
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cf_smem);
+      int per_sm = 0, sms = 148;
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GPBA_CF_THREADS, cf_smem);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
+      if (e == cudaSuccess) e = cudaMemsetAsync(d_cf_cnt.p, 0, sizeof(int) * (3 * (size_t)NT + 1), stream);
+      if (e == cudaSuccess) {
+        static const int cap = getenv("GPBA_CF_CTAS_PER_SM") ? atoi(getenv("GPBA_CF_CTAS_PER_SM")) : 8;
+        const int grid = std::max(1, std::min(std::min(per_sm, cap) * sms, cf_tasks));
+        if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: persistent factorization, %d tasks, %d CTAs (%d per SM), %zu B smem\n", cf_tasks, grid, per_sm, cf_smem);
+        ChFactorArgs F;
+        F.tab = d_cf_tab.p; F.n_tasks = cf_tasks; F.prod = d_cf_prod.p;
+        F.upd_need = d_cf_need.p; F.pan_need = d_cf_need.p + NT;
+        F.upd_cnt = d_cf_cnt.p; F.pan_cnt = d_cf_cnt.p + NT; F.diag_cnt = d_cf_cnt.p + 2 * (size_t)NT; F.task_counter = d_cf_cnt.p + 3 * (size_t)NT;
+        F.d8 = d_cf_d8.p;
+        F.fail = d_fail.p;
+        F.trace = nullptr;
+        if (getenv("GPBA_CF_TRACE")) { if (d_cf_trace.alloc(8 * (size_t)cf_tasks) == GPBA_OK) { F.trace = d_cf_trace.p; cudaMemsetAsync(d_cf_trace.p, 0, 64 * (size_t)cf_tasks, stream); } }
+        // cooperative launch: the runtime refuses a grid that is not resident in full instead of letting the waits spin
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GPBA_CF_THREADS); cfg.dynamicSmemBytes = cf_smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, C, F);
+        ++launches;
+        if (e == cudaSuccess) e = cudaGetLastError();
+      }
+    }
     const size_t lu_smem = (size_t)GPBA_LU_STAGES * (2 * GPBA_TILE_BYTES + GPBA_NB * 8);
     e = cudaFuncSetAttribute(k_chol_lupdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_smem);
     int lu_ctas = 148;
     cudaDeviceGetAttribute(&lu_ctas, cudaDevAttrMultiProcessorCount, device);
-    for (int l = 0; l < n_levels && e == cudaSuccess; ++l) {
+    for (int l = 0; per_level && l < n_levels && e == cudaSuccess; ++l) {
       const int npan = lvl_pan_begin[l + 1] - lvl_pan_begin[l], nupd = lvl_upd_begin[l + 1] - lvl_upd_begin[l];
       const int2* pt = d_pan_tab.p + lvl_pan_begin[l];
       const int4* ut = d_upd_tab.p + lvl_upd_begin[l];
@@ -1465,6 +1569,17 @@ int Solver::solve(double lambda) {
     if (!chol_graph) CKR(capture_cholesky_graph());
     CK(cudaGraphLaunch(chol_graph, stream));
     t1(6, chol_graph_launches);
+    if (d_cf_trace.p && getenv("GPBA_CF_TRACE")) {   // tools only: dump the task timeline of this factorization
+      std::vector<long long> tr(8 * (size_t)cf_tasks);
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaMemcpy(tr.data(), d_cf_trace.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      std::vector<int4> tab((size_t)cf_tasks);
+      CK(cudaMemcpy(tab.data(), d_cf_tab.p, tab.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(getenv("GPBA_CF_TRACE"), "wb")) {
+        fwrite(&cf_tasks, sizeof(int), 1, f); fwrite(tab.data(), sizeof(int4), tab.size(), f); fwrite(tr.data(), sizeof(long long), tr.size(), f);
+        fclose(f);
+      }
+    }
     t0();
     CK(cudaGraphLaunch(chol_back_graph, stream));
     t1(7, chol_back_launches);
