@@ -2223,7 +2223,7 @@ int gpba_outlier_flags(gpba_handle* h, const gpba_thresholds* th, uint8_t* flags
   DBuf<uint8_t> d_flags;
   CKR(d_flags.alloc((size_t)s.n_obs));
   const int g = (int)std::min<int64_t>((s.n_obs + 255) / 256 + 1, 148 * 8);
-  k_flags<<<g, 256, 0, s.stream>>>(s.Vb(s.cur), s.n_obs, s.d_chi2.p, s.stereo ? s.d_all_ur.p : nullptr, s.d_all_rec.p, s.d_all_flags.p, nullptr,
+  k_flags<<<g, 256, 0, s.stream>>>(s.Vb(s.cur), s.n_obs, s.d_chi2.p, s.stereo ? s.d_all_ur.p : nullptr, s.d_all_rec.p, s.d_all_flags.p,
                                    s.d_all_pt.p, s.d_pt_full.p, s.d_pose[s.cur].p, th->chi2_mono, th->chi2_mono_close, th->chi2_stereo, d_flags.p);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(flags, d_flags.p, (size_t)s.n_obs, cudaMemcpyDeviceToHost, s.stream));

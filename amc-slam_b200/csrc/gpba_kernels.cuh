@@ -1027,10 +1027,8 @@ __global__ void k_ext_prior(DevView V, const double* __restrict__ ext, int mode,
 // stereo edges: chi2 only (Optimizer.cc:1283-1296).  Runs over ALL observations in original order.
 __global__ void k_flags(DevView V, int64_t n_obs, const double* __restrict__ chi2, const double* __restrict__ ur,
                         const int* __restrict__ obs_rec, const uint8_t* __restrict__ obs_flags,
-                        const double* __restrict__ obs_X /* current landmark xyz per observation's point, gathered by host index */,
                         const int* __restrict__ obs_pt, const double* __restrict__ pt_all, const double* __restrict__ pose,
                         double th_mono, double th_close, double th_stereo, uint8_t* __restrict__ flags) {
-  (void)obs_X;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
     const double c2 = chi2[i];
     bool out;

@@ -91,3 +91,46 @@ def reproj(T1, T2, v1, v2, t1, t2, t, Tbc, intr, Xw, gp=True):
     Twb = query_pose(T1, T2, v1, v2, t1, t2, t) if gp else T2
     Xc = np.linalg.inv(Twb @ Tbc) @ np.append(Xw, 1.0)
     return np.array([intr[0] * Xc[0] / Xc[2] + intr[2], intr[1] * Xc[1] / Xc[2] + intr[3]]), Xc[2]
+
+
+def gp_edge_jacobians(T1, T2, v1, v2, t1, t2, t, Tbc, intr, bf, Xw, stereo):
+    """Analytic Jacobians of the GP reprojection edges, composed from THIS module's pieces (scipy logm/expm, the power
+    series of the SE(3) Jacobians, the closed-form GP weights) after the formulas of EdgeMonoGP / EdgeStereoGP::linearizeOplus
+    (src/G2oTypes.cc:262-311 mono, :329-396 stereo; QueryPose with At1 / Pt1: src/GaussianProcess.cc:23-42).  Returns
+    (J_kf1 [dim x 12], J_kf2 [dim x 12], J_point [dim x 3]) with the reference's block order [pose(6) | velocity(6)].
+    The pose blocks carry the reference's first-order term -0.5 ad(v2), so they are NOT the derivative
+    of the error; this function pins the restated FORMULAS, a numeric derivative cannot."""
+    v1 = np.asarray(v1, float); v2 = np.asarray(v2, float)
+    l11, l12, p11, p12 = gp_weights(t1, t2, t)
+    I6 = np.eye(6); Z6 = np.zeros((6, 6))
+    At1 = np.hstack([l11 * I6, l12 * I6]); Pt1 = np.hstack([p11 * I6, p12 * I6])
+    xi12 = log_se3(np.linalg.inv(T1) @ T2)
+    Jr_inv_xi12 = np.linalg.inv(Jr_series(xi12))
+    dxi = At1 @ np.concatenate([np.zeros(6), v1]) + Pt1 @ np.concatenate([xi12, Jr_inv_xi12 @ v2])
+    dT = exp_se3(dxi)
+    Twb = T1 @ dT
+    Tcb = np.linalg.inv(Tbc)
+    Rcb = Tcb[:3, :3]
+    Rbw = Twb[:3, :3].T
+    Xb = (np.linalg.inv(Twb) @ np.append(Xw, 1.0))[:3]
+    Xc = Rcb @ Xb + Tcb[:3, 3]
+    x, y, z = Xc
+    fx, fy = intr[0], intr[1]
+    pj = np.array([[fx / z, 0, -fx * x / (z * z)], [0, fy / z, -fy * y / (z * z)]])
+    if stereo:
+        pj = np.vstack([pj, pj[0] + np.array([0, 0, bf / (z * z)])])
+    SE3deriv = np.hstack([-Rcb, Rcb @ hat3(Xb)])
+    J1 = -pj @ SE3deriv
+    Ad_dT = Adj(exp_se3(-dxi))
+    Jr_dxi = Jr_series(dxi)
+    ad_v2 = ad(v2)
+    ad_T12_inv = np.linalg.inv(Adj(exp_se3(xi12)))
+    JinT1 = np.vstack([-Jr_inv_xi12 @ ad_T12_inv, -0.5 * ad_v2 @ (-Jr_inv_xi12 @ ad_T12_inv)])
+    JinV1 = np.vstack([Z6, I6])
+    JinT2 = np.vstack([Jr_inv_xi12, -0.5 * ad_v2 @ Jr_inv_xi12])
+    JinV2 = np.vstack([Z6, Jr_inv_xi12])
+    Ja = np.hstack([J1 @ (Jr_dxi @ Pt1 @ JinT1 + Ad_dT), J1 @ Jr_dxi @ At1 @ JinV1])
+    Jj1 = J1 @ Jr_dxi @ Pt1
+    Jb = np.hstack([Jj1 @ JinT2, Jj1 @ JinV2])
+    Jp = -pj @ Rcb @ Rbw
+    return Ja, Jb, Jp

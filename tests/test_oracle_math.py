@@ -148,6 +148,27 @@ def test_edge_error_and_jacobian(oracle_mod, stereo):
         np.testing.assert_allclose(J2[:, :6], num2[:, :6], atol=2e-3 * scale)
 
 
+@pytest.mark.parametrize("stereo", [False, True])
+def test_edge_jacobian_formulas_vs_numpy_mirror(oracle_mod, stereo):
+    """Second, independent pin of the analytic Jacobians (all blocks, including the pose blocks that a numeric derivative
+    can only confirm to 1e-3 because of the reference's first-order term): the formulas of src/G2oTypes.cc:262-311 / :329-396
+    composed in numpy from scipy logm/expm and the power series of the SE(3) Jacobians.  1e-10 relative to the largest entry."""
+    O = oracle_mod
+    rng = np.random.default_rng(40 + stereo)
+    worst = 0.0
+    for _ in range(12):
+        qc, T1, v1, t1, T2, v2, t2, t, Tbc, intr, Xw = _edge_setup(rng, O)
+        bf = 501.7
+        obs = np.array([470.0, 310.0, 455.0 if stereo else -1.0])
+        _, J1, J2, Jp = O.edge_eval(qc, 1, T1, v1, t1, T2, v2, t2, t, Tbc, intr, bf, Xw, obs)
+        Ma, Mb, Mp = M.gp_edge_jacobians(O.se3_matrix(T1), O.se3_matrix(T2), v1, v2, t1, t2, t, O.se3_matrix(Tbc), intr, bf, Xw, stereo)
+        scale = max(np.abs(Ma).max(), np.abs(Mb).max())
+        for got, ref in ((J1, Ma), (J2, Mb), (Jp, Mp)):
+            assert got.shape == ref.shape
+            worst = max(worst, np.abs(got - ref).max() / max(scale, np.abs(ref).max()))
+    assert worst < 1e-10, worst
+
+
 def test_sync_edge_jacobian(oracle_mod):
     O = oracle_mod
     rng = np.random.default_rng(9)
