@@ -1546,6 +1546,9 @@ int Solver::solve(double lambda) {
     CK(cudaMemsetAsync(d_fail.p + 1, 0, sizeof(int), stream));
     static const int pairs_ctas_per_sm = getenv("GPBA_PAIRS_CTAS") ? atoi(getenv("GPBA_PAIRS_CTAS")) : 16;
     static const int pairs_batch = getenv("GPBA_PAIRS_BATCH") ? std::max(1, atoi(getenv("GPBA_PAIRS_BATCH"))) : 16;   // measured at C4: 8 -> 7.9, 16 -> 7.4, 32 -> 8.4, 64 -> 11.2 ms per optimize
+    // Measured alternatives at C4 (profiles/r02_k4b_experiments.txt): CTAs of 512 / 1024 threads sharing 64..256 items (first-side rows
+    // kept in one SM's L1) 8.1 .. 12.7 ms per optimize; first-side rows of a (chunk, first record) group staged in shared memory with
+    // cp.async.bulk, second side streamed, 7.8 .. 14.4 ms; this kernel 7.3 .. 7.5 ms.
     k_schur_pairs<<<std::min((n_items + 3) / 4, 148 * pairs_ctas_per_sm), 128, 0, stream>>>(n_items, d_item_rp.p, d_item_begin.p, d_item_end.p, d_item_flags.p,
                                                                              d_pairs.p, d_o_lm.p, d_U.p, d_ptL.p, d_C.p, d_fail.p + 1, pairs_batch);
     CK(cudaGetLastError());

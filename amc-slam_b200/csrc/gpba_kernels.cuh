@@ -635,12 +635,13 @@ __global__ void __launch_bounds__(64) k_priors(DevView V, const double* __restri
 // K4a: one warp per landmark: D = Hll + lambda I = L L^T, U_o = W_o L^-T (so that W_o D^-1 W_o'^T = U_o U_o'^T),
 // z = L^-1 b_l.  ptL[9*lm] = {l00,l10,l11,l20,l21,l22, z0,z1,z2}.  Pure streaming: each W row is read and each U row
 // written once.
-// U layout (GPBA_U_STRIDE = 24 doubles per observation): three k-slices of eight, U[k][m] = (U_o)_(m,k) for m < 6,
-// U[k][6] = z_k of the observation's landmark, U[k][7] = 0.  A k-slice is one aligned 64-byte segment, which is exactly what
-// a DMMA operand fetch of K4b wants (8 rows x one k per pair): the 6 x 3 row-major layout of round 1 made every fetch straddle
-// two 128-byte lines and kept K4b on the L1 tag limit (ncu l1tex 98 %, profiles/r02_ncu_streaming.txt).  The z slot hands K4b
-// the g'_r = sum U_o z_l column without a second gather.
-#define GPBA_U_STRIDE 24
+// U layout (GPBA_U_STRIDE = 18 doubles per observation, dense): three k-slices of six, U[k][m] = (U_o)_(m,k).  A DMMA operand
+// fetch of K4b wants 6 rows x one k per pair: here that is one contiguous 48-byte run, the three fetches of an operand cover
+// 144 contiguous bytes = 5 sectors.  History: the 6 x 3 row-major layout of round 1 spread every fetch over the whole row
+// (15 sector requests per operand, K4b on the L1 tag limit: l1tex 98 %); three padded 64-byte slices (with z_l in slot 6) cut
+// that to 6 sectors but moved 192 B per row through the L1 miss path, which is what bounds K4b (profiles/r02_k4b_experiments.txt).
+#define GPBA_U_STRIDE 18
+#define GPBA_U_K 6
 __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, const double* __restrict__ hll,
                                                     const double* __restrict__ bl, const double* __restrict__ W,
                                                     double* __restrict__ U, double* __restrict__ ptL, int* __restrict__ fail) {
@@ -666,27 +667,22 @@ __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, co
     const double* B = W + (size_t)ob * 18;
     double* Uo = U + (size_t)ob * GPBA_U_STRIDE;
     const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
-    // eight slots per observation: rows 0..5 of the block, the z slot and the zero slot
-    for (int rr = lane; rr < nobs * 8; rr += 32) {
-      const int o = rr >> 3, m = rr & 7;
-      double u0, u1, u2;
-      if (m < 6) {
-        const double b0 = B[(o * 6 + m) * 3], b1 = B[(o * 6 + m) * 3 + 1], b2 = B[(o * 6 + m) * 3 + 2];
-        u0 = b0 * i00;
-        u1 = (b1 - u0 * l10) * i11;
-        u2 = (b2 - u0 * l20 - u1 * l21) * i22;
-      } else if (m == 6) { u0 = z0; u1 = z1; u2 = z2; }
-      else { u0 = 0.0; u1 = 0.0; u2 = 0.0; }
+    for (int rr = lane; rr < nobs * 6; rr += 32) {
+      const int o = rr / 6, m = rr - 6 * o;
+      const double b0 = B[rr * 3], b1 = B[rr * 3 + 1], b2 = B[rr * 3 + 2];
+      const double u0 = b0 * i00;
+      const double u1 = (b1 - u0 * l10) * i11;
+      const double u2 = (b2 - u0 * l20 - u1 * l21) * i22;
       double* d = Uo + (size_t)o * GPBA_U_STRIDE + m;
-      d[0] = u0; d[8] = u1; d[16] = u2;
+      d[0] = u0; d[GPBA_U_K] = u1; d[2 * GPBA_U_K] = u2;
     }
   }
 }
 
 // K4b: C_(r,r') = sum U_o U_o'^T over the observation pairs (o in r, o' in r') of common landmarks: a 6 x 6 x 3L GEMM
 // per record pair on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA), one warp per work item = (record pair, chunk
-// of its pair list).  Diagonal record pairs hold the self pairs (o, o): there the padding column 6 carries z_l, which
-// yields g'_r = sum_o U_o z_l (the record's share of Hpl D^-1 b_l) for free.  C is stored 6 x 8 row-major.
+// of its pair list).  Diagonal record pairs hold the self pairs (o, o): there row 6 of the second operand carries z_l (from
+// ptL), which yields g'_r = sum_o U_o z_l (the record's share of Hpl D^-1 b_l) in column 6.  C is stored 6 x 8 row-major.
 GPBA_D void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
@@ -736,13 +732,18 @@ __global__ void __launch_bounds__(128) k_schur_pairs(int n_items, const int* __r
       if (j + 4 + tig < np) pr = pairs[pb + j + 4 + tig];
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
       if (live) {
-        // eight lanes fetch one aligned 64-byte k-slice of a row: slots 0..5 the block's column k, slot 6 z_k (so that
-        // column 6 of a diagonal record pair accumulates g'_r; ignored elsewhere), slot 7 zero
+        // six lanes fetch one contiguous 48-byte k-slice of a row; lane group 6 of the second operand supplies z_l on
+        // diagonal record pairs (column 6 of C: g'_r), lane group 7 stays zero
         const unsigned oa = (unsigned)(cur >> 32), ob = (unsigned)cur;
-        const double* pa = U + (size_t)oa * GPBA_U_STRIDE + gid;
-        const double* pbb = U + (size_t)ob * GPBA_U_STRIDE + gid;
-        a0 = pa[0]; a1 = pa[8]; a2 = pa[16];
-        b0 = pbb[0]; b1 = pbb[8]; b2 = pbb[16];
+        if (gid < 6) {
+          const double* pa = U + (size_t)oa * GPBA_U_STRIDE + gid;
+          const double* pbb = U + (size_t)ob * GPBA_U_STRIDE + gid;
+          a0 = pa[0]; a1 = pa[GPBA_U_K]; a2 = pa[2 * GPBA_U_K];
+          b0 = pbb[0]; b1 = pbb[GPBA_U_K]; b2 = pbb[2 * GPBA_U_K];
+        } else if (gid == 6 && (fl & 1u)) {
+          const double* z = ptL + 9 * (size_t)o_lm[ob] + 6;
+          b0 = z[0]; b1 = z[1]; b2 = z[2];
+        }
       }
       dmma884(c0, c1, a0, b0);
       dmma884(e0, e1, a1, b1);
@@ -901,7 +902,7 @@ __global__ void __launch_bounds__(128) k_backsub(DevView V, double lambda, const
     for (int rr = lane; rr < nrow; rr += 32) {
       const double y = Y[(size_t)V.o_rec[ob + rr / 6] * 6 + rr % 6];
       const double* u = U + (size_t)(ob + rr / 6) * GPBA_U_STRIDE + rr % 6;
-      a0 = fma(u[0], y, a0); a1 = fma(u[8], y, a1); a2 = fma(u[16], y, a2);
+      a0 = fma(u[0], y, a0); a1 = fma(u[GPBA_U_K], y, a1); a2 = fma(u[2 * GPBA_U_K], y, a2);
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) {
