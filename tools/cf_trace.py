@@ -33,7 +33,7 @@ ch = ~panel
 nprod = (tab[ch, 3] - tab[ch, 2])
 print(f"  chunk detail: products/chunk {nprod.mean():.2f}; consumer wait-for-operands inside chunk mean {tr8[ch, 4].mean() / 1e3:.2f} us; "
       f"compute end -> counted mean {(tr8[ch, 3] - tr8[ch, 5]).mean() / 1e3:.2f} us; producer wait-for-free-stage mean {tr8[ch, 6].mean() / 1e3:.2f} us")
-pm = panel
+pm = panel & (tr8[:, 4] > 0)   # tasks that factorize (solve-only tasks of wide levels leave the slot empty)
 print(f"  panel detail: start -> potrf done mean {(tr8[pm, 4] - tr8[pm, 2]).mean() / 1e3:.2f} us, potrf -> trsm done {(tr8[pm, 5] - tr8[pm, 4]).mean() / 1e3:.2f} us, trsm -> counted {(tr8[pm, 3] - tr8[pm, 5]).mean() / 1e3:.2f} us")
 busy = (tr[:, 3] - tr[:, 2]).sum()
 print(f"  consumer-busy fraction over {n_ctas} CTAs: {busy / (span * n_ctas):.3f}")
