@@ -1535,7 +1535,7 @@ int Solver::solve(double lambda) {
   t0();
   // K4a + K4b: per-landmark factor and the record-pair products
   if (n_lm > 0) {
-    k_schur_prep<<<std::min((n_lm + 3) / 4, 148 * 16), 128, 0, stream>>>(V, lambda, d_hll.p, d_bl.p, d_W.p, d_U.p, d_ptL.p, d_fail.p);
+    k_schur_prep<<<std::min((n_lm + 15) / 16, 148 * 16), 128, 0, stream>>>(V, lambda, d_hll.p, d_bl.p, d_W.p, d_U.p, d_ptL.p, d_fail.p);
     CK(cudaGetLastError());
   }
   t1(4, n_lm > 0 ? 1 : 0);
@@ -1626,7 +1626,7 @@ int Solver::apply_update(double lambda, double* scale) {
   t0();
   int gp = 0;
   if (n_lm > 0) {
-    gp = std::min((n_lm + 3) / 4, 148 * 16);
+    gp = std::min((n_lm + 15) / 16, 148 * 16);   // four landmarks per warp, four warps per CTA
     k_rec_y<<<(n_rec * 6 + 127) / 128, 128, 0, stream>>>(V, d_rec.p, d_x.p, d_Y.p);
     k_backsub<<<gp, 128, 0, stream>>>(V, lambda, d_U.p, d_ptL.p, d_bl.p, d_Y.p, d_ptS[cur].p, d_ptS[nb].p, d_xl.p, d_partial.p);
     CK(cudaGetLastError());

@@ -645,8 +645,12 @@ __global__ void __launch_bounds__(64) k_priors(DevView V, const double* __restri
 __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, const double* __restrict__ hll,
                                                     const double* __restrict__ bl, const double* __restrict__ W,
                                                     double* __restrict__ U, double* __restrict__ ptL, int* __restrict__ fail) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int lm = blockIdx.x * 4 + warp; lm < V.n_lm; lm += gridDim.x * 4) {
+  // eight lanes per landmark, four landmarks per warp (a landmark has ~60 rows; the factorization of its 3 x 3 block is a
+  // chain of three square roots and six divisions that a whole warp per landmark only waited for)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7;
+  for (int base = (blockIdx.x * 4 + warp) * 4; base < V.n_lm; base += gridDim.x * 16) {
+    const int lm = base + grp;
+    if (lm >= V.n_lm) continue;
     const double* H = hll + 9 * (size_t)lm;
     const double d00 = H[0] + lambda, d10 = H[3], d11 = H[4] + lambda, d20 = H[6], d21 = H[7], d22 = H[8] + lambda;
     const double l00 = sqrt(d00);
@@ -657,7 +661,7 @@ __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, co
     const double z0 = bl[3 * (size_t)lm] / l00;
     const double z1 = (bl[3 * (size_t)lm + 1] - l10 * z0) / l11;
     const double z2 = (bl[3 * (size_t)lm + 2] - l20 * z0 - l21 * z1) / l22;
-    if (lane == 0) {
+    if (sl == 0) {
       if (!(l00 > 0.0) || !(l11 > 0.0) || !(l22 > 0.0)) atomicExch(fail, 1);
       double* o = ptL + 9 * (size_t)lm;
       o[0] = l00; o[1] = l10; o[2] = l11; o[3] = l20; o[4] = l21; o[5] = l22; o[6] = z0; o[7] = z1; o[8] = z2;
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(128) k_schur_prep(DevView V, double lambda, co
     const double* B = W + (size_t)ob * 18;
     double* Uo = U + (size_t)ob * GPBA_U_STRIDE;
     const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
-    for (int rr = lane; rr < nobs * 6; rr += 32) {
+    for (int rr = sl; rr < nobs * 6; rr += 8) {
       const int o = rr / 6, m = rr - 6 * o;
       const double b0 = B[rr * 3], b1 = B[rr * 3 + 1], b2 = B[rr * 3 + 2];
       const double u0 = b0 * i00;
@@ -887,25 +891,34 @@ __global__ void k_rec_y(DevView V, const double* __restrict__ rec, const double*
 
 // Landmarks: x_l = D^-1 (b_l - Hpl^T x_p) = L^-T (z - sum_o U_o^T y_r(o)); pt_new = pt + x_l.
 // partial[] receives sum x_l (lambda x_l + b_l) for computeScale (optimization_algorithm_levenberg.cpp:187-194).
+// Eight lanes per landmark, four landmarks per warp: a landmark has ~60 rows (10 observations x 6), so a whole warp per
+// landmark spent most of its time in three 5-step reductions and a one-lane triangular solve with three divisions (ncu:
+// latency-bound, 34 % of HBM); here the reductions are 3 steps and four solves run side by side.
 __global__ void __launch_bounds__(128) k_backsub(DevView V, double lambda, const double* __restrict__ U,
                                                  const double* __restrict__ ptL, const double* __restrict__ bl,
                                                  const double* __restrict__ Y, const double* __restrict__ pt_cur,
                                                  double* __restrict__ pt_new, double* __restrict__ xl,
                                                  double* __restrict__ partial) {
   __shared__ double red[32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7;
   double sc = 0.0;
-  for (int lm = blockIdx.x * 4 + warp; lm < V.n_lm; lm += gridDim.x * 4) {
-    const int64_t ob = V.lm_obs_begin[lm];
-    const int nrow = (int)(V.lm_obs_begin[lm + 1] - ob) * 6;
+  for (int base = (blockIdx.x * 4 + warp) * 4; base < V.n_lm; base += gridDim.x * 16) {
+    const int lm = base + grp;
+    const bool live = lm < V.n_lm;
+    const int64_t ob = live ? V.lm_obs_begin[lm] : 0;
+    const int nrow = live ? (int)(V.lm_obs_begin[lm + 1] - ob) * 6 : 0;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int rr = lane; rr < nrow; rr += 32) {
-      const double y = Y[(size_t)V.o_rec[ob + rr / 6] * 6 + rr % 6];
-      const double* u = U + (size_t)(ob + rr / 6) * GPBA_U_STRIDE + rr % 6;
+    for (int rr = sl; rr < nrow; rr += 8) {
+      const int o = rr / 6, m = rr - 6 * o;
+      const double y = Y[(size_t)V.o_rec[ob + o] * 6 + m];
+      const double* u = U + (size_t)(ob + o) * GPBA_U_STRIDE + m;
       a0 = fma(u[0], y, a0); a1 = fma(u[GPBA_U_K], y, a1); a2 = fma(u[2 * GPBA_U_K], y, a2);
     }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-    if (lane == 0) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {   // sum over the eight lanes of the group
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (live && sl == 0) {
       const double* L = ptL + 9 * (size_t)lm;
       const double y0 = L[6] - a0, y1 = L[7] - a1, y2 = L[8] - a2;
       const double x2 = y2 / L[5];
