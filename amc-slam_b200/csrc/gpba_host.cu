@@ -24,6 +24,7 @@
 #include <vector>
 #include <dlfcn.h>
 #include <functional>
+#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -198,6 +199,151 @@ struct StreamHolder {
   ~StreamHolder() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
 };
 
+// Host part of the factorization's structure: symbolic phase (gpba_order.h) and the schedule tables derived from it.  No device
+// call in here: build_structure runs it on a second host thread while the main thread finishes the device-side structure.
+struct CholHost {
+  CholSymbolic sym;
+  std::vector<int2> pan_tab, back_tab;
+  std::vector<int4> upd_tab, cf_tab, prod;
+  std::vector<unsigned> klist;
+  std::vector<int> cf_need, lvl_pan_begin, lvl_upd_begin, lvl_back_begin, lvl_ncols;
+  int64_t products = 0, update_ctas = 0;
+  int rc = GPBA_OK;
+  std::string err;
+};
+static int chol_host_phase(int n_pose, int n_hs, const int* hs_row, const int* hs_col, CholHost& H) {
+  const int n = n_pose * 12;
+  const int bpt = GPBA_NB / 12;  // pose blocks per tile
+  // symbolic phase on the host (gpba_order.h): nested-dissection order, tile-level fill, level schedule
+  CholSymbolic& sym = H.sym;
+  chol_symbolic(n_pose, n_hs, hs_row, hs_col, bpt, GPBA_TILE, getenv("GPBA_CHOL_ND_DEPTH") ? atoi(getenv("GPBA_CHOL_ND_DEPTH")) : -1,
+                getenv("GPBA_VERBOSE") != nullptr, sym);
+  const int NT = sym.NT;
+  const int64_t chol_doubles = sym.doubles;
+  const std::vector<int>& chol_col_begin = sym.col_begin;
+  const std::vector<int>& chol_row_begin = sym.row_begin;
+  const std::vector<int>& col_rows = sym.col_rows;
+  const std::vector<int>& perm = sym.perm;
+  const std::vector<int64_t>& off = sym.tile_off;
+  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: n=%d NT=%d tiles=%lld (dense lower would be %d), %.1f MB\n", n, NT, (long long)(chol_doubles / GPBA_TILE), NT * (NT + 1) / 2, chol_doubles * 8 / 1e6);
+  const int n_levels = sym.n_levels;
+  const std::vector<int>& level = sym.level;
+  std::vector<std::vector<int>> lvl_cols(n_levels);
+  for (int k = 0; k < NT; ++k) lvl_cols[level[k]].push_back(k);
+  std::vector<int2>&pan_tab = H.pan_tab, &back_tab = H.back_tab;
+  std::vector<int4>& upd_tab = H.upd_tab;     // left-looking update: {column j, tile slot q, klist begin, klist end}
+  std::vector<unsigned>& klist = H.klist;   // finished columns k with L_ik != 0 and L_jk != 0 per tile (i, j); bit 31: column of the previous level
+  std::vector<int>&lvl_pan_begin = H.lvl_pan_begin, &lvl_upd_begin = H.lvl_upd_begin, &lvl_back_begin = H.lvl_back_begin, &lvl_ncols = H.lvl_ncols;
+  lvl_pan_begin.assign(n_levels + 1, 0); lvl_upd_begin.assign(n_levels + 1, 0); lvl_back_begin.assign(n_levels + 1, 0);
+  lvl_ncols.assign(n_levels, 0);
+  std::vector<unsigned> late_scratch;
+  std::vector<int4> early_chunks, late_chunks;
+  std::vector<int4>& cf_tab = H.cf_tab;
+  std::vector<int>& cf_need = H.cf_need;
+  cf_need.assign(2 * (size_t)NT, 0);
+  for (int l = 0; l < n_levels; ++l) {
+    lvl_ncols[l] = (int)lvl_cols[l].size();
+    early_chunks.clear(); late_chunks.clear();
+    struct TileList { int k, q, kb, cnt, n_late; };
+    std::vector<TileList> lists;
+    for (int k : lvl_cols[l]) {
+      const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
+      for (int q = 0; q <= nr; ++q) pan_tab.push_back(make_int2(k, q));
+      // tile (i, k) of column k receives L_ic L_kc^T from every finished column c that touches both rows: the
+      // intersection of the two row patterns (both ascending)
+      for (int q = 0; q <= nr; ++q) {
+        const int i = q == 0 ? k : col_rows[chol_col_begin[k] + q - 1];
+        const int *pa = sym.row_cols.data() + chol_row_begin[i], *pae = sym.row_cols.data() + chol_row_begin[i + 1];
+        const int *pb = sym.row_cols.data() + chol_row_begin[k], *pbe = sym.row_cols.data() + chol_row_begin[k + 1];
+        const int kb = (int)klist.size();
+        // sources of older levels first, sources of the previous level (whose panel step overlaps with this update) last
+        size_t n_late = 0;
+        std::vector<unsigned>& late = late_scratch;
+        late.clear();
+        while (pa < pae && pb < pbe) {
+          if (*pa < *pb) ++pa; else if (*pb < *pa) ++pb;
+          else { if (level[*pa] == l - 1) late.push_back((unsigned)*pa | GPBA_LU_LATE); else klist.push_back((unsigned)*pa); ++pa; ++pb; }
+        }
+        n_late = late.size();
+        klist.insert(klist.end(), late.begin(), late.end());
+        const int cnt = (int)klist.size() - kb;
+        if (cnt == 0) continue;
+        lists.push_back({k, q, kb, cnt, (int)n_late});
+      }
+      const int nrow = chol_row_begin[k + 1] - chol_row_begin[k];
+      for (int q = 0; q <= nrow; ++q) back_tab.push_back(make_int2(k, q));
+      if (nr >= 65536) { H.err = "tile column with more than 65535 rows"; return GPBA_ERR_INVALID; }
+    }
+    // Chunk size: at least GPBA_LU_CHUNK products (a chunk ends with 12 reductions per thread, a fence and a counter
+    // update), more where the level has enough products to keep every SM busy with fewer, longer chunks.
+    {
+      static const int lu_chunk = getenv("GPBA_LU_CHUNK") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK"))) : GPBA_LU_CHUNK;
+      static const int lu_chunk_max = getenv("GPBA_LU_CHUNK_MAX") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK_MAX"))) : 12;
+      int64_t total = 0;
+      for (const TileList& t : lists) total += t.cnt;
+      const int chunk = (int)std::min<int64_t>(std::max<int64_t>(lu_chunk, total / (2 * 148)), std::max(lu_chunk, lu_chunk_max));
+      // products whose source column belongs to the previous level sit on the critical path (panel -> product -> next
+      // panel): they get short chunks of their own so that several SMs work on one tile's late tail at once
+      static const int late_chunk = getenv("GPBA_LU_LATE_CHUNK") ? std::max(0, atoi(getenv("GPBA_LU_LATE_CHUNK"))) : 1;
+      auto cut = [&](const TileList& t, int b, int cnt, int size, bool late) {
+        const int nch = (cnt + size - 1) / size;
+        for (int c = 0; c < nch; ++c)
+          (late ? late_chunks : early_chunks).push_back(make_int4(t.k, t.q, b + (int)((int64_t)cnt * c / nch), b + (int)((int64_t)cnt * (c + 1) / nch)));
+      };
+      for (const TileList& t : lists) {
+        if (late_chunk > 0) {
+          if (t.cnt > t.n_late) cut(t, t.kb, t.cnt - t.n_late, chunk, false);
+          if (t.n_late > 0) cut(t, t.kb + t.cnt - t.n_late, t.n_late, late_chunk, true);
+          continue;
+        }
+        const int nch = (t.cnt + chunk - 1) / chunk;
+        for (int c = 0; c < nch; ++c) {
+          const int cb = t.kb + (int)((int64_t)t.cnt * c / nch), ce = t.kb + (int)((int64_t)t.cnt * (c + 1) / nch);
+          const bool is_late = ce > t.kb + t.cnt - t.n_late;   // the chunk reaches into the late tail
+          (is_late ? late_chunks : early_chunks).push_back(make_int4(t.k, t.q, cb, ce));
+        }
+      }
+    }
+    // chunks that only need finished levels are handed out first: they overlap with the previous level's panel step
+    upd_tab.insert(upd_tab.end(), early_chunks.begin(), early_chunks.end());
+    upd_tab.insert(upd_tab.end(), late_chunks.begin(), late_chunks.end());
+    // the same work as one task list for the persistent kernel: this level's chunks, then its panel tasks
+    auto tile_of = [&](int i, int j) { return (int)(off[(size_t)i * NT + j] / GPBA_TILE); };
+    auto row_of = [&](int k, int q) { return q == 0 ? k : col_rows[chol_col_begin[k] + q - 1]; };
+    for (const std::vector<int4>* v : {&early_chunks, &late_chunks})
+      for (const int4& c : *v) {
+        cf_tab.push_back(make_int4(c.x | (c.y == 0 ? GPBA_CF_DIAG : 0), tile_of(row_of(c.x, c.y), c.x), c.z, c.w));
+        cf_need[c.x] += 1;
+      }
+    // Wide levels (more panel tasks than resident CTAs can take at once) are throughput bound: one task per column
+    // factorizes the diagonal tile and publishes it, the others only solve.  Narrow levels are latency bound: every task
+    // factorizes the diagonal tile itself, which saves a publish / wait / reload hop on the critical path.
+    static const int split_min = getenv("GPBA_CF_SPLIT_MIN") ? atoi(getenv("GPBA_CF_SPLIT_MIN")) : 120;
+    const bool split = lvl_pan_begin.size() > 0 && ((int)pan_tab.size() - lvl_pan_begin[l]) >= split_min;
+    for (int pass = 0; pass < 2; ++pass)   // diagonal tasks first
+      for (int k : lvl_cols[l]) {
+        const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
+        if (pass == 0) { cf_tab.push_back(make_int4(k | GPBA_CF_DIAG, tile_of(k, k), split && nr > 0 ? -2 : -1, tile_of(k, k))); cf_need[(size_t)NT + k] = nr + 1; }
+        else for (int q = 1; q <= nr; ++q) cf_tab.push_back(make_int4(k, tile_of(row_of(k, q), k), split ? -3 : -1, tile_of(k, k)));
+      }
+    lvl_pan_begin[l + 1] = (int)pan_tab.size(); lvl_upd_begin[l + 1] = (int)upd_tab.size(); lvl_back_begin[l + 1] = (int)back_tab.size();
+  }
+  H.products = (int64_t)klist.size(); H.update_ctas = (int64_t)upd_tab.size();
+  if (upd_tab.empty()) upd_tab.push_back(make_int4(0, 0, 0, 0));
+  if (klist.empty()) klist.push_back(0);
+  // one record per product: the tiles of L_ik and L_jk and the source column k
+  H.prod.assign(klist.size(), make_int4(0, 0, 0, 0));
+  for (const int4& c : upd_tab) {
+    if (c.z >= c.w) continue;
+    const int j = c.x, i = c.y == 0 ? j : col_rows[chol_col_begin[j] + c.y - 1];
+    for (int p = c.z; p < c.w; ++p) {
+      const int k = (int)(klist[p] & ~GPBA_LU_LATE);
+      H.prod[p] = make_int4((int)(off[(size_t)i * NT + k] / GPBA_TILE), (int)(off[(size_t)j * NT + k] / GPBA_TILE), k, 0);
+    }
+  }
+  return GPBA_OK;
+}
+
 struct Solver {
   int device = 0;
   StreamHolder stream_holder;   // first member: destroyed after every buffer has been returned to the pool
@@ -292,6 +438,7 @@ struct Solver {
   DBuf<int> d_cf_need;               // [2 NT]: upd_need | pan_need
   DBuf<int> d_cf_cnt;                // [2 NT + 1]: upd_cnt | pan_cnt | task counter (zeroed by the graph)
   int cf_tasks = 0;
+  std::future<std::unique_ptr<CholHost>> chol_future;   // host tables of the factorization, computed beside the device-side structure build
   DBuf<double> d_cf_d8;              // [NT][6][8][8] inverted diagonal blocks published by the diagonal tasks of wide levels
   DBuf<long long> d_cf_trace;        // GPBA_CF_TRACE=<file>: per-task timestamps of the last factorization (tools/cf_trace.py)
   DBuf<int> d_tile_lm, d_tile_rlo, d_tile_rcnt;   // landmark-aligned observation tiles + their record windows (K1 / K2a)
@@ -374,6 +521,7 @@ struct Solver {
 
   int init(const gpba_problem* P, int dev, bool async_upload);
   int build_structure();
+  int count_hpl();
   int build_cholesky_structure();
   int capture_cholesky_graph();
   void fill_view();
@@ -587,6 +735,7 @@ __global__ void k_merge_chi2(int64_t n_obs, const uint8_t* __restrict__ flags, c
 // (sparse_optimizer.cpp:199-267,166-190; block_solver.hpp:142-295), integer and bit-exact.  The host does the O(n_obs)
 // bucket passes and the (small) pose-level patterns; the O(sum d^2) pairing runs on the device (gpba_structure.cuh).
 int Solver::build_structure() {
+  if (chol_future.valid()) chol_future.get();   // tables of an earlier, abandoned build
   CK(cudaSetDevice(device));
   g_alloc_stream = stream;
   const bool verbose = getenv("GPBA_VERBOSE") != nullptr;
@@ -893,19 +1042,10 @@ int Solver::build_structure() {
     pat_key = &pat_key_store;
   }
   lap("pair sort");
-  // --- #Hpl blocks (reported only)
+  // --- #Hpl blocks: reported only (gpba_structure_info), counted on demand by count_hpl(): 0.6 ms and a host synchronisation
+  // that a gpba_optimize on a fresh handle does not need
   fill_view();
-  {
-    DBuf<unsigned long long> d_cnt;
-    CKR(d_cnt.alloc(1));
-    CK(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), stream));
-    if (n_lm > 0) { k_count_hpl<<<std::min((n_lm + 7) / 8, 148 * 16), 256, 0, stream>>>(V, d_o_rec.p, d_cnt.p); CK(cudaGetLastError()); }
-    unsigned long long h = 0;
-    CK(cudaMemcpyAsync(&h, d_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    n_hpl = (int64_t)h;
-  }
-  lap("hpl count");
+  n_hpl = -1;
   // --- Hpp pattern (upper, host: a few thousand blocks): diagonals + priors + the keyframe pair of every used record
   std::vector<std::vector<int>> pp_rows(n_pose);
   auto add_pair = [](std::vector<std::vector<int>>& rows, int a, int b) {
@@ -983,6 +1123,19 @@ int Solver::build_structure() {
     hs_row.resize(n_hs); hs_col.resize(n_hs);
     std::vector<int> hs_from(n_hs, -1), hs_diag(n_hs, -1);
     for (int k = 0; k < n_hs; ++k) { hs_row[k] = (int)(unsigned)hs_key[k]; hs_col[k] = (int)(hs_key[k] >> 32); if (hs_row[k] == hs_col[k]) hs_diag[k] = hs_row[k]; }
+    // The host tables of the factorization (ordering, fill, level schedule, task list: 3.6 ms at C4) need nothing but this
+    // block pattern: a helper thread builds them while this thread finishes the device-side structure.  hs_row / hs_col are
+    // not touched again before build_cholesky_structure() has collected the result.
+    static const bool chol_async = !getenv("GPBA_SYMBOLIC_SYNC");
+    if (linear_solver != GPBA_SOLVER_PCG && chol_async) {
+      const int np_ = n_pose, nh_ = n_hs;
+      const int *hr = hs_row.data(), *hc = hs_col.data();
+      chol_future = std::async(std::launch::async, [np_, nh_, hr, hc]() {
+        std::unique_ptr<CholHost> H(new CholHost);
+        H->rc = chol_host_phase(np_, nh_, hr, hc, *H);
+        return H;
+      });
+    }
     for (int k = 0; k < n_hpp; ++k) hs_from[(int)(std::lower_bound(hs_key.begin(), hs_key.begin() + n_hs, hpp_key[k]) - hs_key.begin())] = k;
     CKR(d_hs_from_hpp.upload(hs_from, stream)); CKR(d_hs_diag_pose.upload(hs_diag, stream));
     CKR(d_hs_row.upload(hs_row, stream)); CKR(d_hs_col.upload(hs_col, stream));
@@ -1098,149 +1251,51 @@ int Solver::build_structure() {
   return GPBA_OK;
 }
 
-// tile-level symbolic factorization (the analyzePattern of the sparse path)
+// #(free pose, landmark) blocks of Hpl = _Hpl->nonZeroBlocks() (block_solver.hpp:206-254)
+int Solver::count_hpl() {
+  if (n_hpl >= 0) return GPBA_OK;
+  fill_view();
+  DBuf<unsigned long long> d_cnt;
+  CKR(d_cnt.alloc(1));
+  CK(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), stream));
+  if (n_lm > 0) { k_count_hpl<<<std::min((n_lm + 7) / 8, 148 * 16), 256, 0, stream>>>(V, d_o_rec.p, d_cnt.p); CK(cudaGetLastError()); }
+  unsigned long long h = 0;
+  CK(cudaMemcpyAsync(&h, d_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  n_hpl = (int64_t)h;
+  info.n_hpl = n_hpl;
+  return GPBA_OK;
+}
+
+
+// tile-level symbolic factorization (the analyzePattern of the sparse path): host tables (computed here, or already by the
+// helper thread build_structure started), then allocation and upload
 int Solver::build_cholesky_structure() {
-  const int n = n_pose * 12;
-  const int bpt = GPBA_NB / 12;  // pose blocks per tile
-  // symbolic phase on the host (gpba_order.h): nested-dissection order, tile-level fill, level schedule
-  CholSymbolic sym;
-  chol_symbolic(n_pose, n_hs, hs_row.data(), hs_col.data(), bpt, GPBA_TILE, getenv("GPBA_CHOL_ND_DEPTH") ? atoi(getenv("GPBA_CHOL_ND_DEPTH")) : -1,
-                getenv("GPBA_VERBOSE") != nullptr, sym);
+  std::unique_ptr<CholHost> Hp;
+  if (chol_future.valid()) Hp = chol_future.get();
+  else { Hp.reset(new CholHost); Hp->rc = chol_host_phase(n_pose, n_hs, hs_row.data(), hs_col.data(), *Hp); }
+  CholHost& H = *Hp;
+  if (H.rc != GPBA_OK) { g_err = H.err; return H.rc; }
+  const CholSymbolic& sym = H.sym;
   NT = sym.NT; chol_parts = sym.n_parts; chol_doubles = sym.doubles;
   chol_col_begin = sym.col_begin; chol_row_begin = sym.row_begin;
-  const std::vector<int>& col_rows = sym.col_rows;
-  const std::vector<int>& perm = sym.perm;
-  const std::vector<int64_t>& off = sym.tile_off;
-  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: n=%d NT=%d tiles=%lld (dense lower would be %d), %.1f MB\n", n, NT, (long long)(chol_doubles / GPBA_TILE), NT * (NT + 1) / 2, chol_doubles * 8 / 1e6);
+  lvl_pan_begin = H.lvl_pan_begin; lvl_upd_begin = H.lvl_upd_begin; lvl_back_begin = H.lvl_back_begin; lvl_ncols = H.lvl_ncols;
+  chol_products = H.products; chol_update_ctas = H.update_ctas;
+  const int n_levels = sym.n_levels;
   CKR(d_chol_pos_used.upload(sym.pos_used, stream));
-  CKR(d_tile_off.upload(off, stream)); CKR(d_col_begin.upload(chol_col_begin, stream)); CKR(d_col_rows.upload(col_rows, stream));
-  CKR(d_chol_perm.upload(perm, stream));
+  CKR(d_tile_off.upload(sym.tile_off, stream)); CKR(d_col_begin.upload(chol_col_begin, stream)); CKR(d_col_rows.upload(sym.col_rows, stream));
+  CKR(d_chol_perm.upload(sym.perm, stream));
   CKR(d_tiles.alloc((size_t)chol_doubles)); CKR(d_chol_work.alloc((size_t)NT * GPBA_NB));
   CKR(d_chol_dinv.alloc((size_t)NT * GPBA_NB * GPBA_NB)); CKR(d_chol_x.alloc((size_t)NT * GPBA_NB));
   CKR(d_row_begin.upload(chol_row_begin, stream)); CKR(d_row_cols.upload(sym.row_cols, stream));
-  const int n_levels = sym.n_levels;
-  const std::vector<int>& level = sym.level;
-  std::vector<std::vector<int>> lvl_cols(n_levels);
-  for (int k = 0; k < NT; ++k) lvl_cols[level[k]].push_back(k);
-  std::vector<int2> pan_tab, back_tab;
-  std::vector<int4> upd_tab;     // left-looking update: {column j, tile slot q (| GPBA_LU_SPLIT), klist begin, klist end}
-  std::vector<unsigned> klist;   // finished columns k with L_ik != 0 and L_jk != 0 per tile (i, j); bit 31: column of the previous level
-  lvl_pan_begin.assign(n_levels + 1, 0); lvl_upd_begin.assign(n_levels + 1, 0); lvl_back_begin.assign(n_levels + 1, 0);
-  lvl_ncols.assign(n_levels, 0);
-  std::vector<unsigned> late_scratch;
-  std::vector<int4> early_chunks, late_chunks;
-  std::vector<int4> cf_tab;
-  std::vector<int> cf_need(2 * (size_t)NT, 0);
-  for (int l = 0; l < n_levels; ++l) {
-    lvl_ncols[l] = (int)lvl_cols[l].size();
-    early_chunks.clear(); late_chunks.clear();
-    struct TileList { int k, q, kb, cnt, n_late; };
-    std::vector<TileList> lists;
-    for (int k : lvl_cols[l]) {
-      const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
-      for (int q = 0; q <= nr; ++q) pan_tab.push_back(make_int2(k, q));
-      // tile (i, k) of column k receives L_ic L_kc^T from every finished column c that touches both rows: the
-      // intersection of the two row patterns (both ascending)
-      for (int q = 0; q <= nr; ++q) {
-        const int i = q == 0 ? k : col_rows[chol_col_begin[k] + q - 1];
-        const int *pa = sym.row_cols.data() + chol_row_begin[i], *pae = sym.row_cols.data() + chol_row_begin[i + 1];
-        const int *pb = sym.row_cols.data() + chol_row_begin[k], *pbe = sym.row_cols.data() + chol_row_begin[k + 1];
-        const int kb = (int)klist.size();
-        // sources of older levels first, sources of the previous level (whose panel step overlaps with this update) last
-        size_t n_late = 0;
-        std::vector<unsigned>& late = late_scratch;
-        late.clear();
-        while (pa < pae && pb < pbe) {
-          if (*pa < *pb) ++pa; else if (*pb < *pa) ++pb;
-          else { if (level[*pa] == l - 1) late.push_back((unsigned)*pa | GPBA_LU_LATE); else klist.push_back((unsigned)*pa); ++pa; ++pb; }
-        }
-        n_late = late.size();
-        klist.insert(klist.end(), late.begin(), late.end());
-        const int cnt = (int)klist.size() - kb;
-        if (cnt == 0) continue;
-        lists.push_back({k, q, kb, cnt, (int)n_late});
-      }
-      const int nrow = chol_row_begin[k + 1] - chol_row_begin[k];
-      for (int q = 0; q <= nrow; ++q) back_tab.push_back(make_int2(k, q));
-      if (nr >= 65536) { g_err = "tile column with more than 65535 rows"; return GPBA_ERR_INVALID; }
-    }
-    // Chunk size: at least GPBA_LU_CHUNK products (a chunk ends with 12 reductions per thread, a fence and a counter
-    // update), more where the level has enough products to keep every SM busy with fewer, longer chunks.
-    {
-      static const int lu_chunk = getenv("GPBA_LU_CHUNK") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK"))) : GPBA_LU_CHUNK;
-      static const int lu_chunk_max = getenv("GPBA_LU_CHUNK_MAX") ? std::max(1, atoi(getenv("GPBA_LU_CHUNK_MAX"))) : 12;
-      int64_t total = 0;
-      for (const TileList& t : lists) total += t.cnt;
-      const int chunk = (int)std::min<int64_t>(std::max<int64_t>(lu_chunk, total / (2 * 148)), std::max(lu_chunk, lu_chunk_max));
-      // products whose source column belongs to the previous level sit on the critical path (panel -> product -> next
-      // panel): they get short chunks of their own so that several SMs work on one tile's late tail at once
-      static const int late_chunk = getenv("GPBA_LU_LATE_CHUNK") ? std::max(0, atoi(getenv("GPBA_LU_LATE_CHUNK"))) : 1;
-      auto cut = [&](const TileList& t, int b, int cnt, int size, bool late) {
-        const int nch = (cnt + size - 1) / size;
-        for (int c = 0; c < nch; ++c)
-          (late ? late_chunks : early_chunks).push_back(make_int4(t.k, t.q, b + (int)((int64_t)cnt * c / nch), b + (int)((int64_t)cnt * (c + 1) / nch)));
-      };
-      for (const TileList& t : lists) {
-        if (late_chunk > 0) {
-          if (t.cnt > t.n_late) cut(t, t.kb, t.cnt - t.n_late, chunk, false);
-          if (t.n_late > 0) cut(t, t.kb + t.cnt - t.n_late, t.n_late, late_chunk, true);
-          continue;
-        }
-        const int nch = (t.cnt + chunk - 1) / chunk;
-        for (int c = 0; c < nch; ++c) {
-          const int cb = t.kb + (int)((int64_t)t.cnt * c / nch), ce = t.kb + (int)((int64_t)t.cnt * (c + 1) / nch);
-          const bool is_late = ce > t.kb + t.cnt - t.n_late;   // the chunk reaches into the late tail
-          (is_late ? late_chunks : early_chunks).push_back(make_int4(t.k, t.q, cb, ce));
-        }
-      }
-    }
-    // chunks that only need finished levels are handed out first: they overlap with the previous level's panel step
-    upd_tab.insert(upd_tab.end(), early_chunks.begin(), early_chunks.end());
-    upd_tab.insert(upd_tab.end(), late_chunks.begin(), late_chunks.end());
-    // the same work as one task list for the persistent kernel: this level's chunks, then its panel tasks
-    auto tile_of = [&](int i, int j) { return (int)(off[(size_t)i * NT + j] / GPBA_TILE); };
-    auto row_of = [&](int k, int q) { return q == 0 ? k : col_rows[chol_col_begin[k] + q - 1]; };
-    for (const std::vector<int4>* v : {&early_chunks, &late_chunks})
-      for (const int4& c : *v) {
-        cf_tab.push_back(make_int4(c.x | (c.y == 0 ? GPBA_CF_DIAG : 0), tile_of(row_of(c.x, c.y), c.x), c.z, c.w));
-        cf_need[c.x] += 1;
-      }
-    // Wide levels (more panel tasks than resident CTAs can take at once) are throughput bound: one task per column
-    // factorizes the diagonal tile and publishes it, the others only solve.  Narrow levels are latency bound: every task
-    // factorizes the diagonal tile itself, which saves a publish / wait / reload hop on the critical path.
-    static const int split_min = getenv("GPBA_CF_SPLIT_MIN") ? atoi(getenv("GPBA_CF_SPLIT_MIN")) : 120;
-    const bool split = lvl_pan_begin.size() > 0 && ((int)pan_tab.size() - lvl_pan_begin[l]) >= split_min;
-    for (int pass = 0; pass < 2; ++pass)   // diagonal tasks first
-      for (int k : lvl_cols[l]) {
-        const int nr = chol_col_begin[k + 1] - chol_col_begin[k];
-        if (pass == 0) { cf_tab.push_back(make_int4(k | GPBA_CF_DIAG, tile_of(k, k), split && nr > 0 ? -2 : -1, tile_of(k, k))); cf_need[(size_t)NT + k] = nr + 1; }
-        else for (int q = 1; q <= nr; ++q) cf_tab.push_back(make_int4(k, tile_of(row_of(k, q), k), split ? -3 : -1, tile_of(k, k)));
-      }
-    lvl_pan_begin[l + 1] = (int)pan_tab.size(); lvl_upd_begin[l + 1] = (int)upd_tab.size(); lvl_back_begin[l + 1] = (int)back_tab.size();
-  }
-  chol_products = (int64_t)klist.size(); chol_update_ctas = (int64_t)upd_tab.size();
-  if (upd_tab.empty()) upd_tab.push_back(make_int4(0, 0, 0, 0));
-  if (klist.empty()) klist.push_back(0);
-  CKR(d_pan_tab.upload(pan_tab, stream)); CKR(d_upd_tab.upload(upd_tab, stream)); CKR(d_back_tab.upload(back_tab, stream));
-  CKR(d_klist.upload(klist, stream));
+  CKR(d_pan_tab.upload(H.pan_tab, stream)); CKR(d_upd_tab.upload(H.upd_tab, stream)); CKR(d_back_tab.upload(H.back_tab, stream));
+  CKR(d_klist.upload(H.klist, stream));
   CKR(d_lu_counter.alloc(2 * (size_t)std::max(n_levels, 1)));
-  cf_tasks = (int)cf_tab.size();
-  {
-    // one record per product: the tiles of L_ik and L_jk and the source column k
-    std::vector<int4> prod(klist.size(), make_int4(0, 0, 0, 0));
-    for (const int4& c : upd_tab) {
-      if (c.z >= c.w) continue;
-      const int j = c.x, i = c.y == 0 ? j : col_rows[chol_col_begin[j] + c.y - 1];
-      for (int p = c.z; p < c.w; ++p) {
-        const int k = (int)(klist[p] & ~GPBA_LU_LATE);
-        prod[p] = make_int4((int)(off[(size_t)i * NT + k] / GPBA_TILE), (int)(off[(size_t)j * NT + k] / GPBA_TILE), k, 0);
-      }
-    }
-    CKR(d_cf_prod.upload(prod, stream));
-  }
-  CKR(d_cf_tab.upload(cf_tab, stream)); CKR(d_cf_need.upload(cf_need, stream)); CKR(d_cf_cnt.alloc(3 * (size_t)NT + 1)); CKR(d_cf_d8.alloc((size_t)NT * (GPBA_CF_D8_BYTES / 8)));
-  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns, %zu panel CTAs, %zu update CTAs for %zu tile products\n", chol_parts, n_levels, NT, pan_tab.size(), upd_tab.size(), klist.size());
-  CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
+  cf_tasks = (int)H.cf_tab.size();
+  CKR(d_cf_prod.upload(H.prod, stream));
+  CKR(d_cf_tab.upload(H.cf_tab, stream)); CKR(d_cf_need.upload(H.cf_need, stream)); CKR(d_cf_cnt.alloc(3 * (size_t)NT + 1)); CKR(d_cf_d8.alloc((size_t)NT * (GPBA_CF_D8_BYTES / 8)));
+  if (getenv("GPBA_VERBOSE")) fprintf(stderr, "[gpba] cholesky: %d partitions, %d levels for %d tile columns, %zu panel CTAs, %zu update CTAs for %zu tile products\n", chol_parts, n_levels, NT, H.pan_tab.size(), H.upd_tab.size(), H.klist.size());
+  CK(cudaStreamSynchronize(stream));  // the host tables go out of scope
   if (chol_graph) { cudaGraphExecDestroy(chol_graph); chol_graph = nullptr; }
   if (chol_back_graph) { cudaGraphExecDestroy(chol_back_graph); chol_back_graph = nullptr; }
   return GPBA_OK;
@@ -1908,7 +1963,7 @@ int gpba_create_ex(const gpba_problem* prob, const gpba_create_options* opt, gpb
 int gpba_build_structure(gpba_handle* h, gpba_structure_info* info) {
   NEED(h);
   CKR(S(h).build_structure());
-  if (info) *info = S(h).info;
+  if (info) { CKR(S(h).count_hpl()); *info = S(h).info; }
   return GPBA_OK;
 }
 int gpba_get_hpp_pattern(gpba_handle* h, int32_t* rows, int32_t* cols) {
