@@ -143,7 +143,7 @@ typedef struct gpba_structure_info {
   int32_t n_free_kf;       /* _numPoses                                 */
   int32_t n_active_pt;     /* _numLandmarks                             */
   int64_t n_active_obs;    /* active reprojection edges                 */
-  int64_t n_hpl;           /* #(pose, landmark) blocks of Hpl           */
+  int64_t n_hpl;           /* #(pose, landmark) blocks of Hpl (counted only when `info` is asked for) */
   int32_t n_hpp;           /* #upper blocks of Hpp (incl. diagonal)     */
   int32_t n_hschur;        /* #upper blocks of Hschur (incl. diagonal)  */
 } gpba_structure_info;
