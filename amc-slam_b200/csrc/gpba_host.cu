@@ -2456,6 +2456,72 @@ int gpba_symbolic_analyze(int32_t n_pose, int32_t n_hs, const int32_t* hs_row, c
   if (perm_out) for (int i = 0; i < n_pose; ++i) perm_out[i] = sym.perm[i];
   return GPBA_OK;
 }
+// Host only: build the task list of the persistent factorization for a block pattern and check the invariants its
+// in-kernel waits rely on.  out[0] tasks, out[1] update chunks, out[2] tile products, out[3] panel tasks,
+// out[4] VIOLATIONS (must be 0):
+//   * every product of a chunk reads a source column whose panel tasks ALL sit in front of the chunk in the list;
+//   * every panel task sits behind all chunks that target its column, a solve-only task behind its column's publishing task;
+//   * the completion counts the kernel waits for (chunks per column, panel tasks per column) equal what the list holds;
+//   * every tile referenced by a task or a product exists, every below-diagonal tile has exactly one panel task.
+int gpba_factor_schedule_check(int32_t n_pose, int32_t n_hs, const int32_t* hs_row, const int32_t* hs_col, int64_t out[5]) {
+  if (n_pose < 0 || n_hs < 0 || (n_hs > 0 && (!hs_row || !hs_col)) || !out) { g_err = "invalid argument"; return GPBA_ERR_INVALID; }
+  for (int k = 0; k < n_hs; ++k)
+    if (hs_row[k] < 0 || hs_col[k] < hs_row[k] || hs_col[k] >= n_pose) { g_err = "block index out of range (upper pattern expected)"; return GPBA_ERR_INVALID; }
+  CholHost H;
+  const int rc = chol_host_phase(n_pose, n_hs, hs_row, hs_col, H);
+  if (rc != GPBA_OK) { g_err = H.err; return rc; }
+  const int NT = H.sym.NT;
+  const int64_t n_tiles = H.sym.doubles / GPBA_TILE;
+  int64_t bad = 0, chunks = 0, products = 0, panels = 0;
+  std::vector<int> pan_seen(NT, 0), upd_seen(NT, 0), diag_pos(NT, -1), publishes(NT, 0);
+  std::vector<char> tile_has_task((size_t)std::max<int64_t>(n_tiles, 1), 0);
+  // first pass: position of the last panel task of every column, number of chunks per column
+  std::vector<int> last_panel(NT, -1), last_chunk(NT, -1);
+  for (size_t t = 0; t < H.cf_tab.size(); ++t) {
+    const int4 e = H.cf_tab[t];
+    const int j = e.x & ~GPBA_CF_DIAG;
+    if (j < 0 || j >= NT || e.y < 0 || e.y >= n_tiles) { ++bad; continue; }
+    if (e.z < 0) last_panel[j] = (int)t; else last_chunk[j] = (int)t;
+  }
+  for (size_t t = 0; t < H.cf_tab.size(); ++t) {
+    const int4 e = H.cf_tab[t];
+    const int j = e.x & ~GPBA_CF_DIAG;
+    if (j < 0 || j >= NT || e.y < 0 || e.y >= n_tiles) continue;
+    const bool diag = (e.x & GPBA_CF_DIAG) != 0;
+    if (e.z >= 0) {
+      ++chunks; ++upd_seen[j];
+      if (e.w <= e.z || e.w > (int)H.prod.size()) { ++bad; continue; }
+      if (diag != (H.sym.tile_off[(size_t)j * NT + j] / GPBA_TILE == e.y)) ++bad;
+      for (int p = e.z; p < e.w; ++p) {
+        ++products;
+        const int4 r = H.prod[p];
+        if (r.z < 0 || r.z >= j || r.x < 0 || r.x >= n_tiles || r.y < 0 || r.y >= n_tiles) { ++bad; continue; }
+        if (last_panel[r.z] < 0 || last_panel[r.z] > (int)t) ++bad;                       // the source column is complete in front of the chunk
+        if (H.sym.tile_off[(size_t)j * NT + r.z] / GPBA_TILE != r.y) ++bad;                // second operand: tile (j, k)
+      }
+    } else {
+      ++panels; ++pan_seen[j];
+      if (last_chunk[j] > (int)t) ++bad;                                                   // all updates of the column are in front of its panel tasks
+      if (e.w != H.sym.tile_off[(size_t)j * NT + j] / GPBA_TILE) ++bad;                    // the diagonal tile the task factorizes / reads
+      if (diag) { if (diag_pos[j] >= 0) ++bad; diag_pos[j] = (int)t; if (e.z == -2) publishes[j] = 1; if (e.z == -3) ++bad; }
+      else {
+        if (tile_has_task[e.y]) ++bad;
+        tile_has_task[e.y] = 1;
+        if (e.z == -3 && !(publishes[j] && diag_pos[j] >= 0 && diag_pos[j] < (int)t)) ++bad;   // solve-only: behind the publishing task
+        if (e.z == -1 && publishes[j]) ++bad;                                               // one mode per column
+      }
+    }
+  }
+  for (int j = 0; j < NT; ++j) {
+    const int nr = H.sym.col_begin[j + 1] - H.sym.col_begin[j];
+    if (pan_seen[j] != nr + 1 || H.cf_need[(size_t)NT + j] != nr + 1) ++bad;
+    if (upd_seen[j] != H.cf_need[j]) ++bad;
+    if (diag_pos[j] < 0) ++bad;
+  }
+  if (products != H.products) ++bad;
+  out[0] = (int64_t)H.cf_tab.size(); out[1] = chunks; out[2] = products; out[3] = panels; out[4] = bad;
+  return GPBA_OK;
+}
 int gpba_set_profiling(gpba_handle* h, int enabled) { NEED(h); S(h).collect_events(); S(h).profiling = enabled != 0; return GPBA_OK; }
 void* gpba_get_stream(gpba_handle* h) { return h ? (void*)S(h).stream : nullptr; }
 

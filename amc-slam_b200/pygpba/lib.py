@@ -22,7 +22,7 @@ SYMBOLS = [
     "gpba_optimize", "gpba_download_state", "gpba_edge_chi2", "gpba_edge_errors", "gpba_download_evaluated_state", "gpba_active_robust_chi2", "gpba_outlier_flags",
     "gpba_set_levels", "gpba_set_robust_kernel", "gpba_compute_errors_inactive", "gpba_rejection_rounds",
     "gpba_set_extrinsics", "gpba_get_extrinsics", "gpba_count_camera_observations", "gpba_calibrate_extrinsics",
-    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_symbolic_analyze", "gpba_pose_optimize", "gpba_vel_ransac", "gpba_pose_graph_optimize", "gpba_correct_points",
+    "gpba_stage_stats", "gpba_set_profiling", "gpba_reset_state", "gpba_get_stream", "gpba_schur_stats", "gpba_solver_stats", "gpba_symbolic_analyze", "gpba_factor_schedule_check", "gpba_pose_optimize", "gpba_vel_ransac", "gpba_pose_graph_optimize", "gpba_correct_points",
 ]
 
 
@@ -68,6 +68,17 @@ def symbolic_analyze(n_pose, hs_row, hs_col, nd_depth=-1):
     if rc != 0:
         raise GpbaError(f"gpba_symbolic_analyze: {lib().gpba_last_error().decode()}")
     return perm, dict(tile_columns=out[0], levels=out[1], parts=out[2], tiles=out[3], update_pairs=out[4])
+
+
+def factor_schedule_check(n_pose, hs_row, hs_col):
+    """Host-only: task list of the persistent factorization kernel for a block pattern + its dependency invariants.
+    Returns dict(tasks, chunks, products, panel_tasks, violations)."""
+    r = np.ascontiguousarray(hs_row, np.int32); c = np.ascontiguousarray(hs_col, np.int32)
+    out = (C.c_int64 * 5)()
+    rc = lib().gpba_factor_schedule_check(C.c_int32(n_pose), C.c_int32(len(r)), _p(r), _p(c), out)
+    if rc != 0:
+        raise GpbaError(f"gpba_factor_schedule_check: {lib().gpba_last_error().decode()}")
+    return dict(tasks=out[0], chunks=out[1], products=out[2], panel_tasks=out[3], violations=out[4])
 
 
 def nccl_unique_id():

@@ -405,6 +405,12 @@ int gpba_solver_stats(gpba_handle* h, int64_t out[6]);
  * out[3] non-zero tiles of the factor, out[4] tile pairs of the trailing updates (x 2 * 48^3 = their flops). */
 int gpba_symbolic_analyze(int32_t n_pose, int32_t n_hs, const int32_t* hs_row, const int32_t* hs_col, int32_t nd_depth,
                           int32_t* perm_out, int64_t out[5]);
+/* Host only (no device needed): builds the task list of the persistent factorization kernel for an upper block pattern and
+ * checks what its in-kernel waits rely on -- every task depends only on tasks in front of it in the list (source columns of
+ * a chunk complete before it, all chunks of a column before its panel tasks, solve-only tasks behind the task that publishes
+ * their diagonal factor) and the completion counts match.  out[0] tasks, out[1] update chunks, out[2] tile products,
+ * out[3] panel tasks, out[4] violations (0 for a valid schedule). */
+int gpba_factor_schedule_check(int32_t n_pose, int32_t n_hs, const int32_t* hs_row, const int32_t* hs_col, int64_t out[5]);
 /* cudaStream_t every kernel of this handle is launched on (for CUDA-event timing by the caller). */
 void* gpba_get_stream(gpba_handle* h);
 /* Re-upload estimates only (same structure): lets a benchmark repeat optimize() from the same start. */

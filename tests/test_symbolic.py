@@ -67,3 +67,43 @@ def test_small_windows_keep_the_banded_order_and_bad_input_is_refused():
         gl.symbolic_analyze(4, np.array([0], np.int32), np.array([7], np.int32))     # out of range
     perm, st = gl.symbolic_analyze(0, np.zeros(0, np.int32), np.zeros(0, np.int32))   # empty system
     assert st["tile_columns"] == 1 and st["tiles"] == 1
+
+
+# ---- the task list of the persistent factorization kernel (k_chol_factor): its in-kernel waits are deadlock-free only if every
+# task depends on tasks in FRONT of it in the list (they are claimed in list order by resident CTAs).  Checked on the host.
+SCHEDULE_ENVS = [{}, {"GPBA_CF_SPLIT_MIN": "0"}, {"GPBA_CF_SPLIT_MIN": "1000000"}, {"GPBA_LU_CHUNK": "5", "GPBA_LU_LATE_CHUNK": "0"},
+                 {"GPBA_LU_CHUNK": "1"}, {"GPBA_CHOL_ND_DEPTH": "0"}]
+
+
+def _schedule_in_subprocess(env_extra, n, lap, band):
+    """the chunking / publishing switches are read once per process"""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from test_symbolic import ring_pattern\nfrom pygpba import lib as gl\n"
+            "r, c = ring_pattern(%d, %d, %d)\nprint(json.dumps(gl.factor_schedule_check(%d, r, c)))\n"
+            % (os.path.join(root, "amc-slam_b200"), os.path.join(root, "tests"), n, lap, band, n))
+    env = dict(os.environ); env.update(env_extra)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-1500:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("env", SCHEDULE_ENVS)
+def test_factor_task_list_only_depends_on_earlier_tasks(env):
+    st = _schedule_in_subprocess(env, 999, 500, 20)
+    assert st["violations"] == 0, st
+    assert st["tasks"] == st["chunks"] + st["panel_tasks"] and st["products"] >= st["chunks"] > 0
+    _, sym = gl.symbolic_analyze(999, *ring_pattern(999, 500, 20), int(env.get("GPBA_CHOL_ND_DEPTH", -1)))
+    assert st["panel_tasks"] == sym["tiles"]                            # one panel task per non-zero tile of the factor
+
+
+def test_factor_task_list_small_and_empty_systems():
+    for n, lap, band in ((30, 1000, 29), (5, 1000, 1), (1, 1000, 0)):
+        r, c = ring_pattern(n, lap, band)
+        st = gl.factor_schedule_check(n, r, c)
+        assert st["violations"] == 0 and st["panel_tasks"] >= 1, (n, st)
+    st = gl.factor_schedule_check(0, np.zeros(0, np.int32), np.zeros(0, np.int32))
+    assert st["violations"] == 0
+    with pytest.raises(gl.GpbaError):
+        gl.factor_schedule_check(4, np.array([2], np.int32), np.array([1], np.int32))
