@@ -141,10 +141,12 @@ gpba_window* new_window() {
   }
   if (!w) return new gpba_window();
   w->local = true; w->large = false; w->iterations = 10; w->any_stereo = false;
-  for (auto* v : {&w->cam_intr, &w->cam_Tbc, &w->kf_pose, &w->kf_vel, &w->kf_time, &w->pt_xyz, &w->rec_t, &w->obs_u, &w->obs_v, &w->obs_ur, &w->obs_w}) v->clear();
-  for (auto* v : {&w->kf_fixed, &w->obs_flags}) v->clear();
-  for (auto* v : {&w->rec_kf1, &w->rec_kf2, &w->rec_cam, &w->obs_rec, &w->obs_pt, &w->prior_kf1, &w->prior_kf2, &w->velp_kf, &w->kf_role, &w->cam_obs}) v->clear();
-  for (auto* v : {&w->kf_slot, &w->pt_slot, &w->obs_slot}) v->clear();
+  // the per-observation arrays keep their old length: the emitter resizes them to the new count and overwrites every element,
+  // and a clear() here would make that resize zero-fill ~50 B per observation on one thread first (1 ms at C2)
+  for (auto* v : {&w->cam_intr, &w->cam_Tbc, &w->kf_pose, &w->kf_vel, &w->kf_time, &w->pt_xyz, &w->rec_t}) v->clear();
+  for (auto* v : {&w->kf_fixed}) v->clear();
+  for (auto* v : {&w->rec_kf1, &w->rec_kf2, &w->rec_cam, &w->prior_kf1, &w->prior_kf2, &w->velp_kf, &w->kf_role, &w->cam_obs}) v->clear();
+  for (auto* v : {&w->kf_slot, &w->pt_slot}) v->clear();
   for (auto* v : {&w->kf_id, &w->pt_id}) v->clear();
   return w;
 }
@@ -185,6 +187,14 @@ struct Emitter {
     size_t work = 0;
     for (int ps : pslots) work += m.pts[ps].obs.size();
     const int T = map_threads(work);
+    static const bool timing = std::getenv("GPBA_MAP_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!timing) return;
+      auto t1 = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "    [emit] %-10s %.3f ms (T=%d)\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count(), T);
+      t0 = t1;
+    };
     std::vector<int64_t> offset(np + 1, 0);
     std::vector<std::vector<uint8_t>> used(T, std::vector<uint8_t>(n_kf_w * n_cam, 0));
     // walks one point; calls visit(o, kw, pw) for every edge
@@ -216,6 +226,7 @@ struct Emitter {
         offset[i + 1] = c;
       }
     });
+    lap("count");
     for (size_t i = 0; i < np; ++i) offset[i + 1] += offset[i];
     const size_t n = (size_t)offset[np];
     std::vector<int> rec_of(n_kf_w * n_cam, -1);
@@ -232,22 +243,35 @@ struct Emitter {
       }
     w.obs_u.resize(n); w.obs_v.resize(n); w.obs_ur.resize(n); w.obs_w.resize(n);
     w.obs_rec.resize(n); w.obs_pt.resize(n); w.obs_flags.resize(n); w.obs_slot.resize(n);
+    lap("resize");
     std::vector<std::vector<int32_t>> cam_obs(T, std::vector<int32_t>(n_cam, 0));
     std::vector<uint8_t> stereo_seen(T, 0);
     parallel_chunks(np, T, [&](size_t b, size_t e, int t) {
+      // per-thread tallies live on the thread's stack until the end: the shared arrays sit in one cache line, and a write
+      // per observation from every thread made this pass 4x slower than the copies themselves
+      std::vector<int32_t> cam_local(n_cam, 0);
+      bool stereo_local = false;
+      double *ou = w.obs_u.data(), *ov = w.obs_v.data(), *our = w.obs_ur.data(), *ow = w.obs_w.data();
+      int32_t *orec = w.obs_rec.data(), *opt = w.obs_pt.data();
+      auto* oflags = w.obs_flags.data();
+      auto* oslot = w.obs_slot.data();
+      const int* rec = rec_of.data();
       for (size_t i = b; i < e; ++i) {
         size_t k = (size_t)offset[i];
         walk(m.pts[pslots[i]], [&](const PObs& o, const Kf&, int kw, int) {
           const bool stereo = o.cam == n_cam - 1 && o.ur >= 0;
-          w.obs_u[k] = o.u; w.obs_v[k] = o.v; w.obs_ur[k] = stereo ? o.ur : -1.0; w.obs_w[k] = o.w;
-          w.obs_rec[k] = rec_of[(size_t)kw * n_cam + o.cam]; w.obs_pt[k] = (int32_t)i;
-          w.obs_flags[k] = o.close_flag ? GPBA_OBS_CLOSE : 0; w.obs_slot[k] = o.slot;
-          if (o.cam < n_cam - 1) ++cam_obs[t][o.cam];
-          stereo_seen[t] |= stereo ? 1 : 0;
+          ou[k] = o.u; ov[k] = o.v; our[k] = stereo ? o.ur : -1.0; ow[k] = o.w;
+          orec[k] = rec[(size_t)kw * n_cam + o.cam]; opt[k] = (int32_t)i;
+          oflags[k] = o.close_flag ? GPBA_OBS_CLOSE : 0; oslot[k] = o.slot;
+          if (o.cam < n_cam - 1) ++cam_local[o.cam];
+          stereo_local |= stereo;
           ++k;
         });
       }
+      for (int c = 0; c < n_cam; ++c) cam_obs[t][c] = cam_local[c];
+      stereo_seen[t] = stereo_local ? 1 : 0;
     });
+    lap("fill");
     for (int t = 0; t < T; ++t) {
       for (int c = 0; c < n_cam; ++c) w.cam_obs[c] += cam_obs[t][c];
       w.any_stereo |= stereo_seen[t] != 0;
@@ -559,7 +583,13 @@ int gpba_map_local_window(gpba_map* m, int64_t kf_id, int32_t large, const int64
   }
   lap("select");
   const size_t maxFixKF = 50;                                           // :815-836
-  for (int ps : lpts) {
+  // sequential by definition (a point adds at most the first keyframe nobody has marked yet), and a pointer chase: every
+  // point's observation list is its own heap block.  The loads are prefetched two hops ahead (point header, then list).
+  const size_t nl = lpts.size();
+  for (size_t li = 0; li < nl; ++li) {
+    if (li + 16 < nl) __builtin_prefetch(&m->pts[lpts[li + 16]]);
+    if (li + 8 < nl) __builtin_prefetch(m->pts[lpts[li + 8]].obs.data());
+    const int ps = lpts[li];
     const Pt& p = m->pts[ps];
     int last_kf = -1;
     for (const PObs& o : p.obs) {
