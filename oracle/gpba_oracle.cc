@@ -1394,6 +1394,37 @@ void oracle_prior_eval(const double* T1, const double* v1, double t1, const doub
   prior_error(f1, f2, err12);
   if (Ji144) { M12 Ji, Jj; prior_jacobian(f1, f2, &Ji, &Jj); std::memcpy(Ji144, Ji.a, 144 * 8); std::memcpy(Jj144, Jj.a, 144 * 8); }
 }
+// EdgeVelReproj on one match (vel_ransac.h): error (2) and Jacobian (2 x 6) wrt the body velocity
+void oracle_vel_edge_eval(const double* Tlast7, const double* Tbc7, const double* intr, double dt, const double* vel,
+                          const double* Xw, const double* obs2, double* err2, double* J12) {
+  gpba_vel_batch B;
+  std::memset(&B, 0, sizeof(B));
+  const int32_t cam0 = 0;
+  const double w = 1.0;
+  B.n_cam = 1; B.cam_intr = intr; B.cam_Tbc = Tbc7; B.cam_dt = &dt;
+  std::memcpy(B.last_pose, Tlast7, 56);
+  B.n_match = 1; B.obs_u = obs2; B.obs_v = obs2 + 1; B.obs_inv_sigma2 = &w; B.obs_xw = Xw; B.obs_cam = &cam0;
+  B.huber_delta = 1.0;
+  VelHypothesis H(&B);
+  H.error(0, v6(vel), err2);
+  double J[2][6];
+  H.jacobian(0, v6(vel), J);
+  std::memcpy(J12, J, sizeof(J));
+}
+// PoseVelocity::Update as the pose-only path applies it (pose_only.h), same arithmetic as Oracle::oplus
+void oracle_posevel_update(const double* T7, const double* v, const double* upd12, double* T7_out, double* v_out) {
+  KfState s;
+  s.Twb = se3_from7(T7); s.vel = v6(v); s.time = 0;
+  PoseOnlyFrame::oplus(s, upd12);
+  se3_to7(s.Twb, T7_out);
+  std::memcpy(v_out, s.vel.a, 48);
+}
+// RightJacobianSO3 as ORB-SLAM3 writes it (G2oTypes.cc:573-590), used by EdgeExtrinsicPrior
+void oracle_right_jacobian_so3_orb(const double* w3, double* out9) {
+  V3 w; w[0] = w3[0]; w[1] = w3[1]; w[2] = w3[2];
+  const M3 J = RightJacobianSO3_orb(w);
+  for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) out9[3 * i + k] = J(i, k);
+}
 void oracle_huber(double delta, double e, double* rho3) { Huber h; h.setDelta(delta); h.robustify(e, rho3); }
 int oracle_ldlt_dense(int n, const double* A, const double* b, double* x) {
   std::vector<double> M(A, A + (size_t)n * n);

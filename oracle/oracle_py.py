@@ -19,7 +19,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libgpba_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("gpba_oracle.cc", "gp_edges.h", "lie.h", "pose_only.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("gpba_oracle.cc", "gp_edges.h", "lie.h", "pose_only.h", "vel_ransac.h", "pose_graph.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -280,6 +280,24 @@ def prior_eval(T1, v1, t1, T2, v2, t2):
     lib().oracle_prior_eval(_p(_d(T1)), _p(_d(v1)), C.c_double(t1), _p(_d(T2)), _p(_d(v2)), C.c_double(t2), _p(e),
                             _p(Ji), _p(Jj))
     return e, Ji, Jj
+
+
+def vel_edge_eval(Tlast, Tbc, intr, dt, vel, Xw, obs2):
+    """EdgeVelReproj on one match: error (2), Jacobian (2 x 6)."""
+    e = np.zeros(2); J = np.zeros((2, 6))
+    lib().oracle_vel_edge_eval(_p(_d(Tlast)), _p(_d(Tbc)), _p(_d(intr)), C.c_double(dt), _p(_d(vel)), _p(_d(Xw)), _p(_d(obs2)),
+                               _p(e), _p(J))
+    return e, J
+
+
+def posevel_update(T7, v, upd12):
+    To = np.zeros(7); vo = np.zeros(6)
+    lib().oracle_posevel_update(_p(_d(T7)), _p(_d(v)), _p(_d(upd12)), _p(To), _p(vo))
+    return To, vo
+
+
+def right_jacobian_so3_orb(w):
+    o = np.zeros((3, 3)); lib().oracle_right_jacobian_so3_orb(_p(_d(w)), _p(o)); return o
 
 
 def huber(delta, e):

@@ -1,0 +1,148 @@
+"""TEST INFRASTRUCTURE: ctypes access to oracle/_ref/libamc_ref_edges.so -- the reference's own src/Pose3utils.cc,
+src/GaussianProcess.cc and src/G2oTypes.cc compiled unmodified against the stand-in headers in oracle/ref_shim/
+(oracle/Makefile target _ref, entry points in oracle/ref_pin.cc).  Only tests/ and tests/golden/make_golden_ref.py use it.
+The library exists only where /root/reference does (this container, not the GPU box); `available()` says which.
+Conventions as oracle_py: poses [qx qy qz qw tx ty tz], matrices row-major, tangent [translation, rotation]."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libamc_ref_edges.so")
+REFERENCE = "/root/reference"
+_LIB = None
+
+
+def build(force=False):
+    """Compile oracle/_ref when the reference sources are present; returns the path or None."""
+    if not os.path.isdir(os.path.join(REFERENCE, "src")):
+        return _SO if os.path.exists(_SO) else None
+    if force and os.path.exists(_SO):
+        os.remove(_SO)
+    subprocess.check_call(["make", "-C", _HERE, "-s", "_ref"])
+    return _SO
+
+
+def available():
+    return os.path.exists(_SO) or os.path.isdir(os.path.join(REFERENCE, "src"))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = build()
+        if so is None:
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        _LIB = C.CDLL(so)
+        for n in ("ref_query_pose", "ref_edge_eval", "ref_edge_ext_eval", "ref_pose_edge_eval"):
+            getattr(_LIB, n).restype = C.c_int
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _f(x):
+    return C.c_double(float(x))
+
+
+def jac_pose3(xi, which):
+    o = np.zeros((6, 6)); lib().ref_jac_pose3(_p(_d(xi)), int(which), _p(o)); return o
+
+
+def jac_small(xi, which):
+    """0 LeftJacobianPose3Q, 1 LeftJacobianRot3(xi[3:]), 2 LeftJacobianRot3Inv(xi[3:])."""
+    o = np.zeros((3, 3)); lib().ref_jac_small(_p(_d(xi)), int(which), _p(o)); return o
+
+
+def circle_dot(p3):
+    o = np.zeros((4, 6)); lib().ref_circle_dot(_p(_d(p3)), _p(o)); return o
+
+
+def so3_helper(w, which):
+    """0 RightJacobianSO3, 1 InverseRightJacobianSO3, 2 ExpSO3, 3 Skew (src/G2oTypes.cc:514-599)."""
+    o = np.zeros((3, 3)); lib().ref_so3_helper(_p(_d(w)), int(which), _p(o)); return o
+
+
+def log_so3(R):
+    o = np.zeros(3); lib().ref_log_so3(_p(_d(R)), _p(o)); return o
+
+
+def query_pose(qc, T1, T2, v1, v2, t1, t2, t):
+    o = np.zeros(7); A = np.zeros((6, 12)); P = np.zeros((6, 12)); dT = np.zeros(7); xi = np.zeros(6)
+    same = lib().ref_query_pose(_p(_d(qc)), _p(_d(T1)), _p(_d(T2)), _p(_d(v1)), _p(_d(v2)), _f(t1), _f(t2), _f(t), _p(o), _p(A),
+                                _p(P), _p(dT), _p(xi))
+    return o, A, P, dT, xi, bool(same)
+
+
+def gp_matrices(qc, dt, t1, t2):
+    a = np.zeros((12, 12)); b = np.zeros((12, 12)); c = np.zeros((12, 12))
+    lib().ref_gp_matrices(_p(_d(qc)), _f(dt), _f(t1), _f(t2), _p(a), _p(b), _p(c))
+    return a, b, c
+
+
+def edge_eval(qc, gp, T1, v1, t1, T2, v2, t2, t, Tbc, intr, bf, Xw, obs3):
+    dim = 3 if obs3[2] >= 0 else 2
+    err = np.zeros(3); J1 = np.zeros((dim, 12)); J2 = np.zeros((dim, 12)); Jp = np.zeros((dim, 3))
+    depth = lib().ref_edge_eval(_p(_d(qc)), int(gp), _p(_d(T1)), _p(_d(v1)), _f(t1), _p(_d(T2)), _p(_d(v2)), _f(t2), _f(t),
+                                _p(_d(Tbc)), _p(_d(intr)), _f(bf), _p(_d(Xw)), _p(_d(obs3)), _p(err), _p(J1), _p(J2), _p(Jp))
+    return err[:dim], J1, J2, Jp, depth
+
+
+def edge_ext_eval(qc, T1, v1, t1, T2, v2, t2, t, Tbc, intr, bf, Xw, obs2):
+    err = np.zeros(2); J1 = np.zeros((2, 12)); J2 = np.zeros((2, 12)); Jp = np.zeros((2, 3)); Je = np.zeros((2, 6))
+    depth = lib().ref_edge_ext_eval(_p(_d(qc)), _p(_d(T1)), _p(_d(v1)), _f(t1), _p(_d(T2)), _p(_d(v2)), _f(t2), _f(t),
+                                    _p(_d(Tbc)), _p(_d(intr)), _f(bf), _p(_d(Xw)), _p(_d(obs2)), _p(err), _p(J1), _p(J2), _p(Jp),
+                                    _p(Je))
+    return err, J1, J2, Jp, Je, depth
+
+
+def pose_edge_eval(qc, gp, T1, v1, t1, T2, v2, t2, t, Tbc, intr, bf, Xw, obs3):
+    dim = 3 if obs3[2] >= 0 else 2
+    err = np.zeros(3); J1 = np.zeros((dim, 12)); J2 = np.zeros((dim, 12))
+    depth = lib().ref_pose_edge_eval(_p(_d(qc)), int(gp), _p(_d(T1)), _p(_d(v1)), _f(t1), _p(_d(T2)), _p(_d(v2)), _f(t2), _f(t),
+                                     _p(_d(Tbc)), _p(_d(intr)), _f(bf), _p(_d(Xw)), _p(_d(obs3)), _p(err), _p(J1), _p(J2))
+    return err[:dim], J1, J2, depth
+
+
+def prior_eval(T1, v1, t1, T2, v2, t2):
+    e = np.zeros(12); Ji = np.zeros((12, 12)); Jj = np.zeros((12, 12))
+    lib().ref_prior_eval(_p(_d(T1)), _p(_d(v1)), _f(t1), _p(_d(T2)), _p(_d(v2)), _f(t2), _p(e), _p(Ji), _p(Jj))
+    return e, Ji, Jj
+
+
+def ext_prior_eval(q_ini, Tbc):
+    e = np.zeros(3); J = np.zeros((3, 6)); lib().ref_ext_prior_eval(_p(_d(q_ini)), _p(_d(Tbc)), _p(e), _p(J)); return e, J
+
+
+def velocity_edge_eval(T7, v):
+    e = np.zeros(1); J = np.zeros((1, 12)); lib().ref_velocity_edge_eval(_p(_d(T7)), _p(_d(v)), _p(e), _p(J)); return e, J
+
+
+def vel_edge_eval(Tlast, Tbc, intr, dt, vel, Xw, obs2):
+    e = np.zeros(2); J = np.zeros((2, 6))
+    lib().ref_vel_edge_eval(_p(_d(Tlast)), _p(_d(Tbc)), _p(_d(intr)), _f(dt), _p(_d(vel)), _p(_d(Xw)), _p(_d(obs2)), _p(e), _p(J))
+    return e, J
+
+
+def posevel_update(T7, v, upd12):
+    To = np.zeros(7); vo = np.zeros(6); lib().ref_posevel_update(_p(_d(T7)), _p(_d(v)), _p(_d(upd12)), _p(To), _p(vo)); return To, vo
+
+
+def extrinsic_update(Tbc, upd6):
+    To = np.zeros(7); lib().ref_extrinsic_update(_p(_d(Tbc)), _p(_d(upd6)), _p(To)); return To
+
+
+def standin_se3_exp(xi):
+    o = np.zeros(7); lib().ref_standin_se3_exp(_p(_d(xi)), _p(o)); return o
+
+
+def standin_se3_log(T7):
+    o = np.zeros(6); lib().ref_standin_se3_log(_p(_d(T7)), _p(o)); return o

@@ -1,0 +1,149 @@
+"""Mints tests/golden/ref_edges.npz from the REFERENCE'S OWN edge code.
+
+oracle/_ref/libamc_ref_edges.so is the reference's src/Pose3utils.cc, src/GaussianProcess.cc and src/G2oTypes.cc compiled
+unmodified (oracle/Makefile target _ref, stand-in headers oracle/ref_shim/, entry points oracle/ref_pin.cc).  This script
+runs it on seeded inputs and stores inputs and outputs; tests/test_ref_pin.py replays the inputs through the oracle
+restatement.  Needs /root/reference, so it runs in the build container only; the .npz travels.
+
+    python tests/golden/make_golden_ref.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+N_CASES = 40
+SEED = 20261019
+
+
+def unit_pose(rng, scale_t, scale_r):
+    """A pose built without any library exp: random unit quaternion by axis-angle, translation."""
+    axis = rng.normal(size=3); axis /= np.linalg.norm(axis)
+    ang = rng.normal() * scale_r
+    q = np.append(axis * np.sin(ang / 2), np.cos(ang / 2))
+    return np.concatenate([q, rng.normal(size=3) * scale_t])
+
+
+def quat_mul(a, b):
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def quat_rot(q, p):
+    v = q[:3]; uv = 2 * np.cross(v, p)
+    return p + q[3] * uv + np.cross(v, uv)
+
+
+def compose(A, B):
+    q = quat_mul(A[:4], B[:4]); q /= np.linalg.norm(q)
+    return np.concatenate([q, A[4:] + quat_rot(A[:4], B[4:])])
+
+
+def make_inputs(seed=SEED, n=N_CASES):
+    """Inputs of every probe, one row per case.  The relative motion between the two keyframes cycles through ordinary
+    (0.2), small (1e-3), below the 1e-5 series threshold of LeftJacobianPose3Q (1e-7), pure translation, and large (2.5 rad);
+    the query time cycles through interior points and both ends of the interval."""
+    rng = np.random.default_rng(seed)
+    I = {k: [] for k in ("qc", "T1", "T2", "v1", "v2", "t1", "t2", "t", "Tbc", "intr", "bf", "Xw", "obs_mono", "obs_stereo", "xi",
+                         "q_ini", "upd12", "Tlast", "dt_cam", "vel", "Xw_vel", "obs_vel", "w3")}
+    rel_scales = [0.2, 1e-3, 1e-7, 0.0, 2.5]
+    for c in range(n):
+        rs = rel_scales[c % len(rel_scales)]
+        T1 = unit_pose(rng, 3.0, 1.0)
+        rel = unit_pose(rng, 0.3, rs)
+        T2 = compose(T1, rel)
+        v1 = np.concatenate([rng.normal(size=3), rng.normal(size=3) * 0.3]); v2 = v1 + rng.normal(size=6) * 0.1
+        t1 = rng.uniform(0, 10); t2 = t1 + rng.uniform(0.05, 0.5)
+        t = [t1 + rng.uniform(0.1, 0.9) * (t2 - t1), t1, t2][(c // len(rel_scales)) % 3]
+        Tbc = unit_pose(rng, 0.5, 0.6)
+        Tbc[4:] = np.float32(Tbc[4:])
+        intr = np.array([rng.uniform(400, 600), rng.uniform(400, 600), rng.uniform(300, 340), rng.uniform(220, 260)])
+        bf = rng.uniform(20, 60)
+        # a landmark a few metres in front of the camera near the second keyframe; float-representable because the
+        # pose-only edges take Eigen::Vector3f (include/G2oTypes.h:190,223,250)
+        Xc = np.array([rng.normal(), rng.normal(), rng.uniform(3, 12)])
+        Xw = np.float32(compose(compose(T2, Tbc), np.concatenate([[0, 0, 0, 1], Xc]))[4:]).astype(np.float64)
+        I["qc"].append(rng.uniform(0.3, 3.0, size=6)); I["T1"].append(T1); I["T2"].append(T2); I["v1"].append(v1); I["v2"].append(v2)
+        I["t1"].append(t1); I["t2"].append(t2); I["t"].append(t); I["Tbc"].append(Tbc); I["intr"].append(intr); I["bf"].append(bf)
+        I["Xw"].append(Xw)
+        I["obs_mono"].append(np.array([rng.uniform(0, 640), rng.uniform(0, 480), -1.0]))
+        I["obs_stereo"].append(np.array([rng.uniform(0, 640), rng.uniform(0, 480), rng.uniform(0, 600)]))
+        xi_scale = [1.0, 1e-7, 1e-3, 3.0][c % 4]
+        I["xi"].append(np.concatenate([rng.normal(size=3), rng.normal(size=3) * xi_scale]))
+        I["q_ini"].append(unit_pose(rng, 0, 0.6)[:4])
+        I["upd12"].append(rng.normal(size=12) * [0.1, 1e-8, 1.0][c % 3])
+        Tlast = unit_pose(rng, 3.0, 1.0)
+        vel = np.concatenate([rng.normal(size=3), rng.normal(size=3) * 0.3]) * [1.0, 1e-6][c % 2]
+        I["Tlast"].append(Tlast); I["dt_cam"].append(rng.uniform(-0.1, 0.1)); I["vel"].append(vel)
+        Xc2 = np.array([rng.normal(), rng.normal(), rng.uniform(3, 12)])
+        I["Xw_vel"].append(compose(compose(Tlast, Tbc), np.concatenate([[0, 0, 0, 1], Xc2]))[4:])
+        I["obs_vel"].append(np.array([rng.uniform(0, 640), rng.uniform(0, 480)]))
+        I["w3"].append(rng.normal(size=3) * [1.0, 1e-7, 2.5][c % 3])
+    return {k: np.array(v) for k, v in I.items()}
+
+
+def run_reference(I):
+    import ref_py as R
+    n = len(I["t"])
+    out = {}
+
+    def put(k, c, v):
+        v = np.asarray(v, dtype=np.float64)
+        out.setdefault(k, np.zeros((n,) + v.shape))[c] = v
+    for c in range(n):
+        g = {k: I[k][c] for k in I}
+        for w in range(5):
+            put("jac_pose3_%d" % w, c, R.jac_pose3(g["xi"], w))
+        for w in range(3):
+            put("jac_small_%d" % w, c, R.jac_small(g["xi"], w))
+        put("circle_dot", c, R.circle_dot(g["Xw"]))
+        put("so3_rj", c, R.so3_helper(g["w3"], 0)); put("so3_rj_inv", c, R.so3_helper(g["w3"], 1))
+        Tq, A, P, dT, xi12, same = R.query_pose(g["qc"], g["T1"], g["T2"], g["v1"], g["v2"], g["t1"], g["t2"], g["t"])
+        assert same, "the two QueryPose overloads of the reference disagree"
+        put("query_T", c, Tq); put("query_At1", c, A); put("query_Pt1", c, P); put("query_dT", c, dT); put("query_xi12", c, xi12)
+        Qi, QiInv, Phi = R.gp_matrices(g["qc"], g["t2"] - g["t1"], g["t1"], g["t2"])
+        put("gp_Qi", c, Qi); put("gp_QiInv", c, QiInv); put("gp_Phi", c, Phi)
+        args = (g["T1"], g["v1"], g["t1"], g["T2"], g["v2"], g["t2"], g["t"], g["Tbc"], g["intr"], g["bf"], g["Xw"])
+        for gp in (1, 0):
+            for name, obs in (("mono", g["obs_mono"]), ("stereo", g["obs_stereo"])):
+                e, J1, J2, Jp, depth = R.edge_eval(g["qc"], gp, *args, obs)
+                k = "edge_%s_%s_" % ("gp" if gp else "sync", name)
+                put(k + "err", c, e); put(k + "J1", c, J1); put(k + "J2", c, J2); put(k + "Jp", c, Jp); put(k + "depth", c, depth)
+                if not (gp and name == "stereo"):   # the reference has no stereo GP pose-only edge
+                    e, J1, J2, depth = R.pose_edge_eval(g["qc"], gp, *args, obs)
+                    k = "pose_%s_%s_" % ("gp" if gp else "sync", name)
+                    put(k + "err", c, e); put(k + "J1", c, J1); put(k + "J2", c, J2)
+        e, J1, J2, Jp, Je, depth = R.edge_ext_eval(g["qc"], *args, g["obs_mono"][:2])
+        put("ext_err", c, e); put("ext_J1", c, J1); put("ext_J2", c, J2); put("ext_Jp", c, Jp); put("ext_Jext", c, Je)
+        put("ext_depth", c, depth)
+        e, Ji, Jj = R.prior_eval(g["T1"], g["v1"], g["t1"], g["T2"], g["v2"], g["t2"])
+        put("prior_err", c, e); put("prior_Ji", c, Ji); put("prior_Jj", c, Jj)
+        e, J = R.ext_prior_eval(g["q_ini"], g["Tbc"])
+        put("extprior_err", c, e); put("extprior_J", c, J)
+        e, J = R.velocity_edge_eval(g["T1"], g["v1"])
+        put("velocity_err", c, e); put("velocity_J", c, J)
+        e, J = R.vel_edge_eval(g["Tlast"], g["Tbc"], g["intr"], g["dt_cam"], g["vel"], g["Xw_vel"], g["obs_vel"])
+        put("veledge_err", c, e); put("veledge_J", c, J)
+        To, vo = R.posevel_update(g["T1"], g["v1"], g["upd12"])
+        put("update_T", c, To); put("update_v", c, vo)
+        put("update_Tbc", c, R.extrinsic_update(g["Tbc"], g["upd12"][:6]))
+    return out
+
+
+def main():
+    import ref_py as R
+    assert R.build(force=True), "needs /root/reference"
+    I = make_inputs()
+    out = run_reference(I)
+    path = os.path.join(HERE, "ref_edges.npz")
+    np.savez_compressed(path, seed=SEED, **{"in_" + k: v for k, v in I.items()}, **{"ref_" + k: v for k, v in out.items()})
+    print("wrote %s: %d cases, %d reference arrays, %.0f kB" % (path, len(I["t"]), len(out), os.path.getsize(path) / 1e3))
+
+
+if __name__ == "__main__":
+    main()
