@@ -14,6 +14,7 @@
 // (Eigen), quaternion algebra and SE(3) exp/log/Adj (Sophus), the pinhole projection (Pinhole.cpp:35-41, 71-81 restated below).
 #include <cstring>
 #include "G2oTypes.h"
+#include "Thirdparty/g2o/g2o/core/robust_kernel_impl.h"
 
 using namespace ORB_SLAM3;
 typedef Eigen::Matrix<double, 6, 1> V6;
@@ -295,6 +296,14 @@ void ref_extrinsic_update(const double* Tbc7, const double* upd6, double* T7_out
   VertexExtrinsic ve(from7(Tbc7));
   ve.oplus(upd6);
   to7(ve.estimate(), T7_out);
+}
+// RobustKernelHuber (Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp:65-91, the reference's own file): rho, rho', rho''
+void ref_huber(double delta, double e, double* rho3) {
+  g2o::RobustKernelHuber k;
+  k.setDelta(delta);
+  Eigen::Vector3d rho;
+  k.robustify(e, rho);
+  out(rho, rho3);
 }
 // stand-in arithmetic, exported so the tests can state how far the stand-in Lie layer is from the oracle's
 void ref_standin_se3_exp(const double* xi, double* out7) { to7(Sophus::SE3d::exp(v6(xi)), out7); }

@@ -19,8 +19,10 @@ def build(force=False):
     """Compile oracle/_ref when the reference sources are present; returns the path or None."""
     if not os.path.isdir(os.path.join(REFERENCE, "src")):
         return _SO if os.path.exists(_SO) else None
-    if force and os.path.exists(_SO):
-        os.remove(_SO)
+    if force:
+        for so in (_SO, os.path.join(_HERE, "_ref", "libg2o_ref_lm.so")):
+            if os.path.exists(so):
+                os.remove(so)
     subprocess.check_call(["make", "-C", _HERE, "-s", "_ref"])
     return _SO
 
@@ -146,3 +148,34 @@ def standin_se3_exp(xi):
 
 def standin_se3_log(T7):
     o = np.zeros(6); lib().ref_standin_se3_log(_p(_d(T7)), _p(o)); return o
+
+
+# ---- the reference's Levenberg-Marquardt controller on the oracle's level-1 steps (oracle/ref_lm_pin.cc) ---------------
+_LM_SO = os.path.join(_HERE, "_ref", "libg2o_ref_lm.so")
+_LM = None
+
+
+def lm_lib():
+    global _LM
+    if _LM is None:
+        if build() is None or not os.path.exists(_LM_SO):
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        import oracle_py
+        oracle_py.lib()                      # libgpba_oracle.so first: libg2o_ref_lm.so resolves the oracle_* symbols from it
+        _LM = C.CDLL(_LM_SO)
+        _LM.ref_lm_optimize.restype = C.c_int
+    return _LM
+
+
+def lm_optimize(oracle, iters, lambda_init, max_trials=0):
+    """g2o's OptimizationAlgorithmLevenberg::solve (compiled from the reference) inside SparseOptimizer::optimize's loop,
+    on an oracle_py.Oracle instance.  Returns (trace, every chi2 the controller read)."""
+    from pygpba.problem import LmTrace
+    tr = LmTrace(); log = np.zeros(4096); n = C.c_int()
+    lm_lib().ref_lm_optimize(oracle.h, int(iters), _f(lambda_init), int(max_trials), None, C.byref(tr), _p(log), len(log), C.byref(n))
+    return tr, log[:n.value].copy()
+
+
+def huber(delta, e):
+    """RobustKernelHuber::robustify compiled from the reference's g2o (robust_kernel_impl.cpp:65-91)."""
+    r = np.zeros(3); lib().ref_huber(_f(delta), _f(e), _p(r)); return r

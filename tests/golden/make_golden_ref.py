@@ -135,13 +135,79 @@ def run_reference(I):
     return out
 
 
+# (problem, lambda_init (0 = computeLambdaInit), noise on the start [m], maxTrialsAfterFailure, seed, outlier fraction):
+# plain runs, the tau * max-diagonal start, runs with up to 8 rejected trials in one iteration, termination by the trial limit
+# and by the three-bad-iterations rule
+LM_CASES = [("tiny", 1.0, 0.0, 10, 0, None), ("tiny", 0.0, 0.0, 10, 0, None), ("tiny_global", 1e-5, 0.0, 10, 0, None),
+            ("tiny_global", 0.0, 0.3, 10, 0, None), ("c1", 1.0, 0.0, 10, 0, None), ("loop", 1e-5, 0.0, 10, 0, None),
+            ("tiny", 1e-8, 3.0, 10, 0, None), ("tiny", 1.0, 3.0, 10, 0, None), ("tiny", 1e-10, 3.0, 2, 0, None),
+            ("tiny_global", 1e-10, 5.0, 2, 0, None), ("c1", 1e-8, 1.0, 10, 0, 0.3), ("tiny", 1e-10, 10.0, 3, 3, None)]
+LM_ITERS = 10
+
+
+def lm_case_oracles(case, n=2):
+    """n oracle instances of one LM case at the same perturbed start (the perturbation is part of the case)."""
+    sys.path.insert(0, os.path.join(ROOT, "amc-slam_b200"))
+    import oracle_py as O
+    from pygpba import synth
+    name, lam, noise, max_trials, seed, outliers = case
+    P = synth.make_problem(name, **({} if outliers is None else dict(outliers=outliers)))
+    P.lambda_init = lam
+    rng = np.random.default_rng(seed)
+    out = [O.Oracle(P) for _ in range(n)]
+    kp, kv, pt = out[0].state()
+    pt2 = pt + rng.normal(size=pt.shape) * noise
+    kp2 = kp.copy(); kp2[:, 4:] += rng.normal(size=(len(kp), 3)) * noise * 0.2
+    for o in out:
+        o.L.oracle_reset_state(o.h, O._p(kp2), O._p(kv), O._p(pt2))
+    return out
+
+
+def run_reference_lm():
+    import ref_py as R
+    res = {}
+    for i, case in enumerate(LM_CASES):
+        (o,) = lm_case_oracles(case, 1)
+        tr, log = R.lm_optimize(o, LM_ITERS, case[1], case[3])
+        s = tr.summary()
+        res["lm%d_trials" % i] = np.array(s["trials"], np.int32)
+        res["lm%d_result" % i] = np.int32(s["result"])
+        for k in ("chi2_before", "chi2_after", "lam"):
+            res["lm%d_%s" % (i, k)] = np.array(s[k])
+        res["lm%d_last_trial_chi2" % i] = np.float64(s["last_trial_chi2"])
+        res["lm%d_chi2_log" % i] = log
+        res["lm%d_pose" % i] = o.state()[0]
+    return res
+
+
+# Huber deltas of the path (Optimizer.cc: sqrt(5.991) mono, sqrt(7.815) stereo, sqrt(21.026) priors in global BA) and chi2
+# values on both sides of delta^2, including the doubles next to the FLOAT-rounded threshold (robust_kernel_impl.h:84)
+HUBER_DELTAS = [np.sqrt(5.991), np.sqrt(7.815), np.sqrt(21.026), 1.0, 2.5]
+
+
+def huber_inputs():
+    rows = []
+    for d in HUBER_DELTAS:
+        f = float(np.float32(d * d))
+        for e in (0.0, 0.5 * f, np.nextafter(f, 0), f, np.nextafter(f, np.inf), d * d, 1.5 * f, 10 * f, 1e4 * f):
+            rows.append((d, e))
+    return np.array(rows)
+
+
 def main():
     import ref_py as R
     assert R.build(force=True), "needs /root/reference"
+    lm = run_reference_lm()
+    path = os.path.join(HERE, "ref_lm_traces.npz")
+    np.savez_compressed(path, **lm)
+    print("wrote %s: %d LM cases, %.0f kB" % (path, len(LM_CASES), os.path.getsize(path) / 1e3))
     I = make_inputs()
     out = run_reference(I)
     path = os.path.join(HERE, "ref_edges.npz")
-    np.savez_compressed(path, seed=SEED, **{"in_" + k: v for k, v in I.items()}, **{"ref_" + k: v for k, v in out.items()})
+    hub = huber_inputs()
+    out["huber"] = np.array([R.huber(d, e) for d, e in hub])
+    np.savez_compressed(path, seed=SEED, huber_in=hub, **{"in_" + k: v for k, v in I.items()},
+                        **{"ref_" + k: v for k, v in out.items()})
     print("wrote %s: %d cases, %d reference arrays, %.0f kB" % (path, len(I["t"]), len(out), os.path.getsize(path) / 1e3))
 
 

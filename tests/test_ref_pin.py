@@ -105,6 +105,18 @@ def test_oracle_matches_reference_code_on_golden_vectors(oracle_mod):
         check_case(oracle_mod, g, lambda name: Z["ref_" + name][c], "case %d" % c)
 
 
+def test_huber_kernel_matches_reference_code(oracle_mod):
+    """RobustKernelHuber from the reference's g2o, float-typed dsqr included: equal, not close."""
+    Z = np.load(GOLDEN)
+    mod = _golden_mod()
+    assert np.array_equal(Z["huber_in"], mod.huber_inputs())
+    inl = 0
+    for (d, e), rho in zip(Z["huber_in"], Z["ref_huber"]):
+        assert np.array_equal(oracle_mod.huber(d, e), rho), (d, e)
+        inl += rho[1] == 1.0
+    assert 0 < inl < len(Z["ref_huber"])
+
+
 def test_golden_covers_the_branches():
     """The fixture exercises both sides of the thresholds the closed forms switch on."""
     Z = np.load(GOLDEN)
@@ -146,3 +158,58 @@ def test_standin_lie_layer_agrees_with_the_oracle(oracle_mod):
         T = oracle_mod.se3_exp(xi)
         close(R.standin_se3_exp(xi), T, "exp", 1e-14)
         close(R.standin_se3_log(T), oracle_mod.se3_log(T), "log", 1e-13)
+
+
+# ---- the Levenberg-Marquardt controller ----------------------------------------------------------------
+# oracle/_ref/libg2o_ref_lm.so is the reference's Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp (with
+# optimization_algorithm_with_hessian.cpp, optimization_algorithm.cpp, solver.cpp, stuff/property.cpp ...) compiled
+# unmodified; oracle/ref_lm_pin.cc gives it a g2o::Solver and a SparseOptimizer made of the oracle's level-1 steps.  The
+# linear algebra is then the same code on both sides, so the traces must be EQUAL, not close.
+
+def _golden_mod():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_ref", os.path.join(HERE, "golden", "make_golden_ref.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    return mod
+
+
+def test_oracle_lm_controller_equals_reference_controller_live(oracle_mod):
+    import ref_py as R
+    if not R.available():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent (GPU box)")
+    from pygpba.problem import LmParams
+    import ctypes as C
+    mod = _golden_mod()
+    seen_rejections = seen_trial_limit = seen_bad_stop = 0
+    for case in mod.LM_CASES:
+        a, b = mod.lm_case_oracles(case, 2)
+        prm = LmParams(); a.L.oracle_default_lm_params(C.byref(prm)); prm.max_trials_after_failure = case[3]
+        sa = a.optimize(mod.LM_ITERS, prm).summary()
+        tb, log = R.lm_optimize(b, mod.LM_ITERS, case[1], case[3])
+        sb = tb.summary()
+        assert sa == sb, (case, sa, sb)                      # iterations, trials, chi2 before / after, lambda, result: bit for bit
+        for x, y in zip(a.state(), b.state()):
+            assert np.array_equal(x, y), case
+        assert len(log) == sa["n_iters"] + sa["total_trials"]   # one chi2 per linearisation and one per trial
+        seen_rejections += max(sa["trials"]) > 2
+        seen_trial_limit += sa["result"] == 2 and sa["trials"][-1] == case[3]
+        seen_bad_stop += sa["result"] == 2 and sa["trials"][-1] < case[3]
+    assert seen_rejections >= 2 and seen_trial_limit >= 2 and seen_bad_stop >= 2   # the cases reach every exit of solve()
+
+
+def test_oracle_lm_controller_matches_reference_traces_golden(oracle_mod):
+    """The same comparison against the committed traces (runs everywhere).  Equal iteration / trial counts and result; the
+    chi2 and lambda values within 1e-9 relative: the stored numbers went through this container's build of the oracle."""
+    from pygpba.problem import LmParams
+    import ctypes as C
+    mod = _golden_mod()
+    Z = np.load(os.path.join(HERE, "golden", "ref_lm_traces.npz"))
+    for i, case in enumerate(mod.LM_CASES):
+        (a,) = mod.lm_case_oracles(case, 1)
+        prm = LmParams(); a.L.oracle_default_lm_params(C.byref(prm)); prm.max_trials_after_failure = case[3]
+        s = a.optimize(mod.LM_ITERS, prm).summary()
+        assert s["trials"] == list(Z["lm%d_trials" % i]) and s["result"] == int(Z["lm%d_result" % i]), case
+        for k in ("chi2_before", "chi2_after", "lam"):
+            np.testing.assert_allclose(s[k], Z["lm%d_%s" % (i, k)], rtol=1e-9, err_msg=str(case))
+        np.testing.assert_allclose(s["last_trial_chi2"], float(Z["lm%d_last_trial_chi2" % i]), rtol=1e-9)
+        np.testing.assert_allclose(a.state()[0], Z["lm%d_pose" % i], atol=1e-9)
