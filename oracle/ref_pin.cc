@@ -15,6 +15,7 @@
 #include <cstring>
 #include "G2oTypes.h"
 #include "Thirdparty/g2o/g2o/core/robust_kernel_impl.h"
+#include "Thirdparty/g2o/g2o/types/sim3.h"
 
 using namespace ORB_SLAM3;
 typedef Eigen::Matrix<double, 6, 1> V6;
@@ -304,6 +305,31 @@ void ref_huber(double delta, double e, double* rho3) {
   Eigen::Vector3d rho;
   k.robustify(e, rho);
   out(rho, rho3);
+}
+// g2o::Sim3 from the reference's own Thirdparty/g2o/g2o/types/sim3.h (exp = the Vector7d constructor :69-139, log :146-222,
+// product :262-268, inverse :225-228), the arithmetic of VertexSim3Expmap / EdgeSim3 in the essential-graph optimisation.
+// S8 = [qx qy qz qw tx ty tz s], tangent [omega, upsilon, sigma].
+static g2o::Sim3 sim3_from8(const double* p) {
+  return g2o::Sim3(Eigen::Quaterniond(p[3], p[0], p[1], p[2]), Eigen::Vector3d(p[4], p[5], p[6]), p[7]);
+}
+static void sim3_to8(const g2o::Sim3& S, double* p) { for (int i = 0; i < 8; ++i) p[i] = S[i]; }
+static g2o::Vector7d v7(const double* p) { g2o::Vector7d v; for (int i = 0; i < 7; ++i) v[i] = p[i]; return v; }
+void ref_sim3_exp(const double* u7, double* S8) { sim3_to8(g2o::Sim3(v7(u7)), S8); }
+void ref_sim3_log(const double* S8, double* u7) { out(sim3_from8(S8).log(), u7); }
+void ref_sim3_mul(const double* a, const double* b, double* o8) { sim3_to8(sim3_from8(a) * sim3_from8(b), o8); }
+void ref_sim3_inv(const double* a, double* o8) { sim3_to8(sim3_from8(a).inverse(), o8); }
+void ref_sim3_map(const double* a, const double* p3, double* o3) { out(sim3_from8(a).map(Eigen::Vector3d(p3[0], p3[1], p3[2])), o3); }
+// EdgeSim3::computeError (types_seven_dof_expmap.h:111-119): log(C * S_i * S_j^-1), the composition restated on sim3.h
+void ref_sim3_edge_error(const double* meas8, const double* Si8, const double* Sj8, double* err7) {
+  const g2o::Sim3 C = sim3_from8(meas8);
+  const g2o::Sim3 error_ = C * sim3_from8(Si8) * sim3_from8(Sj8).inverse();
+  out(error_.log(), err7);
+}
+// VertexSim3Expmap::oplusImpl (types_seven_dof_expmap.h:60-69): S <- Sim3(update) * S, update[6] = 0 when the scale is fixed
+void ref_sim3_update(const double* S8, const double* u7, int fix_scale, double* o8) {
+  g2o::Vector7d update = v7(u7);
+  if (fix_scale) update[6] = 0;
+  sim3_to8(g2o::Sim3(update) * sim3_from8(S8), o8);
 }
 // stand-in arithmetic, exported so the tests can state how far the stand-in Lie layer is from the oracle's
 void ref_standin_se3_exp(const double* xi, double* out7) { to7(Sophus::SE3d::exp(v6(xi)), out7); }

@@ -179,3 +179,28 @@ def lm_optimize(oracle, iters, lambda_init, max_trials=0):
 def huber(delta, e):
     """RobustKernelHuber::robustify compiled from the reference's g2o (robust_kernel_impl.cpp:65-91)."""
     r = np.zeros(3); lib().ref_huber(_f(delta), _f(e), _p(r)); return r
+
+
+# ---- g2o::Sim3 from the reference's Thirdparty/g2o/g2o/types/sim3.h (essential graph) ----------------------------------
+def sim3_exp(u7):
+    o = np.zeros(8); lib().ref_sim3_exp(_p(_d(u7)), _p(o)); return o
+
+
+def sim3_log(S8):
+    o = np.zeros(7); lib().ref_sim3_log(_p(_d(S8)), _p(o)); return o
+
+
+def sim3_mul(a, b):
+    o = np.zeros(8); lib().ref_sim3_mul(_p(_d(a)), _p(_d(b)), _p(o)); return o
+
+
+def sim3_inv(a):
+    o = np.zeros(8); lib().ref_sim3_inv(_p(_d(a)), _p(o)); return o
+
+
+def sim3_edge_error(meas, Si, Sj):
+    o = np.zeros(7); lib().ref_sim3_edge_error(_p(_d(meas)), _p(_d(Si)), _p(_d(Sj)), _p(o)); return o
+
+
+def sim3_update(S, u7, fix_scale):
+    o = np.zeros(8); lib().ref_sim3_update(_p(_d(S)), _p(_d(u7)), int(fix_scale), _p(o)); return o

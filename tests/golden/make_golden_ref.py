@@ -194,6 +194,27 @@ def huber_inputs():
     return np.array(rows)
 
 
+def sim3_inputs(seed=SEED + 1, n=60):
+    """Tangents [omega, upsilon, sigma] on both sides of the 1e-5 thresholds of g2o::Sim3's exp / log (sim3.h:88, 161)."""
+    rng = np.random.default_rng(seed)
+    u = np.array([np.concatenate([rng.normal(size=3) * [1.0, 1e-7, 1e-3, 2.5][i % 4], rng.normal(size=3) * 3,
+                                  [rng.normal() * [0.3, 1e-7, 0.0][i % 3]]]) for i in range(n)])
+    u2 = np.array([np.concatenate([rng.normal(size=3), rng.normal(size=3) * 3, [rng.normal() * 0.2]]) for i in range(n)])
+    return u, u2
+
+
+def run_reference_sim3(u, u2):
+    import ref_py as R
+    out = {k: [] for k in ("exp", "log", "mul", "inv", "edge", "update_free", "update_fixed")}
+    for a, b in zip(u, u2):
+        S, S2 = R.sim3_exp(a), R.sim3_exp(b)
+        meas = R.sim3_mul(R.sim3_exp(0.05 * b), R.sim3_mul(S2, R.sim3_inv(S)))   # a relative-pose measurement, slightly off
+        out["exp"].append(S); out["log"].append(R.sim3_log(S)); out["mul"].append(R.sim3_mul(S, S2)); out["inv"].append(R.sim3_inv(S))
+        out["edge"].append(np.concatenate([meas, R.sim3_edge_error(meas, S, S2)]))
+        out["update_free"].append(R.sim3_update(S, 0.1 * b, 0)); out["update_fixed"].append(R.sim3_update(S, 0.1 * b, 1))
+    return {"sim3_" + k: np.array(v) for k, v in out.items()}
+
+
 def main():
     import ref_py as R
     assert R.build(force=True), "needs /root/reference"
@@ -206,6 +227,7 @@ def main():
     path = os.path.join(HERE, "ref_edges.npz")
     hub = huber_inputs()
     out["huber"] = np.array([R.huber(d, e) for d, e in hub])
+    out.update(run_reference_sim3(*sim3_inputs()))
     np.savez_compressed(path, seed=SEED, huber_in=hub, **{"in_" + k: v for k, v in I.items()},
                         **{"ref_" + k: v for k, v in out.items()})
     print("wrote %s: %d cases, %d reference arrays, %.0f kB" % (path, len(I["t"]), len(out), os.path.getsize(path) / 1e3))

@@ -117,6 +117,30 @@ def test_huber_kernel_matches_reference_code(oracle_mod):
     assert 0 < inl < len(Z["ref_huber"])
 
 
+def test_sim3_matches_reference_code(oracle_mod):
+    """g2o::Sim3 exp / log / product / inverse, EdgeSim3's error and VertexSim3Expmap's update from the reference's own
+    Thirdparty/g2o/g2o/types/sim3.h against the oracle of the essential-graph optimisation (oracle/pose_graph.h)."""
+    O = oracle_mod
+    Z = np.load(GOLDEN)
+    u, u2 = _golden_mod().sim3_inputs()
+    assert len(u) == len(Z["ref_sim3_exp"])
+    th = np.linalg.norm(u[:, :3], axis=1)
+    assert (th < 1e-5).any() and (th > 1e-5).any() and (np.abs(u[:, 6]) < 1e-5).any() and (np.abs(u[:, 6]) > 1e-5).any()
+    for i, (a, b) in enumerate(zip(u, u2)):
+        S, S2 = O.sim3_exp(a), O.sim3_exp(b)
+        close(S, Z["ref_sim3_exp"][i], "Sim3 exp %d" % i, 1e-14)
+        close(O.sim3_log(Z["ref_sim3_exp"][i]), Z["ref_sim3_log"][i], "Sim3 log %d" % i)
+        close(O.sim3_mul(S, S2), Z["ref_sim3_mul"][i], "Sim3 product %d" % i, 1e-14)
+        close(O.sim3_inv(S), Z["ref_sim3_inv"][i], "Sim3 inverse %d" % i, 1e-14)
+        meas, err = Z["ref_sim3_edge"][i][:8], Z["ref_sim3_edge"][i][8:]
+        close(O.sim3_log(O.sim3_mul(O.sim3_mul(meas, S), O.sim3_inv(S2))), err, "EdgeSim3 error %d" % i)
+        for fixed, key in ((0, "ref_sim3_update_free"), (1, "ref_sim3_update_fixed")):
+            d = 0.1 * b
+            if fixed:
+                d = d.copy(); d[6] = 0.0
+            close(O.sim3_mul(O.sim3_exp(d), S), Z[key][i], "VertexSim3Expmap update %d" % i, 1e-14)
+
+
 def test_golden_covers_the_branches():
     """The fixture exercises both sides of the thresholds the closed forms switch on."""
     Z = np.load(GOLDEN)
