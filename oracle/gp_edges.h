@@ -1,5 +1,7 @@
 // oracle/gp_edges.h -- TEST INFRASTRUCTURE ONLY (CPU restatement; never linked into libgpba.so).
-// PARITY UNPINNED (see oracle/lie.h header).
+// PARITY: PINNED against the reference's own src/GaussianProcess.cc, src/G2oTypes.cc and g2o robust_kernel_impl.cpp, compiled
+// unmodified into oracle/_ref (oracle/Makefile target _ref, stand-in headers oracle/ref_shim/): QueryPose and its 6x12 blocks,
+// error and every Jacobian block of every edge below, the Huber kernel -- tests/test_ref_pin.py at 1e-11 (Huber: equal).
 //
 // GP interpolation + every edge type of the BA path, restated per edge exactly as the reference
 // evaluates them (including the redundant per-observation QueryPose and the 12x12 products):

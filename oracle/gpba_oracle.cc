@@ -3,8 +3,13 @@
 // Optimizer::BundleAdjustment / Optimizer::LocalGPBA.  Only tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs may load this library; libgpba.so never does.
 //
-// PARITY UNPINNED: no golden vectors exist in the reference and it cannot be built here
-// (SURVEY.md 0.5/0.6); see oracle/lie.h and DESIGN.md for what pins this restatement instead.
+// PARITY, per layer (no golden vectors exist in the reference and as a whole it cannot be built here, SURVEY.md
+// 0.5/0.6).  PINNED against the reference's own code compiled into oracle/_ref: the LM controller lm_solve() / optimize() --
+// g2o's optimization_algorithm_levenberg.cpp drives this file's level-1 steps and must reproduce oracle_optimize bit for bit
+// (oracle/ref_lm_pin.cc, tests/test_ref_pin.py) -- and the edge layer it calls (gp_edges.h).  NOT pinned by oracle/_ref: the
+// block solver below (structure, Hessian assembly, Schur complement, linear solve, back-substitution; block_solver.hpp needs
+// far more of Eigen than the stand-in headers have); that layer is pinned by dense numpy normal equations assembled edge by
+// edge (tests/test_oracle_system.py, tests/test_extrinsic_oracle.py).
 //
 // Follows (paths relative to the AMC-SLAM tree, g2o = Thirdparty/g2o/g2o):
 //   g2o/core/sparse_optimizer.cpp:199-267  initializeOptimization (active set)      -> build_structure()

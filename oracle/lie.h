@@ -1,10 +1,14 @@
 // oracle/lie.h -- TEST INFRASTRUCTURE ONLY (CPU restatement; never linked into libgpba.so).
 //
-// PARITY UNPINNED: the reference holds no golden vectors / known-answer tests for this path
-//  and cannot be compiled here (no Eigen3/OpenCV/Boost, fact 0.6), so this
-// restatement is pinned only by (a) the Sophus property tests restated in tests/test_oracle_lie.py,
-// (b) an independent scipy expm/logm + series mirror (oracle/numpy_mirror.py) and (c) g2o's own
-// central-difference Jacobian scheme.  See DESIGN.md "Oracle".
+// PARITY, per layer: the reference holds no golden vectors / known-answer tests for this path
+//  and as a whole cannot be compiled here (no Eigen3/OpenCV/Boost, fact 0.6).
+//  * The Pose3utils part of this file (Q, J_l/J_r and inverses, SO3 J_l/J_l^-1, se3Adj) IS pinned against the reference's
+//    own src/Pose3utils.cc, compiled unmodified into oracle/_ref (stand-in Eigen/Sophus headers, oracle/ref_shim/):
+//    tests/test_ref_pin.py, 1e-11.
+//  * The Sophus part (SO3/SE3 exp, log, Adj, products) is NOT pinned by oracle/_ref -- the vendored Sophus needs the real
+//    Eigen, so the reference side uses a stand-in there; it is pinned by (a) the Sophus property tests restated in
+//    tests/test_oracle_math.py, (b) an independent scipy expm/logm + series mirror (oracle/numpy_mirror.py) and (c) g2o's
+//    own central-difference Jacobian scheme.
 //
 // Fixed-size dense helpers + SO(3)/SE(3) restated from the vendored Sophus and from Pose3utils:
 //   Thirdparty/Sophus/sophus/so3.hpp  expAndTheta :583-619, logAndTheta :247-291, product :324-338,

@@ -1,7 +1,7 @@
 """ctypes binding of oracle/libgpba_oracle.so -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this.
-PARITY UNPINNED: see oracle/lie.h.
+PARITY: pinned per layer against the reference's own sources compiled into oracle/_ref (ref_py.py).
 """
 import ctypes as C
 import os

@@ -5,7 +5,9 @@
 // point vertex), EdgeGaussianPrior without kernel, EdgeVelocity on both vertices, BlockSolverX + LinearSolverDense
 // (no marginalized vertex => no Schur complement, optimization_algorithm_with_hessian.cpp:50-73) under g2o's LM
 // (optimization_algorithm_levenberg.cpp:61-194) with the default lambda (computeLambdaInit: tau * max diag, :171-185),
-// four rounds with float-typed chi2 tests.  PARITY UNPINNED like the rest of the oracle (no reference fixtures exist).
+// four rounds with float-typed chi2 tests.  PARITY: the edges (EdgeMonoGPOnlyPose, EdgeMonoOnlyPose,
+// EdgeStereoOnlyPose, EdgeGaussianPrior, EdgeVelocity) and the update are pinned against the reference's own G2oTypes.cc
+// (oracle/_ref, tests/test_ref_pin.py); the round structure of the function is a restatement (no reference fixtures exist).
 #pragma once
 #include <vector>
 #include <cmath>

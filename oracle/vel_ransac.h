@@ -3,7 +3,8 @@
 // does (src/Tracking.cc:1939-2002): VertexVel (include/G2oTypes.h:128-145), EdgeVelReproj (G2oTypes.h:521-547,
 // src/G2oTypes.cc:497-510), Huber delta 5.991, BlockSolverX + LinearSolverDense under g2o's LM with the default lambda
 // (optimization_algorithm_levenberg.cpp:61-194), 40 iterations, then |e| <= threshold over all edges.
-// PARITY UNPINNED like the rest of the oracle (no reference fixtures exist for this function either).
+// PARITY: EdgeVelReproj (error, Jacobian) is pinned against the reference's own G2oTypes.cc (oracle/_ref,
+// tests/test_ref_pin.py); the RANSAC loop around it is a restatement (no reference fixtures exist for this function).
 #pragma once
 #include <vector>
 #include <cmath>

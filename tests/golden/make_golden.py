@@ -1,8 +1,8 @@
 """Mints the golden vectors under tests/golden/ from the CPU oracle (oracle/gpba_oracle.cc).
 
 The reference holds no golden vectors, known-answer tests or fixtures for this path and cannot be built here
-(SURVEY.md 0.5 / 0.6), so PARITY IS UNPINNED against the reference binary; these files freeze the oracle's own
-outputs on seeded inputs so that (a) the oracle cannot drift silently (CPU test) and (b) the CUDA path is checked
+(SURVEY.md 0.5 / 0.6), so these files are not reference outputs: they freeze the oracle's own outputs on seeded inputs
+(the oracle itself is pinned per layer against the reference's own sources compiled into oracle/_ref (tests/test_ref_pin.py)) so that (a) the oracle cannot drift silently (CPU test) and (b) the CUDA path is checked
 against committed numbers and not only against a freshly compiled checker (GPU test).
 
     python tests/golden/make_golden.py          # rewrites tests/golden/*.npz

@@ -3,8 +3,8 @@ outliers, 4 chi2 rejection rounds, ~490k observations) and C4 (global GP-BA, 1k 
 
     python tests/golden/make_golden_baseline.py [c2 c3 c4]      # rewrites tests/golden/baseline_<name>.npz
 
-The oracle is the CPU restatement of the reference's g2o path (oracle/gpba_oracle.cc; PARITY UNPINNED against the
-reference binary, which cannot be built here -- SURVEY.md 0.5 / 0.6).  A run at these sizes takes the oracle tens of
+The oracle is the CPU restatement of the reference's g2o path (oracle/gpba_oracle.cc; the reference as a whole cannot be
+built here -- SURVEY.md 0.5 / 0.6; the oracle itself is pinned per layer against the reference's own sources compiled into oracle/_ref (tests/test_ref_pin.py)).  A run at these sizes takes the oracle tens of
 seconds (C2, C3) to minutes (C4), so the GPU suite and bench.py compare the CUDA path with the committed numbers.
 
 Every fixture also carries the oracle's REPRODUCIBILITY BAND: the same problem solved again with the reprojection edges

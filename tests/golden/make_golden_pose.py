@@ -1,6 +1,7 @@
 """Mints tests/golden/pose_*.npz from the CPU oracle of the pose-only GP optimisation (oracle/pose_only.h).
 
-The reference holds no fixtures for Optimizer::PoseGPOptimizationFromeLastFrame either: PARITY IS UNPINNED
+The reference holds no fixtures for Optimizer::PoseGPOptimizationFromeLastFrame either: the function as a whole is a restatement (its edges are pinned
+against the reference's own G2oTypes.cc, tests/test_ref_pin.py) and is not checked
 against the reference binary; these files freeze the oracle's outputs on seeded frames.
 
     python tests/golden/make_golden_pose.py

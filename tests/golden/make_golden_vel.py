@@ -1,5 +1,6 @@
-"""Mints tests/golden/vel_*.npz from the CPU oracle of the velocity RANSAC (oracle/vel_ransac.h).  PARITY IS UNPINNED
-against the reference binary (no fixtures exist for Optimizer::OptimizeVel); these files freeze the oracle.
+"""Mints tests/golden/vel_*.npz from the CPU oracle of the velocity RANSAC (oracle/vel_ransac.h).  No fixtures exist
+for Optimizer::OptimizeVel; these files freeze the oracle, whose EdgeVelReproj is pinned against the reference's
+own G2oTypes.cc (tests/test_ref_pin.py) while the RANSAC loop around it is a restatement.
 
     python tests/golden/make_golden_vel.py
 """

@@ -3,8 +3,9 @@
 CPU: the oracle still reproduces the committed numbers (it cannot drift silently).
 GPU: the CUDA path, through the C ABI, reproduces the committed numbers -- bit-exact pattern and flags, cost within
 1e-6 relative, poses within 1e-6 m / 1e-7 rad (tolerances of BASELINE.json's north_star).
-The reference itself holds no golden vectors for this path: parity against the reference BINARY is
-unpinned; these fixtures pin the oracle, and the oracle is pinned by tests/test_oracle_*.py.
+The reference itself holds no golden vectors for this path and cannot be run as a whole; these fixtures
+freeze the oracle, and the oracle is pinned by tests/test_ref_pin.py (the reference's own edge code, LM controller and Sim3,
+compiled into oracle/_ref) and tests/test_oracle_*.py (numpy / scipy mirrors for the block-solver and Lie-group layers).
 """
 import importlib.util
 import os
