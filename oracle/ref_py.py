@@ -11,6 +11,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libamc_ref_edges.so")
+_LM_SO = os.path.join(_HERE, "_ref", "libg2o_ref_lm.so")
+_G2O_SO = os.path.join(_HERE, "_ref", "libamc_ref_g2o.so")
 REFERENCE = "/root/reference"
 _LIB = None
 
@@ -20,10 +22,12 @@ def build(force=False):
     if not os.path.isdir(os.path.join(REFERENCE, "src")):
         return _SO if os.path.exists(_SO) else None
     if force:
-        for so in (_SO, os.path.join(_HERE, "_ref", "libg2o_ref_lm.so")):
+        import shutil
+        shutil.rmtree(os.path.join(_HERE, "_ref", "obj"), ignore_errors=True)
+        for so in (_SO, _LM_SO, _G2O_SO):
             if os.path.exists(so):
                 os.remove(so)
-    subprocess.check_call(["make", "-C", _HERE, "-s", "_ref"])
+    subprocess.check_call(["make", "-C", _HERE, "-s", "-j", str(min(16, os.cpu_count() or 1)), "_ref"])
     return _SO
 
 
@@ -151,7 +155,6 @@ def standin_se3_log(T7):
 
 
 # ---- the reference's Levenberg-Marquardt controller on the oracle's level-1 steps (oracle/ref_lm_pin.cc) ---------------
-_LM_SO = os.path.join(_HERE, "_ref", "libg2o_ref_lm.so")
 _LM = None
 
 
@@ -204,3 +207,31 @@ def sim3_edge_error(meas, Si, Sj):
 
 def sim3_update(S, u7, fix_scale):
     o = np.zeros(8); lib().ref_sim3_update(_p(_d(S)), _p(_d(u7)), int(fix_scale), _p(o)); return o
+
+
+# ---- the reference's whole optimisation path: real g2o + real AMC-SLAM edges (oracle/ref_g2o_run.cc) ---------------------
+_G2O = None
+
+
+def g2o_lib():
+    global _G2O
+    if _G2O is None:
+        if build() is None or not os.path.exists(_G2O_SO):
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        _G2O = C.CDLL(_G2O_SO)
+        _G2O.ref_g2o_optimize.restype = C.c_int
+    return _G2O
+
+
+def g2o_optimize(prob, iters=10, max_trials=0):
+    """Builds the reference's g2o graph from a pygpba Problem and runs the real SparseOptimizer::optimize (BlockSolverX,
+    LinearSolverDense, Levenberg-Marquardt).  Returns a dict: n (optimize's return value), trace summary, kf_pose, kf_vel,
+    pt_xyz, edge_chi2 (stored errors), sizes [active vertices, active edges, pose dimension, landmark dimension]."""
+    from pygpba.problem import LmTrace
+    c = prob.to_c()
+    kp = np.zeros((prob.n_kf, 7)); kv = np.zeros((prob.n_kf, 6)); pt = np.zeros((prob.n_pt, 3)); chi = np.zeros(prob.n_obs)
+    tr = LmTrace(); sz = np.zeros(4, np.int64)
+    n = g2o_lib().ref_g2o_optimize(C.byref(c), int(iters), int(max_trials), _p(kp), _p(kv), _p(pt), _p(chi), C.byref(tr), _p(sz))
+    s = tr.summary()
+    return dict(n=n, trials=s["trials"], chi2_start=tr.chi2_before[0], chi2_stored=s["chi2_after"], lam=s["lam"],
+                last_trial_chi2=s["last_trial_chi2"], kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, sizes=sz)

@@ -1,0 +1,91 @@
+"""Mints tests/golden/ref_g2o_<case>.npz from THE REFERENCE'S OWN OPTIMISATION PATH.
+
+oracle/_ref/libamc_ref_g2o.so is g2o's core (hyper graph, optimizable graph, sparse optimizer, BlockSolverX, sparse block
+matrices, the quadratic forms of base_*_edge.hpp, robust kernels, Levenberg-Marquardt, LinearSolverDense) and AMC-SLAM's
+src/G2oTypes.cc, GaussianProcess.cc, Pose3utils.cc, all compiled UNMODIFIED from /root/reference against the stand-in headers
+of oracle/ref_shim/ (oracle/Makefile target _ref; oracle/ref_g2o_run.cc builds the graph the way Optimizer.cc does and calls
+SparseOptimizer::optimize).  This script runs it on seeded problems and stores what it returns; tests/test_ref_g2o.py holds
+the oracle (CPU) and the CUDA path (-m gpu) to these numbers.  Needs /root/reference: build container only; the .npz travels.
+
+    python tests/golden/make_golden_ref_g2o.py [case ...]
+
+The reference run always uses LinearSolverDense (the sparse one, LinearSolverEigen, needs Eigen's SimplicialLDLT); the reduced
+system has one solution, so this only moves rounding.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "amc-slam_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "make_golden.py"))
+mg = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mg)
+
+ITERS = 10
+N_PT_SAMPLE, N_OBS_SAMPLE = 512, 2048
+
+
+def make_case(key):
+    """The four seeded problems of make_golden.py (same inputs as the oracle's own fixtures), BASELINE config C1 as it is,
+    stereo edges (EdgeStereo and EdgeStereoGP), a start far from the optimum (rejected trials), inactive edges and edges
+    without kernel."""
+    from pygpba import synth
+    if key in mg.CASES:
+        return mg.make_case(mg.CASES[key])
+    if key == "c1_full":
+        return synth.make_problem("c1")
+    if key == "stereo":
+        return synth.add_stereo(synth.make_problem("c1", n_pt=500, seed=39), 0.5, gp_fraction=0.4)
+    if key == "far_start":
+        P = synth.make_problem("tiny", seed=51)
+        rng = np.random.default_rng(51)
+        P.pt_xyz = np.ascontiguousarray(P.pt_xyz + rng.normal(size=P.pt_xyz.shape) * 3.0)
+        P.lambda_init = 1e-8
+        return P
+    if key == "levels":
+        from pygpba.problem import OBS_LEVEL1, OBS_NO_KERNEL
+        P = synth.make_problem("c1", n_pt=400, outliers=0.2, seed=53)
+        rng = np.random.default_rng(53)
+        fl = np.array(P.obs_flags, np.uint8)
+        fl[rng.random(P.n_obs) < 0.15] |= OBS_LEVEL1
+        fl[rng.random(P.n_obs) < 0.30] |= OBS_NO_KERNEL
+        P.obs_flags = fl
+        return P
+    raise KeyError(key)
+
+
+CASES = list(mg.CASES) + ["c1_full", "stereo", "far_start", "levels"]
+
+
+def samples(P):
+    rng = np.random.default_rng(12345)
+    ip = np.sort(rng.choice(P.n_pt, min(P.n_pt, N_PT_SAMPLE), replace=False))
+    io = np.sort(rng.choice(P.n_obs, min(P.n_obs, N_OBS_SAMPLE), replace=False))
+    return ip, io
+
+
+def run_reference(P):
+    import ref_py as R
+    out = R.g2o_optimize(P, ITERS)
+    ip, io = samples(P)
+    return dict(n=np.int32(out["n"]), trials=np.array(out["trials"], np.int32), chi2_start=np.float64(out["chi2_start"]),
+                chi2_stored=np.array(out["chi2_stored"]), lam=np.array(out["lam"]),
+                last_trial_chi2=np.float64(out["last_trial_chi2"]), kf_pose=out["kf_pose"], kf_vel=out["kf_vel"],
+                pt_xyz=out["pt_xyz"][ip], edge_chi2=out["edge_chi2"][io], sizes=out["sizes"])
+
+
+if __name__ == "__main__":
+    import ref_py as R
+    assert R.build(), "needs /root/reference"
+    for key in (sys.argv[1:] or CASES):
+        P = make_case(key)
+        out = run_reference(P)
+        out["input_sha256"] = np.array(mg.input_checksum(P))
+        np.savez_compressed(os.path.join(HERE, "ref_g2o_" + key + ".npz"), **out)
+        print(key, "n_obs", P.n_obs, "iterations", int(out["n"]), "trials", [int(t) for t in out["trials"]], "chi2", float(out["chi2_start"]),
+              "->", float(out["chi2_stored"][-1]))
