@@ -3,13 +3,14 @@
 // Optimizer::BundleAdjustment / Optimizer::LocalGPBA.  Only tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs may load this library; libgpba.so never does.
 //
-// PARITY, per layer (no golden vectors exist in the reference and as a whole it cannot be built here, SURVEY.md
-// 0.5/0.6).  PINNED against the reference's own code compiled into oracle/_ref: the LM controller lm_solve() / optimize() --
-// g2o's optimization_algorithm_levenberg.cpp drives this file's level-1 steps and must reproduce oracle_optimize bit for bit
-// (oracle/ref_lm_pin.cc, tests/test_ref_pin.py) -- and the edge layer it calls (gp_edges.h).  NOT pinned by oracle/_ref: the
-// block solver below (structure, Hessian assembly, Schur complement, linear solve, back-substitution; block_solver.hpp needs
-// far more of Eigen than the stand-in headers have); that layer is pinned by dense numpy normal equations assembled edge by
-// edge (tests/test_oracle_system.py, tests/test_extrinsic_oracle.py).
+// PARITY (the reference holds no golden vectors and its own build -- cmake, Eigen3, OpenCV, Boost -- cannot run
+// here): PINNED against the reference's own code.  oracle/_ref/libamc_ref_g2o.so is g2o's core, BlockSolverX,
+// LinearSolverDense, Levenberg-Marquardt and AMC-SLAM's edge sources compiled UNMODIFIED against stand-in Eigen / Sophus headers
+// (oracle/ref_shim/, oracle/ref_g2o_run.cc); tests/test_ref_g2o.py holds optimize() of this file to its runs on 8 problems incl.
+// BASELINE C1: identical iteration and trial counts, cost 1e-9, poses 1e-8 m.  Beside it the LM controller alone (g2o's
+// optimization_algorithm_levenberg.cpp on this file's level-1 steps: bit for bit, oracle/ref_lm_pin.cc) and every edge probe by
+// probe (tests/test_ref_pin.py).  Not reachable that way: the sparse linear solver (Eigen's SimplicialLDLT; unique solution,
+// checked against numpy normal equations) and Optimizer.cc's own logic (flags, rejection rounds, extrinsic stage: restated).
 //
 // Follows (paths relative to the AMC-SLAM tree, g2o = Thirdparty/g2o/g2o):
 //   g2o/core/sparse_optimizer.cpp:199-267  initializeOptimization (active set)      -> build_structure()

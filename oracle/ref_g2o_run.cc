@@ -23,6 +23,7 @@
 #include "Thirdparty/g2o/g2o/core/robust_kernel_impl.h"
 #include "Thirdparty/g2o/g2o/core/sparse_optimizer.h"
 #include "Thirdparty/g2o/g2o/solvers/linear_solver_dense.h"
+#include "Thirdparty/g2o/g2o/types/types_seven_dof_expmap.h"
 
 using namespace ORB_SLAM3;
 typedef Eigen::Matrix<double, 6, 1> V6;
@@ -216,6 +217,54 @@ int ref_g2o_optimize(const gpba_problem* P, int iters, int max_trials, double* k
   }
   if (pt_out) for (int p = 0; p < P->n_pt; ++p) for (int i = 0; i < 3; ++i) pt_out[3 * p + i] = vpt[p]->estimate()(i);
   if (edge_chi2_out) for (int64_t i = 0; i < P->n_obs; ++i) edge_chi2_out[i] = eobs[i]->chi2();
+  optimizer.removePostIterationAction(&rec);
+  return n;
+}
+
+// The optimisation inside Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:1434-1717): real VertexSim3Expmap / EdgeSim3
+// (Thirdparty/g2o/g2o/types/types_seven_dof_expmap.{h,cpp}, sim3.h; EdgeSim3 has no analytic Jacobian, so g2o's numeric
+// differentiation of base_binary_edge.hpp runs), BlockSolver_7_3, Levenberg-Marquardt with lambda_0 = 1e-16, identity
+// information (:1505), LinearSolverDense in place of LinearSolverEigen.  sim3_out [n_kf][8] = the optimised S_iw.
+int ref_g2o_pose_graph(const gpba_pose_graph* G, int iters, double* sim3_out, gpba_lm_trace* tr) {
+  g2o::SparseOptimizer optimizer;
+  optimizer.setVerbose(false);
+  g2o::BlockSolver_7_3::LinearSolverType* linearSolver = new g2o::LinearSolverDense<g2o::BlockSolver_7_3::PoseMatrixType>();
+  g2o::BlockSolver_7_3* solver_ptr = new g2o::BlockSolver_7_3(linearSolver);
+  g2o::OptimizationAlgorithmLevenberg* solver = new g2o::OptimizationAlgorithmLevenberg(solver_ptr);
+  if (G->lambda_init > 0) solver->setUserLambdaInit(G->lambda_init);
+  optimizer.setAlgorithm(solver);
+  std::vector<g2o::VertexSim3Expmap*> v(G->n_kf);
+  for (int k = 0; k < G->n_kf; ++k) {
+    const double* p = G->sim3 + 8 * k;
+    g2o::VertexSim3Expmap* V = new g2o::VertexSim3Expmap();
+    V->setEstimate(g2o::Sim3(Eigen::Quaterniond(p[3], p[0], p[1], p[2]), Eigen::Vector3d(p[4], p[5], p[6]), p[7]));
+    if (G->fixed[k]) V->setFixed(true);
+    V->setId(k);
+    V->setMarginalized(false);
+    V->_fix_scale = G->fix_scale != 0;
+    optimizer.addVertex(V);
+    v[k] = V;
+  }
+  const Eigen::Matrix<double, 7, 7> matLambda = Eigen::Matrix<double, 7, 7>::Identity();
+  for (int64_t e = 0; e < G->n_edge; ++e) {
+    const double* p = G->edge_meas + 8 * e;
+    g2o::EdgeSim3* E = new g2o::EdgeSim3();
+    E->setVertex(1, v[G->edge_j[e]]);
+    E->setVertex(0, v[G->edge_i[e]]);
+    E->setMeasurement(g2o::Sim3(Eigen::Quaterniond(p[3], p[0], p[1], p[2]), Eigen::Vector3d(p[4], p[5], p[6]), p[7]));
+    E->information() = matLambda;
+    optimizer.addEdge(E);
+  }
+  if (tr) { std::memset(tr, 0, sizeof(*tr)); tr->result = GPBA_RESULT_OK; }
+  Recorder rec;
+  rec.opt = &optimizer; rec.alg = solver; rec.tr = tr;
+  optimizer.addPostIterationAction(&rec);
+  optimizer.initializeOptimization();
+  if (tr) { optimizer.computeActiveErrors(); tr->chi2_before[0] = optimizer.activeRobustChi2(); }
+  const int n = optimizer.optimize(iters);
+  if (tr) tr->n_iters = n;
+  if (sim3_out)
+    for (int k = 0; k < G->n_kf; ++k) for (int i = 0; i < 8; ++i) sim3_out[8 * k + i] = v[k]->estimate()[i];
   optimizer.removePostIterationAction(&rec);
   return n;
 }

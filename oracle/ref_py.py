@@ -235,3 +235,14 @@ def g2o_optimize(prob, iters=10, max_trials=0):
     s = tr.summary()
     return dict(n=n, trials=s["trials"], chi2_start=tr.chi2_before[0], chi2_stored=s["chi2_after"], lam=s["lam"],
                 last_trial_chi2=s["last_trial_chi2"], kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, sizes=sz)
+
+
+def g2o_pose_graph(G, iters=20):
+    """The essential-graph optimisation with the real VertexSim3Expmap / EdgeSim3 / BlockSolver_7_3 / LM of the reference
+    (oracle/ref_g2o_run.cc) on a pygpba.posegraph.PoseGraph.  Returns (sim3 [n_kf][8], trace)."""
+    from pygpba.problem import LmTrace
+    c = G.to_c()
+    out = np.zeros((G.n_kf, 8)); tr = LmTrace()
+    g2o_lib().ref_g2o_pose_graph.restype = C.c_int
+    g2o_lib().ref_g2o_pose_graph(C.byref(c), int(iters), _p(out), C.byref(tr))
+    return out, tr

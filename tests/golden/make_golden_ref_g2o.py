@@ -79,9 +79,34 @@ def run_reference(P):
                 pt_xyz=out["pt_xyz"][ip], edge_chi2=out["edge_chi2"][io], sizes=out["sizes"])
 
 
+# essential graph (Optimizer::OptimizeEssentialGraph): closed loops, with the scale fixed and free
+POSE_GRAPHS = {"pg60": dict(n_kf=60, seed=1), "pg120_scale": dict(n_kf=120, seed=2, fix_scale=False, scale_drift=0.01)}
+PG_ITERS = 20
+
+
+def make_pose_graph(key):
+    from pygpba import posegraph as pg
+    return pg.make_pose_graph(**POSE_GRAPHS[key])
+
+
+def run_reference_pose_graph(G):
+    import ref_py as R
+    sim3, tr = R.g2o_pose_graph(G, PG_ITERS)
+    s = tr.summary()
+    return dict(sim3=sim3, n=np.int32(s["n_iters"]), trials=np.array(s["trials"], np.int32), chi2_start=np.float64(tr.chi2_before[0]),
+                chi2_stored=np.array(s["chi2_after"]), lam=np.array(s["lam"]))
+
+
 if __name__ == "__main__":
     import ref_py as R
     assert R.build(), "needs /root/reference"
+    if not sys.argv[1:]:
+        out = {}
+        for key in POSE_GRAPHS:
+            r = run_reference_pose_graph(make_pose_graph(key))
+            out.update({key + "_" + k: v for k, v in r.items()})
+            print(key, "iterations", int(r["n"]), "trials", [int(t) for t in r["trials"]], "chi2", float(r["chi2_start"]), "->", float(r["chi2_stored"][-1]))
+        np.savez_compressed(os.path.join(HERE, "ref_g2o_posegraph.npz"), **out)
     for key in (sys.argv[1:] or CASES):
         P = make_case(key)
         out = run_reference(P)
