@@ -269,4 +269,221 @@ int ref_g2o_pose_graph(const gpba_pose_graph* G, int iters, double* sim3_out, gp
   return n;
 }
 
+// Optimizer::PoseGPOptimizationFromeLastFrame (src/Optimizer.cc:369-686) for frame f of a batch: the real graph (two
+// VertexPoseVel, EdgeMonoGPOnlyPose / EdgeMonoOnlyPose / EdgeStereoOnlyPose with Huber kernels, EdgeGaussianPrior, two
+// EdgeVelocity; BlockSolverX + LinearSolverDense + LM with the default lambda, :373-382) and the four rounds of
+// optimize(10) + re-flagging (:545-670), the round logic restated from those lines with the reference's float-typed
+// thresholds.  Outputs as gpba_pose_optimize: states, mvbOutlier per match of the frame, nInitialCorrespondences - nBad.
+int ref_g2o_pose_optimize(const gpba_pose_batch* B, int f, double* cur_pose_out, double* cur_vel_out, double* prev_pose_out,
+                          double* prev_vel_out, uint8_t* outlier_out, int32_t* n_inliers_out, gpba_lm_trace* traces) {
+  Eigen::Matrix<double, 6, 6> Qc = Eigen::Matrix<double, 6, 6>::Zero();
+  for (int i = 0; i < 6; ++i) Qc(i, i) = B->qc[i];
+  GaussianProcess gp(Qc);
+  std::vector<PinholeStandIn> cams;
+  for (int c = 0; c < B->n_cam; ++c) cams.emplace_back(B->cam_intr + 4 * c);
+  std::vector<GeometricCamera*> cam_ptrs;
+  for (auto& c : cams) cam_ptrs.push_back(&c);
+  MultiKeyFrame::mTbc.clear();
+  for (int c = 0; c < B->n_cam; ++c) MultiKeyFrame::mTbc.push_back(from7(B->cam_Tbc + 7 * c));
+  MultiFrame::mTbc = MultiKeyFrame::mTbc;
+
+  g2o::SparseOptimizer optimizer;
+  g2o::BlockSolverX::LinearSolverType* linearSolver = new g2o::LinearSolverDense<g2o::BlockSolverX::PoseMatrixType>();
+  g2o::BlockSolverX* solver_ptr = new g2o::BlockSolverX(linearSolver);
+  g2o::OptimizationAlgorithmLevenberg* solver = new g2o::OptimizationAlgorithmLevenberg(solver_ptr);
+  optimizer.setAlgorithm(solver);
+  optimizer.setVerbose(false);
+
+  auto make_pv = [&](const double* T7, const double* vel, double time) {
+    PoseVelocity pv;
+    pv.Twb = from7(T7);
+    for (int i = 0; i < 6; ++i) pv.Vel(i) = vel[i];
+    pv.time = time; pv.bf = B->bf; pv.vpCameras = cam_ptrs;
+    return pv;
+  };
+  VertexPoseVel* v1 = new VertexPoseVel();
+  v1->setEstimate(make_pv(B->prev_pose + 7 * f, B->prev_vel + 6 * f, B->prev_time[f]));
+  v1->setFixed(B->prev_fixed[f] != 0);
+  v1->setId(0);
+  optimizer.addVertex(v1);
+  VertexPoseVel* v2 = new VertexPoseVel();
+  v2->setEstimate(make_pv(B->cur_pose + 7 * f, B->cur_vel + 6 * f, B->cur_time[f]));
+  v2->setFixed(false);
+  v2->setId(1);
+  optimizer.addVertex(v2);
+
+  const int64_t ob = B->obs_begin[f], oe = B->obs_begin[f + 1];
+  std::vector<uint8_t> outlier((size_t)(oe - ob), 0);
+  std::vector<EdgeStereoOnlyPose*> eS; std::vector<EdgeMonoOnlyPose*> eM; std::vector<EdgeMonoGPOnlyPose*> eG;
+  std::vector<int64_t> iS, iM, iG;
+  const float thHuberMono = (float)B->huber_mono, thHuberStereo = (float)B->huber_stereo;
+  for (int64_t i = ob; i < oe; ++i) {
+    const int cam_idx = B->obs_cam[i];
+    const Eigen::Vector3f Xw((float)B->obs_xw[3 * i], (float)B->obs_xw[3 * i + 1], (float)B->obs_xw[3 * i + 2]);
+    const double w = B->obs_inv_sigma2[i];
+    const bool out0 = (B->obs_flags && (B->obs_flags[i] & GPBA_OBS_LEVEL1));
+    outlier[i - ob] = out0;
+    if (cam_idx != B->n_cam - 1) {
+      EdgeMonoGPOnlyPose* e = new EdgeMonoGPOnlyPose(Xw, cam_idx, B->cam_time[(size_t)f * B->n_cam + cam_idx], &gp);
+      e->setVertex(0, v1); e->setVertex(1, v2);
+      e->setMeasurement(Eigen::Vector2d(B->obs_u[i], B->obs_v[i]));
+      e->setInformation(Eigen::Matrix2d::Identity() * w);
+      g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+      e->setRobustKernel(rk); rk->setDelta(thHuberMono);
+      e->setLevel(out0 ? 1 : 0);
+      optimizer.addEdge(e);
+      eG.push_back(e); iG.push_back(i);
+    } else if (!(B->obs_ur && B->obs_ur[i] >= 0)) {
+      EdgeMonoOnlyPose* e = new EdgeMonoOnlyPose(Xw);
+      e->setVertex(0, v2);
+      e->setMeasurement(Eigen::Vector2d(B->obs_u[i], B->obs_v[i]));
+      e->setInformation(Eigen::Matrix2d::Identity() * w);
+      g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+      e->setRobustKernel(rk); rk->setDelta(thHuberMono);
+      e->setLevel(out0 ? 1 : 0);
+      optimizer.addEdge(e);
+      eM.push_back(e); iM.push_back(i);
+    } else {
+      EdgeStereoOnlyPose* e = new EdgeStereoOnlyPose(Xw);
+      e->setVertex(0, v2);
+      e->setMeasurement(Eigen::Vector3d(B->obs_u[i], B->obs_v[i], B->obs_ur[i]));
+      e->setInformation(Eigen::Matrix3d::Identity() * w);
+      g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+      e->setRobustKernel(rk); rk->setDelta(thHuberStereo);
+      e->setLevel(out0 ? 1 : 0);
+      optimizer.addEdge(e);
+      eS.push_back(e); iS.push_back(i);
+    }
+  }
+  const int nInitialCorrespondences = (int)(oe - ob);
+  EdgeGaussianPrior* egp = new EdgeGaussianPrior();
+  egp->setVertex(0, v1); egp->setVertex(1, v2);
+  egp->setInformation(gp.QiInv(B->cur_time[f] - B->prev_time[f]));
+  optimizer.addEdge(egp);
+  EdgeVelocity* ev1 = new EdgeVelocity();
+  ev1->setVertex(0, v1); ev1->setInformation(gp.mQcInv.block<1, 1>(2, 2));
+  optimizer.addEdge(ev1);
+  EdgeVelocity* ev2 = new EdgeVelocity();
+  ev2->setVertex(0, v2); ev2->setInformation(gp.mQcInv.block<1, 1>(2, 2));
+  optimizer.addEdge(ev2);
+
+  const float chi2Mono[4] = {5.991, 5.991, 5.991, 5.991};
+  const float chi2Stereo[4] = {15.6f, 9.8f, 7.815f, 7.815f};
+  const int its[4] = {10, 10, 10, 10};
+  int nBad = 0;
+  Recorder rec;
+  rec.opt = &optimizer; rec.alg = solver;
+  optimizer.addPostIterationAction(&rec);
+  for (size_t it = 0; it < 4; ++it) {
+    gpba_lm_trace* tr = traces ? traces + it : nullptr;
+    if (tr) { std::memset(tr, 0, sizeof(*tr)); tr->result = GPBA_RESULT_OK; }
+    rec.tr = tr;
+    optimizer.initializeOptimization(0);
+    const int n = optimizer.optimize(its[it]);
+    if (tr) tr->n_iters = n;
+    nBad = 0;
+    const float chi2close = 1.5 * chi2Mono[it];
+    for (size_t i = 0; i < eG.size(); ++i) {
+      EdgeMonoGPOnlyPose* e = eG[i];
+      const int64_t idx = iG[i];
+      const bool bclose = B->obs_flags && (B->obs_flags[idx] & GPBA_OBS_CLOSE);
+      if (outlier[idx - ob]) e->computeError();
+      const float chi2 = e->chi2();
+      if ((chi2 > chi2Mono[it] && !bclose) || (bclose && chi2 > chi2close) || !e->isDepthPositive()) { outlier[idx - ob] = 1; e->setLevel(1); nBad++; }
+      else { outlier[idx - ob] = 0; e->setLevel(0); }
+      if (it == 2) e->setRobustKernel(0);
+    }
+    for (size_t i = 0; i < eS.size(); ++i) {
+      EdgeStereoOnlyPose* e = eS[i];
+      const int64_t idx = iS[i];
+      if (outlier[idx - ob]) e->computeError();
+      const float chi2 = e->chi2();
+      if (chi2 > chi2Stereo[it]) { outlier[idx - ob] = 1; e->setLevel(1); nBad++; }
+      else { outlier[idx - ob] = 0; e->setLevel(0); }
+      if (it == 2) e->setRobustKernel(0);
+    }
+    for (size_t i = 0; i < eM.size(); ++i) {
+      EdgeMonoOnlyPose* e = eM[i];
+      const int64_t idx = iM[i];
+      const bool bclose = B->obs_flags && (B->obs_flags[idx] & GPBA_OBS_CLOSE);
+      if (outlier[idx - ob]) e->computeError();
+      const float chi2 = e->chi2();
+      if ((chi2 > chi2Mono[it] && !bclose) || (bclose && chi2 > chi2close) || !e->isDepthPositive()) { outlier[idx - ob] = 1; e->setLevel(1); nBad++; }
+      else { outlier[idx - ob] = 0; e->setLevel(0); }
+      if (it == 2) e->setRobustKernel(0);
+    }
+    if (optimizer.edges().size() < 10) break;
+  }
+  optimizer.removePostIterationAction(&rec);
+  if (cur_pose_out) to7(v2->estimate().Twb, cur_pose_out);
+  if (cur_vel_out) for (int i = 0; i < 6; ++i) cur_vel_out[i] = v2->estimate().Vel(i);
+  if (prev_pose_out) to7(v1->estimate().Twb, prev_pose_out);
+  if (prev_vel_out) for (int i = 0; i < 6; ++i) prev_vel_out[i] = v1->estimate().Vel(i);
+  if (outlier_out) std::memcpy(outlier_out, outlier.data(), outlier.size());
+  if (n_inliers_out) *n_inliers_out = nInitialCorrespondences - nBad;
+  return 0;
+}
+
+// Optimizer::OptimizeVel (src/Optimizer.cc:2364-2447) for hypothesis h of a velocity-RANSAC batch: one VertexVel, one
+// EdgeVelReproj per match (Huber 5.991, level 0 only for the sampled matches), BlockSolverX + LinearSolverDense + LM with the
+// default lambda, optimize(40), then every edge re-evaluated and counted as inlier when |e| <= threshold.  The GN_ITERS
+// constant is the batch's `iterations` (40).  Returns the inlier count; vel_out[6], mask_out[n_match].
+int ref_g2o_optimize_vel(const gpba_vel_batch* B, int h, double* vel_out, uint8_t* mask_out, gpba_lm_trace* tr) {
+  std::vector<PinholeStandIn> cams;
+  for (int c = 0; c < B->n_cam; ++c) cams.emplace_back(B->cam_intr + 4 * c);
+  MultiKeyFrame::mTbc.clear();
+  for (int c = 0; c < B->n_cam; ++c) MultiKeyFrame::mTbc.push_back(from7(B->cam_Tbc + 7 * c));
+  MultiFrame::mTbc = MultiKeyFrame::mTbc;
+  MultiFrame F1;
+  for (auto& c : cams) F1.mvpCamera.push_back(&c);
+
+  g2o::SparseOptimizer optimizer;
+  g2o::BlockSolverX::LinearSolverType* linearSolver = new g2o::LinearSolverDense<g2o::BlockSolverX::PoseMatrixType>();
+  g2o::BlockSolverX* solver_ptr = new g2o::BlockSolverX(linearSolver);
+  g2o::OptimizationAlgorithmLevenberg* solver = new g2o::OptimizationAlgorithmLevenberg(solver_ptr);
+  optimizer.setAlgorithm(solver);
+  int inliers = 0;
+  VertexVel* vVel = new VertexVel();
+  V6 v0;
+  for (int i = 0; i < 6; ++i) v0(i) = B->vel_init[i];
+  vVel->setEstimate(v0);
+  vVel->setId(0);
+  vVel->setFixed(false);
+  optimizer.addVertex(vVel);
+  const int32_t* set = B->samples + (size_t)h * B->set_size;
+  std::vector<EdgeVelReproj*> vpEdges;
+  for (int i = 0; i < B->n_match; ++i) {
+    const int cam = B->obs_cam[i];
+    EdgeVelReproj* e = new EdgeVelReproj(from7(B->last_pose), B->cam_dt[cam],
+                                         Eigen::Vector3d(B->obs_xw[3 * i], B->obs_xw[3 * i + 1], B->obs_xw[3 * i + 2]), cam, &F1);
+    e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(optimizer.vertex(0)));
+    e->setMeasurement(Eigen::Vector2d(B->obs_u[i], B->obs_v[i]));
+    e->setInformation(Eigen::Matrix2d::Identity() * B->obs_inv_sigma2[i]);
+    g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+    e->setRobustKernel(rk);
+    rk->setDelta(B->huber_delta);
+    bool sampled = false;
+    for (int k = 0; k < B->set_size; ++k) sampled = sampled || set[k] == i;
+    e->setLevel(sampled ? 0 : 1);
+    optimizer.addEdge(e);
+    vpEdges.push_back(e);
+  }
+  if (tr) { std::memset(tr, 0, sizeof(*tr)); tr->result = GPBA_RESULT_OK; }
+  Recorder rec;
+  rec.opt = &optimizer; rec.alg = solver; rec.tr = tr;
+  optimizer.addPostIterationAction(&rec);
+  optimizer.initializeOptimization(0);
+  const int n = optimizer.optimize(B->iterations);
+  if (tr) tr->n_iters = n;
+  optimizer.removePostIterationAction(&rec);
+  for (size_t i = 0; i < vpEdges.size(); ++i) {
+    vpEdges[i]->computeError();
+    const bool in = vpEdges[i]->error().norm() <= B->threshold;
+    inliers += in;
+    if (mask_out) mask_out[i] = in ? 1 : 0;
+  }
+  if (vel_out) for (int i = 0; i < 6; ++i) vel_out[i] = vVel->estimate()(i);
+  return inliers;
+}
+
 }  // extern "C"

@@ -246,3 +246,43 @@ def g2o_pose_graph(G, iters=20):
     g2o_lib().ref_g2o_pose_graph.restype = C.c_int
     g2o_lib().ref_g2o_pose_graph(C.byref(c), int(iters), _p(out), C.byref(tr))
     return out, tr
+
+
+def g2o_pose_optimize(B):
+    """Optimizer::PoseGPOptimizationFromeLastFrame with the reference's real graph and solver for every frame of a
+    pygpba.pose.PoseBatch (oracle/ref_g2o_run.cc).  Returns a pygpba.pose.PoseResult like oracle_py.pose_optimize."""
+    from pygpba.pose import PoseResult, GPBA_POSE_ROUNDS
+    from pygpba.problem import LmTrace
+    c = B.to_c()
+    R = PoseResult(B)
+    L = g2o_lib()
+    ob = np.asarray(B.obs_begin)
+    for f in range(B.n_frames):
+        tr = (LmTrace * GPBA_POSE_ROUNDS)()
+        n_in = C.c_int32()
+        out = np.zeros(int(ob[f + 1] - ob[f]), np.uint8)
+        L.ref_g2o_pose_optimize(C.byref(c), f, _p(R.cur_pose[f]), _p(R.cur_vel[f]), _p(R.prev_pose[f]), _p(R.prev_vel[f]), _p(out),
+                                C.byref(n_in), tr)
+        R.outlier[ob[f]:ob[f + 1]] = out
+        R.n_inliers[f] = n_in.value
+        for r in range(GPBA_POSE_ROUNDS):
+            C.memmove(C.byref(R.traces[f * GPBA_POSE_ROUNDS + r]), C.byref(tr[r]), C.sizeof(LmTrace))
+    return R
+
+
+def g2o_vel_ransac(B):
+    """Every hypothesis of a pygpba.velransac.VelBatch through the reference's real Optimizer::OptimizeVel graph and solver
+    (oracle/ref_g2o_run.cc); the winner rule of Tracking::MCRansac (first hypothesis with the most inliers, Tracking.cc:1973)
+    is applied here.  Returns a pygpba.velransac.VelResult like oracle_py.vel_ransac."""
+    from pygpba.velransac import VelResult
+    c = B.to_c()
+    R = VelResult(B)
+    L = g2o_lib()
+    L.ref_g2o_optimize_vel.restype = C.c_int
+    best, best_inl = -1, 0
+    for h in range(B.n_hyp):
+        R.inliers[h] = L.ref_g2o_optimize_vel(C.byref(c), h, _p(R.vel[h]), _p(R.mask[h]), C.byref(R.traces[h]))
+        if R.inliers[h] > best_inl:
+            best, best_inl = h, int(R.inliers[h])
+    R.best.value = best
+    return R

@@ -97,10 +97,44 @@ def run_reference_pose_graph(G):
                 chi2_stored=np.array(s["chi2_after"]), lam=np.array(s["lam"]))
 
 
+def _load(name):
+    sp = importlib.util.spec_from_file_location(name, os.path.join(HERE, name + ".py"))
+    m = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(m)
+    return m
+
+
+mgp, mgv = _load("make_golden_pose"), _load("make_golden_vel")   # same seeded batches as the oracle's own fixtures
+
+
+def run_reference_pose(key):
+    """Optimizer::PoseGPOptimizationFromeLastFrame: real graph, solver and edges; packed like make_golden_pose.pack, except
+    that chi2_after holds the chi2 of the STORED errors (see Recorder in oracle/ref_g2o_run.cc)."""
+    import ref_py as R
+    from pygpba.pose import make_pose_batch
+    B = make_pose_batch(**mgp.CASES[key])
+    return mgp.pack(B, R.g2o_pose_optimize(B))
+
+
+def run_reference_vel(key):
+    import ref_py as R
+    from pygpba.velransac import make_vel_batch
+    B = make_vel_batch(**mgv.CASES[key])
+    return mgv.pack(B, R.g2o_vel_ransac(B))
+
+
 if __name__ == "__main__":
     import ref_py as R
     assert R.build(), "needs /root/reference"
     if not sys.argv[1:]:
+        for key in mgp.CASES:
+            r = run_reference_pose(key)
+            np.savez_compressed(os.path.join(HERE, "ref_g2o_pose_" + key + ".npz"), **r)
+            print("pose", key, "inliers", r["n_inliers"], "iterations", r["n_iters"])
+        for key in mgv.CASES:
+            r = run_reference_vel(key)
+            np.savez_compressed(os.path.join(HERE, "ref_g2o_vel_" + key + ".npz"), **r)
+            print("vel", key, "best", int(r["best"]), "inliers of the winner", int(r["inliers"][int(r["best"])]))
         out = {}
         for key in POSE_GRAPHS:
             r = run_reference_pose_graph(make_pose_graph(key))

@@ -117,6 +117,73 @@ def test_oracle_pose_graph_matches_reference_run(oracle_mod, key):
         assert np.array_equal(R[:, 7], G.sim3[:, 7])                           # _fix_scale: the reference never moves the scale
 
 
+# ---- tracking-side paths: pose-only GP optimisation and velocity RANSAC (f4) -------------------------------
+def rot_angle(qa, qb):
+    return angle(qa, qb)
+
+
+@pytest.mark.parametrize("key", sorted(mr.mgp.CASES))
+def test_oracle_pose_only_matches_reference_run(oracle_mod, key):
+    """Optimizer::PoseGPOptimizationFromeLastFrame with the reference's real graph / solver / edges (four rounds, float
+    chi2 tests): the oracle classifies every match the same way, runs the same iterations and trials in every round, and
+    lands on the same states."""
+    from pygpba.pose import make_pose_batch
+    G = np.load(os.path.join(HERE, "golden", "ref_g2o_pose_" + key + ".npz"))
+    B = make_pose_batch(**mr.mgp.CASES[key])
+    out = mr.mgp.pack(B, oracle_mod.pose_optimize(B))
+    for f in ("outlier", "n_inliers", "n_iters", "trials"):
+        assert np.array_equal(out[f], G[f]), f
+    for f, tol in (("cur_pose", 1e-9), ("prev_pose", 1e-9), ("cur_vel", 1e-8), ("prev_vel", 1e-8)):
+        assert np.abs(out[f] - G[f]).max() <= tol, f
+    # and the oracle's own committed fixture says the same as the reference run
+    F = np.load(os.path.join(HERE, "golden", "pose_" + key + ".npz"))
+    for f in ("outlier", "n_inliers", "n_iters", "trials"):
+        assert np.array_equal(F[f], G[f]), f
+
+
+@pytest.mark.parametrize("key", sorted(mr.mgv.CASES))
+def test_oracle_vel_ransac_matches_reference_run(oracle_mod, key):
+    """Tracking::MCRansac = maxIt x Optimizer::OptimizeVel with the reference's real graph / solver / EdgeVelReproj: same
+    winner, same inlier counts and masks, same velocities.  (Iteration counts are not compared: three matches determine the
+    twist, chi2 goes to zero and the last LM iterations sit on rounding noise -- on both sides.)"""
+    from pygpba.velransac import make_vel_batch
+    G = np.load(os.path.join(HERE, "golden", "ref_g2o_vel_" + key + ".npz"))
+    B = make_vel_batch(**mr.mgv.CASES[key])
+    R = oracle_mod.vel_ransac(B)
+    assert int(R.best.value) == int(G["best"])
+    assert np.array_equal(R.inliers, G["inliers"]) and np.array_equal(R.mask, G["mask"])
+    well = G["inliers"] >= 30
+    assert np.abs(R.vel[well] - G["vel"][well]).max() <= 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(mr.mgp.CASES))
+def test_cuda_pose_only_matches_reference_run(key):
+    """Same calls and bars as tests/test_pose_only.py::test_pose_optimize_matches_golden, against the reference's run."""
+    from pygpba import pose as PO
+    G = np.load(os.path.join(HERE, "golden", "ref_g2o_pose_" + key + ".npz"))
+    B = PO.make_pose_batch(**mr.mgp.CASES[key])
+    out = mr.mgp.pack(B, PO.pose_optimize(B))
+    for f in ("outlier", "n_inliers", "n_iters", "trials"):
+        assert np.array_equal(out[f], G[f]), f
+    assert np.abs(out["cur_pose"][:, 4:] - G["cur_pose"][:, 4:]).max() <= 1e-6
+    assert rot_angle(out["cur_pose"][:, :4], G["cur_pose"][:, :4]).max() <= 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(mr.mgv.CASES))
+def test_cuda_vel_ransac_matches_reference_run(key):
+    """Same calls and bars as tests/test_vel_ransac.py::test_vel_ransac_matches_golden, against the reference's run."""
+    from pygpba import velransac as VR
+    G = np.load(os.path.join(HERE, "golden", "ref_g2o_vel_" + key + ".npz"))
+    B = VR.make_vel_batch(**mr.mgv.CASES[key])
+    R = VR.vel_ransac(B)
+    well = G["inliers"] >= 30
+    assert np.abs(R.vel[well] - G["vel"][well]).max() <= 2e-7      # 1e-7 against the oracle + the oracle's 2e-9 from the reference
+    assert (R.mask[well] != G["mask"][well]).sum() <= 1
+    assert int(R.best.value) == int(G["best"])
+
+
 # The device cases are the ones whose inputs the GPU suite already runs against the oracle (tests/test_golden.py and smoke());
 # the remaining cases reach the device through the oracle (tests/test_gpu_parity.py has their analogues).
 GPU_CASES = ["tiny_local", "tiny_global", "loop_global", "c1_outliers", "c1_full"]
