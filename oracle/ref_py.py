@@ -286,3 +286,18 @@ def g2o_vel_ransac(B):
             best, best_inl = h, int(R.inliers[h])
     R.best.value = best
     return R
+
+
+def g2o_local_gpba_ext(prob, ext_free, prior_q, prior_info, it1=10, it2=10):
+    """LocalGPBA's two stages with extrinsic self-calibration through the reference's real VertexExtrinsic /
+    EdgeMonoGPExtrinsic / EdgeExtrinsicPrior (oracle/ref_g2o_run.cc).  ext_free [n_cam]: cameras released in stage 2."""
+    from pygpba.problem import LmTrace
+    c = prob.to_c()
+    kp = np.zeros((prob.n_kf, 7)); kv = np.zeros((prob.n_kf, 6)); pt = np.zeros((prob.n_pt, 3)); T = np.zeros((prob.n_cam, 7))
+    t1, t2 = LmTrace(), LmTrace()
+    f = np.ascontiguousarray(ext_free, np.uint8); q = _d(prior_q); w = _d(prior_info)
+    L = g2o_lib()
+    L.ref_g2o_local_gpba_ext.restype = C.c_int
+    L.ref_g2o_local_gpba_ext(C.byref(c), _p(f), _p(q), _p(w), int(it1), int(it2), _p(kp), _p(kv), _p(pt), _p(T), C.byref(t1), C.byref(t2))
+    return dict(kf_pose=kp, kf_vel=kv, pt_xyz=pt, Tbc=T, stage1=t1.summary(), stage2=t2.summary(), chi2_start=t1.chi2_before[0],
+                chi2_start2=t2.chi2_before[0])

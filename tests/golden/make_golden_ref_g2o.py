@@ -97,6 +97,45 @@ def run_reference_pose_graph(G):
                 chi2_stored=np.array(s["chi2_after"]), lam=np.array(s["lam"]))
 
 
+# extrinsic self-calibration (LocalGPBA's two stages): the inputs of tests/test_extrinsic_gpu.py::setup
+EXT_CASES = {"ext_tiny": ("tiny", {}), "ext_c1": ("c1", dict(n_pt=800))}
+EXT_ITERS = 10
+
+
+def make_ext_case(key):
+    from pygpba import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_extrinsic_oracle import perturb_tbc
+    name, kw = EXT_CASES[key]
+    P0 = synth.make_problem(name, **kw)
+    P = synth.make_problem(name, **kw)
+    P.cam_Tbc = perturb_tbc(P, 0, 0.05, 1.5, seed=5)
+    free = np.zeros(P.n_cam, np.uint8); free[:P.n_cam - 1] = 1
+    info3 = np.tile(np.diag([40.0, 30.0, 50.0]) + 2.0, (P.n_cam, 1, 1))
+    return P, free, P0.cam_Tbc[:, :4].copy(), info3
+
+
+def camera_observations(P):
+    """cam_obs of LocalGPBA (:1131): GP observations per asynchronous camera"""
+    n = np.zeros(P.n_cam, np.int64)
+    gp = P.rec_kf1[P.obs_rec] >= 0
+    np.add.at(n, P.rec_cam[P.obs_rec][gp], 1)
+    return n
+
+
+def run_reference_ext(key):
+    import ref_py as R
+    P, free, q_ini, info3 = make_ext_case(key)
+    freed = (free * (camera_observations(P) >= 50)).astype(np.uint8)       # the >= 50 observations rule (:1224-1235)
+    r = R.g2o_local_gpba_ext(P, freed, q_ini, info3, EXT_ITERS, EXT_ITERS)
+    out = dict(freed=freed, kf_pose=r["kf_pose"], kf_vel=r["kf_vel"], pt_xyz=r["pt_xyz"], Tbc=r["Tbc"], chi2_start=np.float64(r["chi2_start"]),
+               chi2_start2=np.float64(r["chi2_start2"]))
+    for st in ("stage1", "stage2"):
+        out[st + "_trials"] = np.array(r[st]["trials"], np.int32)
+        out[st + "_chi2_stored"] = np.array(r[st]["chi2_after"]); out[st + "_lam"] = np.array(r[st]["lam"])
+    return out
+
+
 def _load(name):
     sp = importlib.util.spec_from_file_location(name, os.path.join(HERE, name + ".py"))
     m = importlib.util.module_from_spec(sp)
@@ -131,6 +170,11 @@ if __name__ == "__main__":
             r = run_reference_pose(key)
             np.savez_compressed(os.path.join(HERE, "ref_g2o_pose_" + key + ".npz"), **r)
             print("pose", key, "inliers", r["n_inliers"], "iterations", r["n_iters"])
+        for key in EXT_CASES:
+            r = run_reference_ext(key)
+            np.savez_compressed(os.path.join(HERE, "ref_g2o_" + key + ".npz"), **r)
+            print("ext", key, "freed", r["freed"], "stage 2 trials", [int(t) for t in r["stage2_trials"]], "chi2", float(r["chi2_start2"]), "->",
+                  float(r["stage2_chi2_stored"][-1]))
         for key in mgv.CASES:
             r = run_reference_vel(key)
             np.savez_compressed(os.path.join(HERE, "ref_g2o_vel_" + key + ".npz"), **r)

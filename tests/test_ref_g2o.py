@@ -184,6 +184,57 @@ def test_cuda_vel_ransac_matches_reference_run(key):
     assert int(R.best.value) == int(G["best"])
 
 
+# ---- extrinsic self-calibration: LocalGPBA's two stages ------------------------------------------------
+def check_ext(t1, t2, state, Tbc, G, cost_rtol, pos_tol, ang_tol):
+    assert t1["trials"] == [int(t) for t in G["stage1_trials"]] and t2["trials"] == [int(t) for t in G["stage2_trials"]]
+    for t, st in ((t1, "stage1"), (t2, "stage2")):
+        before, after = np.array(t["chi2_before"]), np.array(t["chi2_after"])
+        acc = after < before
+        np.testing.assert_allclose(after[acc], G[st + "_chi2_stored"][acc], rtol=cost_rtol)
+        np.testing.assert_allclose(t["lam"], G[st + "_lam"], rtol=max(1e-9, 10 * cost_rtol))
+    np.testing.assert_allclose(t1["chi2_before"][0], float(G["chi2_start"]), rtol=cost_rtol)
+    np.testing.assert_allclose(t2["chi2_before"][0], float(G["chi2_start2"]), rtol=cost_rtol)   # the priors have joined
+    kp, kv, pt = state
+    assert np.abs(kp[:, 4:] - G["kf_pose"][:, 4:]).max() <= pos_tol and angle(kp[:, :4], G["kf_pose"][:, :4]).max() <= ang_tol
+    assert np.abs(kv - G["kf_vel"]).max() <= 10 * pos_tol and np.abs(pt - G["pt_xyz"]).max() <= 10 * pos_tol
+    assert np.abs(Tbc[:, 4:] - G["Tbc"][:, 4:]).max() <= pos_tol and angle(Tbc[:, :4], G["Tbc"][:, :4]).max() <= ang_tol
+
+
+@pytest.mark.parametrize("key", sorted(mr.EXT_CASES))
+def test_oracle_extrinsic_calibration_matches_reference_run(oracle_mod, key):
+    """The reference's real VertexExtrinsic / EdgeMonoGPExtrinsic (four Jacobian blocks) / EdgeExtrinsicPrior inside the real
+    solver: stage 1 with the extrinsics fixed, stage 2 with the cameras of >= 50 observations released."""
+    G = np.load(os.path.join(HERE, "golden", "ref_g2o_" + key + ".npz"))
+    P, free, q_ini, info3 = mr.make_ext_case(key)
+    o = oracle_mod.Oracle(P)
+    assert np.array_equal(o.count_camera_observations(), mr.camera_observations(P))
+    t1 = o.optimize(mr.EXT_ITERS).summary()
+    freed = free * (o.count_camera_observations() >= 50)
+    assert np.array_equal(freed, G["freed"]) and freed.sum() >= 1
+    o.set_extrinsics(freed, q_ini, info3)
+    t2 = o.optimize(mr.EXT_ITERS).summary()
+    check_ext(t1, t2, o.state(), o.extrinsics(), G, cost_rtol=1e-9, pos_tol=1e-8, ang_tol=1e-9)
+    moved = np.abs(G["Tbc"] - P.cam_Tbc).max(axis=1) > 1e-12     # (the run re-normalises the quaternions it is given)
+    assert np.array_equal(moved, freed.astype(bool))             # the reference moves exactly the released extrinsics
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(mr.EXT_CASES))
+def test_cuda_extrinsic_calibration_matches_reference_run(key):
+    """Same calls as tests/test_extrinsic_gpu.py::test_two_stage_calibration_matches_oracle (same inputs), against the
+    reference's run, at the north-star tolerances."""
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from pygpba import lib as G_
+    G = np.load(os.path.join(HERE, "golden", "ref_g2o_" + key + ".npz"))
+    P, free, q_ini, info3 = mr.make_ext_case(key)
+    g = G_.GpBa(P)
+    t1 = g.optimize(mr.EXT_ITERS).summary()
+    tg, freed = g.calibrate_extrinsics(free, q_ini, info3, min_obs=50, iters=mr.EXT_ITERS)
+    assert np.array_equal(freed, G["freed"])
+    check_ext(t1, tg.summary(), g.state(), g.extrinsics(), G, cost_rtol=1e-6, pos_tol=1e-6, ang_tol=1e-7)
+
+
 # The device cases are the ones whose inputs the GPU suite already runs against the oracle (tests/test_golden.py and smoke());
 # the remaining cases reach the device through the oracle (tests/test_gpu_parity.py has their analogues).
 GPU_CASES = ["tiny_local", "tiny_global", "loop_global", "c1_outliers", "c1_full"]
