@@ -81,124 +81,177 @@ struct Recorder : g2o::HyperGraphAction {
 
 extern "C" {
 
+}  // extern "C" (re-opened below)
+
+namespace {
+
+// The graph of Optimizer::BundleAdjustment / LocalGPBA (src/Optimizer.cc:66-330, 838-1210) over a flattened problem.
+struct BaGraph {
+  GaussianProcess gp;
+  std::vector<PinholeStandIn> cams;
+  std::vector<GeometricCamera*> cam_ptrs;
+  g2o::SparseOptimizer optimizer;                      // destroyed first (declared last of the owners below is not needed:
+  g2o::OptimizationAlgorithmLevenberg* solver = nullptr;   // the graph only holds pointers into gp / cams)
+  std::vector<VertexPoseVel*> vkf;
+  std::vector<g2o::VertexSBAPointXYZ*> vpt;
+  std::vector<g2o::OptimizableGraph::Edge*> eobs;
+  std::vector<int> kind;                               // per observation: 0 EdgeMonoGP, 1 EdgeStereoGP, 2 EdgeMono, 3 EdgeStereo
+
+  static GaussianProcess make_gp(const gpba_problem* P) {
+    Eigen::Matrix<double, 6, 6> Qc = Eigen::Matrix<double, 6, 6>::Zero();
+    for (int i = 0; i < 6; ++i) Qc(i, i) = P->qc[i];
+    return GaussianProcess(Qc);
+  }
+  BaGraph(const gpba_problem* P, int max_trials) : gp(make_gp(P)) {
+    for (int c = 0; c < P->n_cam; ++c) cams.emplace_back(P->cam_intr + 4 * c);
+    for (auto& c : cams) cam_ptrs.push_back(&c);
+    MultiKeyFrame::mTbc.clear();
+    for (int c = 0; c < P->n_cam; ++c) MultiKeyFrame::mTbc.push_back(from7(P->cam_Tbc + 7 * c));   // reference camera last
+    MultiFrame::mTbc = MultiKeyFrame::mTbc;
+
+    // ---- Optimizer.cc:66-77 / 838-856
+    g2o::BlockSolverX::LinearSolverType* linearSolver = new g2o::LinearSolverDense<g2o::BlockSolverX::PoseMatrixType>();
+    g2o::BlockSolverX* solver_ptr = new g2o::BlockSolverX(linearSolver);
+    solver = new g2o::OptimizationAlgorithmLevenberg(solver_ptr);
+    if (P->lambda_init > 0) solver->setUserLambdaInit(P->lambda_init);
+    if (max_trials > 0) solver->setMaxTrialsAfterFailure(max_trials);
+    optimizer.setAlgorithm(solver);
+    optimizer.setVerbose(false);
+
+    // ---- keyframe vertices (:82-95): id = index (ascending id = Hessian order)
+    vkf.resize(P->n_kf);
+    for (int k = 0; k < P->n_kf; ++k) {
+      PoseVelocity pv;
+      pv.Twb = from7(P->kf_pose + 7 * k);
+      for (int i = 0; i < 6; ++i) pv.Vel(i) = P->kf_vel[6 * k + i];
+      pv.time = P->kf_time[k]; pv.bf = P->bf; pv.vpCameras = cam_ptrs;
+      VertexPoseVel* v = new VertexPoseVel();
+      v->setEstimate(pv);
+      v->setId(k);
+      v->setFixed(P->kf_fixed[k] != 0);
+      optimizer.addVertex(v);
+      vkf[k] = v;
+    }
+    // ---- GP constraints (:98-135): EdgeVelocity with QcInv(2,2), EdgeGaussianPrior with QiInv(dt) (+ Huber 21.026 in global BA)
+    for (int i = 0; i < P->n_velp; ++i) {
+      EdgeVelocity* e = new EdgeVelocity();
+      e->setVertex(0, vkf[P->velp_kf[i]]);
+      e->setInformation(gp.mQcInv.block<1, 1>(2, 2));
+      optimizer.addEdge(e);
+    }
+    for (int i = 0; i < P->n_prior; ++i) {
+      EdgeGaussianPrior* e = new EdgeGaussianPrior();
+      e->setVertex(0, vkf[P->prior_kf1[i]]);
+      e->setVertex(1, vkf[P->prior_kf2[i]]);
+      if (P->huber_prior > 0) {
+        g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+        e->setRobustKernel(rk);
+        rk->setDelta(P->huber_prior);
+      }
+      e->setInformation(gp.QiInv(P->kf_time[P->prior_kf2[i]] - P->kf_time[P->prior_kf1[i]]));
+      optimizer.addEdge(e);
+    }
+    // ---- landmark vertices (:144-153), marginalized
+    vpt.resize(P->n_pt);
+    for (int p = 0; p < P->n_pt; ++p) {
+      g2o::VertexSBAPointXYZ* vP = new g2o::VertexSBAPointXYZ();
+      vP->setEstimate(Eigen::Vector3d(P->pt_xyz[3 * p], P->pt_xyz[3 * p + 1], P->pt_xyz[3 * p + 2]));
+      vP->setId(P->n_kf + p);
+      vP->setMarginalized(true);
+      optimizer.addVertex(vP);
+      vpt[p] = vP;
+    }
+    // ---- reprojection edges in insertion order (:168-330)
+    eobs.resize((size_t)P->n_obs);
+    kind.resize((size_t)P->n_obs);
+    for (int64_t i = 0; i < P->n_obs; ++i) {
+      const int r = P->obs_rec[i], kf1 = P->rec_kf1[r], kf2 = P->rec_kf2[r], cam = P->rec_cam[r];
+      const double ur = P->obs_ur ? P->obs_ur[i] : -1.0, w = P->obs_inv_sigma2[i];
+      const unsigned flags = P->obs_flags ? P->obs_flags[i] : 0u;
+      const bool stereo = ur >= 0;
+      g2o::OptimizableGraph::Edge* edge = nullptr;
+      if (kf1 >= 0 && !stereo) {
+        EdgeMonoGP* e = new EdgeMonoGP(cam, P->rec_t[r], &gp);
+        e->setVertex(0, vkf[kf1]); e->setVertex(1, vkf[kf2]); e->setVertex(2, vpt[P->obs_pt[i]]);
+        e->setMeasurement(Eigen::Vector2d(P->obs_u[i], P->obs_v[i]));
+        e->setInformation(Eigen::Matrix2d::Identity() * w);
+        edge = e; kind[i] = 0;
+      } else if (kf1 >= 0) {
+        EdgeStereoGP* e = new EdgeStereoGP(cam, P->rec_t[r], &gp);
+        e->setVertex(0, vkf[kf1]); e->setVertex(1, vkf[kf2]); e->setVertex(2, vpt[P->obs_pt[i]]);
+        e->setMeasurement(Eigen::Vector3d(P->obs_u[i], P->obs_v[i], ur));
+        e->setInformation(Eigen::Matrix3d::Identity() * w);
+        edge = e; kind[i] = 1;
+      } else if (!stereo) {
+        EdgeMono* e = new EdgeMono();
+        e->setVertex(0, vkf[kf2]); e->setVertex(1, vpt[P->obs_pt[i]]);
+        e->setMeasurement(Eigen::Vector2d(P->obs_u[i], P->obs_v[i]));
+        e->setInformation(Eigen::Matrix2d::Identity() * w);
+        edge = e; kind[i] = 2;
+      } else {
+        EdgeStereo* e = new EdgeStereo();
+        e->setVertex(0, vkf[kf2]); e->setVertex(1, vpt[P->obs_pt[i]]);
+        e->setMeasurement(Eigen::Vector3d(P->obs_u[i], P->obs_v[i], ur));
+        e->setInformation(Eigen::Matrix3d::Identity() * w);
+        edge = e; kind[i] = 3;
+      }
+      const double delta = stereo ? P->huber_stereo : P->huber_mono;
+      if (delta > 0 && !(flags & GPBA_OBS_NO_KERNEL)) {
+        g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+        edge->setRobustKernel(rk);
+        rk->setDelta(delta);
+      }
+      if (flags & GPBA_OBS_LEVEL1) edge->setLevel(1);
+      optimizer.addEdge(edge);
+      eobs[i] = edge;
+    }
+  }
+  bool depth_positive(int64_t i) const {   // the edge's own isDepthPositive(); the stereo edges have none (G2oTypes.h:404-468)
+    if (kind[i] == 0) return static_cast<EdgeMonoGP*>(eobs[i])->isDepthPositive();
+    if (kind[i] == 2) return static_cast<EdgeMono*>(eobs[i])->isDepthPositive();
+    return true;
+  }
+  // LocalGPBA's inlier check (:1263-1348) on the edges' stored chi2: mono > chi2Mono (x1.5 for close points) or negative
+  // depth, stereo > chi2Stereo
+  void flags(const gpba_problem* P, const gpba_thresholds& th, uint8_t* fl) const {
+    for (int64_t i = 0; i < P->n_obs; ++i) {
+      const double c2 = eobs[i]->chi2();
+      bool out;
+      if (kind[i] == 1 || kind[i] == 3) out = c2 > th.chi2_stereo;
+      else {
+        const bool close = P->obs_flags && (P->obs_flags[i] & GPBA_OBS_CLOSE);
+        out = (c2 > th.chi2_mono && !close) || (c2 > th.chi2_mono_close && close) || !depth_positive(i);
+      }
+      fl[i] = out ? 1 : 0;
+    }
+  }
+  void read_back(const gpba_problem* P, double* kf_pose_out, double* kf_vel_out, double* pt_out, double* edge_chi2_out) const {
+    for (int k = 0; k < P->n_kf; ++k) {
+      if (kf_pose_out) to7(vkf[k]->estimate().Twb, kf_pose_out + 7 * k);
+      if (kf_vel_out) for (int i = 0; i < 6; ++i) kf_vel_out[6 * k + i] = vkf[k]->estimate().Vel(i);
+    }
+    if (pt_out) for (int p = 0; p < P->n_pt; ++p) for (int i = 0; i < 3; ++i) pt_out[3 * p + i] = vpt[p]->estimate()(i);
+    if (edge_chi2_out) for (int64_t i = 0; i < P->n_obs; ++i) edge_chi2_out[i] = eobs[i]->chi2();
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
 // Returns what SparseOptimizer::optimize returns (the number of iterations run, 0 on Fail, -1 when nothing is free).
 // Outputs (any may be NULL): the estimates after the run, the stored chi2 of every reprojection edge (obs order), the trace
 // (chi2_before[0] = robust chi2 at the start; chi2_after[i] = chi2 of the stored errors after iteration i, see Recorder),
-// sizes[0..3] = #active vertices, #active edges, Hessian dimension of the poses, of the landmarks.
+// sizes[0..3] = #active vertices, #active edges, Hessian dimension of the poses, of the landmarks; flags_out = LocalGPBA's
+// inlier check on the final graph (thresholds th, :1263-1348).
 int ref_g2o_optimize(const gpba_problem* P, int iters, int max_trials, double* kf_pose_out, double* kf_vel_out, double* pt_out,
-                     double* edge_chi2_out, gpba_lm_trace* tr, int64_t* sizes) {
-  Eigen::Matrix<double, 6, 6> Qc = Eigen::Matrix<double, 6, 6>::Zero();
-  for (int i = 0; i < 6; ++i) Qc(i, i) = P->qc[i];
-  GaussianProcess gp(Qc);
-  std::vector<PinholeStandIn> cams;
-  for (int c = 0; c < P->n_cam; ++c) cams.emplace_back(P->cam_intr + 4 * c);
-  std::vector<GeometricCamera*> cam_ptrs;
-  for (auto& c : cams) cam_ptrs.push_back(&c);
-  MultiKeyFrame::mTbc.clear();
-  for (int c = 0; c < P->n_cam; ++c) MultiKeyFrame::mTbc.push_back(from7(P->cam_Tbc + 7 * c));   // reference camera last
-  MultiFrame::mTbc = MultiKeyFrame::mTbc;
-
-  // ---- Optimizer.cc:66-77 / 838-856
-  g2o::SparseOptimizer optimizer;
-  g2o::BlockSolverX::LinearSolverType* linearSolver = new g2o::LinearSolverDense<g2o::BlockSolverX::PoseMatrixType>();
-  g2o::BlockSolverX* solver_ptr = new g2o::BlockSolverX(linearSolver);
-  g2o::OptimizationAlgorithmLevenberg* solver = new g2o::OptimizationAlgorithmLevenberg(solver_ptr);
-  if (P->lambda_init > 0) solver->setUserLambdaInit(P->lambda_init);
-  if (max_trials > 0) solver->setMaxTrialsAfterFailure(max_trials);
-  optimizer.setAlgorithm(solver);
-  optimizer.setVerbose(false);
-
-  // ---- keyframe vertices (:82-95): id = index (ascending id = Hessian order)
-  std::vector<VertexPoseVel*> vkf(P->n_kf);
-  for (int k = 0; k < P->n_kf; ++k) {
-    PoseVelocity pv;
-    pv.Twb = from7(P->kf_pose + 7 * k);
-    for (int i = 0; i < 6; ++i) pv.Vel(i) = P->kf_vel[6 * k + i];
-    pv.time = P->kf_time[k]; pv.bf = P->bf; pv.vpCameras = cam_ptrs;
-    VertexPoseVel* v = new VertexPoseVel();
-    v->setEstimate(pv);
-    v->setId(k);
-    v->setFixed(P->kf_fixed[k] != 0);
-    optimizer.addVertex(v);
-    vkf[k] = v;
-  }
-  // ---- GP constraints (:98-135): EdgeVelocity with QcInv(2,2), EdgeGaussianPrior with QiInv(dt) (+ Huber 21.026 in global BA)
-  for (int i = 0; i < P->n_velp; ++i) {
-    EdgeVelocity* e = new EdgeVelocity();
-    e->setVertex(0, vkf[P->velp_kf[i]]);
-    e->setInformation(gp.mQcInv.block<1, 1>(2, 2));
-    optimizer.addEdge(e);
-  }
-  for (int i = 0; i < P->n_prior; ++i) {
-    EdgeGaussianPrior* e = new EdgeGaussianPrior();
-    e->setVertex(0, vkf[P->prior_kf1[i]]);
-    e->setVertex(1, vkf[P->prior_kf2[i]]);
-    if (P->huber_prior > 0) {
-      g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
-      e->setRobustKernel(rk);
-      rk->setDelta(P->huber_prior);
-    }
-    e->setInformation(gp.QiInv(P->kf_time[P->prior_kf2[i]] - P->kf_time[P->prior_kf1[i]]));
-    optimizer.addEdge(e);
-  }
-  // ---- landmark vertices (:144-153), marginalized
-  std::vector<g2o::VertexSBAPointXYZ*> vpt(P->n_pt);
-  for (int p = 0; p < P->n_pt; ++p) {
-    g2o::VertexSBAPointXYZ* vP = new g2o::VertexSBAPointXYZ();
-    vP->setEstimate(Eigen::Vector3d(P->pt_xyz[3 * p], P->pt_xyz[3 * p + 1], P->pt_xyz[3 * p + 2]));
-    vP->setId(P->n_kf + p);
-    vP->setMarginalized(true);
-    optimizer.addVertex(vP);
-    vpt[p] = vP;
-  }
-  // ---- reprojection edges in insertion order (:168-330)
-  std::vector<g2o::OptimizableGraph::Edge*> eobs((size_t)P->n_obs);
-  for (int64_t i = 0; i < P->n_obs; ++i) {
-    const int r = P->obs_rec[i], kf1 = P->rec_kf1[r], kf2 = P->rec_kf2[r], cam = P->rec_cam[r];
-    const double ur = P->obs_ur ? P->obs_ur[i] : -1.0, w = P->obs_inv_sigma2[i];
-    const unsigned flags = P->obs_flags ? P->obs_flags[i] : 0u;
-    const bool stereo = ur >= 0;
-    g2o::OptimizableGraph::Edge* edge = nullptr;
-    if (kf1 >= 0 && !stereo) {
-      EdgeMonoGP* e = new EdgeMonoGP(cam, P->rec_t[r], &gp);
-      e->setVertex(0, vkf[kf1]); e->setVertex(1, vkf[kf2]); e->setVertex(2, vpt[P->obs_pt[i]]);
-      e->setMeasurement(Eigen::Vector2d(P->obs_u[i], P->obs_v[i]));
-      e->setInformation(Eigen::Matrix2d::Identity() * w);
-      edge = e;
-    } else if (kf1 >= 0) {
-      EdgeStereoGP* e = new EdgeStereoGP(cam, P->rec_t[r], &gp);
-      e->setVertex(0, vkf[kf1]); e->setVertex(1, vkf[kf2]); e->setVertex(2, vpt[P->obs_pt[i]]);
-      e->setMeasurement(Eigen::Vector3d(P->obs_u[i], P->obs_v[i], ur));
-      e->setInformation(Eigen::Matrix3d::Identity() * w);
-      edge = e;
-    } else if (!stereo) {
-      EdgeMono* e = new EdgeMono();
-      e->setVertex(0, vkf[kf2]); e->setVertex(1, vpt[P->obs_pt[i]]);
-      e->setMeasurement(Eigen::Vector2d(P->obs_u[i], P->obs_v[i]));
-      e->setInformation(Eigen::Matrix2d::Identity() * w);
-      edge = e;
-    } else {
-      EdgeStereo* e = new EdgeStereo();
-      e->setVertex(0, vkf[kf2]); e->setVertex(1, vpt[P->obs_pt[i]]);
-      e->setMeasurement(Eigen::Vector3d(P->obs_u[i], P->obs_v[i], ur));
-      e->setInformation(Eigen::Matrix3d::Identity() * w);
-      edge = e;
-    }
-    const double delta = stereo ? P->huber_stereo : P->huber_mono;
-    if (delta > 0 && !(flags & GPBA_OBS_NO_KERNEL)) {
-      g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
-      edge->setRobustKernel(rk);
-      rk->setDelta(delta);
-    }
-    if (flags & GPBA_OBS_LEVEL1) edge->setLevel(1);
-    optimizer.addEdge(edge);
-    eobs[i] = edge;
-  }
-
+                     double* edge_chi2_out, gpba_lm_trace* tr, int64_t* sizes, const gpba_thresholds* th, uint8_t* flags_out) {
+  BaGraph G(P, max_trials);
+  g2o::SparseOptimizer& optimizer = G.optimizer;
   // ---- optimize (:333-335 / 1253-1256)
   if (tr) { std::memset(tr, 0, sizeof(*tr)); tr->result = GPBA_RESULT_OK; }
   Recorder rec;
-  rec.opt = &optimizer; rec.alg = solver; rec.tr = tr;
+  rec.opt = &optimizer; rec.alg = G.solver; rec.tr = tr;
   optimizer.addPostIterationAction(&rec);
   optimizer.initializeOptimization(0);
   if (tr) { optimizer.computeActiveErrors(); tr->chi2_before[0] = optimizer.activeRobustChi2(); }
@@ -210,15 +263,45 @@ int ref_g2o_optimize(const gpba_problem* P, int iters, int max_trials, double* k
     for (auto* v : optimizer.indexMapping()) (v->marginalized() ? dl : dp) += v->dimension();
     sizes[2] = dp; sizes[3] = dl;
   }
-  // ---- read back (:338-367 write the estimates into the map)
-  for (int k = 0; k < P->n_kf; ++k) {
-    if (kf_pose_out) to7(vkf[k]->estimate().Twb, kf_pose_out + 7 * k);
-    if (kf_vel_out) for (int i = 0; i < 6; ++i) kf_vel_out[6 * k + i] = vkf[k]->estimate().Vel(i);
-  }
-  if (pt_out) for (int p = 0; p < P->n_pt; ++p) for (int i = 0; i < 3; ++i) pt_out[3 * p + i] = vpt[p]->estimate()(i);
-  if (edge_chi2_out) for (int64_t i = 0; i < P->n_obs; ++i) edge_chi2_out[i] = eobs[i]->chi2();
+  G.read_back(P, kf_pose_out, kf_vel_out, pt_out, edge_chi2_out);   // (:338-367 write the estimates into the map)
+  if (th && flags_out) G.flags(P, *th, flags_out);
   optimizer.removePostIterationAction(&rec);
   return n;
+}
+
+// BASELINE config C3's schedule: n_rounds x (initializeOptimization(0) + optimize(iters)), after each round the errors of
+// the excluded edges are recomputed ("if (mvbOutlier[idx]) e->computeError()", :591-592), every edge is re-flagged with
+// LocalGPBA's inlier check, flagged edges move to level 1 and after the third round the kernels are removed
+// ("if (it==2) e->setRobustKernel(0)") -- the round structure of src/Optimizer.cc:548-675 on the BA graph, with the real
+// solver and edges.  traces [n_rounds]; flags_out [n_obs] after the last round.
+int ref_g2o_rejection_rounds(const gpba_problem* P, int n_rounds, int iters, const gpba_thresholds* th, double* kf_pose_out,
+                             double* kf_vel_out, double* pt_out, double* edge_chi2_out, uint8_t* flags_out, gpba_lm_trace* traces) {
+  BaGraph G(P, 0);
+  g2o::SparseOptimizer& optimizer = G.optimizer;
+  std::vector<uint8_t> fl((size_t)P->n_obs, 0);
+  for (int64_t i = 0; i < P->n_obs; ++i) fl[i] = (P->obs_flags && (P->obs_flags[i] & GPBA_OBS_LEVEL1)) ? 1 : 0;
+  Recorder rec;
+  rec.opt = &optimizer; rec.alg = G.solver;
+  optimizer.addPostIterationAction(&rec);
+  for (int it = 0; it < n_rounds; ++it) {
+    gpba_lm_trace* tr = traces ? traces + it : nullptr;
+    if (tr) { std::memset(tr, 0, sizeof(*tr)); tr->result = GPBA_RESULT_OK; }
+    rec.tr = tr;
+    optimizer.initializeOptimization(0);
+    if (tr) { optimizer.computeActiveErrors(); tr->chi2_before[0] = optimizer.activeRobustChi2(); }
+    const int n = optimizer.optimize(iters);
+    if (tr) tr->n_iters = n;
+    for (int64_t i = 0; i < P->n_obs; ++i) if (fl[i]) G.eobs[i]->computeError();
+    G.flags(P, *th, fl.data());
+    for (int64_t i = 0; i < P->n_obs; ++i) {
+      G.eobs[i]->setLevel(fl[i] ? 1 : 0);
+      if (it == 2) G.eobs[i]->setRobustKernel(0);
+    }
+  }
+  optimizer.removePostIterationAction(&rec);
+  G.read_back(P, kf_pose_out, kf_vel_out, pt_out, edge_chi2_out);
+  if (flags_out) std::memcpy(flags_out, fl.data(), fl.size());
+  return 0;
 }
 
 // The optimisation inside Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:1434-1717): real VertexSim3Expmap / EdgeSim3

@@ -226,15 +226,31 @@ def g2o_lib():
 def g2o_optimize(prob, iters=10, max_trials=0):
     """Builds the reference's g2o graph from a pygpba Problem and runs the real SparseOptimizer::optimize (BlockSolverX,
     LinearSolverDense, Levenberg-Marquardt).  Returns a dict: n (optimize's return value), trace summary, kf_pose, kf_vel,
-    pt_xyz, edge_chi2 (stored errors), sizes [active vertices, active edges, pose dimension, landmark dimension]."""
-    from pygpba.problem import LmTrace
+    pt_xyz, edge_chi2 (stored errors), sizes [active vertices, active edges, pose dimension, landmark dimension], flags
+    (LocalGPBA's inlier check on the final graph, float-typed thresholds)."""
+    from pygpba.problem import LmTrace, Thresholds
     c = prob.to_c()
     kp = np.zeros((prob.n_kf, 7)); kv = np.zeros((prob.n_kf, 6)); pt = np.zeros((prob.n_pt, 3)); chi = np.zeros(prob.n_obs)
-    tr = LmTrace(); sz = np.zeros(4, np.int64)
-    n = g2o_lib().ref_g2o_optimize(C.byref(c), int(iters), int(max_trials), _p(kp), _p(kv), _p(pt), _p(chi), C.byref(tr), _p(sz))
+    tr = LmTrace(); sz = np.zeros(4, np.int64); th = Thresholds.local_gpba(); fl = np.zeros(prob.n_obs, np.uint8)
+    n = g2o_lib().ref_g2o_optimize(C.byref(c), int(iters), int(max_trials), _p(kp), _p(kv), _p(pt), _p(chi), C.byref(tr), _p(sz),
+                                   C.byref(th), _p(fl))
     s = tr.summary()
     return dict(n=n, trials=s["trials"], chi2_start=tr.chi2_before[0], chi2_stored=s["chi2_after"], lam=s["lam"],
-                last_trial_chi2=s["last_trial_chi2"], kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, sizes=sz)
+                last_trial_chi2=s["last_trial_chi2"], kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, sizes=sz, flags=fl)
+
+
+def g2o_rejection_rounds(prob, n_rounds=4, iters=10):
+    """BASELINE config C3's schedule (rounds of optimize + re-flagging, kernels off after the third) with the reference's
+    real solver and edges.  Returns flags, trace summaries per round (chi2_after = chi2 of the stored errors), state, edge chi2."""
+    from pygpba.problem import LmTrace, Thresholds
+    c = prob.to_c()
+    kp = np.zeros((prob.n_kf, 7)); kv = np.zeros((prob.n_kf, 6)); pt = np.zeros((prob.n_pt, 3)); chi = np.zeros(prob.n_obs)
+    th = Thresholds.local_gpba(); fl = np.zeros(prob.n_obs, np.uint8); traces = (LmTrace * n_rounds)()
+    L = g2o_lib()
+    L.ref_g2o_rejection_rounds.restype = C.c_int
+    L.ref_g2o_rejection_rounds(C.byref(c), int(n_rounds), int(iters), C.byref(th), _p(kp), _p(kv), _p(pt), _p(chi), _p(fl), traces)
+    return dict(flags=fl, traces=[t.summary() for t in traces], chi2_start=[t.chi2_before[0] for t in traces], kf_pose=kp, kf_vel=kv,
+                pt_xyz=pt, edge_chi2=chi)
 
 
 def g2o_pose_graph(G, iters=20):

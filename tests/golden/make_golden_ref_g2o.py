@@ -76,7 +76,55 @@ def run_reference(P):
     return dict(n=np.int32(out["n"]), trials=np.array(out["trials"], np.int32), chi2_start=np.float64(out["chi2_start"]),
                 chi2_stored=np.array(out["chi2_stored"]), lam=np.array(out["lam"]),
                 last_trial_chi2=np.float64(out["last_trial_chi2"]), kf_pose=out["kf_pose"], kf_vel=out["kf_vel"],
-                pt_xyz=out["pt_xyz"][ip], edge_chi2=out["edge_chi2"][io], sizes=out["sizes"])
+                pt_xyz=out["pt_xyz"][ip], edge_chi2=out["edge_chi2"][io], sizes=out["sizes"], flags_packed=np.packbits(out["flags"]),
+                edge_chi2_near=near_threshold(out["edge_chi2"]))
+
+
+def near_threshold(chi2):
+    """indices and values of the edges whose chi2 lies within 1e-3 of a threshold (the north star excludes 1e-6)"""
+    from pygpba.problem import Thresholds
+    th = Thresholds.local_gpba()
+    idx = np.nonzero((np.abs(chi2 - th.chi2_mono) < 1e-3) | (np.abs(chi2 - th.chi2_mono_close) < 1e-3) | (np.abs(chi2 - th.chi2_stereo) < 1e-3))[0]
+    return np.stack([idx.astype(np.float64), chi2[idx]]) if len(idx) else np.zeros((2, 0))
+
+
+# BASELINE config C3's schedule (30 % outliers, Huber, four chi2 rejection rounds) on a C3 map cut to 2 000 points (29.5k
+# observations; the stand-in matrices make the full 490k-observation C3 a half-hour run)
+ROUNDS_CASE = dict(name="c3", n_pt=2000, seed=3)
+
+
+def make_rounds_case():
+    from pygpba import synth
+    a = dict(ROUNDS_CASE)
+    return synth.make_problem(a.pop("name"), **a)
+
+
+def run_reference_rounds():
+    import ref_py as R
+    P = make_rounds_case()
+    r = R.g2o_rejection_rounds(P, 4, ITERS)
+    ip, io = samples(P)
+    out = dict(flags_packed=np.packbits(r["flags"]), n_flagged=np.int64(r["flags"].sum()), kf_pose=r["kf_pose"], kf_vel=r["kf_vel"],
+               pt_xyz=r["pt_xyz"][ip], edge_chi2=r["edge_chi2"][io], edge_chi2_near=near_threshold(r["edge_chi2"]),
+               chi2_start=np.array(r["chi2_start"]), input_sha256=np.array(mg.input_checksum(P)))
+    for i, t in enumerate(r["traces"]):
+        out["round%d_trials" % i] = np.array(t["trials"], np.int32); out["round%d_chi2_stored" % i] = np.array(t["chi2_after"])
+    return out
+
+
+def run_reference_c2():
+    """BASELINE config C2 (4 async cameras, 30 keyframes, 20k points, ~300k observations), the config the local-BA metric is
+    quoted on; the same problem and sample indices as the oracle's fixture tests/golden/baseline_c2.npz.  Minutes."""
+    import ref_py as R
+    sys.path.insert(0, HERE)
+    import make_golden_baseline as mb
+    P = mb.make_case("c2")
+    r = R.g2o_optimize(P, mb.CASES["c2"]["iters"])
+    si_pt, si_obs = mb.sample_idx(P.n_pt, 101), mb.sample_idx(P.n_obs, 102)
+    return dict(n=np.int32(r["n"]), trials=np.array(r["trials"], np.int32), chi2_start=np.float64(r["chi2_start"]),
+                chi2_stored=np.array(r["chi2_stored"]), lam=np.array(r["lam"]), kf_pose=r["kf_pose"], kf_vel=r["kf_vel"],
+                pt_xyz=r["pt_xyz"][si_pt], edge_chi2=r["edge_chi2"][si_obs], flags_packed=np.packbits(r["flags"]), sizes=r["sizes"],
+                input_sha256=np.array(mg.input_checksum(P)))
 
 
 # essential graph (Optimizer::OptimizeEssentialGraph): closed loops, with the scale fixed and free
@@ -165,7 +213,15 @@ def run_reference_vel(key):
 if __name__ == "__main__":
     import ref_py as R
     assert R.build(), "needs /root/reference"
+    if sys.argv[1:] == ["c2"]:
+        r = run_reference_c2()
+        np.savez_compressed(os.path.join(HERE, "ref_g2o_c2.npz"), **r)
+        print("c2 iterations", int(r["n"]), "trials", [int(t) for t in r["trials"]], "chi2", float(r["chi2_start"]), "->", float(r["chi2_stored"][-1]))
+        sys.exit(0)
     if not sys.argv[1:]:
+        r = run_reference_rounds()
+        np.savez_compressed(os.path.join(HERE, "ref_g2o_rounds_c3.npz"), **r)
+        print("rounds flagged", int(r["n_flagged"]), "trials", [[int(t) for t in r["round%d_trials" % i]] for i in range(4)])
         for key in mgp.CASES:
             r = run_reference_pose(key)
             np.savez_compressed(os.path.join(HERE, "ref_g2o_pose_" + key + ".npz"), **r)
