@@ -317,3 +317,49 @@ def g2o_local_gpba_ext(prob, ext_free, prior_q, prior_info, it1=10, it2=10):
     L.ref_g2o_local_gpba_ext(C.byref(c), _p(f), _p(q), _p(w), int(it1), int(it2), _p(kp), _p(kv), _p(pt), _p(T), C.byref(t1), C.byref(t2))
     return dict(kf_pose=kp, kf_vel=kv, pt_xyz=pt, Tbc=T, stage1=t1.summary(), stage2=t2.summary(), chi2_start=t1.chi2_before[0],
                 chi2_start2=t2.chi2_before[0])
+
+
+# ---- the reference-side binding adapter/g2o_gpba_solver.h against the real g2o headers (oracle/ref_adapter_check.cc) -------
+_ADAPTER_SO = os.path.join(_HERE, "_ref", "libadapter_check.so")
+_ADAPTER = None
+
+
+def adapter_lib():
+    global _ADAPTER
+    if _ADAPTER is None:
+        if build() is None or not os.path.exists(_ADAPTER_SO):
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        import oracle_py
+        oracle_py.lib()
+        _ADAPTER = C.CDLL(_ADAPTER_SO)
+        _ADAPTER.ref_adapter_roundtrip.restype = C.c_int
+        _ADAPTER.ref_adapter_no_device.restype = C.c_int
+    return _ADAPTER
+
+
+def adapter_roundtrip(prob, iters=10):
+    """problem -> the reference's real g2o graph -> the adapter's FlatGraph::build -> the oracle's optimize on what came out."""
+    from pygpba.problem import LmTrace
+    c = prob.to_c()
+    kp = np.zeros((prob.n_kf, 7)); kv = np.zeros((prob.n_kf, 6)); pt = np.zeros((prob.n_pt, 3)); chi = np.zeros(prob.n_obs)
+    counts = np.zeros(6, np.int64); tr = LmTrace()
+    rc = adapter_lib().ref_adapter_roundtrip(C.byref(c), int(iters), _p(counts), _p(kp), _p(kv), _p(pt), _p(chi), C.byref(tr))
+    return dict(rc=rc, counts=counts, kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, trace=tr.summary())
+
+
+def adapter_no_device(prob):
+    c = prob.to_c()
+    kp = np.zeros((prob.n_kf, 7))
+    return adapter_lib().ref_adapter_no_device(C.byref(c), _p(kp)), kp
+
+
+def adapter_optimize(prob, iters=10, device=0):
+    """gpba::GpBaLevenberg inside the reference's real SparseOptimizer on a CUDA device (needs a GPU)."""
+    from pygpba.problem import LmTrace
+    c = prob.to_c()
+    kp = np.zeros((prob.n_kf, 7)); kv = np.zeros((prob.n_kf, 6)); pt = np.zeros((prob.n_pt, 3)); chi = np.zeros(prob.n_obs)
+    tr = LmTrace()
+    L = adapter_lib()
+    L.ref_adapter_optimize.restype = C.c_int
+    n = L.ref_adapter_optimize(C.byref(c), int(iters), int(device), _p(kp), _p(kv), _p(pt), _p(chi), C.byref(tr))
+    return dict(n=n, kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, trace=tr.summary())

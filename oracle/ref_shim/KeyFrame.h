@@ -18,6 +18,7 @@ class GeometricCamera {
   virtual ~GeometricCamera() {}
   virtual Eigen::Vector2d project(const Eigen::Vector3d& v3D) = 0;
   virtual Eigen::Matrix<double, 2, 3> projectJac(const Eigen::Vector3d& v3D) = 0;
+  virtual float getParameter(const int i) { (void)i; return 0.f; }   // GeometricCamera.h:101 (float intrinsics), read by adapter/
 };
 
 class MultiKeyFrame {

@@ -17,6 +17,8 @@ template <class S> class SE3 {
   SE3() {}
   SE3(const SO3<S>& so3, const Point& t) : so3_(so3), t_(t) {}
   SE3(const Eigen::Matrix<S, 3, 3>& R, const Point& t) : so3_(R), t_(t) {}
+  SE3(const Eigen::Quaternion<S>& q, const Point& t) : so3_(q), t_(t) {}
+  Eigen::Quaternion<S> unit_quaternion() const { return so3_.unit_quaternion(); }
 
   const SO3<S>& so3() const { return so3_; }
   SO3<S>& so3() { return so3_; }

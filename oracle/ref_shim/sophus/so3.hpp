@@ -54,6 +54,8 @@ template <class S> class SO3 {
     }
     *this = fromQuaternion(q[0], q[1], q[2], q[3]);
   }
+  Eigen::Quaternion<S> unit_quaternion() const { return Eigen::Quaternion<S>(w_, x_, y_, z_); }
+  explicit SO3(const Eigen::Quaternion<S>& q) { *this = fromQuaternion(q.x(), q.y(), q.z(), q.w()); }
   S qx() const { return x_; }
   S qy() const { return y_; }
   S qz() const { return z_; }
