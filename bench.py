@@ -253,8 +253,39 @@ def run_reference(args):
         "g2o_batch_stats_s_per_step": {k: round(v / max(args.steps, 1), 4) for k, v in stats.items()},
         "lm_iters_per_step": REF_LM_ITERS,
     }
+    out["reference_code"] = reference_code_check()
     emit(out)
     return 0
+
+
+def reference_code_check():
+    """The reference's OWN sources (g2o core + BlockSolverX + LinearSolverDense + LM + AMC-SLAM's edge code, compiled unmodified
+    against stand-in Eigen headers into oracle/_ref/libamc_ref_g2o.so) on BASELINE config C1, beside the port on
+    the same problem: that the port IS the reference's arithmetic is shown here, in the run that times it.  The real-code
+    library is not the timed arm: its eager stand-in matrices allocate on every operation, which would flatter the device."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libamc_ref_g2o.so")
+    if not os.path.exists(so):
+        return {"available": False, "why": "oracle/_ref is built where /root/reference is and travels with the snapshot; it is not here"}
+    try:
+        import numpy as np
+        import oracle_py
+        import ref_py
+        from pygpba import synth
+        P = synth.make_problem("c1")
+        t = time.perf_counter(); r = ref_py.g2o_optimize(P, 10); t_ref = time.perf_counter() - t
+        o = oracle_py.Oracle(P, threads=1)
+        t = time.perf_counter(); tr = o.optimize(10).summary(); t_port = time.perf_counter() - t
+        kp, kv, pt = o.state()
+        o.close()
+        n = tr["n_iters"]
+        acc = [i for i in range(n) if tr["chi2_after"][i] < tr["chi2_before"][i]]
+        return {"available": True, "library": "oracle/_ref/libamc_ref_g2o.so", "workload": f"C1: {P.n_kf} keyframes, {P.n_pt} points, {P.n_obs} observations, optimize(10)",
+                "iterations": [int(r["n"]), n], "trials_equal": [int(x) for x in r["trials"]] == tr["trials"],
+                "cost_rel": float(max(abs(r["chi2_stored"][i] - tr["chi2_after"][i]) / tr["chi2_after"][i] for i in acc)),
+                "pos_m": float(np.abs(kp[:, 4:] - r["kf_pose"][:, 4:]).max()), "pt_m": float(np.abs(pt - r["pt_xyz"]).max()),
+                "seconds_reference_code": round(t_ref, 2), "seconds_port_1_thread": round(t_port, 3)}
+    except Exception as e:   # the line must still be printed
+        return {"available": True, "error": repr(e)}
 
 
 def run_gpba(args):
