@@ -184,6 +184,24 @@ def run_reference_ext(key):
     return out
 
 
+def run_reference_c3():
+    """BASELINE config C3 as it is stated (4 cameras, 50 keyframes, ~490k observations, 30 % outliers, Huber + four chi2
+    rejection rounds): same problem and sample indices as the oracle's fixture tests/golden/baseline_c3.npz.  Half an hour."""
+    import ref_py as R
+    sys.path.insert(0, HERE)
+    import make_golden_baseline as mb
+    P = mb.make_case("c3")
+    r = R.g2o_rejection_rounds(P, mb.CASES["c3"]["rounds"], mb.CASES["c3"]["iters"])
+    si_pt, si_obs = mb.sample_idx(P.n_pt, 101), mb.sample_idx(P.n_obs, 102)
+    out = dict(flags_packed=np.packbits(r["flags"]), n_flagged=np.int64(r["flags"].sum()), kf_pose=r["kf_pose"], kf_vel=r["kf_vel"],
+               pt_xyz=r["pt_xyz"][si_pt], edge_chi2=r["edge_chi2"][si_obs], chi2_start=np.array(r["chi2_start"]),
+               input_sha256=np.array(mg.input_checksum(P)))
+    for i, t in enumerate(r["traces"]):
+        out["round%d_trials" % i] = np.array(t["trials"], np.int32); out["round%d_chi2_stored" % i] = np.array(t["chi2_after"])
+        out["round%d_lam" % i] = np.array(t["lam"])
+    return out
+
+
 def _load(name):
     sp = importlib.util.spec_from_file_location(name, os.path.join(HERE, name + ".py"))
     m = importlib.util.module_from_spec(sp)
@@ -213,6 +231,11 @@ def run_reference_vel(key):
 if __name__ == "__main__":
     import ref_py as R
     assert R.build(), "needs /root/reference"
+    if sys.argv[1:] == ["c3"]:
+        r = run_reference_c3()
+        np.savez_compressed(os.path.join(HERE, "ref_g2o_c3.npz"), **r)
+        print("c3 flagged", int(r["n_flagged"]), "trials", [[int(t) for t in r["round%d_trials" % i]] for i in range(4)])
+        sys.exit(0)
     if sys.argv[1:] == ["c2"]:
         r = run_reference_c2()
         np.savez_compressed(os.path.join(HERE, "ref_g2o_c2.npz"), **r)

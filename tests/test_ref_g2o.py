@@ -189,6 +189,37 @@ def test_c2_fixture_matches_reference_run():
     assert np.array_equal(ref[~excl], mine[~excl])                                              # outlier flags: bit-exact
 
 
+def test_c3_fixture_matches_reference_run():
+    """BASELINE config C3 AS IT IS STATED (4 cameras, 50 keyframes, ~490k observations, 30 % injected outliers, Huber kernel +
+    four chi2 rejection rounds) through the reference's own solver and edges, compared with the oracle's committed fixture
+    tests/golden/baseline_c3.npz -- the file tests/test_baseline_fixtures.py holds the CUDA path to."""
+    path = os.path.join(HERE, "golden", "ref_g2o_c3.npz")
+    if not os.path.exists(path):
+        pytest.skip("ref_g2o_c3.npz not minted (a half-hour run of oracle/_ref)")
+    G = np.load(path)
+    F = np.load(os.path.join(HERE, "golden", "baseline_c3.npz"))
+    assert str(G["input_sha256"]) == str(F["input_sha256"])
+    for r in range(4):
+        n = int(F["tr_n_iters"][r])
+        assert [int(t) for t in G["round%d_trials" % r]] == [int(t) for t in F["tr_trials"][r][:n]]
+        np.testing.assert_allclose(G["chi2_start"][r], F["tr_chi2_before"][r][0], rtol=1e-9)
+        np.testing.assert_allclose(G["round%d_lam" % r], F["tr_lam"][r][:n], rtol=1e-9)
+        acc = F["tr_chi2_after"][r][:n] < F["tr_chi2_before"][r][:n]
+        np.testing.assert_allclose(G["round%d_chi2_stored" % r][acc], F["tr_chi2_after"][r][:n][acc], rtol=1e-9)
+    assert np.abs(G["kf_pose"][:, 4:] - F["kf_pose"][:, 4:]).max() <= 1e-8                      # metres
+    assert angle(G["kf_pose"][:, :4], F["kf_pose"][:, :4]).max() <= 1e-9                       # radians
+    assert np.abs(G["kf_vel"] - F["kf_vel"]).max() <= 1e-7 and np.abs(G["pt_xyz"] - F["pt_xyz"]).max() <= 1e-6
+    np.testing.assert_allclose(G["edge_chi2"], F["edge_chi2"], rtol=1e-6, atol=1e-8)
+    n_obs = int(F["n_obs"])
+    ref, mine = np.unpackbits(G["flags_packed"])[:n_obs], np.unpackbits(F["flags_packed"])[:n_obs]
+    th = Thresholds.local_gpba()
+    excl = np.zeros(n_obs, bool)
+    for i, c2 in zip(F["near_idx"], F["near_chi2"]):
+        excl[i] = min(abs(c2 - th.chi2_mono), abs(c2 - th.chi2_mono_close)) < 1e-6
+    assert int(ref.sum()) > 0.3 * n_obs and excl.sum() <= 2
+    assert np.array_equal(ref[~excl], mine[~excl])                                              # outlier flags: bit-exact
+
+
 # ---- tracking-side paths: pose-only GP optimisation (SURVEY 8 f1) and velocity RANSAC (f4) -------------------------------
 def rot_angle(qa, qb):
     return angle(qa, qb)
