@@ -2,7 +2,7 @@
 //
 // Header-only C++11, to be compiled INSIDE the AMC-SLAM tree (it needs the reference's own g2o, Eigen, Sophus and
 // G2oTypes.h).  In this repository it is compiled against the reference's real g2o headers with stand-in Eigen / Sophus
-// headers and exercised on real g2o graphs by oracle/ref_adapter_check.cc (tests/test_ref_g2o.py).  It is the code a
+// headers and exercised on real g2o graphs by oracle/ref_adapter_check.cc (tests/test_whole_path_reference.py).  It is the code a
 // maintainer adds to swap solvers at the two construction sites, without touching Tracking / LocalMapping /
 // LoopClosing (see INTEGRATION.md for the exact diff):
 //

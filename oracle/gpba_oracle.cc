@@ -6,7 +6,7 @@
 // PARITY (the reference holds no golden vectors and its own build -- cmake, Eigen3, OpenCV, Boost -- cannot run
 // here): PINNED against the reference's own code.  oracle/_ref/libamc_ref_g2o.so is g2o's core, BlockSolverX,
 // LinearSolverDense, Levenberg-Marquardt and AMC-SLAM's edge sources compiled UNMODIFIED against stand-in Eigen / Sophus headers
-// (oracle/ref_shim/, oracle/ref_g2o_run.cc); tests/test_ref_g2o.py holds optimize() of this file to its runs on 8 problems incl.
+// (oracle/ref_shim/, oracle/ref_g2o_run.cc); tests/test_whole_path_reference.py holds optimize() of this file to its runs on 8 problems incl.
 // BASELINE C1: identical iteration and trial counts, cost 1e-9, poses 1e-8 m.  Beside it the LM controller alone (g2o's
 // optimization_algorithm_levenberg.cpp on this file's level-1 steps: bit for bit, oracle/ref_lm_pin.cc) and every edge probe by
 // probe (tests/test_ref_pin.py).  Not reachable that way: the sparse linear solver (Eigen's SimplicialLDLT; unique solution,

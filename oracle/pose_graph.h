@@ -1,6 +1,6 @@
 // pose_graph.h -- CPU restatement (TEST INFRASTRUCTURE ONLY; g2o::Sim3 exp/log/product/inverse, the EdgeSim3 error
 // and the vertex update are pinned against the reference's own g2o/types/sim3.h compiled into oracle/_ref, tests/test_ref_pin.py;
-// the whole optimisation against the reference's real VertexSim3Expmap / EdgeSim3 / BlockSolver_7_3 / LM, tests/test_ref_g2o.py,
+// the whole optimisation against the reference's real VertexSim3Expmap / EdgeSim3 / BlockSolver_7_3 / LM, tests/test_whole_path_reference.py,
 // within the reproducibility band of g2o's numeric Jacobians) of the
 // optimisation inside Optimizer::OptimizeEssentialGraph (src/Optimizer.cc:1434-1717): a g2o graph of VertexSim3Expmap
 // (Thirdparty/g2o/g2o/types/types_seven_dof_expmap.h:48-96) and EdgeSim3 (:99-126) with identity information, solved by

@@ -8,7 +8,7 @@
 // four rounds with float-typed chi2 tests.  PARITY: the edges (EdgeMonoGPOnlyPose, EdgeMonoOnlyPose,
 // EdgeStereoOnlyPose, EdgeGaussianPrior, EdgeVelocity) and the update are pinned against the reference's own G2oTypes.cc
 // (oracle/_ref, tests/test_ref_pin.py), and the whole function against the reference's real graph / solver run with the four rounds
-// around it (oracle/ref_g2o_run.cc ref_g2o_pose_optimize, tests/test_ref_g2o.py: every match classified identically, same states).
+// around it (oracle/ref_g2o_run.cc ref_g2o_pose_optimize, tests/test_whole_path_reference.py: every match classified identically, same states).
 #pragma once
 #include <vector>
 #include <cmath>

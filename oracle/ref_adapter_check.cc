@@ -3,7 +3,7 @@
 // oracle/ref_shim/), which the repository could not do before, and runs its graph flattening on a real g2o graph:
 //   gpba_problem P -> the reference's graph (BaGraph, ref_g2o_graph.h) -> initializeOptimization(0)
 //                  -> gpba::FlatGraph::build (the adapter) -> gpba_problem Q -> the ORACLE's optimize on Q.
-// tests/test_ref_g2o.py requires the oracle's run on Q to be the oracle's run on P: then the adapter hands the C ABI what the
+// tests/test_whole_path_reference.py requires the oracle's run on Q to be the oracle's run on P: then the adapter hands the C ABI what the
 // graph holds.  (The C ABI itself is exercised on the device by the GPU suite; here libgpba.so is only linked so that the
 // header's calls resolve.)  Built by `make -C oracle _ref` into oracle/_ref/libadapter_check.so.
 #define REF_G2O_DEFINE_STATICS

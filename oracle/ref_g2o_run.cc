@@ -12,7 +12,7 @@
 // Stand-in arithmetic on this path: dense products / inverses, the pivoted LDLT behind LinearSolverDense (third party in the
 // reference too: Eigen::LDLT), quaternion and SE(3) exp / log, the pinhole projection.  What this file restates is only the
 // graph CONSTRUCTION (which vertices and edges exist is the input); built by `make -C oracle _ref` into
-// oracle/_ref/libamc_ref_g2o.so and compared with the oracle in tests/test_ref_g2o.py.
+// oracle/_ref/libamc_ref_g2o.so and compared with the oracle in tests/test_whole_path_reference.py.
 #define REF_G2O_DEFINE_STATICS
 #include "ref_g2o_graph.h"
 

@@ -5,7 +5,7 @@
 // (optimization_algorithm_levenberg.cpp:61-194), 40 iterations, then |e| <= threshold over all edges.
 // PARITY: EdgeVelReproj (error, Jacobian) is pinned against the reference's own G2oTypes.cc (oracle/_ref,
 // tests/test_ref_pin.py), and every hypothesis against the reference's real OptimizeVel graph / solver (ref_g2o_optimize_vel,
-// tests/test_ref_g2o.py: same winner, inlier counts, masks and velocities).
+// tests/test_whole_path_reference.py: same winner, inlier counts, masks and velocities).
 #pragma once
 #include <vector>
 #include <cmath>

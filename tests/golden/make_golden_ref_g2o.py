@@ -4,7 +4,7 @@ oracle/_ref/libamc_ref_g2o.so is g2o's core (hyper graph, optimizable graph, spa
 matrices, the quadratic forms of base_*_edge.hpp, robust kernels, Levenberg-Marquardt, LinearSolverDense) and AMC-SLAM's
 src/G2oTypes.cc, GaussianProcess.cc, Pose3utils.cc, all compiled UNMODIFIED from /root/reference against the stand-in headers
 of oracle/ref_shim/ (oracle/Makefile target _ref; oracle/ref_g2o_run.cc builds the graph the way Optimizer.cc does and calls
-SparseOptimizer::optimize).  This script runs it on seeded problems and stores what it returns; tests/test_ref_g2o.py holds
+SparseOptimizer::optimize).  This script runs it on seeded problems and stores what it returns; tests/test_whole_path_reference.py holds
 the oracle (CPU) and the CUDA path (-m gpu) to these numbers.  Needs /root/reference: build container only; the .npz travels.
 
     python tests/golden/make_golden_ref_g2o.py [case ...]

@@ -381,7 +381,7 @@ _DROP_IN = """
 import sys, numpy as np
 sys.path.insert(0, {root!r} + "/oracle"); sys.path.insert(0, {root!r} + "/amc-slam_b200"); sys.path.insert(0, {root!r} + "/tests")
 import ref_py as R
-import test_ref_g2o as T
+import test_whole_path_reference as T
 key = sys.argv[1]
 G = T.load(key); P = T.mr.make_case(key)
 r = R.adapter_optimize(P, T.mr.ITERS, 0)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for d in ("amc-slam_b200", "oracle", "tests"):
     sys.path.insert(0, os.path.join(ROOT, d))
 import oracle_py as O  # noqa: E402
-import test_ref_g2o as T  # noqa: E402
+import test_whole_path_reference as T  # noqa: E402
 
 mr = T.mr
 print("Oracle (CPU restatement) against the reference's own sources run as they are (oracle/_ref/libamc_ref_g2o.so: g2o core,")
