@@ -24,10 +24,14 @@ def build(force=False):
     if force:
         import shutil
         shutil.rmtree(os.path.join(_HERE, "_ref", "obj"), ignore_errors=True)
-        for so in (_SO, _LM_SO, _G2O_SO):
+        for so in (_SO, _LM_SO, _G2O_SO, os.path.join(_HERE, "_ref", "libadapter_check.so")):
             if os.path.exists(so):
                 os.remove(so)
-    subprocess.check_call(["make", "-C", _HERE, "-s", "-j", str(min(16, os.cpu_count() or 1)), "_ref"])
+    jobs = str(min(16, os.cpu_count() or 1))
+    subprocess.check_call(["make", "-C", _HERE, "-s", "-j", jobs, "_ref_core"])
+    # the adapter check links libgpba.so; where that has not been built yet the three libraries above are still usable
+    if os.path.exists(os.path.join(os.path.dirname(_HERE), "amc-slam_b200", "libgpba.so")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-j", jobs, "_ref/libadapter_check.so"])
     return _SO
 
 
@@ -324,11 +328,16 @@ _ADAPTER_SO = os.path.join(_HERE, "_ref", "libadapter_check.so")
 _ADAPTER = None
 
 
+def adapter_available():
+    build()
+    return os.path.exists(_ADAPTER_SO)
+
+
 def adapter_lib():
     global _ADAPTER
     if _ADAPTER is None:
         if build() is None or not os.path.exists(_ADAPTER_SO):
-            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+            raise RuntimeError("oracle/_ref/libadapter_check.so is not built (needs /root/reference and libgpba.so)")
         import oracle_py
         oracle_py.lib()
         _ADAPTER = C.CDLL(_ADAPTER_SO)

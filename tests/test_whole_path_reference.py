@@ -349,8 +349,8 @@ def test_adapter_flattening_round_trip(oracle_mod, name, kw):
     problem: same counts, and the oracle's optimize on it is the oracle's optimize on the original (rounding apart: the
     poses went through Sophus quaternions).  Without a device GpBaLevenberg fails cleanly and leaves the graph untouched."""
     import ref_py as R
-    if not R.available():
-        pytest.skip("oracle/_ref is not built and /root/reference is absent (GPU box)")
+    if not R.available() or not R.adapter_available():
+        pytest.skip("oracle/_ref/libadapter_check.so is not built (needs /root/reference and libgpba.so)")
     from pygpba import synth
     P = synth.make_problem(name, **kw)
     r = R.adapter_roundtrip(P, mr.ITERS)
@@ -368,8 +368,8 @@ def test_adapter_flattening_round_trip(oracle_mod, name, kw):
 def test_adapter_without_a_device_fails_cleanly():
     import torch
     import ref_py as R
-    if not R.available() or torch.cuda.is_available():
-        pytest.skip("needs oracle/_ref and no CUDA device")
+    if not R.available() or not R.adapter_available() or torch.cuda.is_available():
+        pytest.skip("needs oracle/_ref/libadapter_check.so and no CUDA device")
     from pygpba import synth
     P = synth.make_problem("tiny")
     n, kp = R.adapter_no_device(P)
@@ -403,7 +403,7 @@ def test_adapter_drop_in_on_the_device(key):
     import subprocess
     import sys
     import ref_py as R
-    if not R.available():
+    if not R.available() or not R.adapter_available():
         pytest.skip("oracle/_ref/libadapter_check.so did not travel")
     out = subprocess.run([sys.executable, "-c", _DROP_IN.format(root=os.path.dirname(HERE)), key], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DROP-IN OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
