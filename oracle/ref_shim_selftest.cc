@@ -92,4 +92,46 @@ void shim_se3_mul_act(const double* a7, const double* b7, const double* p3, doub
   store(from7(a7) * Eigen::Vector3d(p3[0], p3[1], p3[2]), ap3);
 }
 
+// what the g2o core uses beyond the edge sources: pivoted LDLT (linear_solver_dense.h:105-110), llt().solve and determinant
+// (base_vertex.hpp:38-41), symmetric eigenvalues (optimizable_graph.cpp:870-880)
+int shim_ldlt(int n, const double* A, const double* b, double* x) {
+  Eigen::LDLT<MatrixXd> ch;
+  ch.compute(load(A, n, n));
+  Eigen::VectorXd::ConstMapType bvec(b, n);
+  Eigen::VectorXd::MapType xvec(x, n);
+  xvec = ch.solve(bvec);
+  return ch.isPositive() ? 1 : 0;
+}
+double shim_llt_det(int n, const double* A, const double* b, double* x) {
+  const MatrixXd M = load(A, n, n);
+  Eigen::VectorXd bv(n);
+  for (int i = 0; i < n; ++i) bv(i) = b[i];
+  store(M.llt().solve(bv), x);
+  return M.determinant();
+}
+void shim_eigenvalues(int n, const double* A, double* ev) {
+  Eigen::SelfAdjointEigenSolver<MatrixXd> es;
+  es.compute(load(A, n, n), Eigen::EigenvaluesOnly);
+  store(es.eigenvalues(), ev);
+}
+// Map as a view over foreign memory, the way block_solver.hpp / base_*_edge.hpp use it: segment += on a mapped vector
+// (matrix_operations.h:38-41), noalias() += on a mapped block, diagonal().array() += lambda and diagonal() = backup
+// (block_solver.hpp:576-602), assignment through a Map of a fixed type (base_multi_edge.hpp), copy of a Map = the same view.
+void shim_map_views(int n, double* vec, double* mat, const double* A, double lambda, double* diag_backup) {
+  Eigen::Map<Eigen::VectorXd> y(vec, n);
+  Eigen::Map<const Eigen::VectorXd> yc(vec, n);
+  const MatrixXd M = load(A, n, n);
+  const Eigen::VectorXd x0 = yc;                         // a value copy of the mapped data
+  y.segment(0, n) += M * x0;                             // vec <- vec + A vec
+  y.segment<2>(1) += Eigen::Vector2d(10.0, 20.0);
+  Eigen::Map<MatrixXd> H(mat, n, n);
+  Eigen::Map<MatrixXd> H2(H);                            // same memory
+  H2.noalias() += M.transpose() * M;                     // mat <- mat + A^T A
+  store(Eigen::VectorXd(H.diagonal()), diag_backup);
+  H.diagonal().array() += lambda;
+  H.block(0, 0, 2, 2) = MatrixXd(Eigen::Matrix2d::Identity() * 7.0);
+  Eigen::Map<Eigen::Matrix<double, 1, 2>> last2(mat + (size_t)n * n - 2);   // a fixed-size view: the last two entries of the last row
+  last2 = Eigen::Matrix<double, 1, 2>(Eigen::Vector2d(-1.0, -2.0).transpose());
+}
+
 }  // extern "C"

@@ -148,3 +148,39 @@ def test_sophus_standin_vs_scipy(S):
         S.shim_se3_mul_act(p(T7), p(T7b), p(d(pt)), p(ab), p(ap))
         np.testing.assert_allclose(T4(ab), E @ sl.expm(hat6(xi2)), atol=1e-12)
         np.testing.assert_allclose(ap, R @ pt + t, atol=1e-12)
+
+
+def test_ldlt_llt_determinant_eigenvalues(S):
+    S.shim_llt_det.restype = C.c_double
+    rng = np.random.default_rng(6)
+    for n in (1, 3, 7, 24, 60):
+        B = rng.normal(size=(n, n)); A = B @ B.T + 0.5 * np.eye(n); b = rng.normal(size=n)
+        x = np.zeros(n)
+        assert S.shim_ldlt(n, p(d(A)), p(d(b)), p(x)) == 1
+        np.testing.assert_allclose(x, np.linalg.solve(A, b), rtol=1e-9, atol=1e-11)
+        x2 = np.zeros(n)
+        det = S.shim_llt_det(n, p(d(A)), p(d(b)), p(x2))
+        np.testing.assert_allclose(x2, np.linalg.solve(A, b), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(det, np.linalg.det(A), rtol=1e-9)
+        ev = np.zeros(n); S.shim_eigenvalues(n, p(d(A)), p(ev))
+        np.testing.assert_allclose(ev, np.linalg.eigvalsh(A), rtol=1e-9, atol=1e-11)
+    # an indefinite matrix: still solved (pivoted), reported as not positive (g2o's LinearSolverDense then returns false)
+    A = np.diag([2.0, -1.0, 3.0]) + 0.1; b = np.ones(3); x = np.zeros(3)
+    assert S.shim_ldlt(3, p(d(A)), p(d(b)), p(x)) == 0
+    np.testing.assert_allclose(x, np.linalg.solve(A, b), atol=1e-12)
+
+
+def test_map_views_write_through(S):
+    rng = np.random.default_rng(7)
+    n = 5
+    A = rng.normal(size=(n, n)); v = rng.normal(size=n); M = rng.normal(size=(n, n))
+    vec = d(v.copy()); mat = d(M.copy()); backup = np.zeros(n)
+    S.shim_map_views(n, p(vec), p(mat), p(d(A)), C.c_double(0.25), p(backup))
+    ev = v + A @ v; ev[1] += 10.0; ev[2] += 20.0
+    np.testing.assert_allclose(vec, ev, atol=1e-13)
+    E = M + A.T @ A
+    np.testing.assert_allclose(backup, np.diag(E), atol=1e-13)
+    E[np.arange(n), np.arange(n)] += 0.25
+    E[:2, :2] = 7.0 * np.eye(2)
+    E[n - 1, n - 2:] = [-1.0, -2.0]
+    np.testing.assert_allclose(mat, E, atol=1e-13)
