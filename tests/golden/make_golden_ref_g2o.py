@@ -39,6 +39,8 @@ def make_case(key):
         return mg.make_case(mg.CASES[key])
     if key == "c1_full":
         return synth.make_problem("c1")
+    if key == "loop_full":      # global BA after a loop closure at its preset size: 60 keyframes, 3 000 points, Huber on the priors
+        return synth.make_problem("loop")
     if key == "stereo":
         return synth.add_stereo(synth.make_problem("c1", n_pt=500, seed=39), 0.5, gp_fraction=0.4)
     if key == "far_start":
@@ -59,7 +61,7 @@ def make_case(key):
     raise KeyError(key)
 
 
-CASES = list(mg.CASES) + ["c1_full", "stereo", "far_start", "levels"]
+CASES = list(mg.CASES) + ["c1_full", "loop_full", "stereo", "far_start", "levels"]
 
 
 def samples(P):
