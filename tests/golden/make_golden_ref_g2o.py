@@ -41,6 +41,8 @@ def make_case(key):
         return synth.make_problem("c1")
     if key == "loop_full":      # global BA after a loop closure at its preset size: 60 keyframes, 3 000 points, Huber on the priors
         return synth.make_problem("loop")
+    if key == "loop_200":       # the C4 family cut to 200 keyframes driven twice round a 100-keyframe loop, 20 000 points
+        return synth.make_problem("loop", n_kf=200, n_pt=20000, lap=100, seed=14)
     if key == "stereo":
         return synth.add_stereo(synth.make_problem("c1", n_pt=500, seed=39), 0.5, gp_fraction=0.4)
     if key == "far_start":
@@ -62,6 +64,7 @@ def make_case(key):
 
 
 CASES = list(mg.CASES) + ["c1_full", "loop_full", "stereo", "far_start", "levels"]
+SLOW_CASES = ["loop_200"]      # minutes through oracle/_ref; minted on request, tested when the file is there
 
 
 def samples(P):

@@ -95,6 +95,22 @@ def check_flags(flags, P, G):
     assert np.array_equal(np.asarray(flags)[~excl], ref[~excl])
 
 
+@pytest.mark.parametrize("key", mr.SLOW_CASES)
+def test_oracle_matches_reference_run_large(oracle_mod, key):
+    """The C4 family at 200 keyframes (loop driven twice, 20 000 points, ~200k observations, 2 388 pose unknowns): the
+    oracle's block-sparse Cholesky with its fill-reducing order against g2o's block solver over a dense LDLT."""
+    if not os.path.exists(os.path.join(HERE, "golden", "ref_g2o_" + key + ".npz")):
+        pytest.skip("not minted (minutes through oracle/_ref)")
+    G = load(key)
+    P = mr.make_case(key)
+    assert mr.mg.input_checksum(P) == str(G["input_sha256"])
+    o = oracle_mod.Oracle(P, threads=min(8, os.cpu_count() or 1))
+    tr = o.optimize(mr.ITERS).summary()
+    check_against_reference(tr, o.state(), o.edge_chi2(), P, G, cost_rtol=1e-9, pos_tol=1e-8, ang_tol=1e-9, vel_tol=1e-7,
+                            pt_tol=1e-6, chi_rtol=1e-6, chi_atol=1e-8)
+    check_flags(o.outlier_flags(Thresholds.local_gpba()), P, G)
+
+
 def test_reference_run_is_reproduced_live(oracle_mod):
     """Where oracle/_ref is present: the committed numbers are what the committed script produces."""
     import ref_py as R
