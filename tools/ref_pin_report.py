@@ -41,6 +41,28 @@ print("%-14s %8d %6d  %-30s %10.1e %10.1e %10.1e %10.1e %8s   (oracle side = the
     "c2 (BASELINE)", int(F["n_obs"]), n, ("same " if list(F["tr_trials"][0][:n]) == list(G["trials"]) else "DIFFERENT ") + str([int(t) for t in G["trials"]]),
     np.abs(F["tr_chi2_after"][0][:n] - G["chi2_stored"]).max() / G["chi2_stored"].min(), np.abs(F["kf_pose"][:, 4:] - G["kf_pose"][:, 4:]).max(),
     T.angle(F["kf_pose"][:, :4], G["kf_pose"][:, :4]).max(), np.abs(F["pt_xyz"] - G["pt_xyz"]).max(), "%d/%d" % (int((a != b).sum()), int(b.sum()))))
+p3 = os.path.join(ROOT, "tests", "golden", "ref_g2o_c3.npz")
+if os.path.exists(p3):
+    F = np.load(os.path.join(ROOT, "tests", "golden", "baseline_c3.npz")); G = np.load(p3)
+    a, b = np.unpackbits(F["flags_packed"])[:int(F["n_obs"])], np.unpackbits(G["flags_packed"])[:int(F["n_obs"])]
+    same = all([int(t) for t in G["round%d_trials" % r]] == [int(t) for t in F["tr_trials"][r][:int(F["tr_n_iters"][r])]] for r in range(4))
+    cost = max(np.abs(F["tr_chi2_after"][r][:int(F["tr_n_iters"][r])] - G["round%d_chi2_stored" % r]).max() / G["round%d_chi2_stored" % r].min() for r in range(4))
+    print("%-14s %8d %6s  %-30s %10.1e %10.1e %10.1e %10.1e %8s   (BASELINE C3 as stated: 30 %% outliers, 4 rejection rounds; oracle side = baseline_c3.npz)" % (
+        "c3 (BASELINE)", int(F["n_obs"]), "+".join(str(int(x)) for x in F["tr_n_iters"]), ("same" if same else "DIFFERENT") + " in all 4 rounds", cost,
+        np.abs(F["kf_pose"][:, 4:] - G["kf_pose"][:, 4:]).max(), T.angle(F["kf_pose"][:, :4], G["kf_pose"][:, :4]).max(),
+        np.abs(F["pt_xyz"] - G["pt_xyz"]).max(), "%d/%d" % (int((a != b).sum()), int(b.sum()))))
+for key in mr.SLOW_CASES:
+    if not os.path.exists(os.path.join(ROOT, "tests", "golden", "ref_g2o_" + key + ".npz")):
+        continue
+    G = T.load(key); P = mr.make_case(key)
+    o = O.Oracle(P, threads=8); tr = o.optimize(mr.ITERS).summary()
+    kp, kv, pt = o.state(); ip, io = mr.samples(P); n = tr["n_iters"]
+    acc = [i for i in range(n) if tr["chi2_after"][i] < tr["chi2_before"][i]]
+    fl = o.outlier_flags(T.Thresholds.local_gpba()); ref_fl = np.unpackbits(G["flags_packed"])[:P.n_obs]
+    print("%-14s %8d %6d  %-30s %10.1e %10.1e %10.1e %10.1e %8s   (%d keyframes, sparse block Cholesky in the oracle, dense LDLT in the reference run)" % (
+        key, P.n_obs, n, ("same " if tr["trials"] == [int(t) for t in G["trials"]] else "DIFFERENT ") + str(tr["trials"]),
+        max(abs(tr["chi2_after"][i] - G["chi2_stored"][i]) / G["chi2_stored"][i] for i in acc), np.abs(kp[:, 4:] - G["kf_pose"][:, 4:]).max(),
+        T.angle(kp[:, :4], G["kf_pose"][:, :4]).max(), np.abs(pt[ip] - G["pt_xyz"]).max(), "%d/%d" % (int((fl != ref_fl).sum()), int(ref_fl.sum())), P.n_kf))
 print("\nflags = observations classified differently by LocalGPBA's inlier check / observations the reference flags.")
 # rejection rounds
 G = np.load(os.path.join(ROOT, "tests", "golden", "ref_g2o_rounds_c3.npz")); P = mr.make_rounds_case()
