@@ -6,7 +6,11 @@ base_*_edge.hpp with robust kernels, LinearSolverDense, Levenberg-Marquardt) and
 Pose3utils.cc, compiled unmodified into oracle/_ref/libamc_ref_g2o.so against stand-in headers for the absent Eigen / Sophus
 (oracle/ref_g2o_run.cc, tests/golden/make_golden_ref_g2o.py; the stand-ins are checked in tests/test_ref_shim.py).  Cases: the
 four seeded problems of the oracle's own fixtures, BASELINE config C1 as it is (10 keyframes, 20k observations, 10 LM
-iterations), stereo edges incl. EdgeStereoGP, a far start with 6 rejected trials, inactive edges and edges without kernel.
+iterations), the global BA after a loop closure, stereo edges incl. EdgeStereoGP, a far start with 6 rejected trials, inactive
+edges and edges without kernel; BASELINE C2 and C3 (as stated: 491k observations, 30 % outliers, four rejection rounds) and
+the C4 family at 200 keyframes against the oracle's committed fixtures; LocalGPBA's inlier flags; the two-stage extrinsic
+self-calibration; the pose-only GP optimisation; the velocity RANSAC; the essential graph; and the reference-side binding
+(adapter/g2o_gpba_solver.h) compiled against the real g2o headers.
 
 Tolerances are BASELINE.json's north star or tighter: identical iteration and trial counts, cost 1e-6 relative (held: 1e-9),
 poses 1e-6 m / 1e-7 rad (held: 1e-8 m on the CPU).  CPU: the oracle; -m gpu: the CUDA path through the C ABI.
