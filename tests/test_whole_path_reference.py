@@ -126,7 +126,7 @@ def test_reference_run_is_reproduced_live(oracle_mod):
         for f in ("n", "trials", "sizes"):
             assert np.array_equal(out[f], G[f]), (key, f)
         for f in ("chi2_start", "chi2_stored", "lam", "kf_pose", "kf_vel", "pt_xyz", "edge_chi2"):
-            np.testing.assert_allclose(out[f], G[f], rtol=1e-12, atol=1e-14, err_msg=key + " " + f)
+            np.testing.assert_allclose(out[f], G[f], rtol=1e-9, atol=1e-12, err_msg=key + " " + f)   # (libm may differ between machines)
 
 
 @pytest.mark.parametrize("key", sorted(mr.POSE_GRAPHS))
