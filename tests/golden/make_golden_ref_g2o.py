@@ -43,6 +43,8 @@ def make_case(key):
         return synth.make_problem("loop")
     if key == "loop_200":       # the C4 family cut to 200 keyframes driven twice round a 100-keyframe loop, 20 000 points
         return synth.make_problem("loop", n_kf=200, n_pt=20000, lap=100, seed=14)
+    if key == "loop_500":       # half of C4's trajectory: 500 keyframes round a 250-keyframe loop, 50 000 points, 5 988 pose unknowns
+        return synth.make_problem("loop", n_kf=500, n_pt=50000, lap=250, seed=15)
     if key == "stereo":
         return synth.add_stereo(synth.make_problem("c1", n_pt=500, seed=39), 0.5, gp_fraction=0.4)
     if key == "far_start":

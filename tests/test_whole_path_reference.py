@@ -397,6 +397,30 @@ def test_adapter_without_a_device_fails_cleanly():
     assert np.abs(kp - P.kf_pose).max() <= 1e-15             # nothing was written back
 
 
+def test_adapters_compile_against_the_reference_headers(tmp_path):
+    """Both reference-side bindings, as a maintainer would compile them inside the AMC-SLAM tree: adapter/g2o_gpba_solver.h
+    against the reference's REAL g2o headers and G2oTypes.h, adapter/tracking_gpba.h against MultiFrame / MapPoint declared
+    with the reference's own member types (oracle/ref_shim_tracking/Frame.h); Eigen / Sophus are the stand-ins."""
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "include")):
+        pytest.skip("/root/reference is absent (GPU box)")
+    root = os.path.dirname(HERE)
+    a = tmp_path / "solver.cc"
+    a.write_text('#include "g2o_gpba_solver.h"\n#include "Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.h"\n'
+                 'void f(g2o::SparseOptimizer& o) { o.setAlgorithm(new gpba::GpBaLevenberg()); o.initializeOptimization(0); o.optimize(5); }\n'
+                 'void g(g2o::SparseOptimizer& o) { o.setAlgorithm(new g2o::OptimizationAlgorithmLevenberg(new gpba::GpBaBlockSolver())); o.optimize(5); }\n')
+    b = tmp_path / "tracking.cc"
+    b.write_text('#include "tracking_gpba.h"\n'
+                 'int f(ORB_SLAM3::MultiFrame* F) { return gpba::PoseGPOptimizationFromeLastFrame(F, true); }\n')
+    base = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unused-variable", "-I", root + "/adapter", "-I", root + "/include"]
+    r1 = subprocess.run(base + ["-DCONVERTER_H", "-I", ref, "-I", root + "/oracle/ref_shim", "-I", ref + "/include", str(a)], capture_output=True, text=True)
+    assert r1.returncode == 0, r1.stderr[-3000:]
+    r2 = subprocess.run(base + ["-I", root + "/oracle/ref_shim_tracking", "-I", root + "/oracle/ref_shim", "-I", ref + "/include", str(b)],
+                        capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr[-3000:]
+
+
 _DROP_IN = """
 import sys, numpy as np
 sys.path.insert(0, {root!r} + "/oracle"); sys.path.insert(0, {root!r} + "/amc-slam_b200"); sys.path.insert(0, {root!r} + "/tests")
