@@ -333,6 +333,8 @@ struct Oracle {
 
   // ---- backup stack (BaseVertex::push/pop)
   struct Snapshot { std::vector<KfState> kf; std::vector<V3> pt; std::vector<SE3> Tbc; };
+  std::vector<KfState> eval_kf;
+  std::vector<SE3> eval_Tbc;
   // ---- extrinsic self-calibration: VertexExtrinsic + EdgeExtrinsicPrior of LocalGPBA (src/Optimizer.cc:983-995, 1228-1240).
   // An extrinsic is a non-marginalized 6-dim vertex whose id follows every keyframe id (:986), so its Hessian block follows
   // the keyframes' (sparse_optimizer.cpp:166-190).  Here it occupies a 12-slot whose last six dimensions are padding (zero
@@ -583,6 +585,7 @@ struct Oracle {
 
   void compute_errors() {  // SparseOptimizer::computeActiveErrors
     const double t_res = now();
+    eval_kf = kf; eval_Tbc = Tbc;   // the state the stored errors belong to (stale-error quirk: may differ from the estimate)
     for (int i = 0; i < n_velp; ++i)
       if (velp_active[i]) velp_err[i] = kf[velp_kf[i]].vel[2];
     for (int i = 0; i < n_prior; ++i)
@@ -1271,6 +1274,17 @@ int oracle_rejection_rounds(void* h, int n_rounds, int iters, const gpba_thresho
 // ---- math probes used by tests/test_oracle_*.py (pin the Lie / GP layer against the numpy mirror)
 static SE3 se3_from7(const double* p) { SE3 T; T.q = {p[0], p[1], p[2], p[3]}; T.t[0] = p[4]; T.t[1] = p[5]; T.t[2] = p[6]; return T; }
 static void se3_to7(const SE3& T, double* p) { p[0] = T.q.x; p[1] = T.q.y; p[2] = T.q.z; p[3] = T.q.w; p[4] = T.t[0]; p[5] = T.t[1]; p[6] = T.t[2]; }
+// keyframe states / extrinsics of the last EVALUATED state (what gpba_download_evaluated_state hands back on the device)
+int oracle_download_evaluated_state(void* h, double* kf_pose, double* kf_vel, double* cam_Tbc) {
+  Oracle* o = ORA(h);
+  if (o->eval_kf.empty()) { o->eval_kf = o->kf; o->eval_Tbc = o->Tbc; }
+  for (int k = 0; k < o->n_kf; ++k) {
+    se3_to7(o->eval_kf[k].Twb, kf_pose + 7 * k);
+    for (int i = 0; i < 6; ++i) kf_vel[6 * k + i] = o->eval_kf[k].vel[i];
+  }
+  if (cam_Tbc) for (int c = 0; c < o->n_cam; ++c) se3_to7(o->eval_Tbc[c], cam_Tbc + 7 * c);
+  return 0;
+}
 static V6 v6(const double* p) { V6 v; for (int i = 0; i < 6; ++i) v[i] = p[i]; return v; }
 // Optimizer::PoseGPOptimizationFromeLastFrame for every frame of the batch (oracle/pose_only.h)
 int oracle_pose_optimize(const gpba_pose_batch* B, double* cur_pose_out, double* cur_vel_out, double* prev_pose_out, double* prev_vel_out,

@@ -68,4 +68,27 @@ int ref_adapter_optimize(const gpba_problem* P, int iters, int device, double* k
   return n;
 }
 
+// Seam B: gpba::GpBaBlockSolver as the g2o::Solver of the reference's STOCK OptimizationAlgorithmLevenberg -- g2o evaluates the
+// residuals and applies oplus on its own objects, the level-1 entry points do the linear algebra.
+int ref_adapter_block_solver(const gpba_problem* P, int iters, int device, double* kf_pose_out, double* kf_vel_out, double* pt_out,
+                             double* edge_chi2_out, gpba_lm_trace* tr) {
+  BaGraph G(P, 0);
+  gpba::GpBaBlockSolver* bs = new gpba::GpBaBlockSolver(P->linear_solver, device);
+  g2o::OptimizationAlgorithmLevenberg* alg = new g2o::OptimizationAlgorithmLevenberg(bs);
+  if (P->lambda_init > 0) alg->setUserLambdaInit(P->lambda_init);
+  G.optimizer.setAlgorithm(alg);
+  G.solver = alg;
+  if (tr) { std::memset(tr, 0, sizeof(*tr)); tr->result = GPBA_RESULT_OK; }
+  Recorder rec;
+  rec.opt = &G.optimizer; rec.alg = alg; rec.tr = tr;
+  G.optimizer.addPostIterationAction(&rec);
+  G.optimizer.initializeOptimization(0);
+  if (tr) { G.optimizer.computeActiveErrors(); tr->chi2_before[0] = G.optimizer.activeRobustChi2(); }
+  const int n = G.optimizer.optimize(iters);
+  if (tr) tr->n_iters = n;
+  G.optimizer.removePostIterationAction(&rec);
+  G.read_back(P, kf_pose_out, kf_vel_out, pt_out, edge_chi2_out);
+  return n;
+}
+
 }  // extern "C"

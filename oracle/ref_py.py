@@ -372,3 +372,29 @@ def adapter_optimize(prob, iters=10, device=0):
     L.ref_adapter_optimize.restype = C.c_int
     n = L.ref_adapter_optimize(C.byref(c), int(iters), int(device), _p(kp), _p(kv), _p(pt), _p(chi), C.byref(tr))
     return dict(n=n, kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, trace=tr.summary())
+
+
+# ---- the binding's host logic on a TEST DOUBLE of the C ABI (oracle/abi_double.cc; no GPU needed, never shipped) ----------
+_DOUBLE_SO = os.path.join(_HERE, "_ref", "libadapter_on_double.so")
+_DOUBLE = None
+
+
+def adapter_on_double(prob, iters=10, seam="A"):
+    """seam "A": gpba::GpBaLevenberg, seam "B": gpba::GpBaBlockSolver under the stock g2o LM -- inside the reference's real
+    SparseOptimizer, with the C ABI answered by the CPU oracle (test double).  Returns like g2o_optimize."""
+    global _DOUBLE
+    from pygpba.problem import LmTrace
+    if _DOUBLE is None:
+        if build() is None or not os.path.exists(_DOUBLE_SO):
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        import oracle_py
+        oracle_py.lib()
+        _DOUBLE = C.CDLL(_DOUBLE_SO)
+        _DOUBLE.ref_adapter_optimize.restype = C.c_int
+        _DOUBLE.ref_adapter_block_solver.restype = C.c_int
+    c = prob.to_c()
+    kp = np.zeros((prob.n_kf, 7)); kv = np.zeros((prob.n_kf, 6)); pt = np.zeros((prob.n_pt, 3)); chi = np.zeros(prob.n_obs)
+    tr = LmTrace()
+    fn = _DOUBLE.ref_adapter_optimize if seam == "A" else _DOUBLE.ref_adapter_block_solver
+    n = fn(C.byref(c), int(iters), 0, _p(kp), _p(kv), _p(pt), _p(chi), C.byref(tr))
+    return dict(n=n, kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, trace=tr.summary())
