@@ -68,7 +68,21 @@ def test_product_does_not_reference_oracle():
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 if re.search(r"oracle_py|libgpba_oracle|oracle/|numpy_mirror", txt):
                     bad.append(os.path.join(base, f))
+    # the boundary headers, the reference-side bindings and the example neither include nor link anything of the oracle, the
+    # compiled reference (oracle/_ref) or the C-ABI test double (oracle/abi_double.cc)
+    for d in ("include", "adapter", "examples"):
+        for base, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r'#include\s*[<"][^>"]*(oracle|ref_shim|_ref)|gpba_oracle|abi_double|oracle_[a-z_]+\(', txt):
+                    bad.append(os.path.join(base, f))
     assert not bad, bad
+    # and the shipped library has no dependency on them
+    import subprocess
+    so = os.path.join(ROOT, "amc-slam_b200", "libgpba.so")
+    if os.path.exists(so):
+        needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+        assert "oracle" not in needed and "abi_double" not in needed and "_ref" not in needed
 
 
 def _build_c_example(tmpdir):
