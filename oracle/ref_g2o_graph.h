@@ -78,8 +78,8 @@ struct BaGraph {
   GaussianProcess gp;
   std::vector<PinholeStandIn> cams;
   std::vector<GeometricCamera*> cam_ptrs;
-  g2o::SparseOptimizer optimizer;                      // destroyed first (declared last of the owners below is not needed:
-  g2o::OptimizationAlgorithmLevenberg* solver = nullptr;   // the graph only holds pointers into gp / cams)
+  g2o::SparseOptimizer optimizer;                      // declared after gp / cams, so destroyed before them: the edges point into both
+  g2o::OptimizationAlgorithmLevenberg* solver = nullptr;   // owned by the optimizer
   std::vector<VertexPoseVel*> vkf;
   std::vector<g2o::VertexSBAPointXYZ*> vpt;
   std::vector<g2o::OptimizableGraph::Edge*> eobs;
