@@ -91,4 +91,31 @@ int ref_adapter_block_solver(const gpba_problem* P, int iters, int device, doubl
   return n;
 }
 
+// LocalGPBA's two stages through the binding (src/Optimizer.cc:1219-1240): the graph holds VertexExtrinsic / EdgeMonoGPExtrinsic /
+// EdgeExtrinsicPrior; stage 1 with the extrinsics fixed, stage 2 with those of `ext_free` released -- each stage one
+// optimize() of gpba::GpBaLevenberg, which passes the released extrinsics and their priors through gpba_set_extrinsics and
+// writes the calibrated extrinsics back into the VertexExtrinsic objects.
+int ref_adapter_ext(const gpba_problem* P, const uint8_t* ext_free, const double* prior_q, const double* prior_info, int it1, int it2,
+                    int device, double* kf_pose_out, double* kf_vel_out, double* pt_out, double* Tbc_out, gpba_lm_trace* tr1,
+                    gpba_lm_trace* tr2) {
+  ExtGraph G(P, prior_q, prior_info);
+  gpba::GpBaLevenberg* alg = new gpba::GpBaLevenberg(P->linear_solver, device);
+  if (P->lambda_init > 0) alg->setUserLambdaInit(P->lambda_init);
+  G.optimizer.setAlgorithm(alg);
+  G.solver = nullptr;
+  alg->setMaxIterations(it1);
+  G.optimizer.initializeOptimization();
+  G.optimizer.computeActiveErrors();
+  int n = G.optimizer.optimize(it1);
+  if (tr1) *tr1 = alg->trace();
+  for (int c = 0; c < P->n_cam - 1; ++c) if (ext_free[c]) G.vext[c]->setFixed(false);
+  alg->setMaxIterations(it2);
+  G.optimizer.initializeOptimization();
+  G.optimizer.computeActiveErrors();
+  n = G.optimizer.optimize(it2);
+  if (tr2) *tr2 = alg->trace();
+  G.read_back(P, kf_pose_out, kf_vel_out, pt_out, Tbc_out);
+  return n;
+}
+
 }  // extern "C"

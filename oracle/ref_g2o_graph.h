@@ -223,4 +223,124 @@ struct BaGraph {
   }
 };
 
+// The graph of LocalGPBA with extrinsic vertices (src/Optimizer.cc:983-995, 1100-1135): every asynchronous camera a
+// VertexExtrinsic (fixed at first) with an EdgeExtrinsicPrior, every GP observation an EdgeMonoGPExtrinsic.
+struct ExtGraph {
+  GaussianProcess gp;
+  std::vector<PinholeStandIn> cams;
+  std::vector<GeometricCamera*> cam_ptrs;
+  g2o::SparseOptimizer optimizer;
+  g2o::OptimizationAlgorithmLevenberg* solver = nullptr;
+  std::vector<VertexPoseVel*> vkf;
+  std::vector<VertexExtrinsic*> vext;
+  std::vector<g2o::VertexSBAPointXYZ*> vpt;
+  ExtGraph(const gpba_problem* P, const double* prior_q, const double* prior_info) : gp(BaGraph::make_gp(P)) {
+    for (int c = 0; c < P->n_cam; ++c) cams.emplace_back(P->cam_intr + 4 * c);
+    for (auto& c : cams) cam_ptrs.push_back(&c);
+    MultiKeyFrame::mTbc.clear();
+    for (int c = 0; c < P->n_cam; ++c) MultiKeyFrame::mTbc.push_back(from7(P->cam_Tbc + 7 * c));
+    MultiFrame::mTbc = MultiKeyFrame::mTbc;
+
+    g2o::BlockSolverX::LinearSolverType* linearSolver = new g2o::LinearSolverDense<g2o::BlockSolverX::PoseMatrixType>();
+    g2o::BlockSolverX* solver_ptr = new g2o::BlockSolverX(linearSolver);
+    solver = new g2o::OptimizationAlgorithmLevenberg(solver_ptr);
+    if (P->lambda_init > 0) solver->setUserLambdaInit(P->lambda_init);
+    optimizer.setAlgorithm(solver);
+    optimizer.setVerbose(false);
+
+    vkf.resize(P->n_kf);
+    for (int k = 0; k < P->n_kf; ++k) {
+      PoseVelocity pv;
+      pv.Twb = from7(P->kf_pose + 7 * k);
+      for (int i = 0; i < 6; ++i) pv.Vel(i) = P->kf_vel[6 * k + i];
+      pv.time = P->kf_time[k]; pv.bf = P->bf; pv.vpCameras = cam_ptrs;
+      VertexPoseVel* v = new VertexPoseVel();
+      v->setEstimate(pv);
+      v->setId(k);
+      v->setFixed(P->kf_fixed[k] != 0);
+      optimizer.addVertex(v);
+      vkf[k] = v;
+    }
+    for (int i = 0; i < P->n_velp; ++i) {
+      EdgeVelocity* e = new EdgeVelocity();
+      e->setVertex(0, vkf[P->velp_kf[i]]);
+      e->setInformation(gp.mQcInv.block<1, 1>(2, 2));
+      optimizer.addEdge(e);
+    }
+    for (int i = 0; i < P->n_prior; ++i) {
+      EdgeGaussianPrior* e = new EdgeGaussianPrior();
+      e->setVertex(0, vkf[P->prior_kf1[i]]);
+      e->setVertex(1, vkf[P->prior_kf2[i]]);
+      if (P->huber_prior > 0) { g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber; e->setRobustKernel(rk); rk->setDelta(P->huber_prior); }
+      e->setInformation(gp.QiInv(P->kf_time[P->prior_kf2[i]] - P->kf_time[P->prior_kf1[i]]));
+      optimizer.addEdge(e);
+    }
+    // ---- extrinsic vertices with their rotation priors (:983-995), ids between the keyframes and the points
+    vext.resize(P->n_cam - 1);
+    for (int c = 0; c < P->n_cam - 1; ++c) {
+      VertexExtrinsic* v = new VertexExtrinsic(MultiKeyFrame::mTbc[c].cast<double>());
+      v->setId(P->n_kf + c);
+      v->setFixed(true);
+      optimizer.addVertex(v);
+      vext[c] = v;
+      EdgeExtrinsicPrior* e = new EdgeExtrinsicPrior(Sophus::SO3d::fromQuaternion(prior_q[4 * c], prior_q[4 * c + 1], prior_q[4 * c + 2], prior_q[4 * c + 3]));
+      e->setVertex(0, v);
+      Eigen::Matrix3d W;
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) W(i, j) = prior_info[9 * c + 3 * i + j];
+      e->setInformation(W);
+      optimizer.addEdge(e);
+    }
+    vpt.resize(P->n_pt);
+    for (int p = 0; p < P->n_pt; ++p) {
+      g2o::VertexSBAPointXYZ* vP = new g2o::VertexSBAPointXYZ();
+      vP->setEstimate(Eigen::Vector3d(P->pt_xyz[3 * p], P->pt_xyz[3 * p + 1], P->pt_xyz[3 * p + 2]));
+      vP->setId(P->n_kf + P->n_cam + p);
+      vP->setMarginalized(true);
+      optimizer.addVertex(vP);
+      vpt[p] = vP;
+    }
+    for (int64_t i = 0; i < P->n_obs; ++i) {
+      const int r = P->obs_rec[i], kf1 = P->rec_kf1[r], kf2 = P->rec_kf2[r], cam = P->rec_cam[r];
+      const double ur = P->obs_ur ? P->obs_ur[i] : -1.0, w = P->obs_inv_sigma2[i];
+      const unsigned flags = P->obs_flags ? P->obs_flags[i] : 0u;
+      g2o::OptimizableGraph::Edge* edge = nullptr;
+      double delta = P->huber_mono;
+      if (kf1 >= 0) {   // :1118-1135
+        EdgeMonoGPExtrinsic* e = new EdgeMonoGPExtrinsic(cam, P->rec_t[r], &gp);
+        e->setVertex(0, vkf[kf1]); e->setVertex(1, vkf[kf2]); e->setVertex(2, vpt[P->obs_pt[i]]); e->setVertex(3, vext[cam]);
+        e->setMeasurement(Eigen::Vector2d(P->obs_u[i], P->obs_v[i]));
+        e->setInformation(Eigen::Matrix2d::Identity() * w);
+        edge = e;
+      } else if (ur < 0) {
+        EdgeMono* e = new EdgeMono();
+        e->setVertex(0, vkf[kf2]); e->setVertex(1, vpt[P->obs_pt[i]]);
+        e->setMeasurement(Eigen::Vector2d(P->obs_u[i], P->obs_v[i]));
+        e->setInformation(Eigen::Matrix2d::Identity() * w);
+        edge = e;
+      } else {
+        EdgeStereo* e = new EdgeStereo();
+        e->setVertex(0, vkf[kf2]); e->setVertex(1, vpt[P->obs_pt[i]]);
+        e->setMeasurement(Eigen::Vector3d(P->obs_u[i], P->obs_v[i], ur));
+        e->setInformation(Eigen::Matrix3d::Identity() * w);
+        edge = e;
+        delta = P->huber_stereo;
+      }
+      if (delta > 0 && !(flags & GPBA_OBS_NO_KERNEL)) { g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber; edge->setRobustKernel(rk); rk->setDelta(delta); }
+      if (flags & GPBA_OBS_LEVEL1) edge->setLevel(1);
+      optimizer.addEdge(edge);
+    }
+  }
+  void read_back(const gpba_problem* P, double* kf_pose_out, double* kf_vel_out, double* pt_out, double* Tbc_out) const {
+    for (int k = 0; k < P->n_kf; ++k) {
+      if (kf_pose_out) to7(vkf[k]->estimate().Twb, kf_pose_out + 7 * k);
+      if (kf_vel_out) for (int i = 0; i < 6; ++i) kf_vel_out[6 * k + i] = vkf[k]->estimate().Vel(i);
+    }
+    if (pt_out) for (int p = 0; p < P->n_pt; ++p) for (int i = 0; i < 3; ++i) pt_out[3 * p + i] = vpt[p]->estimate()(i);
+    if (Tbc_out) {
+      for (int c = 0; c < P->n_cam - 1; ++c) to7(vext[c]->estimate(), Tbc_out + 7 * c);
+      to7(MultiKeyFrame::mTbc.back(), Tbc_out + 7 * (P->n_cam - 1));
+    }
+  }
+};
+
 }  // namespace

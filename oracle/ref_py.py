@@ -398,3 +398,23 @@ def adapter_on_double(prob, iters=10, seam="A"):
     fn = _DOUBLE.ref_adapter_optimize if seam == "A" else _DOUBLE.ref_adapter_block_solver
     n = fn(C.byref(c), int(iters), 0, _p(kp), _p(kv), _p(pt), _p(chi), C.byref(tr))
     return dict(n=n, kf_pose=kp, kf_vel=kv, pt_xyz=pt, edge_chi2=chi, trace=tr.summary())
+
+
+def adapter_ext_on_double(prob, ext_free, prior_q, prior_info, it1=10, it2=10):
+    """LocalGPBA's two stages through gpba::GpBaLevenberg on the graph with extrinsic vertices, C ABI = the test double."""
+    from pygpba.problem import LmTrace
+    adapter_on_double  # noqa: B018  (the loader below is shared)
+    global _DOUBLE
+    if _DOUBLE is None:
+        import oracle_py
+        build(); oracle_py.lib()
+        _DOUBLE = C.CDLL(_DOUBLE_SO)
+        _DOUBLE.ref_adapter_optimize.restype = C.c_int
+        _DOUBLE.ref_adapter_block_solver.restype = C.c_int
+    c = prob.to_c()
+    kp = np.zeros((prob.n_kf, 7)); kv = np.zeros((prob.n_kf, 6)); pt = np.zeros((prob.n_pt, 3)); T = np.zeros((prob.n_cam, 7))
+    t1, t2 = LmTrace(), LmTrace()
+    f = np.ascontiguousarray(ext_free, np.uint8); q = _d(prior_q); w = _d(prior_info)
+    _DOUBLE.ref_adapter_ext.restype = C.c_int
+    n = _DOUBLE.ref_adapter_ext(C.byref(c), _p(f), _p(q), _p(w), int(it1), int(it2), 0, _p(kp), _p(kv), _p(pt), _p(T), C.byref(t1), C.byref(t2))
+    return dict(n=n, kf_pose=kp, kf_vel=kv, pt_xyz=pt, Tbc=T, stage1=t1.summary(), stage2=t2.summary())

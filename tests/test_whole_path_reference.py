@@ -415,6 +415,23 @@ def test_adapter_host_logic_inside_the_real_optimizer(key, seam):
         np.testing.assert_allclose(r["edge_chi2"][io], G["edge_chi2"], rtol=1e-6, atol=1e-8)
 
 
+@pytest.mark.parametrize("key", sorted(mr.EXT_CASES))
+def test_adapter_extrinsic_stages_inside_the_real_optimizer(key):
+    """LocalGPBA's two stages through gpba::GpBaLevenberg on the reference's real graph with VertexExtrinsic /
+    EdgeMonoGPExtrinsic / EdgeExtrinsicPrior (C ABI = the test double): the binding recognises the released extrinsics and
+    their priors, hands them over through gpba_set_extrinsics and writes the calibrated extrinsics back into the
+    VertexExtrinsic objects -- which then hold what the reference's own two-stage run leaves there."""
+    import ref_py as R
+    if not R.available():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent (GPU box)")
+    G = np.load(os.path.join(HERE, "golden", "ref_g2o_" + key + ".npz"))
+    P, free, q_ini, info3 = mr.make_ext_case(key)
+    r = R.adapter_ext_on_double(P, G["freed"], q_ini, info3, mr.EXT_ITERS, mr.EXT_ITERS)
+    check_ext(r["stage1"], r["stage2"], (r["kf_pose"], r["kf_vel"], r["pt_xyz"]), r["Tbc"], G, cost_rtol=1e-9, pos_tol=1e-8, ang_tol=1e-9)
+    moved = np.abs(r["Tbc"] - P.cam_Tbc).max(axis=1) > 1e-12
+    assert np.array_equal(moved, G["freed"].astype(bool))
+
+
 def test_adapter_without_a_device_fails_cleanly():
     import torch
     import ref_py as R
