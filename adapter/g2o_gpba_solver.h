@@ -292,7 +292,8 @@ struct FlatGraph {
 class GpBaLevenberg : public g2o::OptimizationAlgorithm {
  public:
   // linear_solver: GPBA_SOLVER_DENSE_CHOL where the reference uses LinearSolverDense (LocalGPBA) or wants the direct
-  // factorization, GPBA_SOLVER_PCG for very large sparse global systems.
+  // factorization, GPBA_SOLVER_SPARSE_CHOL where it uses LinearSolverEigen (BundleAdjustment; the device runs the same tile
+  // Cholesky for both).  GPBA_SOLVER_PCG exists but is not recommended.
   explicit GpBaLevenberg(int linear_solver = GPBA_SOLVER_DENSE_CHOL, int device = -1)
       : _h(nullptr), _linear(linear_solver), _device(device), _lambda_init(-1.0), _iters(10), _done(false) { std::memset(&_trace, 0, sizeof(_trace)); }
   virtual ~GpBaLevenberg() { gpba_destroy(_h); }
