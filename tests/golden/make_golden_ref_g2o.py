@@ -66,7 +66,7 @@ def make_case(key):
 
 
 CASES = list(mg.CASES) + ["c1_full", "loop_full", "stereo", "far_start", "levels"]
-SLOW_CASES = ["loop_200"]      # minutes through oracle/_ref; minted on request, tested when the file is there
+SLOW_CASES = ["loop_200", "loop_500"]      # minutes through oracle/_ref; minted on request, tested when the file is there
 
 
 def samples(P):

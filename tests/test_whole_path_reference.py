@@ -101,8 +101,9 @@ def check_flags(flags, P, G):
 
 @pytest.mark.parametrize("key", mr.SLOW_CASES)
 def test_oracle_matches_reference_run_large(oracle_mod, key):
-    """The C4 family at 200 keyframes (loop driven twice, 20 000 points, ~200k observations, 2 388 pose unknowns): the
-    oracle's block-sparse Cholesky with its fill-reducing order against g2o's block solver over a dense LDLT."""
+    """The C4 family at 200 keyframes (loop driven twice, 20 000 points, ~200k observations, 2 388 pose unknowns) and at 500
+    keyframes (50 000 points, ~500k observations, 5 988 pose unknowns): the oracle's block-sparse Cholesky with its
+    fill-reducing order against g2o's block solver over a dense LDLT."""
     if not os.path.exists(os.path.join(HERE, "golden", "ref_g2o_" + key + ".npz")):
         pytest.skip("not minted (minutes through oracle/_ref)")
     G = load(key)
